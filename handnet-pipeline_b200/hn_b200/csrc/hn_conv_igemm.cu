@@ -1,0 +1,543 @@
+// Convolution as a shifted GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Replaces every 3x3 / 1x1 nn.Conv2d (+ FrozenBN / BN / bias / residual / ReLU) the reference reaches through
+// cuDNN: torchvision resnet34 + FPN (fcos_utils/fcos.py:476), the FCOS towers and output convs
+// (fcos_utils/fcos.py:232-264, 352-371), a2j/resnet.py and the A2J towers (a2j/a2j.py:44-181).
+//
+// Data layout: activations are haloed NHWC bf16, so for tap (r,s) the A operand of the implicit GEMM is the
+// activation matrix [rows = N*Hp*Wp][Cin] shifted by (r*Wp + s) rows: one 2-D TMA box per (tap, 64-channel
+// chunk), out-of-range rows zero-filled by TMA.  Weights are [Cout_pad][taps*Cin] bf16 (K-major).
+//
+// One persistent CTA per SM, 192 threads:
+//   warp 0      TMA producer   (A box 128 rows x 64 ch, B box BN rows x 64 k, SWIZZLE_128B, STAGES-deep ring)
+//   warp 1      MMA issuer     (tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16; fp32 accumulators in TMEM,
+//                               double-buffered so the epilogue of tile i overlaps the main loop of tile i+1)
+//   warps 2..5  epilogue       (tcgen05.ld -> scale/shift -> +residual -> ReLU -> bf16/fp32 store, GroupNorm partial
+//                               sums, optional phase-split copy for a following stride-2 conv)
+#include "hn_common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_TAPS = 9;
+
+struct ConvParams {
+  // compute geometry (== input geometry)
+  int n_img, hp, wp, halo;     // padded height/width of one image and the halo size
+  int rows;                    // n_img * hp * wp
+  int num_taps, cin_chunks;
+  int tap_shift[MAX_TAPS];     // row shift of each tap
+  int tap_phase[MAX_TAPS];     // phase image of each tap (0 for ordinary inputs)
+  int m_tiles, n_tiles;
+  int cout;
+  const float* scale;
+  const float* shift;
+  int relu_lo, relu_hi;
+  // residual
+  const __nv_bfloat16* res;
+  int res_mode, res_hp, res_wp, res_halo;
+  // output
+  void* out;
+  int out_kind, out_hp, out_wp, out_halo;
+  int out_rows_per_image, out_row_offset, out_ld, out_transpose_hw;
+  __nv_bfloat16* out_phase;
+  int ph_hp, ph_wp, ph_halo;
+  long long ph_stride;         // elements between phase images
+  double* gn_stats;
+  int gn_groups, gn_group_size;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                  const ConvParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::STAGES;
+  uint64_t* tmem_full = bars + 2 * C::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int k_blocks = p.num_taps * p.cin_chunks;
+
+  if (threadIdx.x == 0) {
+    hn_tma_prefetch_desc(&tm_a);
+    hn_tma_prefetch_desc(&tm_b);
+    for (int s = 0; s < C::STAGES; ++s) {
+      hn_mbar_init(&full_bar[s], 1);
+      hn_mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      hn_mbar_init(&tmem_full[b], 1);
+      hn_mbar_init(&tmem_empty[b], 4);   // one arrive per epilogue warp
+    }
+    hn_mbar_init_fence();
+  }
+  if (warp == 1) hn_tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  hn_tc_fence_before();
+  __syncthreads();
+  hn_tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.n_tiles) * BLOCK_M;
+        const int n0 = (tile % p.n_tiles) * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          const int tap = kb / p.cin_chunks;
+          const int cc = kb - tap * p.cin_chunks;
+          hn_mbar_wait(&empty_bar[stage], phase ^ 1);
+          hn_mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          hn_tma_load_3d(sa, &tm_a, &full_bar[stage], cc * BLOCK_K, m0 + p.tap_shift[tap], p.tap_phase[tap]);
+          hn_tma_load_2d(sa + A_STAGE_BYTES, &tm_b, &full_bar[stage], kb * BLOCK_K, n0);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = hn_umma_idesc_bf16(BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        hn_mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
+        hn_tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          hn_mbar_wait(&full_bar[stage], phase);
+          hn_tc_fence_after();
+          const uint32_t a_addr = hn_smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint64_t da = hn_umma_smem_desc(a_addr);
+          const uint64_t db = hn_umma_smem_desc(a_addr + A_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // +32 bytes per K=16 step inside the 128-byte swizzle span: start-address field += 2
+            hn_umma_bf16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0);
+          }
+          hn_umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        hn_umma_commit(&tmem_full[buf]);       // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================================== epilogue ==========================================
+    const int quarter = warp & 3;              // TMEM lanes this warp may touch: 32*quarter .. +31
+    const int img_rows = p.hp * p.wp;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile / p.n_tiles) * BLOCK_M;
+      const int n0 = (tile % p.n_tiles) * BN;
+      const int m = m0 + quarter * 32 + lane;
+      // decode the padded pixel this accumulator row belongs to
+      int img = 0, h = 0, w = 0;
+      bool interior = false;
+      if (m < p.rows) {
+        img = m / img_rows;
+        const int rem = m - img * img_rows;
+        const int hh = rem / p.wp;
+        const int ww = rem - hh * p.wp;
+        h = hh - p.halo;
+        w = ww - p.halo;
+        interior = (h >= 0) && (w >= 0) && (h < p.hp - 2 * p.halo) && (w < p.wp - 2 * p.halo);
+      }
+      const int H = p.hp - 2 * p.halo, W = p.wp - 2 * p.halo;
+      // output / residual element offsets of channel 0 of this row
+      long long out_off = 0, res_off = 0, ph_off = 0;
+      if (interior) {
+        if (p.out_kind == 0) {
+          out_off = ((long long)(img * p.out_hp + h + p.out_halo) * p.out_wp + (w + p.out_halo)) * p.cout;
+        } else {
+          const int pix = p.out_transpose_hw ? (w * H + h) : (h * W + w);
+          out_off = ((long long)img * p.out_rows_per_image + p.out_row_offset + pix) * p.out_ld;
+        }
+        if (p.res_mode == 1) {
+          res_off = ((long long)(img * p.res_hp + h + p.res_halo) * p.res_wp + (w + p.res_halo)) * p.cout;
+        } else if (p.res_mode == 2) {
+          res_off = ((long long)(img * p.res_hp + (h >> 1) + p.res_halo) * p.res_wp + ((w >> 1) + p.res_halo)) * p.cout;
+        }
+        if (p.out_phase) {
+          const int ph = (h & 1) * 2 + (w & 1);
+          ph_off = ph * p.ph_stride +
+                   ((long long)(img * p.ph_hp + (h >> 1) + p.ph_halo) * p.ph_wp + ((w >> 1) + p.ph_halo)) * p.cout;
+        }
+      }
+      // GroupNorm partial sums are reduced per warp when all its interior rows sit in one image
+      const unsigned interior_mask = __ballot_sync(0xffffffffu, interior);
+      const int warp_img = __shfl_sync(0xffffffffu, img, interior_mask ? (__ffs(interior_mask) - 1) : 0);
+      const bool warp_uniform_img = __all_sync(0xffffffffu, (!interior) || (img == warp_img));
+
+      hn_mbar_wait(&tmem_full[buf], acc_phase);
+      hn_tc_fence_after();
+      const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + buf * BN;
+
+      constexpr int CHUNK = (BN >= 32) ? 32 : 16;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += CHUNK) {
+        uint32_t acc[CHUNK];
+        if constexpr (CHUNK == 32) {
+          hn_tmem_ld32(t_row + c0, acc);
+        } else {
+          hn_tmem_ld16(t_row + c0, acc);
+        }
+        hn_tmem_ld_wait();
+        const int cbase = n0 + c0;
+        if (cbase >= p.cout) continue;                 // padded output channels (warp-uniform)
+        float v[CHUNK];
+        if (cbase + CHUNK <= p.cout) {
+#pragma unroll
+          for (int j = 0; j < CHUNK; j += 4) {
+            const float4 sc = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + cbase + j))
+                                      : make_float4(1.f, 1.f, 1.f, 1.f);
+            const float4 sh = p.shift ? __ldg(reinterpret_cast<const float4*>(p.shift + cbase + j))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[j + 0] = __uint_as_float(acc[j + 0]) * sc.x + sh.x;
+            v[j + 1] = __uint_as_float(acc[j + 1]) * sc.y + sh.y;
+            v[j + 2] = __uint_as_float(acc[j + 2]) * sc.z + sh.z;
+            v[j + 3] = __uint_as_float(acc[j + 3]) * sc.w + sh.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < CHUNK; ++j) {
+            const int c = cbase + j;
+            const bool ok = c < p.cout;
+            const float sc = (p.scale && ok) ? __ldg(p.scale + c) : 1.0f;
+            const float sh = (p.shift && ok) ? __ldg(p.shift + c) : 0.0f;
+            v[j] = __uint_as_float(acc[j]) * sc + sh;
+          }
+        }
+        if (p.res_mode != 0 && interior) {
+          const __nv_bfloat16* rp = p.res + res_off + cbase;
+          if (cbase + CHUNK <= p.cout && (p.cout & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < CHUNK; j += 8) {
+              const uint4 r = __ldg(reinterpret_cast<const uint4*>(rp + j));
+              v[j + 0] += hn_bf16_lo(r.x); v[j + 1] += hn_bf16_hi(r.x);
+              v[j + 2] += hn_bf16_lo(r.y); v[j + 3] += hn_bf16_hi(r.y);
+              v[j + 4] += hn_bf16_lo(r.z); v[j + 5] += hn_bf16_hi(r.z);
+              v[j + 6] += hn_bf16_lo(r.w); v[j + 7] += hn_bf16_hi(r.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j)
+              if (cbase + j < p.cout) v[j] += __bfloat162float(rp[j]);
+          }
+        }
+        if (p.relu_hi > p.relu_lo) {
+          if (cbase >= p.relu_lo && cbase + CHUNK <= p.relu_hi) {
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) v[j] = fmaxf(v[j], 0.0f);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j)
+              if (cbase + j >= p.relu_lo && cbase + j < p.relu_hi) v[j] = fmaxf(v[j], 0.0f);
+          }
+        }
+        if (p.out_kind == 1) {
+          if (interior) {
+            float* op = reinterpret_cast<float*>(p.out) + out_off + cbase;
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j)
+              if (cbase + j < p.cout) op[j] = v[j];
+          }
+          continue;
+        }
+        // bf16 outputs
+        uint32_t packed[CHUNK / 2];
+#pragma unroll
+        for (int j = 0; j < CHUNK; j += 2) packed[j / 2] = hn_pack_bf16(v[j], v[j + 1]);
+        if (interior) {
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + cbase;
+          if (cbase + CHUNK <= p.cout && (p.cout & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < CHUNK / 2; j += 4)
+              *reinterpret_cast<uint4*>(op + 2 * j) = make_uint4(packed[j], packed[j + 1], packed[j + 2], packed[j + 3]);
+            if (p.out_phase) {
+              __nv_bfloat16* pp = p.out_phase + ph_off + cbase;
+#pragma unroll
+              for (int j = 0; j < CHUNK / 2; j += 4)
+                *reinterpret_cast<uint4*>(pp + 2 * j) = make_uint4(packed[j], packed[j + 1], packed[j + 2], packed[j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j)
+              if (cbase + j < p.cout) {
+                const __nv_bfloat16 b = __float2bfloat16_rn(v[j]);
+                op[j] = b;
+                if (p.out_phase) p.out_phase[ph_off + cbase + j] = b;
+              }
+          }
+        }
+        if (p.gn_stats) {
+          // partial sums over the bf16-rounded values, per (image, group); groups are multiples of 8 channels
+          if constexpr (CHUNK == 32) {
+            const int per = p.gn_group_size >> 3;       // 8-channel octets per group: 1, 2 or 4
+            float s = 0.f, q = 0.f;
+#pragma unroll
+            for (int o8 = 0; o8 < CHUNK / 8; ++o8) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t pk = packed[o8 * 4 + j];
+                const float x0 = hn_bf16_lo(pk), x1 = hn_bf16_hi(pk);
+                s += x0 + x1;
+                q += x0 * x0 + x1 * x1;
+              }
+              if (((o8 + 1) % per) == 0) {
+                const int group = (cbase + o8 * 8) / p.gn_group_size;
+                float ws = interior ? s : 0.f, wq = interior ? q : 0.f;
+                if (warp_uniform_img) {
+#pragma unroll
+                  for (int o = 16; o > 0; o >>= 1) {
+                    ws += __shfl_xor_sync(0xffffffffu, ws, o);
+                    wq += __shfl_xor_sync(0xffffffffu, wq, o);
+                  }
+                  if (lane == 0 && interior_mask != 0u) {
+                    double* dst = p.gn_stats + ((long long)warp_img * p.gn_groups + group) * 2;
+                    atomicAdd(dst, (double)ws);
+                    atomicAdd(dst + 1, (double)wq);
+                  }
+                } else if (interior) {
+                  double* dst = p.gn_stats + ((long long)img * p.gn_groups + group) * 2;
+                  atomicAdd(dst, (double)ws);
+                  atomicAdd(dst + 1, (double)wq);
+                }
+                s = 0.f;
+                q = 0.f;
+              }
+            }
+          }
+        }
+      }
+      // accumulator buffer drained -> hand it back to the MMA warp
+      hn_tc_fence_before();
+      __syncwarp();
+      if (lane == 0) hn_mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+
+  hn_tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    hn_tc_fence_after();
+    hn_tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+             const cuuint32_t* box) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    hn_set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    return HN_ERR_CUDA;
+  }
+  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides_bytes, box, ones,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    hn_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu %llu)", (int)r, rank,
+                 (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0));
+    return HN_ERR_CUDA;
+  }
+  return HN_OK;
+}
+
+template <int BN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t st) {
+  using C = Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    HN_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < hn_num_sms() ? tiles : hn_num_sms();
+  conv_igemm_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
+  hn_count_launch();
+  HN_LAUNCH_CHECK();
+  return HN_OK;
+}
+
+int pick_block_n(int cout_pad, int m_tiles) {
+  // Largest tile that still gives every SM a tile; tiny-N output convs use their padded width.
+  const int sms = hn_num_sms();
+  const int cands[5] = {256, 128, 64, 32, 16};
+  int best = 16;
+  for (int i = 0; i < 5; ++i) {
+    const int bn = cands[i];
+    if (cout_pad % bn) continue;
+    best = bn;
+    if ((long long)m_tiles * (cout_pad / bn) >= sms) break;
+    if (bn == 64) break;                   // below 64 only when the layer is that narrow
+  }
+  while (cout_pad % best) best >>= 1;
+  return best;
+}
+
+}  // namespace
+
+extern "C" int hn_conv2d_bf16(const hn_conv_desc* d, void* stream) {
+  HN_REQUIRE(d && d->in && d->weight && d->out, "hn_conv2d_bf16: null pointer");
+  HN_REQUIRE(d->cin > 0 && d->cin % BLOCK_K == 0, "hn_conv2d_bf16: cin=%d must be a multiple of 64", d->cin);
+  HN_REQUIRE(d->kh == d->kw && (d->kh == 1 || d->kh == 3), "hn_conv2d_bf16: only 1x1 and 3x3 kernels (got %dx%d)",
+             d->kh, d->kw);
+  HN_REQUIRE(d->stride == 1 || d->stride == 2, "hn_conv2d_bf16: stride %d", d->stride);
+  HN_REQUIRE((d->stride == 2) == (d->in_phases == 4) && (d->in_phases == 1 || d->in_phases == 4),
+             "hn_conv2d_bf16: stride 2 needs a phase-split input (in_phases=4), stride 1 a plain one");
+  HN_REQUIRE(d->dilation >= 1 && (d->stride == 1 || d->dilation == 1), "hn_conv2d_bf16: dilation %d", d->dilation);
+  const int pad = (d->kh / 2) * d->dilation;
+  HN_REQUIRE(d->stride == 2 || d->halo_in >= pad, "hn_conv2d_bf16: halo_in=%d < conv padding %d", d->halo_in, pad);
+  HN_REQUIRE(d->stride == 1 || d->halo_in >= 1 || d->kh == 1, "hn_conv2d_bf16: stride-2 3x3 needs halo_in >= 1");
+  HN_REQUIRE(d->cout > 0 && d->cout_pad >= d->cout && d->cout_pad % 16 == 0, "hn_conv2d_bf16: cout/cout_pad");
+  HN_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0, "hn_conv2d_bf16: empty input");
+
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_img = d->n;
+  p.halo = d->halo_in;
+  p.hp = d->h + 2 * d->halo_in;
+  p.wp = d->w + 2 * d->halo_in;
+  const long long rows_ll = (long long)d->n * p.hp * p.wp;
+  HN_REQUIRE(rows_ll < (1ll << 31) - 4096, "hn_conv2d_bf16: too many rows");
+  p.rows = (int)rows_ll;
+  p.cin_chunks = d->cin / BLOCK_K;
+  p.num_taps = d->kh * d->kw;
+  for (int r = 0; r < d->kh; ++r)
+    for (int s = 0; s < d->kw; ++s) {
+      const int t = r * d->kw + s;
+      const int dr = (r - d->kh / 2) * d->dilation, ds = (s - d->kw / 2) * d->dilation;
+      if (d->stride == 1) {
+        p.tap_shift[t] = dr * p.wp + ds;
+        p.tap_phase[t] = 0;
+      } else {
+        // input pixel (2*oh + dr, 2*ow + ds) lives in phase (dr&1, ds&1) at (oh + floor(dr/2), ow + floor(ds/2))
+        const int pr = dr & 1, ps = ds & 1;
+        const int fr = (dr - pr) / 2, fs = (ds - ps) / 2;
+        p.tap_shift[t] = fr * p.wp + fs;
+        p.tap_phase[t] = pr * 2 + ps;
+      }
+    }
+  p.m_tiles = hn_div_up(p.rows, BLOCK_M);
+  int bn = d->block_n ? d->block_n : pick_block_n(d->cout_pad, p.m_tiles);
+  HN_REQUIRE((bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256) && d->cout_pad % bn == 0,
+             "hn_conv2d_bf16: block_n=%d does not divide cout_pad=%d", bn, d->cout_pad);
+  p.n_tiles = d->cout_pad / bn;
+  p.cout = d->cout;
+  p.scale = d->scale;
+  p.shift = d->shift;
+  p.relu_lo = d->relu_lo;
+  p.relu_hi = d->relu_hi;
+  p.res = reinterpret_cast<const __nv_bfloat16*>(d->res);
+  p.res_mode = d->res ? d->res_mode : 0;
+  if (p.res_mode) {
+    HN_REQUIRE(p.res_mode == 1 || p.res_mode == 2, "hn_conv2d_bf16: res_mode %d", p.res_mode);
+    p.res_halo = d->res_halo;
+    p.res_hp = d->res_h + 2 * d->res_halo;
+    p.res_wp = d->res_w + 2 * d->res_halo;
+    if (p.res_mode == 1)
+      HN_REQUIRE(d->res_h == d->h && d->res_w == d->w, "hn_conv2d_bf16: residual size mismatch");
+    else
+      HN_REQUIRE(d->res_h == (d->h + 1) / 2 && d->res_w == (d->w + 1) / 2, "hn_conv2d_bf16: upsample residual size");
+  }
+  p.out = d->out;
+  p.out_kind = d->out_kind;
+  p.out_halo = d->out_halo;
+  p.out_hp = d->h + 2 * d->out_halo;
+  p.out_wp = d->w + 2 * d->out_halo;
+  p.out_rows_per_image = d->out_rows_per_image;
+  p.out_row_offset = d->out_row_offset;
+  p.out_ld = d->out_ld;
+  p.out_transpose_hw = d->out_transpose_hw;
+  if (d->out_kind == 1) HN_REQUIRE(d->out_ld >= d->cout, "hn_conv2d_bf16: out_ld < cout");
+  p.out_phase = reinterpret_cast<__nv_bfloat16*>(d->out_phase);
+  if (p.out_phase) {
+    HN_REQUIRE(d->out_kind == 0, "hn_conv2d_bf16: phase-split copy only for bf16 outputs");
+    p.ph_halo = d->out_phase_halo;
+    p.ph_hp = (d->h + 1) / 2 + 2 * d->out_phase_halo;
+    p.ph_wp = (d->w + 1) / 2 + 2 * d->out_phase_halo;
+    p.ph_stride = (long long)d->n * p.ph_hp * p.ph_wp * d->cout;
+  }
+  p.gn_stats = d->gn_stats;
+  if (p.gn_stats) {
+    HN_REQUIRE(d->gn_groups > 0 && d->cout % d->gn_groups == 0, "hn_conv2d_bf16: gn_groups");
+    p.gn_groups = d->gn_groups;
+    p.gn_group_size = d->cout / d->gn_groups;
+    HN_REQUIRE(bn >= 32 && (p.gn_group_size == 8 || p.gn_group_size == 16 || p.gn_group_size == 32),
+               "hn_conv2d_bf16: GroupNorm group size %d unsupported (8, 16 or 32 channels per group)",
+               p.gn_group_size);
+  }
+
+  CUtensorMap ta, tb;
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)d->cin, (cuuint64_t)p.rows, (cuuint64_t)d->in_phases};
+    const cuuint64_t strides[2] = {(cuuint64_t)d->cin * 2, (cuuint64_t)p.rows * d->cin * 2};
+    const cuuint32_t box[3] = {BLOCK_K, BLOCK_M, 1};
+    int rc = make_map(&ta, d->in, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const cuuint64_t k_total = (cuuint64_t)p.num_taps * d->cin;
+    const cuuint64_t dims[2] = {k_total, (cuuint64_t)d->cout_pad};
+    const cuuint64_t strides[1] = {k_total * 2};
+    const cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)bn};
+    int rc = make_map(&tb, d->weight, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 256: return launch<256>(ta, tb, p, st);
+    case 128: return launch<128>(ta, tb, p, st);
+    case 64: return launch<64>(ta, tb, p, st);
+    case 32: return launch<32>(ta, tb, p, st);
+    default: return launch<16>(ta, tb, p, st);
+  }
+}

@@ -1,0 +1,585 @@
+// FCOS post-processing (fcos_utils/fcos.py:572-669) as batch-wide kernels:
+//   decode + score + threshold with ordered compaction        (P1-P4, anchors generated on the fly: A1)
+//   stable radix sort by score + 64x64 IoU bitmask + serial scan (P5, torchvision CPU NMS semantics, bit-exact)
+//   gather of the kept detections + resize_boxes                (P6)
+// Integer/fp32 work on tiny data: coalesced vector loads, warp ballots/matches, no tensor cores.
+#include "hn_common.cuh"
+
+namespace {
+
+// x > (double)t for a float x  <=>  x >= smallest float whose value exceeds t.  This is how a python-float
+// threshold meets float32 data in the reference (torchvision's CPU NMS compares against a double; `scores > 0.7`
+// promotes to float32, which gives the same set for 0.7).
+float float_gt_as_ge(double t) {
+  float f = (float)t;
+  if ((double)f <= t) f = nextafterf(f, INFINITY);
+  while ((double)nextafterf(f, -INFINITY) > t) f = nextafterf(f, -INFINITY);
+  return f;
+}
+
+constexpr int MAX_LEVELS = 8;
+struct Levels {
+  int n;
+  int start[MAX_LEVELS + 1];
+  int h[MAX_LEVELS], w[MAX_LEVELS], sh[MAX_LEVELS], sw[MAX_LEVELS], anchor[MAX_LEVELS];
+};
+
+constexpr int SEL_BLOCK = 256;
+
+__device__ __forceinline__ float sigmoid_rn(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+// score = max_c sqrt(sigmoid(cls_c) * sigmoid(ctr)), label = first arg max (fcos_utils/fcos.py:598-599)
+__device__ __forceinline__ void score_label(const float* __restrict__ cls, float ctr, int nc, float& best, int& label) {
+  const float sc = sigmoid_rn(ctr);
+  best = -1.f;
+  label = 0;
+  for (int c = 0; c < nc; ++c) {
+    const float s = __fsqrt_rn(__fmul_rn(sigmoid_rn(__ldg(cls + c)), sc));
+    if (c == 0 || s > best) { best = s; label = c; }
+  }
+}
+
+// pass 1: dense score / label and the number of survivors per 256-location chunk
+__global__ void __launch_bounds__(SEL_BLOCK)
+select_score_kernel(const float* __restrict__ cls, int cls_ld, const float* __restrict__ ctr, int ctr_ld, int locs,
+                    int nc, float thresh_ge,
+                    float* __restrict__ dense_score, int* __restrict__ dense_label, int* __restrict__ chunk_count) {
+  const int b = blockIdx.y;
+  const int loc = blockIdx.x * SEL_BLOCK + threadIdx.x;
+  bool pass = false;
+  if (loc < locs) {
+    float s;
+    int l;
+    score_label(cls + ((size_t)b * locs + loc) * cls_ld, __ldg(ctr + ((size_t)b * locs + loc) * ctr_ld), nc, s, l);
+    dense_score[(size_t)b * locs + loc] = s;
+    dense_label[(size_t)b * locs + loc] = l;
+    pass = s >= thresh_ge;
+  }
+  const int cnt = __syncthreads_count(pass);
+  if (threadIdx.x == 0) chunk_count[b * gridDim.x + blockIdx.x] = cnt;
+}
+
+// pass 2: ordered compaction; boxes are decoded for survivors only (det_utils.py:266-294)
+__global__ void __launch_bounds__(SEL_BLOCK)
+select_compact_kernel(const float* __restrict__ reg, int reg_ld, const float* __restrict__ dense_score,
+                      const int* __restrict__ dense_label, const int* __restrict__ chunk_count, int locs, float thresh_ge,
+                      const Levels lv, int* __restrict__ cand_count, int* __restrict__ cand_loc,
+                      float* __restrict__ cand_score, int* __restrict__ cand_label, float4* __restrict__ cand_box) {
+  __shared__ int warp_sums[SEL_BLOCK / 32];
+  __shared__ int base_s;
+  const int b = blockIdx.y;
+  const int chunks = gridDim.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // offset of this chunk = sum of the counts of the chunks before it
+  if (warp == 0) {
+    int acc = 0;
+    for (int i = lane; i < blockIdx.x; i += 32) acc += chunk_count[b * chunks + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) base_s = acc;
+  }
+  const int loc = blockIdx.x * SEL_BLOCK + threadIdx.x;
+  float s = 0.f;
+  bool pass = false;
+  if (loc < locs) {
+    s = dense_score[(size_t)b * locs + loc];
+    pass = s >= thresh_ge;
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, pass);
+  if (lane == 0) warp_sums[warp] = __popc(bal);
+  __syncthreads();
+  int before = 0;
+  for (int i = 0; i < warp; ++i) before += warp_sums[i];
+  const int rank = base_s + before + __popc(bal & ((1u << lane) - 1u));
+  if (pass) {
+    int l = 0;
+    while (l + 1 < lv.n && loc >= lv.start[l + 1]) ++l;
+    const int cell = loc - lv.start[l];
+    const int y = cell / lv.w[l], x = cell - y * lv.w[l];
+    // anchor = (x*sw, y*sh, x*sw, y*sh) + round([-s,-s,s,s]/2)   (anchor_utils.py:56-112)
+    const float half = rintf((float)lv.anchor[l] * 0.5f);
+    const float a0 = (float)(x * lv.sw[l]) - half, a1 = (float)(y * lv.sh[l]) - half;
+    const float a2 = (float)(x * lv.sw[l]) + half, a3 = (float)(y * lv.sh[l]) + half;
+    const float cx = __fmul_rn(0.5f, __fadd_rn(a0, a2)), cy = __fmul_rn(0.5f, __fadd_rn(a1, a3));
+    const float bw = __fsub_rn(a2, a0), bh = __fsub_rn(a3, a1);
+    const float4 r = __ldg(reinterpret_cast<const float4*>(reg + ((size_t)b * locs + loc) * reg_ld));
+    float4 box;
+    box.x = __fsub_rn(cx, __fmul_rn(r.x, bw));
+    box.y = __fsub_rn(cy, __fmul_rn(r.y, bh));
+    box.z = __fadd_rn(cx, __fmul_rn(r.z, bw));
+    box.w = __fadd_rn(cy, __fmul_rn(r.w, bh));
+    const size_t o = (size_t)b * locs + rank;
+    cand_loc[o] = loc;
+    cand_score[o] = s;
+    cand_label[o] = dense_label[(size_t)b * locs + loc];
+    cand_box[o] = box;
+  }
+  if (blockIdx.x == chunks - 1 && threadIdx.x == SEL_BLOCK - 1) {
+    // last thread of the last chunk knows the total
+    cand_count[b] = base_s + before + __popc(bal);
+  }
+}
+
+// ------------------------------------------------------------------------------------- NMS
+constexpr int SORT_THREADS = 1024;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+
+struct NmsWs {
+  uint32_t* keys[2];      // [batch][cap]
+  uint32_t* idx[2];       // [batch][cap]
+  float4* sbox;           // [batch][cap] boxes in sorted order (coordinate trick applied when active)
+  int* slabel;            // [batch][cap] labels in sorted order (0 when the coordinate trick is active)
+  unsigned long long* mask;  // [batch][cap][words]
+  int words;
+};
+
+__host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+__host__ NmsWs carve(void* base, int batch, int cap) {
+  NmsWs w;
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  const size_t n = (size_t)batch * cap;
+  w.words = (cap + 63) / 64;
+  for (int i = 0; i < 2; ++i) { w.keys[i] = reinterpret_cast<uint32_t*>(p); p += align256(n * 4); }
+  for (int i = 0; i < 2; ++i) { w.idx[i] = reinterpret_cast<uint32_t*>(p); p += align256(n * 4); }
+  w.sbox = reinterpret_cast<float4*>(p); p += align256(n * 16);
+  w.slabel = reinterpret_cast<int*>(p); p += align256(n * 4);
+  w.mask = reinterpret_cast<unsigned long long*>(p);
+  return w;
+}
+
+__device__ __forceinline__ uint32_t desc_key(float s) {
+  uint32_t u = __float_as_uint(s);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // ascending-orderable
+  return ~u;                                         // descending
+}
+
+// One CTA per image: stable LSD radix sort of (score desc) with candidate index payload, then gather the boxes
+// in sorted order, applying torchvision's coordinate trick when 4*n <= trick_max (ops/boxes.py:80-104).
+__global__ void __launch_bounds__(SORT_THREADS)
+nms_sort_kernel(const float4* __restrict__ cand_box, const float* __restrict__ cand_score,
+                const int* __restrict__ cand_label, const int* __restrict__ cand_count, int cap, int trick_max,
+                NmsWs ws) {
+  __shared__ int hist[256 * SORT_WARPS];
+  __shared__ int warp_tot[SORT_WARPS];
+  __shared__ float red[SORT_WARPS];
+  __shared__ int skip_pass;
+  const int b = blockIdx.x;
+  int n = cand_count[b];
+  if (n > cap) n = cap;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t off = (size_t)b * cap;
+  uint32_t* keys[2] = {ws.keys[0] + off, ws.keys[1] + off};
+  uint32_t* idx[2] = {ws.idx[0] + off, ws.idx[1] + off};
+  for (int i = tid; i < n; i += SORT_THREADS) {
+    keys[0][i] = desc_key(cand_score[off + i]);
+    idx[0][i] = i;
+  }
+  __syncthreads();
+  // contiguous, 32-aligned segment per warp keeps the scatter stable
+  const int per_warp = ((n + SORT_WARPS - 1) / SORT_WARPS + 31) & ~31;
+  const int seg0 = min(warp * per_warp, n), seg1 = min(seg0 + per_warp, n);
+  int cur = 0;
+  for (int shift = 0; shift < 32; shift += 8) {
+    for (int i = tid; i < 256 * SORT_WARPS; i += SORT_THREADS) hist[i] = 0;
+    if (tid == 0) skip_pass = 0;
+    __syncthreads();
+    for (int base = seg0; base < seg1; base += 32) {
+      const int i = base + lane;
+      const bool act = i < seg1;
+      const unsigned amask = __ballot_sync(0xffffffffu, act);
+      if (act) {
+        const int d = (keys[cur][i] >> shift) & 255;
+        const unsigned peers = __match_any_sync(amask, d);
+        if (lane == __ffs(peers) - 1) hist[d * SORT_WARPS + warp] += __popc(peers);
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    // exclusive scan over (digit major, warp minor); 8 consecutive entries per thread
+    int v[8], tsum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[j] = hist[tid * 8 + j]; tsum += v[j]; }
+    // a digit owning every element means this pass is the identity
+    {
+      const int dsum_part = tsum;   // entries tid*8..+7 belong to digit (tid*8)/32 = tid/4
+      int dsum = dsum_part;
+      dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+      dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+      if (dsum == n && n > 0) skip_pass = 1;
+    }
+    int inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (skip_pass) { __syncthreads(); continue; }
+    int wbase = 0;
+    for (int i = 0; i < warp; ++i) wbase += warp_tot[i];
+    int run = wbase + inc - tsum;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { hist[tid * 8 + j] = run; run += v[j]; }
+    __syncthreads();
+    for (int base = seg0; base < seg1; base += 32) {
+      const int i = base + lane;
+      const bool act = i < seg1;
+      const unsigned amask = __ballot_sync(0xffffffffu, act);
+      if (act) {
+        const uint32_t k = keys[cur][i];
+        const int d = (k >> shift) & 255;
+        const unsigned peers = __match_any_sync(amask, d);
+        const int pos = hist[d * SORT_WARPS + warp] + __popc(peers & ((1u << lane) - 1u));
+        keys[cur ^ 1][pos] = k;
+        idx[cur ^ 1][pos] = idx[cur][i];
+        __syncwarp(amask);
+        if (lane == __ffs(peers) - 1) hist[d * SORT_WARPS + warp] += __popc(peers);
+      }
+      __syncwarp();
+    }
+    cur ^= 1;
+    __syncthreads();
+  }
+  // sorted candidate indices live in idx[cur]; publish them in idx[0] for the scan kernel
+  if (cur != 0) {
+    for (int i = tid; i < n; i += SORT_THREADS) idx[0][i] = idx[1][i];
+  }
+  // coordinate trick (needs the max coordinate over all candidates of this image)
+  const bool trick = (4 * n <= trick_max);
+  float off_scale = 0.f;
+  if (trick && n > 0) {
+    float m = -INFINITY;
+    for (int i = tid; i < n; i += SORT_THREADS) {
+      const float4 bx = cand_box[off + i];
+      m = fmaxf(m, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+    for (int i = 1; i < SORT_WARPS; ++i) m = fmaxf(m, red[i]);
+    off_scale = __fadd_rn(m, 1.0f);
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += SORT_THREADS) {
+    const int ci = idx[cur][i];
+    float4 bx = cand_box[off + ci];
+    int lab = cand_label[off + ci];
+    if (trick) {
+      const float o = __fmul_rn((float)lab, off_scale);
+      bx.x = __fadd_rn(bx.x, o); bx.y = __fadd_rn(bx.y, o); bx.z = __fadd_rn(bx.z, o); bx.w = __fadd_rn(bx.w, o);
+      lab = 0;
+    }
+    ws.sbox[off + i] = bx;
+    ws.slabel[off + i] = lab;
+  }
+}
+
+// 64x64 tiles of the upper triangle: bit j of mask[i][cb] says "sorted box i suppresses sorted box cb*64+j".
+// Arithmetic follows torchvision/csrc/ops/cpu/nms_kernel.cpp in fp32 with no contraction.
+__global__ void __launch_bounds__(64)
+nms_mask_kernel(const int* __restrict__ cand_count, int batch, int cap, float thr_ge, NmsWs ws) {
+  __shared__ float4 cb_box[64];
+  __shared__ int cb_lab[64];
+  // persistent over the list of (image, row block, col block >= row block)
+  long long tile = blockIdx.x;
+  int b = 0;
+  long long first = 0;
+  while (true) {
+    // advance to the image that owns `tile`
+    long long tiles_b = 0;
+    int n = 0;
+    for (; b < batch; ++b) {
+      n = min(cand_count[b], cap);
+      const long long nb = (n + 63) / 64;
+      tiles_b = nb * (nb + 1) / 2;
+      if (tile < first + tiles_b) break;
+      first += tiles_b;
+    }
+    if (b >= batch) return;
+    const int nb = (n + 63) / 64;
+    // decode the triangular index: row block rb, column block cb >= rb
+    long long t = tile - first;
+    int rb = 0;
+    {
+      // rows have nb, nb-1, ... tiles; solve by a short loop bounded by nb (<= 331) using a closed-form start
+      double x = ((2.0 * nb + 1.0) - sqrt((2.0 * nb + 1.0) * (2.0 * nb + 1.0) - 8.0 * (double)t)) * 0.5;
+      rb = (int)x;
+      if (rb < 0) rb = 0;
+      if (rb > nb - 1) rb = nb - 1;
+      while (rb > 0 && (long long)rb * nb - (long long)rb * (rb - 1) / 2 > t) --rb;
+      while ((long long)(rb + 1) * nb - (long long)(rb + 1) * rb / 2 <= t) ++rb;
+    }
+    const int cb = rb + (int)(t - ((long long)rb * nb - (long long)rb * (rb - 1) / 2));
+    const size_t off = (size_t)b * cap;
+    const int j0 = cb * 64;
+    __syncthreads();
+    if (j0 + (int)threadIdx.x < n) {
+      cb_box[threadIdx.x] = ws.sbox[off + j0 + threadIdx.x];
+      cb_lab[threadIdx.x] = ws.slabel[off + j0 + threadIdx.x];
+    }
+    __syncthreads();
+    const int i = rb * 64 + threadIdx.x;
+    if (i < n) {
+      const float4 bi = ws.sbox[off + i];
+      const int li = ws.slabel[off + i];
+      const float iarea = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+      unsigned long long bits = 0ull;
+      const int jn = min(64, n - j0);
+      for (int j = (cb == rb) ? (int)threadIdx.x + 1 : 0; j < jn; ++j) {
+        const float4 bj = cb_box[j];
+        if (cb_lab[j] != li) continue;
+        const float jarea = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+        const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
+        const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
+        const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+        const float inter = __fmul_rn(w, h);
+        const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(iarea, jarea), inter));
+        if (ovr >= thr_ge) bits |= (1ull << j);     // == ((double)ovr > (double)iou_threshold)
+      }
+      ws.mask[((size_t)b * cap + i) * ws.words + cb] = bits;
+    }
+    tile += gridDim.x;
+  }
+}
+
+// One CTA per image: greedy scan over the bitmask in 64-box chunks.
+constexpr int SCAN_THREADS = 256;
+__global__ void __launch_bounds__(SCAN_THREADS)
+nms_scan_kernel(const int* __restrict__ cand_count, int cap, NmsWs ws, int* __restrict__ keep,
+                int* __restrict__ keep_count) {
+  extern __shared__ unsigned long long removed[];   // [words]
+  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long kept_bits_s;
+  __shared__ int kept_total;
+  const int b = blockIdx.x;
+  const int n = min(cand_count[b], cap);
+  const int nb = (n + 63) / 64;
+  const size_t off = (size_t)b * cap;
+  const uint32_t* order = ws.idx[0] + off;
+  for (int i = threadIdx.x; i < nb; i += SCAN_THREADS) removed[i] = 0ull;
+  if (threadIdx.x == 0) kept_total = 0;
+  __syncthreads();
+  for (int c = 0; c < nb; ++c) {
+    const int cnt = min(64, n - c * 64);
+    if (threadIdx.x < cnt) diag[threadIdx.x] = ws.mask[(off + c * 64 + threadIdx.x) * ws.words + c];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long cur = removed[c], kept = 0ull;
+      int kt = kept_total;
+      for (int r = 0; r < cnt; ++r) {
+        if (!((cur >> r) & 1ull)) {
+          kept |= (1ull << r);
+          cur |= diag[r];
+          keep[off + kt++] = (int)order[c * 64 + r];
+        }
+      }
+      kept_total = kt;
+      kept_bits_s = kept;
+    }
+    __syncthreads();
+    const unsigned long long kept = kept_bits_s;
+    if (kept != 0ull) {
+      for (int wi = c + 1 + threadIdx.x; wi < nb; wi += SCAN_THREADS) {
+        unsigned long long acc = removed[wi];
+        unsigned long long kb = kept;
+        while (kb) {
+          const int r = __ffsll((long long)kb) - 1;
+          kb &= kb - 1;
+          acc |= ws.mask[(off + c * 64 + r) * ws.words + wi];
+        }
+        removed[wi] = acc;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) keep_count[b] = kept_total;
+}
+
+// ---------------------------------------------------------------------------------- gather
+struct GatherParams {
+  int num_levels;
+  int level_start[MAX_LEVELS + 1];
+};
+constexpr int GATHER_MAX_BATCH = 64;
+struct Ratios {
+  float rh[GATHER_MAX_BATCH], rw[GATHER_MAX_BATCH];
+};
+
+__global__ void __launch_bounds__(256)
+gather_kernel(const int* __restrict__ keep, const int* __restrict__ keep_count, const int* __restrict__ cand_loc,
+              const float* __restrict__ cand_score, const int* __restrict__ cand_label,
+              const float4* __restrict__ cand_box, const float* __restrict__ hand_lr, int lr_ld,
+              const float* __restrict__ contact_logits, int contact_ld, const float* __restrict__ dxdy, int dxdy_ld,
+              int cap, int locs,
+              int batch_offset, GatherParams gp, Ratios rt, float4* __restrict__ boxes, float* __restrict__ scores,
+              long long* __restrict__ labels, long long* __restrict__ sides, float* __restrict__ level,
+              long long* __restrict__ contacts, float* __restrict__ dxdymags) {
+  const int bl = blockIdx.y;
+  const int b = batch_offset + bl;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= min(keep_count[b], cap)) return;
+  const size_t off = (size_t)b * cap;
+  const int ci = keep[off + k];
+  const int loc = cand_loc[off + ci];
+  float4 bx = cand_box[off + ci];
+  // resize_boxes (fcos_utils/fcos.py:770-783): x * ratio_w, y * ratio_h in fp32
+  bx.x = __fmul_rn(bx.x, rt.rw[bl]); bx.z = __fmul_rn(bx.z, rt.rw[bl]);
+  bx.y = __fmul_rn(bx.y, rt.rh[bl]); bx.w = __fmul_rn(bx.w, rt.rh[bl]);
+  boxes[off + k] = bx;
+  scores[off + k] = cand_score[off + ci];
+  labels[off + k] = cand_label[off + ci];
+  const float* lr = hand_lr + ((size_t)b * locs + loc) * lr_ld;
+  sides[off + k] = (sigmoid_rn(__ldg(lr + 1)) > sigmoid_rn(__ldg(lr))) ? 1 : 0;
+  int l = 0;
+  while (l + 1 < gp.num_levels && loc >= gp.level_start[l + 1]) ++l;
+  level[off + k] = (float)l;
+  if (contacts) {
+    const float* cl = contact_logits + ((size_t)b * locs + loc) * contact_ld;
+    float best = sigmoid_rn(__ldg(cl));
+    int bi = 0;
+    for (int c = 1; c < 5; ++c) {
+      const float s = sigmoid_rn(__ldg(cl + c));
+      if (s > best) { best = s; bi = c; }
+    }
+    contacts[off + k] = bi;
+  }
+  if (dxdymags) {
+    // (d0, 0.1 * normalize((d1, d2), p=2, eps=1e-12))   fcos_utils/fcos.py:299-303
+    const float* dp = dxdy + ((size_t)b * locs + loc) * dxdy_ld;
+    float* o = dxdymags + (off + k) * 3;
+    const float d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
+    const float nrm = fmaxf(__fsqrt_rn(__fadd_rn(__fmul_rn(d1, d1), __fmul_rn(d2, d2))), 1e-12f);
+    o[0] = __ldg(dp);
+    o[1] = __fmul_rn(0.1f, __fdiv_rn(d1, nrm));
+    o[2] = __fmul_rn(0.1f, __fdiv_rn(d2, nrm));
+  }
+}
+
+}  // namespace
+
+extern "C" int64_t hn_fcos_select_workspace_bytes(int batch, int locs) {
+  const size_t n = (size_t)batch * locs;
+  return (int64_t)(align256(n * 4) * 2 + align256((size_t)batch * hn_div_up(locs, SEL_BLOCK) * 4));
+}
+
+extern "C" int hn_fcos_decode_select(const float* cls_logits, int cls_ld, const float* bbox_ctrness, int ctr_ld,
+                                     const float* bbox_regression, int reg_ld, int batch, int locs, int num_classes, int num_levels, const int* level_h_host,
+                                     const int* level_w_host, const int* level_stride_h_host,
+                                     const int* level_stride_w_host, const int* level_anchor_host, double score_thresh,
+                                     int* cand_count, int* cand_loc, float* cand_score, int* cand_label,
+                                     float* cand_box, void* workspace, int64_t workspace_bytes, void* stream) {
+  HN_REQUIRE(cls_logits && bbox_ctrness && bbox_regression && cand_count && cand_loc && cand_score && cand_label &&
+                 cand_box && workspace, "hn_fcos_decode_select: null pointer");
+  HN_REQUIRE(batch > 0 && locs > 0 && num_classes > 0 && num_levels > 0 && num_levels <= MAX_LEVELS,
+             "hn_fcos_decode_select: bad sizes");
+  HN_REQUIRE(cls_ld >= num_classes && ctr_ld >= 1 && reg_ld >= 4 && reg_ld % 4 == 0 &&
+                 (reinterpret_cast<uintptr_t>(bbox_regression) & 15) == 0,
+             "hn_fcos_decode_select: row strides (reg rows must be 16-byte aligned)");
+  HN_REQUIRE(workspace_bytes >= hn_fcos_select_workspace_bytes(batch, locs), "hn_fcos_decode_select: workspace too small");
+  Levels lv;
+  memset(&lv, 0, sizeof(lv));
+  lv.n = num_levels;
+  int acc = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    lv.start[l] = acc;
+    lv.h[l] = level_h_host[l];
+    lv.w[l] = level_w_host[l];
+    lv.sh[l] = level_stride_h_host[l];
+    lv.sw[l] = level_stride_w_host[l];
+    lv.anchor[l] = level_anchor_host[l];
+    acc += lv.h[l] * lv.w[l];
+  }
+  lv.start[num_levels] = acc;
+  HN_REQUIRE(acc == locs, "hn_fcos_decode_select: levels cover %d locations, locs=%d", acc, locs);
+  const size_t n = (size_t)batch * locs;
+  uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
+  float* dense_score = reinterpret_cast<float*>(w);
+  int* dense_label = reinterpret_cast<int*>(w + align256(n * 4));
+  int* chunk_count = reinterpret_cast<int*>(w + 2 * align256(n * 4));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(hn_div_up(locs, SEL_BLOCK), batch);
+  const float thresh_ge = float_gt_as_ge(score_thresh);
+  select_score_kernel<<<grid, SEL_BLOCK, 0, st>>>(cls_logits, cls_ld, bbox_ctrness, ctr_ld, locs, num_classes, thresh_ge,
+                                                  dense_score, dense_label, chunk_count);
+  hn_count_launch();
+  HN_LAUNCH_CHECK();
+  select_compact_kernel<<<grid, SEL_BLOCK, 0, st>>>(bbox_regression, reg_ld, dense_score, dense_label, chunk_count, locs,
+                                                    thresh_ge, lv, cand_count, cand_loc, cand_score, cand_label,
+                                                    reinterpret_cast<float4*>(cand_box));
+  hn_count_launch();
+  HN_LAUNCH_CHECK();
+  return HN_OK;
+}
+
+extern "C" int64_t hn_nms_workspace_bytes(int batch, int cap) {
+  const size_t n = (size_t)batch * cap;
+  const size_t words = (cap + 63) / 64;
+  return (int64_t)(align256(n * 4) * 4 + align256(n * 16) + align256(n * 4) + align256(n * words * 8));
+}
+
+extern "C" int hn_nms_batched(const float* cand_box, const float* cand_score, const int* cand_label,
+                              const int* cand_count, int batch, int cap, double iou_thresh, int coord_trick_max_numel,
+                              int* keep, int* keep_count, void* workspace, int64_t workspace_bytes, void* stream) {
+  HN_REQUIRE(cand_box && cand_score && cand_label && cand_count && keep && keep_count && workspace,
+             "hn_nms_batched: null pointer");
+  HN_REQUIRE(batch > 0 && cap > 0, "hn_nms_batched: bad sizes");
+  HN_REQUIRE(workspace_bytes >= hn_nms_workspace_bytes(batch, cap), "hn_nms_batched: workspace too small");
+  NmsWs ws = carve(workspace, batch, cap);
+  HN_REQUIRE((size_t)ws.words * 8 <= 200 * 1024, "hn_nms_batched: cap too large for the scan kernel");
+  const float thr_ge = float_gt_as_ge(iou_thresh);   // (double)iou > thr, as torchvision's CPU kernel compares
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  nms_sort_kernel<<<batch, SORT_THREADS, 0, st>>>(reinterpret_cast<const float4*>(cand_box), cand_score, cand_label,
+                                                  cand_count, cap, coord_trick_max_numel, ws);
+  hn_count_launch();
+  HN_LAUNCH_CHECK();
+  nms_mask_kernel<<<hn_num_sms() * 16, 64, 0, st>>>(cand_count, batch, cap, thr_ge, ws);
+  hn_count_launch();
+  HN_LAUNCH_CHECK();
+  const size_t scan_smem = (size_t)ws.words * 8;
+  static bool attr = false;
+  if (!attr && scan_smem > 40 * 1024) {
+    HN_CHECK_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  nms_scan_kernel<<<batch, SCAN_THREADS, scan_smem, st>>>(cand_count, cap, ws, keep, keep_count);
+  hn_count_launch();
+  HN_LAUNCH_CHECK();
+  return HN_OK;
+}
+
+extern "C" int hn_fcos_gather(const int* keep, const int* keep_count, const int* cand_loc, const float* cand_score,
+                              const int* cand_label, const float* cand_box, const float* hand_lr, int lr_ld,
+                              const float* contact_logits, int contact_ld, const float* dxdy, int dxdy_ld, int batch,
+                              int cap, int locs,
+                              int num_levels, const int* level_start_host, const float* ratio_h_host,
+                              const float* ratio_w_host, float* boxes, float* scores, int64_t* labels, int64_t* sides,
+                              float* level, int64_t* contacts, float* dxdymags, void* stream) {
+  HN_REQUIRE(keep && keep_count && cand_loc && cand_score && cand_label && cand_box && hand_lr && boxes && scores &&
+                 labels && sides && level, "hn_fcos_gather: null pointer");
+  HN_REQUIRE((contacts == nullptr) == (contact_logits == nullptr) && (dxdymags == nullptr) == (dxdy == nullptr),
+             "hn_fcos_gather: ext outputs need their inputs");
+  HN_REQUIRE(batch > 0 && cap > 0 && num_levels > 0 && num_levels <= MAX_LEVELS, "hn_fcos_gather: bad sizes");
+  GatherParams gp;
+  memset(&gp, 0, sizeof(gp));
+  gp.num_levels = num_levels;
+  for (int l = 0; l <= num_levels; ++l) gp.level_start[l] = level_start_host[l];
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int b0 = 0; b0 < batch; b0 += GATHER_MAX_BATCH) {
+    const int nb = (batch - b0 < GATHER_MAX_BATCH) ? batch - b0 : GATHER_MAX_BATCH;
+    Ratios rt;
+    for (int i = 0; i < nb; ++i) { rt.rh[i] = ratio_h_host[b0 + i]; rt.rw[i] = ratio_w_host[b0 + i]; }
+    dim3 grid(hn_div_up(cap, 256), nb);
+    gather_kernel<<<grid, 256, 0, st>>>(keep, keep_count, cand_loc, cand_score, cand_label,
+                                        reinterpret_cast<const float4*>(cand_box), hand_lr, lr_ld, contact_logits,
+                                        contact_ld, dxdy, dxdy_ld, cap, locs, b0, gp, rt, reinterpret_cast<float4*>(boxes), scores,
+                                        reinterpret_cast<long long*>(labels), reinterpret_cast<long long*>(sides), level,
+                                        reinterpret_cast<long long*>(contacts), dxdymags);
+    hn_count_launch();
+    HN_LAUNCH_CHECK();
+  }
+  return HN_OK;
+}

@@ -1,0 +1,343 @@
+"""Torch-tensor front end of the C ABI: one thin function per entry point of include/handnet_b200.h.
+
+PyTorch is used for device memory and streams only; all arithmetic happens in libhandnet_b200.so.
+Every function raises RuntimeError when the library reports an error -- there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, check, ptr, stream_ptr
+
+BF16 = torch.bfloat16
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must live on a CUDA device (libhandnet_b200 has no CPU path)")
+
+
+# ------------------------------------------------------------------------------------------------
+# activations
+# ------------------------------------------------------------------------------------------------
+class Act:
+    """Haloed NHWC bf16 activation: t[n, h + 2*halo, w + 2*halo, c]; the halo is zero and stays zero."""
+
+    __slots__ = ("t", "n", "h", "w", "c", "halo")
+
+    def __init__(self, n: int, h: int, w: int, c: int, halo: int, device="cuda", t: Optional[torch.Tensor] = None):
+        self.n, self.h, self.w, self.c, self.halo = n, h, w, c, halo
+        shape = (n, h + 2 * halo, w + 2 * halo, c)
+        self.t = torch.zeros(shape, dtype=BF16, device=device) if t is None else t
+        assert tuple(self.t.shape) == shape and self.t.dtype == BF16 and self.t.is_contiguous()
+
+    def interior(self) -> torch.Tensor:
+        p = self.halo
+        return self.t[:, p:p + self.h, p:p + self.w, :]
+
+    @staticmethod
+    def from_nchw(x: torch.Tensor, halo: int) -> "Act":
+        n, c, h, w = x.shape
+        a = Act(n, h, w, c, halo, x.device)
+        a.interior().copy_(x.permute(0, 2, 3, 1))
+        return a
+
+    def to_nchw(self) -> torch.Tensor:
+        return self.interior().permute(0, 3, 1, 2).float().contiguous()
+
+
+class PhaseAct:
+    """Phase-split haloed NHWC bf16: t[4, n, h2 + 2*halo, w2 + 2*halo, c], phase = (y & 1) * 2 + (x & 1),
+    (h2, w2) = ceil((h, w) / 2).  Input format of the stride-2 convolutions."""
+
+    __slots__ = ("t", "n", "h", "w", "h2", "w2", "c", "halo")
+
+    def __init__(self, n: int, h: int, w: int, c: int, halo: int, device="cuda"):
+        self.n, self.h, self.w, self.c, self.halo = n, h, w, c, halo
+        self.h2, self.w2 = (h + 1) // 2, (w + 1) // 2
+        self.t = torch.zeros((4, n, self.h2 + 2 * halo, self.w2 + 2 * halo, c), dtype=BF16, device=device)
+
+    @staticmethod
+    def from_nchw(x: torch.Tensor, halo: int) -> "PhaseAct":
+        n, c, h, w = x.shape
+        a = PhaseAct(n, h, w, c, halo, x.device)
+        xh = x.permute(0, 2, 3, 1)
+        for py in range(2):
+            for px in range(2):
+                sub = xh[:, py::2, px::2, :]
+                a.t[py * 2 + px, :, halo:halo + sub.shape[1], halo:halo + sub.shape[2], :] = sub
+        return a
+
+
+def pad_cout(cout: int) -> int:
+    if cout <= 16:
+        return 16
+    if cout <= 32:
+        return 32
+    return (cout + 63) // 64 * 64
+
+
+def pack_conv_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """OIHW fp32 -> bf16 [cout_pad][kh*kw*cin] (tap-major K, channels fastest), zero rows beyond cout."""
+    cout, cin, kh, kw = w.shape
+    m = w.detach().float().permute(0, 2, 3, 1).reshape(cout, kh * kw * cin)
+    out = torch.zeros((pad_cout(cout), m.shape[1]), dtype=BF16, device=w.device)
+    out[:cout] = m.to(BF16)
+    return out.contiguous()
+
+
+def pack_stem_weight(w: torch.Tensor, k_pad: int) -> torch.Tensor:
+    """7x7 stem OIHW -> bf16 [cout_pad][k_pad], k = (r*7 + s)*cin + ch (matches hn_im2col_7x7s2)."""
+    cout, cin, kh, kw = w.shape
+    m = w.detach().float().permute(0, 2, 3, 1).reshape(cout, kh * kw * cin)
+    out = torch.zeros((pad_cout(cout), k_pad), dtype=BF16, device=w.device)
+    out[:cout, : m.shape[1]] = m.to(BF16)
+    return out.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# entry points
+# ------------------------------------------------------------------------------------------------
+def device_info() -> Tuple[int, int, int]:
+    sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+    check(_lib.load().hn_device_info(C.byref(sm), C.byref(ma), C.byref(mi)), "hn_device_info")
+    return sm.value, ma.value, mi.value
+
+
+def launch_count() -> int:
+    return int(_lib.load().hn_launch_count())
+
+
+def preprocess(images: Sequence[torch.Tensor], out_sizes: Sequence[Tuple[int, int]], canvas_hw: Tuple[int, int],
+               mean: Sequence[float], std: Sequence[float], canvas: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """T1.  images: list of fp32 [3,H,W] CUDA tensors -> bf16 canvas [B, Hc, Wc, 4]."""
+    b = len(images)
+    imgs = []
+    for im in images:
+        _require_cuda(im, "image")
+        if im.dtype != torch.float32 or im.dim() != 3 or im.shape[0] != 3:
+            raise RuntimeError("images must be float32 [3, H, W]")
+        imgs.append(im.contiguous())
+    dev = imgs[0].device
+    if canvas is None:
+        canvas = torch.empty((b, canvas_hw[0], canvas_hw[1], 4), dtype=BF16, device=dev)
+    ptrs = (C.c_void_p * b)(*[t.data_ptr() for t in imgs])
+    ih = (C.c_int * b)(*[int(t.shape[1]) for t in imgs])
+    iw = (C.c_int * b)(*[int(t.shape[2]) for t in imgs])
+    oh = (C.c_int * b)(*[int(s[0]) for s in out_sizes])
+    ow = (C.c_int * b)(*[int(s[1]) for s in out_sizes])
+    m3 = (C.c_float * 3)(*[float(v) for v in mean])
+    s3 = (C.c_float * 3)(*[float(v) for v in std])
+    check(_lib.load().hn_preprocess_resize_pad(ptrs, ih, iw, oh, ow, b, m3, s3, canvas.data_ptr(), canvas_hw[0],
+                                               canvas_hw[1], stream_ptr()), "hn_preprocess_resize_pad")
+    return canvas
+
+
+def im2col_7x7s2(x: torch.Tensor, k_pad: int, out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, int, int]:
+    """x: bf16 [n,h,w,4] canvas (3 channels used) or fp32 [n,h,w] depth -> bf16 [n*oh*ow, k_pad]."""
+    _require_cuda(x, "x")
+    is_f32 = x.dtype == torch.float32
+    if is_f32:
+        n, h, w = x.shape
+        c = 1
+    else:
+        n, h, w, c4 = x.shape
+        assert c4 == 4 and x.dtype == BF16
+        c = 3
+    oh, ow = (h + 1) // 2, (w + 1) // 2
+    if out is None:
+        out = torch.empty((n * oh * ow, k_pad), dtype=BF16, device=x.device)
+    check(_lib.load().hn_im2col_7x7s2(x.data_ptr(), int(is_f32), n, h, w, c, out.data_ptr(), k_pad, stream_ptr()),
+          "hn_im2col_7x7s2")
+    return out, oh, ow
+
+
+def conv2d(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 1, dilation: int = 1,
+           scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None, relu=False,
+           res: Optional[Act] = None, res_mode: int = 0, out: Optional[Act] = None,
+           out_f32: Optional[torch.Tensor] = None, out_rows_per_image: int = 0, out_row_offset: int = 0,
+           out_transpose_hw: bool = False, out_phase: Optional[PhaseAct] = None,
+           gn_stats: Optional[torch.Tensor] = None, gn_groups: int = 0, block_n: int = 0):
+    """hn_conv2d_bf16.  x: Act (stride 1) or PhaseAct (stride 2).  relu: bool or (lo, hi) channel range."""
+    d = ConvDesc()
+    if isinstance(x, PhaseAct):
+        assert stride == 2
+        d.in_, d.n, d.h, d.w, d.cin, d.halo_in, d.in_phases = x.t.data_ptr(), x.n, x.h2, x.w2, x.c, x.halo, 4
+    else:
+        assert stride == 1
+        d.in_, d.n, d.h, d.w, d.cin, d.halo_in, d.in_phases = x.t.data_ptr(), x.n, x.h, x.w, x.c, x.halo, 1
+    assert weight.dtype == BF16 and weight.is_contiguous() and weight.shape[1] == ksize * ksize * d.cin, \
+        (weight.shape, ksize, d.cin)
+    d.weight, d.cout, d.cout_pad = weight.data_ptr(), cout, weight.shape[0]
+    d.kh = d.kw = ksize
+    d.stride, d.dilation = stride, dilation
+    d.scale, d.shift = ptr(scale), ptr(shift)
+    if relu is True:
+        d.relu_lo, d.relu_hi = 0, cout
+    elif relu:
+        d.relu_lo, d.relu_hi = relu
+    if res is not None:
+        d.res, d.res_mode, d.res_h, d.res_w, d.res_halo = res.t.data_ptr(), res_mode or 1, res.h, res.w, res.halo
+        assert res.c == cout
+    if out_f32 is not None:
+        assert out_f32.dtype == torch.float32 and out_f32.is_contiguous()
+        d.out, d.out_kind = out_f32.data_ptr(), 1
+        d.out_rows_per_image = out_rows_per_image or d.h * d.w
+        d.out_row_offset, d.out_ld, d.out_transpose_hw = out_row_offset, out_f32.shape[-1], int(out_transpose_hw)
+    else:
+        assert out is not None and out.c == cout and (out.n, out.h, out.w) == (d.n, d.h, d.w), "output geometry"
+        d.out, d.out_kind, d.out_halo = out.t.data_ptr(), 0, out.halo
+    if out_phase is not None:
+        assert (out_phase.n, out_phase.h, out_phase.w, out_phase.c) == (d.n, d.h, d.w, cout)
+        d.out_phase, d.out_phase_halo = out_phase.t.data_ptr(), out_phase.halo
+    if gn_stats is not None:
+        assert gn_stats.dtype == torch.float64 and gn_stats.numel() == d.n * gn_groups * 2
+        d.gn_stats, d.gn_groups = gn_stats.data_ptr(), gn_groups
+    d.block_n = block_n
+    check(_lib.load().hn_conv2d_bf16(C.byref(d), stream_ptr()), "hn_conv2d_bf16")
+    return out if out_f32 is None else out_f32
+
+
+def maxpool3x3s2(x: torch.Tensor, out: Act) -> Act:
+    """x: bf16 [n,h,w,c] (no halo) -> out Act [n, ceil(h/2), ceil(w/2), c]."""
+    n, h, w, c = x.shape
+    assert x.dtype == BF16 and x.is_contiguous() and (out.h, out.w, out.c) == ((h + 1) // 2, (w + 1) // 2, c)
+    check(_lib.load().hn_maxpool3x3s2(x.data_ptr(), n, h, w, c, out.t.data_ptr(), out.halo, stream_ptr()),
+          "hn_maxpool3x3s2")
+    return out
+
+
+def groupnorm_relu(x: Act, stats: torch.Tensor, groups: int, gamma: torch.Tensor, beta: torch.Tensor,
+                   eps: float = 1e-5) -> Act:
+    check(_lib.load().hn_groupnorm_relu(x.t.data_ptr(), x.n, x.h, x.w, x.c, x.halo, stats.data_ptr(), groups,
+                                        gamma.data_ptr(), beta.data_ptr(), eps, stream_ptr()), "hn_groupnorm_relu")
+    return x
+
+
+class Levels:
+    """Pyramid description shared by decode and gather."""
+
+    def __init__(self, grids: Sequence[Tuple[int, int]], canvas_hw: Tuple[int, int], anchor_sizes: Sequence[int]):
+        self.grids = [tuple(int(v) for v in g) for g in grids]
+        self.n = len(self.grids)
+        self.locs = sum(h * w for h, w in self.grids)
+        starts = [0]
+        for h, w in self.grids:
+            starts.append(starts[-1] + h * w)
+        self.starts = starts
+        arr = C.c_int * self.n
+        self.h = arr(*[g[0] for g in self.grids])
+        self.w = arr(*[g[1] for g in self.grids])
+        self.sh = arr(*[canvas_hw[0] // g[0] for g in self.grids])      # anchor_utils.py:118-124
+        self.sw = arr(*[canvas_hw[1] // g[1] for g in self.grids])
+        self.anchor = arr(*[int(s) for s in anchor_sizes])
+        self.start_arr = (C.c_int * (self.n + 1))(*starts)
+
+
+def fcos_decode_select(cls: torch.Tensor, ctr: torch.Tensor, reg: torch.Tensor, num_classes: int, levels: Levels,
+                       score_thresh: float, ws: Optional[torch.Tensor] = None):
+    """P1-P4.  cls/ctr/reg are fp32 views [B, locs, k] whose last-dim stride is 1 (row stride = stride(1))."""
+    b, locs = cls.shape[0], cls.shape[1]
+    assert locs == levels.locs
+    dev = cls.device
+    need = int(_lib.load().hn_fcos_select_workspace_bytes(b, locs))
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    cand = {
+        "count": torch.empty(b, dtype=torch.int32, device=dev),
+        "loc": torch.empty((b, locs), dtype=torch.int32, device=dev),
+        "score": torch.empty((b, locs), dtype=torch.float32, device=dev),
+        "label": torch.empty((b, locs), dtype=torch.int32, device=dev),
+        "box": torch.empty((b, locs, 4), dtype=torch.float32, device=dev),
+    }
+    for t in (cls, ctr, reg):
+        assert t.dtype == torch.float32 and t.stride(-1) == 1 and t.stride(0) == t.stride(1) * locs
+    check(_lib.load().hn_fcos_decode_select(
+        cls.data_ptr(), cls.stride(1), ctr.data_ptr(), ctr.stride(1), reg.data_ptr(), reg.stride(1), b, locs,
+        num_classes, levels.n, levels.h, levels.w, levels.sh, levels.sw, levels.anchor, float(score_thresh),
+        cand["count"].data_ptr(), cand["loc"].data_ptr(), cand["score"].data_ptr(), cand["label"].data_ptr(),
+        cand["box"].data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr()), "hn_fcos_decode_select")
+    return cand
+
+
+def nms_workspace(batch: int, cap: int, device) -> torch.Tensor:
+    return torch.empty(int(_lib.load().hn_nms_workspace_bytes(batch, cap)), dtype=torch.uint8, device=device)
+
+
+def nms_batched(box: torch.Tensor, score: torch.Tensor, label: torch.Tensor, count: torch.Tensor,
+                iou_thresh: float, coord_trick_max_numel: int = 4000, ws: Optional[torch.Tensor] = None):
+    """P5.  Returns (keep [B, cap] int32 indices into the candidate list, keep_count [B] int32)."""
+    b, cap = score.shape
+    dev = score.device
+    if ws is None:
+        ws = nms_workspace(b, cap, dev)
+    keep = torch.empty((b, cap), dtype=torch.int32, device=dev)
+    keep_count = torch.empty(b, dtype=torch.int32, device=dev)
+    check(_lib.load().hn_nms_batched(box.data_ptr(), score.data_ptr(), label.data_ptr(), count.data_ptr(), b, cap,
+                                     float(iou_thresh), int(coord_trick_max_numel), keep.data_ptr(),
+                                     keep_count.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr()), "hn_nms_batched")
+    return keep, keep_count
+
+
+def fcos_gather(keep, keep_count, cand, hand_lr: torch.Tensor, levels: Levels, ratios_h: Sequence[float],
+                ratios_w: Sequence[float], contact: Optional[torch.Tensor] = None,
+                dxdy: Optional[torch.Tensor] = None):
+    """P6.  Dense per-image outputs with capacity cap = locs."""
+    b, cap = keep.shape
+    dev = keep.device
+    out = {
+        "boxes": torch.empty((b, cap, 4), dtype=torch.float32, device=dev),
+        "scores": torch.empty((b, cap), dtype=torch.float32, device=dev),
+        "labels": torch.empty((b, cap), dtype=torch.int64, device=dev),
+        "sides": torch.empty((b, cap), dtype=torch.int64, device=dev),
+        "level": torch.empty((b, cap), dtype=torch.float32, device=dev),
+    }
+    if contact is not None:
+        out["contacts"] = torch.empty((b, cap), dtype=torch.int64, device=dev)
+        out["dxdymags"] = torch.empty((b, cap, 3), dtype=torch.float32, device=dev)
+    rh = (C.c_float * b)(*[float(v) for v in ratios_h])
+    rw = (C.c_float * b)(*[float(v) for v in ratios_w])
+    check(_lib.load().hn_fcos_gather(
+        keep.data_ptr(), keep_count.data_ptr(), cand["loc"].data_ptr(), cand["score"].data_ptr(),
+        cand["label"].data_ptr(), cand["box"].data_ptr(), hand_lr.data_ptr(), hand_lr.stride(1),
+        ptr(contact), contact.stride(1) if contact is not None else 0, ptr(dxdy),
+        dxdy.stride(1) if dxdy is not None else 0, b, cap, levels.locs, levels.n, levels.start_arr, rh, rw,
+        out["boxes"].data_ptr(), out["scores"].data_ptr(), out["labels"].data_ptr(), out["sides"].data_ptr(),
+        out["level"].data_ptr(), ptr(out.get("contacts")), ptr(out.get("dxdymags")), stream_ptr()), "hn_fcos_gather")
+    return out
+
+
+def select_crop_resize(boxes: torch.Tensor, labels: torch.Tensor, keep_count: torch.Tensor, hand_label: int,
+                       depth: torch.Tensor, out_size: int = 176):
+    """S1 + S2.  depth: fp32 [B, C, H, W].  Returns (crops [B,4] int64, has_hand [B] int32, depth_batch)."""
+    b, cap = labels.shape
+    _, dc, ih, iw = depth.shape
+    assert depth.dtype == torch.float32 and depth.is_contiguous() and depth.shape[0] == b
+    dev = depth.device
+    crops = torch.empty((b, 4), dtype=torch.int64, device=dev)
+    has = torch.empty(b, dtype=torch.int32, device=dev)
+    db = torch.empty((b, dc, out_size, out_size), dtype=torch.float32, device=dev)
+    check(_lib.load().hn_select_crop_resize(boxes.data_ptr(), labels.data_ptr(), keep_count.data_ptr(), b, cap,
+                                            hand_label, depth.data_ptr(), dc, ih, iw, out_size, crops.data_ptr(),
+                                            has.data_ptr(), db.data_ptr(), stream_ptr()), "hn_select_crop_resize")
+    return crops, has, db
+
+
+def a2j_aggregate(cls: torch.Tensor, reg: torch.Tensor, dep: torch.Tensor, anchors: torch.Tensor,
+                  ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """J4.  cls [n,A,J], reg [n,A,J,2], dep [n,A,J] fp32 contiguous; anchors [A,2] fp32 -> [n,J,3]."""
+    n, a, j = cls.shape
+    for t in (cls, reg, dep, anchors):
+        _require_cuda(t, "a2j head")
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    need = int(_lib.load().hn_a2j_workspace_bytes(n, j))
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=cls.device)
+    out = torch.empty((n, j, 3), dtype=torch.float32, device=cls.device)
+    check(_lib.load().hn_a2j_aggregate(cls.data_ptr(), reg.data_ptr(), dep.data_ptr(), anchors.data_ptr(), n, a, j,
+                                       out.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr()), "hn_a2j_aggregate")
+    return out

@@ -1,0 +1,168 @@
+/*
+ * libhandnet_b200 -- C ABI of the B200 (sm_100a) kernels behind the HandNet detect -> crop -> pose path.
+ *
+ * The reference (IRVLUTD/handnet-pipeline) is pure Python/PyTorch and has no FFI of its own
+ * (SURVEY.md section 8b); each entry point below names the reference code it replaces.  The Python
+ * modules in handnet-pipeline_b200/{handnet_pipeline,fcos_utils,a2j}/ bind these symbols with ctypes
+ * (hn_b200/_lib.py) and keep the reference's class / function surface.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - every function returns 0 on success or a negative hn_status; hn_last_error() gives the text;
+ *   - work is enqueued on the cudaStream_t passed as `stream` (void* here); nothing synchronises the
+ *     device and nothing allocates device memory: scratch space is supplied by the caller;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with HN_ERR_CUDA.
+ *
+ * Activation layout ("haloed NHWC"): bf16 [N][H + 2*halo][W + 2*halo][C], halo rows/columns are zero and
+ * are never written by any kernel, so a KxK convolution is a GEMM whose A operand for tap (r,s) is the
+ * same matrix shifted by (r*Wp + s) rows.  Stride-2 convolutions read a "phase-split" copy
+ * [4][N][ceil(H/2) + 2*halo][ceil(W/2) + 2*halo][C] (phase = (h&1)*2 + (w&1)) that the producing layer
+ * writes next to its normal output.
+ */
+#ifndef HANDNET_B200_H
+#define HANDNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  HN_OK = 0,
+  HN_ERR_ARG = -1,         /* bad argument / unsupported shape */
+  HN_ERR_CUDA = -2,        /* CUDA runtime or driver error (incl. no device) */
+  HN_ERR_UNSUPPORTED = -3  /* device is not sm_100 */
+} hn_status;
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+const char* hn_last_error(void);
+int hn_version(void);
+/* sm_count / cc_major / cc_minor of the current device. */
+int hn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t hn_launch_count(void);
+
+/* ---- T1: GeneralizedRCNNTransform (fcos_utils/fcos.py:505,709; torchvision transform.py:119-255) ---------
+ * (x - mean) / std, bilinear resize (align_corners=False, scale = in/out), zero-padded canvas.
+ * images_host[i] points at DEVICE memory holding image i as fp32 [3][in_h[i]][in_w[i]] in 0..1; the arrays
+ * themselves (images_host, in_h_host, ...) live on the host.  Output: bf16 [batch][canvas_h][canvas_w][4]
+ * (channel 3 is zero); pixels outside (out_h[i], out_w[i]) are zero. */
+int hn_preprocess_resize_pad(const float* const* images_host, const int* in_h_host, const int* in_w_host,
+                             const int* out_h_host, const int* out_w_host, int batch, const float* mean3_host,
+                             const float* std3_host, void* canvas_bf16, int canvas_h, int canvas_w, void* stream);
+
+/* ---- stem: 7x7 stride-2 pad-3 patches as GEMM rows (fcos backbone.body.conv1; a2j/resnet.py:105) ----------
+ * in: [n][h][w][c] (c = 4 bf16 when in_is_f32 == 0, c = 1 fp32 when in_is_f32 == 1).
+ * out: bf16 [n * ceil(h/2) * ceil(w/2)][k_pad], k = (r*7 + s)*c + ch, zero beyond 49*c. */
+int hn_im2col_7x7s2(const void* in, int in_is_f32, int n, int h, int w, int c, void* out_bf16, int k_pad,
+                    void* stream);
+
+/* ---- convolution as shifted GEMM on tcgen05 (all 3x3 / 1x1 convs of B1, B2, H1, H2, J1, J2) ---------------- */
+typedef struct hn_conv_desc {
+  /* input, haloed NHWC bf16.  For stride 2, `in` is the phase-split copy and (h, w) are the per-phase
+   * (= output) sizes.  For the stem GEMM use kh = kw = 1, halo_in = 0, cin = k_pad. */
+  const void* in;
+  int n, h, w, cin, halo_in, in_phases; /* in_phases: 1, or 4 for a phase-split input */
+  /* weights: bf16 [cout_pad][kh*kw][cin] (tap-major K), cout_pad a multiple of block_n */
+  const void* weight;
+  int cout, cout_pad, kh, kw, stride, dilation;
+  /* epilogue: y = acc * scale[c] + shift[c] (+ residual) ; relu on channels [relu_lo, relu_hi) ; store */
+  const float* scale; /* may be NULL (== 1) */
+  const float* shift; /* may be NULL (== 0) */
+  int relu_lo, relu_hi;
+  const void* res; /* bf16 haloed NHWC with `cout` channels, or NULL */
+  int res_mode;    /* 1: same pixel (res_h,res_w == output size); 2: nearest 2x upsample of a coarser map */
+  int res_h, res_w, res_halo;
+  /* output */
+  void* out;
+  int out_kind; /* 0: bf16 haloed NHWC [n][h+2*out_halo][w+2*out_halo][cout];
+                   1: fp32 rows: out[(img*out_rows_per_image + out_row_offset + pix)*out_ld + c],
+                      pix = h*W + w, or w*H + h when out_transpose_hw */
+  int out_halo;
+  int out_rows_per_image, out_row_offset, out_ld, out_transpose_hw;
+  void* out_phase; /* optional second bf16 output, phase-split with halo out_phase_halo; NULL if unused */
+  int out_phase_halo;
+  double* gn_stats; /* optional [n][gn_groups][2] (sum, sum of squares) over the bf16-rounded output,
+                       accumulated with atomics -- caller zeroes it */
+  int gn_groups;
+  int block_n; /* 0 = choose automatically among 16/32/64/128/256 */
+} hn_conv_desc;
+int hn_conv2d_bf16(const hn_conv_desc* desc, void* stream);
+
+/* ---- 3x3 stride-2 pad-1 max pool (torchvision resnet maxpool; a2j/resnet.py:108) ----------------------------
+ * in: bf16 [n][h][w][c] (no halo) -> out: bf16 haloed NHWC [n][oh+2*halo][ow+2*halo][c], oh = (h+1)/2. */
+int hn_maxpool3x3s2(const void* in, int n, int h, int w, int c, void* out, int out_halo, void* stream);
+
+/* ---- GroupNorm + ReLU of the FCOS towers (fcos_utils/fcos.py:232-240, 352-360) ------------------------------
+ * x: bf16 haloed NHWC, normalised in place: relu((x - mean) * rstd * gamma + beta) with mean/rstd from
+ * stats[n][groups][2] (as produced by hn_conv2d_bf16) over h*w*(c/groups) elements.  Halo stays zero. */
+int hn_groupnorm_relu(void* x, int n, int h, int w, int c, int halo, const double* stats, int groups,
+                      const float* gamma, const float* beta, float eps, void* stream);
+
+/* ---- P1..P4: decode + score + threshold (fcos_utils/fcos.py:591-632; det_utils.py:266-294;
+ *      anchor_utils.py:56-132) -------------------------------------------------------------------------------
+ * Head tensors are fp32 rows [batch][locs][*_ld] (the fused output convs write several heads side by side, so
+ * each tensor has its own row stride; reg_ld must be a multiple of 4 and bbox_regression 16-byte aligned).
+ * Levels are described by level_h/w/stride (host arrays).  For every
+ * location: box = anchor-centre -/+ reg * anchor-size (anchors are generated on the fly), score = max over classes
+ * of sqrt(sigmoid(cls_c) * sigmoid(ctr)), label = first arg-max class (class 0 included), candidate when
+ * score > score_thresh (a double, compared the way `scores > 0.7` is in the reference).  Candidates are written
+ * per image in ascending location order:
+ *   cand_count[batch], cand_loc[batch][locs] (int32), cand_score[batch][locs] (fp32),
+ *   cand_label[batch][locs] (int32), cand_box[batch][locs][4] (fp32, canvas pixels, NOT clipped). */
+int hn_fcos_decode_select(const float* cls_logits, int cls_ld, const float* bbox_ctrness, int ctr_ld,
+                          const float* bbox_regression, int reg_ld, int batch, int locs, int num_classes, int num_levels, const int* level_h_host,
+                          const int* level_w_host, const int* level_stride_h_host, const int* level_stride_w_host,
+                          const int* level_anchor_host, double score_thresh, int* cand_count, int* cand_loc,
+                          float* cand_score, int* cand_label, float* cand_box, void* workspace,
+                          int64_t workspace_bytes, void* stream);
+int64_t hn_fcos_select_workspace_bytes(int batch, int locs);
+
+/* ---- P5: batched NMS (fcos_utils/fcos.py:635 -> torchvision.ops.boxes.batched_nms, CPU semantics) ----------
+ * Per image: stable descending score order; class-aware greedy suppression with IoU evaluated in fp32 and
+ * compared as torchvision's CPU kernel does ((double)iou > (double)iou_thresh).  When 4*count <=
+ * coord_trick_max_numel the "coordinate trick" of torchvision (boxes + label*(max+1)) is reproduced, above it
+ * suppression is restricted to equal labels.  keep[batch][cap] receives indices INTO THE CANDIDATE LIST in
+ * score-descending order (ties: ascending candidate index), keep_count[batch] their number.
+ * workspace: hn_nms_workspace_bytes(batch, cap) bytes. */
+int64_t hn_nms_workspace_bytes(int batch, int cap);
+int hn_nms_batched(const float* cand_box, const float* cand_score, const int* cand_label, const int* cand_count,
+                   int batch, int cap, double iou_thresh, int coord_trick_max_numel, int* keep, int* keep_count,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- P6: gather kept detections + resize_boxes (fcos_utils/fcos.py:648-669, 770-783) -----------------------
+ * ratio_h[i] = orig_h / resized_h, ratio_w likewise, as fp32 (host arrays).  Outputs are dense per image with
+ * capacity cap: boxes[batch][cap][4], scores[batch][cap], labels[batch][cap] (int64), sides[batch][cap]
+ * (int64, argmax of hand_lr), level[batch][cap] (fp32 pyramid level = the reference's feature_idx).
+ * hand_lr is fp32 rows [batch][locs][lr_ld] (2 used).  Optional ext heads (pass NULL to skip):
+ * contact_logits rows [..][contact_ld] (5 used) -> contacts[batch][cap] (int64, argmax of sigmoid);
+ * dxdy rows [..][dxdy_ld] (3 used, already ReLU'd) -> dxdymags[batch][cap][3] = (d0, 0.1 * normalize(d1, d2))
+ * (fcos_utils/fcos.py:299-303). */
+int hn_fcos_gather(const int* keep, const int* keep_count, const int* cand_loc, const float* cand_score,
+                   const int* cand_label, const float* cand_box, const float* hand_lr, int lr_ld,
+                   const float* contact_logits, int contact_ld, const float* dxdy, int dxdy_ld, int batch, int cap, int locs, int num_levels, const int* level_start_host,
+                   const float* ratio_h_host, const float* ratio_w_host, float* boxes, float* scores, int64_t* labels,
+                   int64_t* sides, float* level, int64_t* contacts, float* dxdymags, void* stream);
+
+/* ---- S1 + S2: hand select, box pad, depth crop, nearest resize (handnet_pipeline.py:74-102) ------------------
+ * For image i: first kept detection with label == hand_label; truncate to integers; pad by 0.4*w / 0.4*h in
+ * fp32 and clamp to the image; crop depth[i][:, y1:y2+1, x1:x2+1] and resize to out_size x out_size with the
+ * legacy nearest rule.  depth: fp32 [batch][depth_c][img_h][img_w].  Outputs: crops[batch][4] (int64),
+ * has_hand[batch] (int32), depth_batch fp32 [batch][depth_c][out][out] (zeros where no hand). */
+int hn_select_crop_resize(const float* boxes, const int64_t* labels, const int* keep_count, int batch, int cap,
+                          int hand_label, const float* depth, int depth_c, int img_h, int img_w, int out_size,
+                          int64_t* crops, int* has_hand, float* depth_batch, void* stream);
+
+/* ---- J4: anchor aggregation (a2j/anchor.py:57-82) ------------------------------------------------------------
+ * cls [n][anchors][joints], reg [n][anchors][joints][2], depth [n][anchors][joints] fp32; anchor_xy
+ * [anchors][2].  out [n][joints][3] = (sum w*(a0+r0), sum w*(a1+r1), sum w*d), w = softmax over anchors.
+ * workspace: hn_a2j_workspace_bytes(n, joints). */
+int64_t hn_a2j_workspace_bytes(int n, int joints);
+int hn_a2j_aggregate(const float* cls, const float* reg, const float* depth, const float* anchor_xy, int n,
+                     int anchors, int joints, float* out, void* workspace, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HANDNET_B200_H */

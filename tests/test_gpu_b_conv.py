@@ -1,0 +1,228 @@
+"""GPU parity: tcgen05 shifted-GEMM convolution and the glue kernels around it.
+
+The comparator for a single layer is torch's fp32 convolution (TF32 off) on the same bf16-rounded inputs and
+weights: both sides accumulate bf16 x bf16 products in fp32, so they agree to fp32 summation-order noise; the
+output is then rounded to bf16 by the kernel (tolerance: 1 bf16 ulp = 2^-8 relative)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import fcos_oracle
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from hn_b200 import ops as _ops
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return _ops
+
+
+def q(x):
+    return x.to(torch.bfloat16).float()
+
+
+def close_bf16(got, ref, what=""):
+    """|got - ref| <= 2^-7 * |ref| + small: one bf16 rounding plus fp32 reorder noise."""
+    err = (got - ref).abs()
+    tol = ref.abs() * 2 ** -7 + 2e-3 * ref.abs().max().clamp(min=1e-3)
+    bad = err > tol
+    assert not bad.any(), f"{what}: {int(bad.sum())} of {bad.numel()} off, max err {err.max().item():.4e}"
+
+
+def rand(g, *shape, scale=1.0):
+    return q(torch.randn(*shape, generator=g) * scale)
+
+
+CASES = [
+    # name, n, h, w, cin, cout, k, stride, dil, halo, block_n
+    ("1x1_64_64_bn64", 2, 9, 13, 64, 64, 1, 1, 1, 1, 64),
+    ("3x3_64_64_bn64", 2, 20, 28, 64, 64, 3, 1, 1, 1, 64),
+    ("3x3_128_128_bn128", 2, 20, 28, 128, 128, 3, 1, 1, 1, 128),
+    ("3x3_256_256_bn256", 2, 25, 34, 256, 256, 3, 1, 1, 1, 256),
+    ("3x3_256_256_auto", 3, 50, 68, 256, 256, 3, 1, 1, 1, 0),
+    ("1x1_512_2048_auto", 3, 11, 11, 512, 2048, 1, 1, 1, 1, 0),
+    ("3x3_2048_256_auto", 2, 11, 11, 2048, 256, 3, 1, 1, 1, 0),
+    ("3x3_64_32_bn32", 1, 12, 20, 64, 32, 3, 1, 1, 1, 32),
+    ("3x3_256_5_bn16", 2, 25, 34, 256, 5, 3, 1, 1, 1, 16),
+    ("3x3_256_336_pad", 2, 11, 11, 256, 336, 3, 1, 1, 1, 0),
+    ("3x3_s2_64_128", 2, 20, 28, 64, 128, 3, 2, 1, 1, 0),
+    ("3x3_s2_odd_128_256", 2, 25, 33, 128, 256, 3, 2, 1, 1, 0),
+    ("1x1_s2_256_512", 2, 22, 22, 256, 512, 1, 2, 1, 1, 0),
+    ("3x3_dil2_512_512", 3, 11, 11, 512, 512, 3, 1, 2, 2, 0),
+    ("3x3_halo2_in_halo1_conv", 2, 11, 11, 64, 64, 3, 1, 1, 2, 64),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv_scale_shift_relu(ops, case):
+    name, n, h, w, cin, cout, k, stride, dil, halo, bn = case
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
+    x = rand(g, n, cin, h, w).to(DEV)
+    wt = rand(g, cout, cin, k, k, scale=(cin * k * k) ** -0.5).to(DEV)
+    scale = (0.5 + torch.rand(cout, generator=g)).to(DEV)
+    shift = (0.3 * torch.randn(cout, generator=g)).to(DEV)
+    ref = F.conv2d(x, wt, None, stride=stride, padding=(k // 2) * dil, dilation=dil)
+    ref = F.relu(ref * scale[None, :, None, None] + shift[None, :, None, None])
+    xin = ops.Act.from_nchw(x, halo) if stride == 1 else ops.PhaseAct.from_nchw(x, halo)
+    out = ops.Act(n, ref.shape[2], ref.shape[3], cout, 1, DEV)
+    ops.conv2d(xin, ops.pack_conv_weight(wt), cout=cout, ksize=k, stride=stride, dilation=dil, scale=scale,
+               shift=shift, relu=True, out=out, block_n=bn)
+    torch.cuda.synchronize()
+    close_bf16(out.to_nchw(), ref, name)
+    full = out.t.float().abs().sum()
+    assert torch.isclose(full, out.interior().float().abs().sum()), "halo of the output must stay zero"
+
+
+def test_conv_residual_phase_copy_and_geometry_remap(ops):
+    """BasicBlock tail: conv + scale/shift + identity + ReLU, written twice (plain halo-2 and phase-split)."""
+    g = torch.Generator().manual_seed(7)
+    n, h, w, c = 2, 26, 18, 128
+    x = rand(g, n, c, h, w).to(DEV)
+    idn = rand(g, n, c, h, w).to(DEV)
+    wt = rand(g, c, c, 3, 3, scale=(c * 9) ** -0.5).to(DEV)
+    scale = (0.5 + torch.rand(c, generator=g)).to(DEV)
+    shift = (0.3 * torch.randn(c, generator=g)).to(DEV)
+    ref = F.relu(F.conv2d(x, wt, padding=1) * scale[None, :, None, None] + shift[None, :, None, None] + idn)
+    out = ops.Act(n, h, w, c, 2, DEV)
+    ph = ops.PhaseAct(n, h, w, c, 1, DEV)
+    ops.conv2d(ops.Act.from_nchw(x, 1), ops.pack_conv_weight(wt), cout=c, ksize=3, scale=scale, shift=shift,
+               relu=True, res=ops.Act.from_nchw(idn, 3), res_mode=1, out=out, out_phase=ph)
+    torch.cuda.synchronize()
+    close_bf16(out.to_nchw(), ref, "plain")
+    want = ops.PhaseAct.from_nchw(out.to_nchw(), 1)
+    assert torch.equal(ph.t, want.t), "phase-split copy must hold the same bf16 values"
+
+
+def test_conv_fpn_lateral_upsample_add(ops):
+    g = torch.Generator().manual_seed(8)
+    n, h, w = 2, 50, 68
+    x = rand(g, n, 256, h, w).to(DEV)
+    top = rand(g, n, 256, h // 2, w // 2).to(DEV)
+    wt = rand(g, 256, 256, 1, 1, scale=1 / 16).to(DEV)
+    bias = (0.1 * torch.randn(256, generator=g)).to(DEV)
+    ref = F.conv2d(x, wt, bias) + F.interpolate(top, size=(h, w), mode="nearest")
+    out = ops.Act(n, h, w, 256, 1, DEV)
+    ops.conv2d(ops.Act.from_nchw(x, 1), ops.pack_conv_weight(wt), cout=256, ksize=1, shift=bias,
+               res=ops.Act.from_nchw(top, 1), res_mode=2, out=out)
+    torch.cuda.synchronize()
+    close_bf16(out.to_nchw(), ref, "fpn lateral")
+
+
+def test_conv_fp32_rows_output_fused_heads(ops):
+    """FCOS output convs: [cls(3) | lr(2)] fused, ReLU on a channel sub-range, fp32 rows at a level offset."""
+    g = torch.Generator().manual_seed(9)
+    n, h, w = 2, 25, 34
+    x = rand(g, n, 256, h, w).to(DEV)
+    wt = rand(g, 5, 256, 3, 3, scale=0.02).to(DEV)
+    bias = torch.randn(5, generator=g).to(DEV)
+    ref = F.conv2d(x, wt, bias, padding=1)
+    ref[:, 3:5] = F.relu(ref[:, 3:5])
+    ref_rows = ref.permute(0, 2, 3, 1).reshape(n, h * w, 5)
+    buf = torch.full((n, 1000 + h * w, 8), -7.0, device=DEV)
+    ops.conv2d(ops.Act.from_nchw(x, 1), ops.pack_conv_weight(wt), cout=5, ksize=3, shift=bias, relu=(3, 5),
+               out_f32=buf, out_rows_per_image=1000 + h * w, out_row_offset=1000)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(buf[:, 1000:, :5], ref_rows, rtol=1e-4, atol=1e-4)
+    assert (buf[:, :1000] == -7.0).all() and (buf[:, 1000:, 5:] == -7.0).all(), "nothing else may be written"
+
+
+def test_conv_fp32_rows_transposed_a2j_layout(ops):
+    """A2J output convs: rows ordered w-major (permute(0,3,2,1), a2j/a2j.py:85-89)."""
+    g = torch.Generator().manual_seed(10)
+    n, h, w, cout = 3, 11, 11, 336
+    x = rand(g, n, 256, h, w).to(DEV)
+    wt = rand(g, cout, 256, 3, 3, scale=0.02).to(DEV)
+    bias = torch.randn(cout, generator=g).to(DEV)
+    ref = F.conv2d(x, wt, bias, padding=1).permute(0, 3, 2, 1).reshape(n, w * h, cout)
+    buf = torch.zeros((n, w * h, cout), device=DEV)
+    ops.conv2d(ops.Act.from_nchw(x, 1), ops.pack_conv_weight(wt), cout=cout, ksize=3, shift=bias, out_f32=buf,
+               out_transpose_hw=True)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(buf, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_conv_groupnorm_tower_layer(ops):
+    """conv3x3 + bias -> GroupNorm(32) -> ReLU (fcos_utils/fcos.py:232-240): stats from the conv epilogue."""
+    g = torch.Generator().manual_seed(11)
+    n, h, w, c = 3, 25, 34, 256
+    x = rand(g, n, c, h, w).to(DEV)
+    wt = rand(g, c, c, 3, 3, scale=0.02).to(DEV)
+    bias = (0.05 * torch.randn(c, generator=g)).to(DEV)
+    gamma = (0.7 + 0.6 * torch.rand(c, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(c, generator=g)).to(DEV)
+    raw = q(F.conv2d(x, wt, bias, padding=1))
+    ref = F.relu(F.group_norm(raw, 32, gamma, beta, eps=1e-5))
+    out = ops.Act(n, h, w, c, 1, DEV)
+    stats = torch.zeros(n, 32, 2, dtype=torch.float64, device=DEV)
+    ops.conv2d(ops.Act.from_nchw(x, 1), ops.pack_conv_weight(wt), cout=c, ksize=3, shift=bias, out=out,
+               gn_stats=stats, gn_groups=32)
+    torch.cuda.synchronize()
+    raw_got = out.to_nchw()
+    close_bf16(raw_got, raw, "raw conv")
+    want = torch.stack((raw_got.double().reshape(n, 32, -1).sum(-1), (raw_got.double() ** 2).reshape(n, 32, -1).sum(-1)), -1)
+    torch.testing.assert_close(stats, want, rtol=1e-5, atol=1e-3)
+    ops.groupnorm_relu(out, stats, 32, gamma, beta, 1e-5)
+    torch.cuda.synchronize()
+    close_bf16(out.to_nchw(), F.relu(F.group_norm(raw_got, 32, gamma, beta, eps=1e-5)), "gn apply")
+    close_bf16(out.to_nchw(), ref, "gn vs reference chain")
+    assert torch.isclose(out.t.float().abs().sum(), out.interior().float().abs().sum()), "halo must stay zero"
+
+
+def test_preprocess_matches_transform(ops):
+    g = torch.Generator().manual_seed(12)
+    imgs = [torch.rand(3, 120, 160, generator=g), torch.rand(3, 97, 131, generator=g)]
+    canvas, sizes = fcos_oracle.transform(imgs, 256, 448)
+    got = ops.preprocess([i.cuda() for i in imgs], sizes, tuple(canvas.shape[-2:]), fcos_oracle.IMAGE_MEAN,
+                         fcos_oracle.IMAGE_STD)
+    torch.cuda.synchronize()
+    got = got.float().cpu()
+    assert (got[..., 3] == 0).all()
+    ref = canvas.permute(0, 2, 3, 1)
+    err = (got[..., :3] - ref).abs()
+    assert (err <= ref.abs() * 2 ** -8 + 1e-5).all(), err.max()
+    for i, (oh, ow) in enumerate(sizes):
+        assert got[i, oh:].abs().sum() == 0 and got[i, :, ow:].abs().sum() == 0, "padding must be zero"
+
+
+def test_stem_im2col_gemm_and_maxpool(ops):
+    """backbone.body.conv1 + FrozenBN + ReLU + maxpool as im2col -> tcgen05 GEMM -> pool."""
+    g = torch.Generator().manual_seed(13)
+    n, h, w = 2, 64, 96
+    canvas = torch.zeros(n, h, w, 4)
+    canvas[..., :3] = rand(g, n, h, w, 3)
+    wt = rand(g, 64, 3, 7, 7, scale=0.08)
+    scale = 0.5 + torch.rand(64, generator=g)
+    shift = 0.2 * torch.randn(64, generator=g)
+    x_nchw = canvas[..., :3].permute(0, 3, 1, 2).contiguous()
+    conv = q(F.relu(F.conv2d(x_nchw, wt, stride=2, padding=3) * scale[None, :, None, None] + shift[None, :, None, None]))
+    ref = F.max_pool2d(conv, 3, 2, 1)
+    a, oh, ow = ops.im2col_7x7s2(canvas.to(torch.bfloat16).cuda(), 192)
+    stem = ops.Act(n, oh, ow, 64, 0, DEV)
+    ops.conv2d(ops.Act(n, oh, ow, 192, 0, DEV, t=a.view(n, oh, ow, 192)), ops.pack_stem_weight(wt.cuda(), 192),
+               cout=64, ksize=1, scale=scale.cuda(), shift=shift.cuda(), relu=True, out=stem)
+    pooled = ops.Act(n, (oh + 1) // 2, (ow + 1) // 2, 64, 1, DEV)
+    ops.maxpool3x3s2(stem.t, pooled)
+    torch.cuda.synchronize()
+    close_bf16(stem.to_nchw().cpu(), conv, "stem conv")
+    close_bf16(pooled.to_nchw().cpu(), ref, "maxpool")
+
+
+def test_stem_fp32_depth_one_channel(ops):
+    """A2J stem: one depth channel expanded to three == weights summed over Cin (a2j/a2j.py:197-199)."""
+    g = torch.Generator().manual_seed(14)
+    n = 3
+    depth = torch.rand(n, 176, 176, generator=g) * 1.5
+    wt = torch.randn(64, 3, 7, 7, generator=g) * 0.05
+    wsum = q(wt.sum(1, keepdim=True))
+    ref = F.conv2d(q(depth)[:, None], wsum, stride=2, padding=3)
+    a, oh, ow = ops.im2col_7x7s2(depth.cuda(), 64)
+    out = ops.Act(n, oh, ow, 64, 0, DEV)
+    ops.conv2d(ops.Act(n, oh, ow, 64, 0, DEV, t=a.view(n, oh, ow, 64)), ops.pack_stem_weight(wsum.cuda(), 64),
+               cout=64, ksize=1, out=out)
+    torch.cuda.synchronize()
+    close_bf16(out.to_nchw().cpu(), ref, "a2j stem")
