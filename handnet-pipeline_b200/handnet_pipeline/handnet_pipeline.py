@@ -1,0 +1,95 @@
+"""HandNet: detect -> pick hand -> pad box -> depth crop -> A2J pose, on B200 kernels.
+
+Drop-in for the reference's ``handnet_pipeline.handnet_pipeline`` (handnet_pipeline.py:14-116): same
+``HandNet(args, reload_detector, num_classes, reload_a2j, RGBD)`` constructor, ``.detector`` / ``.a2j``
+attributes, and ``forward(images, depth_images, is_3D=False, is_detect=False)`` returning
+``(final_results [B,21,3] float32 CPU, depth_batch [n,C,176,176] float32 device, crops [n,4] int64 device)``.
+
+The whole frame batch stays on the device: detector kernels, then ONE kernel for hand selection + box padding
++ crop + nearest resize (``hn_select_crop_resize``), then the pose net for all frames at once; the only
+host synchronisation is the final read-back of the joints / hit mask, where the reference has three
+(``.cpu()`` per stage) plus several per frame inside its Python loop.
+
+Differences, by design: a batch with hits and misses returns the hits (the reference raises in
+``torch.stack`` over a list containing ``None``, handnet_pipeline.py:110-111); an empty crop (box entirely
+outside the image) yields a zero crop instead of the reference's bare ``except: print("hi")``.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+from torch import nn
+
+from a2j.a2j import A2JModel, A2JModelLightning
+from fcos_utils.fcos import FCOS
+from hn_b200 import ops
+
+CROP_SIZE = 176     # handnet_pipeline.py:101
+
+
+def load_pretrained_fcos(args, reload_detector=False, num_classes=2):
+    print("Loading pretrained detector")
+    detector = FCOS(num_classes=num_classes, ext=False, nms_thresh=0.5)
+    if reload_detector:
+        checkpoint = torch.load(args.pretrained_fcos, map_location="cpu", weights_only=False)
+        detector.load_state_dict(checkpoint["model"], strict=False)
+    for p in detector.parameters():
+        p.requires_grad = False
+    return detector
+
+
+def load_pretrained_a2j(args, reload_a2j=False, RGBD=False):
+    print("Loading pretrained a2j")
+    if RGBD or "ckpt" in str(getattr(args, "pretrained_a2j", "")):
+        return A2JModelLightning.load_from_checkpoint(args.pretrained_a2j).eval()
+    a2j = A2JModel(21, crop_height=CROP_SIZE, crop_width=CROP_SIZE, is_RGBD=False)
+    if reload_a2j:
+        checkpoint = torch.load(args.pretrained_a2j, map_location="cpu", weights_only=False)
+        a2j.load_state_dict(checkpoint["model"], strict=False)
+    for p in a2j.parameters():
+        p.requires_grad = False
+    return a2j
+
+
+class HandNet(nn.Module):
+    """End-to-end HandNet."""
+
+    def __init__(self, args, reload_detector: bool = False, num_classes: int = 2, reload_a2j: bool = False,
+                 RGBD: bool = False):
+        super().__init__()
+        self.detector = load_pretrained_fcos(args, reload_detector, num_classes)
+        self.detector.eval()
+        self.a2j = load_pretrained_a2j(args, reload_a2j, RGBD)
+        self.RGBD = RGBD
+        self.num_classes = num_classes
+
+    def _pose_net(self) -> A2JModel:
+        return self.a2j.a2j if isinstance(self.a2j, A2JModelLightning) else self.a2j
+
+    def forward_device(self, images: List[torch.Tensor], depth_images: torch.Tensor):
+        """Everything on the device, no host sync.  Returns a dict with
+        joints [B,21,3], has_hand [B] int32, crops [B,4] int64, depth_batch [B,C,176,176], and the dense
+        detector output under 'det'."""
+        det = self.detector.forward_device(images)
+        depth = depth_images.float().contiguous()
+        crops, has_hand, depth_batch = ops.select_crop_resize(det["boxes"], det["labels"], det["keep_count"],
+                                                              self.num_classes - 1, depth, CROP_SIZE)
+        if self.RGBD:
+            depth_batch = depth_batch[:, [2, 1, 0, 3]].contiguous()        # handnet_pipeline.py:102
+        joints = self._pose_net().forward_device(depth_batch)
+        return {"joints": joints, "has_hand": has_hand, "crops": crops, "depth_batch": depth_batch, "det": det}
+
+    def forward(self, images, depth_images=None, is_3D: bool = False, is_detect: bool = False):
+        if is_detect or is_3D:
+            return None                                  # the reference falls through and returns None
+        out = self.forward_device(images, depth_images)
+        bsz = len(images)
+        # single read-back: hit mask + joints
+        hit = out["has_hand"].bool()
+        hit_cpu = hit.cpu()
+        final_results = torch.zeros((bsz, 21, 3))
+        if not bool(hit_cpu.any()):
+            return final_results, torch.zeros_like(depth_images), torch.zeros((bsz, 4))
+        final_results[hit_cpu] = out["joints"][hit].cpu()
+        return final_results, out["depth_batch"][hit], out["crops"][hit]

@@ -1,0 +1,450 @@
+"""Layer schedules of the detector and the pose net over the C-ABI kernels (hn_b200.ops).
+
+The nn.Modules in fcos_utils/ and a2j/ own the parameters (ordinary nn.Parameters / buffers with the
+reference's state-dict keys).  The executors here derive a packed bf16 copy of the weights (rebuilt when a
+parameter changes) and a set of statically shaped activation buffers per (batch, canvas) and then enqueue
+the kernels layer by layer on the current CUDA stream.  No torch arithmetic runs on the hot path.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .ops import Act, PhaseAct
+
+BN_EPS = 1e-5      # FrozenBatchNorm2d / nn.BatchNorm2d default eps
+GN_EPS = 1e-5
+STEM_K_RGB = 192   # 7*7*3 = 147 -> next multiple of 64
+STEM_K_DEPTH = 64  # 7*7*1 = 49
+
+
+def _sig(tensors: Sequence[torch.Tensor]):
+    return tuple((t.data_ptr(), t._version, str(t.device), tuple(t.shape)) for t in tensors)
+
+
+def bn_affine(weight, bias, mean, var, eps=BN_EPS, conv_bias=None):
+    """Eval-mode BatchNorm as y = x*scale + shift (torchvision/ops/misc.py:54-63), conv bias folded in."""
+    scale = weight.float() * (var.float() + eps).rsqrt()
+    shift = bias.float() - mean.float() * scale
+    if conv_bias is not None:
+        shift = shift + scale * conv_bias.float()
+    return scale.contiguous(), shift.contiguous()
+
+
+class ConvLayer:
+    """Packed weights + epilogue vectors of one convolution."""
+
+    __slots__ = ("w", "cout", "k", "stride", "dil", "scale", "shift")
+
+    def __init__(self, weight, *, stride=1, dil=1, scale=None, shift=None):
+        self.cout, _, self.k, _ = weight.shape
+        self.w = ops.pack_conv_weight(weight)
+        self.stride, self.dil = stride, dil
+        self.scale = None if scale is None else scale.detach().float().contiguous()
+        self.shift = None if shift is None else shift.detach().float().contiguous()
+
+    def run(self, x, **kw):
+        return ops.conv2d(x, self.w, cout=self.cout, ksize=self.k, stride=self.stride, dilation=self.dil,
+                          scale=self.scale, shift=self.shift, **kw)
+
+
+# =================================================================================================
+# FCOS detector
+# =================================================================================================
+def resized_size(h: int, w: int, min_size: int, max_size: int) -> Tuple[int, int]:
+    """torchvision transform.py:25-72 (eager branch): scale in python doubles, floor(in * scale)."""
+    scale = min(min_size / min(h, w), max_size / max(h, w))
+    return int(math.floor(float(h) * scale)), int(math.floor(float(w) * scale))
+
+
+class FCOSWeights:
+    def __init__(self, model):
+        sd = {k: v for k, v in model.state_dict().items()}
+        g = lambda k: sd[k]
+        bn = lambda p: bn_affine(g(p + ".weight"), g(p + ".bias"), g(p + ".running_mean"), g(p + ".running_var"))
+        b = "backbone.body."
+        s, sh = bn(b + "bn1")
+        self.stem_w = ops.pack_stem_weight(g(b + "conv1.weight"), STEM_K_RGB)
+        self.stem_scale, self.stem_shift = s, sh
+        self.blocks: List[List[Dict[str, ConvLayer]]] = []
+        for li, nblocks in enumerate((3, 4, 6, 3), start=1):
+            layer = []
+            for bi in range(nblocks):
+                p = f"{b}layer{li}.{bi}."
+                stride = 2 if (li > 1 and bi == 0) else 1
+                blk = {}
+                s1, b1 = bn(p + "bn1")
+                blk["conv1"] = ConvLayer(g(p + "conv1.weight"), stride=stride, scale=s1, shift=b1)
+                s2, b2 = bn(p + "bn2")
+                blk["conv2"] = ConvLayer(g(p + "conv2.weight"), scale=s2, shift=b2)
+                if (p + "downsample.0.weight") in sd:
+                    sd_, bd_ = bn(p + "downsample.1")
+                    blk["down"] = ConvLayer(g(p + "downsample.0.weight"), stride=stride, scale=sd_, shift=bd_)
+                layer.append(blk)
+            self.blocks.append(layer)
+        f = "backbone.fpn."
+        self.inner = [ConvLayer(g(f"{f}inner_blocks.{i}.0.weight"), shift=g(f"{f}inner_blocks.{i}.0.bias")) for i in range(3)]
+        self.outer = [ConvLayer(g(f"{f}layer_blocks.{i}.0.weight"), shift=g(f"{f}layer_blocks.{i}.0.bias")) for i in range(3)]
+        self.towers = {}
+        for name, hp in (("cls", "head.classification_head."), ("reg", "head.regression_head.")):
+            layers = []
+            for i in range(4):
+                conv = ConvLayer(g(f"{hp}conv.{3 * i}.weight"), shift=g(f"{hp}conv.{3 * i}.bias"))
+                layers.append((conv, g(f"{hp}conv.{3 * i + 1}.weight").float().contiguous(),
+                               g(f"{hp}conv.{3 * i + 1}.bias").float().contiguous()))
+            self.towers[name] = layers
+        # fused output convs: [cls | hand_lr | contact | dydx(ReLU)] and [bbox_reg(ReLU) | ctrness]
+        cp, rp = "head.classification_head.", "head.regression_head."
+        names = [cp + "cls_logits", cp + "hand_lr_layer"]
+        if model.ext:
+            names += [cp + "hand_contact_state_layer", cp + "hand_dydx_layer"]
+        self.cls_out = ConvLayer(torch.cat([g(n + ".weight") for n in names]), shift=torch.cat([g(n + ".bias") for n in names]))
+        nc = g(cp + "cls_logits.weight").shape[0]
+        self.num_classes = nc
+        self.cls_cols = {"cls": (0, nc), "lr": (nc, nc + 2)}
+        self.cls_relu = False
+        if model.ext:
+            self.cls_cols.update({"contact": (nc + 2, nc + 7), "dxdy": (nc + 7, nc + 10)})
+            self.cls_relu = (nc + 7, nc + 10)                       # fcos_utils/fcos.py:301
+        self.cls_ld = 8 if self.cls_out.cout <= 8 else 16
+        self.reg_out = ConvLayer(torch.cat([g(rp + "bbox_reg.weight"), g(rp + "bbox_ctrness.weight")]),
+                                 shift=torch.cat([g(rp + "bbox_reg.bias"), g(rp + "bbox_ctrness.bias")]))
+        self.reg_relu = (0, 4)                                      # fcos_utils/fcos.py:379
+        self.reg_ld = 8
+
+
+class FCOSPlan:
+    """Statically shaped buffers for one (batch, canvas) configuration."""
+
+    def __init__(self, wts: FCOSWeights, batch: int, canvas_hw: Tuple[int, int], device, anchor_sizes):
+        hc, wc = canvas_hw
+        assert hc % 32 == 0 and wc % 32 == 0
+        B = batch
+        self.batch, self.canvas_hw = B, canvas_hw
+        self.canvas = torch.zeros((B, hc, wc, 4), dtype=torch.bfloat16, device=device)
+        h1, w1 = hc // 2, wc // 2
+        self.stem_a = torch.empty((B * h1 * w1, STEM_K_RGB), dtype=torch.bfloat16, device=device)
+        self.stem = Act(B, h1, w1, 64, 0, device)
+        sizes = [(hc // 4, wc // 4, 64), (hc // 8, wc // 8, 128), (hc // 16, wc // 16, 256), (hc // 32, wc // 32, 512)]
+        self.stage = []
+        for (h, w, c) in sizes:
+            self.stage.append([Act(B, h, w, c, 1, device) for _ in range(3)])
+        # phase-split copies of the outputs of layer1..3 feed the stride-2 convs of layer2..4
+        self.phase = [PhaseAct(B, h, w, c, 1, device) for (h, w, c) in sizes[:3]]
+        self.lvl_hw = [(h, w) for (h, w, _) in sizes[1:]]
+        self.inner = [Act(B, h, w, 256, 1, device) for (h, w) in self.lvl_hw]
+        self.p = [Act(B, h, w, 256, 1, device) for (h, w) in self.lvl_hw]
+        self.tower = {t: [[Act(B, h, w, 256, 1, device) for _ in range(2)] for (h, w) in self.lvl_hw] for t in ("cls", "reg")}
+        self.levels = ops.Levels(self.lvl_hw, canvas_hw, anchor_sizes)
+        L = self.levels.locs
+        self.locs = L
+        self.cls_buf = torch.zeros((B, L, wts.cls_ld), dtype=torch.float32, device=device)
+        self.reg_buf = torch.zeros((B, L, wts.reg_ld), dtype=torch.float32, device=device)
+        self.gn_stats = torch.zeros((2, 4, 3, B, 32, 2), dtype=torch.float64, device=device)
+        self.sel_ws = torch.empty(int(ops._lib.load().hn_fcos_select_workspace_bytes(B, L)), dtype=torch.uint8, device=device)
+        self.nms_ws = ops.nms_workspace(B, L, device)
+
+
+class FCOSExecutor:
+    """Eval-mode FCOS.forward (fcos_utils/fcos.py:675-767) on the GPU."""
+
+    def __init__(self, model):
+        self.model = model
+        self._wsig = None
+        self.wts: Optional[FCOSWeights] = None
+        self.plans: Dict[Tuple, FCOSPlan] = {}
+
+    def weights(self) -> FCOSWeights:
+        sig = _sig(list(self.model.state_dict().values()))
+        if sig != self._wsig:
+            self.wts = FCOSWeights(self.model)
+            self._wsig = sig
+            self.plans.clear()
+        return self.wts
+
+    def plan(self, batch, canvas_hw, device) -> FCOSPlan:
+        key = (batch, canvas_hw, str(device))
+        if key not in self.plans:
+            self.plans[key] = FCOSPlan(self.wts, batch, canvas_hw, device, self.model.anchor_sizes)
+        return self.plans[key]
+
+    # ------------------------------------------------------------------------------------------
+    def backbone_heads(self, pl: FCOSPlan):
+        """canvas -> fused fp32 head buffers."""
+        w = self.wts
+        B = pl.batch
+        hc, wc = pl.canvas_hw
+        h1, w1 = hc // 2, wc // 2
+        ops.im2col_7x7s2(pl.canvas, STEM_K_RGB, out=pl.stem_a)
+        a = Act(B, h1, w1, STEM_K_RGB, 0, pl.canvas.device, t=pl.stem_a.view(B, h1, w1, STEM_K_RGB))
+        ops.conv2d(a, w.stem_w, cout=64, ksize=1, scale=w.stem_scale, shift=w.stem_shift, relu=True, out=pl.stem)
+        x = ops.maxpool3x3s2(pl.stem.t, pl.stage[0][0])
+        feats = []
+        for li in range(4):
+            bufs = pl.stage[li]
+            blocks = w.blocks[li]
+            for bi, blk in enumerate(blocks):
+                free = [b for b in bufs if b is not x]
+                last = bi == len(blocks) - 1
+                if "down" in blk:
+                    src = pl.phase[li - 1]
+                    y = blk["conv1"].run(src, relu=True, out=free[0])
+                    idn = blk["down"].run(src, out=free[1])
+                    # the identity buffer is read and overwritten by the same threads of the epilogue
+                    x = blk["conv2"].run(y, relu=True, res=idn, res_mode=1, out=idn,
+                                         out_phase=pl.phase[li] if (last and li < 3) else None)
+                else:
+                    y = blk["conv1"].run(x, relu=True, out=free[0])
+                    x = blk["conv2"].run(y, relu=True, res=x, res_mode=1, out=free[1],
+                                         out_phase=pl.phase[li] if (last and li < 3) else None)
+            if li >= 1:
+                feats.append(x)
+        # FPN top-down (torchvision/ops/feature_pyramid_network.py:172-204)
+        for i in (2, 1, 0):
+            if i == 2:
+                w.inner[i].run(feats[i], out=pl.inner[i])
+            else:
+                w.inner[i].run(feats[i], res=pl.inner[i + 1], res_mode=2, out=pl.inner[i])
+        for i in range(3):
+            w.outer[i].run(pl.inner[i], out=pl.p[i])
+        # heads (fcos_utils/fcos.py:267-329, 373-395)
+        pl.gn_stats.zero_()
+        for ti, t in enumerate(("cls", "reg")):
+            for lvl in range(3):
+                x = pl.p[lvl]
+                for i, (conv, gamma, beta) in enumerate(w.towers[t]):
+                    o = pl.tower[t][lvl][i & 1]
+                    st = pl.gn_stats[ti, i, lvl]
+                    conv.run(x, out=o, gn_stats=st, gn_groups=32)
+                    ops.groupnorm_relu(o, st, 32, gamma, beta, GN_EPS)
+                    x = o
+                if t == "cls":
+                    w.cls_out.run(x, relu=w.cls_relu, out_f32=pl.cls_buf, out_rows_per_image=pl.locs,
+                                  out_row_offset=pl.levels.starts[lvl])
+                else:
+                    w.reg_out.run(x, relu=w.reg_relu, out_f32=pl.reg_buf, out_rows_per_image=pl.locs,
+                                  out_row_offset=pl.levels.starts[lvl])
+        return pl.cls_buf, pl.reg_buf
+
+    def head_views(self, pl: FCOSPlan):
+        c = self.wts.cls_cols
+        v = {"cls_logits": pl.cls_buf[..., c["cls"][0]:c["cls"][1]], "hand_lr": pl.cls_buf[..., c["lr"][0]:c["lr"][1]],
+             "bbox_regression": pl.reg_buf[..., 0:4], "bbox_ctrness": pl.reg_buf[..., 4:5]}
+        if "contact" in c:
+            v["hand_contact_state"] = pl.cls_buf[..., c["contact"][0]:c["contact"][1]]
+            v["hand_dxdy_relu"] = pl.cls_buf[..., c["dxdy"][0]:c["dxdy"][1]]
+        return v
+
+    def postprocess(self, pl: FCOSPlan, ratios_h, ratios_w):
+        """fcos_utils/fcos.py:572-669 on the fused head buffers -> dense per-image detections on the device."""
+        m = self.model
+        v = self.head_views(pl)
+        cand = ops.fcos_decode_select(v["cls_logits"], v["bbox_ctrness"], v["bbox_regression"], self.wts.num_classes,
+                                      pl.levels, m.score_cut, ws=pl.sel_ws)
+        keep, keep_count = ops.nms_batched(cand["box"], cand["score"], cand["label"], cand["count"], m.nms_iou,
+                                           m.nms_coord_trick_numel, ws=pl.nms_ws)
+        out = ops.fcos_gather(keep, keep_count, cand, v["hand_lr"], pl.levels, ratios_h, ratios_w,
+                              contact=v.get("hand_contact_state"), dxdy=v.get("hand_dxdy_relu"))
+        out["keep_count"] = keep_count
+        out["cand_count"] = cand["count"]
+        return out
+
+    def forward_device(self, images: Sequence[torch.Tensor]):
+        """Whole detector; returns dense device tensors (capacity = #locations) + keep_count, no host sync."""
+        m = self.model
+        self.weights()
+        dev = images[0].device
+        orig = [(int(im.shape[-2]), int(im.shape[-1])) for im in images]
+        sizes = [resized_size(h, w, m.min_size, m.max_size) for h, w in orig]
+        hc = int(math.ceil(max(s[0] for s in sizes) / 32.0) * 32)
+        wc = int(math.ceil(max(s[1] for s in sizes) / 32.0) * 32)
+        pl = self.plan(len(images), (hc, wc), dev)
+        ops.preprocess(images, sizes, (hc, wc), m.image_mean, m.image_std, canvas=pl.canvas)
+        self.backbone_heads(pl)
+        # resize_boxes ratios are float32 tensor divisions in the reference (fcos_utils/fcos.py:771-776)
+        f32 = torch.float32
+        rh = [float(torch.tensor(o[0], dtype=f32) / torch.tensor(s[0], dtype=f32)) for o, s in zip(orig, sizes)]
+        rw = [float(torch.tensor(o[1], dtype=f32) / torch.tensor(s[1], dtype=f32)) for o, s in zip(orig, sizes)]
+        out = self.postprocess(pl, rh, rw)
+        out["plan"] = pl
+        return out
+
+
+# =================================================================================================
+# A2J pose net
+# =================================================================================================
+class A2JWeights:
+    def __init__(self, model):
+        sd = model.state_dict()
+        g = lambda k: sd[k]
+
+        def bn(p, conv_bias=None):
+            return bn_affine(g(p + ".weight"), g(p + ".bias"), g(p + ".running_mean"), g(p + ".running_var"),
+                             conv_bias=conv_bias)
+        b = "Backbone.model."
+        w0 = g(b + "conv1.weight").float()
+        self.channel_in = model.Backbone.channel_in
+        if self.channel_in == 1:
+            # x.expand(n,3,h,w) of the depth channel == convolving with the weights summed over Cin (a2j/a2j.py:197-199)
+            w0 = w0.sum(1, keepdim=True)
+            self.stem_k = STEM_K_DEPTH
+        else:
+            raise NotImplementedError("RGBD (4-channel) A2J stem is not built yet (SURVEY.md 8f rank 4)")
+        self.stem_w = ops.pack_stem_weight(w0, self.stem_k)
+        self.stem_scale, self.stem_shift = bn(b + "bn1")
+        self.blocks = []
+        for li, nblocks in enumerate((3, 4, 6, 3), start=1):
+            layer = []
+            for bi in range(nblocks):
+                p = f"{b}layer{li}.{bi}."
+                stride = 2 if (li in (2, 3) and bi == 0) else 1       # stride on the 3x3 (a2j/resnet.py:68)
+                dil = 2 if (li == 4 and bi > 0) else 1                 # a2j/resnet.py:112,142,145
+                blk = {"stride": stride, "dil": dil}
+                s, sh = bn(p + "bn1")
+                blk["conv1"] = ConvLayer(g(p + "conv1.weight"), scale=s, shift=sh)
+                s, sh = bn(p + "bn2")
+                blk["conv2"] = ConvLayer(g(p + "conv2.weight"), stride=stride, dil=dil, scale=s, shift=sh)
+                s, sh = bn(p + "bn3")
+                blk["conv3"] = ConvLayer(g(p + "conv3.weight"), scale=s, shift=sh)
+                if (p + "downsample.0.weight") in sd:
+                    s, sh = bn(p + "downsample.1")
+                    blk["down"] = ConvLayer(g(p + "downsample.0.weight"), stride=stride, scale=s, shift=sh)
+                layer.append(blk)
+            self.blocks.append(layer)
+        self.towers = {}
+        for name in ("classificationModel", "regressionModel", "DepthRegressionModel"):
+            if not hasattr(model, name):
+                continue
+            layers = []
+            for i in range(1, 5):
+                s, sh = bn(f"{name}.bn{i}", conv_bias=g(f"{name}.conv{i}.bias"))
+                layers.append(ConvLayer(g(f"{name}.conv{i}.weight"), scale=s, shift=sh))
+            out = ConvLayer(g(f"{name}.output.weight"), shift=g(f"{name}.output.bias"))
+            self.towers[name] = (layers, out)
+        self.anchors = g("post_process.all_anchors").float().contiguous()
+
+
+class A2JPlan:
+    def __init__(self, wts: A2JWeights, n: int, hw: Tuple[int, int], device, num_joints: int):
+        h, w = hw
+        self.n = n
+        h1, w1 = (h + 1) // 2, (w + 1) // 2
+        self.stem_a = torch.empty((n * h1 * w1, wts.stem_k), dtype=torch.bfloat16, device=device)
+        self.stem = Act(n, h1, w1, 64, 0, device)
+        h2, w2 = (h1 + 1) // 2, (w1 + 1) // 2
+        self.pool = Act(n, h2, w2, 64, 1, device)
+        A = lambda hh, ww, c, halo=1: Act(n, hh, ww, c, halo, device)
+        self.bufs = {}
+        self.hw = [(h2, w2), ((h2 + 1) // 2, (w2 + 1) // 2)]
+        self.hw.append(((self.hw[1][0] + 1) // 2, (self.hw[1][1] + 1) // 2))
+        self.hw.append(self.hw[2])
+        self.A = A
+        self.device = device
+        hf, wf = self.hw[3]
+        self.feat_hw = (hf, wf)
+        na = hf * wf * 16
+        self.cls = torch.zeros((n, na, num_joints), dtype=torch.float32, device=device)
+        self.reg = torch.zeros((n, na, num_joints, 2), dtype=torch.float32, device=device)
+        self.dep = torch.zeros((n, na, num_joints), dtype=torch.float32, device=device)
+        self.agg_ws = torch.empty(int(ops._lib.load().hn_a2j_workspace_bytes(n, num_joints)), dtype=torch.uint8, device=device)
+        self.cache: Dict[str, object] = {}
+
+    def act(self, key, hh, ww, c, halo=1):
+        if key not in self.cache:
+            self.cache[key] = Act(self.n, hh, ww, c, halo, self.device)
+        return self.cache[key]
+
+    def phase(self, key, hh, ww, c):
+        if key not in self.cache:
+            self.cache[key] = PhaseAct(self.n, hh, ww, c, 1, self.device)
+        return self.cache[key]
+
+
+class A2JExecutor:
+    """A2JModel.forward with gt=None (a2j/a2j.py:243-250) on the GPU."""
+
+    def __init__(self, model):
+        self.model = model
+        self._wsig = None
+        self.wts: Optional[A2JWeights] = None
+        self.plans: Dict[Tuple, A2JPlan] = {}
+
+    def weights(self) -> A2JWeights:
+        sig = _sig(list(self.model.state_dict().values()))
+        if sig != self._wsig:
+            self.wts = A2JWeights(self.model)
+            self._wsig = sig
+            self.plans.clear()
+        return self.wts
+
+    def heads_device(self, x: torch.Tensor):
+        """x: fp32 [n, 1, H, W] on the device -> (cls, reg, dep) fp32 head tensors in the reference layout."""
+        w = self.weights()
+        n, _, h, wd = x.shape
+        key = (n, h, wd, str(x.device))
+        if key not in self.plans:
+            self.plans[key] = A2JPlan(w, n, (h, wd), x.device, self.model.num_joints)
+        pl = self.plans[key]
+        depth = x[:, 0].contiguous() if x.shape[1] != 1 else x.reshape(n, h, wd)
+        _, h1, w1 = ops.im2col_7x7s2(depth, w.stem_k, out=pl.stem_a)
+        a = Act(n, h1, w1, w.stem_k, 0, x.device, t=pl.stem_a.view(n, h1, w1, w.stem_k))
+        ops.conv2d(a, w.stem_w, cout=64, ksize=1, scale=w.stem_scale, shift=w.stem_shift, relu=True, out=pl.stem)
+        cur = ops.maxpool3x3s2(pl.stem.t, pl.pool)
+        c4 = None
+        for li in range(4):
+            planes = 64 << li
+            for bi, blk in enumerate(w.blocks[li]):
+                hin, win = cur.h, cur.w
+                stride, dil = blk["stride"], blk["dil"]
+                hout, wout = ((hin + 1) // 2, (win + 1) // 2) if stride == 2 else (hin, win)
+                tag = f"l{li}b{bi}"
+                if stride == 2:
+                    # conv1 (1x1) runs at the input resolution and writes only the phase-split copy needed by the
+                    # stride-2 3x3; the block input needs a phase-split copy too for the stride-2 downsample.
+                    t1 = pl.act(tag + "t1", hin, win, planes)
+                    t1p = pl.phase(tag + "t1p", hin, win, planes)
+                    blk["conv1"].run(cur, relu=True, out=t1, out_phase=t1p)
+                    t2 = pl.act(tag + "t2", hout, wout, planes)
+                    blk["conv2"].run(t1p, relu=True, out=t2)
+                    idn = pl.act(tag + "id", hout, wout, planes * 4)
+                    blk["down"].run(pl.cache[f"l{li - 1}out_phase"], out=idn)
+                else:
+                    halo = dil                                          # dilated 3x3 needs a halo of 2 on its input
+                    t1 = pl.act(tag + "t1", hin, win, planes, halo)
+                    blk["conv1"].run(cur, relu=True, out=t1)
+                    t2 = pl.act(tag + "t2", hout, wout, planes)
+                    blk["conv2"].run(t1, relu=True, out=t2)
+                    if "down" in blk:
+                        idn = pl.act(tag + "id", hout, wout, planes * 4)
+                        blk["down"].run(cur, out=idn)
+                    else:
+                        idn = cur
+                last = bi == len(w.blocks[li]) - 1
+                out = pl.act(tag + "out", hout, wout, planes * 4)
+                out_phase = None
+                if last and li in (0, 1):
+                    out_phase = pl.phase(f"l{li}out_phase", hout, wout, planes * 4)
+                blk["conv3"].run(t2, relu=True, res=idn, res_mode=1, out=out, out_phase=out_phase)
+                cur = out
+            if li == 2:
+                c4 = cur
+        c5 = cur
+        hf, wf = pl.feat_hw
+        for name, src, dst in (("classificationModel", c4, pl.cls), ("regressionModel", c5, pl.reg),
+                               ("DepthRegressionModel", c5, pl.dep)):
+            layers, outc = w.towers[name]
+            t = src
+            for i, conv in enumerate(layers):
+                o = pl.act(f"{name}{i}", hf, wf, 256)
+                conv.run(t, relu=True, out=o)
+                t = o
+            # permute(0,3,2,1) + view of the reference == w-major rows (a2j/a2j.py:85-89)
+            outc.run(t, out_f32=dst.view(n, hf * wf, -1), out_transpose_hw=True)
+        return pl.cls, pl.reg, pl.dep, pl
+
+    def forward_device(self, x: torch.Tensor) -> torch.Tensor:
+        cls, reg, dep, pl = self.heads_device(x)
+        return ops.a2j_aggregate(cls, reg, dep, self.wts.anchors, ws=pl.agg_ws)

@@ -1,0 +1,118 @@
+"""CPU-only checks of the reference-facing Python surface: module paths, constructor
+signatures, state-dict keys and shapes, old-checkpoint key conversion, loud failure without a GPU."""
+import inspect
+
+import numpy as np
+import pytest
+import torch
+
+from hn_b200 import synth
+
+
+def test_fcos_state_dict_keys_match_reference_tables():
+    from fcos_utils.fcos import FCOS
+    for ext, n in ((False, 232), (True, 236)):
+        m = FCOS(num_classes=3, ext=ext)
+        sd = m.state_dict()
+        ref = synth.fcos_state_dict(3, ext)
+        assert list(sd.keys()) == list(ref.keys())
+        assert len(sd) == n
+        for k in sd:
+            assert sd[k].shape == ref[k].shape, k
+        assert m.load_state_dict(ref, strict=True)
+
+
+def test_fcos_accepts_torchvision_0_11_fpn_keys():
+    from fcos_utils.fcos import FCOS
+    ref = synth.fcos_state_dict(3, False)
+    old = {k.replace("_blocks.0.0.", "_blocks.0.").replace("_blocks.1.0.", "_blocks.1.").replace("_blocks.2.0.", "_blocks.2."): v
+           for k, v in ref.items()}
+    assert "backbone.fpn.inner_blocks.1.weight" in old
+    m = FCOS(num_classes=3, ext=False)
+    res = m.load_state_dict(old, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(m.state_dict()["backbone.fpn.inner_blocks.1.0.weight"], ref["backbone.fpn.inner_blocks.1.0.weight"])
+
+
+def test_fcos_signature_and_constants():
+    from fcos_utils.fcos import FCOS, FCOSHead, psum, resize_boxes
+    params = list(inspect.signature(FCOS.__init__).parameters)
+    assert params[1:] == ["num_classes", "ext", "min_size", "max_size", "image_mean", "image_std", "anchor_generator",
+                          "head", "center_sampling_radius", "score_thresh", "nms_thresh", "detections_per_img",
+                          "topk_candidates"]
+    m = FCOS(num_classes=3, ext=False, nms_thresh=0.5)
+    assert (m.score_cut, m.nms_iou) == (0.7, 0.3) and m.nms_thresh == 0.5
+    assert abs(float(m.head.classification_head.cls_logits.bias[0]) + np.log(99)) < 1e-6
+    assert psum([3, 4]) == [0, 3, 7]
+    b = resize_boxes(torch.tensor([[0.0, 0.0, 1066.0, 800.0]]), [800, 1066], [480, 640])
+    assert torch.allclose(b, torch.tensor([[0.0, 0.0, 640.0, 480.0]]), atol=1e-3)
+    assert isinstance(m.head, FCOSHead)
+
+
+def test_a2j_state_dict_keys_match_reference_tables():
+    from a2j.a2j import A2JModel
+    m = A2JModel(21, 176, 176)
+    sd = m.state_dict()
+    ref = synth.a2j_state_dict()
+    assert len(sd) == 414
+    assert set(sd.keys()) == set(ref.keys())
+    for k in sd:
+        assert sd[k].shape == ref[k].shape, k
+    assert torch.equal(sd["post_process.all_anchors"], ref["post_process.all_anchors"])
+    assert m.load_state_dict(ref, strict=True)
+
+
+def test_anchor_helpers_match_oracle():
+    from a2j.anchor import generate_anchors, shift
+    from fcos_utils.anchor_utils import AnchorGenerator
+    from oracle import a2j_oracle, fcos_oracle
+    a = torch.from_numpy(shift([11, 11], 16, generate_anchors())).float()
+    assert torch.equal(a, a2j_oracle.all_anchors())
+
+    class IL:
+        tensors = torch.zeros(1, 3, 800, 1088)
+        image_sizes = [(800, 1066)]
+    grids = [(100, 136), (50, 68), (25, 34)]
+    gen = AnchorGenerator(((8,), (16,), (32,)), ((1.0,),) * 3)
+    got = gen(IL(), [torch.zeros(1, 1, h, w) for h, w in grids])[0]
+    assert torch.equal(got, fcos_oracle.anchors_for((800, 1088), grids))
+
+
+def test_box_coder_and_convert_joints_match_oracle():
+    from a2j.a2j import convert_joints
+    from fcos_utils.det_utils import BoxLinearCoder
+    from oracle import a2j_oracle, fcos_oracle
+    g = torch.Generator().manual_seed(0)
+    anchors = fcos_oracle.anchors_for((64, 96), [(8, 12)], sizes=(8,))
+    rel = torch.rand(96, 4, generator=g) * 3
+    assert torch.equal(BoxLinearCoder(True).decode_single(rel, anchors), fcos_oracle.decode_boxes(rel, anchors))
+    j = torch.rand(21, 3, generator=g).numpy() * 176
+    box = np.array([10.0, 20.0, 200.0, 180.0], dtype=np.float32)
+    par = np.array([600.0, 601.0, 320.0, 240.0], dtype=np.float32)
+    np.testing.assert_allclose(convert_joints(j, None, box, par, 176, 176), a2j_oracle.convert_joints(j, box, par), rtol=1e-6)
+    np.testing.assert_allclose(convert_joints(j, None, box, None, 176, 176), a2j_oracle.convert_joints(j, box), rtol=1e-6)
+
+
+def test_handnet_surface():
+    from handnet_pipeline.handnet_pipeline import HandNet, load_pretrained_a2j, load_pretrained_fcos  # noqa: F401
+
+    class Args:
+        pretrained_fcos = ""
+        pretrained_a2j = ""
+    net = HandNet(Args(), reload_detector=False, num_classes=3, reload_a2j=False, RGBD=False).eval()
+    assert net.num_classes == 3 and net.RGBD is False
+    assert not any(p.requires_grad for p in net.parameters())
+    assert list(inspect.signature(net.forward).parameters) == ["images", "depth_images", "is_3D", "is_detect"]
+    assert net([torch.zeros(3, 8, 8)], None, is_detect=True) is None
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):          # no silent CPU fallback
+            net([torch.zeros(3, 32, 32)], torch.zeros(1, 1, 32, 32))
+
+
+def test_resized_size_matches_oracle():
+    from hn_b200.runtime import resized_size
+    from oracle import fcos_oracle
+    for h, w in ((480, 640), (1080, 1920), (120, 160), (97, 131), (333, 1000)):
+        assert resized_size(h, w, 800, 1333) == fcos_oracle.resized_size(h, w, 800, 1333)
+    assert resized_size(480, 640, 800, 1333) == (800, 1066)
+    assert resized_size(1080, 1920, 800, 1333) == (749, 1333)
