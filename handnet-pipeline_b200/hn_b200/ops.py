@@ -14,6 +14,7 @@ from . import _lib
 from ._lib import ConvDesc, check, ptr, stream_ptr
 
 BF16 = torch.bfloat16
+PROFILE = None      # set to a list by runtime.conv_profile: (start event, end event, algorithmic FLOPs) per conv launch
 
 
 def _require_cuda(t: torch.Tensor, name: str):
@@ -161,7 +162,7 @@ def conv2d(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 1, d
            res: Optional[Act] = None, res_mode: int = 0, out: Optional[Act] = None,
            out_f32: Optional[torch.Tensor] = None, out_rows_per_image: int = 0, out_row_offset: int = 0,
            out_transpose_hw: bool = False, out_phase: Optional[PhaseAct] = None,
-           gn_stats: Optional[torch.Tensor] = None, gn_groups: int = 0, block_n: int = 0):
+           gn_stats: Optional[torch.Tensor] = None, gn_groups: int = 0, block_n: int = 0, algo_k: int = 0):
     """hn_conv2d_bf16.  x: Act (stride 1) or PhaseAct (stride 2).  relu: bool or (lo, hi) channel range."""
     d = ConvDesc()
     if isinstance(x, PhaseAct):
@@ -198,6 +199,13 @@ def conv2d(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 1, d
         assert gn_stats.dtype == torch.float64 and gn_stats.numel() == d.n * gn_groups * 2
         d.gn_stats, d.gn_groups = gn_stats.data_ptr(), gn_groups
     d.block_n = block_n
+    if PROFILE is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        check(_lib.load().hn_conv2d_bf16(C.byref(d), stream_ptr()), "hn_conv2d_bf16")
+        ev1.record()
+        PROFILE.append((ev0, ev1, 2.0 * d.n * d.h * d.w * cout * (algo_k or weight.shape[1])))
+        return out if out_f32 is None else out_f32
     check(_lib.load().hn_conv2d_bf16(C.byref(d), stream_ptr()), "hn_conv2d_bf16")
     return out if out_f32 is None else out_f32
 

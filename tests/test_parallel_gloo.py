@@ -1,0 +1,60 @@
+"""World-size-2 gloo test of the multi-GPU plumbing (frame sharding + record all-gather) on the CPU."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, total, q):
+    sys.path.insert(0, os.path.join(ROOT, "handnet-pipeline_b200"))
+    from hn_b200 import parallel, runtime
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    b, e = parallel.shard_range(total, world, rank)
+    per = (total + world - 1) // world
+    # every frame's record is a function of its global index, so the gathered order can be checked
+    idx = torch.arange(b, e, dtype=torch.float32)
+    joints = idx[:, None, None] + torch.arange(63, dtype=torch.float32).reshape(1, 21, 3) / 100
+    crops = torch.stack((idx, idx + 1, idx + 2, idx + 3), 1).to(torch.int64)
+    has = (idx.to(torch.int64) % 2).to(torch.int32)
+    rec = runtime.pack_records(joints, crops, has)
+    allrec = parallel.gather_records(rec, per)
+    if rank == 0:
+        rows = []
+        for r in range(world):
+            rb, re_ = parallel.shard_range(total, world, r)
+            rows.append(allrec[r * per: r * per + (re_ - rb)])
+        j, c, h = runtime.unpack_records(torch.cat(rows))
+        q.put((j[:, 0, 0].tolist(), c[:, 3].tolist(), h.tolist()))
+    dist.destroy_process_group()
+
+
+def test_shard_range_covers_everything():
+    sys.path.insert(0, os.path.join(ROOT, "handnet-pipeline_b200"))
+    from hn_b200 import parallel
+    for total in (1, 7, 8, 64, 255):
+        for world in (1, 2, 4, 8):
+            spans = [parallel.shard_range(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
+
+
+def test_record_allgather_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    total, world, port = 7, 2, 29000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    j0, c3, h = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert j0 == [float(i) for i in range(total)]
+    assert c3 == [i + 3 for i in range(total)]
+    assert h == [bool(i % 2) for i in range(total)]
