@@ -95,8 +95,12 @@ def test_fcos_ext_heads(golden):
         _, emu = fcos_oracle.fcos_forward(sd, imgs, cfg["num_classes"], True, cfg["min_size"], cfg["max_size"],
                                           emulate_bf16=True, return_taps=True)
     assert set(dets[0]) == {"boxes", "scores", "labels", "dxdymags", "contacts", "sides"}
-    for k in ("hand_contact_state", "hand_dxdy"):
-        assert rel_to_max(ho[k], emu["head"][k]) < 6e-2, k
+    assert rel_to_max(ho["hand_contact_state"], emu["head"]["hand_contact_state"]) < 6e-2
+    # dxdy: channel 0 is a plain ReLU output; channels 1-2 are a unit direction scaled by 0.1, which flips
+    # between 0 and 0.1 when a pre-ReLU value sits at zero, so only the magnitude channel is compared tightly
+    assert rel_to_max(ho["hand_dxdy"][..., 0], emu["head"]["hand_dxdy"][..., 0]) < 6e-2
+    agree = ((ho["hand_dxdy"][..., 1:].cpu() - emu["head"]["hand_dxdy"][..., 1:]).abs() < 5e-3).float().mean()
+    assert agree > 0.97
     r = fx["dets"][0]
     d = dets[0]
     assert abs(len(d["boxes"]) - len(r["boxes"])) <= 0.05 * len(r["boxes"]) + 2
