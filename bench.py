@@ -233,12 +233,14 @@ def main():
         launches0 = ops.launch_count()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         barrier()
+        torch.cuda.nvtx.range_push("hn_timed")
         for s, e in evs:
             l2_flush.zero_()                 # flush L2 between timed iterations (outside the events)
             s.record()
             one_step()
             e.record()
         barrier()
+        torch.cuda.nvtx.range_pop()
         clocks = sampler.stop()
         launches = (ops.launch_count() - launches0) // args.steps if args.no_graph else step.launches_per_step
         dev_ms = sum(s.elapsed_time(e) for s, e in evs)
@@ -281,6 +283,8 @@ def main():
             peaks = load_peaks()
             conv_ms, n_conv = conv_profile(step, repeats=3)
             flops = conv_flops_per_step(step)
+            if os.environ.get("HN_CONV_TABLE"):
+                json.dump(step.last_conv_table, open(os.environ["HN_CONV_TABLE"], "w"))
             ach = flops / (conv_ms * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 shifted GEMM)", "achieved": ach,
                     "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],

@@ -204,7 +204,9 @@ def conv2d(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 1, d
         ev0.record()
         check(_lib.load().hn_conv2d_bf16(C.byref(d), stream_ptr()), "hn_conv2d_bf16")
         ev1.record()
-        PROFILE.append((ev0, ev1, 2.0 * d.n * d.h * d.w * cout * (algo_k or weight.shape[1])))
+        PROFILE.append((ev0, ev1, 2.0 * d.n * d.h * d.w * cout * (algo_k or weight.shape[1]),
+                        dict(n=d.n, h=d.h, w=d.w, cin=d.cin, cout=cout, k=ksize, stride=stride, dil=dilation,
+                             halo=d.halo_in, f32=out_f32 is not None, gn=gn_stats is not None)))
         return out if out_f32 is None else out_f32
     check(_lib.load().hn_conv2d_bf16(C.byref(d), stream_ptr()), "hn_conv2d_bf16")
     return out if out_f32 is None else out_f32

@@ -570,10 +570,12 @@ def conv_profile(step: GraphedHandNet, repeats: int = 3):
         step._eager()
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
-        ms = sum(s.elapsed_time(e) for s, e, _ in prof)
+        ms = sum(p[0].elapsed_time(p[1]) for p in prof)
         n = len(prof)
-        step.last_conv_flops = sum(f for _, _, f in prof)
-        best = ms if best is None else min(best, ms)
+        step.last_conv_flops = sum(p[2] for p in prof)
+        if best is None or ms < best:
+            best = ms
+            step.last_conv_table = [dict(p[3], ms=p[0].elapsed_time(p[1]), gflop=p[2] / 1e9) for p in prof]
     return best, n
 
 
