@@ -109,6 +109,28 @@ __device__ __forceinline__ void hn_tma_load_3d(void* dst, const CUtensorMap* m, 
       : "memory");
 }
 
+__device__ __forceinline__ void hn_tma_load_2d_mcast(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                     uint16_t cta_mask) {
+  // the box lands at the same CTA-relative smem offset in every CTA of cta_mask and signals the mbarrier at the
+  // same offset there
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(hn_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(hn_smem_u32(bar)), "r"(c0), "r"(c1),
+        "h"(cta_mask)
+      : "memory");
+}
+
+// ---- clusters -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hn_cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void hn_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---- tcgen05 ------------------------------------------------------------------------------
 __device__ __forceinline__ void hn_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void hn_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -138,6 +160,12 @@ __device__ __forceinline__ void hn_umma_bf16(uint32_t tmem_d, uint64_t desc_a, u
 __device__ __forceinline__ void hn_umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(hn_smem_u32(bar))
                : "memory");
+}
+__device__ __forceinline__ void hn_umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(hn_smem_u32(bar)), "h"(cta_mask)
+      : "memory");
 }
 __device__ __forceinline__ void hn_tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

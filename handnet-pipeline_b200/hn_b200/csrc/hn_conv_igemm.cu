@@ -59,11 +59,15 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+// CS = thread-block cluster size along M: the CS CTAs of a cluster work on CS consecutive M tiles of the same N
+// tile in lock step; each loads 1/CS of the B (weight) tile and multicasts it to all of them, so the weights
+// cross the L2 -> SM fabric once per cluster instead of once per CTA.
+template <int BN, int CS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                   const ConvParams p) {
   using C = Cfg<BN>;
+  static_assert(CS == 1 || (BN / CS) % 8 == 0, "B slices must keep whole 8-row swizzle atoms");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -75,15 +79,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
   const int k_blocks = p.num_taps * p.cin_chunks;
+  // tile schedule: "super tiles" of CS consecutive M tiles x one N tile, N fastest, strided over the clusters
+  const int cta_rank = (CS > 1) ? (int)hn_cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CS;
+  const int num_clusters = gridDim.x / CS;
+  const int num_super = ((p.m_tiles + CS - 1) / CS) * p.n_tiles;
 
   if (threadIdx.x == 0) {
     hn_tma_prefetch_desc(&tm_a);
     hn_tma_prefetch_desc(&tm_b);
     for (int s = 0; s < C::STAGES; ++s) {
       hn_mbar_init(&full_bar[s], 1);
-      hn_mbar_init(&empty_bar[s], 1);
+      hn_mbar_init(&empty_bar[s], CS);   // every CTA of the cluster releases the slot (its peers write into it)
     }
     for (int b = 0; b < 2; ++b) {
       hn_mbar_init(&tmem_full[b], 1);
@@ -94,6 +102,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   if (warp == 1) hn_tmem_alloc<C::TMEM_COLS>(tmem_slot);
   hn_tc_fence_before();
   __syncthreads();
+  if constexpr (CS > 1) hn_cluster_sync();   // peers' barriers must exist before anyone signals them
   hn_tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -102,9 +111,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.n_tiles) * BLOCK_M;
-        const int n0 = (tile % p.n_tiles) * BN;
+      for (int st = cluster_id; st < num_super; st += num_clusters) {
+        const int m0 = ((st / p.n_tiles) * CS + cta_rank) * BLOCK_M;
+        const int n0 = (st % p.n_tiles) * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
           const int tap = kb / p.cin_chunks;
           const int cc = kb - tap * p.cin_chunks;
@@ -112,7 +121,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           hn_mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           hn_tma_load_3d(sa, &tm_a, &full_bar[stage], cc * BLOCK_K, m0 + p.tap_shift[tap], p.tap_phase[tap]);
-          hn_tma_load_2d(sa + A_STAGE_BYTES, &tm_b, &full_bar[stage], kb * BLOCK_K, n0);
+          if constexpr (CS == 1) {
+            hn_tma_load_2d(sa + A_STAGE_BYTES, &tm_b, &full_bar[stage], kb * BLOCK_K, n0);
+          } else {
+            constexpr int SLICE = BN / CS;   // weight rows this CTA fetches for the whole cluster
+            hn_tma_load_2d_mcast(sa + A_STAGE_BYTES + cta_rank * SLICE * BLOCK_K * 2, &tm_b, &full_bar[stage],
+                                 kb * BLOCK_K, n0 + cta_rank * SLICE, (uint16_t)((1u << CS) - 1u));
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -124,7 +139,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int st = cluster_id; st < num_super; st += num_clusters, ++it) {
         const int buf = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         hn_mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
@@ -141,7 +156,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             // +32 bytes per K=16 step inside the 128-byte swizzle span: start-address field += 2
             hn_umma_bf16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0);
           }
-          hn_umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
+          // frees the smem slot (in every CTA of the cluster) once these MMAs have read it
+          if constexpr (CS == 1) hn_umma_commit(&empty_bar[stage]);
+          else hn_umma_commit_mcast(&empty_bar[stage], (uint16_t)((1u << CS) - 1u));
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
         hn_umma_commit(&tmem_full[buf]);       // accumulator complete -> epilogue
@@ -152,11 +169,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const int quarter = warp & 3;              // TMEM lanes this warp may touch: 32*quarter .. +31
     const int img_rows = p.hp * p.wp;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int st = cluster_id; st < num_super; st += num_clusters, ++it) {
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (tile / p.n_tiles) * BLOCK_M;
-      const int n0 = (tile % p.n_tiles) * BN;
+      const int m0 = ((st / p.n_tiles) * CS + cta_rank) * BLOCK_M;
+      const int n0 = (st % p.n_tiles) * BN;
       const int m = m0 + quarter * 32 + lane;
       // decode the padded pixel this accumulator row belongs to
       int img = 0, h = 0, w = 0;
@@ -346,6 +363,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 
   hn_tc_fence_before();
   __syncthreads();
+  if constexpr (CS > 1) hn_cluster_sync();   // no CTA may retire while a peer can still signal its barriers
   if (warp == 1) {
     hn_tc_fence_after();
     hn_tmem_dealloc<C::TMEM_COLS>(tmem_base);
@@ -390,20 +408,33 @@ int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, 
   return HN_OK;
 }
 
-template <int BN>
+template <int BN, int CS>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t st) {
   using C = Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    HN_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HN_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        C::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = p.m_tiles * p.n_tiles;
-  const int grid = tiles < hn_num_sms() ? tiles : hn_num_sms();
-  conv_igemm_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
+  const int super = hn_div_up(p.m_tiles, CS) * p.n_tiles;
+  const int max_clusters = hn_num_sms() / CS;
+  const int clusters = super < max_clusters ? super : max_clusters;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(clusters * CS);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (CS > 1) ? 1 : 0;
+  HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, CS>, ta, tb, p));
   hn_count_launch();
-  HN_LAUNCH_CHECK();
   return HN_OK;
 }
 
@@ -471,6 +502,9 @@ extern "C" int hn_conv2d_bf16(const hn_conv_desc* d, void* stream) {
   HN_REQUIRE((bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256) && d->cout_pad % bn == 0,
              "hn_conv2d_bf16: block_n=%d does not divide cout_pad=%d", bn, d->cout_pad);
   p.n_tiles = d->cout_pad / bn;
+  // cluster of 2 with multicast weights when there is at least one pair of M tiles per SM pair
+  int cs = d->cluster ? d->cluster : ((bn >= 64 && hn_div_up(p.m_tiles, 2) * p.n_tiles >= hn_num_sms() / 2) ? 2 : 1);
+  HN_REQUIRE(cs == 1 || (cs == 2 && bn >= 64), "hn_conv2d_bf16: cluster=%d unsupported with block_n=%d", cs, bn);
   p.cout = d->cout;
   p.scale = d->scale;
   p.shift = d->shift;
@@ -528,16 +562,23 @@ extern "C" int hn_conv2d_bf16(const hn_conv_desc* d, void* stream) {
     const cuuint64_t k_total = (cuuint64_t)p.num_taps * d->cin;
     const cuuint64_t dims[2] = {k_total, (cuuint64_t)d->cout_pad};
     const cuuint64_t strides[1] = {k_total * 2};
-    const cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)bn};
+    const cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)(bn / cs)};
     int rc = make_map(&tb, d->weight, 2, dims, strides, box);
     if (rc) return rc;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cs == 2) {
+    switch (bn) {
+      case 256: return launch<256, 2>(ta, tb, p, st);
+      case 128: return launch<128, 2>(ta, tb, p, st);
+      default: return launch<64, 2>(ta, tb, p, st);
+    }
+  }
   switch (bn) {
-    case 256: return launch<256>(ta, tb, p, st);
-    case 128: return launch<128>(ta, tb, p, st);
-    case 64: return launch<64>(ta, tb, p, st);
-    case 32: return launch<32>(ta, tb, p, st);
-    default: return launch<16>(ta, tb, p, st);
+    case 256: return launch<256, 1>(ta, tb, p, st);
+    case 128: return launch<128, 1>(ta, tb, p, st);
+    case 64: return launch<64, 1>(ta, tb, p, st);
+    case 32: return launch<32, 1>(ta, tb, p, st);
+    default: return launch<16, 1>(ta, tb, p, st);
   }
 }

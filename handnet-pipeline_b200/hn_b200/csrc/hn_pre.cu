@@ -60,42 +60,53 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p, uint
 }
 
 // ------------------------------------------------------------------------------------- im2col
-template <bool IN_F32>
+// Stem patches as GEMM rows.  K is laid out as 8 kernel rows x 8 pixels x C channels: row r (r < 7) of the 7x7
+// window, pixels x = 2*ox - 4 .. 2*ox + 3 (the first one is outside the 7-wide window and meets a zero weight),
+// so that every 16-byte output chunk is a contiguous, aligned piece of one input row.  r = 7 is zero padding.
+// bf16 canvas (4 channels/pixel): k = r*32 + px*4 + ch, K = 256; one thread = 2 pixels = 16 bytes.
 __global__ void __launch_bounds__(256)
-im2col_7x7s2_kernel(const void* __restrict__ in, int n, int h, int w, int c, int cs, int oh, int ow, int k_pad,
-                    uint4* __restrict__ out) {
-  const int groups = k_pad >> 3;
-  const long long total = (long long)n * oh * ow * groups;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= total) return;
-  const int g = (int)(gid % groups);
-  const long long row = gid / groups;
-  const int ox = (int)(row % ow);
-  const int oy = (int)((row / ow) % oh);
-  const int img = (int)(row / ((long long)ow * oh));
-  const int kmax = 49 * c;
+im2col_rgb_kernel(const uint2* __restrict__ in, int h, int w, int oh, int ow, uint4* __restrict__ out) {
+  // thread -> (output pixel, r, q): 32 threads per output pixel, consecutive threads write consecutive 16 B
+  const int lane32 = threadIdx.x & 31;
+  const int pix_in_block = threadIdx.x >> 5;
+  const int ox = blockIdx.x * 8 + pix_in_block;
+  const int oy = blockIdx.y;
+  const int img = blockIdx.z;
+  if (ox >= ow) return;
+  const int r = lane32 >> 2, q = lane32 & 3;
+  const int iy = 2 * oy - 3 + r;
+  const int ix0 = 2 * ox - 4 + 2 * q;
+  uint2 a = make_uint2(0u, 0u), b = make_uint2(0u, 0u);
+  if (r < 7 && iy >= 0 && iy < h) {
+    const uint2* row = in + ((size_t)img * h + iy) * w;
+    if (ix0 >= 0 && ix0 < w) a = __ldg(row + ix0);
+    if (ix0 + 1 >= 0 && ix0 + 1 < w) b = __ldg(row + ix0 + 1);
+  }
+  out[(((size_t)img * oh + oy) * ow + ox) * 32 + lane32] = make_uint4(a.x, a.y, b.x, b.y);
+}
+
+// fp32 single-channel depth: k = r*8 + px, K = 64; one thread = one kernel row = 8 pixels = 16 bytes of bf16.
+__global__ void __launch_bounds__(256)
+im2col_depth_kernel(const float* __restrict__ in, int h, int w, int oh, int ow, uint4* __restrict__ out) {
+  const int r = threadIdx.x & 7;
+  const int ox = blockIdx.x * 32 + (threadIdx.x >> 3);
+  const int oy = blockIdx.y;
+  const int img = blockIdx.z;
+  if (ox >= ow) return;
+  const int iy = 2 * oy - 3 + r;
   float v[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int k = g * 8 + j;
-    float x = 0.f;
-    if (k < kmax) {
-      const int tap = k / c, ch = k - tap * c;
-      const int r = tap / 7, s = tap - r * 7;
-      const int iy = 2 * oy - 3 + r, ix = 2 * ox - 3 + s;
-      if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
-        const size_t off = (((size_t)img * h + iy) * w + ix) * cs + ch;
-        if constexpr (IN_F32) {
-          x = __ldg(reinterpret_cast<const float*>(in) + off);
-        } else {
-          x = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(in)[off]);
-        }
-      }
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  if (r < 7 && iy >= 0 && iy < h) {
+    const float* row = in + ((size_t)img * h + iy) * w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ix = 2 * ox - 4 + j;
+      if (ix >= 0 && ix < w) v[j] = __ldg(row + ix);
     }
-    v[j] = x;
   }
-  out[gid] = make_uint4(hn_pack_bf16(v[0], v[1]), hn_pack_bf16(v[2], v[3]), hn_pack_bf16(v[4], v[5]),
-                        hn_pack_bf16(v[6], v[7]));
+  out[(((size_t)img * oh + oy) * ow + ox) * 8 + r] =
+      make_uint4(hn_pack_bf16(v[0], v[1]), hn_pack_bf16(v[2], v[3]), hn_pack_bf16(v[4], v[5]), hn_pack_bf16(v[6], v[7]));
 }
 
 // ------------------------------------------------------------------------------------ maxpool
@@ -134,38 +145,48 @@ maxpool3x3s2_kernel(const uint4* __restrict__ in, int n, int h, int w, int c8, i
 }
 
 // ---------------------------------------------------------------------------------- GroupNorm
+// grid (pixel blocks, image).  Each block first turns the fp64 (sum, sumsq) accumulators of its image into fp32
+// per-channel a = rstd*gamma, b = beta - mean*a in shared memory, then streams pixels: y = relu(x*a + b).
+constexpr int GN_MAX_C = 512;
 __global__ void __launch_bounds__(256)
-groupnorm_relu_kernel(uint4* __restrict__ x, int n, int h, int w, int c8, int halo, const double* __restrict__ stats,
+groupnorm_relu_kernel(uint4* __restrict__ x, int h, int w, int c, int halo, const double* __restrict__ stats,
                       int groups, int group_size, const float* __restrict__ gamma, const float* __restrict__ beta,
-                      float eps) {
-  const long long total = (long long)n * h * w * c8;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= total) return;
-  const int cg = (int)(gid % c8);
-  const long long pix = gid / c8;
-  const int xx = (int)(pix % w);
-  const int yy = (int)((pix / w) % h);
-  const int img = (int)(pix / ((long long)w * h));
-  const int c0 = cg * 8;
-  const int group = c0 / group_size;               // group_size is a multiple of 8
-  const double cnt = (double)h * (double)w * (double)group_size;
-  const double s = stats[((size_t)img * groups + group) * 2], q = stats[((size_t)img * groups + group) * 2 + 1];
-  const double mean_d = s / cnt;
-  double var_d = q / cnt - mean_d * mean_d;
-  if (var_d < 0.0) var_d = 0.0;
-  const float mean = (float)mean_d;
-  const float rstd = (float)(1.0 / sqrt(var_d + (double)eps));
+                      float eps, int pixels_per_block) {
+  __shared__ float sa[GN_MAX_C], sb[GN_MAX_C];
+  const int img = blockIdx.y;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    const int g = ch / group_size;
+    const double cnt = (double)h * (double)w * (double)group_size;
+    const double s = stats[((size_t)img * groups + g) * 2], q = stats[((size_t)img * groups + g) * 2 + 1];
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float a = rstd * __ldg(gamma + ch);
+    sa[ch] = a;
+    sb[ch] = __ldg(beta + ch) - (float)mean * a;
+  }
+  __syncthreads();
+  const int c8 = c >> 3;
   const int hp = h + 2 * halo, wp = w + 2 * halo;
-  uint4* ptr = x + (((size_t)img * hp + yy + halo) * wp + xx + halo) * c8 + cg;
-  uint4 v = *ptr;
-  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
-  const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
-  auto f = [&](float xv, float g, float b) { return fmaxf((xv - mean) * rstd * g + b, 0.f); };
-  v.x = hn_pack_bf16(f(hn_bf16_lo(v.x), g0.x, b0.x), f(hn_bf16_hi(v.x), g0.y, b0.y));
-  v.y = hn_pack_bf16(f(hn_bf16_lo(v.y), g0.z, b0.z), f(hn_bf16_hi(v.y), g0.w, b0.w));
-  v.z = hn_pack_bf16(f(hn_bf16_lo(v.z), g1.x, b1.x), f(hn_bf16_hi(v.z), g1.y, b1.y));
-  v.w = hn_pack_bf16(f(hn_bf16_lo(v.w), g1.z, b1.z), f(hn_bf16_hi(v.w), g1.w, b1.w));
-  *ptr = v;
+  const int total = h * w;
+  const int p0 = blockIdx.x * pixels_per_block;
+  const int p1 = min(total, p0 + pixels_per_block);
+  const int items = (p1 - p0) * c8;
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int pix = p0 + i / c8;
+    const int cg = i - (i / c8) * c8;
+    const int yy = pix / w, xx = pix - yy * w;
+    uint4* ptr = x + (((size_t)img * hp + yy + halo) * wp + xx + halo) * c8 + cg;
+    uint4 v = *ptr;
+    const float* a = sa + cg * 8;
+    const float* b = sb + cg * 8;
+    v.x = hn_pack_bf16(fmaxf(hn_bf16_lo(v.x) * a[0] + b[0], 0.f), fmaxf(hn_bf16_hi(v.x) * a[1] + b[1], 0.f));
+    v.y = hn_pack_bf16(fmaxf(hn_bf16_lo(v.y) * a[2] + b[2], 0.f), fmaxf(hn_bf16_hi(v.y) * a[3] + b[3], 0.f));
+    v.z = hn_pack_bf16(fmaxf(hn_bf16_lo(v.z) * a[4] + b[4], 0.f), fmaxf(hn_bf16_hi(v.z) * a[5] + b[5], 0.f));
+    v.w = hn_pack_bf16(fmaxf(hn_bf16_lo(v.w) * a[6] + b[6], 0.f), fmaxf(hn_bf16_hi(v.w) * a[7] + b[7], 0.f));
+    *ptr = v;
+  }
 }
 
 }  // namespace
@@ -211,18 +232,21 @@ extern "C" int hn_preprocess_resize_pad(const float* const* images_host, const i
 extern "C" int hn_im2col_7x7s2(const void* in, int in_is_f32, int n, int h, int w, int c, void* out_bf16, int k_pad,
                                void* stream) {
   HN_REQUIRE(in && out_bf16, "hn_im2col_7x7s2: null pointer");
-  HN_REQUIRE(n > 0 && h > 0 && w > 0 && c >= 1 && c <= 4, "hn_im2col_7x7s2: bad shape");
-  HN_REQUIRE(k_pad % 64 == 0 && k_pad >= 49 * c, "hn_im2col_7x7s2: k_pad=%d must be a multiple of 64 >= %d", k_pad, 49 * c);
+  HN_REQUIRE(n > 0 && h > 0 && w > 0, "hn_im2col_7x7s2: bad shape");
+  HN_REQUIRE((in_is_f32 && c == 1 && k_pad == 64) || (!in_is_f32 && c == 4 && k_pad == 256),
+             "hn_im2col_7x7s2: supported layouts are bf16 [n,h,w,4] -> K=256 and fp32 [n,h,w] -> K=64");
   const int oh = (h + 1) / 2, ow = (w + 1) / 2;   // floor((h + 6 - 7)/2) + 1
-  const int cs = in_is_f32 ? c : 4;               // bf16 canvases are stored with 4 channels per pixel
-  const long long total = (long long)n * oh * ow * (k_pad / 8);
-  const long long blocks = (total + 255) / 256;
-  HN_REQUIRE(blocks < (1ll << 31), "hn_im2col_7x7s2: too large");
+  HN_REQUIRE(n <= 65535 && oh <= 65535, "hn_im2col_7x7s2: too large");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (in_is_f32)
-    im2col_7x7s2_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(in, n, h, w, c, cs, oh, ow, k_pad, reinterpret_cast<uint4*>(out_bf16));
-  else
-    im2col_7x7s2_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(in, n, h, w, c, cs, oh, ow, k_pad, reinterpret_cast<uint4*>(out_bf16));
+  if (in_is_f32) {
+    dim3 grid(hn_div_up(ow, 32), oh, n);
+    im2col_depth_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(in), h, w, oh, ow,
+                                              reinterpret_cast<uint4*>(out_bf16));
+  } else {
+    dim3 grid(hn_div_up(ow, 8), oh, n);
+    im2col_rgb_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint2*>(in), h, w, oh, ow,
+                                            reinterpret_cast<uint4*>(out_bf16));
+  }
   hn_count_launch();
   HN_LAUNCH_CHECK();
   return HN_OK;
@@ -245,13 +269,15 @@ extern "C" int hn_maxpool3x3s2(const void* in, int n, int h, int w, int c, void*
 extern "C" int hn_groupnorm_relu(void* x, int n, int h, int w, int c, int halo, const double* stats, int groups,
                                  const float* gamma, const float* beta, float eps, void* stream) {
   HN_REQUIRE(x && stats && gamma && beta, "hn_groupnorm_relu: null pointer");
-  HN_REQUIRE(n > 0 && h > 0 && w > 0 && groups > 0 && c % groups == 0 && (c / groups) % 8 == 0,
-             "hn_groupnorm_relu: channels per group must be a multiple of 8 (c=%d groups=%d)", c, groups);
-  const long long total = (long long)n * h * w * (c / 8);
-  const long long blocks = (total + 255) / 256;
-  HN_REQUIRE(blocks < (1ll << 31), "hn_groupnorm_relu: too large");
-  groupnorm_relu_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<uint4*>(x), n, h, w, c / 8, halo, stats, groups, c / groups, gamma, beta, eps);
+  HN_REQUIRE(n > 0 && h > 0 && w > 0 && groups > 0 && c % groups == 0 && c % 8 == 0 && c <= GN_MAX_C && n <= 65535,
+             "hn_groupnorm_relu: unsupported shape (c=%d groups=%d)", c, groups);
+  // ~8 waves of 256-thread blocks over the batch; each block amortises its per-image coefficient set-up
+  const int total = h * w;
+  int ppb = hn_div_up(total * n, hn_num_sms() * 8 * 4);
+  if (ppb < 32) ppb = 32;
+  dim3 grid(hn_div_up(total, ppb), n);
+  groupnorm_relu_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<uint4*>(x), h, w, c, halo, stats, groups, c / groups, gamma, beta, eps, ppb);
   hn_count_launch();
   HN_LAUNCH_CHECK();
   return HN_OK;

@@ -92,11 +92,15 @@ def pack_conv_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None) -> t
 
 
 def pack_stem_weight(w: torch.Tensor, k_pad: int) -> torch.Tensor:
-    """7x7 stem OIHW -> bf16 [cout_pad][k_pad], k = (r*7 + s)*cin + ch (matches hn_im2col_7x7s2)."""
+    """7x7 stem OIHW (cin = 3 or 1) -> bf16 [cout_pad][k_pad] in the K order of hn_im2col_7x7s2:
+    k = (r*8 + px)*C + ch with C = 4 (RGB canvas) or 1 (depth); px = 0, r = 7 and ch = 3 carry zero weights."""
     cout, cin, kh, kw = w.shape
-    m = w.detach().float().permute(0, 2, 3, 1).reshape(cout, kh * kw * cin)
+    assert (kh, kw) == (7, 7) and (cin, k_pad) in ((3, 256), (1, 64))
+    c = 4 if cin == 3 else 1
+    m = torch.zeros((cout, 8, 8, c), dtype=torch.float32, device=w.device)
+    m[:, :7, 1:, :cin] = w.detach().float().permute(0, 2, 3, 1)
     out = torch.zeros((pad_cout(cout), k_pad), dtype=BF16, device=w.device)
-    out[:cout, : m.shape[1]] = m.to(BF16)
+    out[:cout] = m.reshape(cout, -1).to(BF16)
     return out.contiguous()
 
 
@@ -139,7 +143,7 @@ def preprocess(images: Sequence[torch.Tensor], out_sizes: Sequence[Tuple[int, in
 
 
 def im2col_7x7s2(x: torch.Tensor, k_pad: int, out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, int, int]:
-    """x: bf16 [n,h,w,4] canvas (3 channels used) or fp32 [n,h,w] depth -> bf16 [n*oh*ow, k_pad]."""
+    """x: bf16 [n,h,w,4] canvas (k_pad 256) or fp32 [n,h,w] depth (k_pad 64) -> bf16 [n*oh*ow, k_pad]."""
     _require_cuda(x, "x")
     is_f32 = x.dtype == torch.float32
     if is_f32:
@@ -148,7 +152,7 @@ def im2col_7x7s2(x: torch.Tensor, k_pad: int, out: Optional[torch.Tensor] = None
     else:
         n, h, w, c4 = x.shape
         assert c4 == 4 and x.dtype == BF16
-        c = 3
+        c = 4
     oh, ow = (h + 1) // 2, (w + 1) // 2
     if out is None:
         out = torch.empty((n * oh * ow, k_pad), dtype=BF16, device=x.device)
@@ -162,7 +166,8 @@ def conv2d(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 1, d
            res: Optional[Act] = None, res_mode: int = 0, out: Optional[Act] = None,
            out_f32: Optional[torch.Tensor] = None, out_rows_per_image: int = 0, out_row_offset: int = 0,
            out_transpose_hw: bool = False, out_phase: Optional[PhaseAct] = None,
-           gn_stats: Optional[torch.Tensor] = None, gn_groups: int = 0, block_n: int = 0, algo_k: int = 0):
+           gn_stats: Optional[torch.Tensor] = None, gn_groups: int = 0, block_n: int = 0, cluster: int = 0,
+           algo_k: int = 0):
     """hn_conv2d_bf16.  x: Act (stride 1) or PhaseAct (stride 2).  relu: bool or (lo, hi) channel range."""
     d = ConvDesc()
     if isinstance(x, PhaseAct):
@@ -199,6 +204,7 @@ def conv2d(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 1, d
         assert gn_stats.dtype == torch.float64 and gn_stats.numel() == d.n * gn_groups * 2
         d.gn_stats, d.gn_groups = gn_stats.data_ptr(), gn_groups
     d.block_n = block_n
+    d.cluster = cluster
     if PROFILE is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()

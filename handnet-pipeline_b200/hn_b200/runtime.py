@@ -17,8 +17,8 @@ from .ops import Act, PhaseAct
 
 BN_EPS = 1e-5      # FrozenBatchNorm2d / nn.BatchNorm2d default eps
 GN_EPS = 1e-5
-STEM_K_RGB = 192   # 7*7*3 = 147 -> next multiple of 64
-STEM_K_DEPTH = 64  # 7*7*1 = 49
+STEM_K_RGB = 256   # 8 kernel rows x 8 pixels x 4 channels (147 real taps), see hn_im2col_7x7s2
+STEM_K_DEPTH = 64  # 8 kernel rows x 8 pixels (49 real taps)
 
 
 def _sig(tensors: Sequence[torch.Tensor]):

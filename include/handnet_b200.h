@@ -53,8 +53,11 @@ int hn_preprocess_resize_pad(const float* const* images_host, const int* in_h_ho
                              const float* std3_host, void* canvas_bf16, int canvas_h, int canvas_w, void* stream);
 
 /* ---- stem: 7x7 stride-2 pad-3 patches as GEMM rows (fcos backbone.body.conv1; a2j/resnet.py:105) ----------
- * in: [n][h][w][c] (c = 4 bf16 when in_is_f32 == 0, c = 1 fp32 when in_is_f32 == 1).
- * out: bf16 [n * ceil(h/2) * ceil(w/2)][k_pad], k = (r*7 + s)*c + ch, zero beyond 49*c. */
+ * K is laid out as 8 kernel rows x 8 pixels x C: k = (r*8 + px)*C + ch with input pixel (2*oy - 3 + r,
+ * 2*ox - 4 + px); r = 7 and px = 0 are padding that meets zero weights (see pack_stem_weight in hn_b200/ops.py).
+ *   in_is_f32 == 0: in = bf16 [n][h][w][4] (the T1 canvas), c = 4, k_pad = 256
+ *   in_is_f32 == 1: in = fp32 [n][h][w]    (depth crops),   c = 1, k_pad = 64
+ * out: bf16 [n * ceil(h/2) * ceil(w/2)][k_pad]. */
 int hn_im2col_7x7s2(const void* in, int in_is_f32, int n, int h, int w, int c, void* out_bf16, int k_pad,
                     void* stream);
 
@@ -87,6 +90,7 @@ typedef struct hn_conv_desc {
                        accumulated with atomics -- caller zeroes it */
   int gn_groups;
   int block_n; /* 0 = choose automatically among 16/32/64/128/256 */
+  int cluster; /* 0 = automatic; 1 = no cluster; 2 = CTA pairs along M that multicast the weight tile */
 } hn_conv_desc;
 int hn_conv2d_bf16(const hn_conv_desc* desc, void* stream);
 

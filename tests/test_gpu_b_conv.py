@@ -55,12 +55,20 @@ CASES = [
     ("1x1_s2_256_512", 2, 22, 22, 256, 512, 1, 2, 1, 1, 0),
     ("3x3_dil2_512_512", 3, 11, 11, 512, 512, 3, 1, 2, 2, 0),
     ("3x3_halo2_in_halo1_conv", 2, 11, 11, 64, 64, 3, 1, 1, 2, 64),
+    # CTA pairs with multicast weights (cluster = 2); odd tile counts leave a dummy CTA in the last cluster
+    ("cs2_3x3_256_256_bn256_odd", 3, 25, 34, 256, 256, 3, 1, 1, 1, 256, 2),
+    ("cs2_3x3_64_64_bn64", 3, 20, 28, 64, 64, 3, 1, 1, 1, 64, 2),
+    ("cs2_3x3_128_128_bn128", 2, 20, 28, 128, 128, 3, 1, 1, 1, 128, 2),
+    ("cs2_1x1_512_2048_bn256", 3, 11, 11, 512, 2048, 1, 1, 1, 1, 256, 2),
+    ("cs2_3x3_s2_128_256", 2, 25, 33, 128, 256, 3, 2, 1, 1, 128, 2),
+    ("cs2_3x3_256_256_auto_big", 4, 100, 136, 256, 256, 3, 1, 1, 1, 0, 0),
 ]
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_conv_scale_shift_relu(ops, case):
-    name, n, h, w, cin, cout, k, stride, dil, halo, bn = case
+    name, n, h, w, cin, cout, k, stride, dil, halo, bn = case[:11]
+    cluster = case[11] if len(case) > 11 else 1
     g = torch.Generator().manual_seed(sum(map(ord, name)))
     x = rand(g, n, cin, h, w).to(DEV)
     wt = rand(g, cout, cin, k, k, scale=(cin * k * k) ** -0.5).to(DEV)
@@ -71,7 +79,7 @@ def test_conv_scale_shift_relu(ops, case):
     xin = ops.Act.from_nchw(x, halo) if stride == 1 else ops.PhaseAct.from_nchw(x, halo)
     out = ops.Act(n, ref.shape[2], ref.shape[3], cout, 1, DEV)
     ops.conv2d(xin, ops.pack_conv_weight(wt), cout=cout, ksize=k, stride=stride, dilation=dil, scale=scale,
-               shift=shift, relu=True, out=out, block_n=bn)
+               shift=shift, relu=True, out=out, block_n=bn, cluster=cluster)
     torch.cuda.synchronize()
     close_bf16(out.to_nchw(), ref, name)
     full = out.t.float().abs().sum()
@@ -201,9 +209,9 @@ def test_stem_im2col_gemm_and_maxpool(ops):
     x_nchw = canvas[..., :3].permute(0, 3, 1, 2).contiguous()
     conv = q(F.relu(F.conv2d(x_nchw, wt, stride=2, padding=3) * scale[None, :, None, None] + shift[None, :, None, None]))
     ref = F.max_pool2d(conv, 3, 2, 1)
-    a, oh, ow = ops.im2col_7x7s2(canvas.to(torch.bfloat16).cuda(), 192)
+    a, oh, ow = ops.im2col_7x7s2(canvas.to(torch.bfloat16).cuda(), 256)
     stem = ops.Act(n, oh, ow, 64, 0, DEV)
-    ops.conv2d(ops.Act(n, oh, ow, 192, 0, DEV, t=a.view(n, oh, ow, 192)), ops.pack_stem_weight(wt.cuda(), 192),
+    ops.conv2d(ops.Act(n, oh, ow, 256, 0, DEV, t=a.view(n, oh, ow, 256)), ops.pack_stem_weight(wt.cuda(), 256),
                cout=64, ksize=1, scale=scale.cuda(), shift=shift.cuda(), relu=True, out=stem)
     pooled = ops.Act(n, (oh + 1) // 2, (ow + 1) // 2, 64, 1, DEV)
     ops.maxpool3x3s2(stem.t, pooled)
