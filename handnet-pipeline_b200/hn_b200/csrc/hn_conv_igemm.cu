@@ -23,6 +23,7 @@ constexpr int BLOCK_K = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 constexpr int NUM_THREADS = 192;
 constexpr int MAX_TAPS = 9;
+constexpr int GN_SMEM_FLOATS = 4096;   // [images][groups][2] fp32 partial sums kept per CTA (16 KiB)
 
 struct ConvParams {
   // compute geometry (== input geometry)
@@ -56,7 +57,8 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ +
+                                    GN_SMEM_FLOATS * 4 /*GroupNorm accumulators*/;
 };
 
 // CS = thread-block cluster size along M: the CS CTAs of a cluster work on CS consecutive M tiles of the same N
@@ -168,6 +170,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     // ===================================== epilogue ==========================================
     const int quarter = warp & 3;              // TMEM lanes this warp may touch: 32*quarter .. +31
     const int img_rows = p.hp * p.wp;
+    // per-CTA GroupNorm accumulator [image][group][2] in shared memory (when it fits)
+    float* gn_acc = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
+    const int gn_vals = p.gn_stats ? p.n_img * p.gn_groups * 2 : 0;
+    const bool gn_smem = gn_vals > 0 && gn_vals <= GN_SMEM_FLOATS;
+    if (gn_smem) {
+      for (int i = threadIdx.x - 64; i < gn_vals; i += 128) gn_acc[i] = 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     int it = 0;
     for (int st = cluster_id; st < num_super; st += num_clusters, ++it) {
       const int buf = it & 1;
@@ -213,13 +223,31 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       const int warp_img = __shfl_sync(0xffffffffu, img, interior_mask ? (__ffs(interior_mask) - 1) : 0);
       const bool warp_uniform_img = __all_sync(0xffffffffu, (!interior) || (img == warp_img));
 
+      constexpr int CHUNK = (BN >= 32) ? 32 : 16;
+      // residual rows are fetched one chunk ahead (the first one before the accumulator wait) so that their
+      // global-load latency hides behind the wait / the previous chunk's work
+      const bool res_vec = p.res_mode != 0 && interior && (p.cout & 7) == 0;
+      uint4 res_next[CHUNK / 8];
+      if (res_vec && n0 + CHUNK <= p.cout) {
+#pragma unroll
+        for (int j = 0; j < CHUNK / 8; ++j)
+          res_next[j] = __ldg(reinterpret_cast<const uint4*>(p.res + res_off + n0) + j);
+      }
+
       hn_mbar_wait(&tmem_full[buf], acc_phase);
       hn_tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + buf * BN;
 
-      constexpr int CHUNK = (BN >= 32) ? 32 : 16;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += CHUNK) {
+        uint4 res_cur[CHUNK / 8];
+#pragma unroll
+        for (int j = 0; j < CHUNK / 8; ++j) res_cur[j] = res_next[j];
+        if (res_vec && c0 + CHUNK < BN && n0 + c0 + 2 * CHUNK <= p.cout) {
+#pragma unroll
+          for (int j = 0; j < CHUNK / 8; ++j)
+            res_next[j] = __ldg(reinterpret_cast<const uint4*>(p.res + res_off + n0 + c0 + CHUNK) + j);
+        }
         uint32_t acc[CHUNK];
         if constexpr (CHUNK == 32) {
           hn_tmem_ld32(t_row + c0, acc);
@@ -257,7 +285,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           if (cbase + CHUNK <= p.cout && (p.cout & 7) == 0) {
 #pragma unroll
             for (int j = 0; j < CHUNK; j += 8) {
-              const uint4 r = __ldg(reinterpret_cast<const uint4*>(rp + j));
+              const uint4 r = res_cur[j / 8];
               v[j + 0] += hn_bf16_lo(r.x); v[j + 1] += hn_bf16_hi(r.x);
               v[j + 2] += hn_bf16_lo(r.y); v[j + 3] += hn_bf16_hi(r.y);
               v[j + 4] += hn_bf16_lo(r.z); v[j + 5] += hn_bf16_hi(r.z);
@@ -315,12 +343,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           }
         }
         if (p.gn_stats) {
-          // partial sums over the bf16-rounded values, per (image, group); groups are multiples of 8 channels
+          // GroupNorm partial sums over the bf16-rounded values.  Per lane: (sum, sumsq) of the 4 channel octets of
+          // this chunk = 8 values; a transposing butterfly (4+2+1+1+1 shuffles) leaves total k in lane 4*k, which
+          // adds it to the CTA's shared-memory accumulator of its (image, group); flushed once at kernel end.
           if constexpr (CHUNK == 32) {
-            const int per = p.gn_group_size >> 3;       // 8-channel octets per group: 1, 2 or 4
-            float s = 0.f, q = 0.f;
+            float v8[8];
 #pragma unroll
-            for (int o8 = 0; o8 < CHUNK / 8; ++o8) {
+            for (int o8 = 0; o8 < 4; ++o8) {
+              float s = 0.f, q = 0.f;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const uint32_t pk = packed[o8 * 4 + j];
@@ -328,27 +358,52 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 s += x0 + x1;
                 q += x0 * x0 + x1 * x1;
               }
-              if (((o8 + 1) % per) == 0) {
-                const int group = (cbase + o8 * 8) / p.gn_group_size;
-                float ws = interior ? s : 0.f, wq = interior ? q : 0.f;
-                if (warp_uniform_img) {
+              v8[2 * o8] = interior ? s : 0.f;
+              v8[2 * o8 + 1] = interior ? q : 0.f;
+            }
+            if (warp_uniform_img) {
+              {
+                const bool hi = lane & 16;
 #pragma unroll
-                  for (int o = 16; o > 0; o >>= 1) {
-                    ws += __shfl_xor_sync(0xffffffffu, ws, o);
-                    wq += __shfl_xor_sync(0xffffffffu, wq, o);
-                  }
-                  if (lane == 0 && interior_mask != 0u) {
-                    double* dst = p.gn_stats + ((long long)warp_img * p.gn_groups + group) * 2;
-                    atomicAdd(dst, (double)ws);
-                    atomicAdd(dst + 1, (double)wq);
-                  }
-                } else if (interior) {
-                  double* dst = p.gn_stats + ((long long)img * p.gn_groups + group) * 2;
-                  atomicAdd(dst, (double)ws);
-                  atomicAdd(dst + 1, (double)wq);
+                for (int i = 0; i < 4; ++i) {
+                  const float send = hi ? v8[i] : v8[i + 4];
+                  const float keep = hi ? v8[i + 4] : v8[i];
+                  v8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
                 }
-                s = 0.f;
-                q = 0.f;
+              }
+              {
+                const bool hi = lane & 8;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  const float send = hi ? v8[i] : v8[i + 2];
+                  const float keep = hi ? v8[i + 2] : v8[i];
+                  v8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+              }
+              {
+                const bool hi = lane & 4;
+                const float send = hi ? v8[0] : v8[1];
+                const float keep = hi ? v8[1] : v8[0];
+                v8[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+              }
+              v8[0] += __shfl_xor_sync(0xffffffffu, v8[0], 2);
+              v8[0] += __shfl_xor_sync(0xffffffffu, v8[0], 1);
+              if ((lane & 3) == 0 && interior_mask != 0u) {
+                const int k = lane >> 2;                         // value index: octet k/2, stat k&1
+                const int group = (cbase + (k >> 1) * 8) / p.gn_group_size;
+                if (group < p.gn_groups) {
+                  if (gn_smem) atomicAdd(&gn_acc[(warp_img * p.gn_groups + group) * 2 + (k & 1)], v8[0]);
+                  else atomicAdd(p.gn_stats + ((long long)warp_img * p.gn_groups + group) * 2 + (k & 1), (double)v8[0]);
+                }
+              }
+            } else if (interior) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int group = (cbase + (k >> 1) * 8) / p.gn_group_size;
+                if (group < p.gn_groups) {
+                  if (gn_smem) atomicAdd(&gn_acc[(img * p.gn_groups + group) * 2 + (k & 1)], v8[k]);
+                  else atomicAdd(p.gn_stats + ((long long)img * p.gn_groups + group) * 2 + (k & 1), (double)v8[k]);
+                }
               }
             }
           }
@@ -358,6 +413,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       hn_tc_fence_before();
       __syncwarp();
       if (lane == 0) hn_mbar_arrive(&tmem_empty[buf]);
+    }
+    if (gn_smem) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = threadIdx.x - 64; i < gn_vals; i += 128) {
+        const float v = gn_acc[i];
+        if (v != 0.f) atomicAdd(p.gn_stats + i, (double)v);
+      }
     }
   }
 
@@ -438,20 +500,24 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cu
   return HN_OK;
 }
 
-int pick_block_n(int cout_pad, int m_tiles) {
-  // Largest tile that still gives every SM a tile; tiny-N output convs use their padded width.
+int pick_block_n(int cout_pad, int m_tiles, int k_blocks) {
+  // Cost model from the measured per-layer table (profiles/): a k-block costs about the same ~800 cycles for every
+  // tile width because the A tile (16 KiB) dominates the L2 -> SM traffic, so wide tiles win unless the extra
+  // waves they leave idle outweigh it.  cost = waves * (k_blocks * kb_cycles + epilogue).
   const int sms = hn_num_sms();
   const int cands[5] = {256, 128, 64, 32, 16};
-  int best = 16;
+  const double kb_cycles[5] = {820.0, 640.0, 560.0, 520.0, 500.0};
+  int best = 0;
+  double best_cost = 1e30;
   for (int i = 0; i < 5; ++i) {
     const int bn = cands[i];
     if (cout_pad % bn) continue;
-    best = bn;
-    if ((long long)m_tiles * (cout_pad / bn) >= sms) break;
-    if (bn == 64) break;                   // below 64 only when the layer is that narrow
+    const long long tiles = (long long)m_tiles * (cout_pad / bn);
+    const double waves = (double)((tiles + sms - 1) / sms);
+    const double cost = waves * (k_blocks * kb_cycles[i] + 400.0 + 10.0 * bn);
+    if (cost < best_cost) { best_cost = cost; best = bn; }
   }
-  while (cout_pad % best) best >>= 1;
-  return best;
+  return best ? best : 16;
 }
 
 }  // namespace
@@ -498,12 +564,13 @@ extern "C" int hn_conv2d_bf16(const hn_conv_desc* d, void* stream) {
       }
     }
   p.m_tiles = hn_div_up(p.rows, BLOCK_M);
-  int bn = d->block_n ? d->block_n : pick_block_n(d->cout_pad, p.m_tiles);
+  int bn = d->block_n ? d->block_n : pick_block_n(d->cout_pad, p.m_tiles, p.num_taps * p.cin_chunks);
   HN_REQUIRE((bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256) && d->cout_pad % bn == 0,
              "hn_conv2d_bf16: block_n=%d does not divide cout_pad=%d", bn, d->cout_pad);
   p.n_tiles = d->cout_pad / bn;
   // cluster of 2 with multicast weights when there is at least one pair of M tiles per SM pair
-  int cs = d->cluster ? d->cluster : ((bn >= 64 && hn_div_up(p.m_tiles, 2) * p.n_tiles >= hn_num_sms() / 2) ? 2 : 1);
+  // measured: pairs with multicast weights gain ~3 % on 256-wide tiles and lose elsewhere -> opt-in only
+  int cs = d->cluster ? d->cluster : 1;
   HN_REQUIRE(cs == 1 || (cs == 2 && bn >= 64), "hn_conv2d_bf16: cluster=%d unsupported with block_n=%d", cs, bn);
   p.cout = d->cout;
   p.scale = d->scale;
