@@ -16,6 +16,8 @@
 //                               sums, optional phase-split copy for a following stride-2 conv)
 #include "hn_common.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 constexpr int BLOCK_M = 128;
@@ -107,6 +109,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   if constexpr (CS > 1) hn_cluster_sync();   // peers' barriers must exist before anyone signals them
   hn_tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may run
+  // while the previous kernel of the stream is still draining; global memory is touched only after the wait.
+  // The early trigger lets the next kernel do the same under this one.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -470,6 +477,15 @@ int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, 
   return HN_OK;
 }
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HN_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 template <int BN, int CS>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t st) {
   using C = Cfg<BN>;
@@ -488,19 +504,28 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cu
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CS > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CS;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = (CS > 1) ? 1 : 0;
+  cfg.numAttrs = na;
   HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, CS>, ta, tb, p));
   hn_count_launch();
   return HN_OK;
 }
 
-int pick_block_n(int cout_pad, int m_tiles, int k_blocks) {
+int pick_block_n(int cout_pad, int m_tiles, int k_blocks, int min_bn) {
   // Cost model from the measured per-layer table (profiles/): a k-block costs about the same ~800 cycles for every
   // tile width because the A tile (16 KiB) dominates the L2 -> SM traffic, so wide tiles win unless the extra
   // waves they leave idle outweigh it.  cost = waves * (k_blocks * kb_cycles + epilogue).
@@ -511,7 +536,7 @@ int pick_block_n(int cout_pad, int m_tiles, int k_blocks) {
   double best_cost = 1e30;
   for (int i = 0; i < 5; ++i) {
     const int bn = cands[i];
-    if (cout_pad % bn) continue;
+    if (cout_pad % bn || bn < min_bn) continue;
     const long long tiles = (long long)m_tiles * (cout_pad / bn);
     const double waves = (double)((tiles + sms - 1) / sms);
     const double cost = waves * (k_blocks * kb_cycles[i] + 400.0 + 10.0 * bn);
@@ -564,7 +589,7 @@ extern "C" int hn_conv2d_bf16(const hn_conv_desc* d, void* stream) {
       }
     }
   p.m_tiles = hn_div_up(p.rows, BLOCK_M);
-  int bn = d->block_n ? d->block_n : pick_block_n(d->cout_pad, p.m_tiles, p.num_taps * p.cin_chunks);
+  int bn = d->block_n ? d->block_n : pick_block_n(d->cout_pad, p.m_tiles, p.num_taps * p.cin_chunks, d->gn_stats ? 32 : 16);
   HN_REQUIRE((bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256) && d->cout_pad % bn == 0,
              "hn_conv2d_bf16: block_n=%d does not divide cout_pad=%d", bn, d->cout_pad);
   p.n_tiles = d->cout_pad / bn;
