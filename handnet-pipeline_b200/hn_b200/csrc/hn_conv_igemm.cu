@@ -496,8 +496,11 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cu
     attr_set = true;
   }
   const int super = hn_div_up(p.m_tiles, CS) * p.n_tiles;
+  // equal work per CTA: with w = ceil(tiles / SMs) waves, ceil(tiles / w) CTAs finish at the same time as a full grid
+  // would and leave the other SMs to kernels of concurrent streams (graph branches)
   const int max_clusters = hn_num_sms() / CS;
-  const int clusters = super < max_clusters ? super : max_clusters;
+  const int waves = hn_div_up(super, max_clusters);
+  const int clusters = hn_div_up(super, waves);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(clusters * CS);

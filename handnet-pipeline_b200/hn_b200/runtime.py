@@ -34,6 +34,41 @@ def bn_affine(weight, bias, mean, var, eps=BN_EPS, conv_bias=None):
     return scale.contiguous(), shift.contiguous()
 
 
+_side_streams: Dict[str, List["torch.cuda.Stream"]] = {}
+PARALLEL_CHAINS = True      # independent layer chains (head towers, A2J towers) on forked streams / graph branches
+
+
+def run_chains(chains, device):
+    """Run independent callables on forked CUDA streams and join them on the current stream.  Under CUDA-graph
+    capture this becomes a fork/join in the graph, so kernels of different chains fill each other's partial
+    waves (most layers here have fewer tiles than a multiple of the 148 SMs)."""
+    if not PARALLEL_CHAINS or len(chains) <= 1:
+        for c in chains:
+            c()
+        return
+    key = str(device)
+    pool = _side_streams.setdefault(key, [])
+    while len(pool) < len(chains) - 1:
+        pool.append(torch.cuda.Stream(device=device))
+    main = torch.cuda.current_stream(device)
+    fork = torch.cuda.Event()
+    fork.record(main)
+    joins = []
+    for i, c in enumerate(chains):
+        if i == 0:
+            continue
+        st = pool[i - 1]
+        st.wait_event(fork)
+        with torch.cuda.stream(st):
+            c()
+            ev = torch.cuda.Event()
+            ev.record(st)
+            joins.append(ev)
+    chains[0]()
+    for ev in joins:
+        main.wait_event(ev)
+
+
 class ConvLayer:
     """Packed weights + epilogue vectors of one convolution."""
 
@@ -209,12 +244,12 @@ class FCOSExecutor:
                 w.inner[i].run(feats[i], out=pl.inner[i])
             else:
                 w.inner[i].run(feats[i], res=pl.inner[i + 1], res_mode=2, out=pl.inner[i])
-        for i in range(3):
-            w.outer[i].run(pl.inner[i], out=pl.p[i])
+        run_chains([(lambda i=i: w.outer[i].run(pl.inner[i], out=pl.p[i])) for i in range(3)], pl.canvas.device)
         # heads (fcos_utils/fcos.py:267-329, 373-395)
         pl.gn_stats.zero_()
-        for ti, t in enumerate(("cls", "reg")):
-            for lvl in range(3):
+
+        def tower_chain(ti, t, lvl):
+            def run():
                 x = pl.p[lvl]
                 for i, (conv, gamma, beta) in enumerate(w.towers[t]):
                     o = pl.tower[t][lvl][i & 1]
@@ -228,6 +263,11 @@ class FCOSExecutor:
                 else:
                     w.reg_out.run(x, relu=w.reg_relu, out_f32=pl.reg_buf, out_rows_per_image=pl.locs,
                                   out_row_offset=pl.levels.starts[lvl])
+            return run
+
+        # six independent chains: (cls, reg) x (P3, P4, P5); the big P3 chains first
+        run_chains([tower_chain(ti, t, lvl) for lvl in range(3) for ti, t in enumerate(("cls", "reg"))],
+                   pl.canvas.device)
         return pl.cls_buf, pl.reg_buf
 
     def head_views(self, pl: FCOSPlan):
@@ -437,16 +477,20 @@ class A2JExecutor:
                 c4 = cur
         c5 = cur
         hf, wf = pl.feat_hw
-        for name, src, dst in (("classificationModel", c4, pl.cls), ("regressionModel", c5, pl.reg),
-                               ("DepthRegressionModel", c5, pl.dep)):
-            layers, outc = w.towers[name]
-            t = src
-            for i, conv in enumerate(layers):
-                o = pl.act(f"{name}{i}", hf, wf, 256)
-                conv.run(t, relu=True, out=o)
-                t = o
-            # permute(0,3,2,1) + view of the reference == w-major rows (a2j/a2j.py:85-89)
-            outc.run(t, out_f32=dst.view(n, hf * wf, -1), out_transpose_hw=True)
+        def a2j_tower(name, src, dst):
+            def run():
+                layers, outc = w.towers[name]
+                t = src
+                for i, conv in enumerate(layers):
+                    o = pl.act(f"{name}{i}", hf, wf, 256)
+                    conv.run(t, relu=True, out=o)
+                    t = o
+                # permute(0,3,2,1) + view of the reference == w-major rows (a2j/a2j.py:85-89)
+                outc.run(t, out_f32=dst.view(n, hf * wf, -1), out_transpose_hw=True)
+            return run
+
+        run_chains([a2j_tower("regressionModel", c5, pl.reg), a2j_tower("DepthRegressionModel", c5, pl.dep),
+                    a2j_tower("classificationModel", c4, pl.cls)], x.device)
         return pl.cls, pl.reg, pl.dep, pl
 
     def forward_device(self, x: torch.Tensor) -> torch.Tensor:
@@ -562,8 +606,10 @@ def conv_profile(step: GraphedHandNet, repeats: int = 3):
     The step is enqueued eagerly behind a long spin kernel so that the host finishes queueing before the GPU
     starts: the CUDA events around each conv launch (on the launch stream) then bracket back-to-back kernels
     and contain no host-induced gaps."""
+    global PARALLEL_CHAINS
     best = None
     n = 0
+    saved, PARALLEL_CHAINS = PARALLEL_CHAINS, False      # one stream: per-launch times must not overlap
     for _ in range(repeats):
         ops.PROFILE = []
         torch.cuda._sleep(150_000_000)
@@ -576,6 +622,7 @@ def conv_profile(step: GraphedHandNet, repeats: int = 3):
         if best is None or ms < best:
             best = ms
             step.last_conv_table = [dict(p[3], ms=p[0].elapsed_time(p[1]), gflop=p[2] / 1e9) for p in prof]
+    PARALLEL_CHAINS = saved
     return best, n
 
 

@@ -58,7 +58,9 @@ def test_fcos_detections_consistent_with_oracle_postprocess(fcos_small, golden):
     imgs = inputs_images(5, 2, 120, 160)
     with torch.inference_mode():
         out = m.forward_device([i.cuda() for i in imgs])
-        dets = m([i.cuda() for i in imgs])
+        # one pass only: GroupNorm partial sums are accumulated with atomics, so two passes may differ in the
+        # last bf16 bit of a few activations
+        dets = m.split_detections(out, m.ext)
     torch.cuda.synchronize()
     ref_dets = golden("fcos_small.pt")["dets"]
     sizes = [fcos_oracle.resized_size(120, 160, 256, 448)] * 2
