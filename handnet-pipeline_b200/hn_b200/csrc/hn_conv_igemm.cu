@@ -20,10 +20,14 @@
 
 namespace {
 
+__device__ __forceinline__ void hn_epi_bar_sync();
+
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;                       // two per TMEM lane quarter; they split the column chunks
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int NUM_THREADS = 64 + EPI_THREADS;
 constexpr int MAX_TAPS = 9;
 constexpr int GN_SMEM_FLOATS = 4096;   // [images][groups][2] fp32 partial sums kept per CTA (16 KiB)
 
@@ -53,6 +57,10 @@ struct ConvParams {
   int gn_groups, gn_group_size;
 };
 
+__device__ __forceinline__ void hn_epi_bar_sync() {   // named barrier 1: the epilogue warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+}
+
 template <int BN>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
@@ -60,7 +68,8 @@ struct Cfg {
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ +
-                                    GN_SMEM_FLOATS * 4 /*GroupNorm accumulators*/;
+                                    GN_SMEM_FLOATS * 4 /*GroupNorm accumulators*/ +
+                                    2 * 2 * 256 * 4 /*scale/shift of the N tile, double buffered*/;
 };
 
 // CS = thread-block cluster size along M: the CS CTAs of a cluster work on CS consecutive M tiles of the same N
@@ -99,7 +108,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     }
     for (int b = 0; b < 2; ++b) {
       hn_mbar_init(&tmem_full[b], 1);
-      hn_mbar_init(&tmem_empty[b], 4);   // one arrive per epilogue warp
+      hn_mbar_init(&tmem_empty[b], EPI_WARPS);   // one arrive per epilogue warp
     }
     hn_mbar_init_fence();
   }
@@ -176,14 +185,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   } else {
     // ===================================== epilogue ==========================================
     const int quarter = warp & 3;              // TMEM lanes this warp may touch: 32*quarter .. +31
+    const int half = (warp - 2) >> 2;          // which of the two warps of this quarter: takes every other chunk
     const int img_rows = p.hp * p.wp;
+    // scale/shift of the current N tile live in shared memory (the L1 left next to ~210 KiB of smem is too small
+    // to keep them, and an L2 round trip per chunk was the epilogue's critical path)
+    float* ss_base = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256 + GN_SMEM_FLOATS * 4);
     // per-CTA GroupNorm accumulator [image][group][2] in shared memory (when it fits)
     float* gn_acc = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
     const int gn_vals = p.gn_stats ? p.n_img * p.gn_groups * 2 : 0;
     const bool gn_smem = gn_vals > 0 && gn_vals <= GN_SMEM_FLOATS;
     if (gn_smem) {
-      for (int i = threadIdx.x - 64; i < gn_vals; i += 128) gn_acc[i] = 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = threadIdx.x - 64; i < gn_vals; i += EPI_THREADS) gn_acc[i] = 0.f;
+      hn_epi_bar_sync();
     }
     int it = 0;
     for (int st = cluster_id; st < num_super; st += num_clusters, ++it) {
@@ -231,14 +244,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       const bool warp_uniform_img = __all_sync(0xffffffffu, (!interior) || (img == warp_img));
 
       constexpr int CHUNK = (BN >= 32) ? 32 : 16;
+      float* ss = ss_base + (it & 1) * 512;   // [0,256) scale, [256,512) shift for columns n0 .. n0+BN
+      for (int i = threadIdx.x - 64; i < BN; i += EPI_THREADS) {
+        const int c = n0 + i;
+        ss[i] = (p.scale && c < p.cout) ? __ldg(p.scale + c) : 1.0f;
+        ss[256 + i] = (p.shift && c < p.cout) ? __ldg(p.shift + c) : 0.0f;
+      }
+      hn_epi_bar_sync();
       // residual rows are fetched one chunk ahead (the first one before the accumulator wait) so that their
       // global-load latency hides behind the wait / the previous chunk's work
       const bool res_vec = p.res_mode != 0 && interior && (p.cout & 7) == 0;
       uint4 res_next[CHUNK / 8];
-      if (res_vec && n0 + CHUNK <= p.cout) {
+      constexpr int STEP = (BN / CHUNK >= 2) ? 2 * CHUNK : CHUNK;   // two warps interleave chunks when there are >= 2
+      const int c_first = (BN / CHUNK >= 2) ? half * CHUNK : 0;
+      const bool idle_half = (BN / CHUNK < 2) && half == 1;         // a single chunk: the second warp only arrives
+      if (res_vec && !idle_half && n0 + c_first + CHUNK <= p.cout) {
 #pragma unroll
         for (int j = 0; j < CHUNK / 8; ++j)
-          res_next[j] = __ldg(reinterpret_cast<const uint4*>(p.res + res_off + n0) + j);
+          res_next[j] = __ldg(reinterpret_cast<const uint4*>(p.res + res_off + n0 + c_first) + j);
       }
 
       hn_mbar_wait(&tmem_full[buf], acc_phase);
@@ -246,14 +269,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + buf * BN;
 
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += CHUNK) {
+      for (int c0 = c_first; c0 < (idle_half ? 0 : BN); c0 += STEP) {
         uint4 res_cur[CHUNK / 8];
 #pragma unroll
         for (int j = 0; j < CHUNK / 8; ++j) res_cur[j] = res_next[j];
-        if (res_vec && c0 + CHUNK < BN && n0 + c0 + 2 * CHUNK <= p.cout) {
+        if (res_vec && c0 + STEP < BN && n0 + c0 + STEP + CHUNK <= p.cout) {
 #pragma unroll
           for (int j = 0; j < CHUNK / 8; ++j)
-            res_next[j] = __ldg(reinterpret_cast<const uint4*>(p.res + res_off + n0 + c0 + CHUNK) + j);
+            res_next[j] = __ldg(reinterpret_cast<const uint4*>(p.res + res_off + n0 + c0 + STEP) + j);
         }
         uint32_t acc[CHUNK];
         if constexpr (CHUNK == 32) {
@@ -265,27 +288,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         const int cbase = n0 + c0;
         if (cbase >= p.cout) continue;                 // padded output channels (warp-uniform)
         float v[CHUNK];
-        if (cbase + CHUNK <= p.cout) {
 #pragma unroll
-          for (int j = 0; j < CHUNK; j += 4) {
-            const float4 sc = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + cbase + j))
-                                      : make_float4(1.f, 1.f, 1.f, 1.f);
-            const float4 sh = p.shift ? __ldg(reinterpret_cast<const float4*>(p.shift + cbase + j))
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-            v[j + 0] = __uint_as_float(acc[j + 0]) * sc.x + sh.x;
-            v[j + 1] = __uint_as_float(acc[j + 1]) * sc.y + sh.y;
-            v[j + 2] = __uint_as_float(acc[j + 2]) * sc.z + sh.z;
-            v[j + 3] = __uint_as_float(acc[j + 3]) * sc.w + sh.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < CHUNK; ++j) {
-            const int c = cbase + j;
-            const bool ok = c < p.cout;
-            const float sc = (p.scale && ok) ? __ldg(p.scale + c) : 1.0f;
-            const float sh = (p.shift && ok) ? __ldg(p.shift + c) : 0.0f;
-            v[j] = __uint_as_float(acc[j]) * sc + sh;
-          }
+        for (int j = 0; j < CHUNK; j += 4) {
+          const float4 sc = *reinterpret_cast<const float4*>(ss + c0 + j);          // broadcast LDS
+          const float4 sh = *reinterpret_cast<const float4*>(ss + 256 + c0 + j);
+          v[j + 0] = __uint_as_float(acc[j + 0]) * sc.x + sh.x;
+          v[j + 1] = __uint_as_float(acc[j + 1]) * sc.y + sh.y;
+          v[j + 2] = __uint_as_float(acc[j + 2]) * sc.z + sh.z;
+          v[j + 3] = __uint_as_float(acc[j + 3]) * sc.w + sh.w;
         }
         if (p.res_mode != 0 && interior) {
           const __nv_bfloat16* rp = p.res + res_off + cbase;
@@ -422,8 +432,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       if (lane == 0) hn_mbar_arrive(&tmem_empty[buf]);
     }
     if (gn_smem) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = threadIdx.x - 64; i < gn_vals; i += 128) {
+      hn_epi_bar_sync();
+      for (int i = threadIdx.x - 64; i < gn_vals; i += EPI_THREADS) {
         const float v = gn_acc[i];
         if (v != 0.f) atomicAdd(p.gn_stats + i, (double)v);
       }
