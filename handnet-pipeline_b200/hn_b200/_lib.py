@@ -32,7 +32,7 @@ class ConvDesc(C.Structure):
         ("out_rows_per_image", _i), ("out_row_offset", _i), ("out_ld", _i), ("out_transpose_hw", _i),
         ("out_phase", _c_p), ("out_phase_halo", _i),
         ("gn_stats", _c_p), ("gn_groups", _i),
-        ("block_n", _i), ("cluster", _i),
+        ("block_n", _i), ("cluster", _i), ("debug", _i),
     ]
 
 

@@ -55,11 +55,22 @@ struct ConvParams {
   long long ph_stride;         // elements between phase images
   double* gn_stats;
   int gn_groups, gn_group_size;
+  int rb_stages, rb_b_bytes;        // resident-weights mode: A stages and bytes of the weight slice
+  int dbg_shift, dbg_base_offset;   // bring-up experiment: A box loaded dbg_shift rows early, descriptor offset back
 };
 
 __device__ __forceinline__ void hn_epi_bar_sync() {   // named barrier 1: the epilogue warps only
   asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
 }
+
+// Shared memory: [0, HDR_BYTES) barriers, GroupNorm accumulators, scale/shift of the N tile; then (1024-aligned)
+// either STAGES x (A tile + B tile), or -- "resident weights" (RB) -- the whole weight slice of the layer followed
+// by A-only stages, which puts more k-blocks in flight per SM for the narrow layers.
+constexpr int MAX_STAGES = 12;
+constexpr int HDR_BARS = 256;
+constexpr int HDR_BYTES = HDR_BARS + GN_SMEM_FLOATS * 4 + 2 * 2 * 256 * 4;   // 20736, padded to 1024 below
+constexpr int HDR_PAD = ((HDR_BYTES + 1023) / 1024) * 1024;
+constexpr int PIPE_BYTES_MAX = 196608;                                        // 192 KiB for the operand ring(s)
 
 template <int BN>
 struct Cfg {
@@ -67,28 +78,34 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ +
-                                    GN_SMEM_FLOATS * 4 /*GroupNorm accumulators*/ +
-                                    2 * 2 * 256 * 4 /*scale/shift of the N tile, double buffered*/;
+  static constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + HDR_PAD + STAGES * STAGE_BYTES;
+  static constexpr int SMEM_BYTES_RB = 1024 + HDR_PAD + PIPE_BYTES_MAX;
 };
 
 // CS = thread-block cluster size along M: the CS CTAs of a cluster work on CS consecutive M tiles of the same N
 // tile in lock step; each loads 1/CS of the B (weight) tile and multicasts it to all of them, so the weights
 // cross the L2 -> SM fabric once per cluster instead of once per CTA.
-template <int BN, int CS>
+template <int BN, int CS, bool RB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                   const ConvParams p) {
   using C = Cfg<BN>;
   static_assert(CS == 1 || (BN / CS) % 8 == 0, "B slices must keep whole 8-row swizzle atoms");
+  static_assert(!(RB && CS > 1), "resident weights are per CTA");
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* smem_hdr = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_hdr);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + C::STAGES;
-  uint64_t* tmem_full = bars + 2 * C::STAGES;
+  uint64_t* empty_bar = bars + MAX_STAGES;
+  uint64_t* tmem_full = bars + 2 * MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* b_full = tmem_empty + 2;                     // resident weights have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  uint8_t* pipe = smem_hdr + HDR_PAD;                    // 1024-aligned operand area
+  // RB: [weights: k_blocks x (BN x 128 B)] [A stages]; otherwise STAGES x [A | B]
+  const int num_stages = RB ? p.rb_stages : C::STAGES;
+  const int stage_bytes = RB ? A_STAGE_BYTES : C::STAGE_BYTES;
+  uint8_t* smem = pipe + (RB ? p.rb_b_bytes : 0);        // base of the stage ring
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -102,10 +119,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   if (threadIdx.x == 0) {
     hn_tma_prefetch_desc(&tm_a);
     hn_tma_prefetch_desc(&tm_b);
-    for (int s = 0; s < C::STAGES; ++s) {
+    for (int s = 0; s < num_stages; ++s) {
       hn_mbar_init(&full_bar[s], 1);
       hn_mbar_init(&empty_bar[s], CS);   // every CTA of the cluster releases the slot (its peers write into it)
     }
+    hn_mbar_init(b_full, 1);
     for (int b = 0; b < 2; ++b) {
       hn_mbar_init(&tmem_full[b], 1);
       hn_mbar_init(&tmem_empty[b], EPI_WARPS);   // one arrive per epilogue warp
@@ -129,6 +147,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if constexpr (RB) {
+        // the layer's whole weight slice (n_tiles == 1), once per CTA
+        hn_mbar_expect_tx(b_full, (uint32_t)p.rb_b_bytes);
+        for (int kb = 0; kb < k_blocks; ++kb)
+          hn_tma_load_2d(pipe + kb * C::B_STAGE_BYTES, &tm_b, b_full, kb * BLOCK_K, 0);
+      }
       for (int st = cluster_id; st < num_super; st += num_clusters) {
         const int m0 = ((st / p.n_tiles) * CS + cta_rank) * BLOCK_M;
         const int n0 = (st % p.n_tiles) * BN;
@@ -136,17 +160,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           const int tap = kb / p.cin_chunks;
           const int cc = kb - tap * p.cin_chunks;
           hn_mbar_wait(&empty_bar[stage], phase ^ 1);
-          hn_mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-          uint8_t* sa = smem + stage * C::STAGE_BYTES;
-          hn_tma_load_3d(sa, &tm_a, &full_bar[stage], cc * BLOCK_K, m0 + p.tap_shift[tap], p.tap_phase[tap]);
-          if constexpr (CS == 1) {
+          hn_mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          uint8_t* sa = smem + stage * stage_bytes;
+          hn_tma_load_3d(sa, &tm_a, &full_bar[stage], cc * BLOCK_K, m0 + p.tap_shift[tap] - p.dbg_shift, p.tap_phase[tap]);
+          if constexpr (RB) {
+          } else if constexpr (CS == 1) {
             hn_tma_load_2d(sa + A_STAGE_BYTES, &tm_b, &full_bar[stage], kb * BLOCK_K, n0);
           } else {
             constexpr int SLICE = BN / CS;   // weight rows this CTA fetches for the whole cluster
             hn_tma_load_2d_mcast(sa + A_STAGE_BYTES + cta_rank * SLICE * BLOCK_K * 2, &tm_b, &full_bar[stage],
                                  kb * BLOCK_K, n0 + cta_rank * SLICE, (uint16_t)((1u << CS) - 1u));
           }
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -157,6 +182,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      if constexpr (RB) hn_mbar_wait(b_full, 0);
       for (int st = cluster_id; st < num_super; st += num_clusters, ++it) {
         const int buf = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -166,9 +192,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         for (int kb = 0; kb < k_blocks; ++kb) {
           hn_mbar_wait(&full_bar[stage], phase);
           hn_tc_fence_after();
-          const uint32_t a_addr = hn_smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint64_t da = hn_umma_smem_desc(a_addr);
-          const uint64_t db = hn_umma_smem_desc(a_addr + A_STAGE_BYTES);
+          const uint32_t a_addr = hn_smem_u32(smem + stage * stage_bytes);
+          const uint64_t da = hn_umma_smem_desc(a_addr + p.dbg_shift * 128) |
+                              (uint64_t(p.dbg_base_offset ? (p.dbg_shift & 7) : 0) << 49);
+          const uint64_t db = hn_umma_smem_desc(RB ? hn_smem_u32(pipe + kb * C::B_STAGE_BYTES) : a_addr + A_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             // +32 bytes per K=16 step inside the 128-byte swizzle span: start-address field += 2
@@ -177,7 +204,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           // frees the smem slot (in every CTA of the cluster) once these MMAs have read it
           if constexpr (CS == 1) hn_umma_commit(&empty_bar[stage]);
           else hn_umma_commit_mcast(&empty_bar[stage], (uint16_t)((1u << CS) - 1u));
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
         hn_umma_commit(&tmem_full[buf]);       // accumulator complete -> epilogue
       }
@@ -189,9 +216,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const int img_rows = p.hp * p.wp;
     // scale/shift of the current N tile live in shared memory (the L1 left next to ~210 KiB of smem is too small
     // to keep them, and an L2 round trip per chunk was the epilogue's critical path)
-    float* ss_base = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256 + GN_SMEM_FLOATS * 4);
+    float* ss_base = reinterpret_cast<float*>(smem_hdr + HDR_BARS + GN_SMEM_FLOATS * 4);
     // per-CTA GroupNorm accumulator [image][group][2] in shared memory (when it fits)
-    float* gn_acc = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
+    float* gn_acc = reinterpret_cast<float*>(smem_hdr + HDR_BARS);
     const int gn_vals = p.gn_stats ? p.n_img * p.gn_groups * 2 : 0;
     const bool gn_smem = gn_vals > 0 && gn_vals <= GN_SMEM_FLOATS;
     if (gn_smem) {
@@ -496,13 +523,14 @@ bool pdl_enabled() {
   return v == 1;
 }
 
-template <int BN, int CS>
+template <int BN, int CS, bool RB>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t st) {
   using C = Cfg<BN>;
+  constexpr int SMEM = RB ? C::SMEM_BYTES_RB : C::SMEM_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
-    HN_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       C::SMEM_BYTES));
+    HN_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, CS, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SMEM));
     attr_set = true;
   }
   const int super = hn_div_up(p.m_tiles, CS) * p.n_tiles;
@@ -515,7 +543,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cu
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(clusters * CS);
   cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.dynamicSmemBytes = SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   int na = 0;
@@ -533,7 +561,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cu
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, CS>, ta, tb, p));
+  HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, CS, RB>, ta, tb, p));
   hn_count_launch();
   return HN_OK;
 }
@@ -610,6 +638,17 @@ extern "C" int hn_conv2d_bf16(const hn_conv_desc* d, void* stream) {
   // measured: pairs with multicast weights gain ~3 % on 256-wide tiles and lose elsewhere -> opt-in only
   int cs = d->cluster ? d->cluster : 1;
   HN_REQUIRE(cs == 1 || (cs == 2 && bn >= 64), "hn_conv2d_bf16: cluster=%d unsupported with block_n=%d", cs, bn);
+  // resident weights: the layer's whole weight slice stays in shared memory and only A tiles stream, when it is one
+  // narrow N tile whose weights fit next to >= 6 A stages and there are enough tiles per CTA to amortise the load
+  const int k_blocks_total = p.num_taps * p.cin_chunks;
+  const long long b_bytes = (long long)k_blocks_total * bn * BLOCK_K * 2;
+  bool rb = cs == 1 && p.n_tiles == 1 && bn <= 64 && b_bytes <= PIPE_BYTES_MAX - 6 * A_STAGE_BYTES &&
+            p.m_tiles >= 2 * hn_num_sms() && !(d->debug & 16);
+  if (rb) {
+    p.rb_b_bytes = (int)b_bytes;
+    int stages = (PIPE_BYTES_MAX - p.rb_b_bytes) / A_STAGE_BYTES;
+    p.rb_stages = stages > MAX_STAGES ? MAX_STAGES : stages;
+  }
   p.cout = d->cout;
   p.scale = d->scale;
   p.shift = d->shift;
@@ -645,6 +684,8 @@ extern "C" int hn_conv2d_bf16(const hn_conv_desc* d, void* stream) {
     p.ph_wp = (d->w + 1) / 2 + 2 * d->out_phase_halo;
     p.ph_stride = (long long)d->n * p.ph_hp * p.ph_wp * d->cout;
   }
+  p.dbg_shift = d->debug & 7;
+  p.dbg_base_offset = (d->debug >> 3) & 1;
   p.gn_stats = d->gn_stats;
   if (p.gn_stats) {
     HN_REQUIRE(d->gn_groups > 0 && d->cout % d->gn_groups == 0, "hn_conv2d_bf16: gn_groups");
@@ -672,18 +713,25 @@ extern "C" int hn_conv2d_bf16(const hn_conv_desc* d, void* stream) {
     if (rc) return rc;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (rb) {
+    switch (bn) {
+      case 64: return launch<64, 1, true>(ta, tb, p, st);
+      case 32: return launch<32, 1, true>(ta, tb, p, st);
+      default: return launch<16, 1, true>(ta, tb, p, st);
+    }
+  }
   if (cs == 2) {
     switch (bn) {
-      case 256: return launch<256, 2>(ta, tb, p, st);
-      case 128: return launch<128, 2>(ta, tb, p, st);
-      default: return launch<64, 2>(ta, tb, p, st);
+      case 256: return launch<256, 2, false>(ta, tb, p, st);
+      case 128: return launch<128, 2, false>(ta, tb, p, st);
+      default: return launch<64, 2, false>(ta, tb, p, st);
     }
   }
   switch (bn) {
-    case 256: return launch<256, 1>(ta, tb, p, st);
-    case 128: return launch<128, 1>(ta, tb, p, st);
-    case 64: return launch<64, 1>(ta, tb, p, st);
-    case 32: return launch<32, 1>(ta, tb, p, st);
-    default: return launch<16, 1>(ta, tb, p, st);
+    case 256: return launch<256, 1, false>(ta, tb, p, st);
+    case 128: return launch<128, 1, false>(ta, tb, p, st);
+    case 64: return launch<64, 1, false>(ta, tb, p, st);
+    case 32: return launch<32, 1, false>(ta, tb, p, st);
+    default: return launch<16, 1, false>(ta, tb, p, st);
   }
 }

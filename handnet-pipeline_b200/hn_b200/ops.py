@@ -167,7 +167,7 @@ def conv2d(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 1, d
            out_f32: Optional[torch.Tensor] = None, out_rows_per_image: int = 0, out_row_offset: int = 0,
            out_transpose_hw: bool = False, out_phase: Optional[PhaseAct] = None,
            gn_stats: Optional[torch.Tensor] = None, gn_groups: int = 0, block_n: int = 0, cluster: int = 0,
-           algo_k: int = 0):
+           algo_k: int = 0, debug: int = 0):
     """hn_conv2d_bf16.  x: Act (stride 1) or PhaseAct (stride 2).  relu: bool or (lo, hi) channel range."""
     d = ConvDesc()
     if isinstance(x, PhaseAct):
@@ -205,6 +205,7 @@ def conv2d(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 1, d
         d.gn_stats, d.gn_groups = gn_stats.data_ptr(), gn_groups
     d.block_n = block_n
     d.cluster = cluster
+    d.debug = debug
     if PROFILE is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()

@@ -91,6 +91,7 @@ typedef struct hn_conv_desc {
   int gn_groups;
   int block_n; /* 0 = choose automatically among 16/32/64/128/256 */
   int cluster; /* 0 = automatic; 1 = no cluster; 2 = CTA pairs along M that multicast the weight tile */
+  int debug;   /* 0 in production; bring-up experiments only */
 } hn_conv_desc;
 int hn_conv2d_bf16(const hn_conv_desc* desc, void* stream);
 

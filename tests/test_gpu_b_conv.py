@@ -62,6 +62,10 @@ CASES = [
     ("cs2_1x1_512_2048_bn256", 3, 11, 11, 512, 2048, 1, 1, 1, 1, 256, 2),
     ("cs2_3x3_s2_128_256", 2, 25, 33, 128, 256, 3, 2, 1, 1, 128, 2),
     ("cs2_3x3_256_256_auto_big", 4, 100, 136, 256, 256, 3, 1, 1, 1, 0, 0),
+    # resident weights (one narrow N tile, >= 2 tiles per SM): layer1-like 3x3 and stem-like 1x1 GEMM
+    ("rb_3x3_64_64_layer1", 2, 200, 272, 64, 64, 3, 1, 1, 1, 0, 0),
+    ("rb_1x1_256_64_stem", 1, 400, 544, 256, 64, 1, 1, 1, 0, 0, 0),
+    ("rb_3x3_256_5_headout", 4, 100, 136, 256, 5, 3, 1, 1, 1, 0, 0),
 ]
 
 
