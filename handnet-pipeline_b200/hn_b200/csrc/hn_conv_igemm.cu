@@ -56,7 +56,7 @@ struct ConvParams {
   double* gn_stats;
   int gn_groups, gn_group_size;
   int rb_stages, rb_b_bytes;        // resident-weights mode: A stages and bytes of the weight slice
-  int dbg_shift, dbg_base_offset;   // bring-up experiment: A box loaded dbg_shift rows early, descriptor offset back
+  int dbg_shift, dbg_base_offset, dbg_flags;   // bring-up experiment: A box loaded dbg_shift rows early, descriptor offset back
 };
 
 __device__ __forceinline__ void hn_epi_bar_sync() {   // named barrier 1: the epilogue warps only
@@ -75,8 +75,12 @@ constexpr int PIPE_BYTES_MAX = 196608;                                        //
 template <int BN>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  // k-blocks (64 channels of one tap) per pipeline stage.  The single-thread producer and MMA loops pay ~220 cycles
+  // per mbarrier wait and ~70 per commit (tools/mma_issue_bench.cu); a 256-wide tile has 512 cycles of tensor work per
+  // k-block to hide that, narrower tiles do not, so they move two k-blocks per barrier round trip.
+  static constexpr int KG = (BN >= 256) ? 1 : 2;
+  static constexpr int STAGE_BYTES = KG * (A_STAGE_BYTES + B_STAGE_BYTES);
+  static constexpr int STAGES = PIPE_BYTES_MAX / STAGE_BYTES > MAX_STAGES ? MAX_STAGES : PIPE_BYTES_MAX / STAGE_BYTES;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + HDR_PAD + STAGES * STAGE_BYTES;
   static constexpr int SMEM_BYTES_RB = 1024 + HDR_PAD + PIPE_BYTES_MAX;
@@ -101,15 +105,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* b_full = tmem_empty + 2;                     // resident weights have landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  const int k_blocks = p.num_taps * p.cin_chunks;
   uint8_t* pipe = smem_hdr + HDR_PAD;                    // 1024-aligned operand area
   // RB: [weights: k_blocks x (BN x 128 B)] [A stages]; otherwise STAGES x [A | B]
   const int num_stages = RB ? p.rb_stages : C::STAGES;
-  const int stage_bytes = RB ? A_STAGE_BYTES : C::STAGE_BYTES;
+  constexpr int KG = C::KG;
+  const int stage_bytes = RB ? KG * A_STAGE_BYTES : C::STAGE_BYTES;
+  const int k_steps = (k_blocks + KG - 1) / KG;
   uint8_t* smem = pipe + (RB ? p.rb_b_bytes : 0);        // base of the stage ring
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int k_blocks = p.num_taps * p.cin_chunks;
   // tile schedule: "super tiles" of CS consecutive M tiles x one N tile, N fastest, strided over the clusters
   const int cta_rank = (CS > 1) ? (int)hn_cluster_ctarank() : 0;
   const int cluster_id = blockIdx.x / CS;
@@ -156,20 +162,34 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       for (int st = cluster_id; st < num_super; st += num_clusters) {
         const int m0 = ((st / p.n_tiles) * CS + cta_rank) * BLOCK_M;
         const int n0 = (st % p.n_tiles) * BN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          const int tap = kb / p.cin_chunks;
-          const int cc = kb - tap * p.cin_chunks;
+        int tap = 0, cc = 0;                                   // k-block kb = tap * cin_chunks + cc
+        for (int step = 0; step < k_steps; ++step) {
+          const int nk = (k_blocks - step * KG < KG) ? k_blocks - step * KG : KG;
           hn_mbar_wait(&empty_bar[stage], phase ^ 1);
-          hn_mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-          uint8_t* sa = smem + stage * stage_bytes;
-          hn_tma_load_3d(sa, &tm_a, &full_bar[stage], cc * BLOCK_K, m0 + p.tap_shift[tap] - p.dbg_shift, p.tap_phase[tap]);
-          if constexpr (RB) {
-          } else if constexpr (CS == 1) {
-            hn_tma_load_2d(sa + A_STAGE_BYTES, &tm_b, &full_bar[stage], kb * BLOCK_K, n0);
+          if (p.dbg_flags & 8) {                               // timing experiment: no loads at all
+            hn_mbar_arrive(&full_bar[stage]);
           } else {
-            constexpr int SLICE = BN / CS;   // weight rows this CTA fetches for the whole cluster
-            hn_tma_load_2d_mcast(sa + A_STAGE_BYTES + cta_rank * SLICE * BLOCK_K * 2, &tm_b, &full_bar[stage],
-                                 kb * BLOCK_K, n0 + cta_rank * SLICE, (uint16_t)((1u << CS) - 1u));
+            const uint32_t kb_bytes = RB ? A_STAGE_BYTES : (A_STAGE_BYTES + C::B_STAGE_BYTES);
+            hn_mbar_expect_tx(&full_bar[stage], nk * kb_bytes);
+            uint8_t* sa = smem + stage * stage_bytes;
+#pragma unroll
+            for (int g = 0; g < KG; ++g) {
+              if (g < nk) {
+                const int kb = step * KG + g;
+                hn_tma_load_3d(sa + g * A_STAGE_BYTES, &tm_a, &full_bar[stage], cc * BLOCK_K,
+                               m0 + p.tap_shift[tap] - p.dbg_shift, p.tap_phase[tap]);
+                if constexpr (RB) {
+                } else if constexpr (CS == 1) {
+                  hn_tma_load_2d(sa + KG * A_STAGE_BYTES + g * C::B_STAGE_BYTES, &tm_b, &full_bar[stage], kb * BLOCK_K, n0);
+                } else {
+                  constexpr int SLICE = BN / CS;   // weight rows this CTA fetches for the whole cluster
+                  hn_tma_load_2d_mcast(sa + KG * A_STAGE_BYTES + g * C::B_STAGE_BYTES + cta_rank * SLICE * BLOCK_K * 2,
+                                       &tm_b, &full_bar[stage], kb * BLOCK_K, n0 + cta_rank * SLICE,
+                                       (uint16_t)((1u << CS) - 1u));
+                }
+                if (++cc == p.cin_chunks) { cc = 0; ++tap; }
+              }
+            }
           }
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
@@ -182,31 +202,58 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      int st = cluster_id;
       if constexpr (RB) hn_mbar_wait(b_full, 0);
-      for (int st = cluster_id; st < num_super; st += num_clusters, ++it) {
-        const int buf = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        hn_mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
+      if (st < num_super) {                                    // prime: first accumulator buffer and first stage
+        hn_mbar_wait(&tmem_empty[0], 1);
+        hn_mbar_wait(&full_bar[0], 0);
         hn_tc_fence_after();
+      }
+      for (; st < num_super; st += num_clusters, ++it) {
+        const int buf = it & 1;
         const uint32_t d_tmem = tmem_base + buf * BN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          hn_mbar_wait(&full_bar[stage], phase);
-          hn_tc_fence_after();
+        const bool has_next_tile = st + num_clusters < num_super;
+        for (int step = 0; step < k_steps; ++step) {
+          const int nk = (k_blocks - step * KG < KG) ? k_blocks - step * KG : KG;
           const uint32_t a_addr = hn_smem_u32(smem + stage * stage_bytes);
-          const uint64_t da = hn_umma_smem_desc(a_addr + p.dbg_shift * 128) |
-                              (uint64_t(p.dbg_base_offset ? (p.dbg_shift & 7) : 0) << 49);
-          const uint64_t db = hn_umma_smem_desc(RB ? hn_smem_u32(pipe + kb * C::B_STAGE_BYTES) : a_addr + A_STAGE_BYTES);
+          if (!(p.dbg_flags & 4)) {                            // (timing experiment: bit 2 skips the MMAs)
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            // +32 bytes per K=16 step inside the 128-byte swizzle span: start-address field += 2
-            hn_umma_bf16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0);
+            for (int g = 0; g < KG; ++g) {
+              if (g < nk) {
+                const int kb = step * KG + g;
+                const uint64_t da = hn_umma_smem_desc(a_addr + g * A_STAGE_BYTES + p.dbg_shift * 128) |
+                                    (uint64_t(p.dbg_base_offset ? (p.dbg_shift & 7) : 0) << 49);
+                const uint64_t db = hn_umma_smem_desc(RB ? hn_smem_u32(pipe + kb * C::B_STAGE_BYTES)
+                                                         : a_addr + KG * A_STAGE_BYTES + g * C::B_STAGE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / 16; ++k) {
+                  // +32 bytes per K=16 step inside the 128-byte swizzle span: start-address field += 2
+                  hn_umma_bf16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (step | g | k) != 0);
+                }
+              }
+            }
+          }
+          const bool last = step == k_steps - 1;
+          if (last) hn_umma_commit(&tmem_full[buf]);           // accumulator complete -> epilogue
+          // Look ahead while the tensor pipe chews on what was just issued: wait for the NEXT stage (and, at a tile
+          // boundary, the next accumulator buffer) before releasing this one.
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == num_stages) { nstage = 0; nphase ^= 1; }
+          if (!last) {
+            hn_mbar_wait(&full_bar[nstage], nphase);
+            hn_tc_fence_after();
+          } else if (has_next_tile) {
+            hn_mbar_wait(&tmem_empty[(it + 1) & 1], (((it + 1) >> 1) & 1) ^ 1);
+            hn_mbar_wait(&full_bar[nstage], nphase);
+            hn_tc_fence_after();
           }
           // frees the smem slot (in every CTA of the cluster) once these MMAs have read it
           if constexpr (CS == 1) hn_umma_commit(&empty_bar[stage]);
           else hn_umma_commit_mcast(&empty_bar[stage], (uint16_t)((1u << CS) - 1u));
-          if (++stage == num_stages) { stage = 0; phase ^= 1; }
+          stage = nstage;
+          phase = nphase;
         }
-        hn_umma_commit(&tmem_full[buf]);       // accumulator complete -> epilogue
       }
     }
   } else {
@@ -296,7 +343,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + buf * BN;
 
 #pragma unroll 1
-      for (int c0 = c_first; c0 < (idle_half ? 0 : BN); c0 += STEP) {
+      for (int c0 = c_first; c0 < ((idle_half || (p.dbg_flags & 2)) ? 0 : BN); c0 += STEP) {
         uint4 res_cur[CHUNK / 8];
 #pragma unroll
         for (int j = 0; j < CHUNK / 8; ++j) res_cur[j] = res_next[j];
@@ -364,7 +411,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         uint32_t packed[CHUNK / 2];
 #pragma unroll
         for (int j = 0; j < CHUNK; j += 2) packed[j / 2] = hn_pack_bf16(v[j], v[j + 1]);
-        if (interior) {
+        if (interior && !(p.dbg_flags & 1)) {
           __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + cbase;
           if (cbase + CHUNK <= p.cout && (p.cout & 7) == 0) {
 #pragma unroll
@@ -642,11 +689,11 @@ extern "C" int hn_conv2d_bf16(const hn_conv_desc* d, void* stream) {
   // narrow N tile whose weights fit next to >= 6 A stages and there are enough tiles per CTA to amortise the load
   const int k_blocks_total = p.num_taps * p.cin_chunks;
   const long long b_bytes = (long long)k_blocks_total * bn * BLOCK_K * 2;
-  bool rb = cs == 1 && p.n_tiles == 1 && bn <= 64 && b_bytes <= PIPE_BYTES_MAX - 6 * A_STAGE_BYTES &&
+  bool rb = cs == 1 && p.n_tiles == 1 && bn <= 64 && b_bytes <= PIPE_BYTES_MAX - 3 * 2 * A_STAGE_BYTES &&
             p.m_tiles >= 2 * hn_num_sms() && !(d->debug & 16);
   if (rb) {
     p.rb_b_bytes = (int)b_bytes;
-    int stages = (PIPE_BYTES_MAX - p.rb_b_bytes) / A_STAGE_BYTES;
+    int stages = (PIPE_BYTES_MAX - p.rb_b_bytes) / (2 * A_STAGE_BYTES);   // KG = 2 A tiles per stage for BN <= 64
     p.rb_stages = stages > MAX_STAGES ? MAX_STAGES : stages;
   }
   p.cout = d->cout;
@@ -684,6 +731,7 @@ extern "C" int hn_conv2d_bf16(const hn_conv_desc* d, void* stream) {
     p.ph_wp = (d->w + 1) / 2 + 2 * d->out_phase_halo;
     p.ph_stride = (long long)d->n * p.ph_hp * p.ph_wp * d->cout;
   }
+  p.dbg_flags = d->debug >> 6;     // bit0: no epilogue stores, bit1: no epilogue work at all (timing experiments)
   p.dbg_shift = d->debug & 7;
   p.dbg_base_offset = (d->debug >> 3) & 1;
   p.gn_stats = d->gn_stats;
