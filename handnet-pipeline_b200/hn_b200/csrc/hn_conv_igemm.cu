@@ -56,7 +56,7 @@ struct ConvParams {
   double* gn_stats;
   int gn_groups, gn_group_size;
   int rb_stages, rb_b_bytes;        // resident-weights mode: A stages and bytes of the weight slice
-  int dbg_shift, dbg_base_offset, dbg_flags;   // bring-up experiment: A box loaded dbg_shift rows early, descriptor offset back
+  int dbg_shift, dbg_base_offset, dbg_flags, lookahead;   // bring-up experiment: A box loaded dbg_shift rows early, descriptor offset back
 };
 
 __device__ __forceinline__ void hn_epi_bar_sync() {   // named barrier 1: the epilogue warps only
@@ -235,11 +235,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           }
           const bool last = step == k_steps - 1;
           if (last) hn_umma_commit(&tmem_full[buf]);           // accumulator complete -> epilogue
-          // Look ahead while the tensor pipe chews on what was just issued: wait for the NEXT stage (and, at a tile
-          // boundary, the next accumulator buffer) before releasing this one.
           int nstage = stage + 1;
           uint32_t nphase = phase;
           if (nstage == num_stages) { nstage = 0; nphase ^= 1; }
+          // release first (keeps the producer fed), then wait for the next stage / accumulator buffer
+          if (!p.lookahead) {
+            if constexpr (CS == 1) hn_umma_commit(&empty_bar[stage]);
+            else hn_umma_commit_mcast(&empty_bar[stage], (uint16_t)((1u << CS) - 1u));
+          }
           if (!last) {
             hn_mbar_wait(&full_bar[nstage], nphase);
             hn_tc_fence_after();
@@ -248,9 +251,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             hn_mbar_wait(&full_bar[nstage], nphase);
             hn_tc_fence_after();
           }
-          // frees the smem slot (in every CTA of the cluster) once these MMAs have read it
-          if constexpr (CS == 1) hn_umma_commit(&empty_bar[stage]);
-          else hn_umma_commit_mcast(&empty_bar[stage], (uint16_t)((1u << CS) - 1u));
+          if (p.lookahead) {                                   // experiment: release after the look-ahead wait
+            if constexpr (CS == 1) hn_umma_commit(&empty_bar[stage]);
+            else hn_umma_commit_mcast(&empty_bar[stage], (uint16_t)((1u << CS) - 1u));
+          }
           stage = nstage;
           phase = nphase;
         }
@@ -731,7 +735,8 @@ extern "C" int hn_conv2d_bf16(const hn_conv_desc* d, void* stream) {
     p.ph_wp = (d->w + 1) / 2 + 2 * d->out_phase_halo;
     p.ph_stride = (long long)d->n * p.ph_hp * p.ph_wp * d->cout;
   }
-  p.dbg_flags = d->debug >> 6;     // bit0: no epilogue stores, bit1: no epilogue work at all (timing experiments)
+  p.lookahead = (d->debug >> 10) & 1;
+  p.dbg_flags = (d->debug >> 6) & 15;     // bit0: no epilogue stores, bit1: no epilogue work at all (timing experiments)
   p.dbg_shift = d->debug & 7;
   p.dbg_base_offset = (d->debug >> 3) & 1;
   p.gn_stats = d->gn_stats;

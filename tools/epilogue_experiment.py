@@ -26,6 +26,7 @@ def time_conv(n, h, w, cin, cout, k, debug, block_n=0, res=False, reps=20):
 NOEPI = 128
 for name, shp in (("layer1 64->64 3x3 @200x272", (8, 200, 272, 64, 64, 3)), ("layer2 128->128 3x3 @100x136", (8, 100, 136, 128, 128, 3)),
                   ("P3 256->256 3x3 @100x136", (8, 100, 136, 256, 256, 3))):
-    for dbg, what in ((0, "full"), (NOEPI | 16, "no epilogue"), (NOEPI | 16 | 256, "no epilogue, no MMA"),
-                      (NOEPI | 16 | 512, "no epilogue, no TMA"), (NOEPI | 16 | 256 | 512, "no epilogue, no MMA, no TMA")):
+    for dbg, what in ((0, "full"), (1024, "full, release after lookahead"), (NOEPI | 16, "no epilogue"),
+                      (NOEPI | 16 | 1024, "no epilogue, release after la"), (NOEPI | 16 | 512, "no epilogue, no TMA"),
+                      (NOEPI | 16 | 512 | 1024, "no epi, no TMA, rel. after la")):
         print(f"{name:32s} {what:30s} {time_conv(*shp, debug=dbg):8.1f} us", flush=True)
