@@ -95,7 +95,7 @@ class ResNetBackBone(nn.Module):
             self.model.conv1 = nn.Conv2d(4, 64, kernel_size=7, stride=2, padding=3, bias=False)
 
 
-class A2JModel(nn.Module):
+class A2JModel(runtime.WeightsEpochMixin, nn.Module):
     """A2JModel(num_classes, crop_height, crop_width, is_3D=True, is_RGBD=False, spatial_factor=0.5)."""
 
     def __init__(self, num_classes, crop_height, crop_width, is_3D=True, is_RGBD=False, spatial_factor=0.5):

@@ -171,7 +171,7 @@ class FCOSHead(nn.Module):
 
 
 # --------------------------------------------------------------------------------------------------
-class FCOS(nn.Module):
+class FCOS(runtime.WeightsEpochMixin, nn.Module):
     """FCOS(num_classes, ext=True, min_size=800, max_size=1333, ...) -- reference fcos.py:455-514.
 
     ``forward(images: List[Tensor[3,H,W]], targets=None) -> List[Dict[str, Tensor]]`` with keys ``boxes``,

@@ -7,6 +7,28 @@
 #include "../handnet-pipeline_b200/hn_b200/csrc/hn_common.cuh"
 void hn_set_error(const char*, ...) {}
 
+__device__ __forceinline__ void wait_ptx(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}"
+      ::"r"(hn_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void wait_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(hn_smem_u32(bar)), "r"(parity) : "memory");
+  }
+}
+
+
 template <int N>
 __global__ void __launch_bounds__(128, 1) bench(int iters, int mmas_per_commit, int mode, long long* out) {
   extern __shared__ uint8_t raw[];
@@ -14,7 +36,7 @@ __global__ void __launch_bounds__(128, 1) bench(int iters, int mmas_per_commit, 
   __shared__ uint64_t bar[8];
   __shared__ uint32_t slot;
   for (int i = threadIdx.x; i < (16384 + N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
-  if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) hn_mbar_init(&bar[i], mode == 0 ? 1 : iters); hn_mbar_init_fence(); }
+  if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) hn_mbar_init(&bar[i], (mode == 0 || mode >= 3) ? 1 : iters); hn_mbar_init_fence(); }
   if (threadIdx.x < 32) hn_tmem_alloc<256>(&slot);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   hn_tc_fence_before();
@@ -33,6 +55,19 @@ __global__ void __launch_bounds__(128, 1) bench(int iters, int mmas_per_commit, 
         for (int k = 0; k < mmas_per_commit; ++k) hn_umma_bf16(tmem, da + 2 * (k & 3), db + 2 * (k & 3), idesc, 1);
         hn_umma_commit(&bar[b]);
       }
+    } else if (mode == 3 || mode == 4) {   // ring of 8 with a PTX-only try_wait loop (3) / test_wait (4)
+      for (int it = 0; it < iters; ++it) {
+        const int b = it & 7;
+        if (it >= 8) { if (mode == 3) wait_ptx(&bar[b], ((it >> 3) - 1) & 1); else wait_test(&bar[b], ((it >> 3) - 1) & 1); }
+        for (int k = 0; k < mmas_per_commit; ++k) hn_umma_bf16(tmem, da + 2 * (k & 3), db + 2 * (k & 3), idesc, 1);
+        hn_umma_commit(&bar[b]);
+      }
+    } else if (mode == 5) {   // waits only (barriers completed by plain arrives), no MMAs: cost of a satisfied wait
+      for (int it = 0; it < iters; ++it) {
+        const int b = it & 7;
+        if (it >= 8) hn_mbar_wait(&bar[b], ((it >> 3) - 1) & 1);
+        hn_mbar_arrive(&bar[b]);
+      }
     } else if (mode == 1) {   // commits but never wait inside the loop (one barrier expecting `iters` arrivals)
       for (int it = 0; it < iters; ++it) {
         for (int k = 0; k < mmas_per_commit; ++k) hn_umma_bf16(tmem, da + 2 * (k & 3), db + 2 * (k & 3), idesc, 1);
@@ -44,7 +79,7 @@ __global__ void __launch_bounds__(128, 1) bench(int iters, int mmas_per_commit, 
       for (int it = 0; it < iters; ++it) hn_umma_commit(&bar[0]);
     }
     long long t1 = clock64();
-    if (mode == 0) { for (int it = iters - 8; it < iters; ++it) hn_mbar_wait(&bar[it & 7], (it >> 3) & 1); }
+    if (mode == 0 || mode >= 3) { for (int it = iters - 8; it < iters; ++it) hn_mbar_wait(&bar[it & 7], (it >> 3) & 1); }
     else hn_mbar_wait(&bar[0], 0);
     long long t2 = clock64();
     out[0] = t1 - t0;
@@ -68,8 +103,8 @@ void run(int iters, int mpc, int mode) {
 }
 
 int main() {
-  for (int mode : {0, 1, 2})
-    for (int mpc : {1, 4, 8}) {
+  for (int mode : {0, 3, 4, 5})
+    for (int mpc : {1, 4}) {
       run<64>(2000, mpc, mode);
       run<256>(2000, mpc, mode);
     }
