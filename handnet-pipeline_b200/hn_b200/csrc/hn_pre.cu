@@ -43,15 +43,14 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p, uint
     bilinear_axis(y, ih, oh, y0, y1, ly0, ly1);
     bilinear_axis(x, iw, ow, x0, x1, lx0, lx1);
     float v[3];
+    const size_t o00 = (size_t)y0 * iw + x0, o01 = (size_t)y0 * iw + x1, o10 = (size_t)y1 * iw + x0, o11 = (size_t)y1 * iw + x1;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float* pl = p.img[b] + (size_t)c * ih * iw;
-      const float m = p.mean[c], s = p.stdv[c];
-      const float p00 = (__ldg(pl + (size_t)y0 * iw + x0) - m) / s;
-      const float p01 = (__ldg(pl + (size_t)y0 * iw + x1) - m) / s;
-      const float p10 = (__ldg(pl + (size_t)y1 * iw + x0) - m) / s;
-      const float p11 = (__ldg(pl + (size_t)y1 * iw + x1) - m) / s;
-      v[c] = ly0 * (lx0 * p00 + lx1 * p01) + ly1 * (lx0 * p10 + lx1 * p11);
+      // the bilinear weights sum to one, so normalising after the interpolation equals torchvision's
+      // normalise-then-resize up to fp32 rounding (the result is rounded to bf16 anyway): 1 division instead of 4
+      const float t = ly0 * (lx0 * __ldg(pl + o00) + lx1 * __ldg(pl + o01)) + ly1 * (lx0 * __ldg(pl + o10) + lx1 * __ldg(pl + o11));
+      v[c] = (t - p.mean[c]) / p.stdv[c];
     }
     outv.x = hn_pack_bf16(v[0], v[1]);
     outv.y = hn_pack_bf16(v[2], 0.f);
@@ -118,14 +117,11 @@ __device__ __forceinline__ uint32_t bf162_max(uint32_t a, uint32_t b) {
 __global__ void __launch_bounds__(256)
 maxpool3x3s2_kernel(const uint4* __restrict__ in, int n, int h, int w, int c8, int oh, int ow, int halo,
                     uint4* __restrict__ out) {
-  const long long total = (long long)n * oh * ow * c8;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= total) return;
-  const int cg = (int)(gid % c8);
-  const long long pix = gid / c8;
-  const int ox = (int)(pix % ow);
-  const int oy = (int)((pix / ow) % oh);
-  const int img = (int)(pix / ((long long)ow * oh));
+  // grid (ceil(ow*c8 / 256), oh, n): consecutive threads = consecutive channel groups of consecutive pixels
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ow * c8) return;
+  const int ox = t / c8, cg = t - ox * c8;
+  const int oy = blockIdx.y, img = blockIdx.z;
   const uint32_t NEG = 0xff80ff80u;   // (-inf, -inf) in bf16
   uint4 m = make_uint4(NEG, NEG, NEG, NEG);
 #pragma unroll
@@ -256,10 +252,9 @@ extern "C" int hn_maxpool3x3s2(const void* in, int n, int h, int w, int c, void*
   HN_REQUIRE(in && out, "hn_maxpool3x3s2: null pointer");
   HN_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && out_halo >= 0, "hn_maxpool3x3s2: bad shape (c %% 8 == 0)");
   const int oh = (h + 1) / 2, ow = (w + 1) / 2;   // floor((h + 2 - 3)/2) + 1
-  const long long total = (long long)n * oh * ow * (c / 8);
-  const long long blocks = (total + 255) / 256;
-  HN_REQUIRE(blocks < (1ll << 31), "hn_maxpool3x3s2: too large");
-  maxpool3x3s2_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  HN_REQUIRE(oh <= 65535 && n <= 65535, "hn_maxpool3x3s2: too large");
+  dim3 grid(hn_div_up(ow * (c / 8), 256), oh, n);
+  maxpool3x3s2_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint4*>(in), n, h, w, c / 8, oh, ow, out_halo, reinterpret_cast<uint4*>(out));
   hn_count_launch();
   HN_LAUNCH_CHECK();

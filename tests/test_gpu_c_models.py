@@ -225,3 +225,27 @@ def test_mixed_frame_sizes_eager_path(fcos_small):
         _, emu = fcos_oracle.fcos_forward(sd, imgs, 3, False, 256, 448, emulate_bf16=True, return_taps=True)
     assert ho["cls_logits"].shape == emu["head"]["cls_logits"].shape
     assert rel_to_max(ho["cls_logits"], emu["head"]["cls_logits"]) < 5e-2
+
+
+def test_fcos_1080p_canvas_config5():
+    """BASELINE.json config 5 geometry: 1920x1080 -> 749x1333 -> canvas 768x1344, 21168 locations."""
+    from fcos_utils.fcos import FCOS
+    sd = synth.fcos_state_dict(3, False, seed=0)
+    m = FCOS(3, ext=False).eval()
+    m.load_state_dict(sd)
+    m.cuda()
+    g = torch.Generator().manual_seed(17)
+    imgs = [torch.rand(3, 1080, 1920, generator=g)]
+    with torch.inference_mode():
+        ho = m.head_outputs([i.cuda() for i in imgs])
+        out = m.forward_device([i.cuda() for i in imgs])
+        _, emu = fcos_oracle.fcos_forward(sd, imgs, 3, False, emulate_bf16=True, return_taps=True)
+    assert tuple(emu["canvas"].shape[-2:]) == (768, 1344) and ho["cls_logits"].shape == (1, 21168, 3)
+    for k in ("cls_logits", "bbox_regression", "bbox_ctrness"):
+        assert rel_to_max(ho[k], emu["head"][k]) < 5e-2, k
+    n, k = int(out["cand_count"][0]), int(out["keep_count"][0])
+    box, score, label = (out["cand"][x][0, :n].cpu() for x in ("box", "score", "label"))
+    keep_ref = nms_oracle.batched_nms(box.numpy(), score.numpy(), label.numpy(), 0.3)
+    assert np.array_equal(out["keep"][0, :k].cpu().numpy(), keep_ref)
+    # boxes are reported in original 1920x1080 pixels
+    assert torch.equal(out["boxes"][0, :k].cpu(), fcos_oracle.resize_boxes(box[keep_ref], (749, 1333), (1080, 1920)))
