@@ -18,6 +18,8 @@
 
 #include <stdlib.h>
 
+#include <vector>
+
 namespace {
 
 __device__ __forceinline__ void hn_epi_bar_sync();
@@ -89,22 +91,24 @@ struct Cfg {
 // CS = thread-block cluster size along M: the CS CTAs of a cluster work on CS consecutive M tiles of the same N
 // tile in lock step; each loads 1/CS of the B (weight) tile and multicasts it to all of them, so the weights
 // cross the L2 -> SM fabric once per cluster instead of once per CTA.
+// ---------------------------------------------------------------------------------------------------------------
+// One convolution's worth of work for the calling warp (role by warp index).  `first_tile` / `tile_stride` select this
+// CTA's (super) tiles; `stage`, `phase`, `it` are the calling thread's pipeline state and persist across calls, so a
+// persistent multi-layer kernel can chain convolutions through the same barriers and TMEM buffers.
+// ---------------------------------------------------------------------------------------------------------------
 template <int BN, int CS, bool RB>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                  const ConvParams p) {
+__device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CUtensorMap* tm_b_ptr, const ConvParams& p,
+                                           uint8_t* smem_hdr, const uint32_t tmem_base, const int first_tile,
+                                           const int tile_stride, int& stage, uint32_t& phase, int& it) {
   using C = Cfg<BN>;
-  static_assert(CS == 1 || (BN / CS) % 8 == 0, "B slices must keep whole 8-row swizzle atoms");
-  static_assert(!(RB && CS > 1), "resident weights are per CTA");
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem_hdr = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const CUtensorMap& tm_a = *tm_a_ptr;
+  const CUtensorMap& tm_b = *tm_b_ptr;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_hdr);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + MAX_STAGES;
   uint64_t* tmem_full = bars + 2 * MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* b_full = tmem_empty + 2;                     // resident weights have landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
   const int k_blocks = p.num_taps * p.cin_chunks;
   uint8_t* pipe = smem_hdr + HDR_PAD;                    // 1024-aligned operand area
   // RB: [weights: k_blocks x (BN x 128 B)] [A stages]; otherwise STAGES x [A | B]
@@ -118,48 +122,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   const int lane = threadIdx.x & 31;
   // tile schedule: "super tiles" of CS consecutive M tiles x one N tile, N fastest, strided over the clusters
   const int cta_rank = (CS > 1) ? (int)hn_cluster_ctarank() : 0;
-  const int cluster_id = blockIdx.x / CS;
-  const int num_clusters = gridDim.x / CS;
   const int num_super = ((p.m_tiles + CS - 1) / CS) * p.n_tiles;
-
-  if (threadIdx.x == 0) {
-    hn_tma_prefetch_desc(&tm_a);
-    hn_tma_prefetch_desc(&tm_b);
-    for (int s = 0; s < num_stages; ++s) {
-      hn_mbar_init(&full_bar[s], 1);
-      hn_mbar_init(&empty_bar[s], CS);   // every CTA of the cluster releases the slot (its peers write into it)
-    }
-    hn_mbar_init(b_full, 1);
-    for (int b = 0; b < 2; ++b) {
-      hn_mbar_init(&tmem_full[b], 1);
-      hn_mbar_init(&tmem_empty[b], EPI_WARPS);   // one arrive per epilogue warp
-    }
-    hn_mbar_init_fence();
-  }
-  if (warp == 1) hn_tmem_alloc<C::TMEM_COLS>(tmem_slot);
-  hn_tc_fence_before();
-  __syncthreads();
-  if constexpr (CS > 1) hn_cluster_sync();   // peers' barriers must exist before anyone signals them
-  hn_tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may run
-  // while the previous kernel of the stream is still draining; global memory is touched only after the wait.
-  // The early trigger lets the next kernel do the same under this one.
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
       if constexpr (RB) {
         // the layer's whole weight slice (n_tiles == 1), once per CTA
         hn_mbar_expect_tx(b_full, (uint32_t)p.rb_b_bytes);
         for (int kb = 0; kb < k_blocks; ++kb)
           hn_tma_load_2d(pipe + kb * C::B_STAGE_BYTES, &tm_b, b_full, kb * BLOCK_K, 0);
       }
-      for (int st = cluster_id; st < num_super; st += num_clusters) {
+      for (int st = first_tile; st < num_super; st += tile_stride) {
         const int m0 = ((st / p.n_tiles) * CS + cta_rank) * BLOCK_M;
         const int n0 = (st % p.n_tiles) * BN;
         int tap = 0, cc = 0;                                   // k-block kb = tap * cin_chunks + cc
@@ -199,20 +173,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
       constexpr uint32_t idesc = hn_umma_idesc_bf16(BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      int st = cluster_id;
+      int st = first_tile;
       if constexpr (RB) hn_mbar_wait(b_full, 0);
-      if (st < num_super) {                                    // prime: first accumulator buffer and first stage
-        hn_mbar_wait(&tmem_empty[0], 1);
-        hn_mbar_wait(&full_bar[0], 0);
+      if (st < num_super) {                                    // prime: this tile's accumulator buffer and first stage
+        hn_mbar_wait(&tmem_empty[it & 1], ((it >> 1) & 1) ^ 1);
+        hn_mbar_wait(&full_bar[stage], phase);
         hn_tc_fence_after();
       }
-      for (; st < num_super; st += num_clusters, ++it) {
+      for (; st < num_super; st += tile_stride, ++it) {
         const int buf = it & 1;
         const uint32_t d_tmem = tmem_base + buf * BN;
-        const bool has_next_tile = st + num_clusters < num_super;
+        const bool has_next_tile = st + tile_stride < num_super;
         for (int step = 0; step < k_steps; ++step) {
           const int nk = (k_blocks - step * KG < KG) ? k_blocks - step * KG : KG;
           const uint32_t a_addr = hn_smem_u32(smem + stage * stage_bytes);
@@ -276,8 +247,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       for (int i = threadIdx.x - 64; i < gn_vals; i += EPI_THREADS) gn_acc[i] = 0.f;
       hn_epi_bar_sync();
     }
-    int it = 0;
-    for (int st = cluster_id; st < num_super; st += num_clusters, ++it) {
+    for (int st = first_tile; st < num_super; st += tile_stride, ++it) {
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m0 = ((st / p.n_tiles) * CS + cta_rank) * BLOCK_M;
@@ -518,13 +488,137 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     }
   }
 
+}
+
+// Barrier init, TMEM allocation.  Returns the TMEM base address.
+template <int BN, int CS>
+__device__ __forceinline__ uint32_t conv_prologue(uint8_t* smem_hdr, int num_stages, const CUtensorMap* pf_a,
+                                                  const CUtensorMap* pf_b) {
+  using C = Cfg<BN>;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_hdr);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + MAX_STAGES;
+  uint64_t* tmem_full = bars + 2 * MAX_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* b_full = tmem_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  if (threadIdx.x == 0) {
+    if (pf_a) hn_tma_prefetch_desc(pf_a);
+    if (pf_b) hn_tma_prefetch_desc(pf_b);
+    for (int s = 0; s < num_stages; ++s) {
+      hn_mbar_init(&full_bar[s], 1);
+      hn_mbar_init(&empty_bar[s], CS);   // every CTA of the cluster releases the slot (its peers write into it)
+    }
+    hn_mbar_init(b_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      hn_mbar_init(&tmem_full[b], 1);
+      hn_mbar_init(&tmem_empty[b], EPI_WARPS);   // one arrive per epilogue warp
+    }
+    hn_mbar_init_fence();
+  }
+  if ((threadIdx.x >> 5) == 1) hn_tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  hn_tc_fence_before();
+  __syncthreads();
+  if constexpr (CS > 1) hn_cluster_sync();   // peers' barriers must exist before anyone signals them
+  hn_tc_fence_after();
+  return *tmem_slot;
+}
+
+template <int BN, int CS>
+__device__ __forceinline__ void conv_teardown(uint32_t tmem_base) {
+  using C = Cfg<BN>;
   hn_tc_fence_before();
   __syncthreads();
   if constexpr (CS > 1) hn_cluster_sync();   // no CTA may retire while a peer can still signal its barriers
-  if (warp == 1) {
+  if ((threadIdx.x >> 5) == 1) {
     hn_tc_fence_after();
     hn_tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
+}
+
+// CS = thread-block cluster size along M: the CS CTAs of a cluster work on CS consecutive M tiles of the same N
+// tile in lock step; each loads 1/CS of the B (weight) tile and multicasts it to all of them.  RB = the layer's
+// whole weight slice stays resident in shared memory.
+template <int BN, int CS, bool RB>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                  const __grid_constant__ ConvParams p) {
+  static_assert(CS == 1 || (BN / CS) % 8 == 0, "B slices must keep whole 8-row swizzle atoms");
+  static_assert(!(RB && CS > 1), "resident weights are per CTA");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem_hdr = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t tmem_base = conv_prologue<BN, CS>(smem_hdr, RB ? p.rb_stages : Cfg<BN>::STAGES, &tm_a, &tm_b);
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may run
+  // while the previous kernel of the stream is still draining; global memory is touched only after the wait.
+  // The early trigger lets the next kernel do the same under this one.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  int stage = 0, it = 0;
+  uint32_t phase = 0;
+  conv_roles<BN, CS, RB>(&tm_a, &tm_b, p, smem_hdr, tmem_base, blockIdx.x / CS, gridDim.x / CS, stage, phase, it);
+  conv_teardown<BN, CS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Several dependent convolutions in ONE launch (the 67 tiny convolutions of the A2J pose net cost ~10 us of fixed
+// latency each as separate launches).  `phases` lists the convolutions, `group_begin` partitions them into groups
+// whose members are independent; a grid-wide barrier separates consecutive groups.  Launched cooperatively so that
+// all CTAs are resident.
+// ---------------------------------------------------------------------------------------------------------------
+struct PhaseDesc {
+  CUtensorMap ta;
+  CUtensorMap tb;
+  ConvParams p;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+  __threadfence();                     // this thread's global writes are visible device-wide ...
+  __syncthreads();                     // ... for every thread of the CTA
+  if (threadIdx.x == 0) {
+    atomicAdd(counter, 1u);
+    unsigned spins = 0;
+    while (true) {
+      unsigned v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v >= target) break;
+      if (++spins > (1u << 26)) {
+        printf("hn: grid barrier timed out (block %d, %u of %u)\n", (int)blockIdx.x, v, target);
+        __trap();
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  // later TMA (async proxy) reads must observe what other CTAs wrote with ordinary stores before the barrier
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_multi_kernel(const PhaseDesc* __restrict__ phases, const int* __restrict__ group_begin, int num_groups,
+                  unsigned* __restrict__ counter) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ ConvParams sp;
+  uint8_t* smem_hdr = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t tmem_base = conv_prologue<BN, 1>(smem_hdr, Cfg<BN>::STAGES, nullptr, nullptr);
+  int stage = 0, it = 0;
+  uint32_t phase = 0;
+  for (int g = 0; g < num_groups; ++g) {
+    int tile_off = 0;                                    // tiles of the group's convs are dealt round-robin
+    for (int j = group_begin[g]; j < group_begin[g + 1]; ++j) {
+      __syncthreads();                                   // everyone is done with the previous sp
+      for (int i = threadIdx.x; i < (int)(sizeof(ConvParams) / 4); i += blockDim.x)
+        reinterpret_cast<uint32_t*>(&sp)[i] = reinterpret_cast<const uint32_t*>(&phases[j].p)[i];
+      __syncthreads();
+      const int tiles = sp.m_tiles * sp.n_tiles;
+      int first = ((int)blockIdx.x - tile_off) % (int)gridDim.x;
+      if (first < 0) first += gridDim.x;
+      conv_roles<BN, 1, false>(&phases[j].ta, &phases[j].tb, sp, smem_hdr, tmem_base, first, gridDim.x, stage, phase, it);
+      tile_off = (tile_off + tiles) % (int)gridDim.x;
+    }
+    if (g + 1 < num_groups) grid_barrier(counter, (unsigned)(g + 1) * gridDim.x);
+  }
+  conv_teardown<BN, 1>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -637,9 +731,16 @@ int pick_block_n(int cout_pad, int m_tiles, int k_blocks, int min_bn) {
   return best ? best : 16;
 }
 
-}  // namespace
+struct BuiltConv {
+  ConvParams p;
+  CUtensorMap ta, tb;
+  int bn, cs;
+  bool rb;
+};
 
-extern "C" int hn_conv2d_bf16(const hn_conv_desc* d, void* stream) {
+// Validate a descriptor and derive kernel parameters + tensor maps.  force_bn > 0 pins the tile width (and disables
+// clusters / resident weights), as the multi-convolution kernel needs.
+int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
   HN_REQUIRE(d && d->in && d->weight && d->out, "hn_conv2d_bf16: null pointer");
   HN_REQUIRE(d->cin > 0 && d->cin % BLOCK_K == 0, "hn_conv2d_bf16: cin=%d must be a multiple of 64", d->cin);
   HN_REQUIRE(d->kh == d->kw && (d->kh == 1 || d->kh == 3), "hn_conv2d_bf16: only 1x1 and 3x3 kernels (got %dx%d)",
@@ -681,19 +782,21 @@ extern "C" int hn_conv2d_bf16(const hn_conv_desc* d, void* stream) {
       }
     }
   p.m_tiles = hn_div_up(p.rows, BLOCK_M);
-  int bn = d->block_n ? d->block_n : pick_block_n(d->cout_pad, p.m_tiles, p.num_taps * p.cin_chunks, d->gn_stats ? 32 : 16);
+  int bn = force_bn ? force_bn
+                    : (d->block_n ? d->block_n
+                                  : pick_block_n(d->cout_pad, p.m_tiles, p.num_taps * p.cin_chunks, d->gn_stats ? 32 : 16));
   HN_REQUIRE((bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256) && d->cout_pad % bn == 0,
              "hn_conv2d_bf16: block_n=%d does not divide cout_pad=%d", bn, d->cout_pad);
   p.n_tiles = d->cout_pad / bn;
   // cluster of 2 with multicast weights when there is at least one pair of M tiles per SM pair
   // measured: pairs with multicast weights gain ~3 % on 256-wide tiles and lose elsewhere -> opt-in only
-  int cs = d->cluster ? d->cluster : 1;
+  int cs = (d->cluster && !force_bn) ? d->cluster : 1;
   HN_REQUIRE(cs == 1 || (cs == 2 && bn >= 64), "hn_conv2d_bf16: cluster=%d unsupported with block_n=%d", cs, bn);
   // resident weights: the layer's whole weight slice stays in shared memory and only A tiles stream, when it is one
   // narrow N tile whose weights fit next to >= 6 A stages and there are enough tiles per CTA to amortise the load
   const int k_blocks_total = p.num_taps * p.cin_chunks;
   const long long b_bytes = (long long)k_blocks_total * bn * BLOCK_K * 2;
-  bool rb = cs == 1 && p.n_tiles == 1 && bn <= 64 && b_bytes <= PIPE_BYTES_MAX - 3 * 2 * A_STAGE_BYTES &&
+  bool rb = !force_bn && cs == 1 && p.n_tiles == 1 && bn <= 64 && b_bytes <= PIPE_BYTES_MAX - 3 * 2 * A_STAGE_BYTES &&
             p.m_tiles >= 2 * hn_num_sms() && !(d->debug & 16);
   if (rb) {
     p.rb_b_bytes = (int)b_bytes;
@@ -749,7 +852,8 @@ extern "C" int hn_conv2d_bf16(const hn_conv_desc* d, void* stream) {
                p.gn_group_size);
   }
 
-  CUtensorMap ta, tb;
+  CUtensorMap& ta = out->ta;
+  CUtensorMap& tb = out->tb;
   {
     const cuuint64_t dims[3] = {(cuuint64_t)d->cin, (cuuint64_t)p.rows, (cuuint64_t)d->in_phases};
     const cuuint64_t strides[2] = {(cuuint64_t)d->cin * 2, (cuuint64_t)p.rows * d->cin * 2};
@@ -765,6 +869,33 @@ extern "C" int hn_conv2d_bf16(const hn_conv_desc* d, void* stream) {
     int rc = make_map(&tb, d->weight, 2, dims, strides, box);
     if (rc) return rc;
   }
+  out->p = p;
+  out->bn = bn;
+  out->cs = cs;
+  out->rb = rb;
+  return HN_OK;
+}
+
+constexpr int MULTI_BN = 64;
+
+struct MultiPlanHeader {        // device layout: [header][group_begin ints][PhaseDesc array]
+  unsigned counter;
+  int n_convs, n_groups, grid;
+};
+size_t multi_groups_off() { return 256; }
+size_t multi_phases_off(int n_groups) { return 256 + (((size_t)(n_groups + 1) * 4 + 255) / 256) * 256; }
+
+}  // namespace
+
+extern "C" int hn_conv2d_bf16(const hn_conv_desc* d, void* stream) {
+  BuiltConv b;
+  int rc = build_conv(d, 0, &b);
+  if (rc) return rc;
+  const ConvParams& p = b.p;
+  const CUtensorMap& ta = b.ta;
+  const CUtensorMap& tb = b.tb;
+  const int bn = b.bn, cs = b.cs;
+  const bool rb = b.rb;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (rb) {
     switch (bn) {
@@ -787,4 +918,75 @@ extern "C" int hn_conv2d_bf16(const hn_conv_desc* d, void* stream) {
     case 32: return launch<32, 1, false>(ta, tb, p, st);
     default: return launch<16, 1, false>(ta, tb, p, st);
   }
+}
+
+extern "C" int64_t hn_conv_multi_plan_bytes(int n_convs, int n_groups) {
+  return (int64_t)(multi_phases_off(n_groups) + (size_t)n_convs * sizeof(PhaseDesc) + 256);
+}
+
+extern "C" int hn_conv_multi_build(const hn_conv_desc* descs, int n_convs, const int* group_begin_host, int n_groups,
+                                   void* plan_dev, int64_t plan_bytes) {
+  HN_REQUIRE(descs && group_begin_host && plan_dev && n_convs > 0 && n_groups > 0, "hn_conv_multi_build: bad arguments");
+  HN_REQUIRE(plan_bytes >= hn_conv_multi_plan_bytes(n_convs, n_groups), "hn_conv_multi_build: plan buffer too small");
+  HN_REQUIRE((reinterpret_cast<uintptr_t>(plan_dev) & 255) == 0, "hn_conv_multi_build: plan buffer must be 256-byte aligned");
+  HN_REQUIRE(group_begin_host[0] == 0 && group_begin_host[n_groups] == n_convs, "hn_conv_multi_build: group table");
+  std::vector<uint8_t> host((size_t)hn_conv_multi_plan_bytes(n_convs, n_groups), 0);
+  MultiPlanHeader* hdr = reinterpret_cast<MultiPlanHeader*>(host.data());
+  int* groups = reinterpret_cast<int*>(host.data() + multi_groups_off());
+  PhaseDesc* ph = reinterpret_cast<PhaseDesc*>(host.data() + multi_phases_off(n_groups));
+  int max_group_tiles = 1;
+  for (int g = 0; g < n_groups; ++g) {
+    groups[g] = group_begin_host[g];
+    HN_REQUIRE(group_begin_host[g + 1] > group_begin_host[g], "hn_conv_multi_build: empty group %d", g);
+    int tiles = 0;
+    for (int j = group_begin_host[g]; j < group_begin_host[g + 1]; ++j) {
+      HN_REQUIRE(descs[j].cout_pad % MULTI_BN == 0, "hn_conv_multi_build: conv %d: cout_pad %% 64 != 0", j);
+      HN_REQUIRE(descs[j].gn_stats == nullptr, "hn_conv_multi_build: GroupNorm statistics are not supported here");
+      BuiltConv b;
+      int rc = build_conv(&descs[j], MULTI_BN, &b);
+      if (rc) return rc;
+      ph[j].ta = b.ta;
+      ph[j].tb = b.tb;
+      ph[j].p = b.p;
+      tiles += b.p.m_tiles * b.p.n_tiles;
+    }
+    if (tiles > max_group_tiles) max_group_tiles = tiles;
+  }
+  groups[n_groups] = n_convs;
+  hdr->n_convs = n_convs;
+  hdr->n_groups = n_groups;
+  hdr->grid = max_group_tiles < hn_num_sms() ? max_group_tiles : hn_num_sms();
+  HN_CHECK_CUDA(cudaMemcpy(plan_dev, host.data(), host.size(), cudaMemcpyHostToDevice));
+  return hdr->grid;     // > 0: number of CTAs hn_conv_multi_run will launch
+}
+
+extern "C" int hn_conv_multi_run(void* plan_dev, int n_convs, int n_groups, int grid, void* stream) {
+  HN_REQUIRE(plan_dev && n_convs > 0 && n_groups > 0 && grid > 0 && grid <= hn_num_sms(), "hn_conv_multi_run: bad arguments");
+  using C = Cfg<MULTI_BN>;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    HN_CHECK_CUDA(cudaFuncSetAttribute(conv_multi_kernel<MULTI_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       C::SMEM_BYTES));
+    attr_set = true;
+  }
+  uint8_t* base = reinterpret_cast<uint8_t*>(plan_dev);
+  HN_CHECK_CUDA(cudaMemsetAsync(base, 0, 4, st));            // the barrier counter
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;              // all CTAs resident: the grid barrier cannot deadlock
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const PhaseDesc* phases = reinterpret_cast<const PhaseDesc*>(base + multi_phases_off(n_groups));
+  const int* groups = reinterpret_cast<const int*>(base + multi_groups_off());
+  unsigned* counter = reinterpret_cast<unsigned*>(base);
+  HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_multi_kernel<MULTI_BN>, phases, groups, n_groups, counter));
+  hn_count_launch();
+  return HN_OK;
 }

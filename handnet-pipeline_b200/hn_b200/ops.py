@@ -15,6 +15,14 @@ from ._lib import ConvDesc, check, ptr, stream_ptr
 
 BF16 = torch.bfloat16
 PROFILE = None      # set to a list by runtime.conv_profile: (start event, end event, algorithmic FLOPs) per conv launch
+RECORD = None       # set to a list to RECORD conv2d calls (descriptor + keep-alive refs) instead of launching them;
+                    # None entries are group boundaries (see MultiConv)
+
+
+def record_barrier():
+    """Group boundary between dependent convolutions while recording a MultiConv plan (no-op otherwise)."""
+    if RECORD is not None and RECORD and RECORD[-1] is not None:
+        RECORD.append(None)
 
 
 def _require_cuda(t: torch.Tensor, name: str):
@@ -206,6 +214,9 @@ def conv2d(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 1, d
     d.block_n = block_n
     d.cluster = cluster
     d.debug = debug
+    if RECORD is not None:
+        RECORD.append((d, (x, weight, scale, shift, res, out, out_f32, out_phase)))
+        return out if out_f32 is None else out_f32
     if PROFILE is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -358,3 +369,38 @@ def a2j_aggregate(cls: torch.Tensor, reg: torch.Tensor, dep: torch.Tensor, ancho
     check(_lib.load().hn_a2j_aggregate(cls.data_ptr(), reg.data_ptr(), dep.data_ptr(), anchors.data_ptr(), n, a, j,
                                        out.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr()), "hn_a2j_aggregate")
     return out
+
+
+class MultiConv:
+    """A recorded sequence of convolutions that runs as ONE cooperative launch (hn_conv_multi_*).  `items` is what
+    ops.RECORD collected: (ConvDesc, keep-alive) tuples with None between dependent groups."""
+
+    def __init__(self, items, device):
+        while items and items[-1] is None:
+            items = items[:-1]
+        convs = [it for it in items if it is not None]
+        begins, k = [0], 0
+        for it in items:
+            if it is None:
+                begins.append(k)
+            else:
+                k += 1
+        begins.append(k)
+        self.keep = [it[1] for it in convs]
+        self.n, self.groups = len(convs), len(begins) - 1
+        arr = (ConvDesc * self.n)()
+        for i, (d, _) in enumerate(convs):
+            C.memmove(C.addressof(arr[i]), C.addressof(d), C.sizeof(ConvDesc))
+        gb = (C.c_int * (self.groups + 1))(*begins)
+        lib = _lib.load()
+        nbytes = int(lib.hn_conv_multi_plan_bytes(self.n, self.groups))
+        self.plan = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        torch.cuda.synchronize(device)
+        rc = lib.hn_conv_multi_build(arr, self.n, gb, self.groups, self.plan.data_ptr(), nbytes)
+        if rc <= 0:
+            check(rc if rc < 0 else -1, "hn_conv_multi_build")
+        self.grid = rc
+
+    def run(self):
+        check(_lib.load().hn_conv_multi_run(self.plan.data_ptr(), self.n, self.groups, self.grid, stream_ptr()),
+              "hn_conv_multi_run")

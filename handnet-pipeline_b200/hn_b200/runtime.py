@@ -56,6 +56,7 @@ def bn_affine(weight, bias, mean, var, eps=BN_EPS, conv_bias=None):
 
 
 _side_streams: Dict[str, List["torch.cuda.Stream"]] = {}
+A2J_MULTI = True            # run the A2J convolutions as one cooperative multi-convolution launch
 PARALLEL_CHAINS = True      # independent layer chains (head towers, A2J towers) on forked streams / graph branches
 
 
@@ -415,6 +416,7 @@ class A2JPlan:
         self.dep = torch.zeros((n, na, num_joints), dtype=torch.float32, device=device)
         self.agg_ws = torch.empty(int(ops._lib.load().hn_a2j_workspace_bytes(n, num_joints)), dtype=torch.uint8, device=device)
         self.cache: Dict[str, object] = {}
+        self.multi = None
 
     def act(self, key, hh, ww, c, halo=1):
         if key not in self.cache:
@@ -458,6 +460,25 @@ class A2JExecutor:
         ops.conv2d(a, w.stem_w, cout=64, ksize=1, scale=w.stem_scale, shift=w.stem_shift, relu=True, out=pl.stem,
                    algo_k=147)       # 3 identical input channels in the reference: 7*7*3 MACs per output
         cur = ops.maxpool3x3s2(pl.stem.t, pl.pool)
+        if A2J_MULTI and ops.PROFILE is None:
+            # layer1..4 and the three towers: 67 convolutions in ONE cooperative launch with grid barriers between
+            # dependent groups (recorded once per buffer set)
+            if pl.multi is None:
+                ops.RECORD = []
+                try:
+                    self._schedule(pl, w, cur, n)
+                    items = ops.RECORD
+                finally:
+                    ops.RECORD = None
+                pl.multi = ops.MultiConv(items, x.device)
+            pl.multi.run()
+        else:
+            self._schedule(pl, w, cur, n)
+        return pl.cls, pl.reg, pl.dep, pl
+
+    def _schedule(self, pl: A2JPlan, w: A2JWeights, cur, n):
+        """Emit the convolutions of layer1..layer4 and the towers in dependency order; ops.record_barrier() marks the
+        boundaries between dependent groups (used when recording a MultiConv plan, a no-op for eager launches)."""
         c4 = None
         for li in range(4):
             planes = 64 << li
@@ -466,53 +487,51 @@ class A2JExecutor:
                 stride, dil = blk["stride"], blk["dil"]
                 hout, wout = ((hin + 1) // 2, (win + 1) // 2) if stride == 2 else (hin, win)
                 tag = f"l{li}b{bi}"
+                # group 1: conv1 (1x1) and, if present, the downsample conv -- both read the block input
                 if stride == 2:
-                    # conv1 (1x1) runs at the input resolution and writes only the phase-split copy needed by the
-                    # stride-2 3x3; the block input needs a phase-split copy too for the stride-2 downsample.
+                    # conv1 runs at the input resolution and also writes the phase-split copy the stride-2 3x3 reads;
+                    # the stride-2 downsample reads the phase-split copy of the block input
                     t1 = pl.act(tag + "t1", hin, win, planes)
                     t1p = pl.phase(tag + "t1p", hin, win, planes)
                     blk["conv1"].run(cur, relu=True, out=t1, out_phase=t1p)
-                    t2 = pl.act(tag + "t2", hout, wout, planes)
-                    blk["conv2"].run(t1p, relu=True, out=t2)
                     idn = pl.act(tag + "id", hout, wout, planes * 4)
                     blk["down"].run(pl.cache[f"l{li - 1}out_phase"], out=idn)
+                    src2 = t1p
                 else:
-                    halo = dil                                          # dilated 3x3 needs a halo of 2 on its input
-                    t1 = pl.act(tag + "t1", hin, win, planes, halo)
+                    t1 = pl.act(tag + "t1", hin, win, planes, dil)       # a dilated 3x3 needs a halo of 2 on its input
                     blk["conv1"].run(cur, relu=True, out=t1)
-                    t2 = pl.act(tag + "t2", hout, wout, planes)
-                    blk["conv2"].run(t1, relu=True, out=t2)
                     if "down" in blk:
                         idn = pl.act(tag + "id", hout, wout, planes * 4)
                         blk["down"].run(cur, out=idn)
                     else:
                         idn = cur
+                    src2 = t1
+                ops.record_barrier()
+                t2 = pl.act(tag + "t2", hout, wout, planes)
+                blk["conv2"].run(src2, relu=True, out=t2)
+                ops.record_barrier()
                 last = bi == len(w.blocks[li]) - 1
                 out = pl.act(tag + "out", hout, wout, planes * 4)
-                out_phase = None
-                if last and li in (0, 1):
-                    out_phase = pl.phase(f"l{li}out_phase", hout, wout, planes * 4)
+                out_phase = pl.phase(f"l{li}out_phase", hout, wout, planes * 4) if (last and li in (0, 1)) else None
                 blk["conv3"].run(t2, relu=True, res=idn, res_mode=1, out=out, out_phase=out_phase)
+                ops.record_barrier()
                 cur = out
             if li == 2:
                 c4 = cur
         c5 = cur
         hf, wf = pl.feat_hw
-        def a2j_tower(name, src, dst):
-            def run():
-                layers, outc = w.towers[name]
-                t = src
-                for i, conv in enumerate(layers):
-                    o = pl.act(f"{name}{i}", hf, wf, 256)
-                    conv.run(t, relu=True, out=o)
-                    t = o
-                # permute(0,3,2,1) + view of the reference == w-major rows (a2j/a2j.py:85-89)
-                outc.run(t, out_f32=dst.view(n, hf * wf, -1), out_transpose_hw=True)
-            return run
+        towers = (("regressionModel", c5, pl.reg), ("DepthRegressionModel", c5, pl.dep), ("classificationModel", c4, pl.cls))
+        t = {name: src for name, src, _ in towers}
+        for i in range(4):
+            for name, _, _ in towers:
+                o = pl.act(f"{name}{i}", hf, wf, 256)
+                w.towers[name][0][i].run(t[name], relu=True, out=o)
+                t[name] = o
+            ops.record_barrier()
+        for name, _, dst in towers:
+            # permute(0,3,2,1) + view of the reference == w-major rows (a2j/a2j.py:85-89)
+            w.towers[name][1].run(t[name], out_f32=dst.view(n, hf * wf, -1), out_transpose_hw=True)
 
-        run_chains([a2j_tower("regressionModel", c5, pl.reg), a2j_tower("DepthRegressionModel", c5, pl.dep),
-                    a2j_tower("classificationModel", c4, pl.cls)], x.device)
-        return pl.cls, pl.reg, pl.dep, pl
 
     def forward_device(self, x: torch.Tensor) -> torch.Tensor:
         cls, reg, dep, pl = self.heads_device(x)

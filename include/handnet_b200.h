@@ -95,6 +95,18 @@ typedef struct hn_conv_desc {
 } hn_conv_desc;
 int hn_conv2d_bf16(const hn_conv_desc* desc, void* stream);
 
+/* Several dependent convolutions in ONE cooperative launch (used for the A2J pose net, whose 67 tiny convolutions
+ * cost ~10 us of fixed latency each as separate launches).  descs[group_begin[g] .. group_begin[g+1]) are mutually
+ * independent; a grid-wide barrier separates consecutive groups.  All convolutions use 64-wide N tiles (cout_pad a
+ * multiple of 64), no GroupNorm statistics.  hn_conv_multi_build validates the descriptors, encodes the tensor maps
+ * and uploads the plan into plan_dev (256-byte aligned device memory of hn_conv_multi_plan_bytes bytes) with a
+ * synchronous copy -- call it once per buffer set, outside stream capture; it returns the grid size (> 0) or a
+ * negative status.  hn_conv_multi_run only enqueues a 4-byte memset and the launch. */
+int64_t hn_conv_multi_plan_bytes(int n_convs, int n_groups);
+int hn_conv_multi_build(const hn_conv_desc* descs, int n_convs, const int* group_begin_host, int n_groups,
+                        void* plan_dev, int64_t plan_bytes);
+int hn_conv_multi_run(void* plan_dev, int n_convs, int n_groups, int grid, void* stream);
+
 /* ---- 3x3 stride-2 pad-1 max pool (torchvision resnet maxpool; a2j/resnet.py:108) ----------------------------
  * in: bf16 [n][h][w][c] (no halo) -> out: bf16 haloed NHWC [n][oh+2*halo][ow+2*halo][c], oh = (h+1)/2. */
 int hn_maxpool3x3s2(const void* in, int n, int h, int w, int c, void* out, int out_halo, void* stream);

@@ -252,3 +252,30 @@ def test_fcos_1080p_canvas_config5():
     assert np.array_equal(out["keep"][0, :k].cpu().numpy(), keep_ref)
     # boxes are reported in original 1920x1080 pixels
     assert torch.equal(out["boxes"][0, :k].cpu(), fcos_oracle.resize_boxes(box[keep_ref], (749, 1333), (1080, 1920)))
+
+
+def test_a2j_multi_conv_kernel_equals_per_layer_launches(golden):
+    """The cooperative multi-convolution launch (67 convs, grid barriers between dependent groups) must produce
+    the same head tensors as one launch per convolution."""
+    from a2j.a2j import A2JModel
+    from hn_b200 import runtime
+    sd = synth.a2j_state_dict(seed=1)
+    g = torch.Generator().manual_seed(23)
+    x = (torch.rand(5, 1, 176, 176, generator=g) * 1.5).cuda()
+    outs = []
+    for multi in (True, False):
+        runtime.A2J_MULTI = multi
+        try:
+            m = A2JModel(21, 176, 176).eval()
+            m.load_state_dict(sd)
+            m.cuda()
+            with torch.inference_mode():
+                cls, reg, dep = m.head_outputs(x)
+                j1 = m.forward_device(x).clone()
+                j2 = m.forward_device(x).clone()          # second run: barrier counter reset, same buffers
+            assert torch.equal(j1, j2)
+            outs.append((cls.clone(), reg.clone(), dep.clone(), j1))
+        finally:
+            runtime.A2J_MULTI = True
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
