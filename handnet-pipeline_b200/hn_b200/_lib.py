@@ -33,6 +33,7 @@ class ConvDesc(C.Structure):
         ("out_phase", _c_p), ("out_phase_halo", _i),
         ("gn_stats", _c_p), ("gn_groups", _i),
         ("block_n", _i), ("cluster", _i), ("debug", _i),
+        ("splitk_ws", _c_p), ("splitk_ws_bytes", _i64), ("splitk_counters", _c_p), ("splitk_counters_len", _i), ("splits", _i),
     ]
 
 

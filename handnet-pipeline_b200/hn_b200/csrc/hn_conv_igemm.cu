@@ -57,6 +57,10 @@ struct ConvParams {
   long long ph_stride;         // elements between phase images
   double* gn_stats;
   int gn_groups, gn_group_size;
+  int splits;                       // split-K factor (>= 1)
+  float* sk_ws;                     // fp32 partial-sum scratch [m_tiles*128][sk_ld], zero between uses
+  unsigned* sk_cnt;                 // arrival counter per (m, n) tile, zero between uses
+  int sk_ld;
   int rb_stages, rb_b_bytes;        // resident-weights mode: A stages and bytes of the weight slice
   int dbg_shift, dbg_base_offset, dbg_flags, lookahead;   // bring-up experiment: A box loaded dbg_shift rows early, descriptor offset back
 };
@@ -133,11 +137,16 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
         for (int kb = 0; kb < k_blocks; ++kb)
           hn_tma_load_2d(pipe + kb * C::B_STAGE_BYTES, &tm_b, b_full, kb * BLOCK_K, 0);
       }
-      for (int st = first_tile; st < num_super; st += tile_stride) {
+      for (int w_ = first_tile; w_ < num_super * p.splits; w_ += tile_stride) {
+        const int st = w_ / p.splits, ks = w_ - st * p.splits;   // (super) tile and K split of this work item
+        const int s_base = k_steps / p.splits, s_rem = k_steps - s_base * p.splits;
+        const int s_begin = ks * s_base + (ks < s_rem ? ks : s_rem);
+        const int s_end = s_begin + s_base + (ks < s_rem ? 1 : 0);
         const int m0 = ((st / p.n_tiles) * CS + cta_rank) * BLOCK_M;
         const int n0 = (st % p.n_tiles) * BN;
-        int tap = 0, cc = 0;                                   // k-block kb = tap * cin_chunks + cc
-        for (int step = 0; step < k_steps; ++step) {
+        int tap = (s_begin * KG) / p.cin_chunks;               // k-block kb = tap * cin_chunks + cc
+        int cc = s_begin * KG - tap * p.cin_chunks;
+        for (int step = s_begin; step < s_end; ++step) {
           const int nk = (k_blocks - step * KG < KG) ? k_blocks - step * KG : KG;
           hn_mbar_wait(&empty_bar[stage], phase ^ 1);
           if (p.dbg_flags & 8) {                               // timing experiment: no loads at all
@@ -173,18 +182,23 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
       constexpr uint32_t idesc = hn_umma_idesc_bf16(BN);
-      int st = first_tile;
+      int w_ = first_tile;
+      const int num_items = num_super * p.splits;
       if constexpr (RB) hn_mbar_wait(b_full, 0);
-      if (st < num_super) {                                    // prime: this tile's accumulator buffer and first stage
+      if (w_ < num_items) {                                    // prime: this item's accumulator buffer and first stage
         hn_mbar_wait(&tmem_empty[it & 1], ((it >> 1) & 1) ^ 1);
         hn_mbar_wait(&full_bar[stage], phase);
         hn_tc_fence_after();
       }
-      for (; st < num_super; st += tile_stride, ++it) {
+      for (; w_ < num_items; w_ += tile_stride, ++it) {
+        const int ks = w_ % p.splits;                          // K split of this work item
+        const int s_base = k_steps / p.splits, s_rem = k_steps - s_base * p.splits;
+        const int s_begin = ks * s_base + (ks < s_rem ? ks : s_rem);
+        const int s_end = s_begin + s_base + (ks < s_rem ? 1 : 0);
         const int buf = it & 1;
         const uint32_t d_tmem = tmem_base + buf * BN;
-        const bool has_next_tile = st + tile_stride < num_super;
-        for (int step = 0; step < k_steps; ++step) {
+        const bool has_next_tile = w_ + tile_stride < num_items;
+        for (int step = s_begin; step < s_end; ++step) {
           const int nk = (k_blocks - step * KG < KG) ? k_blocks - step * KG : KG;
           const uint32_t a_addr = hn_smem_u32(smem + stage * stage_bytes);
           if (!(p.dbg_flags & 4)) {                            // (timing experiment: bit 2 skips the MMAs)
@@ -199,12 +213,12 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / 16; ++k) {
                   // +32 bytes per K=16 step inside the 128-byte swizzle span: start-address field += 2
-                  hn_umma_bf16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (step | g | k) != 0);
+                  hn_umma_bf16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, ((step - s_begin) | g | k) != 0);
                 }
               }
             }
           }
-          const bool last = step == k_steps - 1;
+          const bool last = step == s_end - 1;
           if (last) hn_umma_commit(&tmem_full[buf]);           // accumulator complete -> epilogue
           int nstage = stage + 1;
           uint32_t nphase = phase;
@@ -247,7 +261,9 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       for (int i = threadIdx.x - 64; i < gn_vals; i += EPI_THREADS) gn_acc[i] = 0.f;
       hn_epi_bar_sync();
     }
-    for (int st = first_tile; st < num_super; st += tile_stride, ++it) {
+    uint32_t* sk_flag = reinterpret_cast<uint32_t*>(b_full + 1) + 1;   // "this CTA finalises the tile" (after tmem_slot)
+    for (int w_ = first_tile; w_ < num_super * p.splits; w_ += tile_stride, ++it) {
+      const int st = w_ / p.splits;
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m0 = ((st / p.n_tiles) * CS + cta_rank) * BLOCK_M;
@@ -316,8 +332,47 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       hn_tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + buf * BN;
 
+      // Split-K: every work item adds its partial accumulator into an fp32 scratch tile with vector reductions; the
+      // item that arrives last (per-tile counter) reads the sums back, re-zeroes the scratch and runs the epilogue.
+      const bool split = p.splits > 1;
+      bool finalize = true;
+      float* sk_row = split ? p.sk_ws + (size_t)m * p.sk_ld + n0 : nullptr;
+      if (split) {
+        if constexpr (CHUNK == 32) {
 #pragma unroll 1
-      for (int c0 = c_first; c0 < ((idle_half || (p.dbg_flags & 2)) ? 0 : BN); c0 += STEP) {
+          for (int c0 = c_first; c0 < (idle_half ? 0 : BN); c0 += STEP) {
+            if (n0 + c0 >= p.cout) continue;
+            uint32_t acc[32];
+            hn_tmem_ld32(t_row + c0, acc);
+            hn_tmem_ld_wait();
+            if (interior) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(sk_row + c0 + j),
+                             "f"(__uint_as_float(acc[j])), "f"(__uint_as_float(acc[j + 1])),
+                             "f"(__uint_as_float(acc[j + 2])), "f"(__uint_as_float(acc[j + 3]))
+                             : "memory");
+            }
+          }
+        }
+        hn_tc_fence_before();
+        __syncwarp();
+        if (lane == 0) hn_mbar_arrive(&tmem_empty[buf]);       // TMEM drained already
+        __threadfence();
+        hn_epi_bar_sync();
+        if (threadIdx.x == 64) {
+          const unsigned old = atomicAdd(p.sk_cnt + st, 1u);
+          const bool is_last = old == (unsigned)p.splits - 1u;
+          if (is_last) p.sk_cnt[st] = 0u;                      // everyone has arrived: reset for the next launch
+          *sk_flag = is_last ? 1u : 0u;
+        }
+        hn_epi_bar_sync();
+        finalize = *sk_flag != 0u;
+        if (finalize) __threadfence();
+      }
+
+#pragma unroll 1
+      for (int c0 = c_first; c0 < ((idle_half || (p.dbg_flags & 2) || !finalize) ? 0 : BN); c0 += STEP) {
         uint4 res_cur[CHUNK / 8];
 #pragma unroll
         for (int j = 0; j < CHUNK / 8; ++j) res_cur[j] = res_next[j];
@@ -327,14 +382,30 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
             res_next[j] = __ldg(reinterpret_cast<const uint4*>(p.res + res_off + n0 + c0 + STEP) + j);
         }
         uint32_t acc[CHUNK];
-        if constexpr (CHUNK == 32) {
-          hn_tmem_ld32(t_row + c0, acc);
-        } else {
-          hn_tmem_ld16(t_row + c0, acc);
-        }
-        hn_tmem_ld_wait();
         const int cbase = n0 + c0;
-        if (cbase >= p.cout) continue;                 // padded output channels (warp-uniform)
+        if (split) {
+          if (cbase >= p.cout) continue;
+          if constexpr (CHUNK == 32) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (interior) {
+                t = __ldcg(reinterpret_cast<const float4*>(sk_row + c0 + j));
+                __stcg(reinterpret_cast<float4*>(sk_row + c0 + j), make_float4(0.f, 0.f, 0.f, 0.f));
+              }
+              acc[j] = __float_as_uint(t.x); acc[j + 1] = __float_as_uint(t.y);
+              acc[j + 2] = __float_as_uint(t.z); acc[j + 3] = __float_as_uint(t.w);
+            }
+          }
+        } else {
+          if constexpr (CHUNK == 32) {
+            hn_tmem_ld32(t_row + c0, acc);
+          } else {
+            hn_tmem_ld16(t_row + c0, acc);
+          }
+          hn_tmem_ld_wait();
+          if (cbase >= p.cout) continue;                 // padded output channels (warp-uniform)
+        }
         float v[CHUNK];
 #pragma unroll
         for (int j = 0; j < CHUNK; j += 4) {
@@ -474,10 +545,12 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
           }
         }
       }
-      // accumulator buffer drained -> hand it back to the MMA warp
-      hn_tc_fence_before();
-      __syncwarp();
-      if (lane == 0) hn_mbar_arrive(&tmem_empty[buf]);
+      // accumulator buffer drained -> hand it back to the MMA warp (split-K items did so after their reduction)
+      if (!split) {
+        hn_tc_fence_before();
+        __syncwarp();
+        if (lane == 0) hn_mbar_arrive(&tmem_empty[buf]);
+      }
     }
     if (gn_smem) {
       hn_epi_bar_sync();
@@ -610,7 +683,7 @@ conv_multi_kernel(const PhaseDesc* __restrict__ phases, const int* __restrict__ 
       for (int i = threadIdx.x; i < (int)(sizeof(ConvParams) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(&sp)[i] = reinterpret_cast<const uint32_t*>(&phases[j].p)[i];
       __syncthreads();
-      const int tiles = sp.m_tiles * sp.n_tiles;
+      const int tiles = sp.m_tiles * sp.n_tiles * sp.splits;
       int first = ((int)blockIdx.x - tile_off) % (int)gridDim.x;
       if (first < 0) first += gridDim.x;
       conv_roles<BN, 1, false>(&phases[j].ta, &phases[j].tb, sp, smem_hdr, tmem_base, first, gridDim.x, stage, phase, it);
@@ -678,7 +751,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cu
                                        SMEM));
     attr_set = true;
   }
-  const int super = hn_div_up(p.m_tiles, CS) * p.n_tiles;
+  const int super = hn_div_up(p.m_tiles, CS) * p.n_tiles * p.splits;
   // equal work per CTA: with w = ceil(tiles / SMs) waves, ceil(tiles / w) CTAs finish at the same time as a full grid
   // would and leave the other SMs to kernels of concurrent streams (graph branches)
   const int max_clusters = hn_num_sms() / CS;
@@ -852,6 +925,34 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
                p.gn_group_size);
   }
 
+  // split-K (needs caller-provided scratch): short, deep layers whose tiles cannot fill the GPU
+  p.splits = 1;
+  if (d->splitk_ws && d->splitk_counters && cs == 1 && bn >= 32) {
+    const int kg = bn >= 256 ? 1 : 2;
+    const int k_steps = hn_div_up(k_blocks_total, kg);
+    const int tiles = p.m_tiles * p.n_tiles;
+    int sp = d->splits;
+    if (sp <= 0) {
+      sp = 1;
+      if (tiles * 2 <= hn_num_sms() && k_steps >= 6) {
+        sp = hn_num_sms() / tiles;
+        if (sp > k_steps / 3) sp = k_steps / 3;
+        if (sp > 16) sp = 16;
+        if (sp < 1) sp = 1;
+      }
+    }
+    if (sp > k_steps) sp = k_steps;
+    if (sp > 1) {
+      const long long need = (long long)p.m_tiles * BLOCK_M * d->cout_pad * 4;
+      HN_REQUIRE(d->splitk_ws_bytes >= need, "hn_conv2d_bf16: split-K scratch too small (%lld < %lld bytes)",
+                 (long long)d->splitk_ws_bytes, need);
+      HN_REQUIRE(d->splitk_counters_len >= tiles, "hn_conv2d_bf16: split-K counter array too small");
+      p.splits = sp;
+      p.sk_ws = reinterpret_cast<float*>(d->splitk_ws);
+      p.sk_cnt = reinterpret_cast<unsigned*>(d->splitk_counters);
+      p.sk_ld = d->cout_pad;
+    }
+  }
   CUtensorMap& ta = out->ta;
   CUtensorMap& tb = out->tb;
   {
@@ -948,7 +1049,7 @@ extern "C" int hn_conv_multi_build(const hn_conv_desc* descs, int n_convs, const
       ph[j].ta = b.ta;
       ph[j].tb = b.tb;
       ph[j].p = b.p;
-      tiles += b.p.m_tiles * b.p.n_tiles;
+      tiles += b.p.m_tiles * b.p.n_tiles * b.p.splits;
     }
     if (tiles > max_group_tiles) max_group_tiles = tiles;
   }

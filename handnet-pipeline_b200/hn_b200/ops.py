@@ -175,7 +175,7 @@ def conv2d(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 1, d
            out_f32: Optional[torch.Tensor] = None, out_rows_per_image: int = 0, out_row_offset: int = 0,
            out_transpose_hw: bool = False, out_phase: Optional[PhaseAct] = None,
            gn_stats: Optional[torch.Tensor] = None, gn_groups: int = 0, block_n: int = 0, cluster: int = 0,
-           algo_k: int = 0, debug: int = 0):
+           algo_k: int = 0, debug: int = 0, splitk=None, splits: int = 0):
     """hn_conv2d_bf16.  x: Act (stride 1) or PhaseAct (stride 2).  relu: bool or (lo, hi) channel range."""
     d = ConvDesc()
     if isinstance(x, PhaseAct):
@@ -214,8 +214,13 @@ def conv2d(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 1, d
     d.block_n = block_n
     d.cluster = cluster
     d.debug = debug
+    if splitk is not None:            # (fp32 scratch, uint32 counters): both zero, exclusive to this conv
+        ws_t, cnt_t = splitk
+        d.splitk_ws, d.splitk_ws_bytes = ws_t.data_ptr(), ws_t.numel() * ws_t.element_size()
+        d.splitk_counters, d.splitk_counters_len = cnt_t.data_ptr(), cnt_t.numel()
+        d.splits = splits
     if RECORD is not None:
-        RECORD.append((d, (x, weight, scale, shift, res, out, out_f32, out_phase)))
+        RECORD.append((d, (x, weight, scale, shift, res, out, out_f32, out_phase, splitk)))
         return out if out_f32 is None else out_f32
     if PROFILE is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -56,6 +56,7 @@ def bn_affine(weight, bias, mean, var, eps=BN_EPS, conv_bias=None):
 
 
 _side_streams: Dict[str, List["torch.cuda.Stream"]] = {}
+SPLIT_K = True              # split-K (fp32 scratch + last-arriver epilogue) for the short, deep A2J layers
 A2J_MULTI = True            # run the A2J convolutions as one cooperative multi-convolution launch
 PARALLEL_CHAINS = True      # independent layer chains (head towers, A2J towers) on forked streams / graph branches
 
@@ -428,6 +429,23 @@ class A2JPlan:
             self.cache[key] = PhaseAct(self.n, hh, ww, c, 1, self.device)
         return self.cache[key]
 
+    def splitk(self, key, x, conv: "ConvLayer"):
+        """Split-K scratch (fp32 sums + tile counters, zero between uses) for a convolution reading `x`, or None
+        when the layer has enough tiles on its own.  Exclusive per convolution: members of a group run concurrently."""
+        if not SPLIT_K:
+            return None
+        hh, ww = (x.h2, x.w2) if isinstance(x, PhaseAct) else (x.h, x.w)
+        rows = self.n * (hh + 2 * x.halo) * (ww + 2 * x.halo)
+        m_tiles = (rows + 127) // 128
+        cout_pad = conv.w.shape[0]
+        if m_tiles * (cout_pad // 64) * 2 > 148:
+            return None
+        k = "sk_" + key
+        if k not in self.cache:
+            self.cache[k] = (torch.zeros(m_tiles * 128 * cout_pad, dtype=torch.float32, device=self.device),
+                             torch.zeros(m_tiles * (cout_pad // 32), dtype=torch.int32, device=self.device))
+        return self.cache[k]
+
 
 class A2JExecutor:
     """A2JModel.forward with gt=None (a2j/a2j.py:243-250) on the GPU."""
@@ -493,27 +511,29 @@ class A2JExecutor:
                     # the stride-2 downsample reads the phase-split copy of the block input
                     t1 = pl.act(tag + "t1", hin, win, planes)
                     t1p = pl.phase(tag + "t1p", hin, win, planes)
-                    blk["conv1"].run(cur, relu=True, out=t1, out_phase=t1p)
+                    blk["conv1"].run(cur, relu=True, out=t1, out_phase=t1p, splitk=pl.splitk(tag + "c1", cur, blk["conv1"]))
                     idn = pl.act(tag + "id", hout, wout, planes * 4)
-                    blk["down"].run(pl.cache[f"l{li - 1}out_phase"], out=idn)
+                    blk["down"].run(pl.cache[f"l{li - 1}out_phase"], out=idn,
+                                    splitk=pl.splitk(tag + "dn", pl.cache[f"l{li - 1}out_phase"], blk["down"]))
                     src2 = t1p
                 else:
                     t1 = pl.act(tag + "t1", hin, win, planes, dil)       # a dilated 3x3 needs a halo of 2 on its input
-                    blk["conv1"].run(cur, relu=True, out=t1)
+                    blk["conv1"].run(cur, relu=True, out=t1, splitk=pl.splitk(tag + "c1", cur, blk["conv1"]))
                     if "down" in blk:
                         idn = pl.act(tag + "id", hout, wout, planes * 4)
-                        blk["down"].run(cur, out=idn)
+                        blk["down"].run(cur, out=idn, splitk=pl.splitk(tag + "dn", cur, blk["down"]))
                     else:
                         idn = cur
                     src2 = t1
                 ops.record_barrier()
                 t2 = pl.act(tag + "t2", hout, wout, planes)
-                blk["conv2"].run(src2, relu=True, out=t2)
+                blk["conv2"].run(src2, relu=True, out=t2, splitk=pl.splitk(tag + "c2", src2, blk["conv2"]))
                 ops.record_barrier()
                 last = bi == len(w.blocks[li]) - 1
                 out = pl.act(tag + "out", hout, wout, planes * 4)
                 out_phase = pl.phase(f"l{li}out_phase", hout, wout, planes * 4) if (last and li in (0, 1)) else None
-                blk["conv3"].run(t2, relu=True, res=idn, res_mode=1, out=out, out_phase=out_phase)
+                blk["conv3"].run(t2, relu=True, res=idn, res_mode=1, out=out, out_phase=out_phase,
+                                 splitk=pl.splitk(tag + "c3", t2, blk["conv3"]))
                 ops.record_barrier()
                 cur = out
             if li == 2:
@@ -525,12 +545,14 @@ class A2JExecutor:
         for i in range(4):
             for name, _, _ in towers:
                 o = pl.act(f"{name}{i}", hf, wf, 256)
-                w.towers[name][0][i].run(t[name], relu=True, out=o)
+                w.towers[name][0][i].run(t[name], relu=True, out=o,
+                                         splitk=pl.splitk(f"{name}{i}", t[name], w.towers[name][0][i]))
                 t[name] = o
             ops.record_barrier()
         for name, _, dst in towers:
             # permute(0,3,2,1) + view of the reference == w-major rows (a2j/a2j.py:85-89)
-            w.towers[name][1].run(t[name], out_f32=dst.view(n, hf * wf, -1), out_transpose_hw=True)
+            w.towers[name][1].run(t[name], out_f32=dst.view(n, hf * wf, -1), out_transpose_hw=True,
+                                  splitk=pl.splitk(name + "out", t[name], w.towers[name][1]))
 
 
     def forward_device(self, x: torch.Tensor) -> torch.Tensor:

@@ -92,6 +92,14 @@ typedef struct hn_conv_desc {
   int block_n; /* 0 = choose automatically among 16/32/64/128/256 */
   int cluster; /* 0 = automatic; 1 = no cluster; 2 = CTA pairs along M that multicast the weight tile */
   int debug;   /* 0 in production; bring-up experiments only */
+  /* optional split-K: fp32 scratch of at least ceil(rows/128)*128*cout_pad*4 bytes and one uint32 counter per output
+   * tile, both ZERO on entry and left zero on exit (exclusive to this convolution while it runs).  splits = 0 lets
+   * the library choose (1 = off).  Used for short, deep layers that cannot fill the GPU with tiles. */
+  void* splitk_ws;
+  int64_t splitk_ws_bytes;
+  void* splitk_counters;
+  int splitk_counters_len;
+  int splits;
 } hn_conv_desc;
 int hn_conv2d_bf16(const hn_conv_desc* desc, void* stream);
 
