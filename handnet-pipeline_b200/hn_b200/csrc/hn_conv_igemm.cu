@@ -934,9 +934,11 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
     int sp = d->splits;
     if (sp <= 0) {
       sp = 1;
-      if (tiles * 2 <= hn_num_sms() && k_steps >= 6) {
+      // measured (tools/a2j_timing.py): the reduction + counter round trip + read-back cost ~3-4 us per layer, a
+      // pipeline step ~0.4 us, so only deep layers (>= 24 steps) gain
+      if (tiles * 2 <= hn_num_sms() && k_steps >= 24) {
         sp = hn_num_sms() / tiles;
-        if (sp > k_steps / 3) sp = k_steps / 3;
+        if (sp > k_steps / 6) sp = k_steps / 6;
         if (sp > 16) sp = 16;
         if (sp < 1) sp = 1;
       }

@@ -273,9 +273,11 @@ def test_a2j_multi_conv_kernel_equals_per_layer_launches(golden):
                 cls, reg, dep = m.head_outputs(x)
                 j1 = m.forward_device(x).clone()
                 j2 = m.forward_device(x).clone()          # second run: barrier counter reset, same buffers
-            assert torch.equal(j1, j2)
+            # split-K layers add their partial sums with fp32 atomics: runs agree to summation-order noise
+            assert (j1 - j2).abs().max() < 2e-3
             outs.append((cls.clone(), reg.clone(), dep.clone(), j1))
         finally:
             runtime.A2J_MULTI = True
     for a, b in zip(outs[0], outs[1]):
-        assert torch.equal(a, b)
+        # (a sum that lands on the other side of a bf16 rounding boundary moves one activation by 2^-8 relative)
+        assert ((a - b).abs() / b.abs().clamp(min=1.0)).max() < 1e-2
