@@ -79,16 +79,31 @@ __device__ __forceinline__ bool hn_mbar_try_wait(uint64_t* bar, uint32_t parity)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug turns into a trap (reported as a CUDA error) instead of a hang.
+// Bounded wait: a protocol bug turns into a trap (reported as a CUDA error) instead of a hang.  The report is kept
+// out of line so that the polling loop stays a handful of instructions.
+static __device__ __noinline__ void hn_mbar_timeout(const void* bar, uint32_t parity) {
+  printf("hn: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar,
+         parity);
+  __trap();
+}
 __device__ __forceinline__ void hn_mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (hn_mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   while (!hn_mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) {
-      printf("hn: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n", (int)blockIdx.x,
-             (int)threadIdx.x, (void*)bar, parity);
-      __trap();
-    }
+    if (++spins > (1u << 22)) hn_mbar_timeout(bar, parity);
   }
+}
+// One lane of a CONVERGED warp (all 32 lanes must execute this).  Code guarded by the result is known to the
+// compiler to run in a single thread, so tcgen05 / TMA operands go to uniform registers without a per-lane
+// "waterfall" loop around every instruction (what `if (lane == 0)` compiles to).
+__device__ __forceinline__ bool hn_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // ---- TMA ----------------------------------------------------------------------------------
@@ -166,6 +181,32 @@ __device__ __forceinline__ void hn_umma_commit_mcast(uint64_t* bar, uint16_t cta
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
       ::"r"(hn_smem_u32(bar)), "h"(cta_mask)
       : "memory");
+}
+// Four K=16 steps over one 64-wide (128-byte, SWIZZLE_128B) K block: the start-address field advances by 32 bytes
+// (2 in descriptor units) per step.  `accumulate` = 0 overwrites the accumulator with the first product.
+__device__ __forceinline__ void hn_umma_bf16_x4(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %5, %6, %3, 1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %7, %8, %3, 1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %9, %10, %3, 1;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "l"(desc_a + 2), "l"(desc_b + 2),
+        "l"(desc_a + 4), "l"(desc_b + 4), "l"(desc_a + 6), "l"(desc_b + 6)
+      : "memory");
+}
+// tcgen05.commit on an mbarrier given by its shared-memory address; CS > 1 signals the barrier at the same offset in
+// every CTA of the cluster.
+template <int CS>
+__device__ __forceinline__ void hn_umma_commit_addr(uint32_t bar_addr) {
+  if constexpr (CS == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar_addr), "h"((uint16_t)((1u << CS) - 1u)) : "memory");
+  }
 }
 __device__ __forceinline__ void hn_tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

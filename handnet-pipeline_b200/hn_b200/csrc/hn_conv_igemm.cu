@@ -8,12 +8,19 @@
 // activation matrix [rows = N*Hp*Wp][Cin] shifted by (r*Wp + s) rows: one 2-D TMA box per (tap, 64-channel
 // chunk), out-of-range rows zero-filled by TMA.  Weights are [Cout_pad][taps*Cin] bf16 (K-major).
 //
-// One persistent CTA per SM, 192 threads:
-//   warp 0      TMA producer   (A box 128 rows x 64 ch, B box BN rows x 64 k, SWIZZLE_128B, STAGES-deep ring)
+// One persistent CTA per SM, 320 threads:
+//   warp 0      TMA producer   (two rings: A boxes of 128 or 136 rows x 64 ch, B tiles of BN rows x 64 k, SWIZZLE_128B)
 //   warp 1      MMA issuer     (tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16; fp32 accumulators in TMEM,
 //                               double-buffered so the epilogue of tile i overlaps the main loop of tile i+1)
-//   warps 2..5  epilogue       (tcgen05.ld -> scale/shift -> +residual -> ReLU -> bf16/fp32 store, GroupNorm partial
+//   warps 2..9  epilogue       (tcgen05.ld -> scale/shift -> +residual -> ReLU -> bf16/fp32 store, GroupNorm partial
 //                               sums, optional phase-split copy for a following stride-2 conv)
+//
+// A-box sharing: the three horizontal taps of a 3x3 kernel row read rows m0+shift-1 .. m0+shift+128 of the same
+// matrix, so ONE 136-row box serves all three: their UMMA descriptors start 0, 1 and 2 rows (128 B each) into the
+// box (a SWIZZLE_128B descriptor may start at any 128-byte row with base_offset 0, tools/desc_offset_experiment.py).
+// That cuts the activation traffic L2 -> shared memory of a 3x3 convolution by 3x, which is what bounds the narrow
+// layers: a tcgen05.mma with N <= 128 is limited by the 128 B/clk of shared-memory bandwidth that its operand reads
+// share with the TMA writes (tools/sync_cost_bench.cu, tools/mma_issue_bench2.cu).
 #include "hn_common.cuh"
 
 #include <stdlib.h>
@@ -26,11 +33,13 @@ __device__ __forceinline__ void hn_epi_bar_sync();
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+constexpr int A_BOX_ROWS_MAX = 136;                   // 128 + up to 8 rows of horizontal-tap slack
+constexpr int A_SLOT_BYTES = A_BOX_ROWS_MAX * BLOCK_K * 2;   // 17 KiB (a multiple of 1024: slots keep swizzle alignment)
 constexpr int EPI_WARPS = 8;                       // two per TMEM lane quarter; they split the column chunks
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int NUM_THREADS = 64 + EPI_THREADS;
 constexpr int MAX_TAPS = 9;
+constexpr int MAX_GROUP_TAPS = 3;
 constexpr int GN_SMEM_FLOATS = 4096;   // [images][groups][2] fp32 partial sums kept per CTA (16 KiB)
 
 struct ConvParams {
@@ -38,8 +47,13 @@ struct ConvParams {
   int n_img, hp, wp, halo;     // padded height/width of one image and the halo size
   int rows;                    // n_img * hp * wp
   int num_taps, cin_chunks;
-  int tap_shift[MAX_TAPS];     // row shift of each tap
-  int tap_phase[MAX_TAPS];     // phase image of each tap (0 for ordinary inputs)
+  // A-box groups: taps that read the same box of activation rows at different row offsets
+  int n_groups;
+  int a_box_bytes;                          // bytes one A box brings (128 or 136 rows)
+  int grp_shift[MAX_TAPS];                  // first row of the group's box relative to the tile's first row
+  // packed: ntaps | off_step << 4 | tap0 << 8 | tap_step << 16 | phase << 24.  Member t of the group is weight tap
+  // tap0 + t * tap_step (r * kw + s) and reads the box from row t * off_step on; phase = phase image of the input
+  int grp_info[MAX_TAPS];
   int m_tiles, n_tiles;
   int cout;
   const float* scale;
@@ -61,35 +75,49 @@ struct ConvParams {
   float* sk_ws;                     // fp32 partial-sum scratch [m_tiles*128][sk_ld], zero between uses
   unsigned* sk_cnt;                 // arrival counter per (m, n) tile, zero between uses
   int sk_ld;
-  int rb_stages, rb_b_bytes;        // resident-weights mode: A stages and bytes of the weight slice
-  int dbg_shift, dbg_base_offset, dbg_flags, lookahead;   // bring-up experiment: A box loaded dbg_shift rows early, descriptor offset back
+  uint32_t div_img_mul, div_wp_mul; // x / d == (umulhi(x, mul) + x) >> sh for x < 2^31 (fastdiv())
+  int div_img_sh, div_wp_sh;
+  int na_stages, nb_stages;         // ring depths
+  int rb_b_bytes;                   // resident-weights mode: bytes of the weight slice
+  int dbg_flags;                    // bring-up / timing experiments (bit0 no stores, bit1 no epilogue, bit2 no MMA, bit3 no TMA)
+  long long* trace;                 // bring-up: CTA 0 logs (clock64, tag) pairs per role, TRACE_EVENTS each
 };
+
+constexpr int TRACE_EVENTS = 2048;
+// role 0 producer, 1 MMA issuer, 2 first epilogue warp; written by lane 0 of CTA 0 only
+__device__ __forceinline__ void hn_trace(long long* tr, int role, int& idx, int tag) {
+  if (tr != nullptr && blockIdx.x == 0) {
+    if ((threadIdx.x & 31) == 0 && idx < TRACE_EVENTS) {
+      tr[(role * TRACE_EVENTS + idx) * 2] = clock64();
+      tr[(role * TRACE_EVENTS + idx) * 2 + 1] = tag;
+    }
+    ++idx;
+  }
+}
 
 __device__ __forceinline__ void hn_epi_bar_sync() {   // named barrier 1: the epilogue warps only
   asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
 }
 
-// Shared memory: [0, HDR_BYTES) barriers, GroupNorm accumulators, scale/shift of the N tile; then (1024-aligned)
-// either STAGES x (A tile + B tile), or -- "resident weights" (RB) -- the whole weight slice of the layer followed
-// by A-only stages, which puts more k-blocks in flight per SM for the narrow layers.
+// Shared memory: [0, HDR_BYTES) barriers, GroupNorm accumulators, scale/shift of the N tile; then (1024-aligned) the
+// operand area: [resident weight slice (RB mode only)] [A ring: na x 17 KiB] [B ring: nb x BN*128 B].
 constexpr int MAX_STAGES = 12;
-constexpr int HDR_BARS = 256;
-constexpr int HDR_BYTES = HDR_BARS + GN_SMEM_FLOATS * 4 + 2 * 2 * 256 * 4;   // 20736, padded to 1024 below
+constexpr int HDR_BARS = 512;
+constexpr int HDR_BYTES = HDR_BARS + GN_SMEM_FLOATS * 4 + 2 * 2 * 256 * 4;   // 20992, padded to 1024 below
 constexpr int HDR_PAD = ((HDR_BYTES + 1023) / 1024) * 1024;
-constexpr int PIPE_BYTES_MAX = 196608;                                        // 192 KiB for the operand ring(s)
+constexpr int PIPE_BYTES_MAX = 204800;                                        // 200 KiB for the operand rings
+constexpr int SMEM_BYTES_ALL = 1024 /*alignment slack*/ + HDR_PAD + PIPE_BYTES_MAX;
+static_assert(SMEM_BYTES_ALL <= 232448, "exceeds the 227 KiB of shared memory per CTA");
 
 template <int BN>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
-  // k-blocks (64 channels of one tap) per pipeline stage.  The single-thread producer and MMA loops pay ~220 cycles
-  // per mbarrier wait and ~70 per commit (tools/mma_issue_bench.cu); a 256-wide tile has 512 cycles of tensor work per
-  // k-block to hide that, narrower tiles do not, so they move two k-blocks per barrier round trip.
-  static constexpr int KG = (BN >= 256) ? 1 : 2;
-  static constexpr int STAGE_BYTES = KG * (A_STAGE_BYTES + B_STAGE_BYTES);
-  static constexpr int STAGES = PIPE_BYTES_MAX / STAGE_BYTES > MAX_STAGES ? MAX_STAGES : PIPE_BYTES_MAX / STAGE_BYTES;
+  // ring depths when A and B both stream (a 3x3 group consumes one A slot and three B slots)
+  static constexpr int NA = (BN >= 128) ? 4 : (BN == 64 ? 5 : 6);
+  static constexpr int NB_FIT = (PIPE_BYTES_MAX - NA * A_SLOT_BYTES) / B_STAGE_BYTES;
+  static constexpr int NB = NB_FIT > MAX_STAGES ? MAX_STAGES : NB_FIT;
+  static_assert(NB >= 4, "B ring too shallow");
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + HDR_PAD + STAGES * STAGE_BYTES;
-  static constexpr int SMEM_BYTES_RB = 1024 + HDR_PAD + PIPE_BYTES_MAX;
 };
 
 // CS = thread-block cluster size along M: the CS CTAs of a cluster work on CS consecutive M tiles of the same N
@@ -100,151 +128,253 @@ struct Cfg {
 // CTA's (super) tiles; `stage`, `phase`, `it` are the calling thread's pipeline state and persist across calls, so a
 // persistent multi-layer kernel can chain convolutions through the same barriers and TMEM buffers.
 // ---------------------------------------------------------------------------------------------------------------
+struct PipeState {      // per-thread pipeline state; persists across convolutions of a multi-convolution launch
+  int a_stage, b_stage, it;
+  uint32_t a_phase, b_phase;
+};
+
 template <int BN, int CS, bool RB>
 __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CUtensorMap* tm_b_ptr, const ConvParams& p,
                                            uint8_t* smem_hdr, const uint32_t tmem_base, const int first_tile,
-                                           const int tile_stride, int& stage, uint32_t& phase, int& it) {
+                                           const int tile_stride, PipeState& ps) {
   using C = Cfg<BN>;
   const CUtensorMap& tm_a = *tm_a_ptr;
   const CUtensorMap& tm_b = *tm_b_ptr;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_hdr);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + MAX_STAGES;
-  uint64_t* tmem_full = bars + 2 * MAX_STAGES;
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + MAX_STAGES;
+  uint64_t* b_full_ring = bars + 2 * MAX_STAGES;
+  uint64_t* b_empty = bars + 3 * MAX_STAGES;
+  uint64_t* tmem_full = bars + 4 * MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* b_full = tmem_empty + 2;                     // resident weights have landed
-  const int k_blocks = p.num_taps * p.cin_chunks;
+  // everything the role loops need from the parameter block, read once (the asm statements in the loops clobber
+  // memory, so anything left in `p` would be re-read from the constant bank / shared memory every iteration)
+  const int cin_chunks = p.cin_chunks;
+  const int n_tiles = p.n_tiles;
+  const int splits = p.splits;
+  const int na = p.na_stages, nb = p.nb_stages;
+  const int a_box_bytes = p.a_box_bytes;
+  const int dbg_flags = p.dbg_flags;
+  long long* const trace = p.trace;
+  int tri = 0;
+  const int k_steps = p.n_groups * cin_chunks;           // one k-step = one A box = (group, 64-channel chunk)
   uint8_t* pipe = smem_hdr + HDR_PAD;                    // 1024-aligned operand area
-  // RB: [weights: k_blocks x (BN x 128 B)] [A stages]; otherwise STAGES x [A | B]
-  const int num_stages = RB ? p.rb_stages : C::STAGES;
-  constexpr int KG = C::KG;
-  const int stage_bytes = RB ? KG * A_STAGE_BYTES : C::STAGE_BYTES;
-  const int k_steps = (k_blocks + KG - 1) / KG;
-  uint8_t* smem = pipe + (RB ? p.rb_b_bytes : 0);        // base of the stage ring
+  uint8_t* a_ring = pipe + (RB ? p.rb_b_bytes : 0);
+  uint8_t* b_ring = a_ring + na * A_SLOT_BYTES;
+  int& it = ps.it;
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: tells the compiler it is warp-uniform, so the producer / MMA role loops below run
+  // converged and their addresses and descriptors live in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   // tile schedule: "super tiles" of CS consecutive M tiles x one N tile, N fastest, strided over the clusters
   const int cta_rank = (CS > 1) ? (int)hn_cluster_ctarank() : 0;
-  const int num_super = ((p.m_tiles + CS - 1) / CS) * p.n_tiles;
+  const int num_super = ((p.m_tiles + CS - 1) / CS) * n_tiles;
+  const int num_items = num_super * splits;
+  const int s_base = k_steps / splits, s_rem = k_steps - s_base * splits;
 
+  // The producer and MMA loops are single-instruction-stream code on the kernel's critical path (a 64-wide tile has
+  // only ~50 cycles of tensor work per MMA): no divisions or indexed parameter loads inside the k loop, descriptors
+  // advance by additions.
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      if constexpr (RB) {
-        // the layer's whole weight slice (n_tiles == 1), once per CTA
+    // All 32 lanes walk the loop and poll the barriers; one elected lane issues the copies.
+    int a_stage = ps.a_stage, b_stage = ps.b_stage;
+    uint32_t a_phase = ps.a_phase, b_phase = ps.b_phase;
+    if constexpr (RB) {
+      // the layer's whole weight slice (n_tiles == 1), once per CTA
+      if (hn_elect_one()) {
         hn_mbar_expect_tx(b_full, (uint32_t)p.rb_b_bytes);
+        const int k_blocks = p.num_taps * cin_chunks;
         for (int kb = 0; kb < k_blocks; ++kb)
           hn_tma_load_2d(pipe + kb * C::B_STAGE_BYTES, &tm_b, b_full, kb * BLOCK_K, 0);
       }
-      for (int w_ = first_tile; w_ < num_super * p.splits; w_ += tile_stride) {
-        const int st = w_ / p.splits, ks = w_ - st * p.splits;   // (super) tile and K split of this work item
-        const int s_base = k_steps / p.splits, s_rem = k_steps - s_base * p.splits;
-        const int s_begin = ks * s_base + (ks < s_rem ? ks : s_rem);
-        const int s_end = s_begin + s_base + (ks < s_rem ? 1 : 0);
-        const int m0 = ((st / p.n_tiles) * CS + cta_rank) * BLOCK_M;
-        const int n0 = (st % p.n_tiles) * BN;
-        int tap = (s_begin * KG) / p.cin_chunks;               // k-block kb = tap * cin_chunks + cc
-        int cc = s_begin * KG - tap * p.cin_chunks;
-        for (int step = s_begin; step < s_end; ++step) {
-          const int nk = (k_blocks - step * KG < KG) ? k_blocks - step * KG : KG;
-          hn_mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (p.dbg_flags & 8) {                               // timing experiment: no loads at all
-            hn_mbar_arrive(&full_bar[stage]);
+      __syncwarp();
+    }
+    for (int w_ = first_tile; w_ < num_items; w_ += tile_stride) {
+      int st = w_, s_begin = 0, s_end = k_steps, g = 0, cc = 0;
+      if (splits > 1) {                                    // (super) tile and K split of this work item
+        st = w_ / splits;
+        const int ks = w_ - st * splits;
+        s_begin = ks * s_base + (ks < s_rem ? ks : s_rem);
+        s_end = s_begin + s_base + (ks < s_rem ? 1 : 0);
+        g = s_begin / cin_chunks;                          // k-step = g * cin_chunks + cc
+        cc = s_begin - g * cin_chunks;
+      }
+      int mt = st, nt = 0;
+      if (n_tiles > 1) { mt = st / n_tiles; nt = st - mt * n_tiles; }
+      const int m0 = (mt * CS + cta_rank) * BLOCK_M;
+      const int n0 = nt * BN;
+      int info = p.grp_info[g], shift = p.grp_shift[g];
+      for (int step = s_begin; step < s_end; ++step) {
+        const int ntaps = info & 15;
+        // ---- the A box of this (group, chunk)
+        hn_mbar_wait(&a_empty[a_stage], a_phase ^ 1);
+        hn_trace(trace, 0, tri, 1);
+        if (hn_elect_one()) {
+          if (dbg_flags & 8) {                               // timing experiment: no loads at all
+            hn_mbar_arrive(&a_full[a_stage]);
           } else {
-            const uint32_t kb_bytes = RB ? A_STAGE_BYTES : (A_STAGE_BYTES + C::B_STAGE_BYTES);
-            hn_mbar_expect_tx(&full_bar[stage], nk * kb_bytes);
-            uint8_t* sa = smem + stage * stage_bytes;
-#pragma unroll
-            for (int g = 0; g < KG; ++g) {
-              if (g < nk) {
-                const int kb = step * KG + g;
-                hn_tma_load_3d(sa + g * A_STAGE_BYTES, &tm_a, &full_bar[stage], cc * BLOCK_K,
-                               m0 + p.tap_shift[tap] - p.dbg_shift, p.tap_phase[tap]);
-                if constexpr (RB) {
-                } else if constexpr (CS == 1) {
-                  hn_tma_load_2d(sa + KG * A_STAGE_BYTES + g * C::B_STAGE_BYTES, &tm_b, &full_bar[stage], kb * BLOCK_K, n0);
+            hn_mbar_expect_tx(&a_full[a_stage], (uint32_t)a_box_bytes);
+            hn_tma_load_3d(a_ring + a_stage * A_SLOT_BYTES, &tm_a, &a_full[a_stage], cc * BLOCK_K, m0 + shift, info >> 24);
+          }
+        }
+        if (++a_stage == na) { a_stage = 0; a_phase ^= 1; }
+        // ---- one weight tile per member tap
+        if constexpr (!RB) {
+          int kcol = (((info >> 8) & 255) * cin_chunks + cc) * BLOCK_K;     // K coordinate of the tap's weight tile
+          const int kcol_step = ((info >> 16) & 255) * cin_chunks * BLOCK_K;
+          for (int t = 0; t < ntaps; ++t) {
+            hn_mbar_wait(&b_empty[b_stage], b_phase ^ 1);
+            hn_trace(trace, 0, tri, 2);
+            if (hn_elect_one()) {
+              if (dbg_flags & 8) {
+                hn_mbar_arrive(&b_full_ring[b_stage]);
+              } else {
+                uint8_t* sb = b_ring + b_stage * C::B_STAGE_BYTES;
+                hn_mbar_expect_tx(&b_full_ring[b_stage], (uint32_t)C::B_STAGE_BYTES);
+                if constexpr (CS == 1) {
+                  hn_tma_load_2d(sb, &tm_b, &b_full_ring[b_stage], kcol, n0);
                 } else {
                   constexpr int SLICE = BN / CS;   // weight rows this CTA fetches for the whole cluster
-                  hn_tma_load_2d_mcast(sa + KG * A_STAGE_BYTES + g * C::B_STAGE_BYTES + cta_rank * SLICE * BLOCK_K * 2,
-                                       &tm_b, &full_bar[stage], kb * BLOCK_K, n0 + cta_rank * SLICE,
-                                       (uint16_t)((1u << CS) - 1u));
+                  hn_tma_load_2d_mcast(sb + cta_rank * SLICE * BLOCK_K * 2, &tm_b, &b_full_ring[b_stage], kcol,
+                                       n0 + cta_rank * SLICE, (uint16_t)((1u << CS) - 1u));
                 }
-                if (++cc == p.cin_chunks) { cc = 0; ++tap; }
               }
             }
+            kcol += kcol_step;
+            if (++b_stage == nb) { b_stage = 0; b_phase ^= 1; }
           }
-          if (++stage == num_stages) { stage = 0; phase ^= 1; }
+        }
+        if (++cc == cin_chunks) {
+          cc = 0;
+          ++g;
+          if (step + 1 < s_end) { info = p.grp_info[g]; shift = p.grp_shift[g]; }
         }
       }
     }
+    ps.a_stage = a_stage; ps.b_stage = b_stage; ps.a_phase = a_phase; ps.b_phase = b_phase;
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = hn_umma_idesc_bf16(BN);
-      int w_ = first_tile;
-      const int num_items = num_super * p.splits;
-      if constexpr (RB) hn_mbar_wait(b_full, 0);
-      if (w_ < num_items) {                                    // prime: this item's accumulator buffer and first stage
-        hn_mbar_wait(&tmem_empty[it & 1], ((it >> 1) & 1) ^ 1);
-        hn_mbar_wait(&full_bar[stage], phase);
-        hn_tc_fence_after();
+    // Converged warp; tcgen05.mma / commit are issued by one elected lane.
+    constexpr uint32_t idesc = hn_umma_idesc_bf16(BN);
+    constexpr uint32_t A_SLOT_D = A_SLOT_BYTES >> 4, B_SLOT_D = C::B_STAGE_BYTES >> 4, ROW_D = (BLOCK_K * 2) >> 4;
+    int a_stage = ps.a_stage, b_stage = ps.b_stage;
+    uint32_t a_phase = ps.a_phase, b_phase = ps.b_phase;
+    // low words of the shared-memory descriptors of slot 0 of each ring (start address >> 4 in bits 0..13); the high
+    // word is the same for every operand tile
+    const uint32_t a_desc0 = (uint32_t)hn_umma_smem_desc(hn_smem_u32(a_ring));
+    const uint32_t b_desc0 = (uint32_t)hn_umma_smem_desc(hn_smem_u32(RB ? pipe : b_ring));
+    const uint64_t desc_hi = hn_umma_smem_desc(0) & 0xffffffff00000000ull;
+    if constexpr (RB) hn_mbar_wait(b_full, 0);
+    // The tensor pipe queues only a few MMAs, so whatever the issuing thread does between two bursts must take less
+    // than the burst it has just issued needs to execute.  Wide tiles (256 columns: 512 cycles per tap) poll and issue
+    // tap by tap, so that a tap starts as soon as its weight tile has landed.  Narrow tiles have only ~50-64 cycles of
+    // tensor work per MMA: they poll all barriers of a k-step first and issue its (up to) 12 MMAs and their commits as
+    // one straight-line burst.
+    constexpr bool STEP_ISSUE = BN <= 128;
+    for (int w_ = first_tile; w_ < num_items; w_ += tile_stride, ++it) {
+      int s_begin = 0, s_end = k_steps, g = 0, cc = 0;
+      if (splits > 1) {
+        const int ks = w_ % splits;                          // K split of this work item
+        s_begin = ks * s_base + (ks < s_rem ? ks : s_rem);
+        s_end = s_begin + s_base + (ks < s_rem ? 1 : 0);
+        g = s_begin / cin_chunks;
+        cc = s_begin - g * cin_chunks;
       }
-      for (; w_ < num_items; w_ += tile_stride, ++it) {
-        const int ks = w_ % p.splits;                          // K split of this work item
-        const int s_base = k_steps / p.splits, s_rem = k_steps - s_base * p.splits;
-        const int s_begin = ks * s_base + (ks < s_rem ? ks : s_rem);
-        const int s_end = s_begin + s_base + (ks < s_rem ? 1 : 0);
-        const int buf = it & 1;
-        const uint32_t d_tmem = tmem_base + buf * BN;
-        const bool has_next_tile = w_ + tile_stride < num_items;
-        for (int step = s_begin; step < s_end; ++step) {
-          const int nk = (k_blocks - step * KG < KG) ? k_blocks - step * KG : KG;
-          const uint32_t a_addr = hn_smem_u32(smem + stage * stage_bytes);
-          if (!(p.dbg_flags & 4)) {                            // (timing experiment: bit 2 skips the MMAs)
-#pragma unroll
-            for (int g = 0; g < KG; ++g) {
-              if (g < nk) {
-                const int kb = step * KG + g;
-                const uint64_t da = hn_umma_smem_desc(a_addr + g * A_STAGE_BYTES + p.dbg_shift * 128) |
-                                    (uint64_t(p.dbg_base_offset ? (p.dbg_shift & 7) : 0) << 49);
-                const uint64_t db = hn_umma_smem_desc(RB ? hn_smem_u32(pipe + kb * C::B_STAGE_BYTES)
-                                                         : a_addr + KG * A_STAGE_BYTES + g * C::B_STAGE_BYTES);
-#pragma unroll
-                for (int k = 0; k < BLOCK_K / 16; ++k) {
-                  // +32 bytes per K=16 step inside the 128-byte swizzle span: start-address field += 2
-                  hn_umma_bf16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, ((step - s_begin) | g | k) != 0);
-                }
-              }
+      const int buf = it & 1;
+      const uint32_t d_tmem = tmem_base + buf * BN;
+      int info = p.grp_info[g];
+      if (!(dbg_flags & 32)) hn_mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);   // the epilogue has drained this buffer
+      hn_trace(trace, 1, tri, 4);
+      uint32_t accumulate = 0;
+      for (int step = s_begin; step < s_end; ++step) {
+        const int ntaps = info & 15;
+        const uint32_t off_step = ((info >> 4) & 15) * ROW_D;
+        const uint32_t da_lo = a_desc0 + a_stage * A_SLOT_D;
+        // resident weights: tile of tap (tap0 + t * tap_step), chunk cc
+        const uint32_t db_rb = b_desc0 + (((info >> 8) & 255) * cin_chunks + cc) * B_SLOT_D;
+        const uint32_t db_rb_step = ((info >> 16) & 255) * cin_chunks * B_SLOT_D;
+        const bool last = step == s_end - 1;
+        hn_mbar_wait(&a_full[a_stage], a_phase);
+        hn_trace(trace, 1, tri, 1);
+        if constexpr (STEP_ISSUE) {
+          // ring slots of the (up to) three weight tiles of this step
+          int bs1 = b_stage + 1, bs2 = b_stage + 2;
+          uint32_t bp1 = b_phase, bp2 = b_phase;
+          if (bs1 >= nb) { bs1 -= nb; bp1 ^= 1; }
+          if (bs2 >= nb) { bs2 -= nb; bp2 ^= 1; }
+          uint32_t db0 = db_rb, db1 = db_rb + db_rb_step, db2 = db_rb + 2 * db_rb_step;
+          if constexpr (!RB) {
+            hn_mbar_wait(&b_full_ring[b_stage], b_phase);
+            if (ntaps > 1) hn_mbar_wait(&b_full_ring[bs1], bp1);
+            if (ntaps > 2) hn_mbar_wait(&b_full_ring[bs2], bp2);
+            db0 = b_desc0 + b_stage * B_SLOT_D;
+            db1 = b_desc0 + bs1 * B_SLOT_D;
+            db2 = b_desc0 + bs2 * B_SLOT_D;
+          }
+          const uint32_t eb0 = hn_smem_u32(&b_empty[b_stage]), eb1 = hn_smem_u32(&b_empty[bs1]),
+                         eb2 = hn_smem_u32(&b_empty[bs2]);
+          const uint32_t ea = hn_smem_u32(&a_empty[a_stage]), tf = hn_smem_u32(&tmem_full[buf]);
+          hn_tc_fence_after();
+          if (hn_elect_one()) {
+            const bool mma = !(dbg_flags & 4);                // (timing experiment: bit 2 skips the MMAs)
+            if (mma) hn_umma_bf16_x4(d_tmem, desc_hi | da_lo, desc_hi | db0, idesc, accumulate);
+            if constexpr (!RB) hn_umma_commit_addr<CS>(eb0);
+            if (ntaps > 1) {
+              if (mma) hn_umma_bf16_x4(d_tmem, desc_hi | (da_lo + off_step), desc_hi | db1, idesc, 1u);
+              if constexpr (!RB) hn_umma_commit_addr<CS>(eb1);
+            }
+            if (ntaps > 2) {
+              if (mma) hn_umma_bf16_x4(d_tmem, desc_hi | (da_lo + 2 * off_step), desc_hi | db2, idesc, 1u);
+              if constexpr (!RB) hn_umma_commit_addr<CS>(eb2);
+            }
+            hn_umma_commit_addr<1>(ea);                       // A box free
+            if (last) hn_umma_commit_addr<1>(tf);             // accumulator complete -> epilogue
+          }
+          if constexpr (!RB) {
+            b_stage += ntaps;
+            if (b_stage >= nb) { b_stage -= nb; b_phase ^= 1; }
+          }
+        } else {
+          uint32_t da_t = da_lo, db_t = db_rb;
+          for (int t = 0; t < ntaps; ++t) {
+            if constexpr (!RB) {
+              hn_mbar_wait(&b_full_ring[b_stage], b_phase);
+              hn_trace(trace, 1, tri, 2);
+            }
+            hn_tc_fence_after();
+            const uint32_t db_lo = RB ? db_t : b_desc0 + b_stage * B_SLOT_D;
+            const uint32_t eb = hn_smem_u32(&b_empty[b_stage]);
+            if (hn_elect_one()) {
+              if (!(dbg_flags & 4)) hn_umma_bf16_x4(d_tmem, desc_hi | da_t, desc_hi | db_lo, idesc, accumulate);
+              if constexpr (!RB) hn_umma_commit_addr<CS>(eb);   // weight slot free once these MMAs have read it
+            }
+            accumulate = 1;
+            da_t += off_step;
+            db_t += db_rb_step;
+            if constexpr (!RB) {
+              if (++b_stage == nb) { b_stage = 0; b_phase ^= 1; }
             }
           }
-          const bool last = step == s_end - 1;
-          if (last) hn_umma_commit(&tmem_full[buf]);           // accumulator complete -> epilogue
-          int nstage = stage + 1;
-          uint32_t nphase = phase;
-          if (nstage == num_stages) { nstage = 0; nphase ^= 1; }
-          // release first (keeps the producer fed), then wait for the next stage / accumulator buffer
-          if (!p.lookahead) {
-            if constexpr (CS == 1) hn_umma_commit(&empty_bar[stage]);
-            else hn_umma_commit_mcast(&empty_bar[stage], (uint16_t)((1u << CS) - 1u));
+          const uint32_t ea = hn_smem_u32(&a_empty[a_stage]), tf = hn_smem_u32(&tmem_full[buf]);
+          if (hn_elect_one()) {
+            hn_umma_commit_addr<1>(ea);                         // A box free
+            if (last) hn_umma_commit_addr<1>(tf);               // accumulator complete -> epilogue
           }
-          if (!last) {
-            hn_mbar_wait(&full_bar[nstage], nphase);
-            hn_tc_fence_after();
-          } else if (has_next_tile) {
-            hn_mbar_wait(&tmem_empty[(it + 1) & 1], (((it + 1) >> 1) & 1) ^ 1);
-            hn_mbar_wait(&full_bar[nstage], nphase);
-            hn_tc_fence_after();
-          }
-          if (p.lookahead) {                                   // experiment: release after the look-ahead wait
-            if constexpr (CS == 1) hn_umma_commit(&empty_bar[stage]);
-            else hn_umma_commit_mcast(&empty_bar[stage], (uint16_t)((1u << CS) - 1u));
-          }
-          stage = nstage;
-          phase = nphase;
+        }
+        accumulate = 1;
+        hn_trace(trace, 1, tri, 3);
+        if (++a_stage == na) { a_stage = 0; a_phase ^= 1; }
+        if (++cc == cin_chunks) {
+          cc = 0;
+          ++g;
+          if (!last) info = p.grp_info[g];
         }
       }
     }
+    ps.a_stage = a_stage; ps.b_stage = b_stage; ps.a_phase = a_phase; ps.b_phase = b_phase;
   } else {
     // ===================================== epilogue ==========================================
     const int quarter = warp & 3;              // TMEM lanes this warp may touch: 32*quarter .. +31
@@ -262,24 +392,32 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       hn_epi_bar_sync();
     }
     uint32_t* sk_flag = reinterpret_cast<uint32_t*>(b_full + 1) + 1;   // "this CTA finalises the tile" (after tmem_slot)
-    for (int w_ = first_tile; w_ < num_super * p.splits; w_ += tile_stride, ++it) {
-      const int st = w_ / p.splits;
+    if (dbg_flags & 32) return;                   // experiment: no epilogue role at all (the MMA warp does not wait for it)
+    const uint32_t div_img_mul = p.div_img_mul, div_wp_mul = p.div_wp_mul;
+    const int div_img_sh = p.div_img_sh, div_wp_sh = p.div_wp_sh;
+    const int rows = p.rows, wp = p.wp, halo = p.halo;
+    int ss_n0[2] = {-1, -1};                    // N tile whose scale/shift each staging buffer holds
+    for (int w_ = first_tile; w_ < num_items; w_ += tile_stride, ++it) {
+      const int st = splits > 1 ? w_ / splits : w_;
+      if (warp == 2) hn_trace(trace, 2, tri, 1);
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = ((st / p.n_tiles) * CS + cta_rank) * BLOCK_M;
-      const int n0 = (st % p.n_tiles) * BN;
+      int mt = st, nt = 0;
+      if (n_tiles > 1) { mt = st / n_tiles; nt = st - mt * n_tiles; }
+      const int m0 = (mt * CS + cta_rank) * BLOCK_M;
+      const int n0 = nt * BN;
       const int m = m0 + quarter * 32 + lane;
-      // decode the padded pixel this accumulator row belongs to
+      // decode the padded pixel this accumulator row belongs to (divisions by multiply-high, see fastdiv())
       int img = 0, h = 0, w = 0;
       bool interior = false;
-      if (m < p.rows) {
-        img = m / img_rows;
+      if (m < rows) {
+        img = (int)((__umulhi((uint32_t)m, div_img_mul) + (uint32_t)m) >> div_img_sh);
         const int rem = m - img * img_rows;
-        const int hh = rem / p.wp;
-        const int ww = rem - hh * p.wp;
-        h = hh - p.halo;
-        w = ww - p.halo;
-        interior = (h >= 0) && (w >= 0) && (h < p.hp - 2 * p.halo) && (w < p.wp - 2 * p.halo);
+        const int hh = (int)((__umulhi((uint32_t)rem, div_wp_mul) + (uint32_t)rem) >> div_wp_sh);
+        const int ww = rem - hh * wp;
+        h = hh - halo;
+        w = ww - halo;
+        interior = (h >= 0) && (w >= 0) && (h < p.hp - 2 * halo) && (w < wp - 2 * halo);
       }
       const int H = p.hp - 2 * p.halo, W = p.wp - 2 * p.halo;
       // output / residual element offsets of channel 0 of this row
@@ -309,12 +447,15 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
 
       constexpr int CHUNK = (BN >= 32) ? 32 : 16;
       float* ss = ss_base + (it & 1) * 512;   // [0,256) scale, [256,512) shift for columns n0 .. n0+BN
-      for (int i = threadIdx.x - 64; i < BN; i += EPI_THREADS) {
-        const int c = n0 + i;
-        ss[i] = (p.scale && c < p.cout) ? __ldg(p.scale + c) : 1.0f;
-        ss[256 + i] = (p.shift && c < p.cout) ? __ldg(p.shift + c) : 0.0f;
+      if (ss_n0[it & 1] != n0) {              // (uniform over the epilogue warps) staged once per N tile, not per tile
+        for (int i = threadIdx.x - 64; i < BN; i += EPI_THREADS) {
+          const int c = n0 + i;
+          ss[i] = (p.scale && c < p.cout) ? __ldg(p.scale + c) : 1.0f;
+          ss[256 + i] = (p.shift && c < p.cout) ? __ldg(p.shift + c) : 0.0f;
+        }
+        ss_n0[it & 1] = n0;
+        hn_epi_bar_sync();
       }
-      hn_epi_bar_sync();
       // residual rows are fetched one chunk ahead (the first one before the accumulator wait) so that their
       // global-load latency hides behind the wait / the previous chunk's work
       const bool res_vec = p.res_mode != 0 && interior && (p.cout & 7) == 0;
@@ -328,8 +469,14 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
           res_next[j] = __ldg(reinterpret_cast<const uint4*>(p.res + res_off + n0 + c_first) + j);
       }
 
-      hn_mbar_wait(&tmem_full[buf], acc_phase);
+      if (dbg_flags & 16) {                      // experiment: one polling lane per warp
+        if (lane == 0) hn_mbar_wait(&tmem_full[buf], acc_phase);
+        __syncwarp();
+      } else {
+        hn_mbar_wait(&tmem_full[buf], acc_phase);
+      }
       hn_tc_fence_after();
+      if (warp == 2) hn_trace(trace, 2, tri, 2);
       const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + buf * BN;
 
       // Split-K: every work item adds its partial accumulator into an fp32 scratch tile with vector reductions; the
@@ -551,6 +698,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
         __syncwarp();
         if (lane == 0) hn_mbar_arrive(&tmem_empty[buf]);
       }
+      if (warp == 2) hn_trace(trace, 2, tri, 3);
     }
     if (gn_smem) {
       hn_epi_bar_sync();
@@ -565,22 +713,25 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
 
 // Barrier init, TMEM allocation.  Returns the TMEM base address.
 template <int BN, int CS>
-__device__ __forceinline__ uint32_t conv_prologue(uint8_t* smem_hdr, int num_stages, const CUtensorMap* pf_a,
-                                                  const CUtensorMap* pf_b) {
+__device__ __forceinline__ uint32_t conv_prologue(uint8_t* smem_hdr, const CUtensorMap* pf_a, const CUtensorMap* pf_b) {
   using C = Cfg<BN>;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_hdr);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + MAX_STAGES;
-  uint64_t* tmem_full = bars + 2 * MAX_STAGES;
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + MAX_STAGES;
+  uint64_t* b_full_ring = bars + 2 * MAX_STAGES;
+  uint64_t* b_empty = bars + 3 * MAX_STAGES;
+  uint64_t* tmem_full = bars + 4 * MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* b_full = tmem_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
   if (threadIdx.x == 0) {
     if (pf_a) hn_tma_prefetch_desc(pf_a);
     if (pf_b) hn_tma_prefetch_desc(pf_b);
-    for (int s = 0; s < num_stages; ++s) {
-      hn_mbar_init(&full_bar[s], 1);
-      hn_mbar_init(&empty_bar[s], CS);   // every CTA of the cluster releases the slot (its peers write into it)
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      hn_mbar_init(&a_full[s], 1);
+      hn_mbar_init(&a_empty[s], 1);      // A boxes are private to the CTA
+      hn_mbar_init(&b_full_ring[s], 1);
+      hn_mbar_init(&b_empty[s], CS);     // every CTA of the cluster releases the slot (its peers write into it)
     }
     hn_mbar_init(b_full, 1);
     for (int b = 0; b < 2; ++b) {
@@ -620,15 +771,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   static_assert(!(RB && CS > 1), "resident weights are per CTA");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem_hdr = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t tmem_base = conv_prologue<BN, CS>(smem_hdr, RB ? p.rb_stages : Cfg<BN>::STAGES, &tm_a, &tm_b);
+  const uint32_t tmem_base = conv_prologue<BN, CS>(smem_hdr, &tm_a, &tm_b);
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may run
   // while the previous kernel of the stream is still draining; global memory is touched only after the wait.
   // The early trigger lets the next kernel do the same under this one.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  int stage = 0, it = 0;
-  uint32_t phase = 0;
-  conv_roles<BN, CS, RB>(&tm_a, &tm_b, p, smem_hdr, tmem_base, blockIdx.x / CS, gridDim.x / CS, stage, phase, it);
+  PipeState ps = {0, 0, 0, 0u, 0u};
+  conv_roles<BN, CS, RB>(&tm_a, &tm_b, p, smem_hdr, tmem_base, blockIdx.x / CS, gridDim.x / CS, ps);
   conv_teardown<BN, CS>(tmem_base);
 }
 
@@ -673,9 +823,8 @@ conv_multi_kernel(const PhaseDesc* __restrict__ phases, const int* __restrict__ 
   extern __shared__ uint8_t smem_raw[];
   __shared__ ConvParams sp;
   uint8_t* smem_hdr = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t tmem_base = conv_prologue<BN, 1>(smem_hdr, Cfg<BN>::STAGES, nullptr, nullptr);
-  int stage = 0, it = 0;
-  uint32_t phase = 0;
+  const uint32_t tmem_base = conv_prologue<BN, 1>(smem_hdr, nullptr, nullptr);
+  PipeState ps = {0, 0, 0, 0u, 0u};
   for (int g = 0; g < num_groups; ++g) {
     int tile_off = 0;                                    // tiles of the group's convs are dealt round-robin
     for (int j = group_begin[g]; j < group_begin[g + 1]; ++j) {
@@ -686,7 +835,7 @@ conv_multi_kernel(const PhaseDesc* __restrict__ phases, const int* __restrict__ 
       const int tiles = sp.m_tiles * sp.n_tiles * sp.splits;
       int first = ((int)blockIdx.x - tile_off) % (int)gridDim.x;
       if (first < 0) first += gridDim.x;
-      conv_roles<BN, 1, false>(&phases[j].ta, &phases[j].tb, sp, smem_hdr, tmem_base, first, gridDim.x, stage, phase, it);
+      conv_roles<BN, 1, false>(&phases[j].ta, &phases[j].tb, sp, smem_hdr, tmem_base, first, gridDim.x, ps);
       tile_off = (tile_off + tiles) % (int)gridDim.x;
     }
     if (g + 1 < num_groups) grid_barrier(counter, (unsigned)(g + 1) * gridDim.x);
@@ -744,7 +893,7 @@ bool pdl_enabled() {
 template <int BN, int CS, bool RB>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t st) {
   using C = Cfg<BN>;
-  constexpr int SMEM = RB ? C::SMEM_BYTES_RB : C::SMEM_BYTES;
+  constexpr int SMEM = SMEM_BYTES_ALL;
   static bool attr_set = false;
   if (!attr_set) {
     HN_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, CS, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -804,6 +953,16 @@ int pick_block_n(int cout_pad, int m_tiles, int k_blocks, int min_bn) {
   return best ? best : 16;
 }
 
+// Division by an invariant d >= 1 as (umulhi(x, mul) + x) >> sh, exact for 0 <= x < 2^31 (Granlund-Montgomery round-up
+// method with a 33-bit multiplier 2^32 + mul).
+void fastdiv(uint32_t d, uint32_t* mul, int* sh) {
+  int l = 0;
+  while ((1ull << l) < d) ++l;                                        // l = ceil(log2 d)
+  const unsigned long long m = ((1ull << 32) * ((1ull << l) - d)) / d + 1;   // floor(2^32 * (2^l - d) / d) + 1
+  *mul = (uint32_t)m;
+  *sh = l;
+}
+
 struct BuiltConv {
   ConvParams p;
   CUtensorMap ta, tb;
@@ -837,23 +996,45 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
   const long long rows_ll = (long long)d->n * p.hp * p.wp;
   HN_REQUIRE(rows_ll < (1ll << 31) - 4096, "hn_conv2d_bf16: too many rows");
   p.rows = (int)rows_ll;
+  fastdiv((uint32_t)(p.hp * p.wp), &p.div_img_mul, &p.div_img_sh);
+  fastdiv((uint32_t)p.wp, &p.div_wp_mul, &p.div_wp_sh);
   p.cin_chunks = d->cin / BLOCK_K;
   p.num_taps = d->kh * d->kw;
-  for (int r = 0; r < d->kh; ++r)
-    for (int s = 0; s < d->kw; ++s) {
-      const int t = r * d->kw + s;
-      const int dr = (r - d->kh / 2) * d->dilation, ds = (s - d->kw / 2) * d->dilation;
+  // A-box groups.  Pixel (oh*stride + dr, ow*stride + ds) of tap (r, s), dr = (r - kh/2)*dil, ds = (s - kw/2)*dil, is row
+  // m + shift of the (phase) matrix; taps of one kernel row whose shifts differ by a few rows share one box.
+  HN_REQUIRE(2 * d->dilation <= A_BOX_ROWS_MAX - BLOCK_M, "hn_conv2d_bf16: dilation %d too large for a shared A box",
+             d->dilation);
+  int box_rows = BLOCK_M;
+  p.n_groups = 0;
+  auto add_group = [&](int phase, int shift, int ntaps, const int* taps, const int* offs) {
+    const int g = p.n_groups++;
+    const int off_step = ntaps > 1 ? offs[1] - offs[0] : 0, tap_step = ntaps > 1 ? taps[1] - taps[0] : 0;
+    p.grp_shift[g] = shift;
+    p.grp_info[g] = ntaps | (off_step << 4) | (taps[0] << 8) | (tap_step << 16) | (phase << 24);
+    if (off_step > 0) box_rows = A_BOX_ROWS_MAX;
+  };
+  if (d->kh == 1) {
+    const int taps[1] = {0}, offs[1] = {0};
+    add_group(0, 0, 1, taps, offs);
+  } else {
+    for (int r = 0; r < 3; ++r) {
+      const int dr = (r - 1) * d->dilation;
       if (d->stride == 1) {
-        p.tap_shift[t] = dr * p.wp + ds;
-        p.tap_phase[t] = 0;
+        const int taps[3] = {r * 3, r * 3 + 1, r * 3 + 2};
+        const int offs[3] = {0, d->dilation, 2 * d->dilation};
+        add_group(0, dr * p.wp - d->dilation, 3, taps, offs);
       } else {
-        // input pixel (2*oh + dr, 2*ow + ds) lives in phase (dr&1, ds&1) at (oh + floor(dr/2), ow + floor(ds/2))
-        const int pr = dr & 1, ps = ds & 1;
-        const int fr = (dr - pr) / 2, fs = (ds - ps) / 2;
-        p.tap_shift[t] = fr * p.wp + fs;
-        p.tap_phase[t] = pr * 2 + ps;
+        // input pixel (2*oh + dr, 2*ow + ds) lives in phase (dr&1, ds&1) at (oh + floor(dr/2), ow + floor(ds/2)):
+        // ds = -1 -> column phase 1 at ow-1, ds = +1 -> column phase 1 at ow (one box), ds = 0 -> column phase 0
+        const int pr = dr & 1, fr = (dr - pr) / 2;
+        const int taps_odd[2] = {r * 3, r * 3 + 2}, offs_odd[2] = {0, 1};
+        add_group(pr * 2 + 1, fr * p.wp - 1, 2, taps_odd, offs_odd);
+        const int taps_even[1] = {r * 3 + 1}, offs_even[1] = {0};
+        add_group(pr * 2, fr * p.wp, 1, taps_even, offs_even);
       }
     }
+  }
+  p.a_box_bytes = box_rows * BLOCK_K * 2;
   p.m_tiles = hn_div_up(p.rows, BLOCK_M);
   int bn = force_bn ? force_bn
                     : (d->block_n ? d->block_n
@@ -865,16 +1046,25 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
   // measured: pairs with multicast weights gain ~3 % on 256-wide tiles and lose elsewhere -> opt-in only
   int cs = (d->cluster && !force_bn) ? d->cluster : 1;
   HN_REQUIRE(cs == 1 || (cs == 2 && bn >= 64), "hn_conv2d_bf16: cluster=%d unsupported with block_n=%d", cs, bn);
-  // resident weights: the layer's whole weight slice stays in shared memory and only A tiles stream, when it is one
-  // narrow N tile whose weights fit next to >= 6 A stages and there are enough tiles per CTA to amortise the load
+  // resident weights: the layer's whole weight slice stays in shared memory and only A boxes stream, when it is one
+  // narrow N tile whose weights fit next to >= 4 A slots and there are enough tiles per CTA to amortise the load
   const int k_blocks_total = p.num_taps * p.cin_chunks;
   const long long b_bytes = (long long)k_blocks_total * bn * BLOCK_K * 2;
-  bool rb = !force_bn && cs == 1 && p.n_tiles == 1 && bn <= 64 && b_bytes <= PIPE_BYTES_MAX - 3 * 2 * A_STAGE_BYTES &&
+  bool rb = !force_bn && cs == 1 && p.n_tiles == 1 && bn <= 64 && b_bytes <= PIPE_BYTES_MAX - 4 * A_SLOT_BYTES &&
             p.m_tiles >= 2 * hn_num_sms() && !(d->debug & 16);
   if (rb) {
     p.rb_b_bytes = (int)b_bytes;
-    int stages = (PIPE_BYTES_MAX - p.rb_b_bytes) / (2 * A_STAGE_BYTES);   // KG = 2 A tiles per stage for BN <= 64
-    p.rb_stages = stages > MAX_STAGES ? MAX_STAGES : stages;
+    const int slots = (PIPE_BYTES_MAX - p.rb_b_bytes) / A_SLOT_BYTES;
+    p.na_stages = slots > MAX_STAGES ? MAX_STAGES : slots;
+    p.nb_stages = 1;
+  } else {
+    switch (bn) {
+      case 256: p.na_stages = Cfg<256>::NA; p.nb_stages = Cfg<256>::NB; break;
+      case 128: p.na_stages = Cfg<128>::NA; p.nb_stages = Cfg<128>::NB; break;
+      case 64: p.na_stages = Cfg<64>::NA; p.nb_stages = Cfg<64>::NB; break;
+      case 32: p.na_stages = Cfg<32>::NA; p.nb_stages = Cfg<32>::NB; break;
+      default: p.na_stages = Cfg<16>::NA; p.nb_stages = Cfg<16>::NB; break;
+    }
   }
   p.cout = d->cout;
   p.scale = d->scale;
@@ -911,10 +1101,8 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
     p.ph_wp = (d->w + 1) / 2 + 2 * d->out_phase_halo;
     p.ph_stride = (long long)d->n * p.ph_hp * p.ph_wp * d->cout;
   }
-  p.lookahead = (d->debug >> 10) & 1;
-  p.dbg_flags = (d->debug >> 6) & 15;     // bit0: no epilogue stores, bit1: no epilogue work at all (timing experiments)
-  p.dbg_shift = d->debug & 7;
-  p.dbg_base_offset = (d->debug >> 3) & 1;
+  p.trace = reinterpret_cast<long long*>(d->trace);
+  p.dbg_flags = (d->debug >> 6) & 255;     // bit0: no epilogue stores, bit1: no epilogue work at all (timing experiments)
   p.gn_stats = d->gn_stats;
   if (p.gn_stats) {
     HN_REQUIRE(d->gn_groups > 0 && d->cout % d->gn_groups == 0, "hn_conv2d_bf16: gn_groups");
@@ -928,17 +1116,16 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
   // split-K (needs caller-provided scratch): short, deep layers whose tiles cannot fill the GPU
   p.splits = 1;
   if (d->splitk_ws && d->splitk_counters && cs == 1 && bn >= 32) {
-    const int kg = bn >= 256 ? 1 : 2;
-    const int k_steps = hn_div_up(k_blocks_total, kg);
+    const int k_steps = p.n_groups * p.cin_chunks;
     const int tiles = p.m_tiles * p.n_tiles;
     int sp = d->splits;
     if (sp <= 0) {
       sp = 1;
       // measured (tools/a2j_timing.py): the reduction + counter round trip + read-back cost ~3-4 us per layer, a
-      // pipeline step ~0.4 us, so only deep layers (>= 24 steps) gain
-      if (tiles * 2 <= hn_num_sms() && k_steps >= 24) {
+      // k-block ~0.2 us, so only deep layers (>= 48 k-blocks) gain, with at least 12 k-blocks per split
+      if (tiles * 2 <= hn_num_sms() && k_blocks_total >= 48) {
         sp = hn_num_sms() / tiles;
-        if (sp > k_steps / 6) sp = k_steps / 6;
+        if (sp > k_blocks_total / 12) sp = k_blocks_total / 12;
         if (sp > 16) sp = 16;
         if (sp < 1) sp = 1;
       }
@@ -960,7 +1147,7 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
   {
     const cuuint64_t dims[3] = {(cuuint64_t)d->cin, (cuuint64_t)p.rows, (cuuint64_t)d->in_phases};
     const cuuint64_t strides[2] = {(cuuint64_t)d->cin * 2, (cuuint64_t)p.rows * d->cin * 2};
-    const cuuint32_t box[3] = {BLOCK_K, BLOCK_M, 1};
+    const cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)box_rows, 1};
     int rc = make_map(&ta, d->in, 3, dims, strides, box);
     if (rc) return rc;
   }
@@ -1070,7 +1257,7 @@ extern "C" int hn_conv_multi_run(void* plan_dev, int n_convs, int n_groups, int 
   static bool attr_set = false;
   if (!attr_set) {
     HN_CHECK_CUDA(cudaFuncSetAttribute(conv_multi_kernel<MULTI_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       C::SMEM_BYTES));
+                                       SMEM_BYTES_ALL));
     attr_set = true;
   }
   uint8_t* base = reinterpret_cast<uint8_t*>(plan_dev);
@@ -1079,7 +1266,7 @@ extern "C" int hn_conv_multi_run(void* plan_dev, int n_convs, int n_groups, int 
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.dynamicSmemBytes = SMEM_BYTES_ALL;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeCooperative;              // all CTAs resident: the grid barrier cannot deadlock

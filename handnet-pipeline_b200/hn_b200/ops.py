@@ -175,7 +175,7 @@ def conv2d(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 1, d
            out_f32: Optional[torch.Tensor] = None, out_rows_per_image: int = 0, out_row_offset: int = 0,
            out_transpose_hw: bool = False, out_phase: Optional[PhaseAct] = None,
            gn_stats: Optional[torch.Tensor] = None, gn_groups: int = 0, block_n: int = 0, cluster: int = 0,
-           algo_k: int = 0, debug: int = 0, splitk=None, splits: int = 0):
+           algo_k: int = 0, debug: int = 0, splitk=None, splits: int = 0, trace: Optional[torch.Tensor] = None):
     """hn_conv2d_bf16.  x: Act (stride 1) or PhaseAct (stride 2).  relu: bool or (lo, hi) channel range."""
     d = ConvDesc()
     if isinstance(x, PhaseAct):
@@ -214,6 +214,9 @@ def conv2d(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 1, d
     d.block_n = block_n
     d.cluster = cluster
     d.debug = debug
+    if trace is not None:
+        assert trace.dtype == torch.int64 and trace.numel() >= 3 * 2048 * 2
+        d.trace = trace.data_ptr()
     if splitk is not None:            # (fp32 scratch, uint32 counters): both zero, exclusive to this conv
         ws_t, cnt_t = splitk
         d.splitk_ws, d.splitk_ws_bytes = ws_t.data_ptr(), ws_t.numel() * ws_t.element_size()

@@ -100,6 +100,9 @@ typedef struct hn_conv_desc {
   void* splitk_counters;
   int splitk_counters_len;
   int splits;
+  /* bring-up only: NULL in production.  When set, CTA 0 logs (clock64, tag) pairs of its producer, MMA and first
+   * epilogue warp into trace[3][2048][2] (int64) -- see tools/conv_trace.py. */
+  void* trace;
 } hn_conv_desc;
 int hn_conv2d_bf16(const hn_conv_desc* desc, void* stream);
 
