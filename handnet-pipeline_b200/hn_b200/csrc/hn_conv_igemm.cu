@@ -54,8 +54,18 @@ struct ConvParams {
   // packed: ntaps | off_step << 4 | tap0 << 8 | tap_step << 16 | phase << 24.  Member t of the group is weight tap
   // tap0 + t * tap_step (r * kw + s) and reads the box from row t * off_step on; phase = phase image of the input
   int grp_info[MAX_TAPS];
+  // unified stages (tiles of <= 128 columns, streamed weights): one stage = one A box (1-3 planes) + one B box (1-3
+  // weight tiles), two TMA operations and one barrier pair per k-step.  Unit u of group g multiplies A plane
+  // (units >> 8u) & 3 from row ((units >> (8u+2)) & 15) on with weight tile (units >> (8u+6)) & 3.
+  int grp_units[MAX_TAPS];
+  int k_steps;                              // k-steps per tile
+  int uni_a_bytes, uni_b_bytes;             // bytes the two boxes of a stage bring
+  int uni_plane_bytes;                      // distance between A planes inside a stage
+  int uni_stages, uni_chunk_step;           // ring depth; 64-channel chunks per k-step (1x1 convolutions: up to 2)
+  int uni_stride;                           // bytes between stages (>= uni_a_bytes + uni_b_bytes)
+  int uni_a_rank4;                          // the A tensor map is 4-D (channels, rows, chunks, phases)
   int m_tiles, n_tiles;
-  int cout;
+  int cout, cout_pad;
   const float* scale;
   const float* shift;
   int relu_lo, relu_hi;
@@ -113,7 +123,7 @@ template <int BN>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
   // ring depths when A and B both stream (a 3x3 group consumes one A slot and three B slots)
-  static constexpr int NA = (BN >= 128) ? 4 : (BN == 64 ? 5 : 6);
+  static constexpr int NA = 4;   // (only the 256-wide tiles use two rings; narrower ones use unified stages)
   static constexpr int NB_FIT = (PIPE_BYTES_MAX - NA * A_SLOT_BYTES) / B_STAGE_BYTES;
   static constexpr int NB = NB_FIT > MAX_STAGES ? MAX_STAGES : NB_FIT;
   static_assert(NB >= 4, "B ring too shallow");
@@ -155,10 +165,11 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
   const int splits = p.splits;
   const int na = p.na_stages, nb = p.nb_stages;
   const int a_box_bytes = p.a_box_bytes;
+  const int cout_pad = p.cout_pad;
   const int dbg_flags = p.dbg_flags;
   long long* const trace = p.trace;
   int tri = 0;
-  const int k_steps = p.n_groups * cin_chunks;           // one k-step = one A box = (group, 64-channel chunk)
+  const int k_steps = p.k_steps;                         // one k-step = one A box
   uint8_t* pipe = smem_hdr + HDR_PAD;                    // 1024-aligned operand area
   uint8_t* a_ring = pipe + (RB ? p.rb_b_bytes : 0);
   uint8_t* b_ring = a_ring + na * A_SLOT_BYTES;
@@ -188,10 +199,13 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
         hn_mbar_expect_tx(b_full, (uint32_t)p.rb_b_bytes);
         const int k_blocks = p.num_taps * cin_chunks;
         for (int kb = 0; kb < k_blocks; ++kb)
-          hn_tma_load_2d(pipe + kb * C::B_STAGE_BYTES, &tm_b, b_full, kb * BLOCK_K, 0);
+          hn_tma_load_2d(pipe + kb * C::B_STAGE_BYTES, &tm_b, b_full, 0, kb * p.cout_pad);
       }
       __syncwarp();
     }
+    constexpr bool UNI = (BN <= 128) && !RB;               // unified stages (see ConvParams)
+    const int uni_stage_bytes = p.uni_a_bytes + p.uni_b_bytes, uni_chunk_step = p.uni_chunk_step;
+    const int uni_stride = p.uni_stride;
     for (int w_ = first_tile; w_ < num_items; w_ += tile_stride) {
       int st = w_, s_begin = 0, s_end = k_steps, g = 0, cc = 0;
       if (splits > 1) {                                    // (super) tile and K split of this work item
@@ -199,14 +213,44 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
         const int ks = w_ - st * splits;
         s_begin = ks * s_base + (ks < s_rem ? ks : s_rem);
         s_end = s_begin + s_base + (ks < s_rem ? 1 : 0);
-        g = s_begin / cin_chunks;                          // k-step = g * cin_chunks + cc
-        cc = s_begin - g * cin_chunks;
+        if (UNI && uni_chunk_step > 1) {                   // 1x1: one group, k-step = chunk pair
+          g = 0;
+          cc = s_begin * uni_chunk_step;
+        } else {
+          g = s_begin / cin_chunks;                        // k-step = g * cin_chunks + cc
+          cc = s_begin - g * cin_chunks;
+        }
       }
       int mt = st, nt = 0;
       if (n_tiles > 1) { mt = st / n_tiles; nt = st - mt * n_tiles; }
       const int m0 = (mt * CS + cta_rank) * BLOCK_M;
       const int n0 = nt * BN;
       int info = p.grp_info[g], shift = p.grp_shift[g];
+      if constexpr (UNI) {
+        for (int step = s_begin; step < s_end; ++step) {
+          hn_mbar_wait(&a_empty[a_stage], a_phase ^ 1);
+          hn_trace(trace, 0, tri, 1);
+          if (hn_elect_one()) {
+            if (dbg_flags & 8) {                             // timing experiment: no loads at all
+              hn_mbar_arrive(&a_full[a_stage]);
+            } else {
+              uint8_t* sa = a_ring + a_stage * uni_stride;
+              hn_mbar_expect_tx(&a_full[a_stage], (uint32_t)uni_stage_bytes);
+              if (p.uni_a_rank4) hn_tma_load_4d(sa, &tm_a, &a_full[a_stage], 0, m0 + shift, cc, info >> 24);
+              else hn_tma_load_3d(sa, &tm_a, &a_full[a_stage], cc * BLOCK_K, m0 + shift, info >> 24);
+              hn_tma_load_4d(sa + p.uni_a_bytes, &tm_b, &a_full[a_stage], 0, n0, cc, (info >> 8) & 255);
+            }
+          }
+          if (++a_stage == na) { a_stage = 0; a_phase ^= 1; }
+          cc += uni_chunk_step;
+          if (cc >= cin_chunks) {
+            cc = 0;
+            ++g;
+            if (step + 1 < s_end) { info = p.grp_info[g]; shift = p.grp_shift[g]; }
+          }
+        }
+        continue;
+      }
       for (int step = s_begin; step < s_end; ++step) {
         const int ntaps = info & 15;
         // ---- the A box of this (group, chunk)
@@ -223,8 +267,10 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
         if (++a_stage == na) { a_stage = 0; a_phase ^= 1; }
         // ---- one weight tile per member tap
         if constexpr (!RB) {
-          int kcol = (((info >> 8) & 255) * cin_chunks + cc) * BLOCK_K;     // K coordinate of the tap's weight tile
-          const int kcol_step = ((info >> 16) & 255) * cin_chunks * BLOCK_K;
+          // weights are stored k-block major ([k_block][cout_pad][64]): the tile of (k-block, n0) is one contiguous
+          // run of BN * 128 bytes starting at row k_block * cout_pad + n0
+          int krow = (((info >> 8) & 255) * cin_chunks + cc) * cout_pad + n0;
+          const int krow_step = ((info >> 16) & 255) * cin_chunks * cout_pad;
           for (int t = 0; t < ntaps; ++t) {
             hn_mbar_wait(&b_empty[b_stage], b_phase ^ 1);
             hn_trace(trace, 0, tri, 2);
@@ -235,15 +281,15 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
                 uint8_t* sb = b_ring + b_stage * C::B_STAGE_BYTES;
                 hn_mbar_expect_tx(&b_full_ring[b_stage], (uint32_t)C::B_STAGE_BYTES);
                 if constexpr (CS == 1) {
-                  hn_tma_load_2d(sb, &tm_b, &b_full_ring[b_stage], kcol, n0);
+                  hn_tma_load_2d(sb, &tm_b, &b_full_ring[b_stage], 0, krow);
                 } else {
                   constexpr int SLICE = BN / CS;   // weight rows this CTA fetches for the whole cluster
-                  hn_tma_load_2d_mcast(sb + cta_rank * SLICE * BLOCK_K * 2, &tm_b, &b_full_ring[b_stage], kcol,
-                                       n0 + cta_rank * SLICE, (uint16_t)((1u << CS) - 1u));
+                  hn_tma_load_2d_mcast(sb + cta_rank * SLICE * BLOCK_K * 2, &tm_b, &b_full_ring[b_stage], 0,
+                                       krow + cta_rank * SLICE, (uint16_t)((1u << CS) - 1u));
                 }
               }
             }
-            kcol += kcol_step;
+            krow += krow_step;
             if (++b_stage == nb) { b_stage = 0; b_phase ^= 1; }
           }
         }
@@ -274,14 +320,23 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
     // tensor work per MMA: they poll all barriers of a k-step first and issue its (up to) 12 MMAs and their commits as
     // one straight-line burst.
     constexpr bool STEP_ISSUE = BN <= 128;
+    constexpr bool UNI = (BN <= 128) && !RB;               // unified stages: one barrier pair and one burst per k-step
+    const uint32_t uni_stage_d = (uint32_t)p.uni_stride >> 4, uni_a_d = (uint32_t)p.uni_a_bytes >> 4;
+    const uint32_t uni_plane_d = (uint32_t)p.uni_plane_bytes >> 4;
+    const int uni_chunk_step = p.uni_chunk_step;
     for (int w_ = first_tile; w_ < num_items; w_ += tile_stride, ++it) {
       int s_begin = 0, s_end = k_steps, g = 0, cc = 0;
       if (splits > 1) {
         const int ks = w_ % splits;                          // K split of this work item
         s_begin = ks * s_base + (ks < s_rem ? ks : s_rem);
         s_end = s_begin + s_base + (ks < s_rem ? 1 : 0);
-        g = s_begin / cin_chunks;
-        cc = s_begin - g * cin_chunks;
+        if (UNI && uni_chunk_step > 1) {
+          g = 0;
+          cc = s_begin * uni_chunk_step;
+        } else {
+          g = s_begin / cin_chunks;
+          cc = s_begin - g * cin_chunks;
+        }
       }
       const int buf = it & 1;
       const uint32_t d_tmem = tmem_base + buf * BN;
@@ -289,6 +344,43 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       if (!(dbg_flags & 32)) hn_mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);   // the epilogue has drained this buffer
       hn_trace(trace, 1, tri, 4);
       uint32_t accumulate = 0;
+      if constexpr (UNI) {
+        int units = p.grp_units[g];
+        for (int step = s_begin; step < s_end; ++step) {
+          int nu = info & 15;                                  // units of this k-step
+          if (uni_chunk_step > 1 && cin_chunks - cc < nu) nu = cin_chunks - cc;   // ragged last chunk group of a 1x1
+          const bool last = step == s_end - 1;
+          const uint32_t sa = a_desc0 + a_stage * uni_stage_d, sb = sa + uni_a_d;
+          const uint32_t ea = hn_smem_u32(&a_empty[a_stage]), tf = hn_smem_u32(&tmem_full[buf]);
+          hn_mbar_wait(&a_full[a_stage], a_phase);
+          hn_trace(trace, 1, tri, 1);
+          hn_tc_fence_after();
+          if (hn_elect_one()) {
+            if (!(dbg_flags & 4)) {                            // (timing experiment: bit 2 skips the MMAs)
+              hn_umma_bf16_x4(d_tmem, desc_hi | (sa + (units & 3) * uni_plane_d + ((units >> 2) & 15) * ROW_D),
+                              desc_hi | (sb + ((units >> 6) & 3) * B_SLOT_D), idesc, accumulate);
+              if (nu > 1)
+                hn_umma_bf16_x4(d_tmem, desc_hi | (sa + ((units >> 8) & 3) * uni_plane_d + ((units >> 10) & 15) * ROW_D),
+                                desc_hi | (sb + ((units >> 14) & 3) * B_SLOT_D), idesc, 1u);
+              if (nu > 2)
+                hn_umma_bf16_x4(d_tmem, desc_hi | (sa + ((units >> 16) & 3) * uni_plane_d + ((units >> 18) & 15) * ROW_D),
+                                desc_hi | (sb + ((units >> 22) & 3) * B_SLOT_D), idesc, 1u);
+            }
+            hn_umma_commit_addr<1>(ea);                        // stage free once these MMAs have read it
+            if (last) hn_umma_commit_addr<1>(tf);              // accumulator complete -> epilogue
+          }
+          accumulate = 1;
+          hn_trace(trace, 1, tri, 3);
+          if (++a_stage == na) { a_stage = 0; a_phase ^= 1; }
+          cc += uni_chunk_step;
+          if (cc >= cin_chunks) {
+            cc = 0;
+            ++g;
+            if (!last) { info = p.grp_info[g]; units = p.grp_units[g]; }
+          }
+        }
+        continue;
+      }
       for (int step = s_begin; step < s_end; ++step) {
         const int ntaps = info & 15;
         const uint32_t off_step = ((info >> 4) & 15) * ROW_D;
@@ -819,7 +911,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_multi_kernel(const PhaseDesc* __restrict__ phases, const int* __restrict__ group_begin, int num_groups,
-                  unsigned* __restrict__ counter) {
+                  unsigned* __restrict__ counter, long long* __restrict__ group_clock) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ ConvParams sp;
   uint8_t* smem_hdr = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -839,6 +931,7 @@ conv_multi_kernel(const PhaseDesc* __restrict__ phases, const int* __restrict__ 
       tile_off = (tile_off + tiles) % (int)gridDim.x;
     }
     if (g + 1 < num_groups) grid_barrier(counter, (unsigned)(g + 1) * gridDim.x);
+    if (group_clock != nullptr && blockIdx.x == 0 && threadIdx.x == 0) group_clock[g] = clock64();   // bring-up only
   }
   conv_teardown<BN, 1>(tmem_base);
 }
@@ -1004,37 +1097,6 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
   // m + shift of the (phase) matrix; taps of one kernel row whose shifts differ by a few rows share one box.
   HN_REQUIRE(2 * d->dilation <= A_BOX_ROWS_MAX - BLOCK_M, "hn_conv2d_bf16: dilation %d too large for a shared A box",
              d->dilation);
-  int box_rows = BLOCK_M;
-  p.n_groups = 0;
-  auto add_group = [&](int phase, int shift, int ntaps, const int* taps, const int* offs) {
-    const int g = p.n_groups++;
-    const int off_step = ntaps > 1 ? offs[1] - offs[0] : 0, tap_step = ntaps > 1 ? taps[1] - taps[0] : 0;
-    p.grp_shift[g] = shift;
-    p.grp_info[g] = ntaps | (off_step << 4) | (taps[0] << 8) | (tap_step << 16) | (phase << 24);
-    if (off_step > 0) box_rows = A_BOX_ROWS_MAX;
-  };
-  if (d->kh == 1) {
-    const int taps[1] = {0}, offs[1] = {0};
-    add_group(0, 0, 1, taps, offs);
-  } else {
-    for (int r = 0; r < 3; ++r) {
-      const int dr = (r - 1) * d->dilation;
-      if (d->stride == 1) {
-        const int taps[3] = {r * 3, r * 3 + 1, r * 3 + 2};
-        const int offs[3] = {0, d->dilation, 2 * d->dilation};
-        add_group(0, dr * p.wp - d->dilation, 3, taps, offs);
-      } else {
-        // input pixel (2*oh + dr, 2*ow + ds) lives in phase (dr&1, ds&1) at (oh + floor(dr/2), ow + floor(ds/2)):
-        // ds = -1 -> column phase 1 at ow-1, ds = +1 -> column phase 1 at ow (one box), ds = 0 -> column phase 0
-        const int pr = dr & 1, fr = (dr - pr) / 2;
-        const int taps_odd[2] = {r * 3, r * 3 + 2}, offs_odd[2] = {0, 1};
-        add_group(pr * 2 + 1, fr * p.wp - 1, 2, taps_odd, offs_odd);
-        const int taps_even[1] = {r * 3 + 1}, offs_even[1] = {0};
-        add_group(pr * 2, fr * p.wp, 1, taps_even, offs_even);
-      }
-    }
-  }
-  p.a_box_bytes = box_rows * BLOCK_K * 2;
   p.m_tiles = hn_div_up(p.rows, BLOCK_M);
   int bn = force_bn ? force_bn
                     : (d->block_n ? d->block_n
@@ -1045,28 +1107,98 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
   // cluster of 2 with multicast weights when there is at least one pair of M tiles per SM pair
   // measured: pairs with multicast weights gain ~3 % on 256-wide tiles and lose elsewhere -> opt-in only
   int cs = (d->cluster && !force_bn) ? d->cluster : 1;
-  HN_REQUIRE(cs == 1 || (cs == 2 && bn >= 64), "hn_conv2d_bf16: cluster=%d unsupported with block_n=%d", cs, bn);
+  HN_REQUIRE(cs == 1 || (cs == 2 && bn == 256), "hn_conv2d_bf16: cluster=%d unsupported with block_n=%d", cs, bn);
   // resident weights: the layer's whole weight slice stays in shared memory and only A boxes stream, when it is one
   // narrow N tile whose weights fit next to >= 4 A slots and there are enough tiles per CTA to amortise the load
   const int k_blocks_total = p.num_taps * p.cin_chunks;
   const long long b_bytes = (long long)k_blocks_total * bn * BLOCK_K * 2;
   bool rb = !force_bn && cs == 1 && p.n_tiles == 1 && bn <= 64 && b_bytes <= PIPE_BYTES_MAX - 4 * A_SLOT_BYTES &&
             p.m_tiles >= 2 * hn_num_sms() && !(d->debug & 16);
-  if (rb) {
+  const bool uni = bn <= 128 && !rb;      // unified stages (must match the kernel's constexpr UNI)
+
+  // A-box groups.  Pixel (oh*stride + dr, ow*stride + ds) of tap (r, s), dr = (r - kh/2)*dil, ds = (s - kw/2)*dil, is row
+  // m + shift of the (phase) matrix; taps of one kernel row whose shifts differ by a few rows share one box.
+  int box_rows = BLOCK_M, a_planes = 1, b_tiles = 1;
+  p.n_groups = 0;
+  p.uni_chunk_step = 1;
+  auto add_group = [&](int phase, int shift, int ntaps, const int* taps, const int* offs) {
+    const int g = p.n_groups++;
+    const int off_step = ntaps > 1 ? offs[1] - offs[0] : 0, tap_step = ntaps > 1 ? taps[1] - taps[0] : 0;
+    p.grp_shift[g] = shift;
+    p.grp_info[g] = ntaps | (off_step << 4) | (taps[0] << 8) | (tap_step << 16) | (phase << 24);
+    if (off_step > 0) box_rows = A_BOX_ROWS_MAX;
+  };
+  auto unit = [](int plane, int rowoff, int tile) { return plane | (rowoff << 2) | (tile << 6); };
+  if (d->kh == 1) {
+    const int taps[1] = {0}, offs[1] = {0};
+    add_group(0, 0, 1, taps, offs);
+    if (uni && p.cin_chunks >= 2) {
+      // 1x1: a k-step covers two 64-channel chunks (two A planes, two weight tiles): four MMAs per TMA operation
+      p.uni_chunk_step = 2;
+      a_planes = b_tiles = 2;
+      p.grp_info[0] = 2;
+      p.grp_units[0] = unit(0, 0, 0) | (unit(1, 0, 1) << 8);
+    } else {
+      p.grp_units[0] = unit(0, 0, 0);
+    }
+  } else {
+    for (int r = 0; r < 3; ++r) {
+      const int dr = (r - 1) * d->dilation;
+      if (d->stride == 1) {
+        const int taps[3] = {r * 3, r * 3 + 1, r * 3 + 2};
+        const int offs[3] = {0, d->dilation, 2 * d->dilation};
+        add_group(0, dr * p.wp - d->dilation, 3, taps, offs);
+        p.grp_units[p.n_groups - 1] = unit(0, 0, 0) | (unit(0, d->dilation, 1) << 8) | (unit(0, 2 * d->dilation, 2) << 16);
+        b_tiles = 3;
+      } else if (uni) {
+        // input pixel (2*oh + dr, 2*ow + ds) lives in phase (dr&1, ds&1) at (oh + floor(dr/2), ow + floor(ds/2)).  One
+        // box over both column phases of row phase pr, starting one row early: ds = -1 -> plane 1 row 0, ds = 0 ->
+        // plane 0 row 1, ds = +1 -> plane 1 row 1
+        const int pr = dr & 1, fr = (dr - pr) / 2;
+        const int taps[3] = {r * 3, r * 3 + 1, r * 3 + 2};
+        const int offs[3] = {0, 1, 1};
+        add_group(pr * 2, fr * p.wp - 1, 3, taps, offs);
+        box_rows = A_BOX_ROWS_MAX;
+        p.grp_units[p.n_groups - 1] = unit(1, 0, 0) | (unit(0, 1, 1) << 8) | (unit(1, 1, 2) << 16);
+        a_planes = 2;
+        b_tiles = 3;
+      } else {
+        // ds = -1 -> column phase 1 at ow-1, ds = +1 -> column phase 1 at ow (one box), ds = 0 -> column phase 0
+        const int pr = dr & 1, fr = (dr - pr) / 2;
+        const int taps_odd[2] = {r * 3, r * 3 + 2}, offs_odd[2] = {0, 1};
+        add_group(pr * 2 + 1, fr * p.wp - 1, 2, taps_odd, offs_odd);
+        const int taps_even[1] = {r * 3 + 1}, offs_even[1] = {0};
+        add_group(pr * 2, fr * p.wp, 1, taps_even, offs_even);
+      }
+    }
+  }
+  p.a_box_bytes = box_rows * BLOCK_K * 2;
+  p.k_steps = (uni && p.uni_chunk_step > 1) ? hn_div_up(p.cin_chunks, p.uni_chunk_step) : p.n_groups * p.cin_chunks;
+  if (uni) {
+    p.uni_plane_bytes = box_rows * BLOCK_K * 2;
+    p.uni_a_bytes = a_planes * p.uni_plane_bytes;
+    p.uni_b_bytes = b_tiles * bn * BLOCK_K * 2;
+    // convolutions chained in one multi-convolution launch share the ring: same stage stride and depth for all of
+    // them (the largest stage: two 136-row planes + three weight tiles)
+    p.uni_stride = force_bn ? 2 * A_SLOT_BYTES + 3 * bn * BLOCK_K * 2 : p.uni_a_bytes + p.uni_b_bytes;
+    int stages = PIPE_BYTES_MAX / p.uni_stride;
+    p.uni_stages = stages > MAX_STAGES ? MAX_STAGES : stages;
+    HN_REQUIRE(p.uni_stages >= 2 && p.uni_a_bytes + p.uni_b_bytes <= p.uni_stride,
+               "hn_conv2d_bf16: internal: unified stage too large");
+    p.na_stages = p.uni_stages;
+    p.nb_stages = 1;
+    p.uni_a_rank4 = p.uni_chunk_step > 1 ? 1 : 0;
+  } else if (rb) {
     p.rb_b_bytes = (int)b_bytes;
     const int slots = (PIPE_BYTES_MAX - p.rb_b_bytes) / A_SLOT_BYTES;
     p.na_stages = slots > MAX_STAGES ? MAX_STAGES : slots;
     p.nb_stages = 1;
   } else {
-    switch (bn) {
-      case 256: p.na_stages = Cfg<256>::NA; p.nb_stages = Cfg<256>::NB; break;
-      case 128: p.na_stages = Cfg<128>::NA; p.nb_stages = Cfg<128>::NB; break;
-      case 64: p.na_stages = Cfg<64>::NA; p.nb_stages = Cfg<64>::NB; break;
-      case 32: p.na_stages = Cfg<32>::NA; p.nb_stages = Cfg<32>::NB; break;
-      default: p.na_stages = Cfg<16>::NA; p.nb_stages = Cfg<16>::NB; break;
-    }
+    p.na_stages = Cfg<256>::NA;
+    p.nb_stages = Cfg<256>::NB;
   }
   p.cout = d->cout;
+  p.cout_pad = d->cout_pad;
   p.scale = d->scale;
   p.shift = d->shift;
   p.relu_lo = d->relu_lo;
@@ -1116,7 +1248,7 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
   // split-K (needs caller-provided scratch): short, deep layers whose tiles cannot fill the GPU
   p.splits = 1;
   if (d->splitk_ws && d->splitk_counters && cs == 1 && bn >= 32) {
-    const int k_steps = p.n_groups * p.cin_chunks;
+    const int k_steps = p.k_steps;
     const int tiles = p.m_tiles * p.n_tiles;
     int sp = d->splits;
     if (sp <= 0) {
@@ -1144,17 +1276,52 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
   }
   CUtensorMap& ta = out->ta;
   CUtensorMap& tb = out->tb;
-  {
+  if (uni && p.uni_a_rank4) {
+    // 1x1 with two chunks per k-step: dims (64 channels, rows, chunks, phases); the box puts the two chunk planes one
+    // after the other in shared memory.  (The chunk stride is smaller than the row stride; if a driver refuses that,
+    // fall back to one chunk per k-step.)
+    const cuuint64_t dims[4] = {(cuuint64_t)BLOCK_K, (cuuint64_t)p.rows, (cuuint64_t)p.cin_chunks, (cuuint64_t)d->in_phases};
+    const cuuint64_t strides[3] = {(cuuint64_t)d->cin * 2, (cuuint64_t)BLOCK_K * 2, (cuuint64_t)p.rows * d->cin * 2};
+    const cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)box_rows, (cuuint32_t)a_planes, 1};
+    if (make_map(&ta, d->in, 4, dims, strides, box) != HN_OK) {
+      p.uni_chunk_step = 1;
+      p.uni_a_rank4 = 0;
+      a_planes = b_tiles = 1;
+      p.grp_info[0] = 1;
+      p.grp_units[0] = 0;
+      p.k_steps = p.cin_chunks;
+      p.uni_a_bytes = p.uni_plane_bytes;
+      p.uni_b_bytes = bn * BLOCK_K * 2;
+      if (!force_bn) {
+        p.uni_stride = p.uni_a_bytes + p.uni_b_bytes;
+        const int stages = PIPE_BYTES_MAX / p.uni_stride;
+        p.uni_stages = p.na_stages = stages > MAX_STAGES ? MAX_STAGES : stages;
+      }
+      if (p.splits > p.k_steps) p.splits = p.k_steps;
+    }
+  }
+  if (!(uni && p.uni_a_rank4)) {
+    // dims (channels, rows, phases); unified stride-2 3x3: the box spans both column phases of a row phase
     const cuuint64_t dims[3] = {(cuuint64_t)d->cin, (cuuint64_t)p.rows, (cuuint64_t)d->in_phases};
     const cuuint64_t strides[2] = {(cuuint64_t)d->cin * 2, (cuuint64_t)p.rows * d->cin * 2};
-    const cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)box_rows, 1};
+    const cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)box_rows, (cuuint32_t)(uni ? a_planes : 1)};
     int rc = make_map(&ta, d->in, 3, dims, strides, box);
     if (rc) return rc;
   }
-  {
-    const cuuint64_t k_total = (cuuint64_t)p.num_taps * d->cin;
-    const cuuint64_t dims[2] = {k_total, (cuuint64_t)d->cout_pad};
-    const cuuint64_t strides[1] = {k_total * 2};
+  if (uni) {
+    // [tap][chunk][cout_pad][64]: the box brings the weight tiles of one k-step (three taps of a chunk, or two chunks
+    // of a 1x1) as consecutive BN x 128-byte tiles
+    const cuuint64_t dims[4] = {(cuuint64_t)BLOCK_K, (cuuint64_t)d->cout_pad, (cuuint64_t)p.cin_chunks, (cuuint64_t)p.num_taps};
+    const cuuint64_t strides[3] = {(cuuint64_t)BLOCK_K * 2, (cuuint64_t)d->cout_pad * BLOCK_K * 2,
+                                   (cuuint64_t)p.cin_chunks * d->cout_pad * BLOCK_K * 2};
+    const cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)bn, (cuuint32_t)(p.uni_chunk_step > 1 ? b_tiles : 1),
+                               (cuuint32_t)(p.uni_chunk_step > 1 ? 1 : b_tiles)};
+    int rc = make_map(&tb, d->weight, 4, dims, strides, box);
+    if (rc) return rc;
+  } else {
+    // [k_block][cout_pad][64] bf16: a 2-D matrix of 128-byte rows, row = k_block * cout_pad + n
+    const cuuint64_t dims[2] = {(cuuint64_t)BLOCK_K, (cuuint64_t)k_blocks_total * d->cout_pad};
+    const cuuint64_t strides[1] = {(cuuint64_t)BLOCK_K * 2};
     const cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)(bn / cs)};
     int rc = make_map(&tb, d->weight, 2, dims, strides, box);
     if (rc) return rc;
@@ -1208,6 +1375,13 @@ extern "C" int hn_conv2d_bf16(const hn_conv_desc* d, void* stream) {
     case 32: return launch<32, 1, false>(ta, tb, p, st);
     default: return launch<16, 1, false>(ta, tb, p, st);
   }
+}
+
+static long long* g_multi_trace = nullptr;
+// Bring-up only: when set, CTA 0 of every following hn_conv_multi_run writes clock64() after each group into buf[g].
+extern "C" int hn_conv_multi_set_trace(void* buf) {
+  g_multi_trace = reinterpret_cast<long long*>(buf);
+  return HN_OK;
 }
 
 extern "C" int64_t hn_conv_multi_plan_bytes(int n_convs, int n_groups) {
@@ -1276,7 +1450,7 @@ extern "C" int hn_conv_multi_run(void* plan_dev, int n_convs, int n_groups, int 
   const PhaseDesc* phases = reinterpret_cast<const PhaseDesc*>(base + multi_phases_off(n_groups));
   const int* groups = reinterpret_cast<const int*>(base + multi_groups_off());
   unsigned* counter = reinterpret_cast<unsigned*>(base);
-  HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_multi_kernel<MULTI_BN>, phases, groups, n_groups, counter));
+  HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_multi_kernel<MULTI_BN>, phases, groups, n_groups, counter, g_multi_trace));
   hn_count_launch();
   return HN_OK;
 }

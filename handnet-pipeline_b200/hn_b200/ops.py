@@ -14,6 +14,7 @@ from . import _lib
 from ._lib import ConvDesc, check, ptr, stream_ptr
 
 BF16 = torch.bfloat16
+_ENV_DEBUG = int(__import__('os').environ.get('HN_CONV_DEBUG', '0'))   # bring-up experiments only
 PROFILE = None      # set to a list by runtime.conv_profile: (start event, end event, algorithmic FLOPs) per conv launch
 RECORD = None       # set to a list to RECORD conv2d calls (descriptor + keep-alive refs) instead of launching them;
                     # None entries are group boundaries (see MultiConv)
@@ -90,13 +91,30 @@ def pad_cout(cout: int) -> int:
     return (cout + 63) // 64 * 64
 
 
+def tile_k(m: torch.Tensor) -> torch.Tensor:
+    """[cout_pad][K] -> the kernel's weight layout [K/64][cout_pad][64] (k-block major), returned with the logical
+    shape [cout_pad, K]: the tile of one k-block and BN output channels is then ONE contiguous run of BN*128 bytes,
+    which is what the TMA box of hn_conv2d_bf16 fetches (DRAM- and L2-friendly; a row-major [cout][K] matrix would
+    scatter the box over BN rows K*2 bytes apart)."""
+    cp, k = m.shape
+    assert k % 64 == 0
+    return m.view(cp, k // 64, 64).permute(1, 0, 2).contiguous().view(cp, k)
+
+
+def untile_k(m: torch.Tensor) -> torch.Tensor:
+    """Inverse of tile_k (tests, debugging)."""
+    cp, k = m.shape
+    return m.view(k // 64, cp, 64).permute(1, 0, 2).contiguous().view(cp, k)
+
+
 def pack_conv_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """OIHW fp32 -> bf16 [cout_pad][kh*kw*cin] (tap-major K, channels fastest), zero rows beyond cout."""
+    """OIHW fp32 -> bf16 weights for hn_conv2d_bf16: K = kh*kw*cin in tap-major order (channels fastest), output
+    channels padded with zero rows to cout_pad, stored k-block major (tile_k).  Logical shape [cout_pad, K]."""
     cout, cin, kh, kw = w.shape
     m = w.detach().float().permute(0, 2, 3, 1).reshape(cout, kh * kw * cin)
     out = torch.zeros((pad_cout(cout), m.shape[1]), dtype=BF16, device=w.device)
     out[:cout] = m.to(BF16)
-    return out.contiguous()
+    return tile_k(out)
 
 
 def pack_stem_weight(w: torch.Tensor, k_pad: int) -> torch.Tensor:
@@ -109,7 +127,7 @@ def pack_stem_weight(w: torch.Tensor, k_pad: int) -> torch.Tensor:
     m[:, :7, 1:, :cin] = w.detach().float().permute(0, 2, 3, 1)
     out = torch.zeros((pad_cout(cout), k_pad), dtype=BF16, device=w.device)
     out[:cout] = m.reshape(cout, -1).to(BF16)
-    return out.contiguous()
+    return tile_k(out)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -213,7 +231,7 @@ def conv2d(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 1, d
         d.gn_stats, d.gn_groups = gn_stats.data_ptr(), gn_groups
     d.block_n = block_n
     d.cluster = cluster
-    d.debug = debug
+    d.debug = debug or _ENV_DEBUG
     if trace is not None:
         assert trace.dtype == torch.int64 and trace.numel() >= 3 * 2048 * 2
         d.trace = trace.data_ptr()

@@ -67,7 +67,9 @@ typedef struct hn_conv_desc {
    * (= output) sizes.  For the stem GEMM use kh = kw = 1, halo_in = 0, cin = k_pad. */
   const void* in;
   int n, h, w, cin, halo_in, in_phases; /* in_phases: 1, or 4 for a phase-split input */
-  /* weights: bf16 [cout_pad][kh*kw][cin] (tap-major K), cout_pad a multiple of block_n */
+  /* weights: bf16, K = kh*kw*cin in tap-major order (k = (r*kw + s)*cin + c), stored k-block major:
+   * [K/64][cout_pad][64], so that the tile (64 k, block_n output channels) the kernel streams is one contiguous
+   * run of block_n*128 bytes.  cout_pad a multiple of block_n (rows >= cout are zero). */
   const void* weight;
   int cout, cout_pad, kh, kw, stride, dilation;
   /* epilogue: y = acc * scale[c] + shift[c] (+ residual) ; relu on channels [relu_lo, relu_hi) ; store */
@@ -117,6 +119,9 @@ int64_t hn_conv_multi_plan_bytes(int n_convs, int n_groups);
 int hn_conv_multi_build(const hn_conv_desc* descs, int n_convs, const int* group_begin_host, int n_groups,
                         void* plan_dev, int64_t plan_bytes);
 int hn_conv_multi_run(void* plan_dev, int n_convs, int n_groups, int grid, void* stream);
+/* bring-up only: CTA 0 of every following hn_conv_multi_run writes clock64() after each group into buf[g] (int64);
+ * NULL switches it off. */
+int hn_conv_multi_set_trace(void* buf);
 
 /* ---- 3x3 stride-2 pad-1 max pool (torchvision resnet maxpool; a2j/resnet.py:108) ----------------------------
  * in: bf16 [n][h][w][c] (no halo) -> out: bf16 haloed NHWC [n][oh+2*halo][ow+2*halo][c], oh = (h+1)/2. */

@@ -57,10 +57,8 @@ CASES = [
     ("3x3_halo2_in_halo1_conv", 2, 11, 11, 64, 64, 3, 1, 1, 2, 64),
     # CTA pairs with multicast weights (cluster = 2); odd tile counts leave a dummy CTA in the last cluster
     ("cs2_3x3_256_256_bn256_odd", 3, 25, 34, 256, 256, 3, 1, 1, 1, 256, 2),
-    ("cs2_3x3_64_64_bn64", 3, 20, 28, 64, 64, 3, 1, 1, 1, 64, 2),
-    ("cs2_3x3_128_128_bn128", 2, 20, 28, 128, 128, 3, 1, 1, 1, 128, 2),
     ("cs2_1x1_512_2048_bn256", 3, 11, 11, 512, 2048, 1, 1, 1, 1, 256, 2),
-    ("cs2_3x3_s2_128_256", 2, 25, 33, 128, 256, 3, 2, 1, 1, 128, 2),
+    ("cs2_3x3_s2_128_256", 2, 25, 33, 128, 256, 3, 2, 1, 1, 256, 2),
     ("cs2_3x3_256_256_auto_big", 4, 100, 136, 256, 256, 3, 1, 1, 1, 0, 0),
     # resident weights (one narrow N tile, >= 2 tiles per SM): layer1-like 3x3 and stem-like 1x1 GEMM
     ("rb_3x3_64_64_layer1", 2, 200, 272, 64, 64, 3, 1, 1, 1, 0, 0),
