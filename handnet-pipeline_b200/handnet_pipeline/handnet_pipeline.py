@@ -77,6 +77,7 @@ class HandNet(nn.Module):
         depth = depth_images.float().contiguous()
         crops, has_hand, depth_batch = ops.select_crop_resize(det["boxes"], det["labels"], det["keep_count"],
                                                               self.num_classes - 1, depth, CROP_SIZE)
+        runtime.mark("crop")
         if self.RGBD:
             depth_batch = depth_batch[:, [2, 1, 0, 3]].contiguous()        # handnet_pipeline.py:102
         joints = self._pose_net().forward_device(depth_batch)

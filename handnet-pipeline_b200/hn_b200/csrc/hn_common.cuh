@@ -54,6 +54,18 @@ __device__ __forceinline__ float hn_bf16_lo(uint32_t v) { return __uint_as_float
 __device__ __forceinline__ float hn_bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 __device__ __forceinline__ float hn_round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// 32-byte global accesses (sm_100: LDG/STG.256): one full sector per lane and instruction.  p must be 32-byte aligned.
+__device__ __forceinline__ void hn_ldg256(const void* p, uint32_t* r) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void hn_stg256(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
 // ---- mbarrier ------------------------------------------------------------------------------
 __device__ __forceinline__ void hn_mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(hn_smem_u32(bar)), "r"(count) : "memory");

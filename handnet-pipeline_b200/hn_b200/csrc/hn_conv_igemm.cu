@@ -89,6 +89,7 @@ struct ConvParams {
   int div_img_sh, div_wp_sh;
   int na_stages, nb_stages;         // ring depths
   int rb_b_bytes;                   // resident-weights mode: bytes of the weight slice
+  int vec32;                        // epilogue may use 32-byte global accesses (cout % 16 == 0, 32-byte aligned bases)
   int dbg_flags;                    // bring-up / timing experiments (bit0 no stores, bit1 no epilogue, bit2 no MMA, bit3 no TMA)
   long long* trace;                 // bring-up: CTA 0 logs (clock64, tag) pairs per role, TRACE_EVENTS each
 };
@@ -550,15 +551,15 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       }
       // residual rows are fetched one chunk ahead (the first one before the accumulator wait) so that their
       // global-load latency hides behind the wait / the previous chunk's work
-      const bool res_vec = p.res_mode != 0 && interior && (p.cout & 7) == 0;
-      uint4 res_next[CHUNK / 8];
+      const bool vec32 = p.vec32 != 0;          // 32-byte (full-sector) global accesses: cout % 16 == 0, aligned bases
+      const bool res_vec = p.res_mode != 0 && interior && vec32;
+      uint32_t res_next[CHUNK / 2];
       constexpr int STEP = (BN / CHUNK >= 2) ? 2 * CHUNK : CHUNK;   // two warps interleave chunks when there are >= 2
       const int c_first = (BN / CHUNK >= 2) ? half * CHUNK : 0;
       const bool idle_half = (BN / CHUNK < 2) && half == 1;         // a single chunk: the second warp only arrives
       if (res_vec && !idle_half && n0 + c_first + CHUNK <= p.cout) {
 #pragma unroll
-        for (int j = 0; j < CHUNK / 8; ++j)
-          res_next[j] = __ldg(reinterpret_cast<const uint4*>(p.res + res_off + n0 + c_first) + j);
+        for (int j = 0; j < CHUNK / 16; ++j) hn_ldg256(p.res + res_off + n0 + c_first + 16 * j, &res_next[8 * j]);
       }
 
       if (dbg_flags & 16) {                      // experiment: one polling lane per warp
@@ -612,13 +613,12 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
 
 #pragma unroll 1
       for (int c0 = c_first; c0 < ((idle_half || (p.dbg_flags & 2) || !finalize) ? 0 : BN); c0 += STEP) {
-        uint4 res_cur[CHUNK / 8];
+        uint32_t res_cur[CHUNK / 2];
 #pragma unroll
-        for (int j = 0; j < CHUNK / 8; ++j) res_cur[j] = res_next[j];
+        for (int j = 0; j < CHUNK / 2; ++j) res_cur[j] = res_next[j];
         if (res_vec && c0 + STEP < BN && n0 + c0 + STEP + CHUNK <= p.cout) {
 #pragma unroll
-          for (int j = 0; j < CHUNK / 8; ++j)
-            res_next[j] = __ldg(reinterpret_cast<const uint4*>(p.res + res_off + n0 + c0 + STEP) + j);
+          for (int j = 0; j < CHUNK / 16; ++j) hn_ldg256(p.res + res_off + n0 + c0 + STEP + 16 * j, &res_next[8 * j]);
         }
         uint32_t acc[CHUNK];
         const int cbase = n0 + c0;
@@ -657,14 +657,11 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
         }
         if (p.res_mode != 0 && interior) {
           const __nv_bfloat16* rp = p.res + res_off + cbase;
-          if (cbase + CHUNK <= p.cout && (p.cout & 7) == 0) {
+          if (cbase + CHUNK <= p.cout && vec32) {
 #pragma unroll
-            for (int j = 0; j < CHUNK; j += 8) {
-              const uint4 r = res_cur[j / 8];
-              v[j + 0] += hn_bf16_lo(r.x); v[j + 1] += hn_bf16_hi(r.x);
-              v[j + 2] += hn_bf16_lo(r.y); v[j + 3] += hn_bf16_hi(r.y);
-              v[j + 4] += hn_bf16_lo(r.z); v[j + 5] += hn_bf16_hi(r.z);
-              v[j + 6] += hn_bf16_lo(r.w); v[j + 7] += hn_bf16_hi(r.w);
+            for (int j = 0; j < CHUNK; j += 2) {
+              v[j] += hn_bf16_lo(res_cur[j / 2]);
+              v[j + 1] += hn_bf16_hi(res_cur[j / 2]);
             }
           } else {
 #pragma unroll
@@ -697,15 +694,15 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
         for (int j = 0; j < CHUNK; j += 2) packed[j / 2] = hn_pack_bf16(v[j], v[j + 1]);
         if (interior && !(p.dbg_flags & 1)) {
           __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + cbase;
-          if (cbase + CHUNK <= p.cout && (p.cout & 7) == 0) {
+          if (cbase + CHUNK <= p.cout && vec32) {
+            // 32 bytes per lane and instruction: every store fills whole 32-byte sectors (16-byte stores at a 2*cout
+            // byte lane stride left every sector half written and doubled the L2 requests)
 #pragma unroll
-            for (int j = 0; j < CHUNK / 2; j += 4)
-              *reinterpret_cast<uint4*>(op + 2 * j) = make_uint4(packed[j], packed[j + 1], packed[j + 2], packed[j + 3]);
+            for (int j = 0; j < CHUNK / 2; j += 8) hn_stg256(op + 2 * j, &packed[j]);
             if (p.out_phase) {
               __nv_bfloat16* pp = p.out_phase + ph_off + cbase;
 #pragma unroll
-              for (int j = 0; j < CHUNK / 2; j += 4)
-                *reinterpret_cast<uint4*>(pp + 2 * j) = make_uint4(packed[j], packed[j + 1], packed[j + 2], packed[j + 3]);
+              for (int j = 0; j < CHUNK / 2; j += 8) hn_stg256(pp + 2 * j, &packed[j]);
             }
           } else {
 #pragma unroll
@@ -1233,6 +1230,8 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
     p.ph_wp = (d->w + 1) / 2 + 2 * d->out_phase_halo;
     p.ph_stride = (long long)d->n * p.ph_hp * p.ph_wp * d->cout;
   }
+  p.vec32 = (d->cout % 16 == 0) && (reinterpret_cast<uintptr_t>(d->out) % 32 == 0) &&
+            (reinterpret_cast<uintptr_t>(d->res) % 32 == 0) && (reinterpret_cast<uintptr_t>(d->out_phase) % 32 == 0);
   p.trace = reinterpret_cast<long long*>(d->trace);
   p.dbg_flags = (d->debug >> 6) & 255;     // bit0: no epilogue stores, bit1: no epilogue work at all (timing experiments)
   p.gn_stats = d->gn_stats;

@@ -55,6 +55,17 @@ def bn_affine(weight, bias, mean, var, eps=BN_EPS, conv_bias=None):
     return scale.contiguous(), shift.contiguous()
 
 
+PHASES = None               # set to a list to collect (name, CUDA event) marks of a step (tools/phase_timing.py)
+
+
+def mark(name: str):
+    """Record a timing event on the current stream (only while PHASES is a list)."""
+    if PHASES is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        PHASES.append((name, ev))
+
+
 _side_streams: Dict[str, List["torch.cuda.Stream"]] = {}
 SPLIT_K = True              # split-K (fp32 scratch + last-arriver epilogue) for the short, deep A2J layers
 A2J_MULTI = True            # run the A2J convolutions as one cooperative multi-convolution launch
@@ -236,12 +247,14 @@ class FCOSExecutor:
         B = pl.batch
         hc, wc = pl.canvas_hw
         h1, w1 = hc // 2, wc // 2
+        mark("preprocess")
         ops.im2col_7x7s2(pl.canvas, STEM_K_RGB, out=pl.stem_a)
         a = Act(B, h1, w1, STEM_K_RGB, 0, pl.canvas.device, t=pl.stem_a.view(B, h1, w1, STEM_K_RGB))
         ops.conv2d(a, w.stem_w, cout=64, ksize=1, scale=w.stem_scale, shift=w.stem_shift, relu=True, out=pl.stem,
                    algo_k=147)
         x = ops.maxpool3x3s2(pl.stem.t, pl.stage[0][0])
         feats = []
+        mark("stem+maxpool")
         for li in range(4):
             bufs = pl.stage[li]
             blocks = w.blocks[li]
@@ -261,6 +274,7 @@ class FCOSExecutor:
                                          out_phase=pl.phase[li] if (last and li < 3) else None)
             if li >= 1:
                 feats.append(x)
+            mark(f"layer{li + 1}")
         # FPN top-down (torchvision/ops/feature_pyramid_network.py:172-204)
         for i in (2, 1, 0):
             if i == 2:
@@ -268,6 +282,7 @@ class FCOSExecutor:
             else:
                 w.inner[i].run(feats[i], res=pl.inner[i + 1], res_mode=2, out=pl.inner[i])
         run_chains([(lambda i=i: w.outer[i].run(pl.inner[i], out=pl.p[i])) for i in range(3)], pl.canvas.device)
+        mark("fpn")
         # heads (fcos_utils/fcos.py:267-329, 373-395)
         pl.gn_stats.zero_()
 
@@ -291,6 +306,7 @@ class FCOSExecutor:
         # six independent chains: (cls, reg) x (P3, P4, P5); the big P3 chains first
         run_chains([tower_chain(ti, t, lvl) for lvl in range(3) for ti, t in enumerate(("cls", "reg"))],
                    pl.canvas.device)
+        mark("towers")
         return pl.cls_buf, pl.reg_buf
 
     def head_views(self, pl: FCOSPlan):
@@ -335,6 +351,7 @@ class FCOSExecutor:
         rh = [float(torch.tensor(o[0], dtype=f32) / torch.tensor(s[0], dtype=f32)) for o, s in zip(orig, sizes)]
         rw = [float(torch.tensor(o[1], dtype=f32) / torch.tensor(s[1], dtype=f32)) for o, s in zip(orig, sizes)]
         out = self.postprocess(pl, rh, rw)
+        mark("postprocess")
         out["plan"] = pl
         return out
 
@@ -557,7 +574,10 @@ class A2JExecutor:
 
     def forward_device(self, x: torch.Tensor) -> torch.Tensor:
         cls, reg, dep, pl = self.heads_device(x)
-        return ops.a2j_aggregate(cls, reg, dep, self.wts.anchors, ws=pl.agg_ws)
+        mark("a2j convs")
+        out = ops.a2j_aggregate(cls, reg, dep, self.wts.anchors, ws=pl.agg_ws)
+        mark("a2j aggregate")
+        return out
 
 
 # =================================================================================================

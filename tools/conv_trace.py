@@ -7,7 +7,8 @@ import torch
 from hn_b200 import ops
 
 SHAPES = {"layer1": (8, 200, 272, 64, 64, 3), "layer2": (8, 100, 136, 128, 128, 3), "P3": (8, 100, 136, 256, 256, 3),
-          "layer3": (8, 50, 68, 256, 256, 3)}
+          "layer3": (8, 50, 68, 256, 256, 3), "a2j3x3": (8, 11, 11, 256, 256, 3), "a2j1x1": (8, 11, 11, 1024, 256, 1),
+          "a2j1x1b": (8, 11, 11, 256, 1024, 1)}
 name = sys.argv[1] if len(sys.argv) > 1 else "layer1"
 debug = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 n, h, w, cin, cout, k = SHAPES[name]
@@ -18,7 +19,8 @@ out = ops.Act(n, h, w, cout, 1, "cuda")
 sc = torch.ones(cout, device="cuda"); sh = torch.zeros(cout, device="cuda")
 trace = torch.zeros(3 * 2048 * 2, dtype=torch.int64, device="cuda")
 for i in range(3):
-    ops.conv2d(x, wt, cout=cout, ksize=k, scale=sc, shift=sh, relu=True, out=out, debug=debug, trace=trace if i == 2 else None)
+    ops.conv2d(x, wt, cout=cout, ksize=k, scale=sc, shift=sh, relu=True, out=out, debug=debug, trace=trace if i == 2 else None,
+               block_n=int(os.environ.get("BN", "0")))
 torch.cuda.synchronize()
 tr = trace.cpu().view(3, 2048, 2)
 t0 = min(int(tr[r, 0, 0]) for r in range(3) if tr[r, 0, 0] > 0)

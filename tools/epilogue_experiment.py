@@ -33,13 +33,13 @@ for name, shp in shapes:
     if only and not any(o in name for o in only):
         continue
     flops = 2.0 * shp[0] * shp[1] * shp[2] * shp[3] * shp[4] * shp[5] ** 2
-    for dbg, what in ((0, "full"), (NOEPI, "no epilogue"), (NOEPI | NOMMA, "no epilogue, no MMA"), (NOEPI | NOTMA, "no epilogue, no TMA"),
+    for dbg, what in ((0, "full"), (64, "no stores"), (NOEPI, "no epilogue"), (NOEPI | NOMMA, "no epilogue, no MMA"), (NOEPI | NOTMA, "no epilogue, no TMA"),
                       (NOEPI | NOMMA | NOTMA, "barriers only"), (NORB, "full, streamed weights"), (-1, "full, cluster 2"),
                       (2048 | NOEPI | NOMMA | NOTMA, "barriers only, no epi warps"), (2048 | NOEPI | NOTMA, "MMA only, no epi warps"),
                       (2048 | NOEPI, "MMA+TMA, no epi warps"), (1024, "full, 1-lane epi polling")):
         if dbg == NORB and shp[4] > 64:
             continue
-        if dbg == -1 and shp[4] < 128:
+        if dbg == -1 and shp[4] < 256:
             continue
         us = time_conv(*shp, debug=max(dbg, 0), cluster=2 if dbg == -1 else 0)
         print(f"{name:32s} {what:26s} {us:8.1f} us  {flops / us / 1e6:7.0f} TF/s", flush=True)
