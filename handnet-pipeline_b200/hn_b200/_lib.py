@@ -34,7 +34,7 @@ class ConvDesc(C.Structure):
         ("gn_stats", _c_p), ("gn_groups", _i),
         ("block_n", _i), ("cluster", _i), ("debug", _i),
         ("splitk_ws", _c_p), ("splitk_ws_bytes", _i64), ("splitk_counters", _c_p), ("splitk_counters_len", _i), ("splits", _i),
-        ("trace", _c_p),
+        ("trace", _c_p), ("stem_pitch_h", _i), ("stem_pitch_w", _i),
     ]
 
 
@@ -46,6 +46,8 @@ SIGNATURES = {
     "hn_device_info": (_i, [_ip, _ip, _ip]),
     "hn_launch_count": (_i64, []),
     "hn_preprocess_resize_pad": (_i, [C.POINTER(_c_p), _ip, _ip, _ip, _ip, _i, _fp, _fp, _c_p, _i, _i, _c_p]),
+    "hn_preprocess_resize_pad_framed": (_i, [C.POINTER(_c_p), _ip, _ip, _ip, _ip, _i, _fp, _fp, _c_p, _i, _i, _i, _i, _i, _i,
+                                             _c_p]),
     "hn_im2col_7x7s2": (_i, [_c_p, _i, _i, _i, _i, _i, _c_p, _i, _c_p]),
     "hn_conv2d_bf16": (_i, [C.POINTER(ConvDesc), _c_p]),
     "hn_conv_multi_plan_bytes": (_i64, [_i, _i]),

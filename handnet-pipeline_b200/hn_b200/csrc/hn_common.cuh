@@ -145,6 +145,15 @@ __device__ __forceinline__ void hn_tma_load_4d(void* dst, const CUtensorMap* m, 
       : "memory");
 }
 
+__device__ __forceinline__ void hn_tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                               int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(hn_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(hn_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3), "r"(c4)
+      : "memory");
+}
+
 __device__ __forceinline__ void hn_tma_load_2d_mcast(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
                                                      uint16_t cta_mask) {
   // the box lands at the same CTA-relative smem offset in every CTA of cta_mask and signals the mbarrier at the

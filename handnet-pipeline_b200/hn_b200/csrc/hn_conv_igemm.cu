@@ -64,6 +64,9 @@ struct ConvParams {
   int uni_stages, uni_chunk_step;           // ring depth; 64-channel chunks per k-step (1x1 convolutions: up to 2)
   int uni_stride;                           // bytes between stages (>= uni_a_bytes + uni_b_bytes)
   int uni_a_rank4;                          // the A tensor map is 4-D (channels, rows, chunks, phases)
+  // direct 7x7/2 stem: an M tile is 128 consecutive output columns of one output row; the A tensor map is the 5-D
+  // overlapping-stride patch view of the canvas (build_conv)
+  int stem_tpr, stem_h;                     // tiles per output row (0 = ordinary convolution), output rows per image
   int m_tiles, n_tiles;
   int cout, cout_pad;
   const float* scale;
@@ -228,6 +231,13 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       const int n0 = nt * BN;
       int info = p.grp_info[g], shift = p.grp_shift[g];
       if constexpr (UNI) {
+        int st_n = 0, st_oy = 0, st_ox = 0;                  // stem: image, output row, first output column of the tile
+        if (p.stem_tpr > 0) {
+          const int row = mt / p.stem_tpr;
+          st_ox = (mt - row * p.stem_tpr) * BLOCK_M;
+          st_n = row / p.stem_h;
+          st_oy = row - st_n * p.stem_h;
+        }
         for (int step = s_begin; step < s_end; ++step) {
           hn_mbar_wait(&a_empty[a_stage], a_phase ^ 1);
           hn_trace(trace, 0, tri, 1);
@@ -237,7 +247,8 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
             } else {
               uint8_t* sa = a_ring + a_stage * uni_stride;
               hn_mbar_expect_tx(&a_full[a_stage], (uint32_t)uni_stage_bytes);
-              if (p.uni_a_rank4) hn_tma_load_4d(sa, &tm_a, &a_full[a_stage], 0, m0 + shift, cc, info >> 24);
+              if (p.stem_tpr > 0) hn_tma_load_4d(sa, &tm_a, &a_full[a_stage], 0, st_ox, 2 * (st_oy + cc), st_n);
+              else if (p.uni_a_rank4) hn_tma_load_4d(sa, &tm_a, &a_full[a_stage], 0, m0 + shift, cc, info >> 24);
               else hn_tma_load_3d(sa, &tm_a, &a_full[a_stage], cc * BLOCK_K, m0 + shift, info >> 24);
               hn_tma_load_4d(sa + p.uni_a_bytes, &tm_b, &a_full[a_stage], 0, n0, cc, (info >> 8) & 255);
             }
@@ -357,7 +368,18 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
           hn_trace(trace, 1, tri, 1);
           hn_tc_fence_after();
           if (hn_elect_one()) {
-            if (!(dbg_flags & 4)) {                            // (timing experiment: bit 2 skips the MMAs)
+            if (p.stem_tpr > 0) {
+              // direct stem: four [128 x 64 B] SWIZZLE_64B tiles (kernel rows 4*step .. +3), two K=16 steps each; kernel
+              // rows 2j and 2j+1 meet the two 64-byte halves of weight k-block j
+              const uint64_t hi64 = (uint64_t(512 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(4) << 61);
+#pragma unroll
+              for (int rr = 0; rr < 4; ++rr) {
+                const uint64_t da = hi64 | (uint64_t)(sa + rr * (8192 >> 4));
+                const uint64_t db = desc_hi | (uint64_t)(sb + (rr >> 1) * B_SLOT_D + (rr & 1) * 4);
+                hn_umma_bf16(d_tmem, da, db, idesc, accumulate | (uint32_t)rr);
+                hn_umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
+              }
+            } else if (!(dbg_flags & 4)) {                     // (timing experiment: bit 2 skips the MMAs)
               hn_umma_bf16_x4(d_tmem, desc_hi | (sa + (units & 3) * uni_plane_d + ((units >> 2) & 15) * ROW_D),
                               desc_hi | (sb + ((units >> 6) & 3) * B_SLOT_D), idesc, accumulate);
               if (nu > 1)
@@ -503,7 +525,13 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       // decode the padded pixel this accumulator row belongs to (divisions by multiply-high, see fastdiv())
       int img = 0, h = 0, w = 0;
       bool interior = false;
-      if (m < rows) {
+      if (p.stem_tpr > 0) {                              // stem tile: 128 output columns of one output row
+        const int row = mt / p.stem_tpr;
+        img = row / p.stem_h;
+        h = row - img * p.stem_h;
+        w = (mt - row * p.stem_tpr) * BLOCK_M + quarter * 32 + lane;
+        interior = w < wp && img < p.n_img;
+      } else if (m < rows) {
         img = (int)((__umulhi((uint32_t)m, div_img_mul) + (uint32_t)m) >> div_img_sh);
         const int rem = m - img * img_rows;
         const int hh = (int)((__umulhi((uint32_t)rem, div_wp_mul) + (uint32_t)rem) >> div_wp_sh);
@@ -953,7 +981,7 @@ PFN_encodeTiled get_encode() {
 }
 
 int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-             const cuuint32_t* box) {
+             const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     hn_set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
@@ -961,7 +989,7 @@ int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, 
   }
   cuuint32_t ones[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides_bytes, box, ones,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     hn_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu %llu)", (int)r, rank,
@@ -1095,6 +1123,18 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
   HN_REQUIRE(2 * d->dilation <= A_BOX_ROWS_MAX - BLOCK_M, "hn_conv2d_bf16: dilation %d too large for a shared A box",
              d->dilation);
   p.m_tiles = hn_div_up(p.rows, BLOCK_M);
+  const bool stem = d->stem_pitch_w > 0;
+  if (stem) {
+    HN_REQUIRE(!force_bn && d->kh == 1 && d->stride == 1 && d->cin == 256 && d->halo_in == 0 && d->in_phases == 1 &&
+                   d->cout_pad <= 128 && !d->res && !d->gn_stats && !d->splitk_ws,
+               "hn_conv2d_bf16: a direct stem is a plain 1x1-over-patches convolution with cin = 256, cout_pad <= 128");
+    HN_REQUIRE(d->stem_pitch_h >= 2 * d->h + 6 && d->stem_pitch_h % 2 == 0 && d->stem_pitch_w >= 2 * d->w + 8,
+               "hn_conv2d_bf16: stem frame %dx%d too small for a %dx%d output (needs >= %dx%d, even height)",
+               d->stem_pitch_h, d->stem_pitch_w, d->h, d->w, 2 * d->h + 6, 2 * d->w + 8);
+    p.stem_tpr = hn_div_up(d->w, BLOCK_M);
+    p.stem_h = d->h;
+    p.m_tiles = d->n * d->h * p.stem_tpr;
+  }
   int bn = force_bn ? force_bn
                     : (d->block_n ? d->block_n
                                   : pick_block_n(d->cout_pad, p.m_tiles, p.num_taps * p.cin_chunks, d->gn_stats ? 32 : 16));
@@ -1110,7 +1150,7 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
   const int k_blocks_total = p.num_taps * p.cin_chunks;
   const long long b_bytes = (long long)k_blocks_total * bn * BLOCK_K * 2;
   bool rb = !force_bn && cs == 1 && p.n_tiles == 1 && bn <= 64 && b_bytes <= PIPE_BYTES_MAX - 4 * A_SLOT_BYTES &&
-            p.m_tiles >= 2 * hn_num_sms() && !(d->debug & 16);
+            p.m_tiles >= 2 * hn_num_sms() && !(d->debug & 16) && !stem;
   const bool uni = bn <= 128 && !rb;      // unified stages (must match the kernel's constexpr UNI)
 
   // A-box groups.  Pixel (oh*stride + dr, ow*stride + ds) of tap (r, s), dr = (r - kh/2)*dil, ds = (s - kw/2)*dil, is row
@@ -1275,7 +1315,19 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
   }
   CUtensorMap& ta = out->ta;
   CUtensorMap& tb = out->tb;
-  if (uni && p.uni_a_rank4) {
+  if (stem) {
+    // Patch view of the zero-framed canvas [n][ph][pw][4ch] (8 bytes per pixel).  Kernel row r of output pixel (oy, ox) is
+    // the 8 pixels x 4 channels = 32 elements (64 bytes) starting at frame pixel (2*oy + r, 2*ox):
+    //   dim0 32 elements | dim1 ox (two pixels = 16 bytes: the rows of consecutive ox overlap) | dim2 frame row | dim3 image
+    // box {32, 128, 4, 1} = four [128 output pixels][64 bytes] tiles, one per kernel row, SWIZZLE_64B: two k-blocks of
+    // the GEMM per k-step (a k-block = two kernel rows = 64 elements).
+    const cuuint64_t pw = (cuuint64_t)d->stem_pitch_w, ph = (cuuint64_t)d->stem_pitch_h;
+    const cuuint64_t dims[4] = {32, (cuuint64_t)d->w, ph, (cuuint64_t)d->n};
+    const cuuint64_t strides[3] = {16, pw * 8, ph * pw * 8};
+    const cuuint32_t box[4] = {32, BLOCK_M, 4, 1};
+    int rc = make_map(&ta, d->in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  } else if (uni && p.uni_a_rank4) {
     // 1x1 with two chunks per k-step: dims (64 channels, rows, chunks, phases); the box puts the two chunk planes one
     // after the other in shared memory.  (The chunk stride is smaller than the row stride; if a driver refuses that,
     // fall back to one chunk per k-step.)
@@ -1299,7 +1351,7 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
       if (p.splits > p.k_steps) p.splits = p.k_steps;
     }
   }
-  if (!(uni && p.uni_a_rank4)) {
+  if (!stem && !(uni && p.uni_a_rank4)) {
     // dims (channels, rows, phases); unified stride-2 3x3: the box spans both column phases of a row phase
     const cuuint64_t dims[3] = {(cuuint64_t)d->cin, (cuuint64_t)p.rows, (cuuint64_t)d->in_phases};
     const cuuint64_t strides[2] = {(cuuint64_t)d->cin * 2, (cuuint64_t)p.rows * d->cin * 2};

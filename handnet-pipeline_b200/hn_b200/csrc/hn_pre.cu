@@ -15,6 +15,7 @@ struct PreParams {
   int in_h[PRE_MAX_IMAGES], in_w[PRE_MAX_IMAGES], out_h[PRE_MAX_IMAGES], out_w[PRE_MAX_IMAGES];
   float mean[3], inv_unused[3], stdv[3];
   int canvas_h, canvas_w, batch_offset;
+  int pad_top, pad_left, pitch_h, pitch_w;   // the canvas sits at (pad_top, pad_left) of a [pitch_h][pitch_w] pixel frame
 };
 
 __device__ __forceinline__ void bilinear_axis(int o, int in, int out, int& i0, int& i1, float& l0, float& l1) {
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p, uint
     outv.x = hn_pack_bf16(v[0], v[1]);
     outv.y = hn_pack_bf16(v[2], 0.f);
   }
-  canvas[((size_t)(p.batch_offset + b) * p.canvas_h + y) * p.canvas_w + x] = outv;
+  canvas[((size_t)(p.batch_offset + b) * p.pitch_h + y + p.pad_top) * p.pitch_w + x + p.pad_left] = outv;
 }
 
 // ------------------------------------------------------------------------------------- im2col
@@ -191,9 +192,20 @@ extern "C" int hn_preprocess_resize_pad(const float* const* images_host, const i
                                         const int* out_h_host, const int* out_w_host, int batch,
                                         const float* mean3_host, const float* std3_host, void* canvas_bf16,
                                         int canvas_h, int canvas_w, void* stream) {
+  return hn_preprocess_resize_pad_framed(images_host, in_h_host, in_w_host, out_h_host, out_w_host, batch, mean3_host,
+                                         std3_host, canvas_bf16, canvas_h, canvas_w, 0, 0, canvas_h, canvas_w, stream);
+}
+
+extern "C" int hn_preprocess_resize_pad_framed(const float* const* images_host, const int* in_h_host,
+                                               const int* in_w_host, const int* out_h_host, const int* out_w_host,
+                                               int batch, const float* mean3_host, const float* std3_host,
+                                               void* canvas_bf16, int canvas_h, int canvas_w, int pad_top, int pad_left,
+                                               int pitch_h, int pitch_w, void* stream) {
   HN_REQUIRE(images_host && in_h_host && in_w_host && out_h_host && out_w_host && canvas_bf16 && mean3_host && std3_host,
              "hn_preprocess_resize_pad: null pointer");
   HN_REQUIRE(batch > 0 && canvas_h > 0 && canvas_w > 0, "hn_preprocess_resize_pad: empty batch or canvas");
+  HN_REQUIRE(pad_top >= 0 && pad_left >= 0 && pitch_h >= canvas_h + pad_top && pitch_w >= canvas_w + pad_left,
+             "hn_preprocess_resize_pad: the canvas does not fit its frame");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   for (int b0 = 0; b0 < batch; b0 += PRE_MAX_IMAGES) {
     const int nb = (batch - b0 < PRE_MAX_IMAGES) ? batch - b0 : PRE_MAX_IMAGES;
@@ -216,6 +228,10 @@ extern "C" int hn_preprocess_resize_pad(const float* const* images_host, const i
     }
     p.canvas_h = canvas_h;
     p.canvas_w = canvas_w;
+    p.pad_top = pad_top;
+    p.pad_left = pad_left;
+    p.pitch_h = pitch_h;
+    p.pitch_w = pitch_w;
     p.batch_offset = b0;
     dim3 grid(hn_div_up(canvas_w, 256), canvas_h, nb);
     preprocess_kernel<<<grid, 256, 0, st>>>(p, reinterpret_cast<uint2*>(canvas_bf16));

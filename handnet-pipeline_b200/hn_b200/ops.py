@@ -60,6 +60,21 @@ class Act:
         return self.interior().permute(0, 3, 1, 2).float().contiguous()
 
 
+class StemFrame:
+    """Zero-framed 4-channel bf16 canvas [n, hc+6, wc+8, 4] (canvas at row 3, column 4): input of the direct stem."""
+
+    __slots__ = ("t", "n", "hc", "wc", "fh", "fw", "oh", "ow")
+
+    def __init__(self, n: int, canvas_hw: Tuple[int, int], device="cuda"):
+        self.n, (self.hc, self.wc) = n, canvas_hw
+        self.fh, self.fw = canvas_hw[0] + 6, canvas_hw[1] + 8
+        self.oh, self.ow = canvas_hw[0] // 2, canvas_hw[1] // 2
+        self.t = torch.zeros((n, self.fh, self.fw, 4), dtype=BF16, device=device)
+
+    def canvas(self) -> torch.Tensor:
+        return self.t[:, 3:3 + self.hc, 4:4 + self.wc, :]
+
+
 class PhaseAct:
     """Phase-split haloed NHWC bf16: t[4, n, h2 + 2*halo, w2 + 2*halo, c], phase = (y & 1) * 2 + (x & 1),
     (h2, w2) = ceil((h, w) / 2).  Input format of the stride-2 convolutions."""
@@ -143,9 +158,20 @@ def launch_count() -> int:
     return int(_lib.load().hn_launch_count())
 
 
+STEM_PAD_TOP, STEM_PAD_LEFT = 3, 4       # position of the canvas inside the zero frame the direct stem reads
+
+
+def stem_frame_hw(canvas_hw: Tuple[int, int]) -> Tuple[int, int]:
+    """Frame (pitch) of the zero-padded canvas for hn_conv2d_bf16's direct 7x7/2 stem: 3 rows above / below (the
+    eighth, zero-weight kernel row included) and 4 columns left / right."""
+    return canvas_hw[0] + 6, canvas_hw[1] + 8
+
+
 def preprocess(images: Sequence[torch.Tensor], out_sizes: Sequence[Tuple[int, int]], canvas_hw: Tuple[int, int],
-               mean: Sequence[float], std: Sequence[float], canvas: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """T1.  images: list of fp32 [3,H,W] CUDA tensors -> bf16 canvas [B, Hc, Wc, 4]."""
+               mean: Sequence[float], std: Sequence[float], canvas: Optional[torch.Tensor] = None,
+               frame: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """T1.  images: list of fp32 [3,H,W] CUDA tensors -> bf16 canvas [B, Hc, Wc, 4]; or, with `frame` (bf16
+    [B, Hc+6, Wc+8, 4], zero outside the canvas), into the canvas rectangle at (3, 4) of the frame."""
     b = len(images)
     imgs = []
     for im in images:
@@ -154,7 +180,7 @@ def preprocess(images: Sequence[torch.Tensor], out_sizes: Sequence[Tuple[int, in
             raise RuntimeError("images must be float32 [3, H, W]")
         imgs.append(im.contiguous())
     dev = imgs[0].device
-    if canvas is None:
+    if canvas is None and frame is None:
         canvas = torch.empty((b, canvas_hw[0], canvas_hw[1], 4), dtype=BF16, device=dev)
     ptrs = (C.c_void_p * b)(*[t.data_ptr() for t in imgs])
     ih = (C.c_int * b)(*[int(t.shape[1]) for t in imgs])
@@ -163,6 +189,13 @@ def preprocess(images: Sequence[torch.Tensor], out_sizes: Sequence[Tuple[int, in
     ow = (C.c_int * b)(*[int(s[1]) for s in out_sizes])
     m3 = (C.c_float * 3)(*[float(v) for v in mean])
     s3 = (C.c_float * 3)(*[float(v) for v in std])
+    if frame is not None:
+        fh, fw = stem_frame_hw(canvas_hw)
+        assert frame.dtype == BF16 and tuple(frame.shape) == (b, fh, fw, 4) and frame.is_contiguous()
+        check(_lib.load().hn_preprocess_resize_pad_framed(ptrs, ih, iw, oh, ow, b, m3, s3, frame.data_ptr(), canvas_hw[0],
+                                                          canvas_hw[1], STEM_PAD_TOP, STEM_PAD_LEFT, fh, fw, stream_ptr()),
+              "hn_preprocess_resize_pad_framed")
+        return frame
     check(_lib.load().hn_preprocess_resize_pad(ptrs, ih, iw, oh, ow, b, m3, s3, canvas.data_ptr(), canvas_hw[0],
                                                canvas_hw[1], stream_ptr()), "hn_preprocess_resize_pad")
     return canvas
@@ -194,9 +227,14 @@ def conv2d(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 1, d
            out_transpose_hw: bool = False, out_phase: Optional[PhaseAct] = None,
            gn_stats: Optional[torch.Tensor] = None, gn_groups: int = 0, block_n: int = 0, cluster: int = 0,
            algo_k: int = 0, debug: int = 0, splitk=None, splits: int = 0, trace: Optional[torch.Tensor] = None):
-    """hn_conv2d_bf16.  x: Act (stride 1) or PhaseAct (stride 2).  relu: bool or (lo, hi) channel range."""
+    """hn_conv2d_bf16.  x: Act (stride 1), PhaseAct (stride 2) or StemFrame (direct 7x7/2 stem; ksize = 1, the weight
+    from pack_stem_weight).  relu: bool or (lo, hi) channel range."""
     d = ConvDesc()
-    if isinstance(x, PhaseAct):
+    if isinstance(x, StemFrame):
+        assert stride == 1 and ksize == 1
+        d.in_, d.n, d.h, d.w, d.cin, d.halo_in, d.in_phases = x.t.data_ptr(), x.n, x.oh, x.ow, 256, 0, 1
+        d.stem_pitch_h, d.stem_pitch_w = x.fh, x.fw
+    elif isinstance(x, PhaseAct):
         assert stride == 2
         d.in_, d.n, d.h, d.w, d.cin, d.halo_in, d.in_phases = x.t.data_ptr(), x.n, x.h2, x.w2, x.c, x.halo, 4
     else:

@@ -193,9 +193,10 @@ class FCOSPlan:
         assert hc % 32 == 0 and wc % 32 == 0
         B = batch
         self.batch, self.canvas_hw = B, canvas_hw
-        self.canvas = torch.zeros((B, hc, wc, 4), dtype=torch.bfloat16, device=device)
+        # zero-framed canvas: the stem convolution gathers its 7x7 patches straight from it (no im2col buffer)
+        self.frame = ops.StemFrame(B, (hc, wc), device)
+        self.canvas = self.frame.canvas()
         h1, w1 = hc // 2, wc // 2
-        self.stem_a = torch.empty((B * h1 * w1, STEM_K_RGB), dtype=torch.bfloat16, device=device)
         self.stem = Act(B, h1, w1, 64, 0, device)
         sizes = [(hc // 4, wc // 4, 64), (hc // 8, wc // 8, 128), (hc // 16, wc // 16, 256), (hc // 32, wc // 32, 512)]
         self.stage = []
@@ -248,9 +249,7 @@ class FCOSExecutor:
         hc, wc = pl.canvas_hw
         h1, w1 = hc // 2, wc // 2
         mark("preprocess")
-        ops.im2col_7x7s2(pl.canvas, STEM_K_RGB, out=pl.stem_a)
-        a = Act(B, h1, w1, STEM_K_RGB, 0, pl.canvas.device, t=pl.stem_a.view(B, h1, w1, STEM_K_RGB))
-        ops.conv2d(a, w.stem_w, cout=64, ksize=1, scale=w.stem_scale, shift=w.stem_shift, relu=True, out=pl.stem,
+        ops.conv2d(pl.frame, w.stem_w, cout=64, ksize=1, scale=w.stem_scale, shift=w.stem_shift, relu=True, out=pl.stem,
                    algo_k=147)
         x = ops.maxpool3x3s2(pl.stem.t, pl.stage[0][0])
         feats = []
@@ -344,7 +343,7 @@ class FCOSExecutor:
         hc = int(math.ceil(max(s[0] for s in sizes) / 32.0) * 32)
         wc = int(math.ceil(max(s[1] for s in sizes) / 32.0) * 32)
         pl = self.plan(len(images), (hc, wc), dev)
-        ops.preprocess(images, sizes, (hc, wc), m.image_mean, m.image_std, canvas=pl.canvas)
+        ops.preprocess(images, sizes, (hc, wc), m.image_mean, m.image_std, frame=pl.frame.t)
         self.backbone_heads(pl)
         # resize_boxes ratios are float32 tensor divisions in the reference (fcos_utils/fcos.py:771-776)
         f32 = torch.float32

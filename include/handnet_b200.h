@@ -52,6 +52,14 @@ int hn_preprocess_resize_pad(const float* const* images_host, const int* in_h_ho
                              const int* out_h_host, const int* out_w_host, int batch, const float* mean3_host,
                              const float* std3_host, void* canvas_bf16, int canvas_h, int canvas_w, void* stream);
 
+/* Same, but the canvas is the sub-rectangle at (pad_top, pad_left) of a larger frame bf16 [batch][pitch_h][pitch_w][4]
+ * whose remaining pixels are not touched (the caller keeps them zero): the zero-padded input of hn_conv2d_bf16's
+ * direct 7x7 stem (stem_pitch_*). */
+int hn_preprocess_resize_pad_framed(const float* const* images_host, const int* in_h_host, const int* in_w_host,
+                                    const int* out_h_host, const int* out_w_host, int batch, const float* mean3_host,
+                                    const float* std3_host, void* canvas_bf16, int canvas_h, int canvas_w, int pad_top,
+                                    int pad_left, int pitch_h, int pitch_w, void* stream);
+
 /* ---- stem: 7x7 stride-2 pad-3 patches as GEMM rows (fcos backbone.body.conv1; a2j/resnet.py:105) ----------
  * K is laid out as 8 kernel rows x 8 pixels x C: k = (r*8 + px)*C + ch with input pixel (2*oy - 3 + r,
  * 2*ox - 4 + px); r = 7 and px = 0 are padding that meets zero weights (see pack_stem_weight in hn_b200/ops.py).
@@ -105,6 +113,12 @@ typedef struct hn_conv_desc {
   /* bring-up only: NULL in production.  When set, CTA 0 logs (clock64, tag) pairs of its producer, MMA and first
    * epilogue warp into trace[3][2048][2] (int64) -- see tools/conv_trace.py. */
   void* trace;
+  /* Direct 7x7 stride-2 pad-3 stem over a 4-channel canvas (no im2col buffer).  0 = ordinary convolution.  Otherwise
+   * `in` is bf16 [n][stem_pitch_h][stem_pitch_w][4], all zero except the canvas at row 3, column 4 (stem_pitch_h >=
+   * 2*h + 6 and even, stem_pitch_w >= 2*w + 8); (h, w) are the OUTPUT sizes, kh = kw = 1, cin = 256, halo_in = 0, and
+   * the weights are pack_stem_weight's K = 8 kernel rows x 8 pixels x 4 channels (k-block major like every weight).
+   * TMA gathers the patch rows straight from the canvas with an overlapping-stride tensor map. */
+  int stem_pitch_h, stem_pitch_w;
 } hn_conv_desc;
 int hn_conv2d_bf16(const hn_conv_desc* desc, void* stream);
 

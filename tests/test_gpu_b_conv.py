@@ -222,6 +222,32 @@ def test_stem_im2col_gemm_and_maxpool(ops):
     close_bf16(pooled.to_nchw().cpu(), ref, "maxpool")
 
 
+@pytest.mark.parametrize("n,h,w", [(2, 64, 96), (1, 96, 320), (3, 32, 544)])
+def test_stem_direct_from_framed_canvas(ops, n, h, w):
+    """backbone.body.conv1 + FrozenBN + ReLU straight from the zero-framed canvas (overlapping-stride TMA patches, no
+    im2col buffer) == F.conv2d(stride 2, padding 3); also == the im2col + GEMM path bit for bit (same K order)."""
+    g = torch.Generator().manual_seed(15)
+    canvas = torch.zeros(n, h, w, 4)
+    canvas[..., :3] = rand(g, n, h, w, 3)
+    wt = rand(g, 64, 3, 7, 7, scale=0.08)
+    scale = 0.5 + torch.rand(64, generator=g)
+    shift = 0.2 * torch.randn(64, generator=g)
+    x_nchw = canvas[..., :3].permute(0, 3, 1, 2).contiguous()
+    conv = q(F.relu(F.conv2d(x_nchw, wt, stride=2, padding=3) * scale[None, :, None, None] + shift[None, :, None, None]))
+    frame = ops.StemFrame(n, (h, w), DEV)
+    frame.canvas().copy_(canvas.to(torch.bfloat16))
+    wp = ops.pack_stem_weight(wt.cuda(), 256)
+    stem = ops.Act(n, h // 2, w // 2, 64, 0, DEV)
+    ops.conv2d(frame, wp, cout=64, ksize=1, scale=scale.cuda(), shift=shift.cuda(), relu=True, out=stem)
+    a, oh, ow = ops.im2col_7x7s2(canvas.to(torch.bfloat16).cuda(), 256)
+    stem2 = ops.Act(n, oh, ow, 64, 0, DEV)
+    ops.conv2d(ops.Act(n, oh, ow, 256, 0, DEV, t=a.view(n, oh, ow, 256)), wp, cout=64, ksize=1, scale=scale.cuda(),
+               shift=shift.cuda(), relu=True, out=stem2)
+    torch.cuda.synchronize()
+    close_bf16(stem.to_nchw().cpu(), conv, "direct stem conv")
+    assert torch.equal(stem.t, stem2.t), "direct stem and im2col + GEMM must agree exactly"
+
+
 def test_stem_fp32_depth_one_channel(ops):
     """A2J stem: one depth channel expanded to three == weights summed over Cin (a2j/a2j.py:197-199)."""
     g = torch.Generator().manual_seed(14)

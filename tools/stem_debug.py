@@ -1,0 +1,28 @@
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "handnet-pipeline_b200"))
+import torch, torch.nn.functional as F
+from hn_b200 import ops
+torch.manual_seed(0)
+n, h, w = 1, 64, 96
+mode = sys.argv[1] if len(sys.argv) > 1 else "rand"
+canvas = torch.zeros(n, h, w, 4)
+if mode == "ones":
+    canvas[..., :3] = 1.0
+else:
+    canvas[..., :3] = torch.randn(n, h, w, 3)
+wt = torch.zeros(64, 3, 7, 7)
+if mode == "ones":
+    wt[:, 0, 3, 3] = 1.0          # centre tap only: output == input at (2oy, 2ox)
+else:
+    wt = torch.randn(64, 3, 7, 7) * 0.05
+frame = ops.StemFrame(n, (h, w), "cuda")
+frame.canvas().copy_(canvas.to(torch.bfloat16))
+wp = ops.pack_stem_weight(wt.cuda(), 256)
+stem = ops.Act(n, h // 2, w // 2, 64, 0, "cuda")
+ops.conv2d(frame, wp, cout=64, ksize=1, out=stem)
+torch.cuda.synchronize()
+got = stem.to_nchw().cpu()
+ref = F.conv2d(canvas[..., :3].permute(0, 3, 1, 2).to(torch.bfloat16).float(), wt.to(torch.bfloat16).float(), stride=2, padding=3)
+print("finite frac", torch.isfinite(got).float().mean().item(), "max abs err", (got - ref).abs()[torch.isfinite(got)].max().item() if torch.isfinite(got).any() else None)
+print("got[0,0,:4,:8]\n", got[0, 0, :4, :8]); print("ref[0,0,:4,:8]\n", ref[0, 0, :4, :8])
