@@ -95,6 +95,25 @@ class HandNet(nn.Module):
             self._steps[key] = runtime.GraphedHandNet(self, len(images), shp[-2], shp[-1], int(depth_images.shape[1]))
         return self._steps[key]
 
+    def forward_frames(self, bgr_u8: torch.Tensor, depth_u16: torch.Tensor):
+        """The caller's frame ingest of ros_demo.py (:227-238, :266-267) on the device: camera frames as they arrive --
+        uint8 BGR [B,H,W,3] and uint16 millimetres [B,H,W] (host or device tensors) -> ``forward``.  The host -> device
+        copy moves 5 bytes per pixel instead of the 16 of fp32 RGB + depth; the conversion (x/255, RGB order, mm/1000) is
+        bit-exact with the numpy expressions of the reference's caller."""
+        dev = next(self.parameters()).device
+        bgr = bgr_u8.to(dev, non_blocking=True)
+        dpt = depth_u16.to(dev, non_blocking=True)
+        rgb, depth = ops.ingest_frames(bgr.contiguous(), dpt.contiguous())
+        return self.forward(list(rgb.unbind(0)), depth_images=depth)
+
+    @staticmethod
+    def convert_joints_device(joints: torch.Tensor, crops: torch.Tensor, paras=None, crop_size: int = CROP_SIZE):
+        """Batched a2j.convert_joints on the device (the step after the path in ros_demo.py:289,329-330): crop-space
+        joints [n,21,3] + crops [n,4] int64 (+ camera intrinsics fx, fy, cx, cy) -> image pixels / camera millimetres."""
+        dev = crops.device if crops.is_cuda else torch.device("cuda")
+        p = None if paras is None else torch.as_tensor(paras)          # float64 or float32 intrinsics, as given
+        return ops.convert_joints(joints.to(dev, torch.float32).contiguous(), crops.to(dev, torch.int64), p, crop_size, crop_size)
+
     def forward(self, images, depth_images=None, is_3D: bool = False, is_detect: bool = False):
         if is_detect or is_3D:
             return None                                  # the reference falls through and returns None

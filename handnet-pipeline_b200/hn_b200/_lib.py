@@ -54,6 +54,9 @@ SIGNATURES = {
     "hn_conv_multi_build": (_i, [C.POINTER(ConvDesc), _i, _ip, _i, _c_p, _i64]),
     "hn_conv_multi_run": (_i, [_c_p, _i, _i, _i, _c_p]),
     "hn_conv_multi_set_trace": (_i, [_c_p]),
+    "hn_ingest_frames": (_i, [_c_p, _c_p, _i, _i, _i, _c_p, _c_p, _c_p]),
+    "hn_pack_nhwc4_frame": (_i, [_c_p, _i, _i, _i, _i, _ip, _c_p, _i, _i, _i, _i, _c_p]),
+    "hn_convert_joints": (_i, [_c_p, _c_p, _c_p, _c_p, _i, _i, _i, _i, _i, _c_p, _c_p]),
     "hn_maxpool3x3s2": (_i, [_c_p, _i, _i, _i, _i, _c_p, _i, _c_p]),
     "hn_groupnorm_relu": (_i, [_c_p, _i, _i, _i, _i, _i, _c_p, _i, _c_p, _c_p, _f, _c_p]),
     "hn_fcos_select_workspace_bytes": (_i64, [_i, _i]),

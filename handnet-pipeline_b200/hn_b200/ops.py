@@ -133,11 +133,12 @@ def pack_conv_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None) -> t
 
 
 def pack_stem_weight(w: torch.Tensor, k_pad: int) -> torch.Tensor:
-    """7x7 stem OIHW (cin = 3 or 1) -> bf16 [cout_pad][k_pad] in the K order of hn_im2col_7x7s2:
-    k = (r*8 + px)*C + ch with C = 4 (RGB canvas) or 1 (depth); px = 0, r = 7 and ch = 3 carry zero weights."""
+    """7x7 stem OIHW (cin = 3, 4 or 1) -> bf16 [cout_pad][k_pad] in the K order of hn_im2col_7x7s2 / the direct stem:
+    k = (r*8 + px)*C + ch with C = 4 (RGB or RGBD canvas) or 1 (depth); px = 0, r = 7 and (for RGB) ch = 3 carry zero
+    weights."""
     cout, cin, kh, kw = w.shape
-    assert (kh, kw) == (7, 7) and (cin, k_pad) in ((3, 256), (1, 64))
-    c = 4 if cin == 3 else 1
+    assert (kh, kw) == (7, 7) and (cin, k_pad) in ((3, 256), (4, 256), (1, 64))
+    c = 4 if cin >= 3 else 1
     m = torch.zeros((cout, 8, 8, c), dtype=torch.float32, device=w.device)
     m[:, :7, 1:, :cin] = w.detach().float().permute(0, 2, 3, 1)
     out = torch.zeros((pad_cout(cout), k_pad), dtype=BF16, device=w.device)
@@ -199,6 +200,58 @@ def preprocess(images: Sequence[torch.Tensor], out_sizes: Sequence[Tuple[int, in
     check(_lib.load().hn_preprocess_resize_pad(ptrs, ih, iw, oh, ow, b, m3, s3, canvas.data_ptr(), canvas_hw[0],
                                                canvas_hw[1], stream_ptr()), "hn_preprocess_resize_pad")
     return canvas
+
+
+def ingest_frames(bgr_u8: Optional[torch.Tensor], depth_u16: Optional[torch.Tensor], rgb_out: Optional[torch.Tensor] = None,
+                  depth_out: Optional[torch.Tensor] = None):
+    """Camera frames -> network inputs.  bgr_u8: uint8 [n,h,w,3] (cv2 BGR) -> fp32 [n,3,h,w] RGB in 0..1;
+    depth_u16: uint16 [n,h,w] millimetres (or int16 storage of the same bits) -> fp32 [n,1,h,w] metres."""
+    ref = bgr_u8 if bgr_u8 is not None else depth_u16
+    _require_cuda(ref, "frames")
+    n, h, w = int(ref.shape[0]), int(ref.shape[1]), int(ref.shape[2])
+    if bgr_u8 is not None:
+        assert bgr_u8.dtype == torch.uint8 and tuple(bgr_u8.shape) == (n, h, w, 3) and bgr_u8.is_contiguous()
+        if rgb_out is None:
+            rgb_out = torch.empty((n, 3, h, w), dtype=torch.float32, device=ref.device)
+        assert rgb_out.dtype == torch.float32 and tuple(rgb_out.shape) == (n, 3, h, w) and rgb_out.is_contiguous()
+    if depth_u16 is not None:
+        assert depth_u16.dtype in (torch.uint16, torch.int16) and tuple(depth_u16.shape) == (n, h, w) and depth_u16.is_contiguous()
+        if depth_out is None:
+            depth_out = torch.empty((n, 1, h, w), dtype=torch.float32, device=ref.device)
+        assert depth_out.dtype == torch.float32 and depth_out.numel() == n * h * w and depth_out.is_contiguous()
+    check(_lib.load().hn_ingest_frames(ptr(bgr_u8), ptr(depth_u16), n, h, w, ptr(rgb_out if bgr_u8 is not None else None),
+                                       ptr(depth_out if depth_u16 is not None else None), stream_ptr()), "hn_ingest_frames")
+    return rgb_out, depth_out
+
+
+def pack_nhwc4_frame(src: torch.Tensor, chan_map: Sequence[int], frame: "StemFrame") -> "StemFrame":
+    """fp32 [n,c,h,w] -> the canvas rectangle of a StemFrame, frame channel j = src channel chan_map[j] (-1: zero)."""
+    _require_cuda(src, "src")
+    n, c, h, w = src.shape
+    assert src.dtype == torch.float32 and src.is_contiguous() and (frame.n, frame.hc, frame.wc) == (n, h, w)
+    cm = (C.c_int * 4)(*[int(v) for v in chan_map])
+    check(_lib.load().hn_pack_nhwc4_frame(src.data_ptr(), n, c, h, w, cm, frame.t.data_ptr(), STEM_PAD_TOP, STEM_PAD_LEFT,
+                                          frame.fh, frame.fw, stream_ptr()), "hn_pack_nhwc4_frame")
+    return frame
+
+
+def convert_joints(uvd: torch.Tensor, crops: torch.Tensor, paras: Optional[torch.Tensor] = None, crop_w: int = 176,
+                   crop_h: int = 176, has_hand: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Batched a2j.convert_joints on the device.  uvd fp32 [n,J,3], crops int64 [n,4], paras (fx,fy,cx,cy) as a
+    float64 or float32 tensor (numpy evaluates the back-projection in the intrinsics' precision)."""
+    _require_cuda(uvd, "uvd")
+    n, j, _ = uvd.shape
+    assert uvd.dtype == torch.float32 and uvd.is_contiguous() and crops.dtype == torch.int64 and tuple(crops.shape) == (n, 4)
+    crops = crops.contiguous()
+    f64 = 1
+    if paras is not None:
+        f64 = 0 if paras.dtype == torch.float32 else 1
+        paras = paras.to(device=uvd.device, dtype=torch.float64 if f64 else torch.float32).contiguous()
+        assert paras.numel() == 4
+    out = torch.empty_like(uvd)
+    check(_lib.load().hn_convert_joints(uvd.data_ptr(), crops.data_ptr(), ptr(has_hand), ptr(paras), f64, n, j, crop_w,
+                                        crop_h, out.data_ptr(), stream_ptr()), "hn_convert_joints")
+    return out
 
 
 def im2col_7x7s2(x: torch.Tensor, k_pad: int, out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, int, int]:

@@ -68,7 +68,8 @@ def mark(name: str):
 
 _side_streams: Dict[str, List["torch.cuda.Stream"]] = {}
 SPLIT_K = True              # split-K (fp32 scratch + last-arriver epilogue) for the short, deep A2J layers
-A2J_MULTI = True            # run the A2J convolutions as one cooperative multi-convolution launch
+A2J_MULTI = False           # True: the A2J convolutions as ONE cooperative multi-convolution launch (measured slower than
+                            # per-layer launches with the three towers on forked graph branches: 721 vs 630 us for 8 crops)
 PARALLEL_CHAINS = True      # independent layer chains (head towers, A2J towers) on forked streams / graph branches
 
 
@@ -374,7 +375,9 @@ class A2JWeights:
             w0 = w0.sum(1, keepdim=True)
             self.stem_k = STEM_K_DEPTH
         else:
-            raise NotImplementedError("RGBD (4-channel) A2J stem is not built yet (SURVEY.md 8f rank 4)")
+            # RGBD variant (a2j/a2j.py:191-192): a 4-channel 7x7 stem, run as the direct stem over a framed NHWC4 canvas
+            assert self.channel_in == 4 and w0.shape[1] == 4, "A2J stem: 1 (depth) or 4 (RGBD) input channels"
+            self.stem_k = STEM_K_RGB
         self.stem_w = ops.pack_stem_weight(w0, self.stem_k)
         self.stem_scale, self.stem_shift = bn(b + "bn1")
         self.blocks = []
@@ -414,7 +417,11 @@ class A2JPlan:
         h, w = hw
         self.n = n
         h1, w1 = (h + 1) // 2, (w + 1) // 2
-        self.stem_a = torch.empty((n * h1 * w1, wts.stem_k), dtype=torch.bfloat16, device=device)
+        if wts.channel_in == 4:
+            assert h % 2 == 0 and w % 2 == 0, "RGBD crops must have even sizes"
+            self.frame = ops.StemFrame(n, (h, w), device)
+        else:
+            self.stem_a = torch.empty((n * h1 * w1, wts.stem_k), dtype=torch.bfloat16, device=device)
         self.stem = Act(n, h1, w1, 64, 0, device)
         h2, w2 = (h1 + 1) // 2, (w1 + 1) // 2
         self.pool = Act(n, h2, w2, 64, 1, device)
@@ -488,11 +495,17 @@ class A2JExecutor:
         if key not in self.plans:
             self.plans[key] = A2JPlan(w, n, (h, wd), x.device, self.model.num_joints)
         pl = self.plans[key]
-        depth = x[:, 0].contiguous() if x.shape[1] != 1 else x.reshape(n, h, wd)
-        _, h1, w1 = ops.im2col_7x7s2(depth, w.stem_k, out=pl.stem_a)
-        a = Act(n, h1, w1, w.stem_k, 0, x.device, t=pl.stem_a.view(n, h1, w1, w.stem_k))
-        ops.conv2d(a, w.stem_w, cout=64, ksize=1, scale=w.stem_scale, shift=w.stem_shift, relu=True, out=pl.stem,
-                   algo_k=147)       # 3 identical input channels in the reference: 7*7*3 MACs per output
+        if w.channel_in == 4:
+            # x[:, 0:4] (a2j/a2j.py:196) -> framed bf16 NHWC4 -> direct stem
+            ops.pack_nhwc4_frame(x.contiguous(), (0, 1, 2, 3), pl.frame)
+            ops.conv2d(pl.frame, w.stem_w, cout=64, ksize=1, scale=w.stem_scale, shift=w.stem_shift, relu=True, out=pl.stem,
+                       algo_k=196)
+        else:
+            depth = x[:, 0].contiguous() if x.shape[1] != 1 else x.reshape(n, h, wd)
+            _, h1, w1 = ops.im2col_7x7s2(depth, w.stem_k, out=pl.stem_a)
+            a = Act(n, h1, w1, w.stem_k, 0, x.device, t=pl.stem_a.view(n, h1, w1, w.stem_k))
+            ops.conv2d(a, w.stem_w, cout=64, ksize=1, scale=w.stem_scale, shift=w.stem_shift, relu=True, out=pl.stem,
+                       algo_k=147)       # 3 identical input channels in the reference: 7*7*3 MACs per output
         cur = ops.maxpool3x3s2(pl.stem.t, pl.pool)
         if A2J_MULTI and ops.PROFILE is None:
             # layer1..4 and the three towers: 67 convolutions in ONE cooperative launch with grid barriers between
@@ -557,6 +570,20 @@ class A2JExecutor:
         c5 = cur
         hf, wf = pl.feat_hw
         towers = (("regressionModel", c5, pl.reg), ("DepthRegressionModel", c5, pl.dep), ("classificationModel", c4, pl.cls))
+        if ops.RECORD is None and ops.PROFILE is None and PARALLEL_CHAINS:
+            # eager / per-layer launches: the three towers are independent chains -> forked streams (graph branches)
+            def chain(name, src, dst):
+                def run():
+                    x = src
+                    for i in range(4):
+                        o = pl.act(f"{name}{i}", hf, wf, 256)
+                        w.towers[name][0][i].run(x, relu=True, out=o, splitk=pl.splitk(f"{name}{i}", x, w.towers[name][0][i]))
+                        x = o
+                    w.towers[name][1].run(x, out_f32=dst.view(n, hf * wf, -1), out_transpose_hw=True,
+                                          splitk=pl.splitk(name + "out", x, w.towers[name][1]))
+                return run
+            run_chains([chain(*t) for t in towers], pl.device)
+            return
         t = {name: src for name, src, _ in towers}
         for i in range(4):
             for name, _, _ in towers:
@@ -569,7 +596,6 @@ class A2JExecutor:
             # permute(0,3,2,1) + view of the reference == w-major rows (a2j/a2j.py:85-89)
             w.towers[name][1].run(t[name], out_f32=dst.view(n, hf * wf, -1), out_transpose_hw=True,
                                   splitk=pl.splitk(name + "out", t[name], w.towers[name][1]))
-
 
     def forward_device(self, x: torch.Tensor) -> torch.Tensor:
         cls, reg, dep, pl = self.heads_device(x)

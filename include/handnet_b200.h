@@ -137,6 +137,28 @@ int hn_conv_multi_run(void* plan_dev, int n_convs, int n_groups, int grid, void*
  * NULL switches it off. */
 int hn_conv_multi_set_trace(void* buf);
 
+/* ---- frame ingest (ros_demo.py:227-238, 266-267): what the camera delivers -> what HandNet.forward takes ---------
+ * bgr_u8: DEVICE uint8 [n][h][w][3] (cv2 BGR) -> rgb_out fp32 [n][3][h][w] = float32(byte) / 255 in R,G,B order;
+ * depth_u16: DEVICE uint16 [n][h][w] millimetres -> depth_out fp32 [n][1][h][w] = float32(mm) / 1000.  Either pair may
+ * be NULL.  Bit-exact with numpy's astype(float32) / 255.0 and / 1000.0. */
+int hn_ingest_frames(const void* bgr_u8, const void* depth_u16, int n, int h, int w, float* rgb_out, float* depth_out,
+                     void* stream);
+
+/* fp32 NCHW images -> the zero-framed 4-channel bf16 canvas of the direct stem (hn_conv_desc.stem_pitch_*): frame pixel
+ * (pad_top + y, pad_left + x), channel j = src channel chan_map4_host[j] (-1 = zero).  The RGBD A2J variant feeds its
+ * 4-channel crops this way with the reference's [2,1,0,3] reorder (handnet_pipeline.py:102) as the channel map. */
+int hn_pack_nhwc4_frame(const float* src, int n, int c, int h, int w, const int* chan_map4_host, void* frame_bf16,
+                        int pad_top, int pad_left, int pitch_h, int pitch_w, void* stream);
+
+/* a2j.convert_joints + uvd2xyz, batched on the device (a2j/a2j.py:17-43, datasets3d/a2jdataset.py:31-38).
+ * uvd [n][joints][3] crop-space joints, crops int64 [n][4] = (x_min, y_min, x_max, y_max), paras4_dev = (fx, fy, cx, cy)
+ * in DEVICE memory as 4 doubles (paras_is_f64 = 1) or 4 floats (0), or NULL (pixels only).  out [n][joints][3]:
+ * u*(x_max-x_min)/crop_w + x_min etc. evaluated in float64 and stored as float32, as numpy >= 2 evaluates a float32
+ * array times an int64 scalar; with paras, (uv - c) * z / f in the intrinsics' precision -> float32, then * 1000 in
+ * float32.  has_hand (int32 [n]) may be NULL; frames with has_hand == 0 produce zeros. */
+int hn_convert_joints(const float* uvd, const int64_t* crops, const int* has_hand, const void* paras4_dev,
+                      int paras_is_f64, int n, int joints, int crop_w, int crop_h, float* out, void* stream);
+
 /* ---- 3x3 stride-2 pad-1 max pool (torchvision resnet maxpool; a2j/resnet.py:108) ----------------------------
  * in: bf16 [n][h][w][c] (no halo) -> out: bf16 haloed NHWC [n][oh+2*halo][ow+2*halo][c], oh = (h+1)/2. */
 int hn_maxpool3x3s2(const void* in, int n, int h, int w, int c, void* out, int out_halo, void* stream);

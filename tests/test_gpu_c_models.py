@@ -263,6 +263,7 @@ def test_a2j_multi_conv_kernel_equals_per_layer_launches(golden):
     g = torch.Generator().manual_seed(23)
     x = (torch.rand(5, 1, 176, 176, generator=g) * 1.5).cuda()
     outs = []
+    default = runtime.A2J_MULTI
     for multi in (True, False):
         runtime.A2J_MULTI = multi
         try:
@@ -277,7 +278,7 @@ def test_a2j_multi_conv_kernel_equals_per_layer_launches(golden):
             assert (j1 - j2).abs().max() < 2e-3
             outs.append((cls.clone(), reg.clone(), dep.clone(), j1))
         finally:
-            runtime.A2J_MULTI = True
+            runtime.A2J_MULTI = default
     for a, b in zip(outs[0], outs[1]):
         # (a sum that lands on the other side of a bf16 rounding boundary moves one activation by 2^-8 relative)
         assert ((a - b).abs() / b.abs().clamp(min=1.0)).max() < 1e-2
