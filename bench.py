@@ -164,7 +164,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"e2e_handnet_{IMG_W}x{IMG_H}_cpu_oracle", "frames_per_step": sample,
+        "config": {"workload": f"e2e_handnet_{IMG_W}x{IMG_H}_b{FRAMES_PER_GPU}_per_gpu", "frames_per_step": sample,
+                   "sample": f"{sample} of the {FRAMES_PER_GPU} frames of a step", "canvas": "800x1088",
                    "note": "reference is Python with uninstalled deps on the box; timed its CPU restatement (oracle/)"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} VGA frames per step, {args.steps} steps"},
@@ -294,6 +295,24 @@ def main():
         h2d = rgb_pin.numel() * 4 + depth_pin.numel() * 4
         d2h = step.d2h_bytes
 
+        # ---------------- the same with the frames as the camera delivers them ----------------
+        # uint8 BGR + uint16 millimetres on the host -> HandNet.forward_frames: H2D of 5 bytes per pixel, the
+        # conversion ros_demo.py does with numpy on the host (x/255, BGR->RGB, mm/1000) runs on the device.
+        bgr_pin = (rgb_h.flip(1).permute(0, 2, 3, 1) * 255).round().to(torch.uint8).contiguous().pin_memory()
+        mm_pin = (depth_h[:, 0] * 1000).round().clamp(0, 32767).to(torch.int16).contiguous().pin_memory()
+        for _ in range(3):
+            net.forward_frames(bgr_pin, mm_pin)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            net.forward_frames(bgr_pin, mm_pin)
+        barrier()
+        t = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_u8_value = world * B * args.steps / (float(t.item()) * 1e-3)
+        h2d_u8 = bgr_pin.numel() + mm_pin.numel() * 2
+
         # ---------------- roofline of the dominant kernel (rank 0) ----------------
         roof = None
         counts = step.counts()
@@ -313,8 +332,8 @@ def main():
             ach_all = flops / (conv_ms * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": "conv_igemm_kernel<256> (tcgen05 shifted GEMM), 256->256 3x3 @100x136 x8 frames",
                     "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
-                    # dram__bytes_read.sum + dram__bytes_write.sum of this launch, profiles/r01_conv_igemm_full.txt
-                    "traffic": 68.8e6, "algorithmic_flops_per_launch": dom_flop, "launch_ms": dom_ms,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of this launch, profiles/r01b_conv_igemm_full.txt
+                    "traffic": 77.4e6, "algorithmic_flops_per_launch": dom_flop, "launch_ms": dom_ms,
                     "launches_per_step": len(dom), "step_share": dom_ms * len(dom) / (total_ms / args.steps),
                     "peak_source": peaks["source"] + " sustained",
                     "all_conv_launches": {"achieved": ach_all, "frac": ach_all / peaks["bf16_sustained"],
@@ -339,6 +358,8 @@ def main():
                        "candidates_per_frame": counts["cand"], "kept_per_frame": counts["kept"],
                        "frames_with_hand": counts["hands"], "weights": "random-init (hn_b200.synth), head bias " + str(CLS_BIAS)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e_u8_ingest": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
+                              "api": "HandNet.forward_frames(uint8 BGR, uint16 mm)"},
             "gpu_launches": int(launches) * args.steps,
             "gpu_launches_per_step": int(launches),
             "clocks": clocks,

@@ -92,6 +92,9 @@ struct ConvParams {
   int div_img_sh, div_wp_sh;
   int na_stages, nb_stages;         // ring depths
   int rb_b_bytes;                   // resident-weights mode: bytes of the weight slice
+  int rb3;                          // resident weights, 3x3 stride 1: ONE box brings the A rows of all three kernel rows of a
+                                    // chunk ([3][136 rows][128 B], the third box dimension steps by one image row), so a
+                                    // k-step is a whole 64-channel chunk: 36 MMAs per barrier round trip
   int vec32;                        // epilogue may use 32-byte global accesses (cout % 16 == 0, 32-byte aligned bases)
   int dbg_flags;                    // bring-up / timing experiments (bit0 no stores, bit1 no epilogue, bit2 no MMA, bit3 no TMA)
   long long* trace;                 // bring-up: CTA 0 logs (clock64, tag) pairs per role, TRACE_EVENTS each
@@ -116,7 +119,7 @@ __device__ __forceinline__ void hn_epi_bar_sync() {   // named barrier 1: the ep
 // Shared memory: [0, HDR_BYTES) barriers, GroupNorm accumulators, scale/shift of the N tile; then (1024-aligned) the
 // operand area: [resident weight slice (RB mode only)] [A ring: na x 17 KiB] [B ring: nb x BN*128 B].
 constexpr int MAX_STAGES = 12;
-constexpr int HDR_BARS = 512;
+constexpr int HDR_BARS = 640;
 constexpr int HDR_BYTES = HDR_BARS + GN_SMEM_FLOATS * 4 + 2 * 2 * 256 * 4;   // 20992, padded to 1024 below
 constexpr int HDR_PAD = ((HDR_BYTES + 1023) / 1024) * 1024;
 constexpr int PIPE_BYTES_MAX = 204800;                                        // 200 KiB for the operand rings
@@ -131,7 +134,12 @@ struct Cfg {
   static constexpr int NB_FIT = (PIPE_BYTES_MAX - NA * A_SLOT_BYTES) / B_STAGE_BYTES;
   static constexpr int NB = NB_FIT > MAX_STAGES ? MAX_STAGES : NB_FIT;
   static_assert(NB >= 4, "B ring too shallow");
-  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  // accumulator buffers in TMEM: as many as its 512 columns hold (up to 8), so that the MMA warp can run several
+  // tiles ahead of the epilogue and the hand-off latencies between the two never stall the tensor pipe (narrow tiles
+  // are short: a 64-column tile of a 64-channel layer is ~2000 cycles of MMAs)
+  static constexpr int NBUF = (512 / BN) > 8 ? 8 : (512 / BN);
+  static constexpr int NBUF_LOG = NBUF == 8 ? 3 : (NBUF == 4 ? 2 : 1);
+  static constexpr int TMEM_COLS = (NBUF * BN < 32) ? 32 : NBUF * BN;
 };
 
 // CS = thread-block cluster size along M: the CS CTAs of a cluster work on CS consecutive M tiles of the same N
@@ -142,6 +150,9 @@ struct Cfg {
 // CTA's (super) tiles; `stage`, `phase`, `it` are the calling thread's pipeline state and persist across calls, so a
 // persistent multi-layer kernel can chain convolutions through the same barriers and TMEM buffers.
 // ---------------------------------------------------------------------------------------------------------------
+template <bool V>
+struct FastTag { static constexpr bool value = V; };
+
 struct PipeState {      // per-thread pipeline state; persists across convolutions of a multi-convolution launch
   int a_stage, b_stage, it;
   uint32_t a_phase, b_phase;
@@ -160,8 +171,8 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
   uint64_t* b_full_ring = bars + 2 * MAX_STAGES;
   uint64_t* b_empty = bars + 3 * MAX_STAGES;
   uint64_t* tmem_full = bars + 4 * MAX_STAGES;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* b_full = tmem_empty + 2;                     // resident weights have landed
+  uint64_t* tmem_empty = tmem_full + 8;
+  uint64_t* b_full = tmem_empty + 8;                     // resident weights have landed
   // everything the role loops need from the parameter block, read once (the asm statements in the loops clobber
   // memory, so anything left in `p` would be re-read from the constant bank / shared memory every iteration)
   const int cin_chunks = p.cin_chunks;
@@ -176,7 +187,8 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
   const int k_steps = p.k_steps;                         // one k-step = one A box
   uint8_t* pipe = smem_hdr + HDR_PAD;                    // 1024-aligned operand area
   uint8_t* a_ring = pipe + (RB ? p.rb_b_bytes : 0);
-  uint8_t* b_ring = a_ring + na * A_SLOT_BYTES;
+  const int a_slot_bytes = (RB && p.rb3) ? 3 * A_SLOT_BYTES : A_SLOT_BYTES;
+  uint8_t* b_ring = a_ring + na * a_slot_bytes;
   int& it = ps.it;
 
   // warp index through a shuffle: tells the compiler it is warp-uniform, so the producer / MMA role loops below run
@@ -273,7 +285,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
             hn_mbar_arrive(&a_full[a_stage]);
           } else {
             hn_mbar_expect_tx(&a_full[a_stage], (uint32_t)a_box_bytes);
-            hn_tma_load_3d(a_ring + a_stage * A_SLOT_BYTES, &tm_a, &a_full[a_stage], cc * BLOCK_K, m0 + shift, info >> 24);
+            hn_tma_load_3d(a_ring + a_stage * a_slot_bytes, &tm_a, &a_full[a_stage], cc * BLOCK_K, m0 + shift, info >> 24);
           }
         }
         if (++a_stage == na) { a_stage = 0; a_phase ^= 1; }
@@ -315,7 +327,10 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
     ps.a_stage = a_stage; ps.b_stage = b_stage; ps.a_phase = a_phase; ps.b_phase = b_phase;
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    // Converged warp; tcgen05.mma / commit are issued by one elected lane.
+    // Converged warp; tcgen05.mma / commit are issued by one elected lane.  (A second issuing warp taking alternate
+    // tiles was tried for the narrow tiles: it needs a ring of two whole tiles to keep the parity waits unambiguous and
+    // bought nothing once the epilogue ran -- layer1 52.2 -> 52.9 us -- so there is one issuer.)
+    long long* const trace_m = trace;
     constexpr uint32_t idesc = hn_umma_idesc_bf16(BN);
     constexpr uint32_t A_SLOT_D = A_SLOT_BYTES >> 4, B_SLOT_D = C::B_STAGE_BYTES >> 4, ROW_D = (BLOCK_K * 2) >> 4;
     int a_stage = ps.a_stage, b_stage = ps.b_stage;
@@ -350,11 +365,11 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
           cc = s_begin - g * cin_chunks;
         }
       }
-      const int buf = it & 1;
+      const int buf = it & (C::NBUF - 1);
       const uint32_t d_tmem = tmem_base + buf * BN;
       int info = p.grp_info[g];
-      if (!(dbg_flags & 32)) hn_mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);   // the epilogue has drained this buffer
-      hn_trace(trace, 1, tri, 4);
+      if (!(dbg_flags & 32)) hn_mbar_wait(&tmem_empty[buf], ((it >> C::NBUF_LOG) & 1) ^ 1);   // the epilogue has drained this buffer
+      hn_trace(trace_m, 1, tri, 4);
       uint32_t accumulate = 0;
       if constexpr (UNI) {
         int units = p.grp_units[g];
@@ -365,7 +380,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
           const uint32_t sa = a_desc0 + a_stage * uni_stage_d, sb = sa + uni_a_d;
           const uint32_t ea = hn_smem_u32(&a_empty[a_stage]), tf = hn_smem_u32(&tmem_full[buf]);
           hn_mbar_wait(&a_full[a_stage], a_phase);
-          hn_trace(trace, 1, tri, 1);
+          hn_trace(trace_m, 1, tri, 1);
           hn_tc_fence_after();
           if (hn_elect_one()) {
             if (p.stem_tpr > 0) {
@@ -393,7 +408,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
             if (last) hn_umma_commit_addr<1>(tf);              // accumulator complete -> epilogue
           }
           accumulate = 1;
-          hn_trace(trace, 1, tri, 3);
+          hn_trace(trace_m, 1, tri, 3);
           if (++a_stage == na) { a_stage = 0; a_phase ^= 1; }
           cc += uni_chunk_step;
           if (cc >= cin_chunks) {
@@ -413,8 +428,29 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
         const uint32_t db_rb_step = ((info >> 16) & 255) * cin_chunks * B_SLOT_D;
         const bool last = step == s_end - 1;
         hn_mbar_wait(&a_full[a_stage], a_phase);
-        hn_trace(trace, 1, tri, 1);
-        if constexpr (STEP_ISSUE) {
+        hn_trace(trace_m, 1, tri, 1);
+        if (RB && p.rb3) {
+          // all nine taps of this chunk from one stage: A tile of kernel row t at slot + t * 17 KiB, tap (t, s) reads it
+          // from row s * dil on; weight tile of tap t*3 + s, chunk cc
+          const uint32_t sa = a_desc0 + a_stage * (3 * A_SLOT_D);
+          const uint32_t sb = b_desc0 + cc * B_SLOT_D, tap_d = cin_chunks * B_SLOT_D;
+          const uint32_t ea = hn_smem_u32(&a_empty[a_stage]), tf = hn_smem_u32(&tmem_full[buf]);
+          hn_tc_fence_after();
+          if (hn_elect_one()) {
+            if (!(dbg_flags & 4)) {
+#pragma unroll
+              for (int t = 0; t < 3; ++t) {
+#pragma unroll
+                for (int sx = 0; sx < 3; ++sx) {
+                  hn_umma_bf16_x4(d_tmem, desc_hi | (sa + t * A_SLOT_D + sx * off_step), desc_hi | (sb + (t * 3 + sx) * tap_d),
+                                  idesc, (t | sx) ? 1u : accumulate);
+                }
+              }
+            }
+            hn_umma_commit_addr<1>(ea);
+            if (last) hn_umma_commit_addr<1>(tf);
+          }
+        } else if constexpr (STEP_ISSUE) {
           // ring slots of the (up to) three weight tiles of this step
           int bs1 = b_stage + 1, bs2 = b_stage + 2;
           uint32_t bp1 = b_phase, bp2 = b_phase;
@@ -457,7 +493,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
           for (int t = 0; t < ntaps; ++t) {
             if constexpr (!RB) {
               hn_mbar_wait(&b_full_ring[b_stage], b_phase);
-              hn_trace(trace, 1, tri, 2);
+              hn_trace(trace_m, 1, tri, 2);
             }
             hn_tc_fence_after();
             const uint32_t db_lo = RB ? db_t : b_desc0 + b_stage * B_SLOT_D;
@@ -480,7 +516,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
           }
         }
         accumulate = 1;
-        hn_trace(trace, 1, tri, 3);
+        hn_trace(trace_m, 1, tri, 3);
         if (++a_stage == na) { a_stage = 0; a_phase ^= 1; }
         if (++cc == cin_chunks) {
           cc = 0;
@@ -512,11 +548,14 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
     const int div_img_sh = p.div_img_sh, div_wp_sh = p.div_wp_sh;
     const int rows = p.rows, wp = p.wp, halo = p.halo;
     int ss_n0[2] = {-1, -1};                    // N tile whose scale/shift each staging buffer holds
+    const bool has_scale = p.scale != nullptr;
+    // bf16 output, cout a multiple of the chunk width (no ragged chunks), 32-byte aligned rows, no split-K
+    const bool epi_fast = p.out_kind == 0 && p.vec32 != 0 && (p.cout % 32) == 0 && splits == 1 && !(p.dbg_flags & 64);
     for (int w_ = first_tile; w_ < num_items; w_ += tile_stride, ++it) {
       const int st = splits > 1 ? w_ / splits : w_;
       if (warp == 2) hn_trace(trace, 2, tri, 1);
-      const int buf = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int buf = it & (C::NBUF - 1);
+      const uint32_t acc_phase = (it >> C::NBUF_LOG) & 1;
       int mt = st, nt = 0;
       if (n_tiles > 1) { mt = st / n_tiles; nt = st - mt * n_tiles; }
       const int m0 = (mt * CS + cta_rank) * BLOCK_M;
@@ -639,6 +678,11 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
         if (finalize) __threadfence();
       }
 
+      // The chunk loop exists twice: FAST for the common case (bf16 output, every chunk complete, 32-byte accesses, no
+      // split-K) carries no per-element predicates; the general copy keeps the ragged / fp32-row / split-K paths.
+      // (Inside one body the compiler if-converts the slow paths into ~400 predicated-off instructions per chunk.)
+      auto run_chunks = [&](auto fast_tag) {
+        constexpr bool FAST = decltype(fast_tag)::value;
 #pragma unroll 1
       for (int c0 = c_first; c0 < ((idle_half || (p.dbg_flags & 2) || !finalize) ? 0 : BN); c0 += STEP) {
         uint32_t res_cur[CHUNK / 2];
@@ -650,7 +694,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
         }
         uint32_t acc[CHUNK];
         const int cbase = n0 + c0;
-        if (split) {
+        if (!FAST && split) {
           if (cbase >= p.cout) continue;
           if constexpr (CHUNK == 32) {
 #pragma unroll
@@ -671,43 +715,62 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
             hn_tmem_ld16(t_row + c0, acc);
           }
           hn_tmem_ld_wait();
-          if (cbase >= p.cout) continue;                 // padded output channels (warp-uniform)
+          if (warp == 2) hn_trace(trace, 2, tri, 4);
+          if (!FAST && cbase >= p.cout) continue;        // padded output channels (warp-uniform)
         }
         float v[CHUNK];
+        {
+          // scale / shift of these columns: broadcast ld.shared (explicit state space: through the generic pointer the
+          // compiler emitted generic loads); layers without a scale vector (bias only) skip the multiply
+          const uint32_t ss_addr = hn_smem_u32(ss + c0);
+          if (has_scale) {
 #pragma unroll
-        for (int j = 0; j < CHUNK; j += 4) {
-          const float4 sc = *reinterpret_cast<const float4*>(ss + c0 + j);          // broadcast LDS
-          const float4 sh = *reinterpret_cast<const float4*>(ss + 256 + c0 + j);
-          v[j + 0] = __uint_as_float(acc[j + 0]) * sc.x + sh.x;
-          v[j + 1] = __uint_as_float(acc[j + 1]) * sc.y + sh.y;
-          v[j + 2] = __uint_as_float(acc[j + 2]) * sc.z + sh.z;
-          v[j + 3] = __uint_as_float(acc[j + 3]) * sc.w + sh.w;
+            for (int j = 0; j < CHUNK; j += 4) {
+              const float4 sc = hn_lds128(ss_addr + j * 4), sh = hn_lds128(ss_addr + 1024 + j * 4);
+              v[j + 0] = __uint_as_float(acc[j + 0]) * sc.x + sh.x;
+              v[j + 1] = __uint_as_float(acc[j + 1]) * sc.y + sh.y;
+              v[j + 2] = __uint_as_float(acc[j + 2]) * sc.z + sh.z;
+              v[j + 3] = __uint_as_float(acc[j + 3]) * sc.w + sh.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CHUNK; j += 4) {
+              const float4 sh = hn_lds128(ss_addr + 1024 + j * 4);
+              v[j + 0] = __uint_as_float(acc[j + 0]) + sh.x;
+              v[j + 1] = __uint_as_float(acc[j + 1]) + sh.y;
+              v[j + 2] = __uint_as_float(acc[j + 2]) + sh.z;
+              v[j + 3] = __uint_as_float(acc[j + 3]) + sh.w;
+            }
+          }
         }
         if (p.res_mode != 0 && interior) {
-          const __nv_bfloat16* rp = p.res + res_off + cbase;
-          if (cbase + CHUNK <= p.cout && vec32) {
+          if (FAST || (cbase + CHUNK <= p.cout && vec32)) {
 #pragma unroll
             for (int j = 0; j < CHUNK; j += 2) {
               v[j] += hn_bf16_lo(res_cur[j / 2]);
               v[j + 1] += hn_bf16_hi(res_cur[j / 2]);
             }
-          } else {
+          } else if constexpr (!FAST) {
+            const __nv_bfloat16* rp = p.res + res_off + cbase;
 #pragma unroll
             for (int j = 0; j < CHUNK; ++j)
               if (cbase + j < p.cout) v[j] += __bfloat162float(rp[j]);
           }
         }
-        if (p.relu_hi > p.relu_lo) {
-          if (cbase >= p.relu_lo && cbase + CHUNK <= p.relu_hi) {
+        if constexpr (CHUNK == 32) {
+          // tiles of >= 32 columns: the ReLU range is chunk-aligned (checked by build_conv): one decision per chunk
+          if (cbase >= p.relu_lo && cbase < p.relu_hi) {
 #pragma unroll
             for (int j = 0; j < CHUNK; ++j) v[j] = fmaxf(v[j], 0.0f);
-          } else {
+          }
+        } else {
+          if (p.relu_hi > p.relu_lo) {
 #pragma unroll
             for (int j = 0; j < CHUNK; ++j)
               if (cbase + j >= p.relu_lo && cbase + j < p.relu_hi) v[j] = fmaxf(v[j], 0.0f);
           }
         }
-        if (p.out_kind == 1) {
+        if (!FAST && p.out_kind == 1) {
           if (interior) {
             float* op = reinterpret_cast<float*>(p.out) + out_off + cbase;
 #pragma unroll
@@ -716,13 +779,15 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
           }
           continue;
         }
+        if (warp == 2) hn_trace(trace, 2, tri, 6);
         // bf16 outputs
         uint32_t packed[CHUNK / 2];
 #pragma unroll
         for (int j = 0; j < CHUNK; j += 2) packed[j / 2] = hn_pack_bf16(v[j], v[j + 1]);
+        if (warp == 2) hn_trace(trace, 2, tri, 7);
         if (interior && !(p.dbg_flags & 1)) {
           __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + cbase;
-          if (cbase + CHUNK <= p.cout && vec32) {
+          if (FAST || (cbase + CHUNK <= p.cout && vec32)) {
             // 32 bytes per lane and instruction: every store fills whole 32-byte sectors (16-byte stores at a 2*cout
             // byte lane stride left every sector half written and doubled the L2 requests)
 #pragma unroll
@@ -732,7 +797,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
 #pragma unroll
               for (int j = 0; j < CHUNK / 2; j += 8) hn_stg256(pp + 2 * j, &packed[j]);
             }
-          } else {
+          } else if constexpr (!FAST) {
 #pragma unroll
             for (int j = 0; j < CHUNK; ++j)
               if (cbase + j < p.cout) {
@@ -742,6 +807,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
               }
           }
         }
+        if (warp == 2) hn_trace(trace, 2, tri, 5);
         if (p.gn_stats) {
           // GroupNorm partial sums over the bf16-rounded values.  Per lane: (sum, sumsq) of the 4 channel octets of
           // this chunk = 8 values; a transposing butterfly (4+2+1+1+1 shuffles) leaves total k in lane 4*k, which
@@ -809,6 +875,9 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
           }
         }
       }
+      };
+      if (epi_fast) run_chunks(FastTag<true>{});
+      else run_chunks(FastTag<false>{});
       // accumulator buffer drained -> hand it back to the MMA warp (split-K items did so after their reduction)
       if (!split) {
         hn_tc_fence_before();
@@ -838,8 +907,8 @@ __device__ __forceinline__ uint32_t conv_prologue(uint8_t* smem_hdr, const CUten
   uint64_t* b_full_ring = bars + 2 * MAX_STAGES;
   uint64_t* b_empty = bars + 3 * MAX_STAGES;
   uint64_t* tmem_full = bars + 4 * MAX_STAGES;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* b_full = tmem_empty + 2;
+  uint64_t* tmem_empty = tmem_full + 8;
+  uint64_t* b_full = tmem_empty + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
   if (threadIdx.x == 0) {
     if (pf_a) hn_tma_prefetch_desc(pf_a);
@@ -851,7 +920,7 @@ __device__ __forceinline__ uint32_t conv_prologue(uint8_t* smem_hdr, const CUten
       hn_mbar_init(&b_empty[s], CS);     // every CTA of the cluster releases the slot (its peers write into it)
     }
     hn_mbar_init(b_full, 1);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 8; ++b) {
       hn_mbar_init(&tmem_full[b], 1);
       hn_mbar_init(&tmem_empty[b], EPI_WARPS);   // one arrive per epilogue warp
     }
@@ -1152,6 +1221,8 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
   bool rb = !force_bn && cs == 1 && p.n_tiles == 1 && bn <= 64 && b_bytes <= PIPE_BYTES_MAX - 4 * A_SLOT_BYTES &&
             p.m_tiles >= 2 * hn_num_sms() && !(d->debug & 16) && !stem;
   const bool uni = bn <= 128 && !rb;      // unified stages (must match the kernel's constexpr UNI)
+  const bool rb3 = rb && d->kh == 3 && d->stride == 1 && !(d->debug & 32) &&
+                   PIPE_BYTES_MAX - b_bytes >= 2 * 3 * A_SLOT_BYTES && p.rows > 2 * d->dilation * p.wp;
 
   // A-box groups.  Pixel (oh*stride + dr, ow*stride + ds) of tap (r, s), dr = (r - kh/2)*dil, ds = (s - kw/2)*dil, is row
   // m + shift of the (phase) matrix; taps of one kernel row whose shifts differ by a few rows share one box.
@@ -1181,7 +1252,13 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
   } else {
     for (int r = 0; r < 3; ++r) {
       const int dr = (r - 1) * d->dilation;
-      if (d->stride == 1) {
+      if (rb3) {
+        if (r == 0) {                               // one group: the box spans the three kernel rows
+          const int taps[3] = {0, 1, 2};
+          const int offs[3] = {0, d->dilation, 2 * d->dilation};
+          add_group(0, dr * p.wp - d->dilation, 3, taps, offs);
+        }
+      } else if (d->stride == 1) {
         const int taps[3] = {r * 3, r * 3 + 1, r * 3 + 2};
         const int offs[3] = {0, d->dilation, 2 * d->dilation};
         add_group(0, dr * p.wp - d->dilation, 3, taps, offs);
@@ -1227,7 +1304,9 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
     p.uni_a_rank4 = p.uni_chunk_step > 1 ? 1 : 0;
   } else if (rb) {
     p.rb_b_bytes = (int)b_bytes;
-    const int slots = (PIPE_BYTES_MAX - p.rb_b_bytes) / A_SLOT_BYTES;
+    p.rb3 = rb3 ? 1 : 0;
+    if (rb3) p.a_box_bytes = 3 * A_SLOT_BYTES;
+    const int slots = (PIPE_BYTES_MAX - p.rb_b_bytes) / (rb3 ? 3 * A_SLOT_BYTES : A_SLOT_BYTES);
     p.na_stages = slots > MAX_STAGES ? MAX_STAGES : slots;
     p.nb_stages = 1;
   } else {
@@ -1240,6 +1319,8 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
   p.shift = d->shift;
   p.relu_lo = d->relu_lo;
   p.relu_hi = d->relu_hi;
+  HN_REQUIRE(bn == 16 || d->relu_hi <= d->relu_lo || (d->relu_lo % 32 == 0 && (d->relu_hi % 32 == 0 || d->relu_hi >= d->cout)),
+             "hn_conv2d_bf16: a ReLU range [%d, %d) that cuts a 32-column chunk needs block_n = 16", d->relu_lo, d->relu_hi);
   p.res = reinterpret_cast<const __nv_bfloat16*>(d->res);
   p.res_mode = d->res ? d->res_mode : 0;
   if (p.res_mode) {
@@ -1352,10 +1433,15 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
     }
   }
   if (!stem && !(uni && p.uni_a_rank4)) {
-    // dims (channels, rows, phases); unified stride-2 3x3: the box spans both column phases of a row phase
-    const cuuint64_t dims[3] = {(cuuint64_t)d->cin, (cuuint64_t)p.rows, (cuuint64_t)d->in_phases};
-    const cuuint64_t strides[2] = {(cuuint64_t)d->cin * 2, (cuuint64_t)p.rows * d->cin * 2};
-    const cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)box_rows, (cuuint32_t)(uni ? a_planes : 1)};
+    // dims (channels, rows, phases); unified stride-2 3x3: the box spans both column phases of a row phase.
+    // rb3: the third dimension steps by one (dilated) image row instead -- an overlapping view of the same matrix;
+    // its row count is cut by two image rows so that row + 2 * wp stays inside the allocation (the rows cut off are the
+    // last image's bottom halo, which only halo outputs of kernel row 0 would read)
+    const cuuint64_t dims[3] = {(cuuint64_t)d->cin, (cuuint64_t)(rb3 ? p.rows - 2 * d->dilation * p.wp : p.rows),
+                                (cuuint64_t)(rb3 ? 3 : d->in_phases)};
+    const cuuint64_t strides[2] = {(cuuint64_t)d->cin * 2,
+                                   rb3 ? (cuuint64_t)d->dilation * p.wp * d->cin * 2 : (cuuint64_t)p.rows * d->cin * 2};
+    const cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)box_rows, (cuuint32_t)(rb3 ? 3 : (uni ? a_planes : 1))};
     int rc = make_map(&ta, d->in, 3, dims, strides, box);
     if (rc) return rc;
   }

@@ -26,7 +26,7 @@ tr = trace.cpu().view(3, 2048, 2)
 t0 = min(int(tr[r, 0, 0]) for r in range(3) if tr[r, 0, 0] > 0)
 ROLE = ("producer", "mma", "epilogue")
 TAGS = ({1: "a_empty ok", 2: "b_empty ok"}, {1: "a_full ok", 2: "b_full ok", 3: "commits issued", 4: "tmem_empty ok", 5: "before a_full wait", 6: "mmas issued"},
-        {1: "tile start", 2: "tmem_full ok", 3: "tile done"})
+        {1: "tile start", 2: "tmem_full ok", 3: "tile done", 4: "tmem ld done", 5: "stored", 6: "math done", 7: "packed"})
 limit = int(os.environ.get("TRACE_N", "60"))
 for r in range(3):
     ev = [(int(a), int(b)) for a, b in tr[r].tolist() if a > 0]
