@@ -85,7 +85,8 @@ struct ConvParams {
   double* gn_stats;
   int gn_groups, gn_group_size;
   int splits;                       // split-K factor (>= 1)
-  float* sk_ws;                     // fp32 partial-sum scratch [m_tiles*128][sk_ld], zero between uses
+  float* sk_ws;                     // fp32 partial tiles [splits][m_tiles*128][sk_ld] (plain stores, summed in split order)
+  long long sk_slice;               // floats per split slice
   unsigned* sk_cnt;                 // arrival counter per (m, n) tile, zero between uses
   int sk_ld;
   uint32_t div_img_mul, div_wp_mul; // x / d == (umulhi(x, mul) + x) >> sh for x < 2^31 (fastdiv())
@@ -639,11 +640,13 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       if (warp == 2) hn_trace(trace, 2, tri, 2);
       const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + buf * BN;
 
-      // Split-K: every work item adds its partial accumulator into an fp32 scratch tile with vector reductions; the
-      // item that arrives last (per-tile counter) reads the sums back, re-zeroes the scratch and runs the epilogue.
+      // Split-K: every work item stores its partial accumulator into its own slice of an fp32 scratch; the item that
+      // arrives last (per-tile counter) adds the slices in split order -- a fixed summation order, so results do not
+      // depend on which CTA finishes first -- and runs the epilogue.
       const bool split = p.splits > 1;
       bool finalize = true;
       float* sk_row = split ? p.sk_ws + (size_t)m * p.sk_ld + n0 : nullptr;
+      const int ks_item = split ? w_ - st * splits : 0;
       if (split) {
         if constexpr (CHUNK == 32) {
 #pragma unroll 1
@@ -653,12 +656,12 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
             hn_tmem_ld32(t_row + c0, acc);
             hn_tmem_ld_wait();
             if (interior) {
+              float* dst = sk_row + (size_t)ks_item * p.sk_slice + c0;
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(sk_row + c0 + j),
-                             "f"(__uint_as_float(acc[j])), "f"(__uint_as_float(acc[j + 1])),
-                             "f"(__uint_as_float(acc[j + 2])), "f"(__uint_as_float(acc[j + 3]))
-                             : "memory");
+                __stcg(reinterpret_cast<float4*>(dst + j),
+                       make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
+                                   __uint_as_float(acc[j + 3])));
             }
           }
         }
@@ -701,8 +704,10 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
             for (int j = 0; j < 32; j += 4) {
               float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
               if (interior) {
-                t = __ldcg(reinterpret_cast<const float4*>(sk_row + c0 + j));
-                __stcg(reinterpret_cast<float4*>(sk_row + c0 + j), make_float4(0.f, 0.f, 0.f, 0.f));
+                for (int sl = 0; sl < splits; ++sl) {          // fixed order: split 0, 1, 2, ...
+                  const float4 u = __ldcg(reinterpret_cast<const float4*>(sk_row + (size_t)sl * p.sk_slice + c0 + j));
+                  t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+                }
               }
               acc[j] = __float_as_uint(t.x); acc[j + 1] = __float_as_uint(t.y);
               acc[j + 2] = __float_as_uint(t.z); acc[j + 3] = __float_as_uint(t.w);
@@ -1121,12 +1126,21 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cu
 }
 
 int pick_block_n(int cout_pad, int m_tiles, int k_blocks, int min_bn) {
-  // Cost model from the measured per-layer table (profiles/): a k-block costs about the same ~800 cycles for every
-  // tile width because the A tile (16 KiB) dominates the L2 -> SM traffic, so wide tiles win unless the extra
-  // waves they leave idle outweigh it.  cost = waves * (k_blocks * kb_cycles + epilogue).
+  // Cost model from measurements of the current kernel (profiles/r01b_*): cycles per 64-channel k-block of one tile.
+  // 256 columns run at the tensor pipe's rate (4 x 128 cycles); narrower tiles are bound by MMA issue / shared-memory
+  // bandwidth (48-64 cycles per MMA) plus ~400 cycles of barrier round trip per k-step of three k-blocks.  Tiles
+  // narrower than 64 columns re-read the activations once per N tile and measured clearly slower on the small A2J
+  // layers (8 crops: 590 us with 64, 731 us with 32, 1141 us with 16), so they are used only when cout_pad < 64.
+  // cost = waves * (k_blocks * kb_cycles + epilogue).
   const int sms = hn_num_sms();
+  static int small_bn = -1;                       // experiment: HN_SMALL_BN pins the tile width of layers with < 148 M tiles
+  if (small_bn < 0) {
+    const char* e = getenv("HN_SMALL_BN");
+    small_bn = e ? atoi(e) : 0;
+  }
+  if (small_bn > 0 && m_tiles < sms && cout_pad % small_bn == 0 && small_bn >= min_bn) return small_bn;
   const int cands[5] = {256, 128, 64, 32, 16};
-  const double kb_cycles[5] = {820.0, 640.0, 560.0, 520.0, 500.0};
+  const double kb_cycles[5] = {530.0, 400.0, 330.0, 420.0, 560.0};
   int best = 0;
   double best_cost = 1e30;
   for (int i = 0; i < 5; ++i) {
@@ -1383,13 +1397,19 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
       }
     }
     if (sp > k_steps) sp = k_steps;
+    // one fp32 slice of the whole (padded) output per split: use as many splits as the caller's scratch holds
+    const long long slice_bytes = (long long)p.m_tiles * BLOCK_M * d->cout_pad * 4;
+    if (d->splits > 0) {
+      HN_REQUIRE(d->splitk_ws_bytes >= sp * slice_bytes, "hn_conv2d_bf16: split-K scratch too small (%lld < %lld bytes)",
+                 (long long)d->splitk_ws_bytes, sp * slice_bytes);
+    } else if (sp * slice_bytes > d->splitk_ws_bytes) {
+      sp = (int)(d->splitk_ws_bytes / slice_bytes);
+    }
     if (sp > 1) {
-      const long long need = (long long)p.m_tiles * BLOCK_M * d->cout_pad * 4;
-      HN_REQUIRE(d->splitk_ws_bytes >= need, "hn_conv2d_bf16: split-K scratch too small (%lld < %lld bytes)",
-                 (long long)d->splitk_ws_bytes, need);
       HN_REQUIRE(d->splitk_counters_len >= tiles, "hn_conv2d_bf16: split-K counter array too small");
       p.splits = sp;
       p.sk_ws = reinterpret_cast<float*>(d->splitk_ws);
+      p.sk_slice = slice_bytes / 4;
       p.sk_cnt = reinterpret_cast<unsigned*>(d->splitk_counters);
       p.sk_ld = d->cout_pad;
     }

@@ -453,8 +453,9 @@ class A2JPlan:
         return self.cache[key]
 
     def splitk(self, key, x, conv: "ConvLayer"):
-        """Split-K scratch (fp32 sums + tile counters, zero between uses) for a convolution reading `x`, or None
-        when the layer has enough tiles on its own.  Exclusive per convolution: members of a group run concurrently."""
+        """Split-K scratch (one fp32 slice of the padded output per K split + zeroed tile counters) for a convolution
+        reading `x`, or None when the layer has enough tiles on its own.  Exclusive per convolution: independent
+        convolutions run concurrently."""
         if not SPLIT_K:
             return None
         hh, ww = (x.h2, x.w2) if isinstance(x, PhaseAct) else (x.h, x.w)
@@ -465,8 +466,10 @@ class A2JPlan:
             return None
         k = "sk_" + key
         if k not in self.cache:
-            self.cache[k] = (torch.zeros(m_tiles * 128 * cout_pad, dtype=torch.float32, device=self.device),
-                             torch.zeros(m_tiles * (cout_pad // 32), dtype=torch.int32, device=self.device))
+            tiles = m_tiles * max(1, cout_pad // 64)
+            slices = max(2, min(16, 148 // tiles))          # the library uses as many K splits as slices fit
+            self.cache[k] = (torch.empty(slices * m_tiles * 128 * cout_pad, dtype=torch.float32, device=self.device),
+                             torch.zeros(m_tiles * (cout_pad // 16), dtype=torch.int32, device=self.device))
         return self.cache[k]
 
 

@@ -102,9 +102,12 @@ typedef struct hn_conv_desc {
   int block_n; /* 0 = choose automatically among 16/32/64/128/256 */
   int cluster; /* 0 = automatic; 1 = no cluster; 2 = CTA pairs along M that multicast the weight tile */
   int debug;   /* 0 in production; bring-up experiments only */
-  /* optional split-K: fp32 scratch of at least ceil(rows/128)*128*cout_pad*4 bytes and one uint32 counter per output
-   * tile, both ZERO on entry and left zero on exit (exclusive to this convolution while it runs).  splits = 0 lets
-   * the library choose (1 = off).  Used for short, deep layers that cannot fill the GPU with tiles. */
+  /* optional split-K for short, deep layers that cannot fill the GPU with tiles: an fp32 scratch holding one slice of
+   * ceil(rows/128)*128*cout_pad*4 bytes per K split (contents irrelevant on entry) and one uint32 counter per output
+   * tile, ZERO on entry and left zero on exit; both exclusive to this convolution while it runs.  Every split stores
+   * its partial tile into its own slice and the last one to arrive adds the slices in split order, so the result does
+   * not depend on the order in which CTAs finish.  splits = 0 lets the library choose, limited to the slices that fit
+   * the scratch (1 = off; an explicit value must fit). */
   void* splitk_ws;
   int64_t splitk_ws_bytes;
   void* splitk_counters;
