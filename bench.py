@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -72,17 +72,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, window=None):
+        """Summary of the samples taken inside `window` = (t0, t1) wall-clock seconds (all samples if None)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if window is None or (window[0] <= t <= window[1] + 0.06)]
+        sm = sorted(int(float(r[0])) for r in rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
@@ -178,7 +180,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -225,15 +227,16 @@ def main():
         torch.cuda.synchronize()
 
     with torch.inference_mode():
+        sampler = ClockSampler(local_rank)            # started early: nvidia-smi needs a moment before its first sample
+        sampler.start()
         for _ in range(args.warmup):
             one_step()
         barrier()
         # ---------------- device-resident throughput (`value`) ----------------
-        sampler = ClockSampler(local_rank)
-        sampler.start()
         launches0 = ops.launch_count()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         barrier()
+        t_wall0 = time.time()
         torch.cuda.nvtx.range_push("hn_timed")
         for s, e in evs:
             l2_flush.zero_()                 # flush L2 between timed iterations (outside the events)
@@ -242,7 +245,7 @@ def main():
             e.record()
         barrier()
         torch.cuda.nvtx.range_pop()
-        clocks = sampler.stop()
+        t_wall1 = time.time()
         launches = (ops.launch_count() - launches0) // args.steps if args.no_graph else step.launches_per_step
         dev_ms = sum(s.elapsed_time(e) for s, e in evs)
         t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
@@ -312,6 +315,14 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_u8_value = world * B * args.steps / (float(t.item()) * 1e-3)
         h2d_u8 = bgr_pin.numel() + mm_pin.numel() * 2
+        t_wall2 = time.time()
+        # clocks / throttle reasons sampled DURING the device-timed region; if that region was too short for two
+        # samples (it lasts steps x ~4 ms), the window is extended over the e2e loops that follow it (same load)
+        clocks = sampler.stop((t_wall0, t_wall1))
+        clocks["window"] = "timed region"
+        if (clocks.get("samples") or 0) < 2:
+            clocks = sampler.stop((t_wall0, t_wall2))
+            clocks["window"] = "timed region + e2e loops"
 
         # ---------------- roofline of the dominant kernel (rank 0) ----------------
         roof = None
