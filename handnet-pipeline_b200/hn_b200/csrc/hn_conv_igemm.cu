@@ -162,7 +162,10 @@ struct PipeState {      // per-thread pipeline state; persists across convolutio
 template <int BN, int CS, bool RB>
 __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CUtensorMap* tm_b_ptr, const ConvParams& p,
                                            uint8_t* smem_hdr, const uint32_t tmem_base, const int first_tile,
-                                           const int tile_stride, PipeState& ps) {
+                                           const int tile_stride, PipeState& ps, const bool pdl = false) {
+  // pdl: launched with programmatic stream serialisation.  Each role executes griddepcontrol.wait itself, as late as
+  // it can: the producer first fetches what does not depend on the previous kernel (the WEIGHTS of its first k-steps,
+  // or the whole resident slice), the MMA warp never touches global memory and does not wait at all.
   using C = Cfg<BN>;
   const CUtensorMap& tm_a = *tm_a_ptr;
   const CUtensorMap& tm_b = *tm_b_ptr;
@@ -223,6 +226,27 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
     constexpr bool UNI = (BN <= 128) && !RB;               // unified stages (see ConvParams)
     const int uni_stage_bytes = p.uni_a_bytes + p.uni_b_bytes, uni_chunk_step = p.uni_chunk_step;
     const int uni_stride = p.uni_stride;
+    int early_b = 0;                                       // leading k-steps of the first item whose weights are on the way
+    if (pdl) {
+      if constexpr (UNI) {
+        if (first_tile < num_items && splits == 1 && !(dbg_flags & 8) && a_stage == 0) {
+          const int nt0 = n_tiles > 1 ? first_tile % n_tiles : 0;
+          early_b = k_steps < na ? k_steps : na;
+          if (hn_elect_one()) {
+            int g0 = 0, cc0 = 0;
+            for (int e = 0; e < early_b; ++e) {
+              hn_mbar_expect_tx(&a_full[e], (uint32_t)uni_stage_bytes);
+              hn_tma_load_4d(a_ring + e * uni_stride + p.uni_a_bytes, &tm_b, &a_full[e], 0, nt0 * BN, cc0,
+                             (p.grp_info[g0] >> 8) & 255);
+              cc0 += uni_chunk_step;
+              if (cc0 >= cin_chunks) { cc0 = 0; ++g0; }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
     for (int w_ = first_tile; w_ < num_items; w_ += tile_stride) {
       int st = w_, s_begin = 0, s_end = k_steps, g = 0, cc = 0;
       if (splits > 1) {                                    // (super) tile and K split of this work item
@@ -259,11 +283,12 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
               hn_mbar_arrive(&a_full[a_stage]);
             } else {
               uint8_t* sa = a_ring + a_stage * uni_stride;
-              hn_mbar_expect_tx(&a_full[a_stage], (uint32_t)uni_stage_bytes);
+              const bool b_pending = w_ == first_tile && step - s_begin < early_b;   // armed and B issued before the wait
+              if (!b_pending) hn_mbar_expect_tx(&a_full[a_stage], (uint32_t)uni_stage_bytes);
               if (p.stem_tpr > 0) hn_tma_load_4d(sa, &tm_a, &a_full[a_stage], 0, st_ox, 2 * (st_oy + cc), st_n);
               else if (p.uni_a_rank4) hn_tma_load_4d(sa, &tm_a, &a_full[a_stage], 0, m0 + shift, cc, info >> 24);
               else hn_tma_load_3d(sa, &tm_a, &a_full[a_stage], cc * BLOCK_K, m0 + shift, info >> 24);
-              hn_tma_load_4d(sa + p.uni_a_bytes, &tm_b, &a_full[a_stage], 0, n0, cc, (info >> 8) & 255);
+              if (!b_pending) hn_tma_load_4d(sa + p.uni_a_bytes, &tm_b, &a_full[a_stage], 0, n0, cc, (info >> 8) & 255);
             }
           }
           if (++a_stage == na) { a_stage = 0; a_phase ^= 1; }
@@ -544,6 +569,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       hn_epi_bar_sync();
     }
     uint32_t* sk_flag = reinterpret_cast<uint32_t*>(b_full + 1) + 1;   // "this CTA finalises the tile" (after tmem_slot)
+    if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");       // before the first global read / write of this role
     if (dbg_flags & 32) return;                   // experiment: no epilogue role at all (the MMA warp does not wait for it)
     const uint32_t div_img_mul = p.div_img_mul, div_wp_mul = p.div_wp_mul;
     const int div_img_sh = p.div_img_sh, div_wp_sh = p.div_wp_sh;
@@ -967,9 +993,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   // while the previous kernel of the stream is still draining; global memory is touched only after the wait.
   // The early trigger lets the next kernel do the same under this one.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
   PipeState ps = {0, 0, 0, 0u, 0u};
-  conv_roles<BN, CS, RB>(&tm_a, &tm_b, p, smem_hdr, tmem_base, blockIdx.x / CS, gridDim.x / CS, ps);
+  conv_roles<BN, CS, RB>(&tm_a, &tm_b, p, smem_hdr, tmem_base, blockIdx.x / CS, gridDim.x / CS, ps, true);
   conv_teardown<BN, CS>(tmem_base);
 }
 
