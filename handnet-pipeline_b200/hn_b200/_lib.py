@@ -84,11 +84,14 @@ def load(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    if build_if_missing and _build.needs_build():
-        _build.build()
-    if not os.path.exists(_build.LIB):
-        raise RuntimeError(f"{_build.LIB} is missing: run `python -m hn_b200.build` (there is no CPU fallback)")
-    lib = C.CDLL(_build.LIB)
+    path = os.environ.get("HN_LIB_AB")          # A/B timing of two builds of the library in one GPU call (tools only)
+    if not path:
+        if build_if_missing and _build.needs_build():
+            _build.build()
+        path = _build.LIB
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: run `python -m hn_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)      # AttributeError here means the header and the library disagree
         fn.restype = res

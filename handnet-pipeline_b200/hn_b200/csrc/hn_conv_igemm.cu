@@ -154,6 +154,12 @@ struct Cfg {
 template <bool V>
 struct FastTag { static constexpr bool value = V; };
 
+template <int N>
+__device__ __forceinline__ void hn_tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[N]) {
+  if constexpr (N == 32) hn_tmem_ld32(taddr, r);
+  else hn_tmem_ld16(taddr, r);
+}
+
 struct PipeState {      // per-thread pipeline state; persists across convolutions of a multi-convolution launch
   int a_stage, b_stage, it;
   uint32_t a_phase, b_phase;
@@ -712,8 +718,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       // (Inside one body the compiler if-converts the slow paths into ~400 predicated-off instructions per chunk.)
       auto run_chunks = [&](auto fast_tag) {
         constexpr bool FAST = decltype(fast_tag)::value;
-#pragma unroll 1
-      for (int c0 = c_first; c0 < ((idle_half || (p.dbg_flags & 2) || !finalize) ? 0 : BN); c0 += STEP) {
+      auto chunk_body = [&](const int c0, uint32_t (&acc)[CHUNK], const bool preloaded) {
         uint32_t res_cur[CHUNK / 2];
 #pragma unroll
         for (int j = 0; j < CHUNK / 2; ++j) res_cur[j] = res_next[j];
@@ -721,10 +726,9 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
 #pragma unroll
           for (int j = 0; j < CHUNK / 16; ++j) hn_ldg256(p.res + res_off + n0 + c0 + STEP + 16 * j, &res_next[8 * j]);
         }
-        uint32_t acc[CHUNK];
         const int cbase = n0 + c0;
         if (!FAST && split) {
-          if (cbase >= p.cout) continue;
+          if (cbase >= p.cout) return;
           if constexpr (CHUNK == 32) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -740,14 +744,16 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
             }
           }
         } else {
-          if constexpr (CHUNK == 32) {
-            hn_tmem_ld32(t_row + c0, acc);
-          } else {
-            hn_tmem_ld16(t_row + c0, acc);
+          if (!preloaded) {
+            if constexpr (CHUNK == 32) {
+              hn_tmem_ld32(t_row + c0, acc);
+            } else {
+              hn_tmem_ld16(t_row + c0, acc);
+            }
+            hn_tmem_ld_wait();
           }
-          hn_tmem_ld_wait();
           if (warp == 2) hn_trace(trace, 2, tri, 4);
-          if (!FAST && cbase >= p.cout) continue;        // padded output channels (warp-uniform)
+          if (!FAST && cbase >= p.cout) return;        // padded output channels (warp-uniform)
         }
         float v[CHUNK];
         {
@@ -808,7 +814,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
             for (int j = 0; j < CHUNK; ++j)
               if (cbase + j < p.cout) op[j] = v[j];
           }
-          continue;
+          return;
         }
         if (warp == 2) hn_trace(trace, 2, tri, 6);
         // bf16 outputs
@@ -904,6 +910,36 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
               }
             }
           }
+        }
+            };
+      const int c_end = (idle_half || (p.dbg_flags & 2) || !finalize) ? 0 : BN;
+      // TMEM loads one chunk ahead (tcgen05.ld of chunk i+1 in flight while chunk i is scaled, packed and stored; two
+      // register sets, loop fully unrolled).  Measured A/B on one box: isolated 256-wide layers gain 5 % (layer3 34.2 ->
+      // 32.4 us) but the whole step loses 2 % (2108 -> 2066 frames/s; 48 bytes of spills at the 168-register cap), so
+      // it is compiled out.
+      constexpr bool TMEM_PREFETCH = false;
+      if constexpr (TMEM_PREFETCH && FAST && CHUNK == 32 && (BN / STEP) >= 2) {
+        if (c_first < c_end) {
+          uint32_t acc_a[CHUNK], acc_b[CHUNK];
+          hn_tmem_ld_chunk<CHUNK>(t_row + c_first, acc_a);
+#pragma unroll
+          for (int i = 0; i < BN / STEP; ++i) {
+            const int c0 = c_first + i * STEP;
+            hn_tmem_ld_wait();
+            if (i & 1) {
+              if (i + 1 < BN / STEP) hn_tmem_ld_chunk<CHUNK>(t_row + c0 + STEP, acc_a);
+              chunk_body(c0, acc_b, true);
+            } else {
+              if (i + 1 < BN / STEP) hn_tmem_ld_chunk<CHUNK>(t_row + c0 + STEP, acc_b);
+              chunk_body(c0, acc_a, true);
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c0 = c_first; c0 < c_end; c0 += STEP) {
+          uint32_t acc[CHUNK];
+          chunk_body(c0, acc, false);
         }
       }
       };
@@ -1189,6 +1225,15 @@ void fastdiv(uint32_t d, uint32_t* mul, int* sh) {
   *sh = l;
 }
 
+int split_min_kb() {            // experiment knob: HN_SPLIT_MIN_KB (k-blocks a layer needs before split-K is considered)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HN_SPLIT_MIN_KB");
+    v = e ? atoi(e) : 48;
+  }
+  return v;
+}
+
 struct BuiltConv {
   ConvParams p;
   CUtensorMap ta, tb;
@@ -1414,7 +1459,7 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
       sp = 1;
       // measured (tools/a2j_timing.py): the reduction + counter round trip + read-back cost ~3-4 us per layer, a
       // k-block ~0.2 us, so only deep layers (>= 48 k-blocks) gain, with at least 12 k-blocks per split
-      if (tiles * 2 <= hn_num_sms() && k_blocks_total >= 48) {
+      if (tiles * 2 <= hn_num_sms() && k_blocks_total >= split_min_kb()) {
         sp = hn_num_sms() / tiles;
         if (sp > k_blocks_total / 12) sp = k_blocks_total / 12;
         if (sp > 16) sp = 16;
