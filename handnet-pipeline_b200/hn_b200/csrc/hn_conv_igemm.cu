@@ -99,7 +99,47 @@ struct ConvParams {
   int vec32;                        // epilogue may use 32-byte global accesses (cout % 16 == 0, 32-byte aligned bases)
   int dbg_flags;                    // bring-up / timing experiments (bit0 no stores, bit1 no epilogue, bit2 no MMA, bit3 no TMA)
   long long* trace;                 // bring-up: CTA 0 logs (clock64, tag) pairs per role, TRACE_EVENTS each
+  const struct ConvDeps* deps;      // multi-convolution launches: tile-level dataflow dependencies (NULL otherwise)
 };
+
+// Dataflow synchronisation between the convolutions of one multi-convolution launch.  Every finished (m, n) output tile
+// of a convolution adds 1 to done[m]; a consumer tile waits until the producer M tiles it reads (its own rows +- one
+// image row for a 3x3, the same rows for a 1x1 or a residual) have all their N tiles.  No grid-wide barrier.
+constexpr int MAX_DEPS = 3;
+struct ConvDeps {
+  unsigned* done;                       // this convolution's counters, one per M tile
+  int n_deps;
+  const unsigned* dep_done[MAX_DEPS];   // producers' counters
+  int dep_need[MAX_DEPS];               // value of a producer counter that means "M tile complete" (its n_tiles)
+  const short* dep_first[MAX_DEPS];     // per M tile of THIS convolution: first / last producer M tile read
+  const short* dep_last[MAX_DEPS];
+};
+
+__device__ __forceinline__ void dep_wait(const ConvDeps* dp, int mt) {
+  if ((threadIdx.x & 31) == 0) {
+    const int nd = dp->n_deps;
+    for (int d = 0; d < nd; ++d) {
+      const int t0 = dp->dep_first[d][mt], t1 = dp->dep_last[d][mt];
+      const unsigned need = (unsigned)dp->dep_need[d];
+      const unsigned* cnt = dp->dep_done[d];
+      for (int t = t0; t <= t1; ++t) {
+        unsigned spins = 0;
+        while (true) {
+          unsigned v;
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt + t) : "memory");
+          if (v >= need) break;
+          if (++spins > (1u << 24)) {
+            printf("hn: dependency wait timed out (block %d, producer tile %d: %u of %u)\n", (int)blockIdx.x, t, v, need);
+            __trap();
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  // the TMA (async proxy) reads that follow must observe what other CTAs wrote with ordinary stores
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
 
 constexpr int TRACE_EVENTS = 2048;
 // role 0 producer, 1 MMA issuer, 2 first epilogue warp; written by lane 0 of CTA 0 only
@@ -193,6 +233,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
   const int cout_pad = p.cout_pad;
   const int dbg_flags = p.dbg_flags;
   long long* const trace = p.trace;
+  const ConvDeps* const deps = p.deps;
   int tri = 0;
   const int k_steps = p.k_steps;                         // one k-step = one A box
   uint8_t* pipe = smem_hdr + HDR_PAD;                    // 1024-aligned operand area
@@ -232,7 +273,8 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
     constexpr bool UNI = (BN <= 128) && !RB;               // unified stages (see ConvParams)
     const int uni_stage_bytes = p.uni_a_bytes + p.uni_b_bytes, uni_chunk_step = p.uni_chunk_step;
     const int uni_stride = p.uni_stride;
-    int early_b = 0;                                       // leading k-steps of the first item whose weights are on the way
+    int early_b = 0;                                       // leading k-steps of an item whose weights are on the way
+    int early_item = first_tile;                           // ... and which item that is
     if (pdl) {
       if constexpr (UNI) {
         if (first_tile < num_items && splits == 1 && !(dbg_flags & 8) && a_stage == 0) {
@@ -274,6 +316,29 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       const int n0 = nt * BN;
       int info = p.grp_info[g], shift = p.grp_shift[g];
       if constexpr (UNI) {
+        if (deps != nullptr && splits == 1 && !(dbg_flags & 8)) {
+          // multi-convolution launch: the weights do not depend on the producer tiles -- arm the first stages and fetch
+          // their weight tiles BEFORE waiting for the dependencies, the activations after
+          early_b = k_steps < na ? k_steps : na;
+          early_item = w_;
+          int es = a_stage, g0 = 0, cc0 = 0;
+          uint32_t eph = a_phase;
+          for (int e = 0; e < early_b; ++e) {
+            hn_mbar_wait(&a_empty[es], eph ^ 1);
+            if (hn_elect_one()) {
+              hn_mbar_expect_tx(&a_full[es], (uint32_t)uni_stage_bytes);
+              hn_tma_load_4d(a_ring + es * uni_stride + p.uni_a_bytes, &tm_b, &a_full[es], 0, n0, cc0,
+                             (p.grp_info[g0] >> 8) & 255);
+            }
+            cc0 += uni_chunk_step;
+            if (cc0 >= cin_chunks) { cc0 = 0; ++g0; }
+            if (++es == na) { es = 0; eph ^= 1; }
+          }
+          __syncwarp();
+        }
+      }
+      if (deps != nullptr) dep_wait(deps, mt);             // multi-convolution launch: the tiles this one reads are done
+      if constexpr (UNI) {
         int st_n = 0, st_oy = 0, st_ox = 0;                  // stem: image, output row, first output column of the tile
         if (p.stem_tpr > 0) {
           const int row = mt / p.stem_tpr;
@@ -289,7 +354,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
               hn_mbar_arrive(&a_full[a_stage]);
             } else {
               uint8_t* sa = a_ring + a_stage * uni_stride;
-              const bool b_pending = w_ == first_tile && step - s_begin < early_b;   // armed and B issued before the wait
+              const bool b_pending = w_ == early_item && step - s_begin < early_b;   // armed and B issued before the wait
               if (!b_pending) hn_mbar_expect_tx(&a_full[a_stage], (uint32_t)uni_stage_bytes);
               if (p.stem_tpr > 0) hn_tma_load_4d(sa, &tm_a, &a_full[a_stage], 0, st_ox, 2 * (st_oy + cc), st_n);
               else if (p.uni_a_rank4) hn_tma_load_4d(sa, &tm_a, &a_full[a_stage], 0, m0 + shift, cc, info >> 24);
@@ -657,7 +722,10 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       constexpr int STEP = (BN / CHUNK >= 2) ? 2 * CHUNK : CHUNK;   // two warps interleave chunks when there are >= 2
       const int c_first = (BN / CHUNK >= 2) ? half * CHUNK : 0;
       const bool idle_half = (BN / CHUNK < 2) && half == 1;         // a single chunk: the second warp only arrives
-      if (res_vec && !idle_half && n0 + c_first + CHUNK <= p.cout) {
+      // (in a multi-convolution launch the residual may still be in the making: its dependency is awaited by the
+      // producer warp, which the accumulator wait below orders before us -- so no early fetch there)
+      const bool res_first = res_vec && !idle_half && n0 + c_first + CHUNK <= p.cout;
+      if (res_first && deps == nullptr) {
 #pragma unroll
         for (int j = 0; j < CHUNK / 16; ++j) hn_ldg256(p.res + res_off + n0 + c_first + 16 * j, &res_next[8 * j]);
       }
@@ -669,6 +737,10 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
         hn_mbar_wait(&tmem_full[buf], acc_phase);
       }
       hn_tc_fence_after();
+      if (res_first && deps != nullptr) {
+#pragma unroll
+        for (int j = 0; j < CHUNK / 16; ++j) hn_ldg256(p.res + res_off + n0 + c_first + 16 * j, &res_next[8 * j]);
+      }
       if (warp == 2) hn_trace(trace, 2, tri, 2);
       const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + buf * BN;
 
@@ -951,6 +1023,11 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
         __syncwarp();
         if (lane == 0) hn_mbar_arrive(&tmem_empty[buf]);
       }
+      if (deps != nullptr && finalize) {                  // this (m, n) output tile is in global memory: tell the consumers
+        __threadfence();
+        hn_epi_bar_sync();
+        if (threadIdx.x == 64) atomicAdd(deps->done + mt, 1u);
+      }
       if (warp == 2) hn_trace(trace, 2, tri, 3);
     }
     if (gn_smem) {
@@ -1036,9 +1113,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 
 // ---------------------------------------------------------------------------------------------------------------
 // Several dependent convolutions in ONE launch (the 67 tiny convolutions of the A2J pose net cost ~10 us of fixed
-// latency each as separate launches).  `phases` lists the convolutions, `group_begin` partitions them into groups
-// whose members are independent; a grid-wide barrier separates consecutive groups.  Launched cooperatively so that
-// all CTAs are resident.
+// latency each as separate launches).  `phases` lists the convolutions in a dependency-consistent order; tiles
+// synchronise by dataflow (ConvDeps): hn_conv_multi_build finds, from the buffer pointers, which earlier convolution
+// writes each input / residual and which of its M tiles every tile reads.  Launched cooperatively so that all CTAs are
+// resident (a waiting tile's producers must be able to run).
 // ---------------------------------------------------------------------------------------------------------------
 struct PhaseDesc {
   CUtensorMap ta;
@@ -1046,52 +1124,49 @@ struct PhaseDesc {
   ConvParams p;
 };
 
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
-  __threadfence();                     // this thread's global writes are visible device-wide ...
-  __syncthreads();                     // ... for every thread of the CTA
-  if (threadIdx.x == 0) {
-    atomicAdd(counter, 1u);
-    unsigned spins = 0;
-    while (true) {
-      unsigned v;
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-      if (v >= target) break;
-      if (++spins > (1u << 26)) {
-        printf("hn: grid barrier timed out (block %d, %u of %u)\n", (int)blockIdx.x, v, target);
-        __trap();
-      }
-    }
-    __threadfence();
-  }
-  __syncthreads();
-  // later TMA (async proxy) reads must observe what other CTAs wrote with ordinary stores before the barrier
-  asm volatile("fence.proxy.async;" ::: "memory");
-}
-
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_multi_kernel(const PhaseDesc* __restrict__ phases, const int* __restrict__ group_begin, int num_groups,
-                  unsigned* __restrict__ counter, long long* __restrict__ group_clock) {
+conv_multi_kernel(const PhaseDesc* __restrict__ phases, int n_convs, long long* __restrict__ conv_clock) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ ConvParams sp;
   uint8_t* smem_hdr = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t tmem_base = conv_prologue<BN, 1>(smem_hdr, nullptr, nullptr);
   PipeState ps = {0, 0, 0, 0u, 0u};
-  for (int g = 0; g < num_groups; ++g) {
-    int tile_off = 0;                                    // tiles of the group's convs are dealt round-robin
-    for (int j = group_begin[g]; j < group_begin[g + 1]; ++j) {
-      __syncthreads();                                   // everyone is done with the previous sp
-      for (int i = threadIdx.x; i < (int)(sizeof(ConvParams) / 4); i += blockDim.x)
-        reinterpret_cast<uint32_t*>(&sp)[i] = reinterpret_cast<const uint32_t*>(&phases[j].p)[i];
-      __syncthreads();
-      const int tiles = sp.m_tiles * sp.n_tiles * sp.splits;
-      int first = ((int)blockIdx.x - tile_off) % (int)gridDim.x;
-      if (first < 0) first += gridDim.x;
-      conv_roles<BN, 1, false>(&phases[j].ta, &phases[j].tb, sp, smem_hdr, tmem_base, first, gridDim.x, ps);
-      tile_off = (tile_off + tiles) % (int)gridDim.x;
+  // Every role walks the convolutions in order, straight from the plan in global memory: no block-wide or grid-wide
+  // barrier between convolutions.  The producer warp of a tile waits for the producer tiles it reads (ConvDeps), the
+  // epilogue announces finished tiles; the roles of one CTA may be in different convolutions at the same time.
+  // Each role keeps its own copy of the current convolution's parameters in shared memory (the GroupNorm accumulator
+  // area, unused here): read straight from the plan in global memory, the per-step parameter reads of the role loops
+  // miss the small L1 and cost an L2 round trip each.
+  static_assert(3 * sizeof(ConvParams) <= GN_SMEM_FLOATS * 4, "role parameter slots do not fit");
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int role = warp < 2 ? warp : 2;
+  ConvParams* slot = reinterpret_cast<ConvParams*>(smem_hdr + HDR_BARS) + role;
+  int tile_off = 0;                                      // tiles are dealt round-robin over the CTAs, continuing across convs
+  for (int j = 0; j < n_convs; ++j) {
+    {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(&phases[j].p);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(slot);
+      constexpr int WORDS = (int)(sizeof(ConvParams) / 4);
+      if (role == 2) {
+        hn_epi_bar_sync();                               // every epilogue warp is done with the previous convolution
+        for (int i = threadIdx.x - 64; i < WORDS; i += EPI_THREADS) dst[i] = __ldg(src + i);
+        hn_epi_bar_sync();
+      } else {
+        for (int i = threadIdx.x & 31; i < WORDS; i += 32) dst[i] = __ldg(src + i);
+        __syncwarp();
+      }
     }
-    if (g + 1 < num_groups) grid_barrier(counter, (unsigned)(g + 1) * gridDim.x);
-    if (group_clock != nullptr && blockIdx.x == 0 && threadIdx.x == 0) group_clock[g] = clock64();   // bring-up only
+    if (role == 0 && (threadIdx.x & 31) == 0 && j + 1 < n_convs) {   // descriptors of the next convolution -> descriptor cache
+      hn_tma_prefetch_desc(&phases[j + 1].ta);
+      hn_tma_prefetch_desc(&phases[j + 1].tb);
+    }
+    const ConvParams& cp = *slot;
+    const int tiles = cp.m_tiles * cp.n_tiles * cp.splits;
+    int first = ((int)blockIdx.x - tile_off) % (int)gridDim.x;
+    if (first < 0) first += gridDim.x;
+    conv_roles<BN, 1, false>(&phases[j].ta, &phases[j].tb, cp, smem_hdr, tmem_base, first, gridDim.x, ps);
+    tile_off = (tile_off + tiles) % (int)gridDim.x;
+    if (conv_clock != nullptr && blockIdx.x == 0 && threadIdx.x == 64) conv_clock[j] = clock64();   // bring-up only
   }
   conv_teardown<BN, 1>(tmem_base);
 }
@@ -1562,12 +1637,43 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
 
 constexpr int MULTI_BN = 64;
 
-struct MultiPlanHeader {        // device layout: [header][group_begin ints][PhaseDesc array]
-  unsigned counter;
-  int n_convs, n_groups, grid;
+// device layout of a plan: [counters: n_convs x MULTI_MAX_MT uint32][PhaseDesc array][ConvDeps array][dep tables]
+constexpr int MULTI_MAX_MT = 1024;      // M tiles per convolution (the pose net's largest layer has 133)
+size_t multi_phases_off(int n_convs) { return (((size_t)n_convs * MULTI_MAX_MT * 4 + 255) / 256) * 256; }
+size_t multi_deps_off(int n_convs) { return multi_phases_off(n_convs) + (((size_t)n_convs * sizeof(PhaseDesc) + 255) / 256) * 256; }
+size_t multi_tabs_off(int n_convs) { return multi_deps_off(n_convs) + (((size_t)n_convs * sizeof(ConvDeps) + 255) / 256) * 256; }
+size_t multi_total(int n_convs) { return multi_tabs_off(n_convs) + (size_t)n_convs * MAX_DEPS * 2 * MULTI_MAX_MT * sizeof(short) + 256; }
+
+// Which producer M tiles does M tile `mt` of a consumer read?  `rows_lo..rows_hi` = the consumer's rows (in the geometry
+// of the buffer `geo` describes) that the tile touches; the answer is conservative (whole image rows).
+struct BufGeo {        // a haloed NHWC buffer as a consumer sees it, or the phase-split copy (phases = 4)
+  int n, hp, wp, halo, phases;
 };
-size_t multi_groups_off() { return 256; }
-size_t multi_phases_off(int n_groups) { return 256 + (((size_t)(n_groups + 1) * 4 + 255) / 256) * 256; }
+void producer_tile_range(const BufGeo& g, long long rows_lo, long long rows_hi, const ConvParams& prod, int* t_first,
+                         int* t_last) {
+  const long long img_rows = (long long)g.hp * g.wp, total = (long long)g.n * img_rows;
+  *t_first = 1;
+  *t_last = 0;                                         // empty by default
+  if (rows_lo < 0) rows_lo = 0;
+  if (rows_hi >= total) rows_hi = total - 1;
+  if (rows_lo > rows_hi) return;
+  const int H = g.hp - 2 * g.halo;                     // interior size of the consumer's view
+  const int img_lo = (int)(rows_lo / img_rows), img_hi = (int)(rows_hi / img_rows);
+  int h_lo = (int)((rows_lo - img_lo * img_rows) / g.wp) - g.halo, h_hi = (int)((rows_hi - img_hi * img_rows) / g.wp) - g.halo;
+  if (h_lo < 0) h_lo = 0;
+  if (h_hi > H - 1) h_hi = H - 1;
+  // pixel rows of the producer's OUTPUT grid: the same grid, or twice as fine when the consumer reads the phase split
+  const int ph = prod.hp - 2 * prod.halo, pw = prod.wp - 2 * prod.halo;      // producer output size (= its compute grid)
+  int y_lo = g.phases == 4 ? 2 * h_lo : h_lo, y_hi = g.phases == 4 ? 2 * h_hi + 1 : h_hi;
+  if (y_hi > ph - 1) y_hi = ph - 1;
+  if (img_lo == img_hi && y_lo > y_hi) return;         // only halo rows
+  if (y_lo > ph - 1) y_lo = ph - 1;
+  const long long p_img = (long long)prod.hp * prod.wp;
+  const long long m_lo = img_lo * p_img + (long long)(y_lo + prod.halo) * prod.wp + prod.halo;
+  const long long m_hi = img_hi * p_img + (long long)(y_hi + prod.halo) * prod.wp + prod.halo + pw - 1;
+  *t_first = (int)(m_lo / BLOCK_M);
+  *t_last = (int)(m_hi / BLOCK_M);
+}
 
 }  // namespace
 
@@ -1612,7 +1718,8 @@ extern "C" int hn_conv_multi_set_trace(void* buf) {
 }
 
 extern "C" int64_t hn_conv_multi_plan_bytes(int n_convs, int n_groups) {
-  return (int64_t)(multi_phases_off(n_groups) + (size_t)n_convs * sizeof(PhaseDesc) + 256);
+  (void)n_groups;
+  return (int64_t)multi_total(n_convs);
 }
 
 extern "C" int hn_conv_multi_build(const hn_conv_desc* descs, int n_convs, const int* group_begin_host, int n_groups,
@@ -1621,13 +1728,18 @@ extern "C" int hn_conv_multi_build(const hn_conv_desc* descs, int n_convs, const
   HN_REQUIRE(plan_bytes >= hn_conv_multi_plan_bytes(n_convs, n_groups), "hn_conv_multi_build: plan buffer too small");
   HN_REQUIRE((reinterpret_cast<uintptr_t>(plan_dev) & 255) == 0, "hn_conv_multi_build: plan buffer must be 256-byte aligned");
   HN_REQUIRE(group_begin_host[0] == 0 && group_begin_host[n_groups] == n_convs, "hn_conv_multi_build: group table");
-  std::vector<uint8_t> host((size_t)hn_conv_multi_plan_bytes(n_convs, n_groups), 0);
-  MultiPlanHeader* hdr = reinterpret_cast<MultiPlanHeader*>(host.data());
-  int* groups = reinterpret_cast<int*>(host.data() + multi_groups_off());
-  PhaseDesc* ph = reinterpret_cast<PhaseDesc*>(host.data() + multi_phases_off(n_groups));
+  std::vector<uint8_t> host(multi_total(n_convs), 0);
+  uint8_t* dev = reinterpret_cast<uint8_t*>(plan_dev);
+  PhaseDesc* ph = reinterpret_cast<PhaseDesc*>(host.data() + multi_phases_off(n_convs));
+  ConvDeps* deps = reinterpret_cast<ConvDeps*>(host.data() + multi_deps_off(n_convs));
+  short* tabs = reinterpret_cast<short*>(host.data() + multi_tabs_off(n_convs));
+  auto dev_cnt = [&](int j) { return reinterpret_cast<unsigned*>(dev) + (size_t)j * MULTI_MAX_MT; };
+  auto dev_tab = [&](int j, int d, int which) {
+    return reinterpret_cast<short*>(dev + multi_tabs_off(n_convs)) + ((size_t)(j * MAX_DEPS + d) * 2 + which) * MULTI_MAX_MT;
+  };
+  auto host_tab = [&](int j, int d, int which) { return tabs + ((size_t)(j * MAX_DEPS + d) * 2 + which) * MULTI_MAX_MT; };
   int max_group_tiles = 1;
   for (int g = 0; g < n_groups; ++g) {
-    groups[g] = group_begin_host[g];
     HN_REQUIRE(group_begin_host[g + 1] > group_begin_host[g], "hn_conv_multi_build: empty group %d", g);
     int tiles = 0;
     for (int j = group_begin_host[g]; j < group_begin_host[g + 1]; ++j) {
@@ -1636,24 +1748,64 @@ extern "C" int hn_conv_multi_build(const hn_conv_desc* descs, int n_convs, const
       BuiltConv b;
       int rc = build_conv(&descs[j], MULTI_BN, &b);
       if (rc) return rc;
+      HN_REQUIRE(b.p.m_tiles <= MULTI_MAX_MT, "hn_conv_multi_build: conv %d has %d M tiles (max %d)", j, b.p.m_tiles, MULTI_MAX_MT);
       ph[j].ta = b.ta;
       ph[j].tb = b.tb;
       ph[j].p = b.p;
+      ph[j].p.deps = reinterpret_cast<const ConvDeps*>(dev + multi_deps_off(n_convs)) + j;
       tiles += b.p.m_tiles * b.p.n_tiles * b.p.splits;
     }
     if (tiles > max_group_tiles) max_group_tiles = tiles;
   }
-  groups[n_groups] = n_convs;
-  hdr->n_convs = n_convs;
-  hdr->n_groups = n_groups;
-  hdr->grid = max_group_tiles < hn_num_sms() ? max_group_tiles : hn_num_sms();
+  // dependencies from the buffer pointers: the latest earlier convolution that writes this one's input / residual
+  for (int j = 0; j < n_convs; ++j) {
+    const hn_conv_desc& dj = descs[j];
+    const ConvParams& pj = ph[j].p;
+    ConvDeps& dd = deps[j];
+    dd.done = dev_cnt(j);
+    dd.n_deps = 0;
+    const int reach = dj.kh == 3 ? dj.dilation * pj.wp + dj.dilation : 0;     // rows a tile reads beyond its own
+    struct In { const void* ptr; BufGeo geo; int reach; };
+    In ins[2] = {{dj.in, {dj.n, pj.hp, pj.wp, pj.halo, dj.in_phases}, reach},
+                 {dj.res, {dj.n, pj.res_hp, pj.res_wp, pj.res_halo, 1}, 0}};
+    for (int k = 0; k < 2; ++k) {
+      if (!ins[k].ptr) continue;
+      int prod = -1, via_phase = 0;
+      for (int i = j - 1; i >= 0 && prod < 0; --i) {
+        if (descs[i].out == ins[k].ptr && descs[i].out_kind == 0) prod = i;
+        else if (descs[i].out_phase && descs[i].out_phase == ins[k].ptr) { prod = i; via_phase = 1; }
+      }
+      if (prod < 0) continue;                          // written before this launch
+      HN_REQUIRE((ins[k].geo.phases == 4) == (via_phase == 1), "hn_conv_multi_build: conv %d reads conv %d's %s buffer as %s",
+                 j, prod, via_phase ? "phase-split" : "plain", ins[k].geo.phases == 4 ? "phase-split" : "plain");
+      HN_REQUIRE(dd.n_deps < MAX_DEPS, "hn_conv_multi_build: too many dependencies");
+      const int d = dd.n_deps++;
+      dd.dep_done[d] = dev_cnt(prod);
+      dd.dep_need[d] = ph[prod].p.n_tiles;
+      dd.dep_first[d] = dev_tab(j, d, 0);
+      dd.dep_last[d] = dev_tab(j, d, 1);
+      short* tf = host_tab(j, d, 0);
+      short* tl = host_tab(j, d, 1);
+      for (int mt = 0; mt < pj.m_tiles; ++mt) {
+        // consumer rows of this tile; the residual is indexed by OUTPUT pixel = compute row of the consumer, which maps
+        // to the residual buffer's own geometry through the pixel (for k = 1 use the compute geometry to find pixels)
+        long long lo = (long long)mt * BLOCK_M - ins[k].reach, hi = (long long)mt * BLOCK_M + BLOCK_M - 1 + ins[k].reach;
+        BufGeo geo = ins[k].geo;
+        if (k == 1) geo = {dj.n, pj.hp, pj.wp, pj.halo, 1};   // rows of the consumer's compute grid -> pixels
+        int a = 1, b2 = 0;
+        producer_tile_range(geo, lo, hi, ph[prod].p, &a, &b2);
+        tf[mt] = (short)a;
+        tl[mt] = (short)b2;
+      }
+    }
+  }
+  const int grid = max_group_tiles < hn_num_sms() ? max_group_tiles : hn_num_sms();
   HN_CHECK_CUDA(cudaMemcpy(plan_dev, host.data(), host.size(), cudaMemcpyHostToDevice));
-  return hdr->grid;     // > 0: number of CTAs hn_conv_multi_run will launch
+  return grid;     // > 0: number of CTAs hn_conv_multi_run will launch
 }
 
 extern "C" int hn_conv_multi_run(void* plan_dev, int n_convs, int n_groups, int grid, void* stream) {
   HN_REQUIRE(plan_dev && n_convs > 0 && n_groups > 0 && grid > 0 && grid <= hn_num_sms(), "hn_conv_multi_run: bad arguments");
-  using C = Cfg<MULTI_BN>;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static bool attr_set = false;
   if (!attr_set) {
@@ -1662,7 +1814,7 @@ extern "C" int hn_conv_multi_run(void* plan_dev, int n_convs, int n_groups, int 
     attr_set = true;
   }
   uint8_t* base = reinterpret_cast<uint8_t*>(plan_dev);
-  HN_CHECK_CUDA(cudaMemsetAsync(base, 0, 4, st));            // the barrier counter
+  HN_CHECK_CUDA(cudaMemsetAsync(base, 0, (size_t)n_convs * MULTI_MAX_MT * 4, st));   // the tile completion counters
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
@@ -1670,14 +1822,12 @@ extern "C" int hn_conv_multi_run(void* plan_dev, int n_convs, int n_groups, int 
   cfg.dynamicSmemBytes = SMEM_BYTES_ALL;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;              // all CTAs resident: the grid barrier cannot deadlock
+  attr[0].id = cudaLaunchAttributeCooperative;              // all CTAs resident: a waiting tile's producers can always run
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const PhaseDesc* phases = reinterpret_cast<const PhaseDesc*>(base + multi_phases_off(n_groups));
-  const int* groups = reinterpret_cast<const int*>(base + multi_groups_off());
-  unsigned* counter = reinterpret_cast<unsigned*>(base);
-  HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_multi_kernel<MULTI_BN>, phases, groups, n_groups, counter, g_multi_trace));
+  const PhaseDesc* phases = reinterpret_cast<const PhaseDesc*>(base + multi_phases_off(n_convs));
+  HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_multi_kernel<MULTI_BN>, phases, n_convs, g_multi_trace));
   hn_count_launch();
   return HN_OK;
 }

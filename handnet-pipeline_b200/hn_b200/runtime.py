@@ -68,8 +68,9 @@ def mark(name: str):
 
 _side_streams: Dict[str, List["torch.cuda.Stream"]] = {}
 SPLIT_K = True              # split-K (fp32 scratch + last-arriver epilogue) for the short, deep A2J layers
-A2J_MULTI = False           # True: the A2J convolutions as ONE cooperative multi-convolution launch (measured slower than
-                            # per-layer launches with the three towers on forked graph branches: 721 vs 630 us for 8 crops)
+A2J_MULTI = False           # True: the A2J convolutions as ONE cooperative launch with tile-level dataflow synchronisation
+                            # (hn_conv_multi_*).  Measured slower than per-layer launches with programmatic dependent launch
+                            # and the three towers on forked graph branches: 697 vs 594 us for 8 crops
 PARALLEL_CHAINS = True      # independent layer chains (head towers, A2J towers) on forked streams / graph branches
 
 

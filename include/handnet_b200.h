@@ -125,13 +125,16 @@ typedef struct hn_conv_desc {
 } hn_conv_desc;
 int hn_conv2d_bf16(const hn_conv_desc* desc, void* stream);
 
-/* Several dependent convolutions in ONE cooperative launch (used for the A2J pose net, whose 67 tiny convolutions
- * cost ~10 us of fixed latency each as separate launches).  descs[group_begin[g] .. group_begin[g+1]) are mutually
- * independent; a grid-wide barrier separates consecutive groups.  All convolutions use 64-wide N tiles (cout_pad a
- * multiple of 64), no GroupNorm statistics.  hn_conv_multi_build validates the descriptors, encodes the tensor maps
- * and uploads the plan into plan_dev (256-byte aligned device memory of hn_conv_multi_plan_bytes bytes) with a
- * synchronous copy -- call it once per buffer set, outside stream capture; it returns the grid size (> 0) or a
- * negative status.  hn_conv_multi_run only enqueues a 4-byte memset and the launch. */
+/* Several dependent convolutions in ONE cooperative launch (an alternative to one launch per convolution for the A2J
+ * pose net).  descs[] lists the convolutions in a dependency-consistent order.  hn_conv_multi_build validates the
+ * descriptors, encodes the tensor maps, works out from the buffer pointers which earlier convolution of the list writes
+ * each input / residual and which of its 128-row tiles every tile reads, and uploads the plan into plan_dev (256-byte
+ * aligned device memory of hn_conv_multi_plan_bytes bytes) with a synchronous copy -- call it once per buffer set,
+ * outside stream capture; it returns the grid size (> 0) or a negative status.  In the launch, tiles synchronise by
+ * dataflow: a finished output tile bumps a counter, a consumer tile's loads wait for the producer tiles they read; there
+ * is no grid-wide barrier, and group_begin[] (groups of mutually independent convolutions) only sizes the grid.  All
+ * convolutions use 64-wide N tiles (cout_pad a multiple of 64), no GroupNorm statistics, at most 1024 row tiles each.
+ * hn_conv_multi_run enqueues a memset of the tile counters and the launch. */
 int64_t hn_conv_multi_plan_bytes(int n_convs, int n_groups);
 int hn_conv_multi_build(const hn_conv_desc* descs, int n_convs, const int* group_begin_host, int n_groups,
                         void* plan_dev, int64_t plan_bytes);

@@ -255,8 +255,8 @@ def test_fcos_1080p_canvas_config5():
 
 
 def test_a2j_multi_conv_kernel_equals_per_layer_launches(golden):
-    """The cooperative multi-convolution launch (67 convs, grid barriers between dependent groups) must produce
-    the same head tensors as one launch per convolution."""
+    """The cooperative multi-convolution launch (67 convs, tile-level dataflow synchronisation) must produce the same
+    head tensors as one launch per convolution."""
     from a2j.a2j import A2JModel
     from hn_b200 import runtime
     sd = synth.a2j_state_dict(seed=1)

@@ -5,6 +5,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "handnet-pipelin
 import torch
 from a2j.a2j import A2JModel
 from hn_b200 import runtime, synth, ops, _lib
+runtime.A2J_MULTI = True
 
 sd = synth.a2j_state_dict(seed=1)
 x = (torch.rand(8, 1, 176, 176) * 1.5).cuda()
