@@ -14,13 +14,14 @@ struct PreParams {
   const float* img[PRE_MAX_IMAGES];
   int in_h[PRE_MAX_IMAGES], in_w[PRE_MAX_IMAGES], out_h[PRE_MAX_IMAGES], out_w[PRE_MAX_IMAGES];
   float mean[3], inv_unused[3], stdv[3];
+  float scale_y[PRE_MAX_IMAGES], scale_x[PRE_MAX_IMAGES];   // in / out as fp32, per image
   int canvas_h, canvas_w, batch_offset;
   int pad_top, pad_left, pitch_h, pitch_w;   // the canvas sits at (pad_top, pad_left) of a [pitch_h][pitch_w] pixel frame
 };
 
-__device__ __forceinline__ void bilinear_axis(int o, int in, int out, int& i0, int& i1, float& l0, float& l1) {
-  // ATen area_pixel_compute_source_index(align_corners=false): scale = in/out in fp32, src clamped at 0
-  const float scale = (float)in / (float)out;
+__device__ __forceinline__ void bilinear_axis(int o, int in, float scale, int& i0, int& i1, float& l0, float& l1) {
+  // ATen area_pixel_compute_source_index(align_corners=false): scale = in/out in fp32 (computed once per image on the
+  // host, same IEEE division), src clamped at 0
   float src = scale * ((float)o + 0.5f) - 0.5f;
   if (src < 0.f) src = 0.f;
   i0 = (int)src;
@@ -30,33 +31,55 @@ __device__ __forceinline__ void bilinear_axis(int o, int in, int out, int& i0, i
   l0 = 1.f - l1;
 }
 
+// One thread = four consecutive canvas pixels of one row (the row interpolation is shared, one 32-byte store).
 __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p, uint2* __restrict__ canvas) {
   const int b = blockIdx.z;
   const int y = blockIdx.y;
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= p.canvas_w) return;
-  uint2 outv = make_uint2(0u, 0u);
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (x4 >= p.canvas_w) return;
   const int oh = p.out_h[b], ow = p.out_w[b];
-  if (y < oh && x < ow) {
-    const int ih = p.in_h[b], iw = p.in_w[b];
-    int y0, y1, x0, x1;
-    float ly0, ly1, lx0, lx1;
-    bilinear_axis(y, ih, oh, y0, y1, ly0, ly1);
-    bilinear_axis(x, iw, ow, x0, x1, lx0, lx1);
-    float v[3];
-    const size_t o00 = (size_t)y0 * iw + x0, o01 = (size_t)y0 * iw + x1, o10 = (size_t)y1 * iw + x0, o11 = (size_t)y1 * iw + x1;
+  uint2 outv[4];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float* pl = p.img[b] + (size_t)c * ih * iw;
-      // the bilinear weights sum to one, so normalising after the interpolation equals torchvision's
-      // normalise-then-resize up to fp32 rounding (the result is rounded to bf16 anyway): 1 division instead of 4
-      const float t = ly0 * (lx0 * __ldg(pl + o00) + lx1 * __ldg(pl + o01)) + ly1 * (lx0 * __ldg(pl + o10) + lx1 * __ldg(pl + o11));
-      v[c] = (t - p.mean[c]) / p.stdv[c];
+  for (int j = 0; j < 4; ++j) outv[j] = make_uint2(0u, 0u);
+  if (y < oh && x4 < ow) {
+    const int ih = p.in_h[b], iw = p.in_w[b];
+    int y0, y1;
+    float ly0, ly1;
+    bilinear_axis(y, ih, p.scale_y[b], y0, y1, ly0, ly1);
+    const float* r0 = p.img[b] + (size_t)y0 * iw;
+    const float* r1 = p.img[b] + (size_t)y1 * iw;
+    const size_t plane = (size_t)ih * iw;
+    const float inv_unused = 0.f;
+    (void)inv_unused;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int x = x4 + j;
+      if (x < ow) {
+        int x0, x1;
+        float lx0, lx1;
+        bilinear_axis(x, iw, p.scale_x[b], x0, x1, lx0, lx1);
+        float v[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float* q0 = r0 + c * plane;
+          const float* q1 = r1 + c * plane;
+          // the bilinear weights sum to one, so normalising after the interpolation equals torchvision's
+          // normalise-then-resize up to fp32 rounding (the result is rounded to bf16 anyway): 1 division instead of 4
+          const float t = ly0 * (lx0 * __ldg(q0 + x0) + lx1 * __ldg(q0 + x1)) + ly1 * (lx0 * __ldg(q1 + x0) + lx1 * __ldg(q1 + x1));
+          v[c] = (t - p.mean[c]) / p.stdv[c];
+        }
+        outv[j].x = hn_pack_bf16(v[0], v[1]);
+        outv[j].y = hn_pack_bf16(v[2], 0.f);
+      }
     }
-    outv.x = hn_pack_bf16(v[0], v[1]);
-    outv.y = hn_pack_bf16(v[2], 0.f);
   }
-  canvas[((size_t)(p.batch_offset + b) * p.pitch_h + y + p.pad_top) * p.pitch_w + x + p.pad_left] = outv;
+  uint2* dst = canvas + ((size_t)(p.batch_offset + b) * p.pitch_h + y + p.pad_top) * p.pitch_w + x4 + p.pad_left;
+  if (x4 + 4 <= p.canvas_w && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+    const uint32_t w8[8] = {outv[0].x, outv[0].y, outv[1].x, outv[1].y, outv[2].x, outv[2].y, outv[3].x, outv[3].y};
+    hn_stg256(dst, w8);
+  } else {
+    for (int j = 0; j < 4 && x4 + j < p.canvas_w; ++j) dst[j] = outv[j];
+  }
 }
 
 // ------------------------------------------------------------------------------------- im2col
@@ -221,6 +244,8 @@ extern "C" int hn_preprocess_resize_pad_framed(const float* const* images_host, 
       p.in_w[i] = in_w_host[b0 + i];
       p.out_h[i] = out_h_host[b0 + i];
       p.out_w[i] = out_w_host[b0 + i];
+      p.scale_y[i] = (float)p.in_h[i] / (float)p.out_h[i];
+      p.scale_x[i] = (float)p.in_w[i] / (float)p.out_w[i];
     }
     for (int c = 0; c < 3; ++c) {
       p.mean[c] = mean3_host[c];
@@ -233,7 +258,7 @@ extern "C" int hn_preprocess_resize_pad_framed(const float* const* images_host, 
     p.pitch_h = pitch_h;
     p.pitch_w = pitch_w;
     p.batch_offset = b0;
-    dim3 grid(hn_div_up(canvas_w, 256), canvas_h, nb);
+    dim3 grid(hn_div_up(hn_div_up(canvas_w, 4), 256), canvas_h, nb);
     preprocess_kernel<<<grid, 256, 0, st>>>(p, reinterpret_cast<uint2*>(canvas_bf16));
     hn_count_launch();
     HN_LAUNCH_CHECK();
