@@ -55,6 +55,8 @@ def bn_affine(weight, bias, mean, var, eps=BN_EPS, conv_bias=None):
     return scale.contiguous(), shift.contiguous()
 
 
+PLAN_SLOT = 0               # buffer set in use: steps that are in flight at the same time (GraphedHandNet(slot=...)) must not
+                            # share activation buffers
 PHASES = None               # set to a list to collect (name, CUDA event) marks of a step (tools/phase_timing.py)
 
 
@@ -238,7 +240,7 @@ class FCOSExecutor:
         return self.wts
 
     def plan(self, batch, canvas_hw, device) -> FCOSPlan:
-        key = (batch, canvas_hw, str(device))
+        key = (batch, canvas_hw, str(device), PLAN_SLOT)
         if key not in self.plans:
             self.plans[key] = FCOSPlan(self.wts, batch, canvas_hw, device, self.model.anchor_sizes)
         return self.plans[key]
@@ -495,7 +497,7 @@ class A2JExecutor:
         """x: fp32 [n, 1, H, W] on the device -> (cls, reg, dep) fp32 head tensors in the reference layout."""
         w = self.weights()
         n, _, h, wd = x.shape
-        key = (n, h, wd, str(x.device))
+        key = (n, h, wd, str(x.device), PLAN_SLOT)
         if key not in self.plans:
             self.plans[key] = A2JPlan(w, n, (h, wd), x.device, self.model.num_joints)
         pl = self.plans[key]
@@ -638,8 +640,9 @@ class GraphedHandNet:
     """HandNet.forward_device over fixed (batch, H, W) input buffers, captured once as a CUDA graph and replayed:
     a step is ~180 kernel launches, so replaying removes the host launch path from the critical path."""
 
-    def __init__(self, net, batch: int, h: int, w: int, depth_c: int = 1, use_graph: bool = True):
+    def __init__(self, net, batch: int, h: int, w: int, depth_c: int = 1, use_graph: bool = True, slot: int = 0):
         self.net = net
+        self.slot = slot            # buffer set: give concurrent steps (one per stream) different slots
         dev = next(net.parameters()).device
         self.batch = batch
         self.rgb = torch.zeros((batch, 3, h, w), dtype=torch.float32, device=dev)
@@ -659,7 +662,12 @@ class GraphedHandNet:
         self.depth.copy_(depth, non_blocking=True)
 
     def _eager(self):
-        out = self.net.forward_device(self.images, self.depth)
+        global PLAN_SLOT
+        saved, PLAN_SLOT = PLAN_SLOT, self.slot
+        try:
+            out = self.net.forward_device(self.images, self.depth)
+        finally:
+            PLAN_SLOT = saved
         self.out = out
         self.rec = pack_records(out["joints"], out["crops"], out["has_hand"])
         return out
