@@ -100,8 +100,6 @@ struct ConvParams {
   int dbg_flags;                    // bring-up / timing experiments (bit0 no stores, bit1 no epilogue, bit2 no MMA, bit3 no TMA)
   long long* trace;                 // bring-up: CTA 0 logs (clock64, tag) pairs per role, TRACE_EVENTS each
   const struct ConvDeps* deps;      // multi-convolution launches: tile-level dataflow dependencies (NULL otherwise)
-  unsigned* sched_ctr;              // dynamic tile scheduling: [0] next work item, [1] CTAs that have finished; both zero
-                                    // between launches (NULL: static round-robin assignment)
 };
 
 // Dataflow synchronisation between the convolutions of one multi-convolution launch.  Every finished (m, n) output tile
@@ -205,10 +203,7 @@ __device__ __forceinline__ void hn_tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[N
 struct PipeState {      // per-thread pipeline state; persists across convolutions of a multi-convolution launch
   int a_stage, b_stage, it;
   uint32_t a_phase, b_phase;
-  int s_slot;            // dynamic tile scheduler: position in the CTA's ring of announced work items
-  uint32_t s_phase;
 };
-constexpr int SCHED_SLOTS = 4;
 
 template <int BN, int CS, bool RB>
 __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CUtensorMap* tm_b_ptr, const ConvParams& p,
@@ -228,14 +223,6 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
   uint64_t* tmem_full = bars + 4 * MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 8;
   uint64_t* b_full = tmem_empty + 8;                     // resident weights have landed
-  // Dynamic tile scheduling (p.sched_ctr): the producer warp draws work items from a global counter and announces them
-  // to the MMA and epilogue warps through a small ring (item index or -1 = no more work).  A CTA that starts late --
-  // its SM was busy with a kernel of another stream -- then simply takes fewer tiles instead of delaying the launch.
-  uint64_t* sched_full = b_full + 2;                     // (b_full + 1 holds the TMEM slot and the split-K flag)
-  uint64_t* sched_empty = sched_full + SCHED_SLOTS;
-  volatile int* sched_val = reinterpret_cast<volatile int*>(sched_empty + SCHED_SLOTS);
-  unsigned* const sched_ctr = p.sched_ctr;
-  const bool dyn = sched_ctr != nullptr;
   // everything the role loops need from the parameter block, read once (the asm statements in the loops clobber
   // memory, so anything left in `p` would be re-read from the constant bank / shared memory every iteration)
   const int cin_chunks = p.cin_chunks;
@@ -287,18 +274,11 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
     const int uni_stage_bytes = p.uni_a_bytes + p.uni_b_bytes, uni_chunk_step = p.uni_chunk_step;
     const int uni_stride = p.uni_stride;
     int early_b = 0;                                       // leading k-steps of an item whose weights are on the way
-    // first work item: drawn from the global counter (dynamic) or this CTA's first tile (static)
-    int s_slot = ps.s_slot;
-    uint32_t s_phase = ps.s_phase;
-    int raw = first_tile;
-    const int first_item = first_tile;
-    int early_item = first_item;                           // ... and which item that is
+    int early_item = first_tile;                           // ... and which item that is
     if (pdl) {
       if constexpr (UNI) {
-        // (static assignment only: with the dynamic scheduler the first item is not known before the wait -- its counter
-        // may still belong to a previous launch of the same convolution)
-        if (!dyn && first_item < num_items && splits == 1 && !(dbg_flags & 8) && a_stage == 0) {
-          const int nt0 = n_tiles > 1 ? first_item % n_tiles : 0;
+        if (first_tile < num_items && splits == 1 && !(dbg_flags & 8) && a_stage == 0) {
+          const int nt0 = n_tiles > 1 ? first_tile % n_tiles : 0;
           early_b = k_steps < na ? k_steps : na;
           if (hn_elect_one()) {
             int g0 = 0, cc0 = 0;
@@ -315,25 +295,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       }
       asm volatile("griddepcontrol.wait;" ::: "memory");
     }
-    if (dyn && lane == 0) raw = (int)atomicAdd(sched_ctr, 1u);   // first work item from the global counter
-    while (true) {
-      if (dyn) raw = __shfl_sync(0xffffffffu, raw, 0);     // (lane 0 drew it)
-      const int w_ = raw < num_items ? raw : -1;
-      if (dyn) {                                           // announce the item (or the end) to the MMA and epilogue warps
-        hn_mbar_wait(&sched_empty[s_slot], s_phase ^ 1);
-        if (hn_elect_one()) {
-          sched_val[s_slot] = w_;
-          hn_mbar_arrive(&sched_full[s_slot]);
-        }
-        if (++s_slot == SCHED_SLOTS) { s_slot = 0; s_phase ^= 1; }
-      }
-      if (w_ < 0) break;
-      // the next item: the atomic is issued now, its result is needed only after this item's loads have been issued
-      if (dyn) {
-        if (lane == 0) raw = (int)atomicAdd(sched_ctr, 1u);
-      } else {
-        raw = w_ + tile_stride;
-      }
+    for (int w_ = first_tile; w_ < num_items; w_ += tile_stride) {
       int st = w_, s_begin = 0, s_end = k_steps, g = 0, cc = 0;
       if (splits > 1) {                                    // (super) tile and K split of this work item
         st = w_ / splits;
@@ -460,16 +422,6 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       }
     }
     ps.a_stage = a_stage; ps.b_stage = b_stage; ps.a_phase = a_phase; ps.b_phase = b_phase;
-    ps.s_slot = s_slot; ps.s_phase = s_phase;
-    if (dyn && lane == 0) {
-      // the last CTA to run out of work puts the counters back to zero for the next launch
-      const unsigned done = atomicAdd(sched_ctr + 1, 1u);
-      if (done == gridDim.x - 1) {
-        sched_ctr[0] = 0u;
-        sched_ctr[1] = 0u;
-        __threadfence();
-      }
-    }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     // Converged warp; tcgen05.mma / commit are issued by one elected lane.  (A second issuing warp taking alternate
@@ -496,19 +448,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
     const uint32_t uni_stage_d = (uint32_t)p.uni_stride >> 4, uni_a_d = (uint32_t)p.uni_a_bytes >> 4;
     const uint32_t uni_plane_d = (uint32_t)p.uni_plane_bytes >> 4;
     const int uni_chunk_step = p.uni_chunk_step;
-    int s_slot = ps.s_slot;
-    uint32_t s_phase = ps.s_phase;
-    for (int w_ = first_tile;; w_ += tile_stride, ++it) {
-      if (dyn) {                                             // the producer warp announces the work items
-        hn_mbar_wait(&sched_full[s_slot], s_phase);
-        w_ = sched_val[s_slot];
-        __syncwarp();
-        if (hn_elect_one()) hn_mbar_arrive(&sched_empty[s_slot]);
-        if (++s_slot == SCHED_SLOTS) { s_slot = 0; s_phase ^= 1; }
-        if (w_ < 0) break;
-      } else if (w_ >= num_items) {
-        break;
-      }
+    for (int w_ = first_tile; w_ < num_items; w_ += tile_stride, ++it) {
       int s_begin = 0, s_end = k_steps, g = 0, cc = 0;
       if (splits > 1) {
         const int ks = w_ % splits;                          // K split of this work item
@@ -682,7 +622,6 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
         }
       }
     }
-    ps.s_slot = s_slot; ps.s_phase = s_phase;
     ps.a_stage = a_stage; ps.b_stage = b_stage; ps.a_phase = a_phase; ps.b_phase = b_phase;
   } else {
     // ===================================== epilogue ==========================================
@@ -710,19 +649,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
     const bool has_scale = p.scale != nullptr;
     // bf16 output, cout a multiple of the chunk width (no ragged chunks), 32-byte aligned rows, no split-K
     const bool epi_fast = p.out_kind == 0 && p.vec32 != 0 && (p.cout % 32) == 0 && splits == 1 && !(p.dbg_flags & 64);
-    int s_slot = ps.s_slot;
-    uint32_t s_phase = ps.s_phase;
-    for (int w_ = first_tile;; w_ += tile_stride, ++it) {
-      if (dyn) {
-        hn_mbar_wait(&sched_full[s_slot], s_phase);
-        w_ = sched_val[s_slot];
-        __syncwarp();
-        if (lane == 0) hn_mbar_arrive(&sched_empty[s_slot]);   // one arrival per epilogue warp
-        if (++s_slot == SCHED_SLOTS) { s_slot = 0; s_phase ^= 1; }
-        if (w_ < 0) break;
-      } else if (w_ >= num_items) {
-        break;
-      }
+    for (int w_ = first_tile; w_ < num_items; w_ += tile_stride, ++it) {
       const int st = splits > 1 ? w_ / splits : w_;
       if (warp == 2) hn_trace(trace, 2, tri, 1);
       const int buf = it & (C::NBUF - 1);
@@ -1103,7 +1030,6 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       }
       if (warp == 2) hn_trace(trace, 2, tri, 3);
     }
-    ps.s_slot = s_slot; ps.s_phase = s_phase;
     if (gn_smem) {
       hn_epi_bar_sync();
       for (int i = threadIdx.x - 64; i < gn_vals; i += EPI_THREADS) {
@@ -1138,10 +1064,6 @@ __device__ __forceinline__ uint32_t conv_prologue(uint8_t* smem_hdr, const CUten
       hn_mbar_init(&b_empty[s], CS);     // every CTA of the cluster releases the slot (its peers write into it)
     }
     hn_mbar_init(b_full, 1);
-    for (int s = 0; s < SCHED_SLOTS; ++s) {
-      hn_mbar_init(&b_full[2 + s], 1);                              // sched_full: the producer warp announces an item
-      hn_mbar_init(&b_full[2 + SCHED_SLOTS + s], 1 + EPI_WARPS);    // sched_empty: MMA warp + every epilogue warp have read it
-    }
     for (int b = 0; b < 8; ++b) {
       hn_mbar_init(&tmem_full[b], 1);
       hn_mbar_init(&tmem_empty[b], EPI_WARPS);   // one arrive per epilogue warp
@@ -1184,7 +1106,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   // while the previous kernel of the stream is still draining; global memory is touched only after the wait.
   // The early trigger lets the next kernel do the same under this one.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  PipeState ps = {0, 0, 0, 0u, 0u, 0, 0u};
+  PipeState ps = {0, 0, 0, 0u, 0u};
   conv_roles<BN, CS, RB>(&tm_a, &tm_b, p, smem_hdr, tmem_base, blockIdx.x / CS, gridDim.x / CS, ps, true);
   conv_teardown<BN, CS>(tmem_base);
 }
@@ -1208,7 +1130,7 @@ conv_multi_kernel(const PhaseDesc* __restrict__ phases, int n_convs, long long* 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem_hdr = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t tmem_base = conv_prologue<BN, 1>(smem_hdr, nullptr, nullptr);
-  PipeState ps = {0, 0, 0, 0u, 0u, 0, 0u};
+  PipeState ps = {0, 0, 0, 0u, 0u};
   // Every role walks the convolutions in order, straight from the plan in global memory: no block-wide or grid-wide
   // barrier between convolutions.  The producer warp of a tile waits for the producer tiles it reads (ConvDeps), the
   // epilogue announces finished tiles; the roles of one CTA may be in different convolutions at the same time.
@@ -1590,7 +1512,6 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
   }
   p.vec32 = (d->cout % 16 == 0) && (reinterpret_cast<uintptr_t>(d->out) % 32 == 0) &&
             (reinterpret_cast<uintptr_t>(d->res) % 32 == 0) && (reinterpret_cast<uintptr_t>(d->out_phase) % 32 == 0);
-  p.sched_ctr = (cs == 1 && !force_bn) ? reinterpret_cast<unsigned*>(d->sched_counters) : nullptr;
   p.trace = reinterpret_cast<long long*>(d->trace);
   p.dbg_flags = (d->debug >> 6) & 255;     // bit0: no epilogue stores, bit1: no epilogue work at all (timing experiments)
   p.gn_stats = d->gn_stats;

@@ -20,31 +20,6 @@ RECORD = None       # set to a list to RECORD conv2d calls (descriptor + keep-al
                     # None entries are group boundaries (see MultiConv)
 
 
-DYNAMIC_TILES = __import__('os').environ.get('HN_DYNAMIC_TILES', '0') == '1'
-# True: persistent conv CTAs draw their tiles from a per-launch counter (hn_conv_desc.sched_counters) instead of a fixed
-# round-robin share.  Measured A/B on one box: 4 % SLOWER (2027 -> 1945 frames/s; the atomic + ring hand-off per tile costs
-# more than late-starting CTAs of concurrent launches lose), so it is off by default.
-_sched_pool = {}            # device -> [tensor of uint32 pairs, next free pair, {key: pointer}]
-
-
-def _sched_slot(in_ptr: int, out_ptr: int, w_ptr: int) -> int:
-    """Two zeroed uint32 that belong to ONE convolution of the schedule (keyed by its buffers, which are static per
-    plan): concurrent launches must not share them, and every launch leaves them zero for its next replay."""
-    dev = torch.cuda.current_device()
-    pool = _sched_pool.get(dev)
-    if pool is None:
-        pool = _sched_pool[dev] = [torch.zeros(2 * 16384, dtype=torch.int32, device=f"cuda:{dev}"), 0, {}]
-    key = (in_ptr, out_ptr, w_ptr)
-    ptr_ = pool[2].get(key)
-    if ptr_ is None:
-        if pool[1] >= 16384:
-            raise RuntimeError("hn_b200.ops: out of tile-scheduler counter slots")
-        ptr_ = pool[0].data_ptr() + pool[1] * 8
-        pool[1] += 1
-        pool[2][key] = ptr_
-    return ptr_
-
-
 def record_barrier():
     """Group boundary between dependent convolutions while recording a MultiConv plan (no-op otherwise)."""
     if RECORD is not None and RECORD and RECORD[-1] is not None:
@@ -348,8 +323,6 @@ def conv2d(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 1, d
     d.block_n = block_n
     d.cluster = cluster
     d.debug = debug or _ENV_DEBUG
-    if DYNAMIC_TILES and RECORD is None:
-        d.sched_counters = _sched_slot(d.in_, d.out, weight.data_ptr())
     if trace is not None:
         assert trace.dtype == torch.int64 and trace.numel() >= 3 * 2048 * 2
         d.trace = trace.data_ptr()

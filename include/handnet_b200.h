@@ -122,11 +122,6 @@ typedef struct hn_conv_desc {
    * the weights are pack_stem_weight's K = 8 kernel rows x 8 pixels x 4 channels (k-block major like every weight).
    * TMA gathers the patch rows straight from the canvas with an overlapping-stride tensor map. */
   int stem_pitch_h, stem_pitch_w;
-  /* Optional dynamic tile scheduling: two uint32 in device memory, ZERO on entry and left zero on exit, exclusive to
-   * this launch while it runs.  The persistent CTAs then draw their tiles from a counter instead of a fixed round-robin
-   * share, so a CTA whose SM is still busy with a kernel of another stream takes fewer tiles instead of delaying the
-   * launch.  NULL = static assignment.  Ignored with cluster = 2. */
-  void* sched_counters;
 } hn_conv_desc;
 int hn_conv2d_bf16(const hn_conv_desc* desc, void* stream);
 

@@ -264,36 +264,6 @@ def test_stem_fp32_depth_one_channel(ops):
     close_bf16(out.to_nchw().cpu(), ref, "a2j stem")
 
 
-@pytest.mark.parametrize("case", [c for c in CASES if c[0] in ("3x3_256_256_auto", "3x3_64_64_bn64", "1x1_512_2048_auto",
-                                                                "rb_3x3_64_64_layer1", "3x3_s2_odd_128_256")],
-                         ids=lambda c: c[0])
-def test_conv_dynamic_tile_scheduler(ops, case):
-    """hn_conv_desc.sched_counters: tiles drawn from a global counter give the same result as the static assignment, on
-    repeated launches (the last CTA leaves the counters zero)."""
-    _, n, h, w, cin, cout, k, stride, dil, halo, bn = case[:11]
-    g = torch.Generator().manual_seed(77)
-    x = rand(g, n, cin, h, w).to(DEV)
-    wt = rand(g, cout, cin, k, k, scale=(cin * k * k) ** -0.5).to(DEV)
-    wp = ops.pack_conv_weight(wt)
-    oh, ow = ((h + 1) // 2, (w + 1) // 2) if stride == 2 else (h, w)
-    xin = ops.PhaseAct.from_nchw(x, 1) if stride == 2 else ops.Act.from_nchw(x, halo)
-    outs = []
-    saved = ops.DYNAMIC_TILES
-    try:
-        for dyn in (False, True, True, True):
-            ops.DYNAMIC_TILES = dyn
-            out = ops.Act(n, oh, ow, cout, 1, DEV)
-            ops.conv2d(xin, wp, cout=cout, ksize=k, stride=stride, dilation=dil, relu=True, out=out, block_n=bn)
-            torch.cuda.synchronize()
-            outs.append(out.t.clone())
-    finally:
-        ops.DYNAMIC_TILES = saved
-    for o in outs[1:]:
-        assert torch.equal(o, outs[0])
-    pool = ops._sched_pool[torch.cuda.current_device()]
-    assert int(pool[0].abs().sum()) == 0, "the scheduler counters must be left zero"
-
-
 @pytest.mark.parametrize("shape", [(8, 11, 11, 2048, 256, 3, 0), (8, 11, 11, 1024, 256, 1, 4), (3, 22, 22, 128, 128, 3, 3),
                                    (8, 11, 11, 256, 336, 3, 0)])
 def test_conv_split_k(ops, shape):
