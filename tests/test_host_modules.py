@@ -116,3 +116,28 @@ def test_resized_size_matches_oracle():
         assert resized_size(h, w, 800, 1333) == fcos_oracle.resized_size(h, w, 800, 1333)
     assert resized_size(480, 640, 800, 1333) == (800, 1066)
     assert resized_size(1080, 1920, 800, 1333) == (749, 1333)
+
+
+def test_weight_tiling_round_trip_and_layout():
+    """ops.tile_k: [cout_pad, K] -> k-block-major [K/64][cout_pad][64] (what hn_conv2d_bf16 streams), and back."""
+    from hn_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(48, 32 * 6, generator=g).to(torch.bfloat16)             # K = 192 = 3 k-blocks
+    t = ops.tile_k(w)
+    assert t.shape == w.shape and t.is_contiguous()
+    assert torch.equal(ops.untile_k(t), w)
+    blocks = t.view(3, 48, 64)
+    for kb in range(3):
+        assert torch.equal(blocks[kb], w[:, kb * 64:(kb + 1) * 64])
+    # pack_conv_weight: tap-major K (k = (r*kw + s)*cin + c), zero rows beyond cout, then tiled
+    wt = torch.randn(5, 64, 3, 3, generator=g)
+    p = ops.pack_conv_weight(wt)
+    assert p.shape == (16, 9 * 64) and p.dtype == torch.bfloat16
+    flat = ops.untile_k(p)
+    assert torch.equal(flat[:5], wt.permute(0, 2, 3, 1).reshape(5, -1).to(torch.bfloat16)) and flat[5:].abs().sum() == 0
+    # stem weights: K = 8 kernel rows x 8 pixels x 4 channels, px = 0 / r = 7 / ch = 3 are zero
+    ws = torch.randn(64, 3, 7, 7, generator=g)
+    s = ops.untile_k(ops.pack_stem_weight(ws, 256)).view(64, 8, 8, 4)
+    assert s[:, 7].abs().sum() == 0 and s[:, :, 0].abs().sum() == 0 and s[..., 3].abs().sum() == 0
+    assert torch.equal(s[:, :7, 1:, :3], ws.permute(0, 2, 3, 1).to(torch.bfloat16))
+    assert ops.stem_frame_hw((800, 1088)) == (806, 1096)
