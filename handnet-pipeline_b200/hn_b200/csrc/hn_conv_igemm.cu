@@ -647,8 +647,10 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
     const int rows = p.rows, wp = p.wp, halo = p.halo;
     int ss_n0[2] = {-1, -1};                    // N tile whose scale/shift each staging buffer holds
     const bool has_scale = p.scale != nullptr;
-    // bf16 output, cout a multiple of the chunk width (no ragged chunks), 32-byte aligned rows, no split-K
-    const bool epi_fast = p.out_kind == 0 && p.vec32 != 0 && (p.cout % 32) == 0 && splits == 1 && !(p.dbg_flags & 64);
+    // bf16 output, cout a multiple of the chunk width (no ragged chunks) and no padded N tile (the FAST body does not
+    // skip chunks beyond cout: with cout_pad > cout they would land on the next pixel), 32-byte aligned rows, no split-K
+    const bool epi_fast = p.out_kind == 0 && p.vec32 != 0 && (p.cout % 32) == 0 && p.cout_pad == p.cout && splits == 1 &&
+                          !(p.dbg_flags & 64);
     for (int w_ = first_tile; w_ < num_items; w_ += tile_stride, ++it) {
       const int st = splits > 1 ? w_ / splits : w_;
       if (warp == 2) hn_trace(trace, 2, tri, 1);
@@ -706,6 +708,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       constexpr int CHUNK = (BN >= 32) ? 32 : 16;
       float* ss = ss_base + (it & 1) * 512;   // [0,256) scale, [256,512) shift for columns n0 .. n0+BN
       if (ss_n0[it & 1] != n0) {              // (uniform over the epilogue warps) staged once per N tile, not per tile
+        hn_epi_bar_sync();                      // a slower warp may still read this buffer for the tile before last
         for (int i = threadIdx.x - 64; i < BN; i += EPI_THREADS) {
           const int c = n0 + i;
           ss[i] = (p.scale && c < p.cout) ? __ldg(p.scale + c) : 1.0f;

@@ -50,6 +50,10 @@ CASES = [
     ("3x3_64_32_bn32", 1, 12, 20, 64, 32, 3, 1, 1, 1, 32),
     ("3x3_256_5_bn16", 2, 25, 34, 256, 5, 3, 1, 1, 1, 16),
     ("3x3_256_336_pad", 2, 11, 11, 256, 336, 3, 1, 1, 1, 0),
+    # cout a multiple of 32 but cout_pad > cout: a wholly padded N tile must not be stored (found by tools/conv_fuzz.py)
+    ("3x3_256_96_bn32_padded_tile", 2, 30, 43, 256, 96, 3, 1, 1, 1, 32),
+    ("3x3_256_96_bn16_padded_tile", 2, 30, 43, 256, 96, 3, 1, 1, 1, 16),
+    ("3x3_256_160_auto_padded_tile", 2, 30, 43, 256, 160, 3, 1, 1, 1, 0),
     ("3x3_s2_64_128", 2, 20, 28, 64, 128, 3, 2, 1, 1, 0),
     ("3x3_s2_odd_128_256", 2, 25, 33, 128, 256, 3, 2, 1, 1, 0),
     ("1x1_s2_256_512", 2, 22, 22, 256, 512, 1, 2, 1, 1, 0),
