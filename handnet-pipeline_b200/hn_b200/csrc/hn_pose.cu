@@ -101,6 +101,7 @@ __device__ __forceinline__ void merge(Partial& a, const Partial& b) {
 }
 
 constexpr int AGG_MAX_THREADS = 512;
+constexpr int AGG_SPLITS = 16;          // anchor ranges per crop (workspace is sized for this many)
 
 __global__ void __launch_bounds__(AGG_MAX_THREADS)
 a2j_partial_kernel(const float* __restrict__ cls, const float2* __restrict__ reg, const float* __restrict__ dep,
@@ -114,20 +115,37 @@ a2j_partial_kernel(const float* __restrict__ cls, const float2* __restrict__ reg
   const int j = t % joints, r = t / joints;
   Partial p = {-INFINITY, 0.f, 0.f, 0.f, 0.f};
   if (r < rows_per_iter) {
+    // four anchors per round: their 16 loads are in flight together, one running-max rescale per round
+    constexpr int U = 4;
     const size_t base = (size_t)n * anchors * joints;
-    for (int a = a_begin + r; a < a_end; a += rows_per_iter) {
-      const size_t e = base + (size_t)a * joints + j;
-      const float c = __ldg(cls + e);
-      const float2 rg = __ldg(reg + e);
-      const float d = __ldg(dep + e);
-      const float2 an = __ldg(anchor_xy + a);
-      const float m = fmaxf(p.m, c);
+    for (int a0 = a_begin + r; a0 < a_end; a0 += U * rows_per_iter) {
+      float c[U], d[U];
+      float2 rg[U], an[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int a = a0 + u * rows_per_iter;
+        const bool ok = a < a_end;
+        const size_t e = base + (size_t)(ok ? a : a0) * joints + j;
+        c[u] = __ldg(cls + e);
+        rg[u] = __ldg(reg + e);
+        d[u] = __ldg(dep + e);
+        an[u] = __ldg(anchor_xy + (ok ? a : a0));
+        if (!ok) c[u] = -INFINITY;
+      }
+      float m = p.m;
+#pragma unroll
+      for (int u = 0; u < U; ++u) m = fmaxf(m, c[u]);
+      if (m == -INFINITY) continue;               // only -inf logits so far: nothing to add
       const float f = (p.m == -INFINITY) ? 0.f : expf(p.m - m);
-      const float w = expf(c - m);
-      p.s = p.s * f + w;
-      p.x = p.x * f + w * (an.x + rg.x);
-      p.y = p.y * f + w * (an.y + rg.y);
-      p.d = p.d * f + w * d;
+      p.s *= f; p.x *= f; p.y *= f; p.d *= f;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float w = expf(c[u] - m);           // 0 for the padded slots
+        p.s += w;
+        p.x += w * (an[u].x + rg[u].x);
+        p.y += w * (an[u].y + rg[u].y);
+        p.d += w * d[u];
+      }
       p.m = m;
     }
   }
@@ -140,19 +158,113 @@ a2j_partial_kernel(const float* __restrict__ cls, const float2* __restrict__ reg
   }
 }
 
+// Vectorised variant for the shipped head shape (anchors * joints a multiple of 4, 16-byte aligned tensors): the block
+// streams the flat [anchors * joints] rows with 16-byte loads.  With T = rows_per_round * joints / 4 threads a round
+// covers rows_per_round whole anchors (rows_per_round a multiple of 4), so thread t keeps the same four joints
+// (4t + k) % joints in every round and carries four online-softmax states.  grid (splits, n); a split = a range of rounds.
+template <int U, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+a2j_partial_vec_kernel(const float4* __restrict__ cls, const float4* __restrict__ reg, const float4* __restrict__ dep,
+                       const float2* __restrict__ anchor_xy, int anchors, int joints, int rows_per_round,
+                       Partial* __restrict__ part) {
+  extern __shared__ Partial sh[];                // [4 * T] then reused for the merge tree
+  const int n = blockIdx.y, split = blockIdx.x, splits = gridDim.x;
+  const int T = blockDim.x, t = threadIdx.x;
+  const int rounds = (anchors + rows_per_round - 1) / rows_per_round;
+  const int r_begin = (int)((long long)rounds * split / splits), r_end = (int)((long long)rounds * (split + 1) / splits);
+  const int row_vecs = anchors * joints / 4;     // float4 per crop in cls / dep (reg has twice as many)
+  const size_t base = (size_t)n * row_vecs;
+  int arow[4];                                   // anchor (within a round) of each of this thread's four elements
+#pragma unroll
+  for (int k = 0; k < 4; ++k) arow[k] = (4 * t + k) / joints;
+  Partial p[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) p[k] = Partial{-INFINITY, 0.f, 0.f, 0.f, 0.f};
+  for (int r0 = r_begin; r0 < r_end; r0 += U) {
+    float4 c[U], d[U], g0[U], g1[U];
+    float2 an[U][4];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int v = (r0 + u) * T + t;              // float4 index within the crop
+      ok[u] = (r0 + u) < r_end && v < row_vecs;
+      const size_t e = base + (ok[u] ? v : 0);
+      c[u] = __ldg(cls + e);
+      d[u] = __ldg(dep + e);
+      g0[u] = __ldg(reg + 2 * e);
+      g1[u] = __ldg(reg + 2 * e + 1);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int a = (r0 + u) * rows_per_round + arow[k];
+        an[u][k] = __ldg(anchor_xy + (ok[u] && a < anchors ? a : 0));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float cc[U], xx[U], yy[U], dd[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float ck = k == 0 ? c[u].x : k == 1 ? c[u].y : k == 2 ? c[u].z : c[u].w;
+        cc[u] = ok[u] ? ck : -INFINITY;
+        dd[u] = k == 0 ? d[u].x : k == 1 ? d[u].y : k == 2 ? d[u].z : d[u].w;
+        const float4 g = k < 2 ? g0[u] : g1[u];
+        xx[u] = an[u][k].x + ((k & 1) ? g.z : g.x);
+        yy[u] = an[u][k].y + ((k & 1) ? g.w : g.y);
+      }
+      float m = p[k].m;
+#pragma unroll
+      for (int u = 0; u < U; ++u) m = fmaxf(m, cc[u]);
+      if (m != -INFINITY) {
+        const float f = (p[k].m == -INFINITY) ? 0.f : expf(p[k].m - m);
+        p[k].s *= f; p[k].x *= f; p[k].y *= f; p[k].d *= f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float w = expf(cc[u] - m);
+          p[k].s += w;
+          p[k].x += w * xx[u];
+          p[k].y += w * yy[u];
+          p[k].d += w * dd[u];
+        }
+        p[k].m = m;
+      }
+    }
+  }
+  // merge: entry q = 4t + k belongs to joint q % joints, anchor row q / joints
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sh[4 * t + k] = p[k];
+  __syncthreads();
+  // stage 1: thread (rg, j) folds rows 4*rg .. 4*rg+3 of joint j (T = rows_per_round / 4 * joints threads exactly)
+  const int j = t % joints, rg = t / joints;
+  Partial acc = sh[(4 * rg) * joints + j];
+#pragma unroll
+  for (int i = 1; i < 4; ++i) merge(acc, sh[(4 * rg + i) * joints + j]);
+  __syncthreads();
+  sh[t] = acc;                                   // [rows_per_round / 4][joints]
+  __syncthreads();
+  if (t < joints) {
+    Partial a2 = sh[t];
+    for (int i = 1; i < rows_per_round / 4; ++i) merge(a2, sh[i * joints + t]);
+    part[((size_t)n * splits + split) * joints + t] = a2;
+  }
+}
+
 __global__ void a2j_combine_kernel(const Partial* __restrict__ part, int splits, int joints, int n_total,
                                    float* __restrict__ out) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_total * joints) return;
   const int n = g / joints, j = g - n * joints;
-  Partial acc = part[((size_t)n * splits) * joints + j];
-  for (int s = 1; s < splits; ++s) merge(acc, part[((size_t)n * splits + s) * joints + j]);
+  Partial ps[AGG_SPLITS];                        // all partials are fetched before the (serial) merge chain
+#pragma unroll
+  for (int s = 0; s < AGG_SPLITS; ++s)
+    if (s < splits) ps[s] = part[((size_t)n * splits + s) * joints + j];
+  Partial acc = ps[0];
+#pragma unroll
+  for (int s = 1; s < AGG_SPLITS; ++s)
+    if (s < splits) merge(acc, ps[s]);
   out[(size_t)g * 3 + 0] = acc.x / acc.s;
   out[(size_t)g * 3 + 1] = acc.y / acc.s;
   out[(size_t)g * 3 + 2] = acc.d / acc.s;
 }
-
-constexpr int AGG_SPLITS = 16;
 
 }  // namespace
 
@@ -183,16 +295,36 @@ extern "C" int hn_a2j_aggregate(const float* cls, const float* reg, const float*
   HN_REQUIRE(cls && reg && depth && anchor_xy && out && workspace, "hn_a2j_aggregate: null pointer");
   HN_REQUIRE(n > 0 && anchors > 0 && joints > 0 && joints <= AGG_MAX_THREADS, "hn_a2j_aggregate: bad sizes");
   HN_REQUIRE(workspace_bytes >= hn_a2j_workspace_bytes(n, joints), "hn_a2j_aggregate: workspace too small");
-  const int rows = AGG_MAX_THREADS / joints > 12 ? 12 : AGG_MAX_THREADS / joints;
-  const int threads = ((rows * joints + 31) / 32) * 32;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  dim3 grid(AGG_SPLITS, n);
-  a2j_partial_kernel<<<grid, threads, threads * sizeof(Partial), st>>>(
-      cls, reinterpret_cast<const float2*>(reg), depth, reinterpret_cast<const float2*>(anchor_xy), anchors, joints, rows,
-      reinterpret_cast<Partial*>(workspace));
+  // few crops: many anchor ranges per crop for parallelism; many crops: long ranges, so that the per-block
+  // shared-memory merge tail is amortised over more streamed rows
+  const int splits = n >= 64 ? AGG_SPLITS / 4 : AGG_SPLITS;
+  dim3 grid(splits, n);
+  // vector path: T = rows_per_round * joints / 4 threads, rows_per_round a multiple of 4 -> T a multiple of joints
+  int rows_per_round = (4 * 256 / joints) & ~3;
+  const int vec_threads = rows_per_round * joints / 4;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(cls) | reinterpret_cast<uintptr_t>(reg) |
+                         reinterpret_cast<uintptr_t>(depth)) & 15) == 0;
+  const bool vec = aligned && rows_per_round >= 4 && (anchors * (long long)joints) % 4 == 0;
+  if (vec) {
+    const size_t sh_bytes = (size_t)4 * vec_threads * sizeof(Partial);
+    // one round in flight per thread at >= 4 CTAs per SM measured best (512 crops: 85 us; two rounds in flight at 2
+    // CTAs per SM 93 us; 6 CTAs per SM spills: 140 us)
+    auto* kern = a2j_partial_vec_kernel<1, 4>;
+    kern<<<grid, vec_threads, sh_bytes, st>>>(reinterpret_cast<const float4*>(cls), reinterpret_cast<const float4*>(reg),
+                                              reinterpret_cast<const float4*>(depth),
+                                              reinterpret_cast<const float2*>(anchor_xy), anchors, joints, rows_per_round,
+                                              reinterpret_cast<Partial*>(workspace));
+  } else {
+    const int rows = AGG_MAX_THREADS / joints > 12 ? 12 : AGG_MAX_THREADS / joints;
+    const int threads = ((rows * joints + 31) / 32) * 32;
+    a2j_partial_kernel<<<grid, threads, threads * sizeof(Partial), st>>>(
+        cls, reinterpret_cast<const float2*>(reg), depth, reinterpret_cast<const float2*>(anchor_xy), anchors, joints, rows,
+        reinterpret_cast<Partial*>(workspace));
+  }
   hn_count_launch();
   HN_LAUNCH_CHECK();
-  a2j_combine_kernel<<<hn_div_up(n * joints, 128), 128, 0, st>>>(reinterpret_cast<const Partial*>(workspace), AGG_SPLITS,
+  a2j_combine_kernel<<<hn_div_up(n * joints, 128), 128, 0, st>>>(reinterpret_cast<const Partial*>(workspace), splits,
                                                                  joints, n, out);
   hn_count_launch();
   HN_LAUNCH_CHECK();

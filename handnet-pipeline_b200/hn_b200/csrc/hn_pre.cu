@@ -13,7 +13,7 @@ constexpr int PRE_MAX_IMAGES = 32;
 struct PreParams {
   const float* img[PRE_MAX_IMAGES];
   int in_h[PRE_MAX_IMAGES], in_w[PRE_MAX_IMAGES], out_h[PRE_MAX_IMAGES], out_w[PRE_MAX_IMAGES];
-  float mean[3], inv_unused[3], stdv[3];
+  float mean[3], inv_std[3], stdv[3];             // inv_std = 1 / std (fp32, rounded once on the host)
   float scale_y[PRE_MAX_IMAGES], scale_x[PRE_MAX_IMAGES];   // in / out as fp32, per image
   int canvas_h, canvas_w, batch_offset;
   int pad_top, pad_left, pitch_h, pitch_w;   // the canvas sits at (pad_top, pad_left) of a [pitch_h][pitch_w] pixel frame
@@ -49,8 +49,6 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p, uint
     const float* r0 = p.img[b] + (size_t)y0 * iw;
     const float* r1 = p.img[b] + (size_t)y1 * iw;
     const size_t plane = (size_t)ih * iw;
-    const float inv_unused = 0.f;
-    (void)inv_unused;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int x = x4 + j;
@@ -66,7 +64,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p, uint
           // the bilinear weights sum to one, so normalising after the interpolation equals torchvision's
           // normalise-then-resize up to fp32 rounding (the result is rounded to bf16 anyway): 1 division instead of 4
           const float t = ly0 * (lx0 * __ldg(q0 + x0) + lx1 * __ldg(q0 + x1)) + ly1 * (lx0 * __ldg(q1 + x0) + lx1 * __ldg(q1 + x1));
-          v[c] = (t - p.mean[c]) / p.stdv[c];
+          v[c] = (t - p.mean[c]) * p.inv_std[c];   // (an IEEE division is ~20 instructions: the kernel was issue-bound)
         }
         outv[j].x = hn_pack_bf16(v[0], v[1]);
         outv[j].y = hn_pack_bf16(v[2], 0.f);
@@ -79,6 +77,72 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p, uint
     hn_stg256(dst, w8);
   } else {
     for (int j = 0; j < 4 && x4 + j < p.canvas_w; ++j) dst[j] = outv[j];
+  }
+}
+
+// Row-staged variant (the default): one CTA = one canvas row of one image.  The two source rows of each colour plane
+// are read with coalesced 16-byte loads, blended vertically, and the blended row (3 * in_w floats) is kept in shared
+// memory; then consecutive lanes interpolate consecutive canvas pixels horizontally from there (their source columns
+// are <= one word apart: conflict-free broadcasts).  preprocess_kernel's 48 scattered 4-byte global loads and three
+// IEEE divisions per thread made it issue-bound (ncu: 80 % issue-active at 24 % of the HBM roofline); this one
+// spends ~55 instructions per pixel.  The bilinear weights are applied vertical-first here (ATen: horizontal-first):
+// the same four products, summed in another order -- a few fp32 ulp before the rounding to bf16.
+__global__ void __launch_bounds__(512) preprocess_rows_kernel(const PreParams p, uint2* __restrict__ canvas, int pitch) {
+  extern __shared__ __align__(16) float staged[];   // [3 planes][pitch]
+  const int b = blockIdx.z;
+  const int y = blockIdx.y;
+  const int oh = p.out_h[b], ow = p.out_w[b];
+  const int ih = p.in_h[b], iw = p.in_w[b];
+  const bool live = y < oh;
+  if (live) {
+    int y0, y1;
+    float ly0, ly1;
+    bilinear_axis(y, ih, p.scale_y[b], y0, y1, ly0, ly1);
+    const float* base = p.img[b];
+    const size_t plane = (size_t)ih * iw;
+    if ((iw & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0) {
+      const int q = iw >> 2;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float4* r0 = reinterpret_cast<const float4*>(base + c * plane + (size_t)y0 * iw);
+        const float4* r1 = reinterpret_cast<const float4*>(base + c * plane + (size_t)y1 * iw);
+        float4* dst = reinterpret_cast<float4*>(staged + c * pitch);
+        for (int col = threadIdx.x; col < q; col += blockDim.x) {
+          const float4 u = __ldg(r0 + col), v = __ldg(r1 + col);
+          dst[col] = make_float4(ly0 * u.x + ly1 * v.x, ly0 * u.y + ly1 * v.y, ly0 * u.z + ly1 * v.z, ly0 * u.w + ly1 * v.w);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* r0 = base + c * plane + (size_t)y0 * iw;
+        const float* r1 = base + c * plane + (size_t)y1 * iw;
+        for (int col = threadIdx.x; col < iw; col += blockDim.x) staged[c * pitch + col] = ly0 * __ldg(r0 + col) + ly1 * __ldg(r1 + col);
+      }
+    }
+  }
+  __syncthreads();
+  const float m0 = p.mean[0], m1 = p.mean[1], m2 = p.mean[2];
+  const float s0 = p.inv_std[0], s1 = p.inv_std[1], s2 = p.inv_std[2];
+  const float scale_x = p.scale_x[b];
+  const float* q1 = staged + pitch;
+  const float* q2 = staged + 2 * pitch;
+  uint2* dst_row = canvas + ((size_t)(p.batch_offset + b) * p.pitch_h + y + p.pad_top) * p.pitch_w + p.pad_left;
+  const int x_live = live ? ow : 0;
+#pragma unroll 2
+  for (int x = threadIdx.x; x < p.canvas_w; x += blockDim.x) {
+    uint2 o = make_uint2(0u, 0u);
+    if (x < x_live) {
+      int x0, x1;
+      float lx0, lx1;
+      bilinear_axis(x, iw, scale_x, x0, x1, lx0, lx1);
+      const float t0 = lx0 * staged[x0] + lx1 * staged[x1];
+      const float t1 = lx0 * q1[x0] + lx1 * q1[x1];
+      const float t2 = lx0 * q2[x0] + lx1 * q2[x1];
+      o.x = hn_pack_bf16((t0 - m0) * s0, (t1 - m1) * s1);
+      o.y = hn_pack_bf16((t2 - m2) * s2, 0.f);
+    }
+    dst_row[x] = o;
   }
 }
 
@@ -250,6 +314,7 @@ extern "C" int hn_preprocess_resize_pad_framed(const float* const* images_host, 
     for (int c = 0; c < 3; ++c) {
       p.mean[c] = mean3_host[c];
       p.stdv[c] = std3_host[c];
+      p.inv_std[c] = 1.0f / std3_host[c];
     }
     p.canvas_h = canvas_h;
     p.canvas_w = canvas_w;
@@ -258,8 +323,19 @@ extern "C" int hn_preprocess_resize_pad_framed(const float* const* images_host, 
     p.pitch_h = pitch_h;
     p.pitch_w = pitch_w;
     p.batch_offset = b0;
-    dim3 grid(hn_div_up(hn_div_up(canvas_w, 4), 256), canvas_h, nb);
-    preprocess_kernel<<<grid, 256, 0, st>>>(p, reinterpret_cast<uint2*>(canvas_bf16));
+    int max_w = 0;
+    for (int i = 0; i < nb; ++i) max_w = p.in_w[i] > max_w ? p.in_w[i] : max_w;
+    const int pitch = (max_w + 3) & ~3;
+    const size_t staged_bytes = (size_t)3 * pitch * sizeof(float);
+    if (staged_bytes <= 48 * 1024) {
+      int threads = ((hn_div_up(canvas_w, 4) + 31) / 32) * 32;   // ~4 canvas pixels per thread
+      threads = threads > 512 ? 512 : threads;
+      preprocess_rows_kernel<<<dim3(1, canvas_h, nb), threads, staged_bytes, st>>>(p, reinterpret_cast<uint2*>(canvas_bf16),
+                                                                                  pitch);
+    } else {                                         // source rows too wide to stage: gather from global memory
+      dim3 grid(hn_div_up(hn_div_up(canvas_w, 4), 256), canvas_h, nb);
+      preprocess_kernel<<<grid, 256, 0, st>>>(p, reinterpret_cast<uint2*>(canvas_bf16));
+    }
     hn_count_launch();
     HN_LAUNCH_CHECK();
   }

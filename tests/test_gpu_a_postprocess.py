@@ -198,9 +198,9 @@ def test_select_crop_resize_bit_exact(ops, golden):
         assert torch.equal(db[i], ref)
 
 
-def test_a2j_aggregate_matches_oracle(ops):
+@pytest.mark.parametrize("n", [5, 70])        # 70: the many-crops launch shape (4 anchor ranges per crop instead of 16)
+def test_a2j_aggregate_matches_oracle(ops, n):
     g = torch.Generator().manual_seed(3)
-    n = 5
     cls = torch.randn(n, 1936, 21, generator=g) * 4
     reg = torch.randn(n, 1936, 21, 2, generator=g) * 10
     dep = torch.randn(n, 1936, 21, generator=g)
@@ -209,4 +209,19 @@ def test_a2j_aggregate_matches_oracle(ops):
     out = ops.a2j_aggregate(cls.cuda(), reg.cuda(), dep.cuda(), anchors.cuda())
     torch.cuda.synchronize()
     # fp32 reduction over 1936 anchors in a different order than ATen: 1e-5 relative
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("n,anchors,joints", [(3, 7, 5), (2, 1936, 14), (66, 50, 3), (2, 40, 3)])
+def test_a2j_aggregate_other_shapes(ops, n, anchors, joints):
+    """Shapes other than the shipped 1936 x 21 head: anchors * joints not a multiple of 4 takes the scalar kernel;
+    joints = 14 changes the round geometry of the vector kernel."""
+    g = torch.Generator().manual_seed(11)
+    cls = torch.randn(n, anchors, joints, generator=g) * 4
+    reg = torch.randn(n, anchors, joints, 2, generator=g) * 10
+    dep = torch.randn(n, anchors, joints, generator=g)
+    anc = torch.randn(anchors, 2, generator=g) * 50
+    ref = a2j_oracle.aggregate(cls, reg, dep, anc)
+    out = ops.a2j_aggregate(cls.cuda(), reg.cuda(), dep.cuda(), anc.cuda())
+    torch.cuda.synchronize()
     torch.testing.assert_close(out.cpu(), ref, rtol=1e-5, atol=1e-4)

@@ -11,8 +11,11 @@ from oracle.golden_inputs import stress_head_tensors
 PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
+REPS = int(os.environ.get("HN_MEMBOUND_REPS", "0"))     # 1 under ncu (each profiled launch is replayed ~40 times)
+
 def timeit(fn, reps=10):
-    for _ in range(3): fn()
+    if REPS: reps = REPS
+    for _ in range(1 if REPS else 3): fn()
     ts = []
     for _ in range(reps):
         flush.zero_()
