@@ -136,6 +136,29 @@ def test_nms_stress_config4_matches_oracle(ops):
         assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("thr", [0.3, 0.5])
+def test_nms_random_integer_boxes_all_chunk_shapes(ops, thr):
+    """Boxes on a small integer grid (IoUs are ratios of small integers: many land exactly on the threshold, e.g.
+    3/10 and 1/2, where the fp32 division decides), list lengths around the 64-box chunk boundaries of the scan
+    kernel, three classes and score ties -- kept indices identical to the numpy oracle (torchvision CPU semantics)."""
+    rng = np.random.default_rng(5)
+    boxes, scores, labels = [], [], []
+    for n in (1, 2, 63, 64, 65, 127, 128, 130, 777, 2049):
+        xy = rng.integers(0, 24, size=(n, 2)).astype(np.float32)
+        wh = rng.integers(1, 11, size=(n, 2)).astype(np.float32)
+        boxes.append(torch.from_numpy(np.concatenate([xy, xy + wh], axis=1)))
+        scores.append(torch.from_numpy((rng.integers(0, 200, size=n) / 200.0).astype(np.float32)))
+        labels.append(torch.from_numpy(rng.integers(0, 3, size=n).astype(np.int64)))
+    got = _run_nms(ops, boxes, scores, labels, thr=thr)
+    for bx, sc, lb, g in zip(boxes, scores, labels, got):
+        ref = nms_oracle.batched_nms(bx.numpy(), sc.numpy(), lb.numpy(), thr)
+        if bx.numel() > 4000:      # per-class branch: order inside exact score ties is unspecified in torchvision
+            s64 = sc.numpy().astype(np.float64)
+            ref = ref[np.lexsort((ref, -s64[ref]))]
+            g = g[np.lexsort((g, -s64[g]))]
+        assert np.array_equal(g, ref), (len(sc), g[:10], ref[:10])
+
+
 def test_gather_and_full_postprocess_chain(ops, golden):
     """decode -> NMS -> gather on the reference's own config-4 fixture: boxes / labels / sides / levels of the
     kept detections are identical to the reference's output (scores at 2 ulp)."""
