@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(64)
 nms_mask_kernel(const int* __restrict__ cand_count, int batch, int cap, float thr_ge, NmsWs ws) {
   __shared__ float4 cb_box[64];
   __shared__ int cb_lab[64];
+  __shared__ float cb_area[64];
   // persistent over the list of (image, row block, col block >= row block)
   long long tile = blockIdx.x;
   int b = 0;
@@ -321,8 +322,12 @@ nms_mask_kernel(const int* __restrict__ cand_count, int batch, int cap, float th
     const int j0 = cb * 64;
     __syncthreads();
     if (j0 + (int)threadIdx.x < n) {
-      cb_box[threadIdx.x] = ws.sbox[off + j0 + threadIdx.x];
+      const float4 bx = ws.sbox[off + j0 + threadIdx.x];
+      cb_box[threadIdx.x] = bx;
       cb_lab[threadIdx.x] = ws.slabel[off + j0 + threadIdx.x];
+      cb_area[threadIdx.x] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+    } else {
+      cb_lab[threadIdx.x] = -0x40000000;           // columns beyond n: a label no box has
     }
     __syncthreads();
     const int i = rb * 64 + threadIdx.x;
@@ -331,48 +336,60 @@ nms_mask_kernel(const int* __restrict__ cand_count, int batch, int cap, float th
       const int li = ws.slabel[off + i];
       const float iarea = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
       unsigned long long bits = 0ull;
-      const int jn = min(64, n - j0);
-      for (int j = (cb == rb) ? (int)threadIdx.x + 1 : 0; j < jn; ++j) {
-        const float4 bj = cb_box[j];
-        if (cb_lab[j] != li) continue;
-        const float jarea = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
-        const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
-        const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
-        const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
-        const float inter = __fmul_rn(w, h);
-        const float uni = __fsub_rn(__fadd_rn(iarea, jarea), inter);
-        // The decision is fl(inter / uni) >= thr_ge, exactly as torchvision divides and compares.  The IEEE division
-        // (~15 instructions) is only executed inside a band of +-1e-4 (relative) around the threshold: outside it the
-        // exact quotient is at least 1e-4 away from thr_ge, far more than the 6e-8 the rounding can move it.
-        // (Only for unions and thresholds well inside the normal range, so that the products neither underflow nor
-        // overflow; everything else -- empty or inverted boxes, NaN -- takes the division.)
-        const float q = __fmul_rn(thr_ge, uni);
-        const bool band_ok = uni > 1e-30f && uni < 1e30f && thr_ge > 1e-6f;
-        bool hit;
-        if (band_ok && inter < __fmul_rn(q, 0.9999f)) {
-          hit = false;
-        } else if (band_ok && inter > __fmul_rn(q, 1.0001f)) {
-          hit = true;
-        } else {
-          hit = __fdiv_rn(inter, uni) >= thr_ge;      // == ((double)ovr > (double)iou_threshold); NaN (0/0) compares false
+      // Uniform, branch-free loop over all 64 columns (lanes hold different rows, so a per-lane `continue` on the label
+      // or a per-lane start column only diverges); the diagonal tile clears the bits j <= own column afterwards.
+      // The decision is fl(inter / uni) >= thr_ge, exactly as torchvision divides and compares.  The IEEE division
+      // (~15 instructions) is only executed inside a band of +-1e-4 (relative) around the threshold: outside it the
+      // exact quotient is at least 1e-4 away from thr_ge, far more than the 6e-8 the rounding can move it.  (Only for
+      // unions and thresholds well inside the normal range, so that the products neither underflow nor overflow;
+      // everything else -- empty or inverted boxes, NaN -- takes the division.)
+      const bool thr_ok = thr_ge > 1e-6f;
+#pragma unroll 1
+      for (int jb = 0; jb < 64; jb += 8) {
+        uint32_t g = 0u;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = jb + u;
+          const float4 bj = cb_box[j];
+          const float jarea = cb_area[j];
+          const bool same = cb_lab[j] == li;
+          const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
+          const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
+          const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+          const float inter = __fmul_rn(w, h);
+          const float uni = __fsub_rn(__fadd_rn(iarea, jarea), inter);
+          const float q = __fmul_rn(thr_ge, uni);
+          const bool band_ok = thr_ok && uni > 1e-30f && uni < 1e30f;
+          const bool sure_miss = band_ok && inter < __fmul_rn(q, 0.9999f);
+          const bool sure_hit = band_ok && inter > __fmul_rn(q, 1.0001f);
+          bool hit = same && sure_hit;
+          if (same && !sure_miss && !sure_hit)
+            hit = __fdiv_rn(inter, uni) >= thr_ge;    // == ((double)ovr > (double)iou_threshold); NaN (0/0) compares false
+          g |= hit ? (1u << u) : 0u;
         }
-        if (hit) bits |= (1ull << j);
+        bits |= (unsigned long long)g << jb;
       }
+      if (cb == rb) bits &= ~((2ull << threadIdx.x) - 1ull);     // upper triangle only: j > own column
       ws.mask[((size_t)b * cap + i) * ws.words + cb] = bits;
     }
     tile += gridDim.x;
   }
 }
 
-// One CTA per image: greedy scan over the bitmask in 64-box chunks.  Per chunk: (1) one thread resolves the chunk
-// against its 64 diagonal words (registers / shared memory only), while another warp already fetches the next chunk's
-// diagonal; (2) every kept box's index is written in parallel (rank = popcount of the kept bits below it); (3) the
-// mask rows of the kept boxes are OR-ed into the running `removed` bitmap with all loads independent: warp w takes
-// the kept rows w, w + 32, ..., its lanes the words to the right of the diagonal (coalesced), merged with 32-bit
-// shared-memory atomics.  (The first version walked the kept rows with one dependent global load each per thread and
-// wrote the keep list from the serial loop: 19 us per chunk at 10 k candidates, now ~2.)
+// One CTA per image: greedy scan over the bitmask in 64-box chunks, software-pipelined so that the only serial work
+// per chunk is the 64-step resolve itself.  Iteration c, phase 1 (all concurrent):
+//   thread 0      resolves chunk c against its diagonal words (shared memory / registers only) -> kept bits;
+//   warps 1-2     fetch, for every row of chunk c, its candidate index and its mask word c+1 (the only word the NEXT
+//                 resolve needs) -- before it is known which rows are kept;
+//   warps 3-4     fetch the diagonal words of chunk c+1;
+//   warps 5-31    OR the mask rows of the boxes kept in chunk c-1 into removed[c+1 ..] (one warp per row, lanes
+//                 along the words: coalesced, all loads of a warp in flight together, 32-bit shared atomics).
+// Phase 2: warps 1-2 write the kept indices (rank = popcount of the kept bits below) and OR the prefetched words of
+// the kept rows into removed[c+1].  No global-memory latency is exposed on the c -> c+1 dependency.
+// (First version: one dependent global load per kept row per thread and the keep list written from the serial loop,
+// 19 us per chunk at 10 k candidates; this one ~1.5.)
 constexpr int SCAN_THREADS = 1024;
-constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+constexpr int SCAN_OR_WARPS = SCAN_THREADS / 32 - 5;
 __global__ void __launch_bounds__(SCAN_THREADS)
 nms_scan_kernel(const int* __restrict__ cand_count, int cap, NmsWs ws, int* __restrict__ keep,
                 int* __restrict__ keep_count) {
@@ -387,12 +404,16 @@ nms_scan_kernel(const int* __restrict__ cand_count, int cap, NmsWs ws, int* __re
   const uint32_t* order = ws.idx[0] + off;
   const unsigned long long* mask = ws.mask + off * words;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t* rem32 = reinterpret_cast<uint32_t*>(removed);
   for (int i = tid; i < nb; i += SCAN_THREADS) removed[i] = 0ull;
   if (tid < 64 && tid < n) diag[0][tid] = mask[(size_t)tid * words];
   int kept_total = 0;                                // uniform: every thread adds the popcount of each chunk
+  unsigned long long kept_prev = 0ull;               // kept bits of chunk c-1 (uniform)
   __syncthreads();
   for (int c = 0; c < nb; ++c) {
     const int cnt = min(64, n - c * 64);
+    unsigned long long next_word = 0ull;
+    uint32_t ord = 0u;
     if (tid == 0) {
       const unsigned long long* dg = diag[c & 1];
       unsigned long long cur = removed[c], kept = 0ull;
@@ -410,24 +431,21 @@ nms_scan_kernel(const int* __restrict__ cand_count, int cap, NmsWs ws, int* __re
         }
       }
       kept_bits_s = kept;
-    } else if (warp >= 2 && warp < 4) {              // next chunk's diagonal words
-      const int r = tid - 64, i = (c + 1) * 64 + r;
+    } else if (warp == 1 || warp == 2) {
+      const int r = tid - 32;
+      if (r < cnt) {
+        ord = order[c * 64 + r];
+        if (c + 1 < nb) next_word = mask[(size_t)(c * 64 + r) * words + (c + 1)];
+      }
+    } else if (warp == 3 || warp == 4) {
+      const int r = tid - 96, i = (c + 1) * 64 + r;
       if (c + 1 < nb && i < n) diag[(c + 1) & 1][r] = mask[(size_t)i * words + (c + 1)];
-    }
-    __syncthreads();
-    const unsigned long long kept = kept_bits_s;
-    if (tid < cnt && ((kept >> tid) & 1ull))
-      keep[off + kept_total + __popcll(kept & ((1ull << tid) - 1ull))] = (int)order[c * 64 + tid];
-    kept_total += __popcll(kept);
-    if (kept != 0ull && c + 1 < nb) {
-      unsigned long long kb = kept;
-      int idx = 0;
-      uint32_t* rem32 = reinterpret_cast<uint32_t*>(removed);
-      while (kb) {
-        const int r = __ffsll((long long)kb) - 1;
-        kb &= kb - 1;
-        if ((idx++ & (SCAN_WARPS - 1)) != warp) continue;
-        const unsigned long long* row = mask + (size_t)(c * 64 + r) * words;
+    } else if (warp >= 5 && kept_prev != 0ull && c + 1 < nb) {
+      // warp w owns the rows w-5, w-5+27, w-5+54 of the chunk (no enumeration of the kept bits: ncu showed the
+      // kernel issue-bound on exactly that loop, run by all 27 warps)
+      for (int r = warp - 5; r < 64; r += SCAN_OR_WARPS) {
+        if (!((kept_prev >> r) & 1ull)) continue;
+        const unsigned long long* row = mask + (size_t)((c - 1) * 64 + r) * words;
         for (int w0 = c + 1 + lane; w0 < nb; w0 += 256) {
           unsigned long long v[8];
 #pragma unroll
@@ -441,6 +459,22 @@ nms_scan_kernel(const int* __restrict__ cand_count, int cap, NmsWs ws, int* __re
         }
       }
     }
+    __syncthreads();
+    const unsigned long long kept = kept_bits_s;
+    if (warp == 1 || warp == 2) {
+      const int r = tid - 32;
+      const bool mine = r < cnt && ((kept >> r) & 1ull);
+      if (mine) keep[off + kept_total + __popcll(kept & ((1ull << r) - 1ull))] = (int)ord;
+      const unsigned long long v = mine ? next_word : 0ull;
+      const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)v);
+      const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
+      if (lane == 0 && c + 1 < nb) {
+        if (lo) atomicOr(rem32 + 2 * (c + 1), lo);
+        if (hi) atomicOr(rem32 + 2 * (c + 1) + 1, hi);
+      }
+    }
+    kept_total += __popcll(kept);
+    kept_prev = kept;
     __syncthreads();
   }
   if (tid == 0) keep_count[b] = kept_total;
@@ -583,7 +617,7 @@ extern "C" int hn_nms_batched(const float* cand_box, const float* cand_score, co
                                                   cand_count, cap, coord_trick_max_numel, ws);
   hn_count_launch();
   HN_LAUNCH_CHECK();
-  nms_mask_kernel<<<hn_num_sms() * 16, 64, 0, st>>>(cand_count, batch, cap, thr_ge, ws);
+  nms_mask_kernel<<<hn_num_sms() * 32, 64, 0, st>>>(cand_count, batch, cap, thr_ge, ws);
   hn_count_launch();
   HN_LAUNCH_CHECK();
   const size_t scan_smem = (size_t)ws.words * 8;
