@@ -35,6 +35,14 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int A_BOX_ROWS_MAX = 136;                   // 128 + up to 8 rows of horizontal-tap slack
 constexpr int A_SLOT_BYTES = A_BOX_ROWS_MAX * BLOCK_K * 2;   // 17 KiB (a multiple of 1024: slots keep swizzle alignment)
+// Patch tiles (resident weights, 3x3 stride 1 on large maps): an M tile is a 16-row x 8-pixel patch of ONE image instead
+// of 128 consecutive rows of the flattened matrix.  One 4-D TMA box {64 ch, 10 px, 18 rows} (22.5 KiB) then holds the
+// activations of all nine taps -- 1.4x the tile's own pixels instead of the 3.2x of three 136-row boxes (the layer1
+// convolutions are bound by L2 -> SM traffic).  In shared memory the box is 180 rows of 128 B; tap (t, s) reads it from
+// row t*10 + s on with a stride of 10 rows (1280 B) between the 8-row groups of the UMMA descriptor.
+constexpr int PATCH_H = 16, PATCH_W = 8;
+constexpr int PATCH_BOX_BYTES = (PATCH_H + 2) * (PATCH_W + 2) * BLOCK_K * 2;     // 23 040
+constexpr int PATCH_SLOT_BYTES = (PATCH_BOX_BYTES + 1023) / 1024 * 1024;         // 23 552
 constexpr int EPI_WARPS = 8;                       // two per TMEM lane quarter; they split the column chunks
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int NUM_THREADS = 64 + EPI_THREADS;
@@ -67,6 +75,7 @@ struct ConvParams {
   // direct 7x7/2 stem: an M tile is 128 consecutive output columns of one output row; the A tensor map is the 5-D
   // overlapping-stride patch view of the canvas (build_conv)
   int stem_tpr, stem_h;                     // tiles per output row (0 = ordinary convolution), output rows per image
+  int patch_tx, patch_ty;                   // patch tiles per image row / column (0 = flattened M tiles)
   int m_tiles, n_tiles;
   int cout, cout_pad;
   const float* scale;
@@ -238,7 +247,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
   const int k_steps = p.k_steps;                         // one k-step = one A box
   uint8_t* pipe = smem_hdr + HDR_PAD;                    // 1024-aligned operand area
   uint8_t* a_ring = pipe + (RB ? p.rb_b_bytes : 0);
-  const int a_slot_bytes = (RB && p.rb3) ? 3 * A_SLOT_BYTES : A_SLOT_BYTES;
+  const int a_slot_bytes = (RB && p.patch_tx > 0) ? PATCH_SLOT_BYTES : ((RB && p.rb3) ? 3 * A_SLOT_BYTES : A_SLOT_BYTES);
   uint8_t* b_ring = a_ring + na * a_slot_bytes;
   int& it = ps.it;
 
@@ -372,6 +381,14 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
         }
         continue;
       }
+      int pt_n = 0, pt_y = 0, pt_x = 0;                      // patch tiles: image, first box row / column (padded coords)
+      if (RB && p.patch_tx > 0) {
+        const int per_img = p.patch_tx * p.patch_ty;
+        pt_n = mt / per_img;
+        const int rem = mt - pt_n * per_img, ty = rem / p.patch_tx;
+        pt_y = ty * PATCH_H + p.halo - 1;
+        pt_x = (rem - ty * p.patch_tx) * PATCH_W + p.halo - 1;
+      }
       for (int step = s_begin; step < s_end; ++step) {
         const int ntaps = info & 15;
         // ---- the A box of this (group, chunk)
@@ -382,7 +399,10 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
             hn_mbar_arrive(&a_full[a_stage]);
           } else {
             hn_mbar_expect_tx(&a_full[a_stage], (uint32_t)a_box_bytes);
-            hn_tma_load_3d(a_ring + a_stage * a_slot_bytes, &tm_a, &a_full[a_stage], cc * BLOCK_K, m0 + shift, info >> 24);
+            if (RB && p.patch_tx > 0)
+              hn_tma_load_4d(a_ring + a_stage * a_slot_bytes, &tm_a, &a_full[a_stage], cc * BLOCK_K, pt_x, pt_y, pt_n);
+            else
+              hn_tma_load_3d(a_ring + a_stage * a_slot_bytes, &tm_a, &a_full[a_stage], cc * BLOCK_K, m0 + shift, info >> 24);
           }
         }
         if (++a_stage == na) { a_stage = 0; a_phase ^= 1; }
@@ -529,9 +549,14 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
         if (RB && p.rb3) {
           // all nine taps of this chunk from one stage: A tile of kernel row t at slot + t * 17 KiB, tap (t, s) reads it
           // from row s * dil on; weight tile of tap t*3 + s, chunk cc
-          const uint32_t sa = a_desc0 + a_stage * (3 * A_SLOT_D);
+          const bool patch = p.patch_tx > 0;
+          const uint32_t sa = a_desc0 + a_stage * (patch ? (uint32_t)(PATCH_SLOT_BYTES >> 4) : 3 * A_SLOT_D);
           const uint32_t sb = b_desc0 + cc * B_SLOT_D, tap_d = cin_chunks * B_SLOT_D;
           const uint32_t ea = hn_smem_u32(&a_empty[a_stage]), tf = hn_smem_u32(&tmem_full[buf]);
+          // patch tiles: kernel row t starts t box rows (10 pixels) further, the 8-pixel groups are 10 rows apart
+          const uint32_t t_step = patch ? (PATCH_W + 2) * ROW_D : A_SLOT_D, s_step = patch ? ROW_D : off_step;
+          const uint64_t a_hi = patch ? ((desc_hi & ~(uint64_t(0x3FFF) << 32)) | (uint64_t(((PATCH_W + 2) * BLOCK_K * 2) >> 4) << 32))
+                                      : desc_hi;
           hn_tc_fence_after();
           if (hn_elect_one()) {
             if (!(dbg_flags & 4)) {
@@ -539,7 +564,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
               for (int t = 0; t < 3; ++t) {
 #pragma unroll
                 for (int sx = 0; sx < 3; ++sx) {
-                  hn_umma_bf16_x4(d_tmem, desc_hi | (sa + t * A_SLOT_D + sx * off_step), desc_hi | (sb + (t * 3 + sx) * tap_d),
+                  hn_umma_bf16_x4(d_tmem, a_hi | (sa + t * t_step + sx * s_step), desc_hi | (sb + (t * 3 + sx) * tap_d),
                                   idesc, (t | sx) ? 1u : accumulate);
                 }
               }
@@ -664,7 +689,15 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       // decode the padded pixel this accumulator row belongs to (divisions by multiply-high, see fastdiv())
       int img = 0, h = 0, w = 0;
       bool interior = false;
-      if (p.stem_tpr > 0) {                              // stem tile: 128 output columns of one output row
+      if (p.patch_tx > 0) {                              // patch tile: accumulator row r = pixel (r / 8, r % 8) of the patch
+        const int per_img = p.patch_tx * p.patch_ty;
+        img = mt / per_img;
+        const int rem = mt - img * per_img, ty = rem / p.patch_tx;
+        const int r = quarter * 32 + lane;
+        h = ty * PATCH_H + (r >> 3);
+        w = (rem - ty * p.patch_tx) * PATCH_W + (r & 7);
+        interior = img < p.n_img && h < p.hp - 2 * halo && w < wp - 2 * halo;
+      } else if (p.stem_tpr > 0) {                       // stem tile: 128 output columns of one output row
         const int row = mt / p.stem_tpr;
         img = row / p.stem_h;
         h = row - img * p.stem_h;
@@ -1303,6 +1336,15 @@ void fastdiv(uint32_t d, uint32_t* mul, int* sh) {
   *sh = l;
 }
 
+bool patch_enabled() {          // HN_CONV_PATCH=1|0: patch tiles for the resident-weights 3x3 layers (see PATCH_H)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HN_CONV_PATCH");
+    v = (e && e[0] != '0') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 int split_min_kb() {            // experiment knob: HN_SPLIT_MIN_KB (k-blocks a layer needs before split-K is considered)
   static int v = -1;
   if (v < 0) {
@@ -1385,6 +1427,11 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
   const bool uni = bn <= 128 && !rb;      // unified stages (must match the kernel's constexpr UNI)
   const bool rb3 = rb && d->kh == 3 && d->stride == 1 && !(d->debug & 32) &&
                    PIPE_BYTES_MAX - b_bytes >= 2 * 3 * A_SLOT_BYTES && p.rows > 2 * d->dilation * p.wp;
+  // patch tiles (see PATCH_H): large maps only -- a 16 x 8 patch grid wastes too much on small ones.  Measured neutral
+  // (layer1 60.4 vs 58.4 us, whole step 3.88-3.91 vs 3.89-3.90 ms: these layers are bound by the MMA-issuing warp, not by
+  // L2 -> SM traffic), so it is opt-in: debug bit 14 or HN_CONV_PATCH=1.
+  const bool patch = rb3 && d->dilation == 1 && d->halo_in >= 1 && d->h >= 64 && d->w >= 64 &&
+                     ((d->debug & 16384) || patch_enabled());
 
   // A-box groups.  Pixel (oh*stride + dr, ow*stride + ds) of tap (r, s), dr = (r - kh/2)*dil, ds = (s - kw/2)*dil, is row
   // m + shift of the (phase) matrix; taps of one kernel row whose shifts differ by a few rows share one box.
@@ -1468,7 +1515,13 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
     p.rb_b_bytes = (int)b_bytes;
     p.rb3 = rb3 ? 1 : 0;
     if (rb3) p.a_box_bytes = 3 * A_SLOT_BYTES;
-    const int slots = (PIPE_BYTES_MAX - p.rb_b_bytes) / (rb3 ? 3 * A_SLOT_BYTES : A_SLOT_BYTES);
+    if (patch) {
+      p.patch_tx = hn_div_up(d->w, PATCH_W);
+      p.patch_ty = hn_div_up(d->h, PATCH_H);
+      p.m_tiles = d->n * p.patch_tx * p.patch_ty;
+      p.a_box_bytes = PATCH_BOX_BYTES;
+    }
+    const int slots = (PIPE_BYTES_MAX - p.rb_b_bytes) / (patch ? PATCH_SLOT_BYTES : (rb3 ? 3 * A_SLOT_BYTES : A_SLOT_BYTES));
     p.na_stages = slots > MAX_STAGES ? MAX_STAGES : slots;
     p.nb_stages = 1;
   } else {
@@ -1600,7 +1653,15 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
       if (p.splits > p.k_steps) p.splits = p.k_steps;
     }
   }
-  if (!stem && !(uni && p.uni_a_rank4)) {
+  if (patch) {
+    // the haloed NHWC tensor itself: (channels, padded columns, padded rows, images); out-of-range rows / columns of the
+    // last patches are zero-filled by the TMA unit
+    const cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)p.wp, (cuuint64_t)p.hp, (cuuint64_t)d->n};
+    const cuuint64_t strides[3] = {(cuuint64_t)d->cin * 2, (cuuint64_t)p.wp * d->cin * 2, (cuuint64_t)p.hp * p.wp * d->cin * 2};
+    const cuuint32_t box[4] = {BLOCK_K, PATCH_W + 2, PATCH_H + 2, 1};
+    int rc = make_map(&ta, d->in, 4, dims, strides, box);
+    if (rc) return rc;
+  } else if (!stem && !(uni && p.uni_a_rank4)) {
     // dims (channels, rows, phases); unified stride-2 3x3: the box spans both column phases of a row phase.
     // rb3: the third dimension steps by one (dilated) image row instead -- an overlapping view of the same matrix;
     // its row count is cut by two image rows so that row + 2 * wp stays inside the allocation (the rows cut off are the

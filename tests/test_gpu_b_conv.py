@@ -92,6 +92,30 @@ def test_conv_scale_shift_relu(ops, case):
     assert torch.isclose(full, out.interior().float().abs().sum()), "halo of the output must stay zero"
 
 
+@pytest.mark.parametrize("shape", [(2, 200, 272, 64, 64), (3, 100, 136, 256, 5), (4, 135, 141, 64, 32)])
+def test_conv_patch_tiles(ops, shape):
+    """Opt-in patch tiling of the resident-weights 3x3 path (debug bit 14): an M tile is a 16 x 8 pixel patch, one 4-D TMA
+    box {64, 10, 18} serves all nine taps through UMMA descriptors with a 1280-byte group stride.  Ragged patch grids
+    (135 x 141) read rows / columns beyond the tensor (zero-filled) and must not write outside the interior."""
+    n, h, w, cin, cout = shape
+    g = torch.Generator().manual_seed(h * w + cout)
+    x = rand(g, n, cin, h, w).to(DEV)
+    wt = rand(g, cout, cin, 3, 3, scale=(cin * 9) ** -0.5).to(DEV)
+    shift = (0.3 * torch.randn(cout, generator=g)).to(DEV)
+    idn = rand(g, n, cout, h, w).to(DEV)
+    ref = F.relu(F.conv2d(x, wt, None, padding=1) + shift[None, :, None, None] + idn)
+    outs = []
+    for debug in (16384, 0):
+        out = ops.Act(n, h, w, cout, 1, DEV)
+        ops.conv2d(ops.Act.from_nchw(x, 1), ops.pack_conv_weight(wt), cout=cout, ksize=3, shift=shift, relu=True,
+                   res=ops.Act.from_nchw(idn, 1), res_mode=1, out=out, debug=debug)
+        torch.cuda.synchronize()
+        close_bf16(out.to_nchw(), ref, f"patch debug={debug}")
+        assert torch.isclose(out.t.float().abs().sum(), out.interior().float().abs().sum()), "halo must stay zero"
+        outs.append(out.t.clone())
+    assert torch.equal(outs[0], outs[1]), "patch and flattened tiles accumulate the same products in the same order"
+
+
 def test_conv_residual_phase_copy_and_geometry_remap(ops):
     """BasicBlock tail: conv + scale/shift + identity + ReLU, written twice (plain halo-2 and phase-split)."""
     g = torch.Generator().manual_seed(7)
