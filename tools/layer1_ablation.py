@@ -36,5 +36,7 @@ print(f"{shape}: {n}x{h}x{w} {c}->{co}, {tiles} M tiles, activations {rows * c *
       f"A boxes per launch {tiles * 3 * 136 * 128 * (c // 64) * max(1, co // 256) / 1e6:.1f} MB (3 kernel rows x 136 rows x 128 B per chunk and tile)")
 base = int(os.environ.get("HN_DEBUG_BASE", "0"))     # e.g. 16384 = flattened tiles instead of patch tiles
 for name, dbg in (("full", 0), ("no stores", 64), ("no epilogue", 128), ("no MMA", 256), ("no MMA, no epilogue", 256 | 128),
-                  ("no TMA", 512), ("no TMA, no epilogue", 512 | 128)):
-    print(f"  {name:22s} {t(dbg | base):8.1f} us", flush=True)
+                  ("no TMA", 512), ("no TMA, no epilogue", 512 | 128), ("no TMA, no MMA, no epilogue (role loops only)", 512 | 256 | 128),
+                  ("no TMA, no MMA", 512 | 256), ("no TMA, no MMA, no epilogue ROLE (producer <-> MMA only)", 512 | 256 | 2048),
+                  ("no TMA, no epilogue ROLE (MMA issue + producer handshake)", 512 | 2048)):
+    print(f"  {name:60s} {t(dbg | base):8.1f} us", flush=True)
