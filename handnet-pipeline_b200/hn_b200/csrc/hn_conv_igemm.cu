@@ -76,6 +76,8 @@ struct ConvParams {
   // overlapping-stride patch view of the canvas (build_conv)
   int stem_tpr, stem_h;                     // tiles per output row (0 = ordinary convolution), output rows per image
   int patch_tx, patch_ty;                   // patch tiles per image row / column (0 = flattened M tiles)
+  int epi_alt;                              // epilogue: the two warps of a lane quarter take alternate TILES (all chunks
+                                            // of their tile) instead of alternate chunks of the same tile
   int m_tiles, n_tiles;
   int cout, cout_pad;
   const float* scale;
@@ -676,7 +678,22 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
     // skip chunks beyond cout: with cout_pad > cout they would land on the next pixel), 32-byte aligned rows, no split-K
     const bool epi_fast = p.out_kind == 0 && p.vec32 != 0 && (p.cout % 32) == 0 && p.cout_pad == p.cout && splits == 1 &&
                           !(p.dbg_flags & 64);
+    // Alternate-tile mode (single N tile, no split-K): the epilogue of a tile is a latency chain (accumulator wait,
+    // tcgen05.ld, residual / store round trips); with both warps of a quarter on the SAME tile nothing overlaps it.  Here
+    // warps 2-5 drain the even tiles and warps 6-9 the odd ones, so two tiles are in flight.  Each warp arrives twice on
+    // tmem_empty (the barrier counts eight arrivals per tile).  scale/shift are staged once for both buffers.
+    const bool alt = p.epi_alt != 0;
+    if (alt) {
+      for (int i = threadIdx.x - 64; i < BN; i += EPI_THREADS) {
+        const float sc = (p.scale && i < p.cout) ? __ldg(p.scale + i) : 1.0f;
+        const float sh = (p.shift && i < p.cout) ? __ldg(p.shift + i) : 0.0f;
+        ss_base[i] = sc; ss_base[256 + i] = sh; ss_base[512 + i] = sc; ss_base[768 + i] = sh;
+      }
+      ss_n0[0] = ss_n0[1] = 0;
+      hn_epi_bar_sync();
+    }
     for (int w_ = first_tile; w_ < num_items; w_ += tile_stride, ++it) {
+      if (alt && (it & 1) != half) continue;
       const int st = splits > 1 ? w_ / splits : w_;
       if (warp == 2) hn_trace(trace, 2, tri, 1);
       const int buf = it & (C::NBUF - 1);
@@ -756,8 +773,9 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       const bool res_vec = p.res_mode != 0 && interior && vec32;
       uint32_t res_next[CHUNK / 2];
       constexpr int STEP = (BN / CHUNK >= 2) ? 2 * CHUNK : CHUNK;   // two warps interleave chunks when there are >= 2
-      const int c_first = (BN / CHUNK >= 2) ? half * CHUNK : 0;
-      const bool idle_half = (BN / CHUNK < 2) && half == 1;         // a single chunk: the second warp only arrives
+      const int step_rt = alt ? CHUNK : STEP;                       // (alternate-tile mode: this warp takes every chunk)
+      const int c_first = (!alt && BN / CHUNK >= 2) ? half * CHUNK : 0;
+      const bool idle_half = !alt && (BN / CHUNK < 2) && half == 1; // a single chunk: the second warp only arrives
       // (in a multi-convolution launch the residual may still be in the making: its dependency is awaited by the
       // producer warp, which the accumulator wait below orders before us -- so no early fetch there)
       const bool res_first = res_vec && !idle_half && n0 + c_first + CHUNK <= p.cout;
@@ -830,9 +848,9 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
         uint32_t res_cur[CHUNK / 2];
 #pragma unroll
         for (int j = 0; j < CHUNK / 2; ++j) res_cur[j] = res_next[j];
-        if (res_vec && c0 + STEP < BN && n0 + c0 + STEP + CHUNK <= p.cout) {
+        if (res_vec && c0 + step_rt < BN && n0 + c0 + step_rt + CHUNK <= p.cout) {
 #pragma unroll
-          for (int j = 0; j < CHUNK / 16; ++j) hn_ldg256(p.res + res_off + n0 + c0 + STEP + 16 * j, &res_next[8 * j]);
+          for (int j = 0; j < CHUNK / 16; ++j) hn_ldg256(p.res + res_off + n0 + c0 + step_rt + 16 * j, &res_next[8 * j]);
         }
         const int cbase = n0 + c0;
         if (!FAST && split) {
@@ -1045,7 +1063,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
         }
       } else {
 #pragma unroll 1
-        for (int c0 = c_first; c0 < c_end; c0 += STEP) {
+        for (int c0 = c_first; c0 < c_end; c0 += step_rt) {
           uint32_t acc[CHUNK];
           chunk_body(c0, acc, false);
         }
@@ -1057,7 +1075,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       if (!split) {
         hn_tc_fence_before();
         __syncwarp();
-        if (lane == 0) hn_mbar_arrive(&tmem_empty[buf]);
+        if (lane < (alt ? 2 : 1)) hn_mbar_arrive(&tmem_empty[buf]);
       }
       if (deps != nullptr && finalize) {                  // this (m, n) output tile is in global memory: tell the consumers
         __threadfence();
@@ -1345,6 +1363,15 @@ bool patch_enabled() {          // HN_CONV_PATCH=1|0: patch tiles for the reside
   return v == 1;
 }
 
+int epi_alt_max_bn() {          // HN_EPI_ALT=<bn>: widest single-N-tile layer whose epilogue warps take alternate tiles
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HN_EPI_ALT");
+    v = e ? atoi(e) : 64;      // measured: layer1 66.6 -> 53.2 us, whole step +2.4 %; wider tiles are MMA-bound (no change)
+  }
+  return v;
+}
+
 int split_min_kb() {            // experiment knob: HN_SPLIT_MIN_KB (k-blocks a layer needs before split-K is considered)
   static int v = -1;
   if (v < 0) {
@@ -1615,6 +1642,8 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
       p.sk_ld = d->cout_pad;
     }
   }
+  p.epi_alt = (!force_bn && p.n_tiles == 1 && p.splits == 1 && !(d->debug & 32768) &&
+               ((d->debug & 65536) || bn <= epi_alt_max_bn())) ? 1 : 0;
   CUtensorMap& ta = out->ta;
   CUtensorMap& tb = out->tb;
   if (stem) {

@@ -116,6 +116,38 @@ def test_conv_patch_tiles(ops, shape):
     assert torch.equal(outs[0], outs[1]), "patch and flattened tiles accumulate the same products in the same order"
 
 
+@pytest.mark.parametrize("shape", [(2, 60, 70, 64, 64, 0), (2, 50, 68, 256, 256, 0), (3, 40, 50, 128, 128, 0), (4, 100, 136, 256, 5, 1)])
+def test_conv_epilogue_alternate_tiles(ops, shape):
+    """The two epilogue warps of a TMEM lane quarter either split the column chunks of one tile or take alternate tiles
+    (default for single-N-tile layers up to 64 columns; debug bit 16 forces it, bit 15 forbids it): same values."""
+    n, h, w, cin, cout, rows_out = shape
+    g = torch.Generator().manual_seed(h + w + cout)
+    x = rand(g, n, cin, h, w).to(DEV)
+    wt = rand(g, cout, cin, 3, 3, scale=(cin * 9) ** -0.5).to(DEV)
+    scale = (0.5 + torch.rand(cout, generator=g)).to(DEV)
+    shift = (0.3 * torch.randn(cout, generator=g)).to(DEV)
+    ref = F.conv2d(x, wt, None, padding=1) * scale[None, :, None, None] + shift[None, :, None, None]
+    outs = []
+    for debug in (65536, 32768):
+        if rows_out:
+            buf = torch.zeros(n, h * w, 8, device=DEV)
+            ops.conv2d(ops.Act.from_nchw(x, 1), ops.pack_conv_weight(wt), cout=cout, ksize=3, scale=scale, shift=shift,
+                       out_f32=buf, out_rows_per_image=h * w, out_row_offset=0, debug=debug)
+            torch.cuda.synchronize()
+            got = buf[..., :cout].reshape(n, h, w, cout).permute(0, 3, 1, 2)
+            torch.testing.assert_close(got, ref, rtol=2e-3, atol=2e-3)
+            outs.append(buf.clone())
+        else:
+            idn = rand(g, n, cout, h, w).to(DEV) if debug == 65536 else idn
+            out = ops.Act(n, h, w, cout, 1, DEV)
+            ops.conv2d(ops.Act.from_nchw(x, 1), ops.pack_conv_weight(wt), cout=cout, ksize=3, scale=scale, shift=shift, relu=True,
+                       res=ops.Act.from_nchw(idn, 1), res_mode=1, out=out, debug=debug)
+            torch.cuda.synchronize()
+            close_bf16(out.to_nchw(), F.relu(ref + idn), f"alternate tiles debug={debug}")
+            outs.append(out.t.clone())
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_conv_residual_phase_copy_and_geometry_remap(ops):
     """BasicBlock tail: conv + scale/shift + identity + ReLU, written twice (plain halo-2 and phase-split)."""
     g = torch.Generator().manual_seed(7)
