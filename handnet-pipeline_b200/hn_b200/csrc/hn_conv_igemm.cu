@@ -367,7 +367,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
               uint8_t* sa = a_ring + a_stage * uni_stride;
               const bool b_pending = w_ == early_item && step - s_begin < early_b;   // armed and B issued before the wait
               if (!b_pending) hn_mbar_expect_tx(&a_full[a_stage], (uint32_t)uni_stage_bytes);
-              if (p.stem_tpr > 0) hn_tma_load_4d(sa, &tm_a, &a_full[a_stage], 0, st_ox, 2 * (st_oy + cc), st_n);
+              if (p.stem_tpr > 0) hn_tma_load_4d(sa, &tm_a, &a_full[a_stage], 0, st_ox, st_oy + cc, st_n);
               else if (p.uni_a_rank4) hn_tma_load_4d(sa, &tm_a, &a_full[a_stage], 0, m0 + shift, cc, info >> 24);
               else hn_tma_load_3d(sa, &tm_a, &a_full[a_stage], cc * BLOCK_K, m0 + shift, info >> 24);
               if (!b_pending) hn_tma_load_4d(sa + p.uni_a_bytes, &tm_b, &a_full[a_stage], 0, n0, cc, (info >> 8) & 255);
@@ -503,15 +503,11 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
           hn_tc_fence_after();
           if (hn_elect_one()) {
             if (p.stem_tpr > 0) {
-              // direct stem: four [128 x 64 B] SWIZZLE_64B tiles (kernel rows 4*step .. +3), two K=16 steps each; kernel
-              // rows 2j and 2j+1 meet the two 64-byte halves of weight k-block j
-              const uint64_t hi64 = (uint64_t(512 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(4) << 61);
-#pragma unroll
-              for (int rr = 0; rr < 4; ++rr) {
-                const uint64_t da = hi64 | (uint64_t)(sa + rr * (8192 >> 4));
-                const uint64_t db = desc_hi | (uint64_t)(sb + (rr >> 1) * B_SLOT_D + (rr & 1) * 4);
-                hn_umma_bf16(d_tmem, da, db, idesc, accumulate | (uint32_t)rr);
-                hn_umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
+              // direct stem: two [128 x 128 B] tiles (row pairs oy + 2*step, +1 = kernel rows 4*step .. +3) against the two
+              // weight k-blocks of the step
+              if (!(dbg_flags & 4)) {
+                hn_umma_bf16_x4(d_tmem, desc_hi | sa, desc_hi | sb, idesc, accumulate);
+                hn_umma_bf16_x4(d_tmem, desc_hi | (sa + (uint32_t)((BLOCK_M * BLOCK_K * 2) >> 4)), desc_hi | (sb + B_SLOT_D), idesc, 1u);
               }
             } else if (!(dbg_flags & 4)) {                     // (timing experiment: bit 2 skips the MMAs)
               hn_umma_bf16_x4(d_tmem, desc_hi | (sa + (units & 3) * uni_plane_d + ((units >> 2) & 15) * ROW_D),
@@ -1647,16 +1643,18 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
   CUtensorMap& ta = out->ta;
   CUtensorMap& tb = out->tb;
   if (stem) {
-    // Patch view of the zero-framed canvas [n][ph][pw][4ch] (8 bytes per pixel).  Kernel row r of output pixel (oy, ox) is
-    // the 8 pixels x 4 channels = 32 elements (64 bytes) starting at frame pixel (2*oy + r, 2*ox):
-    //   dim0 32 elements | dim1 ox (two pixels = 16 bytes: the rows of consecutive ox overlap) | dim2 frame row | dim3 image
-    // box {32, 128, 4, 1} = four [128 output pixels][64 bytes] tiles, one per kernel row, SWIZZLE_64B: two k-blocks of
-    // the GEMM per k-step (a k-block = two kernel rows = 64 elements).
-    const cuuint64_t pw = (cuuint64_t)d->stem_pitch_w, ph = (cuuint64_t)d->stem_pitch_h;
-    const cuuint64_t dims[4] = {32, (cuuint64_t)d->w, ph, (cuuint64_t)d->n};
-    const cuuint64_t strides[3] = {16, pw * 8, ph * pw * 8};
-    const cuuint32_t box[4] = {32, BLOCK_M, 4, 1};
-    int rc = make_map(&ta, d->in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    // Patch view of the zero-framed canvas.  The frame stores its rows in PAIRS, [n][ph/2][pw][2 rows][4 ch] (16 bytes per
+    // column), so that kernel rows 2j and 2j+1 of output pixel (oy, ox) -- 8 pixels x 2 rows x 4 channels = 64 elements
+    // -- are ONE contiguous 128-byte run starting at row pair oy + j, column 2*ox:
+    //   dim0 64 elements | dim1 ox (two columns = 32 bytes: the runs of consecutive ox overlap) | dim2 row pair | dim3 image
+    // box {64, 128, 2, 1} = two ordinary [128 output pixels][128 bytes] SWIZZLE_128B tiles = two k-blocks of the GEMM per
+    // k-step.  (Until round 1 session 3 the frame was row-major and a kernel row a 64-byte run: SWIZZLE_64B tiles, twice
+    // the TMA row requests and operand reads at about half the rate -- tools/stem_ablation.py.)
+    const cuuint64_t pw = (cuuint64_t)d->stem_pitch_w, ph2 = (cuuint64_t)d->stem_pitch_h / 2;
+    const cuuint64_t dims[4] = {64, (cuuint64_t)d->w, ph2, (cuuint64_t)d->n};
+    const cuuint64_t strides[3] = {32, pw * 16, ph2 * pw * 16};
+    const cuuint32_t box[4] = {64, BLOCK_M, 2, 1};
+    int rc = make_map(&ta, d->in, 4, dims, strides, box);
     if (rc) return rc;
   } else if (uni && p.uni_a_rank4) {
     // 1x1 with two chunks per k-step: dims (64 channels, rows, chunks, phases); the box puts the two chunk planes one

@@ -70,7 +70,8 @@ pack_nhwc4_kernel(const float* __restrict__ src, int n, int c, int h, int w, Cha
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = (map.c[j] >= 0) ? __ldg(src + ((size_t)img * c + map.c[j]) * hw + rem) : 0.f;
-    frame[((size_t)img * pitch_h + y + pad_top) * pitch_w + x + pad_left] =
+    const int fy = y + pad_top;               // frame rows are stored in pairs: [pitch_h / 2][pitch_w][2 rows][4 ch]
+    frame[(((size_t)img * (pitch_h >> 1) + (fy >> 1)) * pitch_w + x + pad_left) * 2 + (fy & 1)] =
         make_uint2(hn_pack_bf16(v[0], v[1]), hn_pack_bf16(v[2], v[3]));
   }
 }

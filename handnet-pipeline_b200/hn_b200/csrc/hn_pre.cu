@@ -17,6 +17,7 @@ struct PreParams {
   float scale_y[PRE_MAX_IMAGES], scale_x[PRE_MAX_IMAGES];   // in / out as fp32, per image
   int canvas_h, canvas_w, batch_offset;
   int pad_top, pad_left, pitch_h, pitch_w;   // the canvas sits at (pad_top, pad_left) of a [pitch_h][pitch_w] pixel frame
+  int paired;                                // frame rows stored in pairs: [pitch_h/2][pitch_w][2 rows][4 ch] (direct stem)
 };
 
 __device__ __forceinline__ void bilinear_axis(int o, int in, float scale, int& i0, int& i1, float& l0, float& l1) {
@@ -127,7 +128,10 @@ __global__ void __launch_bounds__(512) preprocess_rows_kernel(const PreParams p,
   const float scale_x = p.scale_x[b];
   const float* q1 = staged + pitch;
   const float* q2 = staged + 2 * pitch;
-  uint2* dst_row = canvas + ((size_t)(p.batch_offset + b) * p.pitch_h + y + p.pad_top) * p.pitch_w + p.pad_left;
+  // row-major frame: pixel x of frame row fy at [fy][x]; paired frame (direct stem): at [fy / 2][x][fy & 1]
+  const int fy = y + p.pad_top, xs = p.paired ? 2 : 1;
+  uint2* dst_row = p.paired ? canvas + (((size_t)(p.batch_offset + b) * (p.pitch_h >> 1) + (fy >> 1)) * p.pitch_w + p.pad_left) * 2 + (fy & 1)
+                            : canvas + ((size_t)(p.batch_offset + b) * p.pitch_h + fy) * p.pitch_w + p.pad_left;
   const int x_live = live ? ow : 0;
 #pragma unroll 2
   for (int x = threadIdx.x; x < p.canvas_w; x += blockDim.x) {
@@ -142,7 +146,7 @@ __global__ void __launch_bounds__(512) preprocess_rows_kernel(const PreParams p,
       o.x = hn_pack_bf16((t0 - m0) * s0, (t1 - m1) * s1);
       o.y = hn_pack_bf16((t2 - m2) * s2, 0.f);
     }
-    dst_row[x] = o;
+    dst_row[x * xs] = o;
   }
 }
 
@@ -150,24 +154,24 @@ __global__ void __launch_bounds__(512) preprocess_rows_kernel(const PreParams p,
 // Stem patches as GEMM rows.  K is laid out as 8 kernel rows x 8 pixels x C channels: row r (r < 7) of the 7x7
 // window, pixels x = 2*ox - 4 .. 2*ox + 3 (the first one is outside the 7-wide window and meets a zero weight),
 // so that every 16-byte output chunk is a contiguous, aligned piece of one input row.  r = 7 is zero padding.
-// bf16 canvas (4 channels/pixel): k = r*32 + px*4 + ch, K = 256; one thread = 2 pixels = 16 bytes.
+// bf16 canvas (4 channels/pixel): k = j*64 + px*8 + rr*4 + ch with r = 2*j + rr (the direct stem's order: a k-block is
+// two kernel rows interleaved per pixel), K = 256; one thread = one pixel of two rows = 16 bytes.
 __global__ void __launch_bounds__(256)
 im2col_rgb_kernel(const uint2* __restrict__ in, int h, int w, int oh, int ow, uint4* __restrict__ out) {
-  // thread -> (output pixel, r, q): 32 threads per output pixel, consecutive threads write consecutive 16 B
+  // thread -> (output pixel, j, px): 32 threads per output pixel, consecutive threads write consecutive 16 B.  K order of
+  // the direct stem: k = j*64 + px*8 + rr*4 + ch, kernel row r = 2*j + rr (r = 7 is zero padding)
   const int lane32 = threadIdx.x & 31;
   const int pix_in_block = threadIdx.x >> 5;
   const int ox = blockIdx.x * 8 + pix_in_block;
   const int oy = blockIdx.y;
   const int img = blockIdx.z;
   if (ox >= ow) return;
-  const int r = lane32 >> 2, q = lane32 & 3;
-  const int iy = 2 * oy - 3 + r;
-  const int ix0 = 2 * ox - 4 + 2 * q;
+  const int j = lane32 >> 3, px = lane32 & 7;
+  const int iy0 = 2 * oy - 3 + 2 * j, ix = 2 * ox - 4 + px;
   uint2 a = make_uint2(0u, 0u), b = make_uint2(0u, 0u);
-  if (r < 7 && iy >= 0 && iy < h) {
-    const uint2* row = in + ((size_t)img * h + iy) * w;
-    if (ix0 >= 0 && ix0 < w) a = __ldg(row + ix0);
-    if (ix0 + 1 >= 0 && ix0 + 1 < w) b = __ldg(row + ix0 + 1);
+  if (ix >= 0 && ix < w) {
+    if (iy0 >= 0 && iy0 < h) a = __ldg(in + ((size_t)img * h + iy0) * w + ix);
+    if (j < 3 && iy0 + 1 >= 0 && iy0 + 1 < h) b = __ldg(in + ((size_t)img * h + iy0 + 1) * w + ix);
   }
   out[(((size_t)img * oh + oy) * ow + ox) * 32 + lane32] = make_uint4(a.x, a.y, b.x, b.y);
 }
@@ -275,12 +279,17 @@ groupnorm_relu_kernel(uint4* __restrict__ x, int h, int w, int c, int halo, cons
 
 }  // namespace
 
+static int preprocess_impl(const float* const* images_host, const int* in_h_host, const int* in_w_host,
+                           const int* out_h_host, const int* out_w_host, int batch, const float* mean3_host,
+                           const float* std3_host, void* canvas_bf16, int canvas_h, int canvas_w, int pad_top, int pad_left,
+                           int pitch_h, int pitch_w, int paired, void* stream);
+
 extern "C" int hn_preprocess_resize_pad(const float* const* images_host, const int* in_h_host, const int* in_w_host,
                                         const int* out_h_host, const int* out_w_host, int batch,
                                         const float* mean3_host, const float* std3_host, void* canvas_bf16,
                                         int canvas_h, int canvas_w, void* stream) {
-  return hn_preprocess_resize_pad_framed(images_host, in_h_host, in_w_host, out_h_host, out_w_host, batch, mean3_host,
-                                         std3_host, canvas_bf16, canvas_h, canvas_w, 0, 0, canvas_h, canvas_w, stream);
+  return preprocess_impl(images_host, in_h_host, in_w_host, out_h_host, out_w_host, batch, mean3_host, std3_host, canvas_bf16,
+                         canvas_h, canvas_w, 0, 0, canvas_h, canvas_w, 0, stream);
 }
 
 extern "C" int hn_preprocess_resize_pad_framed(const float* const* images_host, const int* in_h_host,
@@ -288,6 +297,15 @@ extern "C" int hn_preprocess_resize_pad_framed(const float* const* images_host, 
                                                int batch, const float* mean3_host, const float* std3_host,
                                                void* canvas_bf16, int canvas_h, int canvas_w, int pad_top, int pad_left,
                                                int pitch_h, int pitch_w, void* stream) {
+  return preprocess_impl(images_host, in_h_host, in_w_host, out_h_host, out_w_host, batch, mean3_host, std3_host, canvas_bf16,
+                         canvas_h, canvas_w, pad_top, pad_left, pitch_h, pitch_w, 1, stream);
+}
+
+static int preprocess_impl(const float* const* images_host, const int* in_h_host, const int* in_w_host,
+                           const int* out_h_host, const int* out_w_host, int batch, const float* mean3_host,
+                           const float* std3_host, void* canvas_bf16, int canvas_h, int canvas_w, int pad_top, int pad_left,
+                           int pitch_h, int pitch_w, int paired, void* stream) {
+  HN_REQUIRE(!paired || pitch_h % 2 == 0, "hn_preprocess_resize_pad_framed: the frame height must be even (rows are stored in pairs)");
   HN_REQUIRE(images_host && in_h_host && in_w_host && out_h_host && out_w_host && canvas_bf16 && mean3_host && std3_host,
              "hn_preprocess_resize_pad: null pointer");
   HN_REQUIRE(batch > 0 && canvas_h > 0 && canvas_w > 0, "hn_preprocess_resize_pad: empty batch or canvas");
@@ -322,6 +340,7 @@ extern "C" int hn_preprocess_resize_pad_framed(const float* const* images_host, 
     p.pad_left = pad_left;
     p.pitch_h = pitch_h;
     p.pitch_w = pitch_w;
+    p.paired = paired;
     p.batch_offset = b0;
     int max_w = 0;
     for (int i = 0; i < nb; ++i) max_w = p.in_w[i] > max_w ? p.in_w[i] : max_w;
@@ -333,6 +352,7 @@ extern "C" int hn_preprocess_resize_pad_framed(const float* const* images_host, 
       preprocess_rows_kernel<<<dim3(1, canvas_h, nb), threads, staged_bytes, st>>>(p, reinterpret_cast<uint2*>(canvas_bf16),
                                                                                   pitch);
     } else {                                         // source rows too wide to stage: gather from global memory
+      HN_REQUIRE(!paired, "hn_preprocess_resize_pad_framed: source rows wider than %d pixels are not supported", 48 * 1024 / 12);
       dim3 grid(hn_div_up(hn_div_up(canvas_w, 4), 256), canvas_h, nb);
       preprocess_kernel<<<grid, 256, 0, st>>>(p, reinterpret_cast<uint2*>(canvas_bf16));
     }

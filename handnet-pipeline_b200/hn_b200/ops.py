@@ -61,18 +61,33 @@ class Act:
 
 
 class StemFrame:
-    """Zero-framed 4-channel bf16 canvas [n, hc+6, wc+8, 4] (canvas at row 3, column 4): input of the direct stem."""
+    """Zero-framed 4-channel bf16 canvas of the direct stem: logically [n, hc+6, wc+8, 4] with the canvas at row 3,
+    column 4; stored with its rows in PAIRS, t[n, (hc+6)/2, wc+8, 2, 4], so that two kernel rows of the 7x7 window over
+    8 pixels are one contiguous 128-byte run (hn_conv2d_bf16, stem_pitch_*)."""
 
     __slots__ = ("t", "n", "hc", "wc", "fh", "fw", "oh", "ow")
 
     def __init__(self, n: int, canvas_hw: Tuple[int, int], device="cuda"):
         self.n, (self.hc, self.wc) = n, canvas_hw
         self.fh, self.fw = canvas_hw[0] + 6, canvas_hw[1] + 8
+        assert self.fh % 2 == 0, "the stem frame stores its rows in pairs: canvas height must be even"
         self.oh, self.ow = canvas_hw[0] // 2, canvas_hw[1] // 2
-        self.t = torch.zeros((n, self.fh, self.fw, 4), dtype=BF16, device=device)
+        self.t = torch.zeros((n, self.fh // 2, self.fw, 2, 4), dtype=BF16, device=device)
+
+    def rows(self) -> torch.Tensor:
+        """Row-major COPY of the whole frame [n, fh, fw, 4]."""
+        return self.t.permute(0, 1, 3, 2, 4).reshape(self.n, self.fh, self.fw, 4)
 
     def canvas(self) -> torch.Tensor:
-        return self.t[:, 3:3 + self.hc, 4:4 + self.wc, :]
+        """Row-major COPY of the canvas rectangle [n, hc, wc, 4] (the storage is row-pair interleaved)."""
+        return self.rows()[:, 3:3 + self.hc, 4:4 + self.wc, :]
+
+    def set_canvas(self, x: torch.Tensor) -> "StemFrame":
+        """Write a row-major [n, hc, wc, 4] canvas into the frame (tests / tools; the kernels write it directly)."""
+        full = torch.zeros((self.n, self.fh, self.fw, 4), dtype=BF16, device=self.t.device)
+        full[:, 3:3 + self.hc, 4:4 + self.wc, :] = x.to(BF16)
+        self.t.copy_(full.view(self.n, self.fh // 2, 2, self.fw, 4).permute(0, 1, 3, 2, 4))
+        return self
 
 
 class PhaseAct:
@@ -134,13 +149,17 @@ def pack_conv_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None) -> t
 
 def pack_stem_weight(w: torch.Tensor, k_pad: int) -> torch.Tensor:
     """7x7 stem OIHW (cin = 3, 4 or 1) -> bf16 [cout_pad][k_pad] in the K order of hn_im2col_7x7s2 / the direct stem:
-    k = (r*8 + px)*C + ch with C = 4 (RGB or RGBD canvas) or 1 (depth); px = 0, r = 7 and (for RGB) ch = 3 carry zero
-    weights."""
+    C = 1 (depth): k = r*8 + px;  C = 4 (RGB or RGBD canvas): k = j*64 + px*8 + rr*4 + ch with kernel row r = 2j + rr;
+    px = 0, r = 7 and (for RGB) ch = 3 carry zero weights."""
     cout, cin, kh, kw = w.shape
     assert (kh, kw) == (7, 7) and (cin, k_pad) in ((3, 256), (4, 256), (1, 64))
     c = 4 if cin >= 3 else 1
     m = torch.zeros((cout, 8, 8, c), dtype=torch.float32, device=w.device)
     m[:, :7, 1:, :cin] = w.detach().float().permute(0, 2, 3, 1)
+    if c == 4:
+        # 4-channel canvas: a k-block is two kernel rows interleaved per pixel, k = j*64 + px*8 + rr*4 + ch (r = 2j + rr),
+        # the order in which the row-pair frame holds them contiguously
+        m = m.view(cout, 4, 2, 8, c).permute(0, 1, 3, 2, 4)
     out = torch.zeros((pad_cout(cout), k_pad), dtype=BF16, device=w.device)
     out[:cout] = m.reshape(cout, -1).to(BF16)
     return tile_k(out)
@@ -172,7 +191,8 @@ def preprocess(images: Sequence[torch.Tensor], out_sizes: Sequence[Tuple[int, in
                mean: Sequence[float], std: Sequence[float], canvas: Optional[torch.Tensor] = None,
                frame: Optional[torch.Tensor] = None) -> torch.Tensor:
     """T1.  images: list of fp32 [3,H,W] CUDA tensors -> bf16 canvas [B, Hc, Wc, 4]; or, with `frame` (bf16
-    [B, Hc+6, Wc+8, 4], zero outside the canvas), into the canvas rectangle at (3, 4) of the frame."""
+    StemFrame.t: rows in pairs, [B, (Hc+6)/2, Wc+8, 2, 4], zero outside the canvas), into the canvas rectangle at (3, 4)
+    of the frame."""
     b = len(images)
     imgs = []
     for im in images:
@@ -192,7 +212,7 @@ def preprocess(images: Sequence[torch.Tensor], out_sizes: Sequence[Tuple[int, in
     s3 = (C.c_float * 3)(*[float(v) for v in std])
     if frame is not None:
         fh, fw = stem_frame_hw(canvas_hw)
-        assert frame.dtype == BF16 and tuple(frame.shape) == (b, fh, fw, 4) and frame.is_contiguous()
+        assert frame.dtype == BF16 and tuple(frame.shape) == (b, fh // 2, fw, 2, 4) and frame.is_contiguous()
         check(_lib.load().hn_preprocess_resize_pad_framed(ptrs, ih, iw, oh, ow, b, m3, s3, frame.data_ptr(), canvas_hw[0],
                                                           canvas_hw[1], STEM_PAD_TOP, STEM_PAD_LEFT, fh, fw, stream_ptr()),
               "hn_preprocess_resize_pad_framed")

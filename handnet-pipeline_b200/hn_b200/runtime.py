@@ -199,7 +199,7 @@ class FCOSPlan:
         self.batch, self.canvas_hw = B, canvas_hw
         # zero-framed canvas: the stem convolution gathers its 7x7 patches straight from it (no im2col buffer)
         self.frame = ops.StemFrame(B, (hc, wc), device)
-        self.canvas = self.frame.canvas()
+        self.canvas = self.frame.t            # (device handle for the chain launcher; read pixels with frame.canvas())
         h1, w1 = hc // 2, wc // 2
         self.stem = Act(B, h1, w1, 64, 0, device)
         sizes = [(hc // 4, wc // 4, 64), (hc // 8, wc // 8, 128), (hc // 16, wc // 16, 256), (hc // 32, wc // 32, 512)]

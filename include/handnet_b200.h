@@ -52,9 +52,10 @@ int hn_preprocess_resize_pad(const float* const* images_host, const int* in_h_ho
                              const int* out_h_host, const int* out_w_host, int batch, const float* mean3_host,
                              const float* std3_host, void* canvas_bf16, int canvas_h, int canvas_w, void* stream);
 
-/* Same, but the canvas is the sub-rectangle at (pad_top, pad_left) of a larger frame bf16 [batch][pitch_h][pitch_w][4]
- * whose remaining pixels are not touched (the caller keeps them zero): the zero-padded input of hn_conv2d_bf16's
- * direct 7x7 stem (stem_pitch_*). */
+/* Same, but the canvas is the sub-rectangle at (pad_top, pad_left) of a larger frame of pitch_h x pitch_w pixels whose
+ * remaining pixels are not touched (the caller keeps them zero): the zero-padded input of hn_conv2d_bf16's direct 7x7
+ * stem (stem_pitch_*).  The frame stores its rows in PAIRS, bf16 [batch][pitch_h / 2][pitch_w][2][4]: frame pixel
+ * (fy, fx) lives at [fy / 2][fx][fy & 1] (pitch_h even). */
 int hn_preprocess_resize_pad_framed(const float* const* images_host, const int* in_h_host, const int* in_w_host,
                                     const int* out_h_host, const int* out_w_host, int batch, const float* mean3_host,
                                     const float* std3_host, void* canvas_bf16, int canvas_h, int canvas_w, int pad_top,
@@ -117,10 +118,12 @@ typedef struct hn_conv_desc {
    * epilogue warp into trace[3][2048][2] (int64) -- see tools/conv_trace.py. */
   void* trace;
   /* Direct 7x7 stride-2 pad-3 stem over a 4-channel canvas (no im2col buffer).  0 = ordinary convolution.  Otherwise
-   * `in` is bf16 [n][stem_pitch_h][stem_pitch_w][4], all zero except the canvas at row 3, column 4 (stem_pitch_h >=
-   * 2*h + 6 and even, stem_pitch_w >= 2*w + 8); (h, w) are the OUTPUT sizes, kh = kw = 1, cin = 256, halo_in = 0, and
-   * the weights are pack_stem_weight's K = 8 kernel rows x 8 pixels x 4 channels (k-block major like every weight).
-   * TMA gathers the patch rows straight from the canvas with an overlapping-stride tensor map. */
+   * `in` is the row-pair frame bf16 [n][stem_pitch_h / 2][stem_pitch_w][2][4] (frame pixel (fy, fx) at [fy / 2][fx][fy & 1]),
+   * all zero except the canvas at row 3, column 4 (stem_pitch_h >= 2*h + 6 and even, stem_pitch_w >= 2*w + 8); (h, w)
+   * are the OUTPUT sizes, kh = kw = 1, cin = 256, halo_in = 0, and the weights are pack_stem_weight's K = 4 kernel-row
+   * pairs x 8 pixels x 2 rows x 4 channels (k-block major like every weight): a k-block of an output pixel is one
+   * contiguous 128-byte run of the frame.  TMA gathers the runs straight from the frame with an overlapping-stride
+   * tensor map. */
   int stem_pitch_h, stem_pitch_w;
 } hn_conv_desc;
 int hn_conv2d_bf16(const hn_conv_desc* desc, void* stream);
@@ -150,8 +153,9 @@ int hn_conv_multi_set_trace(void* buf);
 int hn_ingest_frames(const void* bgr_u8, const void* depth_u16, int n, int h, int w, float* rgb_out, float* depth_out,
                      void* stream);
 
-/* fp32 NCHW images -> the zero-framed 4-channel bf16 canvas of the direct stem (hn_conv_desc.stem_pitch_*): frame pixel
- * (pad_top + y, pad_left + x), channel j = src channel chan_map4_host[j] (-1 = zero).  The RGBD A2J variant feeds its
+/* fp32 NCHW images -> the zero-framed 4-channel bf16 canvas of the direct stem (hn_conv_desc.stem_pitch_*; row-pair
+ * layout, see hn_preprocess_resize_pad_framed): frame pixel (pad_top + y, pad_left + x), channel j = src channel
+ * chan_map4_host[j] (-1 = zero).  The RGBD A2J variant feeds its
  * 4-channel crops this way with the reference's [2,1,0,3] reorder (handnet_pipeline.py:102) as the channel map. */
 int hn_pack_nhwc4_frame(const float* src, int n, int c, int h, int w, const int* chan_map4_host, void* frame_bf16,
                         int pad_top, int pad_left, int pitch_h, int pitch_w, void* stream);

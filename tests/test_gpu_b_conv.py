@@ -295,7 +295,7 @@ def test_stem_direct_from_framed_canvas(ops, n, h, w):
     x_nchw = canvas[..., :3].permute(0, 3, 1, 2).contiguous()
     conv = q(F.relu(F.conv2d(x_nchw, wt, stride=2, padding=3) * scale[None, :, None, None] + shift[None, :, None, None]))
     frame = ops.StemFrame(n, (h, w), DEV)
-    frame.canvas().copy_(canvas.to(torch.bfloat16))
+    frame.set_canvas(canvas.to(torch.bfloat16))
     wp = ops.pack_stem_weight(wt.cuda(), 256)
     stem = ops.Act(n, h // 2, w // 2, 64, 0, DEV)
     ops.conv2d(frame, wp, cout=64, ksize=1, scale=scale.cuda(), shift=shift.cuda(), relu=True, out=stem)

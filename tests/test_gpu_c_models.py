@@ -42,7 +42,7 @@ def test_fcos_heads_vs_oracle(fcos_small):
         _, f32 = fcos_oracle.fcos_forward(sd, imgs, 3, False, 256, 448, emulate_bf16=False, return_taps=True)
     pl = list(m._executor.plans.values())[0]
     # T1 is exact against the bf16-rounded transform
-    assert rel_to_max(pl.canvas[..., :3].permute(0, 3, 1, 2), emu["canvas"].to(torch.bfloat16)) < 2 ** -7
+    assert rel_to_max(pl.frame.canvas()[..., :3].permute(0, 3, 1, 2), emu["canvas"].to(torch.bfloat16)) < 2 ** -7
     for i in range(3):
         assert rel_to_max(pl.p[i].to_nchw(), emu["p"][i]) < 3e-2          # bf16 path vs bf16-emulating oracle
     for k in ("cls_logits", "bbox_regression", "bbox_ctrness", "hand_lr"):

@@ -50,7 +50,7 @@ def test_pack_nhwc4_frame_exact(ops):
     ref = x[:, [2, 1, 0, 3]].permute(0, 2, 3, 1).to(torch.bfloat16)
     assert torch.equal(fr.canvas(), ref)
     # the frame around the canvas stays zero
-    t = fr.t.clone()
+    t = fr.rows().clone()
     t[:, 3:23, 4:40] = 0
     assert t.abs().sum() == 0
     ops.pack_nhwc4_frame(x, (0, -1, 4, -1), fr)          # -1: zero channel

@@ -10,7 +10,7 @@ from hn_b200.runtime import STEM_K_RGB
 B, hc, wc = 8, 800, 1088
 g = torch.Generator().manual_seed(0)
 frame = ops.StemFrame(B, (hc, wc), "cuda")
-frame.canvas().copy_(torch.randn(B, hc, wc, 4, generator=g).to(torch.bfloat16))
+frame.set_canvas(torch.randn(B, hc, wc, 4, generator=g).cuda())
 w = ops.pack_stem_weight((torch.randn(64, 3, 7, 7, generator=g) * 0.05).cuda(), STEM_K_RGB)
 scale = torch.ones(64, device="cuda"); shift = torch.zeros(64, device="cuda")
 out = ops.Act(B, hc // 2, wc // 2, 64, 0, "cuda")

@@ -17,7 +17,7 @@ if mode == "ones":
 else:
     wt = torch.randn(64, 3, 7, 7) * 0.05
 frame = ops.StemFrame(n, (h, w), "cuda")
-frame.canvas().copy_(canvas.to(torch.bfloat16))
+frame.set_canvas(canvas.to(torch.bfloat16))
 wp = ops.pack_stem_weight(wt.cuda(), 256)
 stem = ops.Act(n, h // 2, w // 2, 64, 0, "cuda")
 ops.conv2d(frame, wp, cout=64, ksize=1, out=stem)
@@ -29,7 +29,7 @@ print("got[0,0,:4,:8]\n", got[0, 0, :4, :8]); print("ref[0,0,:4,:8]\n", ref[0, 0
 if mode == "time":
     n, h, w = 8, 800, 1088
     frame = ops.StemFrame(n, (h, w), "cuda")
-    frame.canvas().normal_()
+    frame.set_canvas(torch.randn(frame.n, frame.hc, frame.wc, 4, device="cuda"))
     stem = ops.Act(n, h // 2, w // 2, 64, 0, "cuda")
     sc = torch.ones(64, device="cuda"); sh = torch.zeros(64, device="cuda")
     trace = torch.zeros(3 * 2048 * 2, dtype=torch.int64, device="cuda")
