@@ -135,9 +135,10 @@ def test_weight_tiling_round_trip_and_layout():
     assert p.shape == (16, 9 * 64) and p.dtype == torch.bfloat16
     flat = ops.untile_k(p)
     assert torch.equal(flat[:5], wt.permute(0, 2, 3, 1).reshape(5, -1).to(torch.bfloat16)) and flat[5:].abs().sum() == 0
-    # stem weights: K = 8 kernel rows x 8 pixels x 4 channels, px = 0 / r = 7 / ch = 3 are zero
+    # stem weights: K = 4 kernel-row pairs x 8 pixels x 2 rows x 4 channels (the order of the row-pair frame);
+    # px = 0 / r = 7 / ch = 3 are zero
     ws = torch.randn(64, 3, 7, 7, generator=g)
-    s = ops.untile_k(ops.pack_stem_weight(ws, 256)).view(64, 8, 8, 4)
+    s = ops.untile_k(ops.pack_stem_weight(ws, 256)).view(64, 4, 8, 2, 4).permute(0, 1, 3, 2, 4).reshape(64, 8, 8, 4)
     assert s[:, 7].abs().sum() == 0 and s[:, :, 0].abs().sum() == 0 and s[..., 3].abs().sum() == 0
     assert torch.equal(s[:, :7, 1:, :3], ws.permute(0, 2, 3, 1).to(torch.bfloat16))
     assert ops.stem_frame_hw((800, 1088)) == (806, 1096)
