@@ -303,12 +303,31 @@ def main():
         # conversion ros_demo.py does with numpy on the host (x/255, BGR->RGB, mm/1000) runs on the device.
         bgr_pin = (rgb_h.flip(1).permute(0, 2, 3, 1) * 255).round().to(torch.uint8).contiguous().pin_memory()
         mm_pin = (depth_h[:, 0] * 1000).round().clamp(0, 32767).to(torch.int16).contiguous().pin_memory()
+        def upload_u8():                       # same double-buffered upload as the fp32 loop above
+            with torch.cuda.stream(copy_stream):
+                b8 = bgr_pin.to(dev, non_blocking=True)
+                m16 = mm_pin.to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return b8, m16, ev
+
+        def api_step_u8(cur):
+            b8, m16, ev = cur
+            main = torch.cuda.current_stream()
+            main.wait_event(ev)
+            b8.record_stream(main)
+            m16.record_stream(main)
+            nxt = upload_u8()
+            net.forward_frames(b8, m16)
+            return nxt
+
+        cur8 = upload_u8()
         for _ in range(3):
-            net.forward_frames(bgr_pin, mm_pin)
+            cur8 = api_step_u8(cur8)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            net.forward_frames(bgr_pin, mm_pin)
+            cur8 = api_step_u8(cur8)
         barrier()
         t = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
         if world > 1:
