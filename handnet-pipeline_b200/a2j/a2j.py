@@ -100,6 +100,7 @@ class A2JModel(runtime.WeightsEpochMixin, nn.Module):
 
     def __init__(self, num_classes, crop_height, crop_width, is_3D=True, is_RGBD=False, spatial_factor=0.5):
         super().__init__()
+        self._install_weight_hooks()
         self.is_3D = is_3D
         self.num_joints = num_classes
         self.Backbone = ResNetBackBone(channel_in=4 if is_RGBD else 1)
@@ -119,6 +120,13 @@ class A2JModel(runtime.WeightsEpochMixin, nn.Module):
             raise RuntimeError("A2JModel (B200 build) needs CUDA tensors: there is no CPU fallback")
         if not self.is_3D:
             raise NotImplementedError("is_3D=False is not used by the pipeline and not built")
+        if self.training and not getattr(self, "_warned_training", False):
+            # the reference's load_pretrained_a2j returns the model without .eval() (handnet_pipeline.py:26-41): a caller
+            # that never calls .eval() gets batch-statistics BatchNorm there; only eval-mode BN is built here
+            import warnings
+            warnings.warn("A2JModel (B200 build) always applies eval-mode BatchNorm (running statistics); call .eval() "
+                          "to get the same behaviour from the reference", stacklevel=2)
+            self._warned_training = True
         return self._executor.forward_device(x.float().contiguous())
 
     def head_outputs(self, x: torch.Tensor):

@@ -186,6 +186,7 @@ class FCOS(runtime.WeightsEpochMixin, nn.Module):
                  center_sampling_radius: float = 1.5, score_thresh: float = 0.2, nms_thresh: float = 0.6,
                  detections_per_img: int = 100, topk_candidates: int = 1000):
         super().__init__()
+        self._install_weight_hooks()
         self.ext = ext
         self.backbone = _BackboneWithFPN()
         if anchor_generator is None:

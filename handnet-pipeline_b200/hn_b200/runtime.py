@@ -26,14 +26,33 @@ def _sig(tensors: Sequence[torch.Tensor]):
 
 
 class WeightsEpochMixin:
-    """O(1) change detection for the derived (packed bf16) weights and captured CUDA graphs: the epoch is bumped by
-    ``load_state_dict`` and by ``.to()/.cuda()/.half()`` (``_apply``).  Code that edits parameters in place must call
-    ``invalidate_weights()`` itself.  (Fingerprinting all ~650 tensors on every call cost 0.7 ms per step.)"""
+    """Change detection for the derived (packed bf16) weights and captured CUDA graphs.
+
+    ``weights_epoch()`` changes whenever the module's parameters or buffers may have changed:
+      * ``load_state_dict`` -- on the module itself or on any PARENT (``HandNet.load_state_dict``,
+        ``A2JModelLightning.load_state_dict``): a load-state-dict post hook fires in nested loads too, where the
+        children's ``load_state_dict`` override never runs;
+      * ``.to()/.cuda()/.half()`` (``_apply``, reached through the parent's recursion as well);
+      * in-place edits (``p.mul_()``, ``p.data.copy_()``, optimiser steps): the sum of the tensors' version counters
+        is part of the epoch (~70 us for the ~650 tensors of both nets; fingerprinting pointers and shapes as well cost
+        0.7 ms per step and is not needed: replacing a Parameter object goes through ``_apply`` or ``load_state_dict``).
+    """
 
     _w_epoch = 0
+    _w_tensors = None
+
+    def _install_weight_hooks(self):
+        # nn.Module.__init__ has run: hooks can be registered (called from the subclasses' __init__)
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_weights())
 
     def invalidate_weights(self):
         self._w_epoch = self._w_epoch + 1
+        self._w_tensors = None
+
+    def weights_epoch(self):
+        if self._w_tensors is None:
+            self._w_tensors = list(self.parameters()) + list(self.buffers())
+        return (self._w_epoch, sum(t._version for t in self._w_tensors))
 
     def load_state_dict(self, *args, **kwargs):
         out = super().load_state_dict(*args, **kwargs)
@@ -232,7 +251,7 @@ class FCOSExecutor:
         self.plans: Dict[Tuple, FCOSPlan] = {}
 
     def weights(self) -> FCOSWeights:
-        sig = self.model._w_epoch
+        sig = self.model.weights_epoch()
         if sig != self._wsig or self.wts is None:
             self.wts = FCOSWeights(self.model)
             self._wsig = sig
@@ -486,7 +505,7 @@ class A2JExecutor:
         self.plans: Dict[Tuple, A2JPlan] = {}
 
     def weights(self) -> A2JWeights:
-        sig = self.model._w_epoch
+        sig = self.model.weights_epoch()
         if sig != self._wsig or self.wts is None:
             self.wts = A2JWeights(self.model)
             self._wsig = sig
@@ -620,7 +639,7 @@ RECORD_WIDTH = 21 * 3 + 4 + 1      # joints, crop box, has_hand  
 def weights_token(net) -> int:
     """Epochs of the two models (see WeightsEpochMixin): changes when weights are reloaded or moved."""
     pose = net.a2j.a2j if hasattr(net.a2j, "a2j") else net.a2j
-    return (net.detector._w_epoch, pose._w_epoch)
+    return (net.detector.weights_epoch(), pose.weights_epoch())
 
 
 def pack_records(joints: torch.Tensor, crops: torch.Tensor, has_hand: torch.Tensor) -> torch.Tensor:

@@ -142,3 +142,95 @@ def test_weight_tiling_round_trip_and_layout():
     assert s[:, 7].abs().sum() == 0 and s[:, :, 0].abs().sum() == 0 and s[..., 3].abs().sum() == 0
     assert torch.equal(s[:, :7, 1:, :3], ws.permute(0, 2, 3, 1).to(torch.bfloat16))
     assert ops.stem_frame_hw((800, 1088)) == (806, 1096)
+
+
+# ------------------------------------------------------------------------------------------------
+# weight-change detection and checkpoint loading (handnet_pipeline.py:14-52)
+# ------------------------------------------------------------------------------------------------
+class _Args:
+    pretrained_fcos = ""
+    pretrained_a2j = ""
+
+
+def _quiet_handnet(*a, **k):
+    import contextlib
+    import io
+    from handnet_pipeline.handnet_pipeline import HandNet
+    with contextlib.redirect_stdout(io.StringIO()):
+        return HandNet(*a, **k)
+
+
+def test_weights_epoch_changes_on_nested_load_inplace_edit_and_apply():
+    """nn.Module.load_state_dict on a PARENT recurses through _load_from_state_dict, so the children's own
+    load_state_dict override never runs: the epoch must still change (post hook), and so must it for in-place edits."""
+    from hn_b200.runtime import weights_token
+    net = _quiet_handnet(_Args(), num_classes=3).eval()
+    t0 = weights_token(net)
+    assert weights_token(net) == t0                       # stable while nothing changes
+    net.load_state_dict(net.state_dict())                 # nested load through the parent
+    t1 = weights_token(net)
+    assert t1[0] != t0[0] and t1[1] != t0[1]
+    with torch.no_grad():
+        net.detector.head.classification_head.cls_logits.bias.mul_(1.0)      # in-place edit of one parameter
+    t2 = weights_token(net)
+    assert t2[0] != t1[0] and t2[1] == t1[1]
+    with torch.inference_mode():
+        net.a2j.regressionModel.output.bias.add_(0.0)
+    t3 = weights_token(net)
+    assert t3[1] != t2[1] and t3[0] == t2[0]
+    net.double()                                          # _apply reaches the children through the parent
+    t4 = weights_token(net)
+    assert t4[0] != t3[0] and t4[1] != t3[1]
+    net.a2j.load_state_dict(net.a2j.state_dict())         # direct load on the child
+    assert weights_token(net)[1] != t4[1]
+
+
+def test_handnet_reloads_fcos_and_a2j_checkpoints(tmp_path):
+    """HandNet(args, reload_detector=True, reload_a2j=True): {"model": state_dict} files, strict=False
+    (handnet_pipeline.py:17-19, 36-38)."""
+    fsd = synth.fcos_state_dict(3, False, seed=3)
+    asd = synth.a2j_state_dict(seed=4)
+    args = _Args()
+    args.pretrained_fcos = str(tmp_path / "fcos_10.pth")
+    args.pretrained_a2j = str(tmp_path / "a2j_25.pth")
+    extra = dict(fsd)
+    extra["not.in.the.model"] = torch.zeros(1)             # strict=False tolerates foreign keys
+    torch.save({"model": extra, "epoch": 10}, args.pretrained_fcos)
+    torch.save({"model": asd}, args.pretrained_a2j)
+    net = _quiet_handnet(args, reload_detector=True, num_classes=3, reload_a2j=True)
+    got = net.detector.state_dict()
+    for k, v in fsd.items():
+        assert torch.equal(got[k], v), k
+    got = net.a2j.state_dict()
+    for k, v in asd.items():
+        assert torch.equal(got[k], v), k
+    assert all(not p.requires_grad for p in net.parameters())
+    assert not net.detector.training
+
+
+@pytest.mark.parametrize("rgbd", [False, True])
+def test_handnet_loads_lightning_ckpt(tmp_path, rgbd):
+    """A Lightning-style .ckpt ({"state_dict": {"a2j.<key>": ...}, "hyper_parameters": {...}}) through
+    load_pretrained_a2j -> A2JModelLightning.load_from_checkpoint (handnet_pipeline.py:28-29, a2j/a2j.py:252-283),
+    for the depth-only and the RGBD (4-channel stem) variants."""
+    from a2j.a2j import A2JModel, A2JModelLightning
+    src = A2JModel(21, 176, 176, is_RGBD=rgbd)
+    g = torch.Generator().manual_seed(11)
+    sd = {k: (torch.randn(v.shape, generator=g) * 0.05 if v.dtype.is_floating_point else v.clone())
+          for k, v in src.state_dict().items()}
+    ckpt = {"state_dict": {"a2j." + k: v for k, v in sd.items()},
+            "hyper_parameters": {"num_classes": 21, "crop_height": 176, "crop_width": 176, "is_3D": True, "is_RGBD": rgbd,
+                                 "spatial_factor": 0.5, "display_freq": 5000, "output_dir": "models/a2j"},
+            "epoch": 3, "global_step": 1234, "pytorch-lightning_version": "1.5.10"}
+    args = _Args()
+    args.pretrained_a2j = str(tmp_path / ("rgbd.ckpt" if rgbd else "depth.ckpt"))
+    torch.save(ckpt, args.pretrained_a2j)
+    net = _quiet_handnet(args, num_classes=3, reload_a2j=True, RGBD=rgbd)
+    assert isinstance(net.a2j, A2JModelLightning) and net.RGBD == rgbd
+    pose = net._pose_net()
+    assert pose.Backbone.channel_in == (4 if rgbd else 1)
+    assert pose.Backbone.model.conv1.weight.shape[1] == (4 if rgbd else 3)
+    got = pose.state_dict()
+    for k, v in sd.items():
+        assert torch.equal(got[k], v), k
+    assert not net.a2j.training

@@ -1,6 +1,6 @@
 // Micro-benchmark: how fast can ONE thread issue tcgen05.mma (SS operands, M=128, K=16) back to back, as a function
 // of N and of how often it commits?  Operands are whatever is in shared memory; only timing matters.
-// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mma_issue_bench mma_issue_bench.cu
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared -o /tmp/mma_issue_bench tools/mma_issue_bench.cu
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>

@@ -1,6 +1,6 @@
 // Micro-benchmark 2: tcgen05 issue / synchronisation costs with a CONVERGED issuing warp (elect.sync), the way the
 // conv kernel issues since round 1 session 2.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mma_issue_bench2 mma_issue_bench2.cu
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared -o /tmp/mma_issue_bench2 tools/mma_issue_bench2.cu
 // (a) back-to-back tcgen05.mma (SS, M=128, K=16) for N = 16..256: cycles per MMA
 // (b) ring of D stages: [wait full] 4*KG MMAs, commit(empty); a second warp turns empty -> full (no data movement):
 //     cycles per k-step as a function of D, N and KG  (the pipeline skeleton of the conv kernel)

@@ -1,7 +1,7 @@
 // Micro-benchmark 3: does a tcgen05.mma (SS, M=128, K=16, bf16) cost more when every MMA reads FRESH operands, the way
 // the conv kernel's resident-weights path issues them (9 taps x 4 k-slices per 64-channel chunk: A tile of kernel row t
 // read from row sx on, weight tile of tap t*3+sx), than in the steady loop of mma_issue_bench2 (one A tile, one B tile)?
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mma_issue_bench3 mma_issue_bench3.cu
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared -o /tmp/mma_issue_bench3 tools/mma_issue_bench3.cu
 // variant bits: 1 = a different weight tile per tap, 2 = A start shifted by sx rows (128 B), 4 = a different A tile per
 // kernel row.  0 = everything reads the same A and B tile.
 #include <cstdio>

@@ -1,5 +1,5 @@
 // Micro-benchmark 3: cost of the synchronisation instructions around tcgen05.mma, issued from a converged warp.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o sync_cost_bench sync_cost_bench.cu
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared -o /tmp/sync_cost_bench tools/sync_cost_bench.cu
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>

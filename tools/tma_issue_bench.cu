@@ -1,5 +1,5 @@
 // Micro-benchmark 5: how fast can one elected lane issue TMA tile loads, as a function of the box size?
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tma_issue_bench tma_issue_bench.cu -lcuda
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared -o /tmp/tma_issue_bench tools/tma_issue_bench.cu -lcuda
 // A producer warp issues `iters` loads of a [ROWS x 64] bf16 box (SWIZZLE_128B) into a ring of 8 slots; a consumer warp
 // frees each slot as soon as it has landed.  Reports cycles per load in steady state (source: a 64 MiB matrix, so
 // most of it comes from L2 after the first pass) and the cycles the issuing thread spends per load when the ring

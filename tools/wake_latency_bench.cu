@@ -1,5 +1,5 @@
 // Micro-benchmark 4: how long after an mbarrier phase completes does a thread blocked in mbarrier.try_wait resume?
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o wake_latency_bench wake_latency_bench.cu
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared -o /tmp/wake_latency_bench tools/wake_latency_bench.cu
 // Ping-pong between warp 1 (signals bar[0], waits bar[1]) and warp 2 (waits bar[0], signals bar[1]); the signal of
 // warp 1 is a plain mbarrier.arrive (mode 0), a tcgen05.commit with nothing pending (mode 1), or a tcgen05.commit
 // behind MMAS tcgen05.mma (N=64) (mode 2).  Reports cycles per round trip.
