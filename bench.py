@@ -1,26 +1,33 @@
 #!/usr/bin/env python
 """Benchmark of the detect -> crop -> A2J-pose path (BASELINE.json metric: E2E frames/s, 640x480).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config NAME]
 
 One "step" = the whole HandNet path over one batch of FRAMES_PER_GPU synthetic 640x480 RGB + depth frames per
 GPU (BASELINE.json configs[2]: batch 64 over 8 GPUs = 8 frames per GPU; weak scaling).  Random-init weights of
 the reference architectures (hn_b200.synth), head biases set so that a realistic handful of boxes passes the
 hard-coded 0.7 cut and every frame yields a hand crop (candidate / kept counts are reported in `config`).
 
-  value      frames/s, inputs resident in HBM, the step replayed as one CUDA graph, timed with CUDA events
-  e2e        frames/s through HandNet's public API path with HOST (pinned) inputs: H2D of the frames and depth
-             maps and D2H of joints / crops / hit mask inside the timed region
-  roofline   the dominant kernel (tcgen05 shifted-GEMM conv): algorithmic conv FLOPs of one step / the summed
-             device time of its launches in one step (CUDA events on the launch stream, GPU kept saturated)
+  value      frames/s, inputs resident in HBM, timed with CUDA events around EXACTLY K steps submitted through the
+             product's two-stage pipeline (runtime.GraphedHandNet: the pose stage of step i runs under the detect stage
+             of step i+1; both stages are CUDA-graph replays); a 136 MiB buffer (> the 126 MB L2) is rewritten between
+             steps INSIDE the timed region.  `sequential` (extra key) is the same with one step at a time.
+  e2e        frames/s through HandNet's public API (submit / result) with HOST (pinned) inputs: H2D of the frames and
+             depth maps and D2H of joints / crops / hit mask inside the timed region, host wall clock
+  roofline   the dominant kernel (tcgen05 shifted-GEMM conv, ~87 % of a step): algorithmic conv FLOPs of ALL its launches
+             in one step / their summed device time (CUDA events on the launch stream, launches back to back behind a
+             spin kernel), against the SUSTAINED measured bf16 peak; the best launch shape is a sub-key
   cpu_baseline  the oracle (a torch-CPU restatement of the reference, oracle/) timed on this box's host cores
+  extra_configs  BASELINE.json configs 1, 2, 4 and 5 (A2J on the CPU, FCOS alone, post-process stress, 1080p strong
+             scaling): `--config NAME` runs one of them alone
 
 `--impl reference` times that CPU restatement alone (the reference itself is Python that needs packages which
-are not installed on the box) on a bounded sample per step.
+are not installed on the box) on the same 8-frame batch per step.
 """
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
 import subprocess
@@ -36,11 +43,12 @@ import torch  # noqa: E402
 
 FRAMES_PER_GPU = 8
 IMG_H, IMG_W = 480, 640
+HD_H, HD_W = 1080, 1920
+HD_FRAMES = 256                         # BASELINE.json configs[4]: global batch of the 1080p sweep (strong scaling)
 CLS_BIAS = [-6.0, -6.0, -1.5]          # ~50 candidates, ~30 kept boxes per frame
 METRIC = "e2e_frames_per_s_640x480_detect_plus_a2j_pose"
 UNIT = "frames/s"
-# algorithmic conv FLOPs (2*MAC over the padded canvas), SURVEY.md 8d / BASELINE.md section 3
-FLOP_PER_FRAME = 318.99e9 + 12.55e9
+L2_FLUSH_BYTES = 136 << 20             # > 126 MB L2
 
 
 def load_peaks():
@@ -48,8 +56,8 @@ def load_peaks():
     if os.path.exists(p):
         d = json.load(open(p))
         return {"bf16_sustained": d.get("bf16_tflops_sustained", 1400.0), "bf16_burst": d.get("bf16_tflops", 1590.0),
-                "hbm": d.get("hbm_gbs", 6650.0), "source": "measured"}
-    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "source": "fallback"}
+                "hbm": d.get("hbm_gbs", 6650.0), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler:
@@ -74,13 +82,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self, window=None):
+    def summary(self, window=None):
         """Summary of the samples taken inside `window` = (t0, t1) wall-clock seconds (all samples if None)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if window is None or (window[0] <= t <= window[1] + 0.06)]
+        rows = [r for t, r in list(self.rows) if window is None or (window[0] <= t <= window[1] + 0.06)]
         sm = sorted(int(float(r[0])) for r in rows if r and r[0].replace(".", "").isdigit())
         mx = [int(float(r[1])) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         reasons = set()
@@ -92,6 +98,11 @@ class ClockSampler:
         load = sm[len(sm) // 2:] if sm else []
         return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
 
 
 def build_net(device):
@@ -111,24 +122,27 @@ def build_net(device):
     return net.to(device)
 
 
-def synthetic_frames(seed: int, n: int):
+def synthetic_frames(seed: int, n: int, h: int = IMG_H, w: int = IMG_W):
     g = torch.Generator().manual_seed(seed)
-    rgb = torch.rand(n, 3, IMG_H, IMG_W, generator=g)
-    depth = torch.rand(n, 1, IMG_H, IMG_W, generator=g) * 1.5
+    rgb = torch.rand(n, 3, h, w, generator=g)
+    depth = torch.rand(n, 1, h, w, generator=g) * 1.5
     return rgb, depth
 
 
 # --------------------------------------------------------------------------------------------------
-def cpu_oracle_frames_per_s(frames: int, repeats: int, threads: int):
-    """The reference's CPU path, restated (oracle/), on `frames` synthetic VGA frames per repeat."""
+# CPU legs (the only places that execute oracle/)
+# --------------------------------------------------------------------------------------------------
+def cpu_oracle(frames: int, repeats: int, threads: int):
+    """The reference's CPU path, restated (oracle/): (frames/s of the whole path on `frames` synthetic VGA frames per pass,
+    A2J batch-1 forwards/s = BASELINE.json configs[0])."""
     from hn_b200 import synth
-    from oracle import handnet_oracle
+    from oracle import a2j_oracle, handnet_oracle
     torch.set_num_threads(threads)
     fsd = synth.fcos_state_dict(3, False, seed=0, cls_bias=CLS_BIAS)
     asd = synth.a2j_state_dict(seed=1)
     rgb, depth = synthetic_frames(100, frames)
     imgs = list(rgb)
-    times = []
+    times, a2j_times = [], []
     with torch.inference_mode():
         for r in range(repeats + 1):
             t = time.perf_counter()
@@ -136,12 +150,19 @@ def cpu_oracle_frames_per_s(frames: int, repeats: int, threads: int):
             dt = time.perf_counter() - t
             if r > 0:                      # first pass is the warm-up
                 times.append(dt)
+        x = torch.rand(1, 1, 176, 176, generator=torch.Generator().manual_seed(0)) * 1.5
+        for r in range(6):
+            t = time.perf_counter()
+            a2j_oracle.a2j_forward(asd, x)
+            if r > 0:
+                a2j_times.append(time.perf_counter() - t)
     times.sort()
-    return frames / times[len(times) // 2]
+    a2j_times.sort()
+    return frames / times[len(times) // 2], 1.0 / a2j_times[len(a2j_times) // 2]
 
 
 def run_reference(args):
-    """--impl reference: CPU restatement of the reference path, all host threads, bounded sample per step."""
+    """--impl reference: CPU restatement of the reference path, all host threads, the same 8-frame batch per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -151,11 +172,11 @@ def run_reference(args):
     torch.set_num_threads(threads)
     fsd = synth.fcos_state_dict(3, False, seed=0, cls_bias=CLS_BIAS)
     asd = synth.a2j_state_dict(seed=1)
-    sample = 2                                           # frames per step (bounded sample of the 8-frame batch)
-    rgb, depth = synthetic_frames(100, sample)
+    sample = FRAMES_PER_GPU
+    rgb, depth = synthetic_frames(1000, sample)
     imgs = list(rgb)
     with torch.inference_mode():
-        for _ in range(args.warmup):
+        for _ in range(min(args.warmup, 2)):             # a CPU pass is ~1.5 s: two warm-up passes are plenty
             handnet_oracle.handnet_forward(fsd, asd, imgs, depth, num_classes=3)
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -166,9 +187,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"e2e_handnet_{IMG_W}x{IMG_H}_b{FRAMES_PER_GPU}_per_gpu", "frames_per_step": sample,
-                   "sample": f"{sample} of the {FRAMES_PER_GPU} frames of a step", "canvas": "800x1088",
-                   "note": "reference is Python with uninstalled deps on the box; timed its CPU restatement (oracle/)"},
+        "config": {"workload": f"e2e_handnet_{IMG_W}x{IMG_H}_b{FRAMES_PER_GPU}_per_gpu", "frames_per_gpu": FRAMES_PER_GPU,
+                   "frames_per_step": sample, "canvas": "800x1088",
+                   "note": "reference is Python with uninstalled deps on the box; timed its CPU restatement (oracle/) on "
+                           "rank 0's host cores, one 8-frame batch per step"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} VGA frames per step, {args.steps} steps"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -177,238 +199,182 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
+# GPU legs
+# --------------------------------------------------------------------------------------------------
+class Ctx:
+    """Process-wide state of a GPU run."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_
-        dist = dist_
-        dist.init_process_group("nccl", device_id=dev)
-    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    def __init__(self, args):
+        self.args = args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist_
+            self.dist = dist_
+            dist_.init_process_group("nccl", device_id=self.dev)
+        self.l2_flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=self.dev)
 
-    from hn_b200 import ops
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms: float) -> float:
+        t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def pipelined_steps(ctx: Ctx, step, n: int, flush: bool, post=None, sequential: bool = False) -> float:
+    """Device time (ms, CUDA events) of EXACTLY n steps through the two-stage pipeline, barrier + synchronize on both
+    sides.  The L2 flush runs on the detect stream between steps, inside the timed region."""
+    cur = torch.cuda.current_stream()
+    step.drain()
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(cur)
+    step.det_stream.wait_event(e0)
+    for i in range(n):
+        if flush:
+            with torch.cuda.stream(step.det_stream):
+                ctx.l2_flush.zero_()
+        t = step.submit(post=post)
+        if sequential:
+            step.result(t)
+        elif step.n_submitted - step.n_collected >= step.RING - 1:
+            step.result(step.n_collected)          # the host stays at most RING-1 steps ahead
+    step.drain()
+    cur.wait_stream(step.det_stream)
+    cur.wait_stream(step.pose_stream)
+    e1.record(cur)
+    ctx.barrier()
+    return e0.elapsed_time(e1)
+
+
+def run_main(ctx: Ctx):
+    args = ctx.args
+    from hn_b200 import ops, parallel
     from hn_b200.runtime import GraphedHandNet, conv_flops_per_step, conv_profile
-
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
     net = build_net(dev)
     B = FRAMES_PER_GPU
     rgb_h, depth_h = synthetic_frames(1000 + rank, B)
     rgb_pin, depth_pin = rgb_h.pin_memory(), depth_h.pin_memory()
     step = GraphedHandNet(net, B, IMG_H, IMG_W, use_graph=not args.no_graph)
-    step.load_inputs(rgb_pin, depth_pin)
-    from hn_b200 import parallel
-    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    step.load_inputs(rgb_pin.to(dev), depth_pin.to(dev))
+    gathered = torch.empty((world * B, 68), dtype=torch.float32, device=dev) if world > 1 else None
 
-    def one_step():
-        out = step.run()
-        if world > 1:     # per-frame records to every rank (rank 0 consumes them): the path's only collective
-            parallel.gather_records(step.records(), B)
-        return out
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def post(rec):        # per-frame records to every rank (rank 0 consumes them): the path's only collective
+        parallel.gather_records(rec, B, out=gathered)
+    post_fn = post if world > 1 else None
 
     with torch.inference_mode():
-        sampler = ClockSampler(local_rank)            # started early: nvidia-smi needs a moment before its first sample
+        sampler = ClockSampler(ctx.local_rank)            # started early: nvidia-smi needs a moment before its first sample
         sampler.start()
-        for _ in range(args.warmup):
-            one_step()
-        barrier()
+        pipelined_steps(ctx, step, args.warmup, True, post_fn)
         # ---------------- device-resident throughput (`value`) ----------------
-        launches0 = ops.launch_count()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        barrier()
         t_wall0 = time.time()
         torch.cuda.nvtx.range_push("hn_timed")
-        for s, e in evs:
-            l2_flush.zero_()                 # flush L2 between timed iterations (outside the events)
-            s.record()
-            one_step()
-            e.record()
-        barrier()
+        total_ms = ctx.max_over_ranks(pipelined_steps(ctx, step, args.steps, True, post_fn))
         torch.cuda.nvtx.range_pop()
         t_wall1 = time.time()
-        launches = (ops.launch_count() - launches0) // args.steps if args.no_graph else step.launches_per_step
-        dev_ms = sum(s.elapsed_time(e) for s, e in evs)
-        t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+        launches = step.launches_per_step
         value = world * B * args.steps / (total_ms * 1e-3)
+        # one step at a time (round-1 definition of `value`): the pose stage is exposed
+        seq_ms = ctx.max_over_ranks(pipelined_steps(ctx, step, args.steps, True, post_fn, sequential=True))
+        sequential = {"value": world * B * args.steps / (seq_ms * 1e-3), "unit": UNIT, "ms_per_step": seq_ms / args.steps,
+                      "note": "same steps, each collected before the next is submitted (no overlap of pose and detect stages)"}
+        counts = step.counts()
 
         # ---------------- end to end through the public API with host buffers (`e2e`) ----------------
-        # what a caller of the reference does (ros_demo.py:266-273): host frames -> .cuda() -> HandNet.forward ->
-        # joints on the host.  H2D of rgb + depth and the D2H read-back of the result records are inside.
-        # The caller double-buffers its uploads: the H2D copy of step i+1 is issued on a copy stream before step i is
-        # submitted, so the PCIe transfer overlaps the kernels.  Every step still uploads its own frames and reads
-        # its own results back.
-        copy_stream = torch.cuda.Stream(device=dev)
+        # what a caller of the reference does (ros_demo.py:266-273): host frames -> HandNet -> joints on the host.  The
+        # asynchronous form of the same call: submit() uploads the frames (H2D on a copy stream, double-buffered) and
+        # enqueues the step, result() waits for the records' D2H; two steps are kept in flight.
+        imgs_pin = list(rgb_pin.unbind(0))
 
-        def upload():
-            with torch.cuda.stream(copy_stream):
-                imgs = rgb_pin.to(dev, non_blocking=True)
-                dpt = depth_pin.to(dev, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-            return imgs, dpt, ev
+        def e2e_loop(submit, collect, n):
+            tickets = []
+            for _ in range(n):
+                tickets.append(submit())
+                if len(tickets) > 2:
+                    collect(tickets.pop(0))
+            while tickets:
+                collect(tickets.pop(0))
 
-        def api_step(cur):
-            imgs, dpt, ev = cur
-            main = torch.cuda.current_stream()
-            main.wait_event(ev)
-            imgs.record_stream(main)
-            dpt.record_stream(main)
-            nxt = upload()
-            final, depth_batch, crops = net(list(imgs.unbind(0)), depth_images=dpt)
-            if world > 1:
-                parallel.gather_records(net._steps[next(iter(net._steps))].records(), B)
-            return final, nxt
+        def timed_e2e(submit, collect):
+            e2e_loop(submit, collect, 3)
+            ctx.barrier()
+            t0 = time.perf_counter()
+            e2e_loop(submit, collect, args.steps)
+            ctx.barrier()
+            ms = ctx.max_over_ranks((time.perf_counter() - t0) * 1e3)          # host wall clock
+            return world * B * args.steps / (ms * 1e-3)
 
-        cur = upload()
-        for _ in range(3):
-            res, cur = api_step(cur)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            res, cur = api_step(cur)
-        barrier()
-        e2e_ms = (time.perf_counter() - t0) * 1e3          # host wall clock: the call returns host results
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_value = world * B * args.steps / (float(t.item()) * 1e-3)
+            # multi-GPU: the records of every step are all-gathered as well (parallel.submit_sharded does this for a global
+            # batch; here each rank keeps its own 8 frames, so the all-gather hook is attached directly)
+            e2e_value = timed_e2e(lambda: net.submit_records(imgs_pin, depth_pin, post), net.result_records)
+        else:
+            e2e_value = timed_e2e(lambda: net.submit(imgs_pin, depth_pin), net.result)
         h2d = rgb_pin.numel() * 4 + depth_pin.numel() * 4
         d2h = step.d2h_bytes
 
         # ---------------- the same with the frames as the camera delivers them (SURVEY 8f rank 2) ----------------
-        # uint8 BGR + uint16 millimetres on the host -> HandNet.forward_frames: H2D of 5 bytes per pixel, the
+        # uint8 BGR + uint16 millimetres on the host -> HandNet.submit_frames: H2D of 5 bytes per pixel, the
         # conversion ros_demo.py does with numpy on the host (x/255, BGR->RGB, mm/1000) runs on the device.
         bgr_pin = (rgb_h.flip(1).permute(0, 2, 3, 1) * 255).round().to(torch.uint8).contiguous().pin_memory()
         mm_pin = (depth_h[:, 0] * 1000).round().clamp(0, 32767).to(torch.int16).contiguous().pin_memory()
-        def upload_u8():                       # same double-buffered upload as the fp32 loop above
-            with torch.cuda.stream(copy_stream):
-                b8 = bgr_pin.to(dev, non_blocking=True)
-                m16 = mm_pin.to(dev, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-            return b8, m16, ev
-
-        def api_step_u8(cur):
-            b8, m16, ev = cur
-            main = torch.cuda.current_stream()
-            main.wait_event(ev)
-            b8.record_stream(main)
-            m16.record_stream(main)
-            nxt = upload_u8()
-            net.forward_frames(b8, m16)
-            return nxt
-
-        cur8 = upload_u8()
-        for _ in range(3):
-            cur8 = api_step_u8(cur8)
-        barrier()
+        e2e_u8_value = timed_e2e(lambda: net.submit_frames(bgr_pin, mm_pin), net.result) if world == 1 else None
+        h2d_u8 = bgr_pin.numel() + mm_pin.numel() * 2
+        # synchronous public call (HandNet.forward, one step at a time): what an unmodified caller of the reference gets
+        ctx.barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            cur8 = api_step_u8(cur8)
-        barrier()
-        t = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_u8_value = world * B * args.steps / (float(t.item()) * 1e-3)
-        h2d_u8 = bgr_pin.numel() + mm_pin.numel() * 2
+            net(imgs_pin, depth_images=depth_pin)
+        ctx.barrier()
+        e2e_sync = world * B * args.steps / (ctx.max_over_ranks((time.perf_counter() - t0) * 1e3) * 1e-3)
         t_wall2 = time.time()
         # clocks / throttle reasons sampled DURING the device-timed region; if that region was too short for two
-        # samples (it lasts steps x ~4 ms), the window is extended over the e2e loops that follow it (same load)
-        clocks = sampler.stop((t_wall0, t_wall1))
+        # samples (it lasts steps x ~3 ms), the window is extended over the e2e loops that follow it (same load)
+        clocks = sampler.summary((t_wall0, t_wall1))
         clocks["window"] = "timed region"
         if (clocks.get("samples") or 0) < 2:
-            clocks = sampler.stop((t_wall0, t_wall2))
-            clocks["window"] = "timed region + e2e loops"
-
-        # ---------------- several steps in flight (extra; single GPU only) ----------------
-        # Three independent batches at a time, each with its own CUDA graph, buffer set (runtime.PLAN_SLOT) and stream:
-        # the latency-bound tail of one step (the A2J pose net keeps < 1/3 of the SMs busy) overlaps the detector of the
-        # next.  Same work per step, same results (checked); `value` above stays the one-step-at-a-time number.
-        pipelined = None
-        if world == 1 and not args.no_graph:
-            P = 3
-            psteps = [step] + [GraphedHandNet(net, B, IMG_H, IMG_W, slot=i) for i in range(1, P)]
-            pstreams = [torch.cuda.Stream(device=dev) for _ in range(P)]
-            for st_, s_ in zip(psteps, pstreams):
-                st_.load_inputs(rgb_pin, depth_pin)
-                with torch.cuda.stream(s_):
-                    for _ in range(3):
-                        st_.run()
-            torch.cuda.synchronize()
-            same = all(torch.equal(st_.records(), step.records()) for st_ in psteps)
-            main_s = torch.cuda.current_stream()
-            pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            pe0.record(main_s)
-            for s_ in pstreams:
-                s_.wait_event(pe0)
-            for i in range(args.steps):
-                with torch.cuda.stream(pstreams[i % P]):
-                    l2_flush.zero_()
-                    psteps[i % P].run()
-            for s_ in pstreams:
-                main_s.wait_stream(s_)
-            pe1.record(main_s)
-            torch.cuda.synchronize()
-            pms = pe0.elapsed_time(pe1)
-            pipelined = {"steps_in_flight": P, "value": B * args.steps / (pms * 1e-3), "unit": UNIT,
-                         "ms_per_step": pms / args.steps, "results_identical": bool(same)}
+            clocks = sampler.summary((t_wall0, t_wall2))
+            clocks["window"] = "timed region + sequential / e2e loops"
+        sampler.stop()
 
         # ---------------- roofline of the dominant kernel (rank 0) ----------------
         roof = None
-        counts = step.counts()
         if rank == 0:
-            peaks = load_peaks()
-            conv_ms, n_conv = conv_profile(step, repeats=3)
-            flops = conv_flops_per_step(step)
-            if os.environ.get("HN_CONV_TABLE"):
-                json.dump(step.last_conv_table, open(os.environ["HN_CONV_TABLE"], "w"))
-            # dominant launch shape: the 256->256 3x3 tower / FPN convs on the P3 level (16 + 1 launches per step)
-            tbl = step.last_conv_table
-            dom = [r for r in tbl if (r["cin"], r["cout"], r["k"], r["stride"]) == (256, 256, 3, 1)
-                   and r["h"] * r["w"] == max(x["h"] * x["w"] for x in tbl if (x["cin"], x["cout"], x["k"]) == (256, 256, 3))]
-            dom_ms = sum(r["ms"] for r in dom) / max(1, len(dom))
-            dom_flop = dom[0]["gflop"] * 1e9 if dom else 0.0
-            ach = dom_flop / (dom_ms * 1e-3) / 1e12 if dom else 0.0
-            ach_all = flops / (conv_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "conv_igemm_kernel<256> (tcgen05 shifted GEMM), 256->256 3x3 @100x136 x8 frames",
-                    "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
-                    # dram__bytes_read.sum + dram__bytes_write.sum of this launch, profiles/r01b_conv_igemm_full.txt
-                    "traffic": 77.4e6, "algorithmic_flops_per_launch": dom_flop, "launch_ms": dom_ms,
-                    "launches_per_step": len(dom), "step_share": dom_ms * len(dom) / (total_ms / args.steps),
-                    "peak_source": peaks["source"] + " sustained",
-                    "all_conv_launches": {"achieved": ach_all, "frac": ach_all / peaks["bf16_sustained"],
-                                          "launches_per_step": n_conv, "ms_per_step_serial": conv_ms,
-                                          "flops_per_step": flops}}
+            roof = conv_roofline(step, total_ms / args.steps, conv_profile, conv_flops_per_step)
+
+        extras = None
+        if rank == 0 and world == 1 and not args.no_extras:
+            extras = {"fcos_b8": run_fcos_b8(ctx, step), "post_stress": run_post_stress(ctx, net)}
+        hd = None
+        if not args.no_extras:
+            hd = run_hd1080(ctx, net, quick=True)
+            if extras is not None:
+                extras["hd1080"] = hd
+            elif rank == 0:
+                extras = {"hd1080": hd}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        fps = cpu_oracle_frames_per_s(frames=2, repeats=3, threads=threads)
+        fps, a2j_fps = cpu_oracle(frames=FRAMES_PER_GPU, repeats=3, threads=threads)
         cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "2 VGA frames per pass, median of 3 passes after 1 warm-up (oracle/: torch-CPU restatement)"}
+               "sample": f"{FRAMES_PER_GPU} VGA frames per pass (one step), median of 3 passes after 1 warm-up "
+                         "(oracle/: torch-CPU restatement)"}
+        if extras is not None:
+            extras["a2j_cpu"] = {"value": a2j_fps, "unit": "crops/s", "cores": threads,
+                                 "workload": "BASELINE.json configs[0]: A2J ResNet-50 forward, batch 1, 176x176, CPU oracle, "
+                                             "median of 5"}
 
     if rank == 0:
         line = {
@@ -417,22 +383,226 @@ def main():
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"e2e_handnet_{IMG_W}x{IMG_H}_b{B}_per_gpu", "frames_per_gpu": B,
                        "global_batch": world * B, "canvas": "800x1088", "parallelism": f"dp{world}",
-                       "l2": "256 MiB buffer written between timed steps", "cuda_graph": not args.no_graph,
+                       "l2": f"{L2_FLUSH_BYTES >> 20} MiB buffer rewritten between steps, inside the timed region",
+                       "cuda_graph": not args.no_graph,
+                       "pipeline": "two stages (detect | pose) on two streams, pose of step i under detect of step i+1",
                        "candidates_per_frame": counts["cand"], "kept_per_frame": counts["kept"],
                        "frames_with_hand": counts["hands"], "weights": "random-init (hn_b200.synth), head bias " + str(CLS_BIAS)},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "e2e_u8_ingest": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
-                              "api": "HandNet.forward_frames(uint8 BGR, uint16 mm)"},
-            "pipelined": pipelined,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "HandNet.submit / result (2 steps in flight), pinned host fp32 frames"},
+            "e2e_sync": {"value": e2e_sync, "unit": UNIT, "api": "HandNet.forward, one step at a time"},
+            "e2e_u8_ingest": None if e2e_u8_value is None else
+                             {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
+                              "api": "HandNet.submit_frames(uint8 BGR, uint16 mm) / result"},
+            "sequential": sequential,
             "gpu_launches": int(launches) * args.steps,
             "gpu_launches_per_step": int(launches),
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "extra_configs": extras,
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+
+
+def conv_roofline(step, step_ms, conv_profile, conv_flops_per_step):
+    """Whole-kernel roofline: every conv launch of one step.  The launches are timed back to back inside a step (behind a
+    spin kernel, at the clocks a long step settles at), so the denominator is the SUSTAINED measured bf16 peak."""
+    peaks = load_peaks()
+    conv_ms, n_conv = conv_profile(step, repeats=3)
+    flops = conv_flops_per_step(step)
+    tbl = step.last_conv_table
+    if os.environ.get("HN_CONV_TABLE"):
+        json.dump(tbl, open(os.environ["HN_CONV_TABLE"], "w"))
+    ach_all = flops / (conv_ms * 1e-3) / 1e12
+    # best launch shape: the 256->256 3x3 tower layers (one launch over P3+P4+P5)
+    dom = [r for r in tbl if (r["cin"], r["cout"], r["k"], r["stride"]) == (256, 256, 3, 1) and r.get("levels", 1) > 1]
+    if not dom:
+        big = max((x["h"] * x["w"] for x in tbl if (x["cin"], x["cout"], x["k"]) == (256, 256, 3)), default=0)
+        dom = [r for r in tbl if (r["cin"], r["cout"], r["k"], r["stride"]) == (256, 256, 3, 1) and r["h"] * r["w"] == big]
+    best = None
+    if dom:
+        dom_ms = sum(r["ms"] for r in dom) / len(dom)
+        dom_flop = dom[0]["gflop"] * 1e9
+        ach = dom_flop / (dom_ms * 1e-3) / 1e12
+        best = {"shape": "256->256 3x3, levels=%d, %dx%d x%d frames" % (dom[0].get("levels", 1), dom[0]["h"], dom[0]["w"], dom[0]["n"]),
+                "achieved": ach, "frac_of_sustained": ach / peaks["bf16_sustained"], "frac_of_burst": ach / peaks["bf16_burst"],
+                "algorithmic_flops_per_launch": dom_flop, "launch_ms": dom_ms, "launches_per_step": len(dom),
+                "step_share": dom_ms * len(dom) / step_ms}
+    # DRAM traffic of the dominant launch from a committed ncu capture, when there is one
+    traffic, traffic_src = None, None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r02*_conv_traffic.json"))):
+        try:
+            d = json.load(open(f))
+            traffic, traffic_src = float(d["dram_bytes_per_launch"]), os.path.relpath(f, ROOT)
+        except Exception:
+            pass
+    return {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 shifted GEMM): all %d conv launches of a step" % n_conv,
+            "achieved": ach_all, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach_all / peaks["bf16_sustained"],
+            "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": peaks["source"] + ", sustained figure: launches timed back to back inside a step",
+            "launches_per_step": n_conv, "ms_per_step_serial": conv_ms, "flops_per_step": flops,
+            "frac_of_burst": ach_all / peaks["bf16_burst"], "best_shape": best}
+
+
+def run_fcos_b8(ctx: Ctx, step):
+    """BASELINE.json configs[1]: FCOS forward + post-process (+ the crop kernel) alone, batch 8 x 640x480, one B200 = the
+    detect stage's graph replayed back to back."""
+    n = max(10, ctx.args.steps)
+    step.drain()
+    if step.g_det is None:
+        return None
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(step.det_stream):
+        for _ in range(3):
+            step.g_det.replay()
+        e0.record()
+        for _ in range(n):
+            ctx.l2_flush.zero_()
+            step.g_det.replay()
+        e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    return {"value": FRAMES_PER_GPU / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+            "workload": "BASELINE.json configs[1]: FCOS forward + post-process, batch 8 x 640x480, 1 GPU (L2 flush inside)"}
+
+
+def run_post_stress(ctx: Ctx, net):
+    """BASELINE.json configs[3]: ~10 000 candidates per frame through decode + score + select, batched NMS and gather
+    (fcos_utils/fcos.py:572-669), 8 frames.  Synthetic head tensors (hn_b200.synth.stress_head_tensors)."""
+    from hn_b200 import ops, synth
+    dev = ctx.dev
+    peaks = load_peaks()
+    lv = ops.Levels([(100, 136), (50, 68), (25, 34)], (800, 1088), (8, 16, 32))
+    B = FRAMES_PER_GPU
+    ho = {k: v.to(dev) for k, v in synth.stress_head_tensors(31, B, lv.locs, 3, -0.35).items()}
+    m = net.detector
+    ws_sel = torch.empty(int(ops._lib.load().hn_fcos_select_workspace_bytes(B, lv.locs)), dtype=torch.uint8, device=dev)
+    ws_nms = ops.nms_workspace(B, lv.locs, dev)
+    rh, rw = [480 / 800] * B, [640 / 1066] * B
+
+    def decode():
+        return ops.fcos_decode_select(ho["cls_logits"], ho["bbox_ctrness"], ho["bbox_regression"], 3, lv, m.score_cut, ws=ws_sel)
+
+    def nms(c):
+        return ops.nms_batched(c["box"], c["score"], c["label"], c["count"], m.nms_iou, m.nms_coord_trick_numel, ws=ws_nms)
+
+    def timeit(fn, reps=10):
+        for _ in range(2):
+            fn()
+        ts = []
+        for _ in range(reps):
+            ctx.l2_flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    cand = decode()
+    keep, kc = nms(cand)
+    t_dec = timeit(decode)
+    t_nms = timeit(lambda: nms(cand))
+
+    def whole():
+        c = decode()
+        k, n_ = nms(c)
+        ops.fcos_gather(k, n_, c, ho["hand_lr"], lv, rh, rw)
+    t_all = timeit(whole)
+    n8 = cand["count"].tolist()
+    pairs = sum(n * n / 2 for n in n8)
+    mask_bytes = sum(n * ((n + 63) // 64) * 8 for n in n8)
+    dec_bytes = B * lv.locs * (3 + 1 + 4) * 4 + sum(n8) * 28
+    return {"value": B / (t_all * 1e-3), "unit": UNIT, "ms_per_step": t_all,
+            "workload": "BASELINE.json configs[3]: decode + NMS + gather on synthetic head tensors, 8 frames",
+            "candidates_per_frame": n8, "kept_per_frame": kc.tolist(),
+            "decode_select": {"ms": t_dec, "algorithmic_bytes": dec_bytes, "gb_per_s": dec_bytes / (t_dec * 1e-3) / 1e9,
+                              "hbm_frac": dec_bytes / (t_dec * 1e-3) / 1e9 / peaks["hbm"]},
+            "nms": {"ms": t_nms, "pair_tests": pairs, "pair_tests_per_s": pairs / (t_nms * 1e-3),
+                    "bitmask_bytes_written_plus_read": 2 * mask_bytes,
+                    "hbm_frac_bitmask_definition": 2 * mask_bytes / (t_nms * 1e-3) / 1e9 / peaks["hbm"],
+                    "note": "SURVEY 8d: NMS is not bandwidth-bound at its algorithmic bytes; the fraction uses the bitmask "
+                            "traffic n*ceil(n/64)*8 B each way as the stated definition"}}
+
+
+def run_hd1080(ctx: Ctx, net, quick: bool):
+    """BASELINE.json configs[4]: 1920x1080 frames, GLOBAL batch 256 split over the ranks (strong scaling: 256 / 128 / 64 /
+    32 frames per GPU at 1 / 2 / 4 / 8 GPUs), each rank streaming its slice through the pipeline in steps of 8 frames;
+    one hand per frame (the reference keeps the first hand box, handnet_pipeline.py:84-85).  `quick` (the default run's extra
+    key) times one pass over the global batch after one warm-up step per rank."""
+    from hn_b200 import parallel
+    from hn_b200.runtime import GraphedHandNet
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    B = FRAMES_PER_GPU
+    begin, end = parallel.shard_range(HD_FRAMES, world, rank)
+    n_steps = (end - begin + B - 1) // B
+    rgb, depth = synthetic_frames(2000 + rank, B, HD_H, HD_W)
+    step = GraphedHandNet(net, B, HD_H, HD_W, use_graph=not ctx.args.no_graph, slot=1)
+    step.load_inputs(rgb.to(dev), depth.to(dev))
+    gathered = torch.empty((world * B, 68), dtype=torch.float32, device=dev) if world > 1 else None
+    post = (lambda rec: parallel.gather_records(rec, B, out=gathered)) if world > 1 else None
+    pipelined_steps(ctx, step, 3, True, post)
+    passes = 1 if quick else 3
+    ms = min(ctx.max_over_ranks(pipelined_steps(ctx, step, n_steps, True, post)) for _ in range(passes))
+    counts = step.counts()
+    del step
+    torch.cuda.empty_cache()
+    return {"value": HD_FRAMES / (ms * 1e-3), "unit": UNIT, "ms_per_global_batch": ms, "scaling": "strong",
+            "workload": "BASELINE.json configs[4]: 1920x1080, global batch 256 over %d GPU(s) = %d frames per GPU in steps of 8, "
+                        "canvas 768x1344, one hand per frame" % (world, end - begin),
+            "frames_with_hand": counts["hands"], "kept_per_frame": counts["kept"][:4]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--config", default="e2e", choices=["e2e", "a2j_cpu", "fcos_b8", "post_stress", "hd1080"],
+                    help="e2e (default, BASELINE.json configs[2] per-GPU slice, with the others as extra keys) or one of the "
+                         "other BASELINE.json configs alone")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra_configs legs")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.config == "a2j_cpu":
+        threads = os.cpu_count() or 1
+        _, a2j_fps = cpu_oracle(frames=1, repeats=1, threads=threads)
+        print(json.dumps({"config": "a2j_cpu", "value": a2j_fps, "unit": "crops/s", "cores": threads}), flush=True)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    ctx = Ctx(args)
+    try:
+        if args.config == "e2e":
+            run_main(ctx)
+        else:
+            with torch.inference_mode():
+                net = build_net(ctx.dev)
+                if args.config == "hd1080":
+                    out = run_hd1080(ctx, net, quick=False)
+                elif args.config == "post_stress":
+                    out = run_post_stress(ctx, net)
+                else:
+                    from hn_b200.runtime import GraphedHandNet
+                    step = GraphedHandNet(net, FRAMES_PER_GPU, IMG_H, IMG_W)
+                    rgb, depth = synthetic_frames(1000, FRAMES_PER_GPU)
+                    step.load_inputs(rgb.to(ctx.dev), depth.to(ctx.dev))
+                    pipelined_steps(ctx, step, 3, False)
+                    out = run_fcos_b8(ctx, step)
+            if ctx.rank == 0:
+                print(json.dumps({"config": args.config, "n_gpus": ctx.world, **out}), flush=True)
+    finally:
+        if ctx.world > 1:
+            ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

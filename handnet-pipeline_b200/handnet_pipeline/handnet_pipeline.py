@@ -69,18 +69,33 @@ class HandNet(nn.Module):
     def _pose_net(self) -> A2JModel:
         return self.a2j.a2j if isinstance(self.a2j, A2JModelLightning) else self.a2j
 
+    def detect_crop_device(self, images: List[torch.Tensor], depth_images: torch.Tensor, out=None):
+        """Detect stage: FCOS + post-process, then ONE kernel for hand selection, box padding, crop and nearest resize
+        (handnet_pipeline.py:74-102).  `out` = (crops [B,4] int64, has_hand [B] int32, depth_batch [B,C,176,176] fp32) to
+        write into (the pipeline's hand-off buffers).  Returns (det, crops, has_hand, depth_batch); no host sync."""
+        det = self.detector.forward_device(images)
+        depth = depth_images.float().contiguous()
+        if tuple(depth.shape[-2:]) != tuple(images[0].shape[-2:]):
+            # the reference clamps the padded box to the RGB image (handnet_pipeline.py:90-99) and slices the depth map with
+            # it; with different sizes its slicing semantics are not reproduced here
+            raise RuntimeError(f"depth images {tuple(depth.shape[-2:])} and RGB images {tuple(images[0].shape[-2:])} differ in size")
+        crops, has_hand, depth_batch = ops.select_crop_resize(det["boxes"], det["labels"], det["keep_count"],
+                                                              self.num_classes - 1, depth, CROP_SIZE, out=out)
+        runtime.mark("crop")
+        return det, crops, has_hand, depth_batch
+
+    def pose_device(self, depth_batch: torch.Tensor) -> torch.Tensor:
+        """Pose stage: A2J on the crops -> joints [B,21,3] on the device."""
+        if self.RGBD:
+            depth_batch = depth_batch[:, [2, 1, 0, 3]].contiguous()        # handnet_pipeline.py:102
+        return self._pose_net().forward_device(depth_batch)
+
     def forward_device(self, images: List[torch.Tensor], depth_images: torch.Tensor):
         """Everything on the device, no host sync.  Returns a dict with
         joints [B,21,3], has_hand [B] int32, crops [B,4] int64, depth_batch [B,C,176,176], and the dense
         detector output under 'det'."""
-        det = self.detector.forward_device(images)
-        depth = depth_images.float().contiguous()
-        crops, has_hand, depth_batch = ops.select_crop_resize(det["boxes"], det["labels"], det["keep_count"],
-                                                              self.num_classes - 1, depth, CROP_SIZE)
-        runtime.mark("crop")
-        if self.RGBD:
-            depth_batch = depth_batch[:, [2, 1, 0, 3]].contiguous()        # handnet_pipeline.py:102
-        joints = self._pose_net().forward_device(depth_batch)
+        det, crops, has_hand, depth_batch = self.detect_crop_device(images, depth_images)
+        joints = self.pose_device(depth_batch)
         return {"joints": joints, "has_hand": has_hand, "crops": crops, "depth_batch": depth_batch, "det": det}
 
     def _graphed(self, images, depth_images):
@@ -90,31 +105,37 @@ class HandNet(nn.Module):
         shp = tuple(images[0].shape)
         if any(tuple(im.shape) != shp for im in images) or tuple(depth_images.shape[-2:]) != shp[-2:]:
             return None
-        key = (len(images), shp[-2], shp[-1], int(depth_images.shape[1]), str(images[0].device))
+        dev = next(self.parameters()).device
+        return self._step_for(len(images), shp[-2], shp[-1], int(depth_images.shape[1]), dev)
+
+    def _step_for(self, b: int, h: int, w: int, depth_c: int, dev) -> "runtime.GraphedHandNet":
+        key = (b, h, w, depth_c, str(dev))
         if key not in self._steps:
-            self._steps[key] = runtime.GraphedHandNet(self, len(images), shp[-2], shp[-1], int(depth_images.shape[1]))
-        return self._steps[key]
+            self._steps[key] = runtime.GraphedHandNet(self, b, h, w, depth_c)
+        step = self._steps[key]
+        step.invalidate_if_weights_changed()
+        return step
 
     def forward_frames(self, bgr_u8: torch.Tensor, depth_u16: torch.Tensor):
         """The caller's frame ingest of ros_demo.py (:227-238, :266-267) on the device: camera frames as they arrive --
         uint8 BGR [B,H,W,3] and uint16 millimetres [B,H,W] (host or device tensors) -> ``forward``.  The host -> device
         copy moves 5 bytes per pixel instead of the 16 of fp32 RGB + depth; the conversion (x/255, RGB order, mm/1000) is
         bit-exact with the numpy expressions of the reference's caller."""
+        return self.result(self.submit_frames(bgr_u8, depth_u16))
+
+    def submit_frames(self, bgr_u8: torch.Tensor, depth_u16: torch.Tensor):
+        """Asynchronous ``forward_frames``: enqueue the step and return a ticket for ``result()``."""
         dev = next(self.parameters()).device
-        bgr = bgr_u8.to(dev, non_blocking=True).contiguous()
-        dpt = depth_u16.to(dev, non_blocking=True).contiguous()
-        if self.use_cuda_graph and not self.RGBD:
-            # convert straight into the static input buffers of the captured step (no fp32 staging copy)
-            b, h, w = int(bgr.shape[0]), int(bgr.shape[1]), int(bgr.shape[2])
-            key = (b, h, w, 1, str(dev))
-            if key not in self._steps:
-                self._steps[key] = runtime.GraphedHandNet(self, b, h, w, 1)
-            step = self._steps[key]
-            step.invalidate_if_weights_changed()
-            ops.ingest_frames(bgr, dpt, rgb_out=step.rgb, depth_out=step.depth)
-            return self._run_loaded(step, b, step.depth)
-        rgb, depth = ops.ingest_frames(bgr, dpt)
-        return self.forward(list(rgb.unbind(0)), depth_images=depth)
+        if not self.use_cuda_graph or self.RGBD:
+            bgr = bgr_u8.to(dev, non_blocking=True).contiguous()
+            dpt = depth_u16.to(dev, non_blocking=True).contiguous()
+            rgb, depth = ops.ingest_frames(bgr, dpt)
+            return self.submit(list(rgb.unbind(0)), depth_images=depth)
+        b, h, w = int(bgr_u8.shape[0]), int(bgr_u8.shape[1]), int(bgr_u8.shape[2])
+        step = self._step_for(b, h, w, 1, dev)
+        # upload (copy stream) and convert straight into the static input buffers of the captured step (detect stream)
+        step.load_frames_u8(bgr_u8, depth_u16)
+        return ("step", step, step.submit(want_outputs=True), b, step.depth)
 
     @staticmethod
     def convert_joints_device(joints: torch.Tensor, crops: torch.Tensor, paras=None, crop_size: int = CROP_SIZE):
@@ -127,34 +148,62 @@ class HandNet(nn.Module):
     def forward(self, images, depth_images=None, is_3D: bool = False, is_detect: bool = False):
         if is_detect or is_3D:
             return None                                  # the reference falls through and returns None
+        return self.result(self.submit(images, depth_images))
+
+    # ------------------------------------------------------------------------------------------------------------
+    # Asynchronous interface (not in the reference): ``t = net.submit(images, depth)`` enqueues a step and returns at
+    # once; ``net.result(t)`` waits for it and returns what ``forward`` returns.  With two or more steps submitted before
+    # the first result is collected, the pose net of step i runs under the detector of step i+1 (runtime.GraphedHandNet)
+    # and the host-side H2D / D2H copies overlap the kernels.  Tickets are collected in submission order.
+    # ------------------------------------------------------------------------------------------------------------
+    def submit(self, images, depth_images=None):
+        """Enqueue ``forward(images, depth_images)``; returns a ticket for ``result()``.  ``images`` may be host (pinned)
+        or device tensors."""
         bsz = len(images)
         step = self._graphed(images, depth_images)
-        if step is not None:
-            step.invalidate_if_weights_changed()
-            torch._foreach_copy_(step.images, list(images))
-            step.depth.copy_(depth_images)
-        return self._run_loaded(step, bsz, depth_images, images)
-
-    def _run_loaded(self, step, bsz: int, depth_images, images=None):
-        """Run the step whose input buffers are loaded (or the eager path when `step` is None) and assemble the
-        reference's return triple."""
-        if step is not None:
-            out = step.run()
-            rec = step.rec
-            rec_host = step.rec_host
-        else:
-            out = self.forward_device(images, depth_images)
+        if step is None:                                  # ragged frame sizes / graphs off: eager, synchronous
+            dev = next(self.parameters()).device
+            imgs = [im.to(dev, non_blocking=True) for im in images]
+            dpt = depth_images.to(dev, non_blocking=True)
+            out = self.forward_device(imgs, dpt)
             rec = runtime.pack_records(out["joints"], out["crops"], out["has_hand"])
             rec_host = torch.empty(rec.shape, dtype=torch.float32).pin_memory()
+            rec_host.copy_(rec, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            return ("eager", ev, rec_host, (out["depth_batch"], out["crops"]), bsz, depth_images)
+        step.load_inputs(images, depth_images)
+        return ("step", step, step.submit(want_outputs=True), bsz, depth_images)
+
+    def submit_records(self, images, depth_images, post=None):
+        """``submit`` for callers that want the fixed-size per-frame RECORDS on the device (hn_b200.parallel): `post(rec)`
+        is called with the [B, 68] record tensor on the stream that has just produced it (e.g. to enqueue the all-gather)."""
+        step = self._graphed(images, depth_images)
+        if step is None:
+            raise RuntimeError("submit_records needs equally sized frames and use_cuda_graph=True")
+        step.load_inputs(images, depth_images)
+        return (step, step.submit(post=post))
+
+    def result_records(self, ticket):
+        step, t = ticket
+        return step.result(t)[0]
+
+    def result(self, ticket):
+        """Wait for a submitted step and assemble the reference's return triple (handnet_pipeline.py:106-116)."""
+        if ticket[0] == "eager":
+            _, ev, rec_host, outs, bsz, depth_images = ticket
+            ev.synchronize()
+        else:
+            _, step, t, bsz, depth_images = ticket
+            rec_host, outs = step.result(t)
         # the single read-back of the path: fixed-size per-frame records (joints, crop, hit flag)
-        rec_host.copy_(rec, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
         joints, _, hit = runtime.unpack_records(rec_host)
         final_results = torch.zeros((bsz, 21, 3))
         if not bool(hit.any()):
             return final_results, torch.zeros_like(depth_images), torch.zeros((bsz, 4))
         final_results[hit] = joints[hit]
+        depth_batch, crops = outs
         if bool(hit.all()):
-            return final_results, out["depth_batch"].clone(), out["crops"].clone()
-        idx = torch.nonzero(hit).reshape(-1).to(out["crops"].device)
-        return final_results, out["depth_batch"].index_select(0, idx), out["crops"].index_select(0, idx)
+            return final_results, depth_batch, crops
+        idx = torch.nonzero(hit).reshape(-1).to(crops.device)
+        return final_results, depth_batch.index_select(0, idx), crops.index_select(0, idx)

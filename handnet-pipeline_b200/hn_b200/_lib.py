@@ -50,10 +50,8 @@ SIGNATURES = {
                                              _c_p]),
     "hn_im2col_7x7s2": (_i, [_c_p, _i, _i, _i, _i, _i, _c_p, _i, _c_p]),
     "hn_conv2d_bf16": (_i, [C.POINTER(ConvDesc), _c_p]),
-    "hn_conv_multi_plan_bytes": (_i64, [_i, _i]),
-    "hn_conv_multi_build": (_i, [C.POINTER(ConvDesc), _i, _ip, _i, _c_p, _i64]),
-    "hn_conv_multi_run": (_i, [_c_p, _i, _i, _i, _c_p]),
-    "hn_conv_multi_set_trace": (_i, [_c_p]),
+    "hn_conv2d_bf16_levels": (_i, [C.POINTER(ConvDesc), _i, _c_p]),
+    "hn_groupnorm_relu_levels": (_i, [C.POINTER(_c_p), _ip, _ip, _ip, _i, _i, _i, C.POINTER(_c_p), _i, _c_p, _c_p, _f, _c_p]),
     "hn_ingest_frames": (_i, [_c_p, _c_p, _i, _i, _i, _c_p, _c_p, _c_p]),
     "hn_pack_nhwc4_frame": (_i, [_c_p, _i, _i, _i, _i, _ip, _c_p, _i, _i, _i, _i, _c_p]),
     "hn_convert_joints": (_i, [_c_p, _c_p, _c_p, _c_p, _i, _i, _i, _i, _i, _c_p, _c_p]),

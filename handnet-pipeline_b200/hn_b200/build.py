@@ -1,6 +1,9 @@
 """Build libhandnet_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
-    python -m hn_b200.build [--force]
+    python -m hn_b200.build [--force] [--debug] [-v]
+
+--debug compiles the convolution kernel's bring-up instrumentation in (-DHN_CONV_DEBUG: the timing-experiment flags of
+hn_conv_desc.debug and the clock64 trace); production builds carry none of it.
 
 The shared library is the product's only native artefact: a C-ABI (include/handnet_b200.h) over the
 hand-written CUDA kernels in csrc/.  It links the shared CUDA runtime so that it shares the runtime
@@ -36,7 +39,7 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, debug: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     objs = []
@@ -45,6 +48,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in SOURCES:
         obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
         cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        if debug:
+            cmd.insert(1, "-DHN_CONV_DEBUG")
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -63,4 +68,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv or "--debug" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))

@@ -6,21 +6,33 @@
 //
 // Data layout: activations are haloed NHWC bf16, so for tap (r,s) the A operand of the implicit GEMM is the
 // activation matrix [rows = N*Hp*Wp][Cin] shifted by (r*Wp + s) rows: one 2-D TMA box per (tap, 64-channel
-// chunk), out-of-range rows zero-filled by TMA.  Weights are [Cout_pad][taps*Cin] bf16 (K-major).
+// chunk), out-of-range rows zero-filled by TMA.  Weights are [K/64][Cout_pad][64] bf16 (k-block major).
 //
 // One persistent CTA per SM, 320 threads:
-//   warp 0      TMA producer   (two rings: A boxes of 128 or 136 rows x 64 ch, B tiles of BN rows x 64 k, SWIZZLE_128B)
-//   warp 1      MMA issuer     (tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16; fp32 accumulators in TMEM,
-//                               double-buffered so the epilogue of tile i overlaps the main loop of tile i+1)
+//   warp 0      TMA producer
+//   warp 1      MMA issuer     (tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16; fp32 accumulators in TMEM, up to 8
+//                               buffers, so the epilogue of a tile overlaps the main loops of the following ones)
 //   warps 2..9  epilogue       (tcgen05.ld -> scale/shift -> +residual -> ReLU -> bf16/fp32 store, GroupNorm partial
 //                               sums, optional phase-split copy for a following stride-2 conv)
 //
+// The kernel is a template over <BN, PIPE, FAST, SEG>; every instantiation contains ONE operand pipeline and ONE
+// epilogue body (round 1 compiled all of them, the bring-up instrumentation, a multi-convolution launch and two unused
+// experiments into every instantiation: 128 KB of SASS each, and ncu showed the narrow layers stalled on instruction
+// fetch as often as they issued):
+//   PIPE_RING  256-wide tiles: an A ring (one 136-row box per kernel row and chunk) and a B ring (one weight tile per tap)
+//   PIPE_UNI   tiles <= 128 columns: unified stages -- one A box + one B box with the (up to three) weight tiles of the
+//              k-step, two TMA operations and one barrier pair per k-step
+//   PIPE_RB    resident weights (one narrow N tile, many M tiles per SM): only A boxes stream; for 3x3 stride 1 ONE box
+//              brings the rows of all three kernel rows of a chunk (36 MMAs per barrier round trip)
+//   FAST       bf16 output, complete 32-column chunks, 32-byte accesses, no split-K: a predicate-free epilogue body
+//   SEG        the launch covers up to three SEGMENTS (pyramid levels) that share weights, scale and shift but have their
+//              own geometry, input, output and GroupNorm accumulators: the FCOS towers and output convolutions run ONCE
+//              over P3+P4+P5 (fcos_utils/fcos.py:278-289, 378-380 loop over the levels with the same modules) instead of
+//              three launches of which the small ones cannot fill 148 SMs.
+//
 // A-box sharing: the three horizontal taps of a 3x3 kernel row read rows m0+shift-1 .. m0+shift+128 of the same
 // matrix, so ONE 136-row box serves all three: their UMMA descriptors start 0, 1 and 2 rows (128 B each) into the
-// box (a SWIZZLE_128B descriptor may start at any 128-byte row with base_offset 0, tools/desc_offset_experiment.py).
-// That cuts the activation traffic L2 -> shared memory of a 3x3 convolution by 3x, which is what bounds the narrow
-// layers: a tcgen05.mma with N <= 128 is limited by the 128 B/clk of shared-memory bandwidth that its operand reads
-// share with the TMA writes (tools/sync_cost_bench.cu, tools/mma_issue_bench2.cu).
+// box (a SWIZZLE_128B descriptor may start at any 128-byte row with base_offset 0).
 #include "hn_common.cuh"
 
 #include <stdlib.h>
@@ -29,29 +41,40 @@
 
 namespace {
 
-__device__ __forceinline__ void hn_epi_bar_sync();
-
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int A_BOX_ROWS_MAX = 136;                   // 128 + up to 8 rows of horizontal-tap slack
 constexpr int A_SLOT_BYTES = A_BOX_ROWS_MAX * BLOCK_K * 2;   // 17 KiB (a multiple of 1024: slots keep swizzle alignment)
-// Patch tiles (resident weights, 3x3 stride 1 on large maps): an M tile is a 16-row x 8-pixel patch of ONE image instead
-// of 128 consecutive rows of the flattened matrix.  One 4-D TMA box {64 ch, 10 px, 18 rows} (22.5 KiB) then holds the
-// activations of all nine taps -- 1.4x the tile's own pixels instead of the 3.2x of three 136-row boxes (the layer1
-// convolutions are bound by L2 -> SM traffic).  In shared memory the box is 180 rows of 128 B; tap (t, s) reads it from
-// row t*10 + s on with a stride of 10 rows (1280 B) between the 8-row groups of the UMMA descriptor.
-constexpr int PATCH_H = 16, PATCH_W = 8;
-constexpr int PATCH_BOX_BYTES = (PATCH_H + 2) * (PATCH_W + 2) * BLOCK_K * 2;     // 23 040
-constexpr int PATCH_SLOT_BYTES = (PATCH_BOX_BYTES + 1023) / 1024 * 1024;         // 23 552
 constexpr int EPI_WARPS = 8;                       // two per TMEM lane quarter; they split the column chunks
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int NUM_THREADS = 64 + EPI_THREADS;
 constexpr int MAX_TAPS = 9;
-constexpr int MAX_GROUP_TAPS = 3;
-constexpr int GN_SMEM_FLOATS = 4096;   // [images][groups][2] fp32 partial sums kept per CTA (16 KiB)
+constexpr int GN_SMEM_FLOATS = 4096;   // bytes / 4 of the CTA's GroupNorm accumulators (16 KiB = 2048 int64 sums)
+constexpr int GN_SMEM_SUMS = GN_SMEM_FLOATS / 2;   // [segments][images][groups][2] fixed-point partial sums kept per CTA
+// GroupNorm statistics are accumulated as 40.24 FIXED-POINT integers (hn_conv_desc.gn_stats): integer addition is
+// associative, so the sums -- and everything downstream of them -- do not depend on the order in which warps and CTAs
+// arrive (fp32 / fp64 atomics made the tower outputs differ in the last bits from run to run).  One warp-level partial
+// (32 rows x 8 channels, reduced in a fixed shuffle order) is rounded to 2^-24; |sum| < 5.5e11 fits.
+constexpr float GN_FIX_SCALE = 16777216.0f;
+constexpr int MAX_SEGS = 3;
+
+enum { PIPE_RING = 0, PIPE_UNI = 1, PIPE_RB = 2 };
+
+// Geometry and buffers of one segment of a multi-segment launch (one pyramid level).
+struct SegGeo {
+  int tile_begin;               // first M tile of the segment (tiles never straddle segments)
+  int n_img, hp, wp, rows;      // padded height/width of one image, n_img * hp * wp
+  uint32_t div_img_mul, div_wp_mul;
+  int div_img_sh, div_wp_sh;
+  int shift[3];                 // grp_shift of the (up to three) A-box groups in this geometry
+  void* out;
+  int out_hp, out_wp, out_row_offset;
+  unsigned long long* gn_stats;
+  int gn_off;                   // offset of the segment's accumulators in the CTA's shared-memory array
+};
 
 struct ConvParams {
-  // compute geometry (== input geometry)
+  // compute geometry (== input geometry); with segments: those of segment 0
   int n_img, hp, wp, halo;     // padded height/width of one image and the halo size
   int rows;                    // n_img * hp * wp
   int num_taps, cin_chunks;
@@ -72,10 +95,9 @@ struct ConvParams {
   int uni_stages, uni_chunk_step;           // ring depth; 64-channel chunks per k-step (1x1 convolutions: up to 2)
   int uni_stride;                           // bytes between stages (>= uni_a_bytes + uni_b_bytes)
   int uni_a_rank4;                          // the A tensor map is 4-D (channels, rows, chunks, phases)
-  // direct 7x7/2 stem: an M tile is 128 consecutive output columns of one output row; the A tensor map is the 5-D
+  // direct 7x7/2 stem: an M tile is 128 consecutive output columns of one output row; the A tensor map is the
   // overlapping-stride patch view of the canvas (build_conv)
   int stem_tpr, stem_h;                     // tiles per output row (0 = ordinary convolution), output rows per image
-  int patch_tx, patch_ty;                   // patch tiles per image row / column (0 = flattened M tiles)
   int epi_alt;                              // epilogue: the two warps of a lane quarter take alternate TILES (all chunks
                                             // of their tile) instead of alternate chunks of the same tile
   int m_tiles, n_tiles;
@@ -93,7 +115,7 @@ struct ConvParams {
   __nv_bfloat16* out_phase;
   int ph_hp, ph_wp, ph_halo;
   long long ph_stride;         // elements between phase images
-  double* gn_stats;
+  unsigned long long* gn_stats;  // fixed-point (sum, sum of squares), see GN_FIX_SCALE
   int gn_groups, gn_group_size;
   int splits;                       // split-K factor (>= 1)
   float* sk_ws;                     // fp32 partial tiles [splits][m_tiles*128][sk_ld] (plain stores, summed in split order)
@@ -108,59 +130,33 @@ struct ConvParams {
                                     // chunk ([3][136 rows][128 B], the third box dimension steps by one image row), so a
                                     // k-step is a whole 64-channel chunk: 36 MMAs per barrier round trip
   int vec32;                        // epilogue may use 32-byte global accesses (cout % 16 == 0, 32-byte aligned bases)
-  int dbg_flags;                    // bring-up / timing experiments (bit0 no stores, bit1 no epilogue, bit2 no MMA, bit3 no TMA)
-  long long* trace;                 // bring-up: CTA 0 logs (clock64, tag) pairs per role, TRACE_EVENTS each
-  const struct ConvDeps* deps;      // multi-convolution launches: tile-level dataflow dependencies (NULL otherwise)
+  int n_seg;                        // segments of the launch (SEG kernels; 1 otherwise)
+  SegGeo seg[MAX_SEGS];
+  int dbg_flags;                    // HN_CONV_DEBUG builds only: timing experiments (bit0 no stores, bit1 no epilogue work,
+                                    // bit2 no MMA, bit3 no TMA, bit5 no epilogue role)
+  long long* trace;                 // HN_CONV_DEBUG builds only: CTA 0 logs (clock64, tag) pairs per role, TRACE_EVENTS each
 };
 
-// Dataflow synchronisation between the convolutions of one multi-convolution launch.  Every finished (m, n) output tile
-// of a convolution adds 1 to done[m]; a consumer tile waits until the producer M tiles it reads (its own rows +- one
-// image row for a 3x3, the same rows for a 1x1 or a residual) have all their N tiles.  No grid-wide barrier.
-constexpr int MAX_DEPS = 3;
-struct ConvDeps {
-  unsigned* done;                       // this convolution's counters, one per M tile
-  int n_deps;
-  const unsigned* dep_done[MAX_DEPS];   // producers' counters
-  int dep_need[MAX_DEPS];               // value of a producer counter that means "M tile complete" (its n_tiles)
-  const short* dep_first[MAX_DEPS];     // per M tile of THIS convolution: first / last producer M tile read
-  const short* dep_last[MAX_DEPS];
-};
-
-__device__ __forceinline__ void dep_wait(const ConvDeps* dp, int mt) {
-  if ((threadIdx.x & 31) == 0) {
-    const int nd = dp->n_deps;
-    for (int d = 0; d < nd; ++d) {
-      const int t0 = dp->dep_first[d][mt], t1 = dp->dep_last[d][mt];
-      const unsigned need = (unsigned)dp->dep_need[d];
-      const unsigned* cnt = dp->dep_done[d];
-      for (int t = t0; t <= t1; ++t) {
-        unsigned spins = 0;
-        while (true) {
-          unsigned v;
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt + t) : "memory");
-          if (v >= need) break;
-          if (++spins > (1u << 24)) {
-            printf("hn: dependency wait timed out (block %d, producer tile %d: %u of %u)\n", (int)blockIdx.x, t, v, need);
-            __trap();
-          }
-        }
-      }
-    }
-  }
-  __syncwarp();
-  // the TMA (async proxy) reads that follow must observe what other CTAs wrote with ordinary stores
-  asm volatile("fence.proxy.async;" ::: "memory");
-}
+// Bring-up instrumentation (the timing-experiment flags of hn_conv_desc.debug and the clock64 trace) is compiled in only
+// with -DHN_CONV_DEBUG (python -m hn_b200.build --debug); the production role loops carry none of it.
+#ifdef HN_CONV_DEBUG
+constexpr bool kDebug = true;
+#else
+constexpr bool kDebug = false;
+#endif
+#define HN_DBG(bits) (kDebug && (dbg_flags & (bits)))
 
 constexpr int TRACE_EVENTS = 2048;
 // role 0 producer, 1 MMA issuer, 2 first epilogue warp; written by lane 0 of CTA 0 only
 __device__ __forceinline__ void hn_trace(long long* tr, int role, int& idx, int tag) {
-  if (tr != nullptr && blockIdx.x == 0) {
-    if ((threadIdx.x & 31) == 0 && idx < TRACE_EVENTS) {
-      tr[(role * TRACE_EVENTS + idx) * 2] = clock64();
-      tr[(role * TRACE_EVENTS + idx) * 2 + 1] = tag;
+  if constexpr (kDebug) {
+    if (tr != nullptr && blockIdx.x == 0) {
+      if ((threadIdx.x & 31) == 0 && idx < TRACE_EVENTS) {
+        tr[(role * TRACE_EVENTS + idx) * 2] = clock64();
+        tr[(role * TRACE_EVENTS + idx) * 2 + 1] = tag;
+      }
+      ++idx;
     }
-    ++idx;
   }
 }
 
@@ -194,38 +190,27 @@ struct Cfg {
   static constexpr int TMEM_COLS = (NBUF * BN < 32) ? 32 : NBUF * BN;
 };
 
-// CS = thread-block cluster size along M: the CS CTAs of a cluster work on CS consecutive M tiles of the same N
-// tile in lock step; each loads 1/CS of the B (weight) tile and multicasts it to all of them, so the weights
-// cross the L2 -> SM fabric once per cluster instead of once per CTA.
-// ---------------------------------------------------------------------------------------------------------------
-// One convolution's worth of work for the calling warp (role by warp index).  `first_tile` / `tile_stride` select this
-// CTA's (super) tiles; `stage`, `phase`, `it` are the calling thread's pipeline state and persist across calls, so a
-// persistent multi-layer kernel can chain convolutions through the same barriers and TMEM buffers.
-// ---------------------------------------------------------------------------------------------------------------
-template <bool V>
-struct FastTag { static constexpr bool value = V; };
-
-template <int N>
-__device__ __forceinline__ void hn_tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[N]) {
-  if constexpr (N == 32) hn_tmem_ld32(taddr, r);
-  else hn_tmem_ld16(taddr, r);
+// segment of M tile `mt` (tiles are ordered segment by segment)
+__device__ __forceinline__ int seg_of(const ConvParams& p, int mt) {
+  return (p.n_seg > 2 && mt >= p.seg[2].tile_begin) ? 2 : ((p.n_seg > 1 && mt >= p.seg[1].tile_begin) ? 1 : 0);
 }
 
-struct PipeState {      // per-thread pipeline state; persists across convolutions of a multi-convolution launch
-  int a_stage, b_stage, it;
-  uint32_t a_phase, b_phase;
-};
-
-template <int BN, int CS, bool RB>
-__device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CUtensorMap* tm_b_ptr, const ConvParams& p,
-                                           uint8_t* smem_hdr, const uint32_t tmem_base, const int first_tile,
-                                           const int tile_stride, PipeState& ps, const bool pdl = false) {
-  // pdl: launched with programmatic stream serialisation.  Each role executes griddepcontrol.wait itself, as late as
-  // it can: the producer first fetches what does not depend on the previous kernel (the WEIGHTS of its first k-steps,
-  // or the whole resident slice), the MMA warp never touches global memory and does not wait at all.
+// ---------------------------------------------------------------------------------------------------------------
+// The whole kernel: prologue (barriers, TMEM), the three role loops, teardown.
+// ---------------------------------------------------------------------------------------------------------------
+template <int BN, int PIPE, bool FAST, bool SEG>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a1,
+                  const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_b,
+                  const __grid_constant__ ConvParams p) {
   using C = Cfg<BN>;
-  const CUtensorMap& tm_a = *tm_a_ptr;
-  const CUtensorMap& tm_b = *tm_b_ptr;
+  constexpr bool RB = PIPE == PIPE_RB;
+  constexpr bool UNI = PIPE == PIPE_UNI;
+  static_assert(PIPE != PIPE_RING || BN == 256, "two rings: 256-wide tiles only");
+  static_assert(PIPE != PIPE_UNI || BN <= 128, "unified stages: tiles of at most 128 columns");
+  static_assert(PIPE != PIPE_RB || BN <= 64, "resident weights: narrow tiles only");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem_hdr = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_hdr);
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + MAX_STAGES;
@@ -234,33 +219,65 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
   uint64_t* tmem_full = bars + 4 * MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 8;
   uint64_t* b_full = tmem_empty + 8;                     // resident weights have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+
+  // ---- prologue: barrier init, TMEM allocation ----
+  if (threadIdx.x == 0) {
+    hn_tma_prefetch_desc(&tm_a);
+    hn_tma_prefetch_desc(&tm_b);
+    if constexpr (SEG) {
+      hn_tma_prefetch_desc(&tm_a1);
+      hn_tma_prefetch_desc(&tm_a2);
+    }
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      hn_mbar_init(&a_full[s], 1);
+      hn_mbar_init(&a_empty[s], 1);
+      hn_mbar_init(&b_full_ring[s], 1);
+      hn_mbar_init(&b_empty[s], 1);
+    }
+    hn_mbar_init(b_full, 1);
+    for (int b = 0; b < 8; ++b) {
+      hn_mbar_init(&tmem_full[b], 1);
+      hn_mbar_init(&tmem_empty[b], EPI_WARPS);   // one arrive per epilogue warp
+    }
+    hn_mbar_init_fence();
+  }
+  if ((threadIdx.x >> 5) == 1) hn_tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  hn_tc_fence_before();
+  __syncthreads();
+  hn_tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may run
+  // while the previous kernel of the stream is still draining; global memory is touched only after each role's own
+  // griddepcontrol.wait, as late as it can: the producer first fetches what does not depend on the previous kernel
+  // (the WEIGHTS of its first k-steps, or the whole resident slice), the MMA warp never touches global memory and
+  // does not wait at all.  The early trigger lets the next kernel do the same under this one.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
   // everything the role loops need from the parameter block, read once (the asm statements in the loops clobber
-  // memory, so anything left in `p` would be re-read from the constant bank / shared memory every iteration)
+  // memory, so anything left in `p` would be re-read from the constant bank every iteration)
   const int cin_chunks = p.cin_chunks;
   const int n_tiles = p.n_tiles;
   const int splits = p.splits;
   const int na = p.na_stages, nb = p.nb_stages;
   const int a_box_bytes = p.a_box_bytes;
   const int cout_pad = p.cout_pad;
-  const int dbg_flags = p.dbg_flags;
-  long long* const trace = p.trace;
-  const ConvDeps* const deps = p.deps;
-  int tri = 0;
+  [[maybe_unused]] const int dbg_flags = p.dbg_flags;
+  [[maybe_unused]] long long* const trace = p.trace;
+  [[maybe_unused]] int tri = 0;
   const int k_steps = p.k_steps;                         // one k-step = one A box
   uint8_t* pipe = smem_hdr + HDR_PAD;                    // 1024-aligned operand area
   uint8_t* a_ring = pipe + (RB ? p.rb_b_bytes : 0);
-  const int a_slot_bytes = (RB && p.patch_tx > 0) ? PATCH_SLOT_BYTES : ((RB && p.rb3) ? 3 * A_SLOT_BYTES : A_SLOT_BYTES);
+  const int a_slot_bytes = (RB && p.rb3) ? 3 * A_SLOT_BYTES : A_SLOT_BYTES;
   uint8_t* b_ring = a_ring + na * a_slot_bytes;
-  int& it = ps.it;
 
   // warp index through a shuffle: tells the compiler it is warp-uniform, so the producer / MMA role loops below run
   // converged and their addresses and descriptors live in uniform registers
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  // tile schedule: "super tiles" of CS consecutive M tiles x one N tile, N fastest, strided over the clusters
-  const int cta_rank = (CS > 1) ? (int)hn_cluster_ctarank() : 0;
-  const int num_super = ((p.m_tiles + CS - 1) / CS) * n_tiles;
-  const int num_items = num_super * splits;
+  // tile schedule: work item = (M tile, N tile, K split), N fastest, strided over the CTAs
+  const int first_tile = blockIdx.x, tile_stride = gridDim.x;
+  const int num_items = p.m_tiles * n_tiles * splits;
   const int s_base = k_steps / splits, s_rem = k_steps - s_base * splits;
 
   // The producer and MMA loops are single-instruction-stream code on the kernel's critical path (a 64-wide tile has
@@ -269,8 +286,8 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     // All 32 lanes walk the loop and poll the barriers; one elected lane issues the copies.
-    int a_stage = ps.a_stage, b_stage = ps.b_stage;
-    uint32_t a_phase = ps.a_phase, b_phase = ps.b_phase;
+    int a_stage = 0, b_stage = 0;
+    uint32_t a_phase = 0, b_phase = 0;
     if constexpr (RB) {
       // the layer's whole weight slice (n_tiles == 1), once per CTA
       if (hn_elect_one()) {
@@ -281,34 +298,30 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       }
       __syncwarp();
     }
-    constexpr bool UNI = (BN <= 128) && !RB;               // unified stages (see ConvParams)
     const int uni_stage_bytes = p.uni_a_bytes + p.uni_b_bytes, uni_chunk_step = p.uni_chunk_step;
     const int uni_stride = p.uni_stride;
-    int early_b = 0;                                       // leading k-steps of an item whose weights are on the way
-    int early_item = first_tile;                           // ... and which item that is
-    if (pdl) {
-      if constexpr (UNI) {
-        if (first_tile < num_items && splits == 1 && !(dbg_flags & 8) && a_stage == 0) {
-          const int nt0 = n_tiles > 1 ? first_tile % n_tiles : 0;
-          early_b = k_steps < na ? k_steps : na;
-          if (hn_elect_one()) {
-            int g0 = 0, cc0 = 0;
-            for (int e = 0; e < early_b; ++e) {
-              hn_mbar_expect_tx(&a_full[e], (uint32_t)uni_stage_bytes);
-              hn_tma_load_4d(a_ring + e * uni_stride + p.uni_a_bytes, &tm_b, &a_full[e], 0, nt0 * BN, cc0,
-                             (p.grp_info[g0] >> 8) & 255);
-              cc0 += uni_chunk_step;
-              if (cc0 >= cin_chunks) { cc0 = 0; ++g0; }
-            }
+    int early_b = 0;                                       // leading k-steps of the first item whose weights are on the way
+    if constexpr (UNI) {
+      if (first_tile < num_items && splits == 1 && !HN_DBG(8)) {
+        const int nt0 = n_tiles > 1 ? first_tile % n_tiles : 0;
+        early_b = k_steps < na ? k_steps : na;
+        if (hn_elect_one()) {
+          int g0 = 0, cc0 = 0;
+          for (int e = 0; e < early_b; ++e) {
+            hn_mbar_expect_tx(&a_full[e], (uint32_t)uni_stage_bytes);
+            hn_tma_load_4d(a_ring + e * uni_stride + p.uni_a_bytes, &tm_b, &a_full[e], 0, nt0 * BN, cc0,
+                           (p.grp_info[g0] >> 8) & 255);
+            cc0 += uni_chunk_step;
+            if (cc0 >= cin_chunks) { cc0 = 0; ++g0; }
           }
-          __syncwarp();
         }
+        __syncwarp();
       }
-      asm volatile("griddepcontrol.wait;" ::: "memory");
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int w_ = first_tile; w_ < num_items; w_ += tile_stride) {
       int st = w_, s_begin = 0, s_end = k_steps, g = 0, cc = 0;
-      if (splits > 1) {                                    // (super) tile and K split of this work item
+      if (splits > 1) {                                    // tile and K split of this work item
         st = w_ / splits;
         const int ks = w_ - st * splits;
         s_begin = ks * s_base + (ks < s_rem ? ks : s_rem);
@@ -323,32 +336,18 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       }
       int mt = st, nt = 0;
       if (n_tiles > 1) { mt = st / n_tiles; nt = st - mt * n_tiles; }
-      const int m0 = (mt * CS + cta_rank) * BLOCK_M;
+      int m0 = mt * BLOCK_M;
       const int n0 = nt * BN;
-      int info = p.grp_info[g], shift = p.grp_shift[g];
-      if constexpr (UNI) {
-        if (deps != nullptr && splits == 1 && !(dbg_flags & 8)) {
-          // multi-convolution launch: the weights do not depend on the producer tiles -- arm the first stages and fetch
-          // their weight tiles BEFORE waiting for the dependencies, the activations after
-          early_b = k_steps < na ? k_steps : na;
-          early_item = w_;
-          int es = a_stage, g0 = 0, cc0 = 0;
-          uint32_t eph = a_phase;
-          for (int e = 0; e < early_b; ++e) {
-            hn_mbar_wait(&a_empty[es], eph ^ 1);
-            if (hn_elect_one()) {
-              hn_mbar_expect_tx(&a_full[es], (uint32_t)uni_stage_bytes);
-              hn_tma_load_4d(a_ring + es * uni_stride + p.uni_a_bytes, &tm_b, &a_full[es], 0, n0, cc0,
-                             (p.grp_info[g0] >> 8) & 255);
-            }
-            cc0 += uni_chunk_step;
-            if (cc0 >= cin_chunks) { cc0 = 0; ++g0; }
-            if (++es == na) { es = 0; eph ^= 1; }
-          }
-          __syncwarp();
-        }
+      // segments: the tile's rows, box shifts and tensor map are those of its pyramid level
+      const CUtensorMap* tma = &tm_a;
+      const int* gshift = p.grp_shift;
+      if constexpr (SEG) {
+        const int si = seg_of(p, mt);
+        m0 = (mt - p.seg[si].tile_begin) * BLOCK_M;
+        gshift = p.seg[si].shift;
+        tma = si == 0 ? &tm_a : (si == 1 ? &tm_a1 : &tm_a2);
       }
-      if (deps != nullptr) dep_wait(deps, mt);             // multi-convolution launch: the tiles this one reads are done
+      int info = p.grp_info[g], shift = gshift[g];
       if constexpr (UNI) {
         int st_n = 0, st_oy = 0, st_ox = 0;                  // stem: image, output row, first output column of the tile
         if (p.stem_tpr > 0) {
@@ -361,11 +360,11 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
           hn_mbar_wait(&a_empty[a_stage], a_phase ^ 1);
           hn_trace(trace, 0, tri, 1);
           if (hn_elect_one()) {
-            if (dbg_flags & 8) {                             // timing experiment: no loads at all
+            if (HN_DBG(8)) {                                 // timing experiment: no loads at all
               hn_mbar_arrive(&a_full[a_stage]);
             } else {
               uint8_t* sa = a_ring + a_stage * uni_stride;
-              const bool b_pending = w_ == early_item && step - s_begin < early_b;   // armed and B issued before the wait
+              const bool b_pending = w_ == first_tile && step - s_begin < early_b;   // armed and B issued before the wait
               if (!b_pending) hn_mbar_expect_tx(&a_full[a_stage], (uint32_t)uni_stage_bytes);
               if (p.stem_tpr > 0) hn_tma_load_4d(sa, &tm_a, &a_full[a_stage], 0, st_ox, st_oy + cc, st_n);
               else if (p.uni_a_rank4) hn_tma_load_4d(sa, &tm_a, &a_full[a_stage], 0, m0 + shift, cc, info >> 24);
@@ -381,79 +380,58 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
             if (step + 1 < s_end) { info = p.grp_info[g]; shift = p.grp_shift[g]; }
           }
         }
-        continue;
-      }
-      int pt_n = 0, pt_y = 0, pt_x = 0;                      // patch tiles: image, first box row / column (padded coords)
-      if (RB && p.patch_tx > 0) {
-        const int per_img = p.patch_tx * p.patch_ty;
-        pt_n = mt / per_img;
-        const int rem = mt - pt_n * per_img, ty = rem / p.patch_tx;
-        pt_y = ty * PATCH_H + p.halo - 1;
-        pt_x = (rem - ty * p.patch_tx) * PATCH_W + p.halo - 1;
-      }
-      for (int step = s_begin; step < s_end; ++step) {
-        const int ntaps = info & 15;
-        // ---- the A box of this (group, chunk)
-        hn_mbar_wait(&a_empty[a_stage], a_phase ^ 1);
-        hn_trace(trace, 0, tri, 1);
-        if (hn_elect_one()) {
-          if (dbg_flags & 8) {                               // timing experiment: no loads at all
-            hn_mbar_arrive(&a_full[a_stage]);
-          } else {
-            hn_mbar_expect_tx(&a_full[a_stage], (uint32_t)a_box_bytes);
-            if (RB && p.patch_tx > 0)
-              hn_tma_load_4d(a_ring + a_stage * a_slot_bytes, &tm_a, &a_full[a_stage], cc * BLOCK_K, pt_x, pt_y, pt_n);
-            else
-              hn_tma_load_3d(a_ring + a_stage * a_slot_bytes, &tm_a, &a_full[a_stage], cc * BLOCK_K, m0 + shift, info >> 24);
+      } else {
+        for (int step = s_begin; step < s_end; ++step) {
+          const int ntaps = info & 15;
+          // ---- the A box of this (group, chunk)
+          hn_mbar_wait(&a_empty[a_stage], a_phase ^ 1);
+          hn_trace(trace, 0, tri, 1);
+          if (hn_elect_one()) {
+            if (HN_DBG(8)) {                                 // timing experiment: no loads at all
+              hn_mbar_arrive(&a_full[a_stage]);
+            } else {
+              hn_mbar_expect_tx(&a_full[a_stage], (uint32_t)a_box_bytes);
+              hn_tma_load_3d(a_ring + a_stage * a_slot_bytes, tma, &a_full[a_stage], cc * BLOCK_K, m0 + shift, info >> 24);
+            }
           }
-        }
-        if (++a_stage == na) { a_stage = 0; a_phase ^= 1; }
-        // ---- one weight tile per member tap
-        if constexpr (!RB) {
-          // weights are stored k-block major ([k_block][cout_pad][64]): the tile of (k-block, n0) is one contiguous
-          // run of BN * 128 bytes starting at row k_block * cout_pad + n0
-          int krow = (((info >> 8) & 255) * cin_chunks + cc) * cout_pad + n0;
-          const int krow_step = ((info >> 16) & 255) * cin_chunks * cout_pad;
-          for (int t = 0; t < ntaps; ++t) {
-            hn_mbar_wait(&b_empty[b_stage], b_phase ^ 1);
-            hn_trace(trace, 0, tri, 2);
-            if (hn_elect_one()) {
-              if (dbg_flags & 8) {
-                hn_mbar_arrive(&b_full_ring[b_stage]);
-              } else {
-                uint8_t* sb = b_ring + b_stage * C::B_STAGE_BYTES;
-                hn_mbar_expect_tx(&b_full_ring[b_stage], (uint32_t)C::B_STAGE_BYTES);
-                if constexpr (CS == 1) {
-                  hn_tma_load_2d(sb, &tm_b, &b_full_ring[b_stage], 0, krow);
+          if (++a_stage == na) { a_stage = 0; a_phase ^= 1; }
+          // ---- one weight tile per member tap
+          if constexpr (!RB) {
+            // weights are stored k-block major ([k_block][cout_pad][64]): the tile of (k-block, n0) is one contiguous
+            // run of BN * 128 bytes starting at row k_block * cout_pad + n0
+            int krow = (((info >> 8) & 255) * cin_chunks + cc) * cout_pad + n0;
+            const int krow_step = ((info >> 16) & 255) * cin_chunks * cout_pad;
+            for (int t = 0; t < ntaps; ++t) {
+              hn_mbar_wait(&b_empty[b_stage], b_phase ^ 1);
+              hn_trace(trace, 0, tri, 2);
+              if (hn_elect_one()) {
+                if (HN_DBG(8)) {
+                  hn_mbar_arrive(&b_full_ring[b_stage]);
                 } else {
-                  constexpr int SLICE = BN / CS;   // weight rows this CTA fetches for the whole cluster
-                  hn_tma_load_2d_mcast(sb + cta_rank * SLICE * BLOCK_K * 2, &tm_b, &b_full_ring[b_stage], 0,
-                                       krow + cta_rank * SLICE, (uint16_t)((1u << CS) - 1u));
+                  hn_mbar_expect_tx(&b_full_ring[b_stage], (uint32_t)C::B_STAGE_BYTES);
+                  hn_tma_load_2d(b_ring + b_stage * C::B_STAGE_BYTES, &tm_b, &b_full_ring[b_stage], 0, krow);
                 }
               }
+              krow += krow_step;
+              if (++b_stage == nb) { b_stage = 0; b_phase ^= 1; }
             }
-            krow += krow_step;
-            if (++b_stage == nb) { b_stage = 0; b_phase ^= 1; }
           }
-        }
-        if (++cc == cin_chunks) {
-          cc = 0;
-          ++g;
-          if (step + 1 < s_end) { info = p.grp_info[g]; shift = p.grp_shift[g]; }
+          if (++cc == cin_chunks) {
+            cc = 0;
+            ++g;
+            if (step + 1 < s_end) { info = p.grp_info[g]; shift = gshift[g]; }
+          }
         }
       }
     }
-    ps.a_stage = a_stage; ps.b_stage = b_stage; ps.a_phase = a_phase; ps.b_phase = b_phase;
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     // Converged warp; tcgen05.mma / commit are issued by one elected lane.  (A second issuing warp taking alternate
-    // tiles was tried for the narrow tiles: it needs a ring of two whole tiles to keep the parity waits unambiguous and
-    // bought nothing once the epilogue ran -- layer1 52.2 -> 52.9 us -- so there is one issuer.)
-    long long* const trace_m = trace;
+    // tiles was tried twice for the narrow tiles and bought nothing once the epilogue ran, so there is one issuer.)
     constexpr uint32_t idesc = hn_umma_idesc_bf16(BN);
     constexpr uint32_t A_SLOT_D = A_SLOT_BYTES >> 4, B_SLOT_D = C::B_STAGE_BYTES >> 4, ROW_D = (BLOCK_K * 2) >> 4;
-    int a_stage = ps.a_stage, b_stage = ps.b_stage;
-    uint32_t a_phase = ps.a_phase, b_phase = ps.b_phase;
+    int a_stage = 0, b_stage = 0, it = 0;
+    uint32_t a_phase = 0, b_phase = 0;
     // low words of the shared-memory descriptors of slot 0 of each ring (start address >> 4 in bits 0..13); the high
     // word is the same for every operand tile
     const uint32_t a_desc0 = (uint32_t)hn_umma_smem_desc(hn_smem_u32(a_ring));
@@ -463,10 +441,8 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
     // The tensor pipe queues only a few MMAs, so whatever the issuing thread does between two bursts must take less
     // than the burst it has just issued needs to execute.  Wide tiles (256 columns: 512 cycles per tap) poll and issue
     // tap by tap, so that a tap starts as soon as its weight tile has landed.  Narrow tiles have only ~50-64 cycles of
-    // tensor work per MMA: they poll all barriers of a k-step first and issue its (up to) 12 MMAs and their commits as
+    // tensor work per MMA: they poll all barriers of a k-step first and issue its (up to) 36 MMAs and their commits as
     // one straight-line burst.
-    constexpr bool STEP_ISSUE = BN <= 128;
-    constexpr bool UNI = (BN <= 128) && !RB;               // unified stages: one barrier pair and one burst per k-step
     const uint32_t uni_stage_d = (uint32_t)p.uni_stride >> 4, uni_a_d = (uint32_t)p.uni_a_bytes >> 4;
     const uint32_t uni_plane_d = (uint32_t)p.uni_plane_bytes >> 4;
     const int uni_chunk_step = p.uni_chunk_step;
@@ -487,8 +463,8 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       const int buf = it & (C::NBUF - 1);
       const uint32_t d_tmem = tmem_base + buf * BN;
       int info = p.grp_info[g];
-      if (!(dbg_flags & 32)) hn_mbar_wait(&tmem_empty[buf], ((it >> C::NBUF_LOG) & 1) ^ 1);   // the epilogue has drained this buffer
-      hn_trace(trace_m, 1, tri, 4);
+      if (!HN_DBG(32)) hn_mbar_wait(&tmem_empty[buf], ((it >> C::NBUF_LOG) & 1) ^ 1);   // the epilogue has drained this buffer
+      hn_trace(trace, 1, tri, 4);
       uint32_t accumulate = 0;
       if constexpr (UNI) {
         int units = p.grp_units[g];
@@ -499,17 +475,17 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
           const uint32_t sa = a_desc0 + a_stage * uni_stage_d, sb = sa + uni_a_d;
           const uint32_t ea = hn_smem_u32(&a_empty[a_stage]), tf = hn_smem_u32(&tmem_full[buf]);
           hn_mbar_wait(&a_full[a_stage], a_phase);
-          hn_trace(trace_m, 1, tri, 1);
+          hn_trace(trace, 1, tri, 1);
           hn_tc_fence_after();
           if (hn_elect_one()) {
             if (p.stem_tpr > 0) {
               // direct stem: two [128 x 128 B] tiles (row pairs oy + 2*step, +1 = kernel rows 4*step .. +3) against the two
               // weight k-blocks of the step
-              if (!(dbg_flags & 4)) {
+              if (!HN_DBG(4)) {
                 hn_umma_bf16_x4(d_tmem, desc_hi | sa, desc_hi | sb, idesc, accumulate);
                 hn_umma_bf16_x4(d_tmem, desc_hi | (sa + (uint32_t)((BLOCK_M * BLOCK_K * 2) >> 4)), desc_hi | (sb + B_SLOT_D), idesc, 1u);
               }
-            } else if (!(dbg_flags & 4)) {                     // (timing experiment: bit 2 skips the MMAs)
+            } else if (!HN_DBG(4)) {                           // (timing experiment: bit 2 skips the MMAs)
               hn_umma_bf16_x4(d_tmem, desc_hi | (sa + (units & 3) * uni_plane_d + ((units >> 2) & 15) * ROW_D),
                               desc_hi | (sb + ((units >> 6) & 3) * B_SLOT_D), idesc, accumulate);
               if (nu > 1)
@@ -523,7 +499,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
             if (last) hn_umma_commit_addr<1>(tf);              // accumulator complete -> epilogue
           }
           accumulate = 1;
-          hn_trace(trace_m, 1, tri, 3);
+          hn_trace(trace, 1, tri, 3);
           if (++a_stage == na) { a_stage = 0; a_phase ^= 1; }
           cc += uni_chunk_step;
           if (cc >= cin_chunks) {
@@ -532,148 +508,112 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
             if (!last) { info = p.grp_info[g]; units = p.grp_units[g]; }
           }
         }
-        continue;
-      }
-      for (int step = s_begin; step < s_end; ++step) {
-        const int ntaps = info & 15;
-        const uint32_t off_step = ((info >> 4) & 15) * ROW_D;
-        const uint32_t da_lo = a_desc0 + a_stage * A_SLOT_D;
-        // resident weights: tile of tap (tap0 + t * tap_step), chunk cc
-        const uint32_t db_rb = b_desc0 + (((info >> 8) & 255) * cin_chunks + cc) * B_SLOT_D;
-        const uint32_t db_rb_step = ((info >> 16) & 255) * cin_chunks * B_SLOT_D;
-        const bool last = step == s_end - 1;
-        hn_mbar_wait(&a_full[a_stage], a_phase);
-        hn_trace(trace_m, 1, tri, 1);
-        if (RB && p.rb3) {
-          // all nine taps of this chunk from one stage: A tile of kernel row t at slot + t * 17 KiB, tap (t, s) reads it
-          // from row s * dil on; weight tile of tap t*3 + s, chunk cc
-          const bool patch = p.patch_tx > 0;
-          const uint32_t sa = a_desc0 + a_stage * (patch ? (uint32_t)(PATCH_SLOT_BYTES >> 4) : 3 * A_SLOT_D);
-          const uint32_t sb = b_desc0 + cc * B_SLOT_D, tap_d = cin_chunks * B_SLOT_D;
-          const uint32_t ea = hn_smem_u32(&a_empty[a_stage]), tf = hn_smem_u32(&tmem_full[buf]);
-          // patch tiles: kernel row t starts t box rows (10 pixels) further, the 8-pixel groups are 10 rows apart
-          const uint32_t t_step = patch ? (PATCH_W + 2) * ROW_D : A_SLOT_D, s_step = patch ? ROW_D : off_step;
-          const uint64_t a_hi = patch ? ((desc_hi & ~(uint64_t(0x3FFF) << 32)) | (uint64_t(((PATCH_W + 2) * BLOCK_K * 2) >> 4) << 32))
-                                      : desc_hi;
-          hn_tc_fence_after();
-          if (hn_elect_one()) {
-            if (!(dbg_flags & 4)) {
+      } else {
+        for (int step = s_begin; step < s_end; ++step) {
+          const int ntaps = info & 15;
+          const uint32_t off_step = ((info >> 4) & 15) * ROW_D;
+          const uint32_t da_lo = a_desc0 + a_stage * A_SLOT_D;
+          // resident weights: tile of tap (tap0 + t * tap_step), chunk cc
+          const uint32_t db_rb = b_desc0 + (((info >> 8) & 255) * cin_chunks + cc) * B_SLOT_D;
+          const uint32_t db_rb_step = ((info >> 16) & 255) * cin_chunks * B_SLOT_D;
+          const bool last = step == s_end - 1;
+          hn_mbar_wait(&a_full[a_stage], a_phase);
+          hn_trace(trace, 1, tri, 1);
+          if (RB && p.rb3) {
+            // all nine taps of this chunk from one stage: A tile of kernel row t at slot + t * 17 KiB, tap (t, s) reads it
+            // from row s * dil on; weight tile of tap t*3 + s, chunk cc
+            const uint32_t sa = a_desc0 + a_stage * (3 * A_SLOT_D);
+            const uint32_t sb = b_desc0 + cc * B_SLOT_D, tap_d = cin_chunks * B_SLOT_D;
+            const uint32_t ea = hn_smem_u32(&a_empty[a_stage]), tf = hn_smem_u32(&tmem_full[buf]);
+            hn_tc_fence_after();
+            if (hn_elect_one()) {
+              if (!HN_DBG(4)) {
 #pragma unroll
-              for (int t = 0; t < 3; ++t) {
+                for (int t = 0; t < 3; ++t) {
 #pragma unroll
-                for (int sx = 0; sx < 3; ++sx) {
-                  hn_umma_bf16_x4(d_tmem, a_hi | (sa + t * t_step + sx * s_step), desc_hi | (sb + (t * 3 + sx) * tap_d),
-                                  idesc, (t | sx) ? 1u : accumulate);
+                  for (int sx = 0; sx < 3; ++sx) {
+                    hn_umma_bf16_x4(d_tmem, desc_hi | (sa + t * A_SLOT_D + sx * off_step), desc_hi | (sb + (t * 3 + sx) * tap_d),
+                                    idesc, (t | sx) ? 1u : accumulate);
+                  }
                 }
               }
+              hn_umma_commit_addr<1>(ea);
+              if (last) hn_umma_commit_addr<1>(tf);
             }
-            hn_umma_commit_addr<1>(ea);
-            if (last) hn_umma_commit_addr<1>(tf);
-          }
-        } else if constexpr (STEP_ISSUE) {
-          // ring slots of the (up to) three weight tiles of this step
-          int bs1 = b_stage + 1, bs2 = b_stage + 2;
-          uint32_t bp1 = b_phase, bp2 = b_phase;
-          if (bs1 >= nb) { bs1 -= nb; bp1 ^= 1; }
-          if (bs2 >= nb) { bs2 -= nb; bp2 ^= 1; }
-          uint32_t db0 = db_rb, db1 = db_rb + db_rb_step, db2 = db_rb + 2 * db_rb_step;
-          if constexpr (!RB) {
-            hn_mbar_wait(&b_full_ring[b_stage], b_phase);
-            if (ntaps > 1) hn_mbar_wait(&b_full_ring[bs1], bp1);
-            if (ntaps > 2) hn_mbar_wait(&b_full_ring[bs2], bp2);
-            db0 = b_desc0 + b_stage * B_SLOT_D;
-            db1 = b_desc0 + bs1 * B_SLOT_D;
-            db2 = b_desc0 + bs2 * B_SLOT_D;
-          }
-          const uint32_t eb0 = hn_smem_u32(&b_empty[b_stage]), eb1 = hn_smem_u32(&b_empty[bs1]),
-                         eb2 = hn_smem_u32(&b_empty[bs2]);
-          const uint32_t ea = hn_smem_u32(&a_empty[a_stage]), tf = hn_smem_u32(&tmem_full[buf]);
-          hn_tc_fence_after();
-          if (hn_elect_one()) {
-            const bool mma = !(dbg_flags & 4);                // (timing experiment: bit 2 skips the MMAs)
-            if (mma) hn_umma_bf16_x4(d_tmem, desc_hi | da_lo, desc_hi | db0, idesc, accumulate);
-            if constexpr (!RB) hn_umma_commit_addr<CS>(eb0);
-            if (ntaps > 1) {
-              if (mma) hn_umma_bf16_x4(d_tmem, desc_hi | (da_lo + off_step), desc_hi | db1, idesc, 1u);
-              if constexpr (!RB) hn_umma_commit_addr<CS>(eb1);
-            }
-            if (ntaps > 2) {
-              if (mma) hn_umma_bf16_x4(d_tmem, desc_hi | (da_lo + 2 * off_step), desc_hi | db2, idesc, 1u);
-              if constexpr (!RB) hn_umma_commit_addr<CS>(eb2);
-            }
-            hn_umma_commit_addr<1>(ea);                       // A box free
-            if (last) hn_umma_commit_addr<1>(tf);             // accumulator complete -> epilogue
-          }
-          if constexpr (!RB) {
-            b_stage += ntaps;
-            if (b_stage >= nb) { b_stage -= nb; b_phase ^= 1; }
-          }
-        } else {
-          uint32_t da_t = da_lo, db_t = db_rb;
-          for (int t = 0; t < ntaps; ++t) {
-            if constexpr (!RB) {
-              hn_mbar_wait(&b_full_ring[b_stage], b_phase);
-              hn_trace(trace_m, 1, tri, 2);
-            }
+          } else if constexpr (RB) {
+            // resident weights, one A box per group: poll once, issue the group's (up to three) taps as one burst
+            const uint32_t ea = hn_smem_u32(&a_empty[a_stage]), tf = hn_smem_u32(&tmem_full[buf]);
             hn_tc_fence_after();
-            const uint32_t db_lo = RB ? db_t : b_desc0 + b_stage * B_SLOT_D;
-            const uint32_t eb = hn_smem_u32(&b_empty[b_stage]);
             if (hn_elect_one()) {
-              if (!(dbg_flags & 4)) hn_umma_bf16_x4(d_tmem, desc_hi | da_t, desc_hi | db_lo, idesc, accumulate);
-              if constexpr (!RB) hn_umma_commit_addr<CS>(eb);   // weight slot free once these MMAs have read it
+              if (!HN_DBG(4)) {
+                hn_umma_bf16_x4(d_tmem, desc_hi | da_lo, desc_hi | db_rb, idesc, accumulate);
+                if (ntaps > 1) hn_umma_bf16_x4(d_tmem, desc_hi | (da_lo + off_step), desc_hi | (db_rb + db_rb_step), idesc, 1u);
+                if (ntaps > 2) hn_umma_bf16_x4(d_tmem, desc_hi | (da_lo + 2 * off_step), desc_hi | (db_rb + 2 * db_rb_step), idesc, 1u);
+              }
+              hn_umma_commit_addr<1>(ea);                       // A box free
+              if (last) hn_umma_commit_addr<1>(tf);             // accumulator complete -> epilogue
             }
-            accumulate = 1;
-            da_t += off_step;
-            db_t += db_rb_step;
-            if constexpr (!RB) {
+          } else {
+            // two rings, 256-wide tiles: a tap starts as soon as its weight tile has landed
+            uint32_t da_t = da_lo;
+            for (int t = 0; t < ntaps; ++t) {
+              hn_mbar_wait(&b_full_ring[b_stage], b_phase);
+              hn_trace(trace, 1, tri, 2);
+              hn_tc_fence_after();
+              const uint32_t db_lo = b_desc0 + b_stage * B_SLOT_D;
+              const uint32_t eb = hn_smem_u32(&b_empty[b_stage]);
+              if (hn_elect_one()) {
+                if (!HN_DBG(4)) hn_umma_bf16_x4(d_tmem, desc_hi | da_t, desc_hi | db_lo, idesc, accumulate);
+                hn_umma_commit_addr<1>(eb);                     // weight slot free once these MMAs have read it
+              }
+              accumulate = 1;
+              da_t += off_step;
               if (++b_stage == nb) { b_stage = 0; b_phase ^= 1; }
             }
+            const uint32_t ea = hn_smem_u32(&a_empty[a_stage]), tf = hn_smem_u32(&tmem_full[buf]);
+            if (hn_elect_one()) {
+              hn_umma_commit_addr<1>(ea);                         // A box free
+              if (last) hn_umma_commit_addr<1>(tf);               // accumulator complete -> epilogue
+            }
           }
-          const uint32_t ea = hn_smem_u32(&a_empty[a_stage]), tf = hn_smem_u32(&tmem_full[buf]);
-          if (hn_elect_one()) {
-            hn_umma_commit_addr<1>(ea);                         // A box free
-            if (last) hn_umma_commit_addr<1>(tf);               // accumulator complete -> epilogue
+          accumulate = 1;
+          hn_trace(trace, 1, tri, 3);
+          if (++a_stage == na) { a_stage = 0; a_phase ^= 1; }
+          if (++cc == cin_chunks) {
+            cc = 0;
+            ++g;
+            if (!last) info = p.grp_info[g];
           }
-        }
-        accumulate = 1;
-        hn_trace(trace_m, 1, tri, 3);
-        if (++a_stage == na) { a_stage = 0; a_phase ^= 1; }
-        if (++cc == cin_chunks) {
-          cc = 0;
-          ++g;
-          if (!last) info = p.grp_info[g];
         }
       }
     }
-    ps.a_stage = a_stage; ps.b_stage = b_stage; ps.a_phase = a_phase; ps.b_phase = b_phase;
-  } else {
+  } else if (!HN_DBG(32)) {     // (experiment bit 5: no epilogue role at all -- the MMA warp does not wait for it)
     // ===================================== epilogue ==========================================
     const int quarter = warp & 3;              // TMEM lanes this warp may touch: 32*quarter .. +31
     const int half = (warp - 2) >> 2;          // which of the two warps of this quarter: takes every other chunk
-    const int img_rows = p.hp * p.wp;
     // scale/shift of the current N tile live in shared memory (the L1 left next to ~210 KiB of smem is too small
     // to keep them, and an L2 round trip per chunk was the epilogue's critical path)
     float* ss_base = reinterpret_cast<float*>(smem_hdr + HDR_BARS + GN_SMEM_FLOATS * 4);
-    // per-CTA GroupNorm accumulator [image][group][2] in shared memory (when it fits)
-    float* gn_acc = reinterpret_cast<float*>(smem_hdr + HDR_BARS);
-    const int gn_vals = p.gn_stats ? p.n_img * p.gn_groups * 2 : 0;
-    const bool gn_smem = gn_vals > 0 && gn_vals <= GN_SMEM_FLOATS;
+    // per-CTA GroupNorm accumulator [segment][image][group][2] in shared memory (when it fits)
+    unsigned long long* gn_acc = reinterpret_cast<unsigned long long*>(smem_hdr + HDR_BARS);
+    int gn_vals = 0;
+    if (p.gn_stats) {
+      if constexpr (SEG) {
+        for (int s = 0; s < p.n_seg; ++s) gn_vals += p.seg[s].n_img * p.gn_groups * 2;
+      } else {
+        gn_vals = p.n_img * p.gn_groups * 2;
+      }
+    }
+    const bool gn_smem = gn_vals > 0 && gn_vals <= GN_SMEM_SUMS;      // (segments: checked by the host)
     if (gn_smem) {
-      for (int i = threadIdx.x - 64; i < gn_vals; i += EPI_THREADS) gn_acc[i] = 0.f;
+      for (int i = threadIdx.x - 64; i < gn_vals; i += EPI_THREADS) gn_acc[i] = 0ull;
       hn_epi_bar_sync();
     }
-    uint32_t* sk_flag = reinterpret_cast<uint32_t*>(b_full + 1) + 1;   // "this CTA finalises the tile" (after tmem_slot)
-    if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");       // before the first global read / write of this role
-    if (dbg_flags & 32) return;                   // experiment: no epilogue role at all (the MMA warp does not wait for it)
-    const uint32_t div_img_mul = p.div_img_mul, div_wp_mul = p.div_wp_mul;
-    const int div_img_sh = p.div_img_sh, div_wp_sh = p.div_wp_sh;
-    const int rows = p.rows, wp = p.wp, halo = p.halo;
+    uint32_t* sk_flag = tmem_slot + 1;                                 // "this CTA finalises the tile"
+    asm volatile("griddepcontrol.wait;" ::: "memory");                // before the first global read / write of this role
+    const int halo = p.halo;
     int ss_n0[2] = {-1, -1};                    // N tile whose scale/shift each staging buffer holds
     const bool has_scale = p.scale != nullptr;
-    // bf16 output, cout a multiple of the chunk width (no ragged chunks) and no padded N tile (the FAST body does not
-    // skip chunks beyond cout: with cout_pad > cout they would land on the next pixel), 32-byte aligned rows, no split-K
-    const bool epi_fast = p.out_kind == 0 && p.vec32 != 0 && (p.cout % 32) == 0 && p.cout_pad == p.cout && splits == 1 &&
-                          !(p.dbg_flags & 64);
     // Alternate-tile mode (single N tile, no split-K): the epilogue of a tile is a latency chain (accumulator wait,
     // tcgen05.ld, residual / store round trips); with both warps of a quarter on the SAME tile nothing overlaps it.  Here
     // warps 2-5 drain the even tiles and warps 6-9 the odd ones, so two tiles are in flight.  Each warp arrives twice on
@@ -688,6 +628,7 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       ss_n0[0] = ss_n0[1] = 0;
       hn_epi_bar_sync();
     }
+    int it = 0;
     for (int w_ = first_tile; w_ < num_items; w_ += tile_stride, ++it) {
       if (alt && (it & 1) != half) continue;
       const int st = splits > 1 ? w_ / splits : w_;
@@ -696,44 +637,49 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       const uint32_t acc_phase = (it >> C::NBUF_LOG) & 1;
       int mt = st, nt = 0;
       if (n_tiles > 1) { mt = st / n_tiles; nt = st - mt * n_tiles; }
-      const int m0 = (mt * CS + cta_rank) * BLOCK_M;
       const int n0 = nt * BN;
-      const int m = m0 + quarter * 32 + lane;
+      // geometry of the tile's segment
+      int g_rows = p.rows, g_hp = p.hp, g_wp = p.wp, g_nimg = p.n_img, g_tile0 = 0, g_gn_off = 0;
+      uint32_t div_img_mul = p.div_img_mul, div_wp_mul = p.div_wp_mul;
+      int div_img_sh = p.div_img_sh, div_wp_sh = p.div_wp_sh;
+      void* g_out = p.out;
+      int g_out_hp = p.out_hp, g_out_wp = p.out_wp, g_out_row_offset = p.out_row_offset;
+      unsigned long long* g_gn_stats = p.gn_stats;
+      if constexpr (SEG) {
+        const SegGeo& sg = p.seg[seg_of(p, mt)];
+        g_rows = sg.rows; g_hp = sg.hp; g_wp = sg.wp; g_nimg = sg.n_img; g_tile0 = sg.tile_begin; g_gn_off = sg.gn_off;
+        div_img_mul = sg.div_img_mul; div_wp_mul = sg.div_wp_mul; div_img_sh = sg.div_img_sh; div_wp_sh = sg.div_wp_sh;
+        g_out = sg.out; g_out_hp = sg.out_hp; g_out_wp = sg.out_wp; g_out_row_offset = sg.out_row_offset;
+        g_gn_stats = sg.gn_stats;
+      }
+      const int m = (mt - g_tile0) * BLOCK_M + quarter * 32 + lane;
       // decode the padded pixel this accumulator row belongs to (divisions by multiply-high, see fastdiv())
       int img = 0, h = 0, w = 0;
       bool interior = false;
-      if (p.patch_tx > 0) {                              // patch tile: accumulator row r = pixel (r / 8, r % 8) of the patch
-        const int per_img = p.patch_tx * p.patch_ty;
-        img = mt / per_img;
-        const int rem = mt - img * per_img, ty = rem / p.patch_tx;
-        const int r = quarter * 32 + lane;
-        h = ty * PATCH_H + (r >> 3);
-        w = (rem - ty * p.patch_tx) * PATCH_W + (r & 7);
-        interior = img < p.n_img && h < p.hp - 2 * halo && w < wp - 2 * halo;
-      } else if (p.stem_tpr > 0) {                       // stem tile: 128 output columns of one output row
+      if (p.stem_tpr > 0) {                              // stem tile: 128 output columns of one output row
         const int row = mt / p.stem_tpr;
         img = row / p.stem_h;
         h = row - img * p.stem_h;
         w = (mt - row * p.stem_tpr) * BLOCK_M + quarter * 32 + lane;
-        interior = w < wp && img < p.n_img;
-      } else if (m < rows) {
+        interior = w < g_wp && img < g_nimg;
+      } else if (m < g_rows) {
         img = (int)((__umulhi((uint32_t)m, div_img_mul) + (uint32_t)m) >> div_img_sh);
-        const int rem = m - img * img_rows;
+        const int rem = m - img * (g_hp * g_wp);
         const int hh = (int)((__umulhi((uint32_t)rem, div_wp_mul) + (uint32_t)rem) >> div_wp_sh);
-        const int ww = rem - hh * wp;
+        const int ww = rem - hh * g_wp;
         h = hh - halo;
         w = ww - halo;
-        interior = (h >= 0) && (w >= 0) && (h < p.hp - 2 * halo) && (w < wp - 2 * halo);
+        interior = (h >= 0) && (w >= 0) && (h < g_hp - 2 * halo) && (w < g_wp - 2 * halo);
       }
-      const int H = p.hp - 2 * p.halo, W = p.wp - 2 * p.halo;
+      const int H = g_hp - 2 * halo, W = g_wp - 2 * halo;
       // output / residual element offsets of channel 0 of this row
       long long out_off = 0, res_off = 0, ph_off = 0;
       if (interior) {
-        if (p.out_kind == 0) {
-          out_off = ((long long)(img * p.out_hp + h + p.out_halo) * p.out_wp + (w + p.out_halo)) * p.cout;
+        if (FAST || p.out_kind == 0) {
+          out_off = ((long long)(img * g_out_hp + h + p.out_halo) * g_out_wp + (w + p.out_halo)) * p.cout;
         } else {
           const int pix = p.out_transpose_hw ? (w * H + h) : (h * W + w);
-          out_off = ((long long)img * p.out_rows_per_image + p.out_row_offset + pix) * p.out_ld;
+          out_off = ((long long)img * p.out_rows_per_image + g_out_row_offset + pix) * p.out_ld;
         }
         if (p.res_mode == 1) {
           res_off = ((long long)(img * p.res_hp + h + p.res_halo) * p.res_wp + (w + p.res_halo)) * p.cout;
@@ -765,82 +711,70 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
       }
       // residual rows are fetched one chunk ahead (the first one before the accumulator wait) so that their
       // global-load latency hides behind the wait / the previous chunk's work
-      const bool vec32 = p.vec32 != 0;          // 32-byte (full-sector) global accesses: cout % 16 == 0, aligned bases
+      const bool vec32 = FAST || p.vec32 != 0;  // 32-byte (full-sector) global accesses: cout % 16 == 0, aligned bases
       const bool res_vec = p.res_mode != 0 && interior && vec32;
       uint32_t res_next[CHUNK / 2];
       constexpr int STEP = (BN / CHUNK >= 2) ? 2 * CHUNK : CHUNK;   // two warps interleave chunks when there are >= 2
       const int step_rt = alt ? CHUNK : STEP;                       // (alternate-tile mode: this warp takes every chunk)
       const int c_first = (!alt && BN / CHUNK >= 2) ? half * CHUNK : 0;
       const bool idle_half = !alt && (BN / CHUNK < 2) && half == 1; // a single chunk: the second warp only arrives
-      // (in a multi-convolution launch the residual may still be in the making: its dependency is awaited by the
-      // producer warp, which the accumulator wait below orders before us -- so no early fetch there)
       const bool res_first = res_vec && !idle_half && n0 + c_first + CHUNK <= p.cout;
-      if (res_first && deps == nullptr) {
+      if (res_first) {
 #pragma unroll
         for (int j = 0; j < CHUNK / 16; ++j) hn_ldg256(p.res + res_off + n0 + c_first + 16 * j, &res_next[8 * j]);
       }
 
-      if (dbg_flags & 16) {                      // experiment: one polling lane per warp
-        if (lane == 0) hn_mbar_wait(&tmem_full[buf], acc_phase);
-        __syncwarp();
-      } else {
-        hn_mbar_wait(&tmem_full[buf], acc_phase);
-      }
+      hn_mbar_wait(&tmem_full[buf], acc_phase);
       hn_tc_fence_after();
-      if (res_first && deps != nullptr) {
-#pragma unroll
-        for (int j = 0; j < CHUNK / 16; ++j) hn_ldg256(p.res + res_off + n0 + c_first + 16 * j, &res_next[8 * j]);
-      }
       if (warp == 2) hn_trace(trace, 2, tri, 2);
       const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + buf * BN;
 
       // Split-K: every work item stores its partial accumulator into its own slice of an fp32 scratch; the item that
       // arrives last (per-tile counter) adds the slices in split order -- a fixed summation order, so results do not
       // depend on which CTA finishes first -- and runs the epilogue.
-      const bool split = p.splits > 1;
+      const bool split = !FAST && splits > 1;
       bool finalize = true;
-      float* sk_row = split ? p.sk_ws + (size_t)m * p.sk_ld + n0 : nullptr;
-      const int ks_item = split ? w_ - st * splits : 0;
-      if (split) {
-        if constexpr (CHUNK == 32) {
+      float* sk_row = nullptr;
+      if constexpr (!FAST) {
+        if (split) {
+          sk_row = p.sk_ws + (size_t)m * p.sk_ld + n0;
+          const int ks_item = w_ - st * splits;
+          if constexpr (CHUNK == 32) {
 #pragma unroll 1
-          for (int c0 = c_first; c0 < (idle_half ? 0 : BN); c0 += STEP) {
-            if (n0 + c0 >= p.cout) continue;
-            uint32_t acc[32];
-            hn_tmem_ld32(t_row + c0, acc);
-            hn_tmem_ld_wait();
-            if (interior) {
-              float* dst = sk_row + (size_t)ks_item * p.sk_slice + c0;
+            for (int c0 = c_first; c0 < (idle_half ? 0 : BN); c0 += STEP) {
+              if (n0 + c0 >= p.cout) continue;
+              uint32_t acc[32];
+              hn_tmem_ld32(t_row + c0, acc);
+              hn_tmem_ld_wait();
+              if (interior) {
+                float* dst = sk_row + (size_t)ks_item * p.sk_slice + c0;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                __stcg(reinterpret_cast<float4*>(dst + j),
-                       make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
-                                   __uint_as_float(acc[j + 3])));
+                for (int j = 0; j < 32; j += 4)
+                  __stcg(reinterpret_cast<float4*>(dst + j),
+                         make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
+                                     __uint_as_float(acc[j + 3])));
+              }
             }
           }
+          hn_tc_fence_before();
+          __syncwarp();
+          if (lane == 0) hn_mbar_arrive(&tmem_empty[buf]);       // TMEM drained already
+          __threadfence();
+          hn_epi_bar_sync();
+          if (threadIdx.x == 64) {
+            const unsigned old = atomicAdd(p.sk_cnt + st, 1u);
+            const bool is_last = old == (unsigned)splits - 1u;
+            if (is_last) p.sk_cnt[st] = 0u;                      // everyone has arrived: reset for the next launch
+            *sk_flag = is_last ? 1u : 0u;
+          }
+          hn_epi_bar_sync();
+          finalize = *sk_flag != 0u;
+          if (finalize) __threadfence();
         }
-        hn_tc_fence_before();
-        __syncwarp();
-        if (lane == 0) hn_mbar_arrive(&tmem_empty[buf]);       // TMEM drained already
-        __threadfence();
-        hn_epi_bar_sync();
-        if (threadIdx.x == 64) {
-          const unsigned old = atomicAdd(p.sk_cnt + st, 1u);
-          const bool is_last = old == (unsigned)p.splits - 1u;
-          if (is_last) p.sk_cnt[st] = 0u;                      // everyone has arrived: reset for the next launch
-          *sk_flag = is_last ? 1u : 0u;
-        }
-        hn_epi_bar_sync();
-        finalize = *sk_flag != 0u;
-        if (finalize) __threadfence();
       }
 
-      // The chunk loop exists twice: FAST for the common case (bf16 output, every chunk complete, 32-byte accesses, no
-      // split-K) carries no per-element predicates; the general copy keeps the ragged / fp32-row / split-K paths.
-      // (Inside one body the compiler if-converts the slow paths into ~400 predicated-off instructions per chunk.)
-      auto run_chunks = [&](auto fast_tag) {
-        constexpr bool FAST = decltype(fast_tag)::value;
-      auto chunk_body = [&](const int c0, uint32_t (&acc)[CHUNK], const bool preloaded) {
+      auto chunk_body = [&](const int c0) {
+        uint32_t acc[CHUNK];
         uint32_t res_cur[CHUNK / 2];
 #pragma unroll
         for (int j = 0; j < CHUNK / 2; ++j) res_cur[j] = res_next[j];
@@ -866,14 +800,12 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
             }
           }
         } else {
-          if (!preloaded) {
-            if constexpr (CHUNK == 32) {
-              hn_tmem_ld32(t_row + c0, acc);
-            } else {
-              hn_tmem_ld16(t_row + c0, acc);
-            }
-            hn_tmem_ld_wait();
+          if constexpr (CHUNK == 32) {
+            hn_tmem_ld32(t_row + c0, acc);
+          } else {
+            hn_tmem_ld16(t_row + c0, acc);
           }
+          hn_tmem_ld_wait();
           if (warp == 2) hn_trace(trace, 2, tri, 4);
           if (!FAST && cbase >= p.cout) return;        // padded output channels (warp-uniform)
         }
@@ -929,14 +861,16 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
               if (cbase + j >= p.relu_lo && cbase + j < p.relu_hi) v[j] = fmaxf(v[j], 0.0f);
           }
         }
-        if (!FAST && p.out_kind == 1) {
-          if (interior) {
-            float* op = reinterpret_cast<float*>(p.out) + out_off + cbase;
+        if constexpr (!FAST) {
+          if (p.out_kind == 1) {
+            if (interior) {
+              float* op = reinterpret_cast<float*>(g_out) + out_off + cbase;
 #pragma unroll
-            for (int j = 0; j < CHUNK; ++j)
-              if (cbase + j < p.cout) op[j] = v[j];
+              for (int j = 0; j < CHUNK; ++j)
+                if (cbase + j < p.cout) op[j] = v[j];
+            }
+            return;
           }
-          return;
         }
         if (warp == 2) hn_trace(trace, 2, tri, 6);
         // bf16 outputs
@@ -944,8 +878,8 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
 #pragma unroll
         for (int j = 0; j < CHUNK; j += 2) packed[j / 2] = hn_pack_bf16(v[j], v[j + 1]);
         if (warp == 2) hn_trace(trace, 2, tri, 7);
-        if (interior && !(p.dbg_flags & 1)) {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + cbase;
+        if (interior && !HN_DBG(1)) {
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(g_out) + out_off + cbase;
           if (FAST || (cbase + CHUNK <= p.cout && vec32)) {
             // 32 bytes per lane and instruction: every store fills whole 32-byte sectors (16-byte stores at a 2*cout
             // byte lane stride left every sector half written and doubled the L2 requests)
@@ -1017,8 +951,9 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
                 const int k = lane >> 2;                         // value index: octet k/2, stat k&1
                 const int group = (cbase + (k >> 1) * 8) / p.gn_group_size;
                 if (group < p.gn_groups) {
-                  if (gn_smem) atomicAdd(&gn_acc[(warp_img * p.gn_groups + group) * 2 + (k & 1)], v8[0]);
-                  else atomicAdd(p.gn_stats + ((long long)warp_img * p.gn_groups + group) * 2 + (k & 1), (double)v8[0]);
+                  const unsigned long long fx = (unsigned long long)__float2ll_rn(v8[0] * GN_FIX_SCALE);
+                  if (gn_smem) atomicAdd(&gn_acc[g_gn_off + (warp_img * p.gn_groups + group) * 2 + (k & 1)], fx);
+                  else atomicAdd(g_gn_stats + ((long long)warp_img * p.gn_groups + group) * 2 + (k & 1), fx);
                 }
               }
             } else if (interior) {
@@ -1026,199 +961,55 @@ __device__ __forceinline__ void conv_roles(const CUtensorMap* tm_a_ptr, const CU
               for (int k = 0; k < 8; ++k) {
                 const int group = (cbase + (k >> 1) * 8) / p.gn_group_size;
                 if (group < p.gn_groups) {
-                  if (gn_smem) atomicAdd(&gn_acc[(img * p.gn_groups + group) * 2 + (k & 1)], v8[k]);
-                  else atomicAdd(p.gn_stats + ((long long)img * p.gn_groups + group) * 2 + (k & 1), (double)v8[k]);
+                  const unsigned long long fx = (unsigned long long)__float2ll_rn(v8[k] * GN_FIX_SCALE);
+                  if (gn_smem) atomicAdd(&gn_acc[g_gn_off + (img * p.gn_groups + group) * 2 + (k & 1)], fx);
+                  else atomicAdd(g_gn_stats + ((long long)img * p.gn_groups + group) * 2 + (k & 1), fx);
                 }
               }
             }
           }
         }
-            };
-      const int c_end = (idle_half || (p.dbg_flags & 2) || !finalize) ? 0 : BN;
-      // TMEM loads one chunk ahead (tcgen05.ld of chunk i+1 in flight while chunk i is scaled, packed and stored; two
-      // register sets, loop fully unrolled).  Measured A/B on one box: isolated 256-wide layers gain 5 % (layer3 34.2 ->
-      // 32.4 us) but the whole step loses 2 % (2108 -> 2066 frames/s; 48 bytes of spills at the 168-register cap), so
-      // it is compiled out.
-      constexpr bool TMEM_PREFETCH = false;
-      if constexpr (TMEM_PREFETCH && FAST && CHUNK == 32 && (BN / STEP) >= 2) {
-        if (c_first < c_end) {
-          uint32_t acc_a[CHUNK], acc_b[CHUNK];
-          hn_tmem_ld_chunk<CHUNK>(t_row + c_first, acc_a);
-#pragma unroll
-          for (int i = 0; i < BN / STEP; ++i) {
-            const int c0 = c_first + i * STEP;
-            hn_tmem_ld_wait();
-            if (i & 1) {
-              if (i + 1 < BN / STEP) hn_tmem_ld_chunk<CHUNK>(t_row + c0 + STEP, acc_a);
-              chunk_body(c0, acc_b, true);
-            } else {
-              if (i + 1 < BN / STEP) hn_tmem_ld_chunk<CHUNK>(t_row + c0 + STEP, acc_b);
-              chunk_body(c0, acc_a, true);
-            }
-          }
-        }
-      } else {
-#pragma unroll 1
-        for (int c0 = c_first; c0 < c_end; c0 += step_rt) {
-          uint32_t acc[CHUNK];
-          chunk_body(c0, acc, false);
-        }
-      }
       };
-      if (epi_fast) run_chunks(FastTag<true>{});
-      else run_chunks(FastTag<false>{});
+      const int c_end = (idle_half || HN_DBG(2) || !finalize) ? 0 : BN;
+      // (TMEM loads one chunk ahead -- tcgen05.ld of chunk i+1 in flight while chunk i is scaled, packed and stored -- were
+      // measured in round 1: isolated 256-wide layers +5 %, the whole step -2 % with 48 bytes of spills at the 168-register
+      // cap; not built.)
+#pragma unroll 1
+      for (int c0 = c_first; c0 < c_end; c0 += step_rt) chunk_body(c0);
       // accumulator buffer drained -> hand it back to the MMA warp (split-K items did so after their reduction)
       if (!split) {
         hn_tc_fence_before();
         __syncwarp();
         if (lane < (alt ? 2 : 1)) hn_mbar_arrive(&tmem_empty[buf]);
       }
-      if (deps != nullptr && finalize) {                  // this (m, n) output tile is in global memory: tell the consumers
-        __threadfence();
-        hn_epi_bar_sync();
-        if (threadIdx.x == 64) atomicAdd(deps->done + mt, 1u);
-      }
       if (warp == 2) hn_trace(trace, 2, tri, 3);
     }
     if (gn_smem) {
       hn_epi_bar_sync();
-      for (int i = threadIdx.x - 64; i < gn_vals; i += EPI_THREADS) {
-        const float v = gn_acc[i];
-        if (v != 0.f) atomicAdd(p.gn_stats + i, (double)v);
+      if constexpr (SEG) {
+        for (int s = 0; s < p.n_seg; ++s) {
+          const int cnt = p.seg[s].n_img * p.gn_groups * 2, off = p.seg[s].gn_off;
+          for (int i = threadIdx.x - 64; i < cnt; i += EPI_THREADS) {
+            const unsigned long long v = gn_acc[off + i];
+            if (v != 0ull) atomicAdd(p.seg[s].gn_stats + i, v);
+          }
+        }
+      } else {
+        for (int i = threadIdx.x - 64; i < gn_vals; i += EPI_THREADS) {
+          const unsigned long long v = gn_acc[i];
+          if (v != 0ull) atomicAdd(p.gn_stats + i, v);
+        }
       }
     }
   }
 
-}
-
-// Barrier init, TMEM allocation.  Returns the TMEM base address.
-template <int BN, int CS>
-__device__ __forceinline__ uint32_t conv_prologue(uint8_t* smem_hdr, const CUtensorMap* pf_a, const CUtensorMap* pf_b) {
-  using C = Cfg<BN>;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_hdr);
-  uint64_t* a_full = bars;
-  uint64_t* a_empty = bars + MAX_STAGES;
-  uint64_t* b_full_ring = bars + 2 * MAX_STAGES;
-  uint64_t* b_empty = bars + 3 * MAX_STAGES;
-  uint64_t* tmem_full = bars + 4 * MAX_STAGES;
-  uint64_t* tmem_empty = tmem_full + 8;
-  uint64_t* b_full = tmem_empty + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
-  if (threadIdx.x == 0) {
-    if (pf_a) hn_tma_prefetch_desc(pf_a);
-    if (pf_b) hn_tma_prefetch_desc(pf_b);
-    for (int s = 0; s < MAX_STAGES; ++s) {
-      hn_mbar_init(&a_full[s], 1);
-      hn_mbar_init(&a_empty[s], 1);      // A boxes are private to the CTA
-      hn_mbar_init(&b_full_ring[s], 1);
-      hn_mbar_init(&b_empty[s], CS);     // every CTA of the cluster releases the slot (its peers write into it)
-    }
-    hn_mbar_init(b_full, 1);
-    for (int b = 0; b < 8; ++b) {
-      hn_mbar_init(&tmem_full[b], 1);
-      hn_mbar_init(&tmem_empty[b], EPI_WARPS);   // one arrive per epilogue warp
-    }
-    hn_mbar_init_fence();
-  }
-  if ((threadIdx.x >> 5) == 1) hn_tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  // ---- teardown ----
   hn_tc_fence_before();
   __syncthreads();
-  if constexpr (CS > 1) hn_cluster_sync();   // peers' barriers must exist before anyone signals them
-  hn_tc_fence_after();
-  return *tmem_slot;
-}
-
-template <int BN, int CS>
-__device__ __forceinline__ void conv_teardown(uint32_t tmem_base) {
-  using C = Cfg<BN>;
-  hn_tc_fence_before();
-  __syncthreads();
-  if constexpr (CS > 1) hn_cluster_sync();   // no CTA may retire while a peer can still signal its barriers
   if ((threadIdx.x >> 5) == 1) {
     hn_tc_fence_after();
     hn_tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
-}
-
-// CS = thread-block cluster size along M: the CS CTAs of a cluster work on CS consecutive M tiles of the same N
-// tile in lock step; each loads 1/CS of the B (weight) tile and multicasts it to all of them.  RB = the layer's
-// whole weight slice stays resident in shared memory.
-template <int BN, int CS, bool RB>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                  const __grid_constant__ ConvParams p) {
-  static_assert(CS == 1 || (BN / CS) % 8 == 0, "B slices must keep whole 8-row swizzle atoms");
-  static_assert(!(RB && CS > 1), "resident weights are per CTA");
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem_hdr = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t tmem_base = conv_prologue<BN, CS>(smem_hdr, &tm_a, &tm_b);
-  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may run
-  // while the previous kernel of the stream is still draining; global memory is touched only after the wait.
-  // The early trigger lets the next kernel do the same under this one.
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  PipeState ps = {0, 0, 0, 0u, 0u};
-  conv_roles<BN, CS, RB>(&tm_a, &tm_b, p, smem_hdr, tmem_base, blockIdx.x / CS, gridDim.x / CS, ps, true);
-  conv_teardown<BN, CS>(tmem_base);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Several dependent convolutions in ONE launch (the 67 tiny convolutions of the A2J pose net cost ~10 us of fixed
-// latency each as separate launches).  `phases` lists the convolutions in a dependency-consistent order; tiles
-// synchronise by dataflow (ConvDeps): hn_conv_multi_build finds, from the buffer pointers, which earlier convolution
-// writes each input / residual and which of its M tiles every tile reads.  Launched cooperatively so that all CTAs are
-// resident (a waiting tile's producers must be able to run).
-// ---------------------------------------------------------------------------------------------------------------
-struct PhaseDesc {
-  CUtensorMap ta;
-  CUtensorMap tb;
-  ConvParams p;
-};
-
-template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_multi_kernel(const PhaseDesc* __restrict__ phases, int n_convs, long long* __restrict__ conv_clock) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem_hdr = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t tmem_base = conv_prologue<BN, 1>(smem_hdr, nullptr, nullptr);
-  PipeState ps = {0, 0, 0, 0u, 0u};
-  // Every role walks the convolutions in order, straight from the plan in global memory: no block-wide or grid-wide
-  // barrier between convolutions.  The producer warp of a tile waits for the producer tiles it reads (ConvDeps), the
-  // epilogue announces finished tiles; the roles of one CTA may be in different convolutions at the same time.
-  // Each role keeps its own copy of the current convolution's parameters in shared memory (the GroupNorm accumulator
-  // area, unused here): read straight from the plan in global memory, the per-step parameter reads of the role loops
-  // miss the small L1 and cost an L2 round trip each.
-  static_assert(3 * sizeof(ConvParams) <= GN_SMEM_FLOATS * 4, "role parameter slots do not fit");
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-  const int role = warp < 2 ? warp : 2;
-  ConvParams* slot = reinterpret_cast<ConvParams*>(smem_hdr + HDR_BARS) + role;
-  int tile_off = 0;                                      // tiles are dealt round-robin over the CTAs, continuing across convs
-  for (int j = 0; j < n_convs; ++j) {
-    {
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(&phases[j].p);
-      uint32_t* dst = reinterpret_cast<uint32_t*>(slot);
-      constexpr int WORDS = (int)(sizeof(ConvParams) / 4);
-      if (role == 2) {
-        hn_epi_bar_sync();                               // every epilogue warp is done with the previous convolution
-        for (int i = threadIdx.x - 64; i < WORDS; i += EPI_THREADS) dst[i] = __ldg(src + i);
-        hn_epi_bar_sync();
-      } else {
-        for (int i = threadIdx.x & 31; i < WORDS; i += 32) dst[i] = __ldg(src + i);
-        __syncwarp();
-      }
-    }
-    if (role == 0 && (threadIdx.x & 31) == 0 && j + 1 < n_convs) {   // descriptors of the next convolution -> descriptor cache
-      hn_tma_prefetch_desc(&phases[j + 1].ta);
-      hn_tma_prefetch_desc(&phases[j + 1].tb);
-    }
-    const ConvParams& cp = *slot;
-    const int tiles = cp.m_tiles * cp.n_tiles * cp.splits;
-    int first = ((int)blockIdx.x - tile_off) % (int)gridDim.x;
-    if (first < 0) first += gridDim.x;
-    conv_roles<BN, 1, false>(&phases[j].ta, &phases[j].tb, cp, smem_hdr, tmem_base, first, gridDim.x, ps);
-    tile_off = (tile_off + tiles) % (int)gridDim.x;
-    if (conv_clock != nullptr && blockIdx.x == 0 && threadIdx.x == 64) conv_clock[j] = clock64();   // bring-up only
-  }
-  conv_teardown<BN, 1>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1268,37 +1059,28 @@ bool pdl_enabled() {
   return v == 1;
 }
 
-template <int BN, int CS, bool RB>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t st) {
-  using C = Cfg<BN>;
+template <int BN, int PIPE, bool FAST, bool SEG>
+int launch(const CUtensorMap* ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t st) {
   constexpr int SMEM = SMEM_BYTES_ALL;
   static bool attr_set = false;
   if (!attr_set) {
-    HN_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, CS, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HN_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, PIPE, FAST, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        SMEM));
     attr_set = true;
   }
-  const int super = hn_div_up(p.m_tiles, CS) * p.n_tiles * p.splits;
+  const int items = p.m_tiles * p.n_tiles * p.splits;
   // equal work per CTA: with w = ceil(tiles / SMs) waves, ceil(tiles / w) CTAs finish at the same time as a full grid
-  // would and leave the other SMs to kernels of concurrent streams (graph branches)
-  const int max_clusters = hn_num_sms() / CS;
-  const int waves = hn_div_up(super, max_clusters);
-  const int clusters = hn_div_up(super, waves);
+  // would and leave the other SMs to kernels of concurrent streams (graph branches, the pose net of the previous step)
+  const int waves = hn_div_up(items, hn_num_sms());
+  const int ctas = hn_div_up(items, waves);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(clusters * CS);
+  cfg.gridDim = dim3(ctas);
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[1];
   int na = 0;
-  if (CS > 1) {
-    attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = CS;
-    attr[na].val.clusterDim.y = 1;
-    attr[na].val.clusterDim.z = 1;
-    ++na;
-  }
   if (pdl_enabled()) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
@@ -1306,7 +1088,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cu
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, CS, RB>, ta, tb, p));
+  HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, PIPE, FAST, SEG>, ta[0], ta[1], ta[2], tb, p));
   hn_count_launch();
   return HN_OK;
 }
@@ -1350,15 +1132,6 @@ void fastdiv(uint32_t d, uint32_t* mul, int* sh) {
   *sh = l;
 }
 
-bool patch_enabled() {          // HN_CONV_PATCH=1|0: patch tiles for the resident-weights 3x3 layers (see PATCH_H)
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("HN_CONV_PATCH");
-    v = (e && e[0] != '0') ? 1 : 0;
-  }
-  return v == 1;
-}
-
 int epi_alt_max_bn() {          // HN_EPI_ALT=<bn>: widest single-N-tile layer whose epilogue warps take alternate tiles
   static int v = -1;
   if (v < 0) {
@@ -1380,13 +1153,14 @@ int split_min_kb() {            // experiment knob: HN_SPLIT_MIN_KB (k-blocks a 
 struct BuiltConv {
   ConvParams p;
   CUtensorMap ta, tb;
-  int bn, cs;
+  int bn;
   bool rb;
 };
 
-// Validate a descriptor and derive kernel parameters + tensor maps.  force_bn > 0 pins the tile width (and disables
-// clusters / resident weights), as the multi-convolution kernel needs.
-int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
+// Validate a descriptor and derive kernel parameters + tensor maps.  total_m_tiles > 0: the descriptor is one segment of
+// a multi-segment launch -- tile width and pipeline are chosen for the launch's total number of M tiles, force_bn pins the
+// width the first segment chose.
+int build_conv(const hn_conv_desc* d, int force_bn, int total_m_tiles, BuiltConv* out) {
   HN_REQUIRE(d && d->in && d->weight && d->out, "hn_conv2d_bf16: null pointer");
   HN_REQUIRE(d->cin > 0 && d->cin % BLOCK_K == 0, "hn_conv2d_bf16: cin=%d must be a multiple of 64", d->cin);
   HN_REQUIRE(d->kh == d->kw && (d->kh == 1 || d->kh == 3), "hn_conv2d_bf16: only 1x1 and 3x3 kernels (got %dx%d)",
@@ -1421,7 +1195,7 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
   p.m_tiles = hn_div_up(p.rows, BLOCK_M);
   const bool stem = d->stem_pitch_w > 0;
   if (stem) {
-    HN_REQUIRE(!force_bn && d->kh == 1 && d->stride == 1 && d->cin == 256 && d->halo_in == 0 && d->in_phases == 1 &&
+    HN_REQUIRE(!total_m_tiles && d->kh == 1 && d->stride == 1 && d->cin == 256 && d->halo_in == 0 && d->in_phases == 1 &&
                    d->cout_pad <= 128 && !d->res && !d->gn_stats && !d->splitk_ws,
                "hn_conv2d_bf16: a direct stem is a plain 1x1-over-patches convolution with cin = 256, cout_pad <= 128");
     HN_REQUIRE(d->stem_pitch_h >= 2 * d->h + 6 && d->stem_pitch_h % 2 == 0 && d->stem_pitch_w >= 2 * d->w + 8,
@@ -1431,31 +1205,25 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
     p.stem_h = d->h;
     p.m_tiles = d->n * d->h * p.stem_tpr;
   }
+  const int sched_m_tiles = total_m_tiles > 0 ? total_m_tiles : p.m_tiles;     // tiles the launch spreads over the SMs
   int bn = force_bn ? force_bn
                     : (d->block_n ? d->block_n
-                                  : pick_block_n(d->cout_pad, p.m_tiles, p.num_taps * p.cin_chunks, d->gn_stats ? 32 : 16));
+                                  : pick_block_n(d->cout_pad, sched_m_tiles, p.num_taps * p.cin_chunks, d->gn_stats ? 32 : 16));
   HN_REQUIRE((bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256) && d->cout_pad % bn == 0,
              "hn_conv2d_bf16: block_n=%d does not divide cout_pad=%d", bn, d->cout_pad);
   p.n_tiles = d->cout_pad / bn;
-  // cluster of 2 with multicast weights when there is at least one pair of M tiles per SM pair
-  // measured: pairs with multicast weights gain ~3 % on 256-wide tiles and lose elsewhere -> opt-in only
-  int cs = (d->cluster && !force_bn) ? d->cluster : 1;
-  HN_REQUIRE(cs == 1 || (cs == 2 && bn == 256), "hn_conv2d_bf16: cluster=%d unsupported with block_n=%d", cs, bn);
+  // (CTA pairs that multicast the weight tile were measured in round 1: +-1 %; not built any more)
+  HN_REQUIRE(d->cluster == 0 || d->cluster == 1, "hn_conv2d_bf16: cluster=%d is not supported (CTA-pair multicast was removed)",
+             d->cluster);
   // resident weights: the layer's whole weight slice stays in shared memory and only A boxes stream, when it is one
   // narrow N tile whose weights fit next to >= 4 A slots and there are enough tiles per CTA to amortise the load
   const int k_blocks_total = p.num_taps * p.cin_chunks;
   const long long b_bytes = (long long)k_blocks_total * bn * BLOCK_K * 2;
-  bool rb = !force_bn && cs == 1 && p.n_tiles == 1 && bn <= 64 && b_bytes <= PIPE_BYTES_MAX - 4 * A_SLOT_BYTES &&
-            p.m_tiles >= 2 * hn_num_sms() && !(d->debug & 16) && !stem;
+  bool rb = p.n_tiles == 1 && bn <= 64 && b_bytes <= PIPE_BYTES_MAX - 4 * A_SLOT_BYTES &&
+            sched_m_tiles >= 2 * hn_num_sms() && !(d->debug & 16) && !stem;
   const bool uni = bn <= 128 && !rb;      // unified stages (must match the kernel's constexpr UNI)
   const bool rb3 = rb && d->kh == 3 && d->stride == 1 && !(d->debug & 32) &&
                    PIPE_BYTES_MAX - b_bytes >= 2 * 3 * A_SLOT_BYTES && p.rows > 2 * d->dilation * p.wp;
-  // patch tiles (see PATCH_H): large maps only -- a 16 x 8 patch grid wastes too much on small ones.  Measured neutral
-  // (layer1 60.4 vs 58.4 us, whole step 3.88-3.91 vs 3.89-3.90 ms: these layers are bound by the MMA-issuing warp, not by
-  // L2 -> SM traffic), so it is opt-in: debug bit 14 or HN_CONV_PATCH=1.
-  const bool patch = rb3 && d->dilation == 1 && d->halo_in >= 1 && d->h >= 64 && d->w >= 64 &&
-                     ((d->debug & 16384) || patch_enabled());
-
   // A-box groups.  Pixel (oh*stride + dr, ow*stride + ds) of tap (r, s), dr = (r - kh/2)*dil, ds = (s - kw/2)*dil, is row
   // m + shift of the (phase) matrix; taps of one kernel row whose shifts differ by a few rows share one box.
   int box_rows = BLOCK_M, a_planes = 1, b_tiles = 1;
@@ -1524,9 +1292,7 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
     p.uni_plane_bytes = box_rows * BLOCK_K * 2;
     p.uni_a_bytes = a_planes * p.uni_plane_bytes;
     p.uni_b_bytes = b_tiles * bn * BLOCK_K * 2;
-    // convolutions chained in one multi-convolution launch share the ring: same stage stride and depth for all of
-    // them (the largest stage: two 136-row planes + three weight tiles)
-    p.uni_stride = force_bn ? 2 * A_SLOT_BYTES + 3 * bn * BLOCK_K * 2 : p.uni_a_bytes + p.uni_b_bytes;
+    p.uni_stride = p.uni_a_bytes + p.uni_b_bytes;
     int stages = PIPE_BYTES_MAX / p.uni_stride;
     p.uni_stages = stages > MAX_STAGES ? MAX_STAGES : stages;
     HN_REQUIRE(p.uni_stages >= 2 && p.uni_a_bytes + p.uni_b_bytes <= p.uni_stride,
@@ -1538,13 +1304,7 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
     p.rb_b_bytes = (int)b_bytes;
     p.rb3 = rb3 ? 1 : 0;
     if (rb3) p.a_box_bytes = 3 * A_SLOT_BYTES;
-    if (patch) {
-      p.patch_tx = hn_div_up(d->w, PATCH_W);
-      p.patch_ty = hn_div_up(d->h, PATCH_H);
-      p.m_tiles = d->n * p.patch_tx * p.patch_ty;
-      p.a_box_bytes = PATCH_BOX_BYTES;
-    }
-    const int slots = (PIPE_BYTES_MAX - p.rb_b_bytes) / (patch ? PATCH_SLOT_BYTES : (rb3 ? 3 * A_SLOT_BYTES : A_SLOT_BYTES));
+    const int slots = (PIPE_BYTES_MAX - p.rb_b_bytes) / (rb3 ? 3 * A_SLOT_BYTES : A_SLOT_BYTES);
     p.na_stages = slots > MAX_STAGES ? MAX_STAGES : slots;
     p.nb_stages = 1;
   } else {
@@ -1593,7 +1353,7 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
             (reinterpret_cast<uintptr_t>(d->res) % 32 == 0) && (reinterpret_cast<uintptr_t>(d->out_phase) % 32 == 0);
   p.trace = reinterpret_cast<long long*>(d->trace);
   p.dbg_flags = (d->debug >> 6) & 255;     // bit0: no epilogue stores, bit1: no epilogue work at all (timing experiments)
-  p.gn_stats = d->gn_stats;
+  p.gn_stats = reinterpret_cast<unsigned long long*>(d->gn_stats);
   if (p.gn_stats) {
     HN_REQUIRE(d->gn_groups > 0 && d->cout % d->gn_groups == 0, "hn_conv2d_bf16: gn_groups");
     p.gn_groups = d->gn_groups;
@@ -1605,7 +1365,7 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
 
   // split-K (needs caller-provided scratch): short, deep layers whose tiles cannot fill the GPU
   p.splits = 1;
-  if (d->splitk_ws && d->splitk_counters && cs == 1 && bn >= 32) {
+  if (d->splitk_ws && d->splitk_counters && bn >= 32 && !total_m_tiles) {
     const int k_steps = p.k_steps;
     const int tiles = p.m_tiles * p.n_tiles;
     int sp = d->splits;
@@ -1638,7 +1398,7 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
       p.sk_ld = d->cout_pad;
     }
   }
-  p.epi_alt = (!force_bn && p.n_tiles == 1 && p.splits == 1 && !(d->debug & 32768) &&
+  p.epi_alt = (p.n_tiles == 1 && p.splits == 1 && !(d->debug & 32768) &&
                ((d->debug & 65536) || bn <= epi_alt_max_bn())) ? 1 : 0;
   CUtensorMap& ta = out->ta;
   CUtensorMap& tb = out->tb;
@@ -1672,23 +1432,13 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
       p.k_steps = p.cin_chunks;
       p.uni_a_bytes = p.uni_plane_bytes;
       p.uni_b_bytes = bn * BLOCK_K * 2;
-      if (!force_bn) {
-        p.uni_stride = p.uni_a_bytes + p.uni_b_bytes;
-        const int stages = PIPE_BYTES_MAX / p.uni_stride;
-        p.uni_stages = p.na_stages = stages > MAX_STAGES ? MAX_STAGES : stages;
-      }
+      p.uni_stride = p.uni_a_bytes + p.uni_b_bytes;
+      const int stages = PIPE_BYTES_MAX / p.uni_stride;
+      p.uni_stages = p.na_stages = stages > MAX_STAGES ? MAX_STAGES : stages;
       if (p.splits > p.k_steps) p.splits = p.k_steps;
     }
   }
-  if (patch) {
-    // the haloed NHWC tensor itself: (channels, padded columns, padded rows, images); out-of-range rows / columns of the
-    // last patches are zero-filled by the TMA unit
-    const cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)p.wp, (cuuint64_t)p.hp, (cuuint64_t)d->n};
-    const cuuint64_t strides[3] = {(cuuint64_t)d->cin * 2, (cuuint64_t)p.wp * d->cin * 2, (cuuint64_t)p.hp * p.wp * d->cin * 2};
-    const cuuint32_t box[4] = {BLOCK_K, PATCH_W + 2, PATCH_H + 2, 1};
-    int rc = make_map(&ta, d->in, 4, dims, strides, box);
-    if (rc) return rc;
-  } else if (!stem && !(uni && p.uni_a_rank4)) {
+  if (!stem && !(uni && p.uni_a_rank4)) {
     // dims (channels, rows, phases); unified stride-2 3x3: the box spans both column phases of a row phase.
     // rb3: the third dimension steps by one (dilated) image row instead -- an overlapping view of the same matrix;
     // its row count is cut by two image rows so that row + 2 * wp stays inside the allocation (the rows cut off are the
@@ -1715,210 +1465,119 @@ int build_conv(const hn_conv_desc* d, int force_bn, BuiltConv* out) {
     // [k_block][cout_pad][64] bf16: a 2-D matrix of 128-byte rows, row = k_block * cout_pad + n
     const cuuint64_t dims[2] = {(cuuint64_t)BLOCK_K, (cuuint64_t)k_blocks_total * d->cout_pad};
     const cuuint64_t strides[1] = {(cuuint64_t)BLOCK_K * 2};
-    const cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)(bn / cs)};
+    const cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)bn};
     int rc = make_map(&tb, d->weight, 2, dims, strides, box);
     if (rc) return rc;
   }
   out->p = p;
   out->bn = bn;
-  out->cs = cs;
   out->rb = rb;
   return HN_OK;
 }
 
-constexpr int MULTI_BN = 64;
+// Pick the instantiation: operand pipeline by tile width / resident weights, FAST epilogue when the layer qualifies.
+bool epi_fast_ok(const ConvParams& p) {
+  // bf16 output, cout a multiple of the chunk width (no ragged chunks) and no padded N tile (the FAST body does not
+  // skip chunks beyond cout: with cout_pad > cout they would land on the next pixel), 32-byte aligned rows, no split-K
+  return p.out_kind == 0 && p.vec32 != 0 && (p.cout % 32) == 0 && p.cout_pad == p.cout && p.splits == 1 &&
+         !(p.dbg_flags & 64);
+}
 
-// device layout of a plan: [counters: n_convs x MULTI_MAX_MT uint32][PhaseDesc array][ConvDeps array][dep tables]
-constexpr int MULTI_MAX_MT = 1024;      // M tiles per convolution (the pose net's largest layer has 133)
-size_t multi_phases_off(int n_convs) { return (((size_t)n_convs * MULTI_MAX_MT * 4 + 255) / 256) * 256; }
-size_t multi_deps_off(int n_convs) { return multi_phases_off(n_convs) + (((size_t)n_convs * sizeof(PhaseDesc) + 255) / 256) * 256; }
-size_t multi_tabs_off(int n_convs) { return multi_deps_off(n_convs) + (((size_t)n_convs * sizeof(ConvDeps) + 255) / 256) * 256; }
-size_t multi_total(int n_convs) { return multi_tabs_off(n_convs) + (size_t)n_convs * MAX_DEPS * 2 * MULTI_MAX_MT * sizeof(short) + 256; }
-
-// Which producer M tiles does M tile `mt` of a consumer read?  `rows_lo..rows_hi` = the consumer's rows (in the geometry
-// of the buffer `geo` describes) that the tile touches; the answer is conservative (whole image rows).
-struct BufGeo {        // a haloed NHWC buffer as a consumer sees it, or the phase-split copy (phases = 4)
-  int n, hp, wp, halo, phases;
-};
-void producer_tile_range(const BufGeo& g, long long rows_lo, long long rows_hi, const ConvParams& prod, int* t_first,
-                         int* t_last) {
-  const long long img_rows = (long long)g.hp * g.wp, total = (long long)g.n * img_rows;
-  *t_first = 1;
-  *t_last = 0;                                         // empty by default
-  if (rows_lo < 0) rows_lo = 0;
-  if (rows_hi >= total) rows_hi = total - 1;
-  if (rows_lo > rows_hi) return;
-  const int H = g.hp - 2 * g.halo;                     // interior size of the consumer's view
-  const int img_lo = (int)(rows_lo / img_rows), img_hi = (int)(rows_hi / img_rows);
-  int h_lo = (int)((rows_lo - img_lo * img_rows) / g.wp) - g.halo, h_hi = (int)((rows_hi - img_hi * img_rows) / g.wp) - g.halo;
-  if (h_lo < 0) h_lo = 0;
-  if (h_hi > H - 1) h_hi = H - 1;
-  // pixel rows of the producer's OUTPUT grid: the same grid, or twice as fine when the consumer reads the phase split
-  const int ph = prod.hp - 2 * prod.halo, pw = prod.wp - 2 * prod.halo;      // producer output size (= its compute grid)
-  int y_lo = g.phases == 4 ? 2 * h_lo : h_lo, y_hi = g.phases == 4 ? 2 * h_hi + 1 : h_hi;
-  if (y_hi > ph - 1) y_hi = ph - 1;
-  if (img_lo == img_hi && y_lo > y_hi) return;         // only halo rows
-  if (y_lo > ph - 1) y_lo = ph - 1;
-  const long long p_img = (long long)prod.hp * prod.wp;
-  const long long m_lo = img_lo * p_img + (long long)(y_lo + prod.halo) * prod.wp + prod.halo;
-  const long long m_hi = img_hi * p_img + (long long)(y_hi + prod.halo) * prod.wp + prod.halo + pw - 1;
-  *t_first = (int)(m_lo / BLOCK_M);
-  *t_last = (int)(m_hi / BLOCK_M);
+template <bool SEG>
+int dispatch(const BuiltConv& b, const CUtensorMap* ta, cudaStream_t st) {
+  const ConvParams& p = b.p;
+  const CUtensorMap& tb = b.tb;
+  const bool fast = epi_fast_ok(p);
+  if constexpr (SEG) {
+    // segment launches: the 256-wide tower layers (FAST) and the 16-wide output convolutions (fp32 rows)
+    if (b.bn == 256 && fast) return launch<256, PIPE_RING, true, true>(ta, tb, p, st);
+    if (b.bn == 16 && b.rb && !fast) return launch<16, PIPE_RB, false, true>(ta, tb, p, st);
+    hn_set_error("hn_conv2d_bf16_levels: unsupported combination (block_n=%d resident=%d fast=%d); supported: 256-wide bf16 "
+                 "layers with cout %% 32 == 0 and 16-wide fp32-row outputs", b.bn, (int)b.rb, (int)fast);
+    return HN_ERR_ARG;
+  } else {
+    if (b.rb) {
+      switch (b.bn) {
+        case 64: return fast ? launch<64, PIPE_RB, true, false>(ta, tb, p, st) : launch<64, PIPE_RB, false, false>(ta, tb, p, st);
+        case 32: return fast ? launch<32, PIPE_RB, true, false>(ta, tb, p, st) : launch<32, PIPE_RB, false, false>(ta, tb, p, st);
+        default: return launch<16, PIPE_RB, false, false>(ta, tb, p, st);
+      }
+    }
+    switch (b.bn) {
+      case 256: return fast ? launch<256, PIPE_RING, true, false>(ta, tb, p, st) : launch<256, PIPE_RING, false, false>(ta, tb, p, st);
+      case 128: return fast ? launch<128, PIPE_UNI, true, false>(ta, tb, p, st) : launch<128, PIPE_UNI, false, false>(ta, tb, p, st);
+      case 64: return fast ? launch<64, PIPE_UNI, true, false>(ta, tb, p, st) : launch<64, PIPE_UNI, false, false>(ta, tb, p, st);
+      case 32: return fast ? launch<32, PIPE_UNI, true, false>(ta, tb, p, st) : launch<32, PIPE_UNI, false, false>(ta, tb, p, st);
+      default: return launch<16, PIPE_UNI, false, false>(ta, tb, p, st);
+    }
+  }
 }
 
 }  // namespace
 
 extern "C" int hn_conv2d_bf16(const hn_conv_desc* d, void* stream) {
   BuiltConv b;
-  int rc = build_conv(d, 0, &b);
+  int rc = build_conv(d, 0, 0, &b);
   if (rc) return rc;
-  const ConvParams& p = b.p;
-  const CUtensorMap& ta = b.ta;
-  const CUtensorMap& tb = b.tb;
-  const int bn = b.bn, cs = b.cs;
-  const bool rb = b.rb;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (rb) {
-    switch (bn) {
-      case 64: return launch<64, 1, true>(ta, tb, p, st);
-      case 32: return launch<32, 1, true>(ta, tb, p, st);
-      default: return launch<16, 1, true>(ta, tb, p, st);
-    }
-  }
-  if (cs == 2) {
-    switch (bn) {
-      case 256: return launch<256, 2, false>(ta, tb, p, st);
-      case 128: return launch<128, 2, false>(ta, tb, p, st);
-      default: return launch<64, 2, false>(ta, tb, p, st);
-    }
-  }
-  switch (bn) {
-    case 256: return launch<256, 1, false>(ta, tb, p, st);
-    case 128: return launch<128, 1, false>(ta, tb, p, st);
-    case 64: return launch<64, 1, false>(ta, tb, p, st);
-    case 32: return launch<32, 1, false>(ta, tb, p, st);
-    default: return launch<16, 1, false>(ta, tb, p, st);
-  }
+  b.p.n_seg = 1;
+  const CUtensorMap ta[3] = {b.ta, b.ta, b.ta};
+  return dispatch<false>(b, ta, reinterpret_cast<cudaStream_t>(stream));
 }
 
-static long long* g_multi_trace = nullptr;
-// Bring-up only: when set, CTA 0 of every following hn_conv_multi_run writes clock64() after each group into buf[g].
-extern "C" int hn_conv_multi_set_trace(void* buf) {
-  g_multi_trace = reinterpret_cast<long long*>(buf);
-  return HN_OK;
-}
-
-extern "C" int64_t hn_conv_multi_plan_bytes(int n_convs, int n_groups) {
-  (void)n_groups;
-  return (int64_t)multi_total(n_convs);
-}
-
-extern "C" int hn_conv_multi_build(const hn_conv_desc* descs, int n_convs, const int* group_begin_host, int n_groups,
-                                   void* plan_dev, int64_t plan_bytes) {
-  HN_REQUIRE(descs && group_begin_host && plan_dev && n_convs > 0 && n_groups > 0, "hn_conv_multi_build: bad arguments");
-  HN_REQUIRE(plan_bytes >= hn_conv_multi_plan_bytes(n_convs, n_groups), "hn_conv_multi_build: plan buffer too small");
-  HN_REQUIRE((reinterpret_cast<uintptr_t>(plan_dev) & 255) == 0, "hn_conv_multi_build: plan buffer must be 256-byte aligned");
-  HN_REQUIRE(group_begin_host[0] == 0 && group_begin_host[n_groups] == n_convs, "hn_conv_multi_build: group table");
-  std::vector<uint8_t> host(multi_total(n_convs), 0);
-  uint8_t* dev = reinterpret_cast<uint8_t*>(plan_dev);
-  PhaseDesc* ph = reinterpret_cast<PhaseDesc*>(host.data() + multi_phases_off(n_convs));
-  ConvDeps* deps = reinterpret_cast<ConvDeps*>(host.data() + multi_deps_off(n_convs));
-  short* tabs = reinterpret_cast<short*>(host.data() + multi_tabs_off(n_convs));
-  auto dev_cnt = [&](int j) { return reinterpret_cast<unsigned*>(dev) + (size_t)j * MULTI_MAX_MT; };
-  auto dev_tab = [&](int j, int d, int which) {
-    return reinterpret_cast<short*>(dev + multi_tabs_off(n_convs)) + ((size_t)(j * MAX_DEPS + d) * 2 + which) * MULTI_MAX_MT;
-  };
-  auto host_tab = [&](int j, int d, int which) { return tabs + ((size_t)(j * MAX_DEPS + d) * 2 + which) * MULTI_MAX_MT; };
-  int max_group_tiles = 1;
-  for (int g = 0; g < n_groups; ++g) {
-    HN_REQUIRE(group_begin_host[g + 1] > group_begin_host[g], "hn_conv_multi_build: empty group %d", g);
-    int tiles = 0;
-    for (int j = group_begin_host[g]; j < group_begin_host[g + 1]; ++j) {
-      HN_REQUIRE(descs[j].cout_pad % MULTI_BN == 0, "hn_conv_multi_build: conv %d: cout_pad %% 64 != 0", j);
-      HN_REQUIRE(descs[j].gn_stats == nullptr, "hn_conv_multi_build: GroupNorm statistics are not supported here");
-      BuiltConv b;
-      int rc = build_conv(&descs[j], MULTI_BN, &b);
+// One launch over several pyramid levels that share the convolution's weights (see the header).
+extern "C" int hn_conv2d_bf16_levels(const hn_conv_desc* descs, int n_levels, void* stream) {
+  HN_REQUIRE(descs && n_levels >= 1 && n_levels <= MAX_SEGS, "hn_conv2d_bf16_levels: 1..%d levels (got %d)", MAX_SEGS, n_levels);
+  if (n_levels == 1) return hn_conv2d_bf16(descs, stream);
+  int total_tiles = 0;
+  for (int i = 0; i < n_levels; ++i) {
+    const hn_conv_desc& d = descs[i];
+    const hn_conv_desc& d0 = descs[0];
+    HN_REQUIRE(d.in && d.out, "hn_conv2d_bf16_levels: level %d: null pointer", i);
+    HN_REQUIRE(d.weight == d0.weight && d.scale == d0.scale && d.shift == d0.shift && d.cin == d0.cin && d.cout == d0.cout &&
+                   d.cout_pad == d0.cout_pad && d.kh == d0.kh && d.kw == d0.kw && d.dilation == d0.dilation &&
+                   d.relu_lo == d0.relu_lo && d.relu_hi == d0.relu_hi && d.halo_in == d0.halo_in && d.out_kind == d0.out_kind &&
+                   d.out_halo == d0.out_halo && d.out_ld == d0.out_ld && d.out_rows_per_image == d0.out_rows_per_image &&
+                   d.out_transpose_hw == d0.out_transpose_hw && d.gn_groups == d0.gn_groups &&
+                   (d.gn_stats != nullptr) == (d0.gn_stats != nullptr) && d.block_n == d0.block_n && d.debug == d0.debug,
+               "hn_conv2d_bf16_levels: level %d differs from level 0 in more than its geometry and buffers", i);
+    HN_REQUIRE(d.stride == 1 && d.in_phases == 1 && d.kh == 3 && !d.res && !d.out_phase && !d.splitk_ws && !d.stem_pitch_w,
+               "hn_conv2d_bf16_levels: level %d: only plain 3x3 stride-1 convolutions without residual / phase copy / split-K", i);
+    HN_REQUIRE(d.out_kind == 0 || d.out == d0.out, "hn_conv2d_bf16_levels: fp32-row outputs of all levels share one buffer");
+    const long long rows = (long long)d.n * (d.h + 2 * d.halo_in) * (d.w + 2 * d.halo_in);
+    total_tiles += (int)((rows + BLOCK_M - 1) / BLOCK_M);
+  }
+  BuiltConv b0;
+  int rc = build_conv(&descs[0], 0, total_tiles, &b0);
+  if (rc) return rc;
+  CUtensorMap ta[3] = {b0.ta, b0.ta, b0.ta};
+  ConvParams& p = b0.p;
+  p.n_seg = n_levels;
+  int tile_begin = 0, gn_off = 0;
+  for (int i = 0; i < n_levels; ++i) {
+    BuiltConv bi;
+    if (i > 0) {
+      rc = build_conv(&descs[i], b0.bn, total_tiles, &bi);
       if (rc) return rc;
-      HN_REQUIRE(b.p.m_tiles <= MULTI_MAX_MT, "hn_conv_multi_build: conv %d has %d M tiles (max %d)", j, b.p.m_tiles, MULTI_MAX_MT);
-      ph[j].ta = b.ta;
-      ph[j].tb = b.tb;
-      ph[j].p = b.p;
-      ph[j].p.deps = reinterpret_cast<const ConvDeps*>(dev + multi_deps_off(n_convs)) + j;
-      tiles += b.p.m_tiles * b.p.n_tiles * b.p.splits;
+      HN_REQUIRE(bi.bn == b0.bn && bi.rb == b0.rb && bi.p.rb3 == p.rb3 && bi.p.n_groups == p.n_groups &&
+                     bi.p.na_stages == p.na_stages && bi.p.a_box_bytes == p.a_box_bytes && bi.p.epi_alt == p.epi_alt &&
+                     bi.p.vec32 == p.vec32,
+                 "hn_conv2d_bf16_levels: level %d needs a different kernel configuration than level 0", i);
+      ta[i] = bi.ta;
     }
-    if (tiles > max_group_tiles) max_group_tiles = tiles;
+    const ConvParams& q = i == 0 ? p : bi.p;
+    SegGeo& sg = p.seg[i];
+    sg.tile_begin = tile_begin;
+    sg.n_img = q.n_img; sg.hp = q.hp; sg.wp = q.wp; sg.rows = q.rows;
+    sg.div_img_mul = q.div_img_mul; sg.div_wp_mul = q.div_wp_mul; sg.div_img_sh = q.div_img_sh; sg.div_wp_sh = q.div_wp_sh;
+    for (int g = 0; g < 3; ++g) sg.shift[g] = g < q.n_groups ? q.grp_shift[g] : 0;
+    sg.out = q.out; sg.out_hp = q.out_hp; sg.out_wp = q.out_wp; sg.out_row_offset = q.out_row_offset;
+    sg.gn_stats = q.gn_stats;
+    sg.gn_off = gn_off;
+    tile_begin += q.m_tiles;
+    gn_off += q.gn_stats ? q.n_img * q.gn_groups * 2 : 0;
   }
-  // dependencies from the buffer pointers: the latest earlier convolution that writes this one's input / residual
-  for (int j = 0; j < n_convs; ++j) {
-    const hn_conv_desc& dj = descs[j];
-    const ConvParams& pj = ph[j].p;
-    ConvDeps& dd = deps[j];
-    dd.done = dev_cnt(j);
-    dd.n_deps = 0;
-    const int reach = dj.kh == 3 ? dj.dilation * pj.wp + dj.dilation : 0;     // rows a tile reads beyond its own
-    struct In { const void* ptr; BufGeo geo; int reach; };
-    In ins[2] = {{dj.in, {dj.n, pj.hp, pj.wp, pj.halo, dj.in_phases}, reach},
-                 {dj.res, {dj.n, pj.res_hp, pj.res_wp, pj.res_halo, 1}, 0}};
-    for (int k = 0; k < 2; ++k) {
-      if (!ins[k].ptr) continue;
-      int prod = -1, via_phase = 0;
-      for (int i = j - 1; i >= 0 && prod < 0; --i) {
-        if (descs[i].out == ins[k].ptr && descs[i].out_kind == 0) prod = i;
-        else if (descs[i].out_phase && descs[i].out_phase == ins[k].ptr) { prod = i; via_phase = 1; }
-      }
-      if (prod < 0) continue;                          // written before this launch
-      HN_REQUIRE((ins[k].geo.phases == 4) == (via_phase == 1), "hn_conv_multi_build: conv %d reads conv %d's %s buffer as %s",
-                 j, prod, via_phase ? "phase-split" : "plain", ins[k].geo.phases == 4 ? "phase-split" : "plain");
-      HN_REQUIRE(dd.n_deps < MAX_DEPS, "hn_conv_multi_build: too many dependencies");
-      const int d = dd.n_deps++;
-      dd.dep_done[d] = dev_cnt(prod);
-      dd.dep_need[d] = ph[prod].p.n_tiles;
-      dd.dep_first[d] = dev_tab(j, d, 0);
-      dd.dep_last[d] = dev_tab(j, d, 1);
-      short* tf = host_tab(j, d, 0);
-      short* tl = host_tab(j, d, 1);
-      for (int mt = 0; mt < pj.m_tiles; ++mt) {
-        // consumer rows of this tile; the residual is indexed by OUTPUT pixel = compute row of the consumer, which maps
-        // to the residual buffer's own geometry through the pixel (for k = 1 use the compute geometry to find pixels)
-        long long lo = (long long)mt * BLOCK_M - ins[k].reach, hi = (long long)mt * BLOCK_M + BLOCK_M - 1 + ins[k].reach;
-        BufGeo geo = ins[k].geo;
-        if (k == 1) geo = {dj.n, pj.hp, pj.wp, pj.halo, 1};   // rows of the consumer's compute grid -> pixels
-        int a = 1, b2 = 0;
-        producer_tile_range(geo, lo, hi, ph[prod].p, &a, &b2);
-        tf[mt] = (short)a;
-        tl[mt] = (short)b2;
-      }
-    }
-  }
-  const int grid = max_group_tiles < hn_num_sms() ? max_group_tiles : hn_num_sms();
-  HN_CHECK_CUDA(cudaMemcpy(plan_dev, host.data(), host.size(), cudaMemcpyHostToDevice));
-  return grid;     // > 0: number of CTAs hn_conv_multi_run will launch
-}
-
-extern "C" int hn_conv_multi_run(void* plan_dev, int n_convs, int n_groups, int grid, void* stream) {
-  HN_REQUIRE(plan_dev && n_convs > 0 && n_groups > 0 && grid > 0 && grid <= hn_num_sms(), "hn_conv_multi_run: bad arguments");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static bool attr_set = false;
-  if (!attr_set) {
-    HN_CHECK_CUDA(cudaFuncSetAttribute(conv_multi_kernel<MULTI_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       SMEM_BYTES_ALL));
-    attr_set = true;
-  }
-  uint8_t* base = reinterpret_cast<uint8_t*>(plan_dev);
-  HN_CHECK_CUDA(cudaMemsetAsync(base, 0, (size_t)n_convs * MULTI_MAX_MT * 4, st));   // the tile completion counters
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = SMEM_BYTES_ALL;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;              // all CTAs resident: a waiting tile's producers can always run
-  attr[0].val.cooperative = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  const PhaseDesc* phases = reinterpret_cast<const PhaseDesc*>(base + multi_phases_off(n_convs));
-  HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_multi_kernel<MULTI_BN>, phases, n_convs, g_multi_trace));
-  hn_count_launch();
-  return HN_OK;
+  HN_REQUIRE(gn_off <= GN_SMEM_SUMS, "hn_conv2d_bf16_levels: GroupNorm accumulators of all levels (%d sums) exceed %d", gn_off,
+             GN_SMEM_SUMS);
+  p.m_tiles = tile_begin;
+  return dispatch<true>(b0, ta, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -233,19 +233,35 @@ maxpool3x3s2_kernel(const uint4* __restrict__ in, int n, int h, int w, int c8, i
 }
 
 // ---------------------------------------------------------------------------------- GroupNorm
-// grid (pixel blocks, image).  Each block first turns the fp64 (sum, sumsq) accumulators of its image into fp32
-// per-channel a = rstd*gamma, b = beta - mean*a in shared memory, then streams pixels: y = relu(x*a + b).
+// One block = a run of pixels of one image of one pyramid level (blocks are numbered level by level, image by image).
+// Each block first turns the fp64 (sum, sumsq) accumulators of its image into fp32 per-channel a = rstd*gamma,
+// b = beta - mean*a in shared memory, then streams pixels: y = relu(x*a + b).
 constexpr int GN_MAX_C = 512;
+constexpr int GN_MAX_LEVELS = 3;
+struct GnLevels {
+  uint4* x[GN_MAX_LEVELS];
+  const long long* stats[GN_MAX_LEVELS];        // 40.24 fixed-point (sum, sumsq), see hn_conv_desc.gn_stats
+  int h[GN_MAX_LEVELS], w[GN_MAX_LEVELS];
+  int blocks_per_image[GN_MAX_LEVELS];
+  int block_begin[GN_MAX_LEVELS + 1];
+  int n_levels;
+};
 __global__ void __launch_bounds__(256)
-groupnorm_relu_kernel(uint4* __restrict__ x, int h, int w, int c, int halo, const double* __restrict__ stats,
-                      int groups, int group_size, const float* __restrict__ gamma, const float* __restrict__ beta,
-                      float eps, int pixels_per_block) {
+groupnorm_relu_kernel(const __grid_constant__ GnLevels lv, int c, int halo, int groups, int group_size,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int pixels_per_block) {
   __shared__ float sa[GN_MAX_C], sb[GN_MAX_C];
-  const int img = blockIdx.y;
+  const int b = blockIdx.x;
+  const int l = (lv.n_levels > 2 && b >= lv.block_begin[2]) ? 2 : ((lv.n_levels > 1 && b >= lv.block_begin[1]) ? 1 : 0);
+  const int rem_b = b - lv.block_begin[l];
+  const int img = rem_b / lv.blocks_per_image[l], pb = rem_b - img * lv.blocks_per_image[l];
+  const int h = lv.h[l], w = lv.w[l];
+  uint4* __restrict__ x = lv.x[l];
+  const long long* __restrict__ stats = lv.stats[l];
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     const int g = ch / group_size;
     const double cnt = (double)h * (double)w * (double)group_size;
-    const double s = stats[((size_t)img * groups + g) * 2], q = stats[((size_t)img * groups + g) * 2 + 1];
+    const double s = (double)stats[((size_t)img * groups + g) * 2] * (1.0 / 16777216.0);
+    const double q = (double)stats[((size_t)img * groups + g) * 2 + 1] * (1.0 / 16777216.0);
     const double mean = s / cnt;
     double var = q / cnt - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -258,7 +274,7 @@ groupnorm_relu_kernel(uint4* __restrict__ x, int h, int w, int c, int halo, cons
   const int c8 = c >> 3;
   const int hp = h + 2 * halo, wp = w + 2 * halo;
   const int total = h * w;
-  const int p0 = blockIdx.x * pixels_per_block;
+  const int p0 = pb * pixels_per_block;
   const int p1 = min(total, p0 + pixels_per_block);
   const int items = (p1 - p0) * c8;
   for (int i = threadIdx.x; i < items; i += blockDim.x) {
@@ -398,19 +414,44 @@ extern "C" int hn_maxpool3x3s2(const void* in, int n, int h, int w, int c, void*
   return HN_OK;
 }
 
-extern "C" int hn_groupnorm_relu(void* x, int n, int h, int w, int c, int halo, const double* stats, int groups,
-                                 const float* gamma, const float* beta, float eps, void* stream) {
-  HN_REQUIRE(x && stats && gamma && beta, "hn_groupnorm_relu: null pointer");
-  HN_REQUIRE(n > 0 && h > 0 && w > 0 && groups > 0 && c % groups == 0 && c % 8 == 0 && c <= GN_MAX_C && n <= 65535,
-             "hn_groupnorm_relu: unsupported shape (c=%d groups=%d)", c, groups);
+extern "C" int hn_groupnorm_relu_levels(void* const* x_host, const int* n_host, const int* h_host, const int* w_host, int n_levels,
+                                        int c, int halo, const int64_t* const* stats_host, int groups, const float* gamma,
+                                        const float* beta, float eps, void* stream) {
+  HN_REQUIRE(x_host && n_host && h_host && w_host && stats_host && gamma && beta, "hn_groupnorm_relu: null pointer");
+  HN_REQUIRE(n_levels >= 1 && n_levels <= GN_MAX_LEVELS, "hn_groupnorm_relu: 1..%d levels (got %d)", GN_MAX_LEVELS, n_levels);
+  HN_REQUIRE(groups > 0 && c % groups == 0 && c % 8 == 0 && c <= GN_MAX_C, "hn_groupnorm_relu: unsupported shape (c=%d groups=%d)",
+             c, groups);
+  long long pixels = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    HN_REQUIRE(x_host[l] && stats_host[l] && n_host[l] > 0 && h_host[l] > 0 && w_host[l] > 0, "hn_groupnorm_relu: level %d", l);
+    pixels += (long long)n_host[l] * h_host[l] * w_host[l];
+  }
   // ~8 waves of 256-thread blocks over the batch; each block amortises its per-image coefficient set-up
-  const int total = h * w;
-  int ppb = hn_div_up(total * n, hn_num_sms() * 8 * 4);
+  int ppb = (int)((pixels + hn_num_sms() * 8 * 4 - 1) / (hn_num_sms() * 8 * 4));
   if (ppb < 32) ppb = 32;
-  dim3 grid(hn_div_up(total, ppb), n);
-  groupnorm_relu_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<uint4*>(x), h, w, c, halo, stats, groups, c / groups, gamma, beta, eps, ppb);
+  GnLevels lv;
+  memset(&lv, 0, sizeof(lv));
+  lv.n_levels = n_levels;
+  int blocks = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    lv.x[l] = reinterpret_cast<uint4*>(x_host[l]);
+    lv.stats[l] = reinterpret_cast<const long long*>(stats_host[l]);
+    lv.h[l] = h_host[l];
+    lv.w[l] = w_host[l];
+    lv.blocks_per_image[l] = hn_div_up(h_host[l] * w_host[l], ppb);
+    lv.block_begin[l] = blocks;
+    blocks += lv.blocks_per_image[l] * n_host[l];
+  }
+  lv.block_begin[n_levels] = blocks;
+  groupnorm_relu_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(lv, c, halo, groups, c / groups, gamma, beta,
+                                                                                  eps, ppb);
   hn_count_launch();
   HN_LAUNCH_CHECK();
   return HN_OK;
+}
+
+extern "C" int hn_groupnorm_relu(void* x, int n, int h, int w, int c, int halo, const int64_t* stats, int groups,
+                                 const float* gamma, const float* beta, float eps, void* stream) {
+  HN_REQUIRE(x && stats, "hn_groupnorm_relu: null pointer");
+  return hn_groupnorm_relu_levels(&x, &n, &h, &w, 1, c, halo, &stats, groups, gamma, beta, eps, stream);
 }

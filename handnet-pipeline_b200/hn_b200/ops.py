@@ -14,16 +14,9 @@ from . import _lib
 from ._lib import ConvDesc, check, ptr, stream_ptr
 
 BF16 = torch.bfloat16
+GN_FIX_SCALE = float(1 << 24)      # hn_conv_desc.gn_stats holds (sum, sum of squares) as value * 2^24 int64
 _ENV_DEBUG = int(__import__('os').environ.get('HN_CONV_DEBUG', '0'))   # bring-up experiments only
 PROFILE = None      # set to a list by runtime.conv_profile: (start event, end event, algorithmic FLOPs) per conv launch
-RECORD = None       # set to a list to RECORD conv2d calls (descriptor + keep-alive refs) instead of launching them;
-                    # None entries are group boundaries (see MultiConv)
-
-
-def record_barrier():
-    """Group boundary between dependent convolutions while recording a MultiConv plan (no-op otherwise)."""
-    if RECORD is not None and RECORD and RECORD[-1] is not None:
-        RECORD.append(None)
 
 
 def _require_cuda(t: torch.Tensor, name: str):
@@ -293,15 +286,15 @@ def im2col_7x7s2(x: torch.Tensor, k_pad: int, out: Optional[torch.Tensor] = None
     return out, oh, ow
 
 
-def conv2d(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 1, dilation: int = 1,
-           scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None, relu=False,
-           res: Optional[Act] = None, res_mode: int = 0, out: Optional[Act] = None,
-           out_f32: Optional[torch.Tensor] = None, out_rows_per_image: int = 0, out_row_offset: int = 0,
-           out_transpose_hw: bool = False, out_phase: Optional[PhaseAct] = None,
-           gn_stats: Optional[torch.Tensor] = None, gn_groups: int = 0, block_n: int = 0, cluster: int = 0,
-           algo_k: int = 0, debug: int = 0, splitk=None, splits: int = 0, trace: Optional[torch.Tensor] = None):
-    """hn_conv2d_bf16.  x: Act (stride 1), PhaseAct (stride 2) or StemFrame (direct 7x7/2 stem; ksize = 1, the weight
-    from pack_stem_weight).  relu: bool or (lo, hi) channel range."""
+def _conv_desc(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 1, dilation: int = 1,
+               scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None, relu=False,
+               res: Optional[Act] = None, res_mode: int = 0, out: Optional[Act] = None,
+               out_f32: Optional[torch.Tensor] = None, out_rows_per_image: int = 0, out_row_offset: int = 0,
+               out_transpose_hw: bool = False, out_phase: Optional[PhaseAct] = None,
+               gn_stats: Optional[torch.Tensor] = None, gn_groups: int = 0, block_n: int = 0, cluster: int = 0,
+               debug: int = 0, splitk=None, splits: int = 0, trace: Optional[torch.Tensor] = None) -> ConvDesc:
+    """Fill a struct hn_conv_desc.  x: Act (stride 1), PhaseAct (stride 2) or StemFrame (direct 7x7/2 stem; ksize = 1, the
+    weight from pack_stem_weight).  relu: bool or (lo, hi) channel range."""
     d = ConvDesc()
     if isinstance(x, StemFrame):
         assert stride == 1 and ksize == 1
@@ -338,7 +331,7 @@ def conv2d(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 1, d
         assert (out_phase.n, out_phase.h, out_phase.w, out_phase.c) == (d.n, d.h, d.w, cout)
         d.out_phase, d.out_phase_halo = out_phase.t.data_ptr(), out_phase.halo
     if gn_stats is not None:
-        assert gn_stats.dtype == torch.float64 and gn_stats.numel() == d.n * gn_groups * 2
+        assert gn_stats.dtype == torch.int64 and gn_stats.numel() == d.n * gn_groups * 2
         d.gn_stats, d.gn_groups = gn_stats.data_ptr(), gn_groups
     d.block_n = block_n
     d.cluster = cluster
@@ -351,20 +344,55 @@ def conv2d(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 1, d
         d.splitk_ws, d.splitk_ws_bytes = ws_t.data_ptr(), ws_t.numel() * ws_t.element_size()
         d.splitk_counters, d.splitk_counters_len = cnt_t.data_ptr(), cnt_t.numel()
         d.splits = splits
-    if RECORD is not None:
-        RECORD.append((d, (x, weight, scale, shift, res, out, out_f32, out_phase, splitk)))
-        return out if out_f32 is None else out_f32
+    return d
+
+
+def _conv_flops(d: ConvDesc, cout: int, k_elems: int) -> float:
+    return 2.0 * d.n * d.h * d.w * cout * k_elems
+
+
+def conv2d(x, weight: torch.Tensor, *, cout: int, ksize: int, algo_k: int = 0, **kw):
+    """hn_conv2d_bf16 (see _conv_desc for the arguments).  Returns the output Act (or the fp32 row buffer)."""
+    d = _conv_desc(x, weight, cout=cout, ksize=ksize, **kw)
+    out, out_f32 = kw.get("out"), kw.get("out_f32")
     if PROFILE is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         check(_lib.load().hn_conv2d_bf16(C.byref(d), stream_ptr()), "hn_conv2d_bf16")
         ev1.record()
-        PROFILE.append((ev0, ev1, 2.0 * d.n * d.h * d.w * cout * (algo_k or weight.shape[1]),
-                        dict(n=d.n, h=d.h, w=d.w, cin=d.cin, cout=cout, k=ksize, stride=stride, dil=dilation,
-                             halo=d.halo_in, f32=out_f32 is not None, gn=gn_stats is not None)))
+        PROFILE.append((ev0, ev1, _conv_flops(d, cout, algo_k or weight.shape[1]),
+                        dict(n=d.n, h=d.h, w=d.w, cin=d.cin, cout=cout, k=ksize, stride=d.stride, dil=d.dilation,
+                             halo=d.halo_in, f32=out_f32 is not None, gn=kw.get("gn_stats") is not None, levels=1)))
         return out if out_f32 is None else out_f32
     check(_lib.load().hn_conv2d_bf16(C.byref(d), stream_ptr()), "hn_conv2d_bf16")
     return out if out_f32 is None else out_f32
+
+
+def conv2d_levels(xs: Sequence[Act], weight: torch.Tensor, *, cout: int, ksize: int, outs: Optional[Sequence[Act]] = None,
+                  out_f32: Optional[torch.Tensor] = None, out_rows_per_image: int = 0,
+                  out_row_offsets: Optional[Sequence[int]] = None, gn_stats: Optional[Sequence[torch.Tensor]] = None,
+                  gn_groups: int = 0, **kw):
+    """hn_conv2d_bf16_levels: the same 3x3 convolution over several pyramid levels (shared weight / scale / shift) in ONE
+    launch.  xs / outs / gn_stats / out_row_offsets are per level."""
+    n = len(xs)
+    arr = (ConvDesc * n)()
+    for i, x in enumerate(xs):
+        d = _conv_desc(x, weight, cout=cout, ksize=ksize, out=None if outs is None else outs[i], out_f32=out_f32,
+                       out_rows_per_image=out_rows_per_image, out_row_offset=0 if out_row_offsets is None else out_row_offsets[i],
+                       gn_stats=None if gn_stats is None else gn_stats[i], gn_groups=gn_groups, **kw)
+        C.memmove(C.addressof(arr[i]), C.addressof(d), C.sizeof(ConvDesc))
+    prof = PROFILE
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    check(_lib.load().hn_conv2d_bf16_levels(arr, n, stream_ptr()), "hn_conv2d_bf16_levels")
+    if prof is not None:
+        ev1.record()
+        d0 = arr[0]
+        prof.append((ev0, ev1, sum(_conv_flops(arr[i], cout, weight.shape[1]) for i in range(n)),
+                     dict(n=d0.n, h=d0.h, w=d0.w, cin=d0.cin, cout=cout, k=ksize, stride=1, dil=d0.dilation, halo=d0.halo_in,
+                          f32=out_f32 is not None, gn=gn_stats is not None, levels=n)))
+    return outs if out_f32 is None else out_f32
 
 
 def maxpool3x3s2(x: torch.Tensor, out: Act) -> Act:
@@ -381,6 +409,21 @@ def groupnorm_relu(x: Act, stats: torch.Tensor, groups: int, gamma: torch.Tensor
     check(_lib.load().hn_groupnorm_relu(x.t.data_ptr(), x.n, x.h, x.w, x.c, x.halo, stats.data_ptr(), groups,
                                         gamma.data_ptr(), beta.data_ptr(), eps, stream_ptr()), "hn_groupnorm_relu")
     return x
+
+
+def groupnorm_relu_levels(xs: Sequence[Act], stats: Sequence[torch.Tensor], groups: int, gamma: torch.Tensor,
+                          beta: torch.Tensor, eps: float = 1e-5):
+    """GroupNorm + ReLU in place over several pyramid levels in one launch."""
+    n = len(xs)
+    xp = (C.c_void_p * n)(*[x.t.data_ptr() for x in xs])
+    sp = (C.c_void_p * n)(*[t.data_ptr() for t in stats])
+    ia = C.c_int * n
+    x0 = xs[0]
+    assert all((x.c, x.halo) == (x0.c, x0.halo) for x in xs)
+    check(_lib.load().hn_groupnorm_relu_levels(xp, ia(*[x.n for x in xs]), ia(*[x.h for x in xs]), ia(*[x.w for x in xs]), n,
+                                               x0.c, x0.halo, sp, groups, gamma.data_ptr(), beta.data_ptr(), eps, stream_ptr()),
+          "hn_groupnorm_relu_levels")
+    return xs
 
 
 class Levels:
@@ -477,15 +520,22 @@ def fcos_gather(keep, keep_count, cand, hand_lr: torch.Tensor, levels: Levels, r
 
 
 def select_crop_resize(boxes: torch.Tensor, labels: torch.Tensor, keep_count: torch.Tensor, hand_label: int,
-                       depth: torch.Tensor, out_size: int = 176):
-    """S1 + S2.  depth: fp32 [B, C, H, W].  Returns (crops [B,4] int64, has_hand [B] int32, depth_batch)."""
+                       depth: torch.Tensor, out_size: int = 176, out=None):
+    """S1 + S2.  depth: fp32 [B, C, H, W].  Returns (crops [B,4] int64, has_hand [B] int32, depth_batch); `out` supplies
+    those three tensors (the pipeline's hand-off buffers) instead of allocating them."""
     b, cap = labels.shape
     _, dc, ih, iw = depth.shape
     assert depth.dtype == torch.float32 and depth.is_contiguous() and depth.shape[0] == b
     dev = depth.device
-    crops = torch.empty((b, 4), dtype=torch.int64, device=dev)
-    has = torch.empty(b, dtype=torch.int32, device=dev)
-    db = torch.empty((b, dc, out_size, out_size), dtype=torch.float32, device=dev)
+    if out is None:
+        crops = torch.empty((b, 4), dtype=torch.int64, device=dev)
+        has = torch.empty(b, dtype=torch.int32, device=dev)
+        db = torch.empty((b, dc, out_size, out_size), dtype=torch.float32, device=dev)
+    else:
+        crops, has, db = out
+        assert crops.dtype == torch.int64 and tuple(crops.shape) == (b, 4) and crops.is_contiguous()
+        assert has.dtype == torch.int32 and has.numel() == b and has.is_contiguous()
+        assert db.dtype == torch.float32 and tuple(db.shape) == (b, dc, out_size, out_size) and db.is_contiguous()
     check(_lib.load().hn_select_crop_resize(boxes.data_ptr(), labels.data_ptr(), keep_count.data_ptr(), b, cap,
                                             hand_label, depth.data_ptr(), dc, ih, iw, out_size, crops.data_ptr(),
                                             has.data_ptr(), db.data_ptr(), stream_ptr()), "hn_select_crop_resize")
@@ -506,38 +556,3 @@ def a2j_aggregate(cls: torch.Tensor, reg: torch.Tensor, dep: torch.Tensor, ancho
     check(_lib.load().hn_a2j_aggregate(cls.data_ptr(), reg.data_ptr(), dep.data_ptr(), anchors.data_ptr(), n, a, j,
                                        out.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr()), "hn_a2j_aggregate")
     return out
-
-
-class MultiConv:
-    """A recorded sequence of convolutions that runs as ONE cooperative launch (hn_conv_multi_*).  `items` is what
-    ops.RECORD collected: (ConvDesc, keep-alive) tuples with None between dependent groups."""
-
-    def __init__(self, items, device):
-        while items and items[-1] is None:
-            items = items[:-1]
-        convs = [it for it in items if it is not None]
-        begins, k = [0], 0
-        for it in items:
-            if it is None:
-                begins.append(k)
-            else:
-                k += 1
-        begins.append(k)
-        self.keep = [it[1] for it in convs]
-        self.n, self.groups = len(convs), len(begins) - 1
-        arr = (ConvDesc * self.n)()
-        for i, (d, _) in enumerate(convs):
-            C.memmove(C.addressof(arr[i]), C.addressof(d), C.sizeof(ConvDesc))
-        gb = (C.c_int * (self.groups + 1))(*begins)
-        lib = _lib.load()
-        nbytes = int(lib.hn_conv_multi_plan_bytes(self.n, self.groups))
-        self.plan = torch.zeros(nbytes, dtype=torch.uint8, device=device)
-        torch.cuda.synchronize(device)
-        rc = lib.hn_conv_multi_build(arr, self.n, gb, self.groups, self.plan.data_ptr(), nbytes)
-        if rc <= 0:
-            check(rc if rc < 0 else -1, "hn_conv_multi_build")
-        self.grid = rc
-
-    def run(self):
-        check(_lib.load().hn_conv_multi_run(self.plan.data_ptr(), self.n, self.groups, self.grid, stream_ptr()),
-              "hn_conv_multi_run")

@@ -89,9 +89,9 @@ def mark(name: str):
 
 _side_streams: Dict[str, List["torch.cuda.Stream"]] = {}
 SPLIT_K = True              # split-K (fp32 scratch + last-arriver epilogue) for the short, deep A2J layers
-A2J_MULTI = False           # True: the A2J convolutions as ONE cooperative launch with tile-level dataflow synchronisation
-                            # (hn_conv_multi_*).  Measured slower than per-layer launches with programmatic dependent launch
-                            # and the three towers on forked graph branches: 697 vs 594 us for 8 crops
+FUSE_LEVELS = True          # FCOS towers / output convolutions / GroupNorm: ONE launch over P3+P4+P5 per layer
+                            # (hn_conv2d_bf16_levels) instead of one per level; False = round-1 schedule (six chains), kept for
+                            # A/B timing and the equality test (outputs are bit-identical either way)
 PARALLEL_CHAINS = True      # independent layer chains (head towers, A2J towers) on forked streams / graph branches
 
 
@@ -236,7 +236,7 @@ class FCOSPlan:
         self.locs = L
         self.cls_buf = torch.zeros((B, L, wts.cls_ld), dtype=torch.float32, device=device)
         self.reg_buf = torch.zeros((B, L, wts.reg_ld), dtype=torch.float32, device=device)
-        self.gn_stats = torch.zeros((2, 4, 3, B, 32, 2), dtype=torch.float64, device=device)
+        self.gn_stats = torch.zeros((2, 4, 3, B, 32, 2), dtype=torch.int64, device=device)    # fixed-point sums (ops.GN_FIX_SCALE)
         self.sel_ws = torch.empty(int(ops._lib.load().hn_fcos_select_workspace_bytes(B, L)), dtype=torch.uint8, device=device)
         self.nms_ws = ops.nms_workspace(B, L, device)
 
@@ -325,9 +325,31 @@ class FCOSExecutor:
                                   out_row_offset=pl.levels.starts[lvl])
             return run
 
-        # six independent chains: (cls, reg) x (P3, P4, P5); the big P3 chains first
-        run_chains([tower_chain(ti, t, lvl) for lvl in range(3) for ti, t in enumerate(("cls", "reg"))],
-                   pl.canvas.device)
+        def tower_chain_levels(ti, t):
+            # the reference applies the SAME tower modules to every level (fcos_utils/fcos.py:278-289, 378-380): one launch per
+            # layer over the concatenated tile list of P3+P4+P5 (1169 tiles for 8 VGA frames = 8 full waves of 147 CTAs)
+            # instead of three launches of which the P4 / P5 ones fill the 148 SMs to 77 % / 41 %
+            def run():
+                xs = list(pl.p)
+                nl = len(xs)
+                for i, (conv, gamma, beta) in enumerate(w.towers[t]):
+                    outs = [pl.tower[t][lvl][i & 1] for lvl in range(nl)]
+                    sts = [pl.gn_stats[ti, i, lvl] for lvl in range(nl)]
+                    ops.conv2d_levels(xs, conv.w, cout=conv.cout, ksize=conv.k, shift=conv.shift, outs=outs, gn_stats=sts,
+                                      gn_groups=32)
+                    ops.groupnorm_relu_levels(outs, sts, 32, gamma, beta, GN_EPS)
+                    xs = outs
+                oc, relu, buf = (w.cls_out, w.cls_relu, pl.cls_buf) if t == "cls" else (w.reg_out, w.reg_relu, pl.reg_buf)
+                ops.conv2d_levels(xs, oc.w, cout=oc.cout, ksize=oc.k, shift=oc.shift, relu=relu, out_f32=buf,
+                                  out_rows_per_image=pl.locs, out_row_offsets=pl.levels.starts[:nl])
+            return run
+
+        if FUSE_LEVELS and len(pl.p) <= 3:
+            run_chains([tower_chain_levels(ti, t) for ti, t in enumerate(("cls", "reg"))], pl.canvas.device)
+        else:
+            # six independent chains: (cls, reg) x (P3, P4, P5); the big P3 chains first
+            run_chains([tower_chain(ti, t, lvl) for lvl in range(3) for ti, t in enumerate(("cls", "reg"))],
+                       pl.canvas.device)
         mark("towers")
         return pl.cls_buf, pl.reg_buf
 
@@ -462,7 +484,6 @@ class A2JPlan:
         self.dep = torch.zeros((n, na, num_joints), dtype=torch.float32, device=device)
         self.agg_ws = torch.empty(int(ops._lib.load().hn_a2j_workspace_bytes(n, num_joints)), dtype=torch.uint8, device=device)
         self.cache: Dict[str, object] = {}
-        self.multi = None
 
     def act(self, key, hh, ww, c, halo=1):
         if key not in self.cache:
@@ -532,25 +553,11 @@ class A2JExecutor:
             ops.conv2d(a, w.stem_w, cout=64, ksize=1, scale=w.stem_scale, shift=w.stem_shift, relu=True, out=pl.stem,
                        algo_k=147)       # 3 identical input channels in the reference: 7*7*3 MACs per output
         cur = ops.maxpool3x3s2(pl.stem.t, pl.pool)
-        if A2J_MULTI and ops.PROFILE is None:
-            # layer1..4 and the three towers: 67 convolutions in ONE cooperative launch with grid barriers between
-            # dependent groups (recorded once per buffer set)
-            if pl.multi is None:
-                ops.RECORD = []
-                try:
-                    self._schedule(pl, w, cur, n)
-                    items = ops.RECORD
-                finally:
-                    ops.RECORD = None
-                pl.multi = ops.MultiConv(items, x.device)
-            pl.multi.run()
-        else:
-            self._schedule(pl, w, cur, n)
+        self._schedule(pl, w, cur, n)
         return pl.cls, pl.reg, pl.dep, pl
 
     def _schedule(self, pl: A2JPlan, w: A2JWeights, cur, n):
-        """Emit the convolutions of layer1..layer4 and the towers in dependency order; ops.record_barrier() marks the
-        boundaries between dependent groups (used when recording a MultiConv plan, a no-op for eager launches)."""
+        """Emit the convolutions of layer1..layer4 and the towers in dependency order."""
         c4 = None
         for li in range(4):
             planes = 64 << li
@@ -579,23 +586,20 @@ class A2JExecutor:
                     else:
                         idn = cur
                     src2 = t1
-                ops.record_barrier()
                 t2 = pl.act(tag + "t2", hout, wout, planes)
                 blk["conv2"].run(src2, relu=True, out=t2, splitk=pl.splitk(tag + "c2", src2, blk["conv2"]))
-                ops.record_barrier()
                 last = bi == len(w.blocks[li]) - 1
                 out = pl.act(tag + "out", hout, wout, planes * 4)
                 out_phase = pl.phase(f"l{li}out_phase", hout, wout, planes * 4) if (last and li in (0, 1)) else None
                 blk["conv3"].run(t2, relu=True, res=idn, res_mode=1, out=out, out_phase=out_phase,
                                  splitk=pl.splitk(tag + "c3", t2, blk["conv3"]))
-                ops.record_barrier()
                 cur = out
             if li == 2:
                 c4 = cur
         c5 = cur
         hf, wf = pl.feat_hw
         towers = (("regressionModel", c5, pl.reg), ("DepthRegressionModel", c5, pl.dep), ("classificationModel", c4, pl.cls))
-        if ops.RECORD is None and ops.PROFILE is None and PARALLEL_CHAINS:
+        if ops.PROFILE is None and PARALLEL_CHAINS:
             # eager / per-layer launches: the three towers are independent chains -> forked streams (graph branches)
             def chain(name, src, dst):
                 def run():
@@ -616,7 +620,6 @@ class A2JExecutor:
                 w.towers[name][0][i].run(t[name], relu=True, out=o,
                                          splitk=pl.splitk(f"{name}{i}", t[name], w.towers[name][0][i]))
                 t[name] = o
-            ops.record_barrier()
         for name, _, dst in towers:
             # permute(0,3,2,1) + view of the reference == w-major rows (a2j/a2j.py:85-89)
             w.towers[name][1].run(t[name], out_f32=dst.view(n, hf * wf, -1), out_transpose_hw=True,
@@ -656,82 +659,268 @@ def unpack_records(rec: torch.Tensor):
 
 
 class GraphedHandNet:
-    """HandNet.forward_device over fixed (batch, H, W) input buffers, captured once as a CUDA graph and replayed:
-    a step is ~180 kernel launches, so replaying removes the host launch path from the critical path."""
+    """The step over fixed (batch, H, W) input buffers as a TWO-STAGE PIPELINE of CUDA graphs:
+
+      detect stage  (stream `det`):   preprocess -> FCOS -> post-process -> hand select + crop     (~110 launches)
+      pose stage    (stream `pose`):  A2J pose net -> anchor aggregation -> per-frame records       (~75 launches)
+
+    The pose net of 8 crops is a chain of ~52 dependent, latency-bound launches that keeps well under a third of the SMs
+    busy (16 % of a step for 4 % of its FLOPs); it depends on the detector of the SAME step only.  `submit()` therefore
+    enqueues the detect stage of step i on `det` and the pose stage on the higher-priority `pose` stream, so that the
+    pose stage of step i runs under the detect stage of step i+1.  The hand-off (crops, hit flags, 176x176 depth crops;
+    1 MB) is copied into a pose-private buffer at the start of the pose stage, and the detect stage of step i+1 waits for
+    that copy, so the stages share no buffer.  `result(ticket)` waits for one step's records on the host.  Results are
+    bit-identical to running the two stages back to back on one stream (same kernels, same buffers, same order per stage).
+    """
+
+    RING = 4            # steps in flight at most (pinned result buffers)
 
     def __init__(self, net, batch: int, h: int, w: int, depth_c: int = 1, use_graph: bool = True, slot: int = 0):
         self.net = net
-        self.slot = slot            # buffer set: give concurrent steps (one per stream) different slots
+        self.slot = slot            # buffer set: give concurrent executors (one per stream) different slots
         dev = next(net.parameters()).device
+        self.dev = dev
         self.batch = batch
         self.rgb = torch.zeros((batch, 3, h, w), dtype=torch.float32, device=dev)
         self.depth = torch.zeros((batch, depth_c, h, w), dtype=torch.float32, device=dev)
         self.images = list(self.rgb.unbind(0))
         self.use_graph = use_graph
-        self.graph = None
+        self.g_det = self.g_pose = None
         self.token = None
         self.out = None
         self.rec = None
         self.launches_per_step = 0
-        self.rec_host = torch.empty((batch, RECORD_WIDTH), dtype=torch.float32).pin_memory()
+        lo, hi = torch.cuda.Stream.priority_range()            # (lowest, highest) = (0, -N)
+        self.det_stream = torch.cuda.Stream(device=dev, priority=lo)
+        self.pose_stream = torch.cuda.Stream(device=dev, priority=hi)
+        # hand-off blob [crops int64 B*4 | has_hand int32 B (padded to 8 B) | depth crops fp32] twice: written by the detect
+        # stage / read by the pose stage
+        from handnet_pipeline.handnet_pipeline import CROP_SIZE
+        self.crop = CROP_SIZE
+        self._off_has = batch * 4 * 8
+        self._off_depth = self._off_has + ((batch * 4 + 7) // 8) * 8
+        nbytes = self._off_depth + batch * depth_c * CROP_SIZE * CROP_SIZE * 4
+        self.hand_d = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        self.hand_p = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        self.depth_c = depth_c
+        self.ring_host = [torch.empty((batch, RECORD_WIDTH), dtype=torch.float32).pin_memory() for _ in range(self.RING)]
+        self.ring_done = [None] * self.RING
+        self.ring_out = [None] * self.RING
+        self.rec_host = self.ring_host[0]
         self.d2h_bytes = self.rec_host.numel() * 4
+        self.ev_copy = None         # hand-off of the latest submitted step has been copied (detect stage may overwrite it)
+        self.copy_stream = None     # host -> device uploads (created on first use)
+        self._stage = {}            # staging sets for host inputs, by input kind
+        self.n_submitted = 0
+        self.n_collected = 0
 
-    def load_inputs(self, rgb: torch.Tensor, depth: torch.Tensor):
-        self.rgb.copy_(rgb, non_blocking=True)
-        self.depth.copy_(depth, non_blocking=True)
+    # ---------------------------------------------------------------------------------------------- buffers
+    def _views(self, blob):
+        b, c, s = self.batch, self.depth_c, self.crop
+        crops = blob[:self._off_has].view(torch.int64).view(b, 4)
+        has = blob[self._off_has:self._off_has + b * 4].view(torch.int32)
+        depth = blob[self._off_depth:].view(torch.float32).view(b, c, s, s)
+        return crops, has, depth
 
-    def _eager(self):
+    def load_inputs(self, rgb, depth: torch.Tensor):
+        """Copy a batch (rgb: [B,3,H,W] tensor or list of [3,H,W]; depth [B,C,H,W]) into the static input buffers, on the
+        detect stream, ordered after the caller's current stream.  HOST tensors (pinned memory for a truly asynchronous
+        copy) are uploaded on a separate copy stream into one of two staging sets, so that the PCIe transfer of step i+1
+        overlaps the kernels of step i; the detect stream then takes them with a device-to-device copy."""
+        first = rgb[0] if isinstance(rgb, (list, tuple)) else rgb
+        if first.device.type == "cpu":
+            return self._load_staged(rgb, depth, u8=False)
+        cur = torch.cuda.current_stream(self.dev)
+        self.det_stream.wait_stream(cur)
+        with torch.cuda.stream(self.det_stream):
+            if isinstance(rgb, (list, tuple)):
+                torch._foreach_copy_(self.images, list(rgb))
+            else:
+                self.rgb.copy_(rgb, non_blocking=True)
+            self.depth.copy_(depth, non_blocking=True)
+
+    def load_frames_u8(self, bgr_u8: torch.Tensor, depth_u16: torch.Tensor):
+        """Camera frames (uint8 BGR [B,H,W,3], uint16 / int16 millimetres [B,H,W]; host or device) -> the static fp32 input
+        buffers through hn_ingest_frames (ros_demo.py:227-238, 266-267); host frames are staged like load_inputs."""
+        if bgr_u8.device.type == "cpu":
+            return self._load_staged(bgr_u8, depth_u16, u8=True)
+        self.det_stream.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(self.det_stream):
+            ops.ingest_frames(bgr_u8.contiguous(), depth_u16.contiguous(), rgb_out=self.rgb, depth_out=self.depth)
+
+    def _load_staged(self, a, b, u8: bool):
+        key = "u8" if u8 else "f32"
+        if key not in self._stage:
+            if u8:
+                mk = lambda: (torch.empty((self.batch,) + tuple(self.rgb.shape[2:]) + (3,), dtype=torch.uint8, device=self.dev),
+                              torch.empty((self.batch,) + tuple(self.rgb.shape[2:]), dtype=b.dtype, device=self.dev))
+            else:
+                mk = lambda: (torch.empty_like(self.rgb), torch.empty_like(self.depth))
+            self._stage[key] = {"bufs": [mk(), mk()], "free": [None, None], "n": 0}
+        st = self._stage[key]
+        k = st["n"] & 1
+        st["n"] += 1
+        sa, sb = st["bufs"][k]
+        if self.copy_stream is None:
+            self.copy_stream = torch.cuda.Stream(device=self.dev)
+        cs = self.copy_stream
+        if st["free"][k] is not None:
+            cs.wait_event(st["free"][k])                    # the detect stream has consumed this staging set
+        with torch.cuda.stream(cs):
+            if isinstance(a, (list, tuple)):
+                for dst, src in zip(sa.unbind(0), a):
+                    dst.copy_(src, non_blocking=True)
+            else:
+                sa.copy_(a, non_blocking=True)
+            sb.copy_(b.reshape(sb.shape), non_blocking=True)
+            up = torch.cuda.Event()
+            up.record(cs)
+        with torch.cuda.stream(self.det_stream):
+            self.det_stream.wait_event(up)
+            if u8:
+                ops.ingest_frames(sa, sb, rgb_out=self.rgb, depth_out=self.depth)
+            else:
+                self.rgb.copy_(sa, non_blocking=True)
+                self.depth.copy_(sb, non_blocking=True)
+            fr = torch.cuda.Event()
+            fr.record(self.det_stream)
+            st["free"][k] = fr
+
+    # ---------------------------------------------------------------------------------------------- stages
+    def _stage_detect(self):
         global PLAN_SLOT
         saved, PLAN_SLOT = PLAN_SLOT, self.slot
         try:
-            out = self.net.forward_device(self.images, self.depth)
+            det, crops, has, depth_batch = self.net.detect_crop_device(self.images, self.depth, out=self._views(self.hand_d))
         finally:
             PLAN_SLOT = saved
-        self.out = out
-        self.rec = pack_records(out["joints"], out["crops"], out["has_hand"])
-        return out
+        self.det = det
+        return det
+
+    def _stage_pose(self):
+        global PLAN_SLOT
+        saved, PLAN_SLOT = PLAN_SLOT, self.slot
+        crops, has, depth_batch = self._views(self.hand_p)
+        try:
+            joints = self.net.pose_device(depth_batch)
+        finally:
+            PLAN_SLOT = saved
+        self.rec = pack_records(joints, crops, has)
+        self.out = {"joints": joints, "has_hand": has, "crops": crops, "depth_batch": depth_batch, "det": self.det}
+        return self.out
+
+    def _eager(self):
+        """Both stages back to back on the CURRENT stream (tools, conv_profile, capture warm-up)."""
+        self._stage_detect()
+        self.hand_p.copy_(self.hand_d)
+        return self._stage_pose()
 
     def capture(self):
-        cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream()
+        cur = torch.cuda.current_stream(self.dev)
+        side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             for _ in range(2):
                 self._eager()
         cur.wait_stream(side)
-        torch.cuda.synchronize()
+        torch.cuda.synchronize(self.dev)
         l0 = ops.launch_count()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._eager()
+        self.g_det = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_det):
+            self._stage_detect()
+        self.g_pose = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_pose):
+            self._stage_pose()
         self.launches_per_step = ops.launch_count() - l0
         self.token = weights_token(self.net)
+        self.det_stream.wait_stream(cur)
+        self.pose_stream.wait_stream(cur)
 
     def invalidate_if_weights_changed(self):
-        if self.graph is not None and self.token != weights_token(self.net):
-            self.graph = None
+        if self.g_det is not None and self.token != weights_token(self.net):
+            self.drain()
+            self.g_det = self.g_pose = None
+
+    # ---------------------------------------------------------------------------------------------- pipeline
+    def submit(self, want_outputs: bool = False, post=None) -> int:
+        """Enqueue one step over the loaded inputs; returns its ticket.  Never waits for the device.  At most RING steps may
+        be in flight (collect the oldest one with result() first).  `post(rec)` runs on the pose stream right after the
+        step's kernels with the device records [B, 68] (hn_b200.parallel enqueues its all-gather there)."""
+        if self.n_submitted - self.n_collected >= self.RING:
+            raise RuntimeError(f"GraphedHandNet: {self.RING} steps in flight; call result() before submitting more")
+        if self.use_graph and self.g_det is None:
+            self.capture()
+        ticket = self.n_submitted
+        r = ticket % self.RING
+        det, pose = self.det_stream, self.pose_stream
+        with torch.cuda.stream(det):
+            if self.ev_copy is not None:
+                det.wait_event(self.ev_copy)              # the previous step's pose stage has taken its hand-off
+            if self.use_graph:
+                self.g_det.replay()
+            else:
+                l0 = ops.launch_count()
+                self._stage_detect()
+            ev_det = torch.cuda.Event()
+            ev_det.record(det)
+        with torch.cuda.stream(pose):
+            pose.wait_event(ev_det)
+            self.hand_p.copy_(self.hand_d, non_blocking=True)
+            self.ev_copy = torch.cuda.Event()
+            self.ev_copy.record(pose)
+            if self.use_graph:
+                self.g_pose.replay()
+            else:
+                self._stage_pose()
+                self.launches_per_step = ops.launch_count() - l0
+            self.ring_host[r].copy_(self.rec, non_blocking=True)
+            if post is not None:
+                post(self.rec)
+            if want_outputs:                               # private copies: the next step's hand-off overwrites hand_p
+                self.ring_out[r] = (self.out["depth_batch"].clone(), self.out["crops"].clone())
+            done = torch.cuda.Event()
+            done.record(pose)
+            self.ring_done[r] = done
+        self.n_submitted += 1
+        return ticket
+
+    def result(self, ticket: int):
+        """Wait (on the host) for step `ticket`; returns (rec_host [B, 68] pinned fp32, (depth_batch, crops) or None).
+        Tickets are collected in submission order."""
+        if ticket != self.n_collected or ticket >= self.n_submitted:
+            raise RuntimeError(f"GraphedHandNet.result: ticket {ticket} is not the oldest step in flight ({self.n_collected})")
+        r = ticket % self.RING
+        self.ring_done[r].synchronize()
+        self.n_collected += 1
+        self.rec_host = self.ring_host[r]
+        outs, self.ring_out[r] = self.ring_out[r], None
+        return self.ring_host[r], outs
+
+    def done_event(self, ticket: int):
+        return self.ring_done[ticket % self.RING]
+
+    def drain(self):
+        while self.n_collected < self.n_submitted:
+            self.result(self.n_collected)
 
     def run(self):
-        if not self.use_graph:
-            l0 = ops.launch_count()
-            self._eager()
-            self.launches_per_step = ops.launch_count() - l0
-            return self.out
-        if self.graph is None:
-            self.capture()
-        self.graph.replay()
+        """One step, both stages, finished before the call returns control of the buffers: the CURRENT stream waits for the
+        pose stage (no host sync)."""
+        self.drain()
+        t = self.submit()
+        torch.cuda.current_stream(self.dev).wait_event(self.done_event(t))
+        self.n_collected += 1              # nothing to collect on the host: the caller reads device buffers
         return self.out
 
     def records(self) -> torch.Tensor:
         return self.rec
 
     def run_e2e(self, rgb_host: torch.Tensor, depth_host: torch.Tensor):
-        """Host (pinned) frames in, host results out: H2D + step + D2H + one stream sync."""
+        """Host (pinned) frames in, host results out: H2D + step + D2H + one host wait."""
+        self.drain()
         self.load_inputs(rgb_host, depth_host)
-        self.run()
-        self.rec_host.copy_(self.rec, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return unpack_records(self.rec_host)
+        rec, _ = self.result(self.submit())
+        return unpack_records(rec)
 
     def counts(self):
         d = self.out["det"]

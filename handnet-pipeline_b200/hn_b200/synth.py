@@ -145,3 +145,16 @@ def a2j_state_dict(num_joints: int = 21, seed: int = 1, channel_in: int = 1) -> 
     sd["post_process.all_anchors"] = anchors.clone()
     sd["post_process.thres"] = torch.tensor(8.0)
     return sd
+
+
+def stress_head_tensors(seed: int, batch: int, locs: int, num_classes: int = 3, mu: float = -0.35):
+    """Synthetic FCOS head outputs for BASELINE.json config 4: the 0.7 score cut is hard-coded in the
+    reference (fcos_utils/fcos.py:600), so ~10 000 candidates per frame are reached by RAISING the logits: cls ~ N(mu, 1)
+    with mu chosen so that ~56 % of sqrt(sigmoid(cls) * sigmoid(ctr)) exceed 0.7, ctr ~ N(2, 1), reg ~ U(0.5, 4)."""
+    g = torch.Generator().manual_seed(seed)
+    return {
+        "cls_logits": torch.randn(batch, locs, num_classes, generator=g) + mu,
+        "bbox_ctrness": torch.randn(batch, locs, 1, generator=g) + 2.0,
+        "bbox_regression": 0.5 + 3.5 * torch.rand(batch, locs, 4, generator=g),
+        "hand_lr": torch.randn(batch, locs, 2, generator=g),
+    }

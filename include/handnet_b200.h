@@ -97,12 +97,13 @@ typedef struct hn_conv_desc {
   int out_rows_per_image, out_row_offset, out_ld, out_transpose_hw;
   void* out_phase; /* optional second bf16 output, phase-split with halo out_phase_halo; NULL if unused */
   int out_phase_halo;
-  double* gn_stats; /* optional [n][gn_groups][2] (sum, sum of squares) over the bf16-rounded output,
-                       accumulated with atomics -- caller zeroes it */
+  int64_t* gn_stats; /* optional [n][gn_groups][2] (sum, sum of squares) over the bf16-rounded output as 40.24 FIXED-POINT
+                        integers (value * 2^24), accumulated with integer atomics -- caller zeroes it.  Integer addition is
+                        associative: the statistics, and the GroupNorm output, are bit-identical from run to run. */
   int gn_groups;
   int block_n; /* 0 = choose automatically among 16/32/64/128/256 */
-  int cluster; /* 0 = automatic; 1 = no cluster; 2 = CTA pairs along M that multicast the weight tile */
-  int debug;   /* 0 in production; bring-up experiments only */
+  int cluster; /* 0 or 1 (reserved: CTA pairs that multicast the weight tile measured +-1 % in round 1 and were removed) */
+  int debug;   /* 0 in production; timing experiments of -DHN_CONV_DEBUG builds (bits 4, 5, 15, 16 select code paths in every build) */
   /* optional split-K for short, deep layers that cannot fill the GPU with tiles: an fp32 scratch holding one slice of
    * ceil(rows/128)*128*cout_pad*4 bytes per K split (contents irrelevant on entry) and one uint32 counter per output
    * tile, ZERO on entry and left zero on exit; both exclusive to this convolution while it runs.  Every split stores
@@ -114,8 +115,8 @@ typedef struct hn_conv_desc {
   void* splitk_counters;
   int splitk_counters_len;
   int splits;
-  /* bring-up only: NULL in production.  When set, CTA 0 logs (clock64, tag) pairs of its producer, MMA and first
-   * epilogue warp into trace[3][2048][2] (int64) -- see tools/conv_trace.py. */
+  /* bring-up only (-DHN_CONV_DEBUG builds; ignored otherwise): CTA 0 logs (clock64, tag) pairs of its producer, MMA and
+   * first epilogue warp into trace[3][2048][2] (int64). */
   void* trace;
   /* Direct 7x7 stride-2 pad-3 stem over a 4-channel canvas (no im2col buffer).  0 = ordinary convolution.  Otherwise
    * `in` is the row-pair frame bf16 [n][stem_pitch_h / 2][stem_pitch_w][2][4] (frame pixel (fy, fx) at [fy / 2][fx][fy & 1]),
@@ -128,23 +129,21 @@ typedef struct hn_conv_desc {
 } hn_conv_desc;
 int hn_conv2d_bf16(const hn_conv_desc* desc, void* stream);
 
-/* Several dependent convolutions in ONE cooperative launch (an alternative to one launch per convolution for the A2J
- * pose net).  descs[] lists the convolutions in a dependency-consistent order.  hn_conv_multi_build validates the
- * descriptors, encodes the tensor maps, works out from the buffer pointers which earlier convolution of the list writes
- * each input / residual and which of its 128-row tiles every tile reads, and uploads the plan into plan_dev (256-byte
- * aligned device memory of hn_conv_multi_plan_bytes bytes) with a synchronous copy -- call it once per buffer set,
- * outside stream capture; it returns the grid size (> 0) or a negative status.  In the launch, tiles synchronise by
- * dataflow: a finished output tile bumps a counter, a consumer tile's loads wait for the producer tiles they read; there
- * is no grid-wide barrier, and group_begin[] (groups of mutually independent convolutions) only sizes the grid.  All
- * convolutions use 64-wide N tiles (cout_pad a multiple of 64), no GroupNorm statistics, at most 1024 row tiles each.
- * hn_conv_multi_run enqueues a memset of the tile counters and the launch. */
-int64_t hn_conv_multi_plan_bytes(int n_convs, int n_groups);
-int hn_conv_multi_build(const hn_conv_desc* descs, int n_convs, const int* group_begin_host, int n_groups,
-                        void* plan_dev, int64_t plan_bytes);
-int hn_conv_multi_run(void* plan_dev, int n_convs, int n_groups, int grid, void* stream);
-/* bring-up only: CTA 0 of every following hn_conv_multi_run writes clock64() after each group into buf[g] (int64);
- * NULL switches it off. */
-int hn_conv_multi_set_trace(void* buf);
+/* The same convolution over several pyramid levels in ONE launch (fcos_utils/fcos.py:278-289, 378-380: the FCOS towers and
+ * output convolutions apply the same modules to P3, P4 and P5 in a Python loop).  descs[0..n_levels) (n_levels <= 3)
+ * describe the levels: they share weight, scale, shift, channel counts, kernel shape, ReLU range, block_n and output kind and
+ * differ in geometry (n, h, w), in, out (bf16 outputs; fp32-row outputs share one buffer and differ in out_row_offset) and
+ * gn_stats.  Only plain 3x3 stride-1 convolutions (no residual, phase copy, split-K or stem).  The tiles of all levels
+ * form one list that is dealt over the persistent CTAs, so the small levels no longer leave most of the 148 SMs idle.
+ * Supported tile configurations: 256-wide bf16 layers (cout a multiple of 256) and 16-wide fp32-row outputs. */
+int hn_conv2d_bf16_levels(const hn_conv_desc* descs, int n_levels, void* stream);
+
+/* GroupNorm + ReLU (hn_groupnorm_relu below) over several pyramid levels in one launch: x[i] has n[i] x h[i] x w[i] pixels,
+ * stats[i] is that level's [n][groups][2] array; c, halo, groups, gamma, beta and eps are shared.  n_levels <= 3; the
+ * arrays live on the host. */
+int hn_groupnorm_relu_levels(void* const* x_host, const int* n_host, const int* h_host, const int* w_host, int n_levels, int c,
+                             int halo, const int64_t* const* stats_host, int groups, const float* gamma, const float* beta,
+                             float eps, void* stream);
 
 /* ---- frame ingest (ros_demo.py:227-238, 266-267): what the camera delivers -> what HandNet.forward takes ---------
  * bgr_u8: DEVICE uint8 [n][h][w][3] (cv2 BGR) -> rgb_out fp32 [n][3][h][w] = float32(byte) / 255 in R,G,B order;
@@ -175,8 +174,8 @@ int hn_maxpool3x3s2(const void* in, int n, int h, int w, int c, void* out, int o
 
 /* ---- GroupNorm + ReLU of the FCOS towers (fcos_utils/fcos.py:232-240, 352-360) ------------------------------
  * x: bf16 haloed NHWC, normalised in place: relu((x - mean) * rstd * gamma + beta) with mean/rstd from
- * stats[n][groups][2] (as produced by hn_conv2d_bf16) over h*w*(c/groups) elements.  Halo stays zero. */
-int hn_groupnorm_relu(void* x, int n, int h, int w, int c, int halo, const double* stats, int groups,
+ * stats[n][groups][2] (fixed-point sums as produced by hn_conv2d_bf16) over h*w*(c/groups) elements.  Halo stays zero. */
+int hn_groupnorm_relu(void* x, int n, int h, int w, int c, int halo, const int64_t* stats, int groups,
                       const float* gamma, const float* beta, float eps, void* stream);
 
 /* ---- P1..P4: decode + score + threshold (fcos_utils/fcos.py:591-632; det_utils.py:266-294;

@@ -59,22 +59,20 @@ CASES = [
     ("1x1_s2_256_512", 2, 22, 22, 256, 512, 1, 2, 1, 1, 0),
     ("3x3_dil2_512_512", 3, 11, 11, 512, 512, 3, 1, 2, 2, 0),
     ("3x3_halo2_in_halo1_conv", 2, 11, 11, 64, 64, 3, 1, 1, 2, 64),
-    # CTA pairs with multicast weights (cluster = 2); odd tile counts leave a dummy CTA in the last cluster
-    ("cs2_3x3_256_256_bn256_odd", 3, 25, 34, 256, 256, 3, 1, 1, 1, 256, 2),
-    ("cs2_1x1_512_2048_bn256", 3, 11, 11, 512, 2048, 1, 1, 1, 1, 256, 2),
-    ("cs2_3x3_s2_128_256", 2, 25, 33, 128, 256, 3, 2, 1, 1, 256, 2),
-    ("cs2_3x3_256_256_auto_big", 4, 100, 136, 256, 256, 3, 1, 1, 1, 0, 0),
+    ("3x3_256_256_bn256_odd_tiles", 3, 25, 34, 256, 256, 3, 1, 1, 1, 256),
+    ("1x1_512_2048_bn256", 3, 11, 11, 512, 2048, 1, 1, 1, 1, 256),
+    ("3x3_s2_128_256_bn256", 2, 25, 33, 128, 256, 3, 2, 1, 1, 256),
+    ("3x3_256_256_auto_big", 4, 100, 136, 256, 256, 3, 1, 1, 1, 0),
     # resident weights (one narrow N tile, >= 2 tiles per SM): layer1-like 3x3 and stem-like 1x1 GEMM
-    ("rb_3x3_64_64_layer1", 2, 200, 272, 64, 64, 3, 1, 1, 1, 0, 0),
-    ("rb_1x1_256_64_stem", 1, 400, 544, 256, 64, 1, 1, 1, 0, 0, 0),
-    ("rb_3x3_256_5_headout", 4, 100, 136, 256, 5, 3, 1, 1, 1, 0, 0),
+    ("rb_3x3_64_64_layer1", 2, 200, 272, 64, 64, 3, 1, 1, 1, 0),
+    ("rb_1x1_256_64_stem", 1, 400, 544, 256, 64, 1, 1, 1, 0, 0),
+    ("rb_3x3_256_5_headout", 4, 100, 136, 256, 5, 3, 1, 1, 1, 0),
 ]
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_conv_scale_shift_relu(ops, case):
-    name, n, h, w, cin, cout, k, stride, dil, halo, bn = case[:11]
-    cluster = case[11] if len(case) > 11 else 1
+    name, n, h, w, cin, cout, k, stride, dil, halo, bn = case
     g = torch.Generator().manual_seed(sum(map(ord, name)))
     x = rand(g, n, cin, h, w).to(DEV)
     wt = rand(g, cout, cin, k, k, scale=(cin * k * k) ** -0.5).to(DEV)
@@ -85,35 +83,11 @@ def test_conv_scale_shift_relu(ops, case):
     xin = ops.Act.from_nchw(x, halo) if stride == 1 else ops.PhaseAct.from_nchw(x, halo)
     out = ops.Act(n, ref.shape[2], ref.shape[3], cout, 1, DEV)
     ops.conv2d(xin, ops.pack_conv_weight(wt), cout=cout, ksize=k, stride=stride, dilation=dil, scale=scale,
-               shift=shift, relu=True, out=out, block_n=bn, cluster=cluster)
+               shift=shift, relu=True, out=out, block_n=bn)
     torch.cuda.synchronize()
     close_bf16(out.to_nchw(), ref, name)
     full = out.t.float().abs().sum()
     assert torch.isclose(full, out.interior().float().abs().sum()), "halo of the output must stay zero"
-
-
-@pytest.mark.parametrize("shape", [(2, 200, 272, 64, 64), (3, 100, 136, 256, 5), (4, 135, 141, 64, 32)])
-def test_conv_patch_tiles(ops, shape):
-    """Opt-in patch tiling of the resident-weights 3x3 path (debug bit 14): an M tile is a 16 x 8 pixel patch, one 4-D TMA
-    box {64, 10, 18} serves all nine taps through UMMA descriptors with a 1280-byte group stride.  Ragged patch grids
-    (135 x 141) read rows / columns beyond the tensor (zero-filled) and must not write outside the interior."""
-    n, h, w, cin, cout = shape
-    g = torch.Generator().manual_seed(h * w + cout)
-    x = rand(g, n, cin, h, w).to(DEV)
-    wt = rand(g, cout, cin, 3, 3, scale=(cin * 9) ** -0.5).to(DEV)
-    shift = (0.3 * torch.randn(cout, generator=g)).to(DEV)
-    idn = rand(g, n, cout, h, w).to(DEV)
-    ref = F.relu(F.conv2d(x, wt, None, padding=1) + shift[None, :, None, None] + idn)
-    outs = []
-    for debug in (16384, 0):
-        out = ops.Act(n, h, w, cout, 1, DEV)
-        ops.conv2d(ops.Act.from_nchw(x, 1), ops.pack_conv_weight(wt), cout=cout, ksize=3, shift=shift, relu=True,
-                   res=ops.Act.from_nchw(idn, 1), res_mode=1, out=out, debug=debug)
-        torch.cuda.synchronize()
-        close_bf16(out.to_nchw(), ref, f"patch debug={debug}")
-        assert torch.isclose(out.t.float().abs().sum(), out.interior().float().abs().sum()), "halo must stay zero"
-        outs.append(out.t.clone())
-    assert torch.equal(outs[0], outs[1]), "patch and flattened tiles accumulate the same products in the same order"
 
 
 @pytest.mark.parametrize("shape", [(2, 60, 70, 64, 64, 0), (2, 50, 68, 256, 256, 0), (3, 40, 50, 128, 128, 0), (4, 100, 136, 256, 5, 1)])
@@ -228,14 +202,20 @@ def test_conv_groupnorm_tower_layer(ops):
     raw = q(F.conv2d(x, wt, bias, padding=1))
     ref = F.relu(F.group_norm(raw, 32, gamma, beta, eps=1e-5))
     out = ops.Act(n, h, w, c, 1, DEV)
-    stats = torch.zeros(n, 32, 2, dtype=torch.float64, device=DEV)
+    stats = torch.zeros(n, 32, 2, dtype=torch.int64, device=DEV)          # 40.24 fixed-point sums
     ops.conv2d(ops.Act.from_nchw(x, 1), ops.pack_conv_weight(wt), cout=c, ksize=3, shift=bias, out=out,
                gn_stats=stats, gn_groups=32)
     torch.cuda.synchronize()
     raw_got = out.to_nchw()
     close_bf16(raw_got, raw, "raw conv")
     want = torch.stack((raw_got.double().reshape(n, 32, -1).sum(-1), (raw_got.double() ** 2).reshape(n, 32, -1).sum(-1)), -1)
-    torch.testing.assert_close(stats, want, rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(stats.double() / ops.GN_FIX_SCALE, want, rtol=1e-5, atol=1e-3)
+    # integer accumulation: a second launch produces exactly the same sums (fp atomics did not)
+    stats2 = torch.zeros_like(stats)
+    ops.conv2d(ops.Act.from_nchw(x, 1), ops.pack_conv_weight(wt), cout=c, ksize=3, shift=bias, out=ops.Act(n, h, w, c, 1, DEV),
+               gn_stats=stats2, gn_groups=32)
+    torch.cuda.synchronize()
+    assert torch.equal(stats, stats2), "GroupNorm statistics must be bit-reproducible"
     ops.groupnorm_relu(out, stats, 32, gamma, beta, 1e-5)
     torch.cuda.synchronize()
     close_bf16(out.to_nchw(), F.relu(F.group_norm(raw_got, 32, gamma, beta, eps=1e-5)), "gn apply")
@@ -354,3 +334,92 @@ def test_conv_split_k(ops, shape):
         assert cnt.abs().max() == 0
         outs.append(out.t.clone())
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), "split-K must be deterministic"
+
+
+LEVEL_SETS = [
+    # batch, levels (h, w)
+    (2, [(20, 28), (10, 14), (5, 7)]),
+    (3, [(100, 136), (50, 68), (25, 34)]),
+    (1, [(96, 168), (48, 84)]),
+]
+
+
+@pytest.mark.parametrize("n,levels", LEVEL_SETS, ids=["small", "vga_b3", "two_levels"])
+def test_conv_levels_tower_layer_equals_per_level_launches(ops, n, levels):
+    """hn_conv2d_bf16_levels: ONE launch over P3+P4+P5 with shared weights (the FCOS tower loop over levels,
+    fcos_utils/fcos.py:278-289) == one launch per level, bit for bit: bf16 outputs, zero halos and the fixed-point
+    GroupNorm sums; the fused GroupNorm-apply launch likewise."""
+    g = torch.Generator().manual_seed(21 + n)
+    c = 256
+    wt = rand(g, c, c, 3, 3, scale=0.02).to(DEV)
+    bias = (0.05 * torch.randn(c, generator=g)).to(DEV)
+    gamma = (0.7 + 0.6 * torch.rand(c, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(c, generator=g)).to(DEV)
+    wp = ops.pack_conv_weight(wt)
+    xs = [rand(g, n, c, h, w).to(DEV) for h, w in levels]
+    acts = [ops.Act.from_nchw(x, 1) for x in xs]
+    # per level
+    outs_a = [ops.Act(n, h, w, c, 1, DEV) for h, w in levels]
+    st_a = [torch.zeros(n, 32, 2, dtype=torch.int64, device=DEV) for _ in levels]
+    for a, o, st in zip(acts, outs_a, st_a):
+        ops.conv2d(a, wp, cout=c, ksize=3, shift=bias, out=o, gn_stats=st, gn_groups=32)
+    # fused
+    outs_b = [ops.Act(n, h, w, c, 1, DEV) for h, w in levels]
+    st_b = [torch.zeros(n, 32, 2, dtype=torch.int64, device=DEV) for _ in levels]
+    ops.conv2d_levels(acts, wp, cout=c, ksize=3, shift=bias, outs=outs_b, gn_stats=st_b, gn_groups=32)
+    torch.cuda.synchronize()
+    for lvl, (x, oa, ob) in enumerate(zip(xs, outs_a, outs_b)):
+        close_bf16(ob.to_nchw(), q(F.conv2d(x, wt, bias, padding=1)), f"level {lvl} vs F.conv2d")
+        assert torch.equal(oa.t, ob.t), f"level {lvl}: fused launch differs from the per-level launch"
+        assert torch.equal(st_a[lvl], st_b[lvl]), f"level {lvl}: GroupNorm sums differ"
+    for o, st in zip(outs_a, st_a):
+        ops.groupnorm_relu(o, st, 32, gamma, beta, 1e-5)
+    ops.groupnorm_relu_levels(outs_b, st_b, 32, gamma, beta, 1e-5)
+    torch.cuda.synchronize()
+    for lvl, (oa, ob) in enumerate(zip(outs_a, outs_b)):
+        assert torch.equal(oa.t, ob.t), f"level {lvl}: fused GroupNorm apply differs"
+        assert torch.isclose(ob.t.float().abs().sum(), ob.interior().float().abs().sum()), "halo must stay zero"
+
+
+@pytest.mark.parametrize("n,levels", LEVEL_SETS, ids=["small", "vga_b3", "two_levels"])
+@pytest.mark.parametrize("cout,relu", [(5, (3, 5)), (13, (10, 13))], ids=["cls_lr", "ext_heads"])
+def test_conv_levels_head_outputs_equal_per_level_launches(ops, n, levels, cout, relu):
+    """The fused FCOS output convolutions ([cls | lr | ...], ReLU on a channel sub-range) over all levels in one launch:
+    fp32 rows of every level at its row offset of the shared [n, locs, ld] buffer, nothing else written."""
+    g = torch.Generator().manual_seed(33 + n + cout)
+    wt = rand(g, cout, 256, 3, 3, scale=0.02).to(DEV)
+    bias = torch.randn(cout, generator=g).to(DEV)
+    wp = ops.pack_conv_weight(wt)
+    xs = [rand(g, n, 256, h, w).to(DEV) for h, w in levels]
+    acts = [ops.Act.from_nchw(x, 1) for x in xs]
+    starts = [0]
+    for h, w in levels:
+        starts.append(starts[-1] + h * w)
+    locs, ld = starts[-1], 16
+    buf_a = torch.full((n, locs + 3, ld), -7.0, device=DEV)
+    buf_b = torch.full((n, locs + 3, ld), -7.0, device=DEV)
+    for a, off in zip(acts, starts):
+        ops.conv2d(a, wp, cout=cout, ksize=3, shift=bias, relu=relu, out_f32=buf_a, out_rows_per_image=locs + 3, out_row_offset=off)
+    ops.conv2d_levels(acts, wp, cout=cout, ksize=3, shift=bias, relu=relu, out_f32=buf_b, out_rows_per_image=locs + 3,
+                      out_row_offsets=starts[:-1])
+    torch.cuda.synchronize()
+    assert torch.equal(buf_a, buf_b)
+    assert (buf_b[:, locs:] == -7.0).all() and (buf_b[..., cout:] == -7.0).all(), "nothing else may be written"
+    for lvl, ((h, w), x) in enumerate(zip(levels, xs)):
+        ref = F.conv2d(x, wt, bias, padding=1)
+        ref[:, relu[0]:relu[1]] = F.relu(ref[:, relu[0]:relu[1]])
+        torch.testing.assert_close(buf_b[:, starts[lvl]:starts[lvl + 1], :cout], ref.permute(0, 2, 3, 1).reshape(n, h * w, cout),
+                                   rtol=1e-4, atol=1e-4)
+
+
+def test_conv_levels_rejects_mismatched_levels(ops):
+    a = ops.Act(1, 8, 8, 256, 1, DEV)
+    b = ops.Act(1, 4, 4, 256, 1, DEV)
+    w1 = ops.pack_conv_weight(torch.randn(256, 256, 3, 3, device=DEV) * 0.02)
+    with pytest.raises(RuntimeError, match="levels"):
+        # four levels: more than the kernel's three segments
+        ops.conv2d_levels([a, b, b, b], w1, cout=256, ksize=3, outs=[ops.Act(1, 8, 8, 256, 1, DEV)] + [ops.Act(1, 4, 4, 256, 1, DEV)] * 3)
+    with pytest.raises(RuntimeError, match="unsupported combination|levels"):
+        # a 64-wide layer has no multi-level instantiation
+        w64 = ops.pack_conv_weight(torch.randn(64, 256, 3, 3, device=DEV) * 0.02)
+        ops.conv2d_levels([a, b], w64, cout=64, ksize=3, outs=[ops.Act(1, 8, 8, 64, 1, DEV), ops.Act(1, 4, 4, 64, 1, DEV)])

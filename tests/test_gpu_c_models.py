@@ -13,6 +13,13 @@ from oracle.golden_inputs import inputs_images
 
 pytestmark = pytest.mark.gpu
 
+# Measured box parity bounds (max |dbox| of location-matched detections, original-image pixels; see PARITY records in
+# profiles/r02_parity.md).  BASELINE.json's north_star names 1e-2 px; a bf16 network with ~50 layers between the pixels
+# and a regression output that is multiplied by an 8-32 px anchor size does not reach that against fp32 -- these are the
+# figures it does reach, with ~2x margin.
+BOX_PX_VS_BF16_ORACLE = 1.0
+BOX_PX_VS_FP32_REFERENCE = 3.0
+
 
 def rel_to_max(got, ref):
     got, ref = got.float().cpu(), ref.float().cpu()
@@ -22,6 +29,42 @@ def rel_to_max(got, ref):
 class Args:
     pretrained_fcos = ""
     pretrained_a2j = ""
+
+
+PARITY = {}          # measured parity figures of this session, written to gpurun_out/parity.json and printed
+
+
+def record(name, **vals):
+    import json
+    import os
+    PARITY[name] = {k: (float(v) if not isinstance(v, (int, str)) else v) for k, v in vals.items()}
+    print("PARITY", name, PARITY[name])
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    try:
+        os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(root, "gpurun_out", "parity.json"), "w") as f:
+            json.dump(PARITY, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+def matched_box_delta(out, b, oracle_det):
+    """Detections of image b of the GPU path (dense FCOS output dict) matched to an oracle run's detections BY CANDIDATE
+    LOCATION (the index of the pyramid location that produced the box): returns (max |dbox| in ORIGINAL-image pixels over
+    the matched detections, median, max |dscore|, matched fraction of the oracle's detections, label agreement)."""
+    k = int(out["keep_count"][b])
+    loc_gpu = out["cand"]["loc"][b].cpu()[out["keep"][b, :k].cpu().long()].long()
+    box_gpu, score_gpu, label_gpu = out["boxes"][b, :k].cpu(), out["scores"][b, :k].cpu(), out["labels"][b, :k].cpu()
+    loc_ref = oracle_det["_candidate_index"].long()
+    pos = {int(l): i for i, l in enumerate(loc_gpu.tolist())}
+    pairs = [(pos[int(l)], j) for j, l in enumerate(loc_ref.tolist()) if int(l) in pos]
+    assert pairs, "no detection of the oracle was found on the GPU side"
+    gi = torch.tensor([p[0] for p in pairs])
+    ri = torch.tensor([p[1] for p in pairs])
+    d = (box_gpu[gi] - oracle_det["boxes"][ri]).abs().amax(dim=1)
+    ds = (score_gpu[gi] - oracle_det["scores"][ri]).abs()
+    lab = (label_gpu[gi] == oracle_det["labels"][ri]).float().mean()
+    return d.max().item(), d.median().item(), ds.max().item(), len(pairs) / max(1, len(loc_ref)), lab.item()
 
 
 @pytest.fixture(scope="module")
@@ -58,9 +101,11 @@ def test_fcos_detections_consistent_with_oracle_postprocess(fcos_small, golden):
     imgs = inputs_images(5, 2, 120, 160)
     with torch.inference_mode():
         out = m.forward_device([i.cuda() for i in imgs])
-        # one pass only: GroupNorm partial sums are accumulated with atomics, so two passes may differ in the
-        # last bf16 bit of a few activations
         dets = m.split_detections(out, m.ext)
+        out2 = m.forward_device([i.cuda() for i in imgs])
+        # fixed-point GroupNorm sums + deterministic split-K: the detector is bit-reproducible from run to run
+        for kk in ("boxes", "scores", "labels", "keep_count", "cand_count"):
+            assert torch.equal(out[kk], out2[kk]), kk
     torch.cuda.synchronize()
     ref_dets = golden("fcos_small.pt")["dets"]
     sizes = [fcos_oracle.resized_size(120, 160, 256, 448)] * 2
@@ -80,6 +125,22 @@ def test_fcos_detections_consistent_with_oracle_postprocess(fcos_small, golden):
         r = ref_dets[b]
         assert abs(k - len(r["boxes"])) <= 0.03 * len(r["boxes"]) + 2
         assert (d["boxes"][0].cpu() - r["boxes"][0]).abs().max() < 1.0
+    # measured box parity through the convolutions (BASELINE.json north_star names 1e-2 px): detections matched by
+    # candidate location, max |dbox| in original-image pixels -- bf16 path vs the bf16-emulating oracle and, stated
+    # separately, vs the fp32 oracle (which reproduces the reference's golden detections bit for bit, checked below)
+    with torch.inference_mode():
+        d_emu = fcos_oracle.fcos_forward(sd, imgs, 3, False, 256, 448, emulate_bf16=True)
+        d_f32 = fcos_oracle.fcos_forward(sd, imgs, 3, False, 256, 448, emulate_bf16=False)
+    for b in range(2):
+        assert torch.equal(d_f32[b]["boxes"], ref_dets[b]["boxes"]), "fp32 oracle == unmodified reference (golden)"
+        e = matched_box_delta(out, b, d_emu[b])
+        f = matched_box_delta(out, b, d_f32[b])
+        record(f"fcos_small_img{b}", box_px_max_vs_bf16_oracle=e[0], box_px_median_vs_bf16_oracle=e[1], score_max_vs_bf16_oracle=e[2],
+               matched_frac_vs_bf16_oracle=e[3], box_px_max_vs_fp32_reference=f[0], box_px_median_vs_fp32_reference=f[1],
+               score_max_vs_fp32_reference=f[2], matched_frac_vs_fp32_reference=f[3])
+        assert e[3] > 0.9 and f[3] > 0.85, "most detections of the oracle must exist on the GPU side"
+        assert e[4] == 1.0 and f[4] > 0.99, "labels of matched detections"
+        assert e[0] < BOX_PX_VS_BF16_ORACLE and f[0] < BOX_PX_VS_FP32_REFERENCE, (e, f)
 
 
 def test_fcos_ext_heads(golden):
@@ -168,10 +229,28 @@ def test_handnet_end_to_end_vga(handnet_vga, golden):
         box = handnet_oracle.pad_box(hand[0].cpu().numpy(), cfg["h"], cfg["w"])
         assert crops[i].tolist() == box.tolist()
         assert torch.equal(depth_batch[i].cpu(), handnet_oracle.crop_resize(depth[i], box))
-    # pose: oracle (bf16-emulating) on the GPU's crops
+    # pose: oracle (bf16-emulating) on the GPU's crops.  Tolerance as BASELINE.json states it: 1e-3 RELATIVE on joint
+    # coordinates (crop pixels 0..176 / depth); values below 1 are compared absolutely at 1e-3
     with torch.inference_mode():
         j_emu = a2j_oracle.a2j_forward(asd, depth_batch.cpu(), emulate_bf16=True)
-    assert ((final - j_emu).abs() / j_emu.abs().clamp(min=1.0)).max() < 1e-3
+        j_f32 = a2j_oracle.a2j_forward(asd, depth_batch.cpu(), emulate_bf16=False)
+    rel_emu = ((final - j_emu).abs() / j_emu.abs().clamp(min=1.0)).max().item()
+    rel_f32 = ((final - j_f32).abs() / j_f32.abs().clamp(min=1.0)).max().item()
+    assert rel_emu < 1e-3
+    # detector boxes at VGA, matched by candidate location (see test_fcos_detections_consistent_with_oracle_postprocess)
+    with torch.inference_mode():
+        out = net.detector.forward_device([i.cuda() for i in imgs])
+        d_emu = fcos_oracle.fcos_forward(fsd, imgs, 3, False, emulate_bf16=True)
+        d_f32 = fcos_oracle.fcos_forward(fsd, imgs, 3, False, emulate_bf16=False)
+    for i in range(2):
+        e = matched_box_delta(out, i, d_emu[i])
+        f = matched_box_delta(out, i, d_f32[i])
+        record(f"handnet_vga_img{i}", box_px_max_vs_bf16_oracle=e[0], box_px_median_vs_bf16_oracle=e[1], score_max_vs_bf16_oracle=e[2],
+               matched_frac_vs_bf16_oracle=e[3], box_px_max_vs_fp32_reference=f[0], box_px_median_vs_fp32_reference=f[1],
+               score_max_vs_fp32_reference=f[2], matched_frac_vs_fp32_reference=f[3],
+               joints_rel_max_vs_bf16_oracle=rel_emu, joints_rel_max_vs_fp32_oracle_same_crops=rel_f32)
+        assert e[3] > 0.9 and f[3] > 0.85
+        assert e[0] < BOX_PX_VS_BF16_ORACLE and f[0] < BOX_PX_VS_FP32_REFERENCE, (e, f)
     # against the fp32 reference run (golden).  With random-init weights the top scores are near-ties (0.9709 vs
     # 0.9687 ...), so bf16 may rank another box first: the reference's top box must be among our first few hand
     # detections, and where the chosen crop is the same the joints must agree within 0.02.
@@ -195,8 +274,70 @@ def test_handnet_graph_replay_equals_eager(handnet_vga):
         b = net(imgs, depth_images=depth)
         net.use_cuda_graph = True
     assert torch.equal(a[2], b[2]) and torch.equal(a[1], b[1])
-    # GroupNorm statistics are accumulated with atomics: replays agree to accumulation-order noise
-    assert (a[0] - b[0]).abs().max() < 5e-3 and (a[0] - a2[0]).abs().max() < 5e-3
+    # every kernel of the path is deterministic (GroupNorm sums are integers, split-K adds its slices in a fixed order, the
+    # anchor aggregation merges its partials in a fixed order): graph replay == replay == eager launches, bit for bit
+    assert torch.equal(a[0], a2[0]) and torch.equal(a[0], b[0])
+
+
+def test_handnet_async_pipeline_equals_synchronous(handnet_vga):
+    """HandNet.submit / result with several steps in flight (pose stage of step i under the detect stage of step i+1, host
+    uploads on the copy stream) returns exactly what the synchronous forward returns for each batch, from device or pinned
+    host inputs; results come back in submission order."""
+    net, _, _ = handnet_vga
+    batches = []
+    for s_ in (81, 82, 83, 84, 85):
+        imgs = inputs_images(s_, 2, 480, 640)
+        depth = torch.rand(2, 1, 480, 640, generator=torch.Generator().manual_seed(s_)) * 1.5
+        batches.append((imgs, depth))
+    with torch.inference_mode():
+        sync = [net([i.cuda() for i in imgs], depth_images=depth.cuda()) for imgs, depth in batches]
+        # device inputs, all five in flight at once is more than the ring holds: keep three
+        tickets, got = [], []
+        for imgs, depth in batches:
+            tickets.append(net.submit([i.cuda() for i in imgs], depth.cuda()))
+            if len(tickets) == 3:
+                got.append(net.result(tickets.pop(0)))
+        while tickets:
+            got.append(net.result(tickets.pop(0)))
+        # pinned host inputs (staged uploads)
+        got_host = []
+        for imgs, depth in batches:
+            tickets.append(net.submit([i.pin_memory() for i in imgs], depth.pin_memory()))
+            if len(tickets) == 2:
+                got_host.append(net.result(tickets.pop(0)))
+        while tickets:
+            got_host.append(net.result(tickets.pop(0)))
+    for ref, a, b in zip(sync, got, got_host):
+        for x, y, z in zip(ref, a, b):
+            assert torch.equal(x.cpu(), y.cpu()) and torch.equal(x.cpu(), z.cpu())
+    # collecting out of order is refused
+    with torch.inference_mode():
+        t1 = net.submit([i.cuda() for i in batches[0][0]], batches[0][1].cuda())
+        t2 = net.submit([i.cuda() for i in batches[1][0]], batches[1][1].cuda())
+        with pytest.raises(RuntimeError, match="oldest"):
+            net.result(t2)
+        net.result(t1)
+        net.result(t2)
+
+
+def test_fcos_fused_levels_equal_per_level_schedule(fcos_small):
+    """runtime.FUSE_LEVELS: towers / output convolutions / GroupNorm as one launch over P3+P4+P5 == the per-level
+    schedule, bit for bit (same MMAs per tile; integer GroupNorm sums do not depend on the accumulation order)."""
+    from hn_b200 import runtime
+    m, _ = fcos_small
+    imgs = [i.cuda() for i in inputs_images(5, 2, 120, 160)]
+    outs = {}
+    saved = runtime.FUSE_LEVELS
+    try:
+        for fuse in (True, False):
+            runtime.FUSE_LEVELS = fuse
+            with torch.inference_mode():
+                ho = m.head_outputs(imgs)
+            outs[fuse] = {k: v.clone() for k, v in ho.items()}
+    finally:
+        runtime.FUSE_LEVELS = saved
+    for k in outs[True]:
+        assert torch.equal(outs[True][k], outs[False][k]), k
 
 
 def test_handnet_no_detection_early_return():
@@ -254,31 +395,107 @@ def test_fcos_1080p_canvas_config5():
     assert torch.equal(out["boxes"][0, :k].cpu(), fcos_oracle.resize_boxes(box[keep_ref], (749, 1333), (1080, 1920)))
 
 
-def test_a2j_multi_conv_kernel_equals_per_layer_launches(golden):
-    """The cooperative multi-convolution launch (67 convs, tile-level dataflow synchronisation) must produce the same
-    head tensors as one launch per convolution."""
+def test_a2j_forward_is_bit_reproducible():
+    """Split-K layers add their per-split slices in a fixed order: two runs over the same buffers and a run of a freshly
+    built model give identical head tensors and joints."""
     from a2j.a2j import A2JModel
-    from hn_b200 import runtime
     sd = synth.a2j_state_dict(seed=1)
     g = torch.Generator().manual_seed(23)
     x = (torch.rand(5, 1, 176, 176, generator=g) * 1.5).cuda()
     outs = []
-    default = runtime.A2J_MULTI
-    for multi in (True, False):
-        runtime.A2J_MULTI = multi
-        try:
-            m = A2JModel(21, 176, 176).eval()
-            m.load_state_dict(sd)
-            m.cuda()
-            with torch.inference_mode():
-                cls, reg, dep = m.head_outputs(x)
-                j1 = m.forward_device(x).clone()
-                j2 = m.forward_device(x).clone()          # second run: barrier counter reset, same buffers
-            # split-K layers add their partial sums with fp32 atomics: runs agree to summation-order noise
-            assert (j1 - j2).abs().max() < 2e-3
-            outs.append((cls.clone(), reg.clone(), dep.clone(), j1))
-        finally:
-            runtime.A2J_MULTI = default
+    for _ in range(2):
+        m = A2JModel(21, 176, 176).eval()
+        m.load_state_dict(sd)
+        m.cuda()
+        with torch.inference_mode():
+            cls, reg, dep = (t.clone() for t in m.head_outputs(x))
+            j1 = m.forward_device(x).clone()
+            j2 = m.forward_device(x).clone()
+        assert torch.equal(j1, j2)
+        outs.append((cls, reg, dep, j1))
     for a, b in zip(outs[0], outs[1]):
-        # (a sum that lands on the other side of a bf16 rounding boundary moves one activation by 2^-8 relative)
-        assert ((a - b).abs() / b.abs().clamp(min=1.0)).max() < 1e-2
+        assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The reference's entry scripts, restated call for call against the package (the scripts themselves need rospy /
+# cv_bridge / the 100DOH loaders and are not on the GPU box; tests/test_host_modules.py checks in the build container
+# that every name they import from handnet_pipeline / fcos_utils / a2j resolves here).
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rgbd", [False, True])
+def test_ros_demo_run_network_call_sequence(rgbd):
+    """ros_demo.py:388 (construction) and :264-289 (ImageListener.run_network), incl. the rgbd branch that passes a
+    [1,4,H,W] tensor as depth_images and an A2J Lightning checkpoint as the pose net."""
+    import numpy as np
+    from a2j.a2j import A2JModelLightning, convert_joints
+    from handnet_pipeline.handnet_pipeline import HandNet
+    args = Args()
+    # ros_demo.py:388: HandNet(args, reload_detector=True, num_classes=3, reload_a2j=True, RGBD=args.rgbd).cuda().eval()
+    # (checkpoint files: tests/test_host_modules.py; here random-init weights are put in after construction)
+    if rgbd:
+        import os
+        import tempfile
+        lm = A2JModelLightning(is_RGBD=True)
+        lm.a2j.load_state_dict(synth.a2j_state_dict(seed=1, channel_in=4))
+        with tempfile.TemporaryDirectory() as d:
+            args.pretrained_a2j = os.path.join(d, "epoch=44.ckpt")
+            torch.save({"state_dict": lm.state_dict(), "hyper_parameters": {"is_RGBD": True}}, args.pretrained_a2j)
+            network = HandNet(args, reload_detector=False, num_classes=3, reload_a2j=True, RGBD=True)
+    else:
+        network = HandNet(args, reload_detector=False, num_classes=3, reload_a2j=False, RGBD=False)
+        network.a2j.load_state_dict(synth.a2j_state_dict(seed=1))
+    network.detector.load_state_dict(synth.fcos_state_dict(3, False, seed=0))
+    network = network.cuda().eval()
+    rng = np.random.default_rng(5)
+    im_color = rng.integers(0, 256, size=(480, 640, 3), dtype=np.uint8)                  # cv2 BGR frame (:227-231)
+    depth_img = (rng.random((480, 640), dtype=np.float32) * 1.5)                          # metres (:233-238)
+    for _ in range(2):                                                                    # the main loop calls it per frame
+        with torch.inference_mode():                                                      # :265
+            rgb = im_color[:, :, ::-1]                                                    # cv2.cvtColor(BGR2RGB)
+            im_color_forward = [torch.from_numpy(rgb.transpose(2, 0, 1).astype(np.float32) / 255.0).cuda()]     # :266
+            depth_t = torch.from_numpy(depth_img).unsqueeze(0).unsqueeze(0).cuda()        # :267
+            if rgbd:
+                im_rgbd = torch.cat([im_color_forward[0].unsqueeze(0), depth_t], dim=1)   # :269
+            keypoint_pred, depth_im, detections = network(im_color_forward, depth_images=im_rgbd if rgbd else depth_t)   # :270
+            keypoint_pred = keypoint_pred.cpu()
+            depth_im = depth_im.cpu()
+            detections = detections.cpu()
+        detection = detections[0].clone()                                                 # :276-277
+        keypoint_pred = keypoint_pred[0].clone()
+        detection[:2] = torch.clamp(detection[:2], 0, im_color.shape[0])                  # :280-282
+        detection[2:] = torch.clamp(detection[2:], 0, im_color.shape[1])
+        detection = detection.numpy()
+        keypoint_pred = torch.clamp(keypoint_pred, min=0.0, max=176.0).cpu().numpy()      # :284-285
+        joint_input = convert_joints(keypoint_pred, None, detection, None, 176, 176)[:, :2]           # :289
+        assert keypoint_pred.shape == (21, 3) and joint_input.shape == (21, 2) and np.isfinite(joint_input).all()
+        assert depth_im.shape == (1, 4 if rgbd else 1, 176, 176) and detections.max() > 0
+
+
+def test_trainval_net_fcos_evaluate_call_sequence():
+    """trainval_net_fcos.py:185 (FCOS(num_classes=num_classes, nms_thresh=0.5) -- ext defaults to True), :120-130
+    (evaluate: images to the device, model(images)) and :94-103 (reshape_output reads boxes / labels / scores / contacts
+    / dxdymags / sides), :132-133 (index by score and label)."""
+    from fcos_utils.fcos import FCOS
+    model = FCOS(num_classes=3, nms_thresh=0.5)
+    model.load_state_dict(synth.fcos_state_dict(3, True, seed=3))
+    model = model.to(torch.device("cuda"))
+    model.eval()
+    g = torch.Generator().manual_seed(4)
+    batch = [torch.rand(3, 375, 500, generator=g), torch.rand(3, 360, 480, generator=g)]     # 100DOH-like, unequal sizes
+    with torch.inference_mode():
+        images = list(img.to("cuda") for img in batch)
+        torch.cuda.synchronize()
+        outputs = model(images)
+        obj_ind = [torch.nonzero((t["scores"] > 0.1) & (t["labels"] == 1)).squeeze() for t in outputs]
+        hand_ind = [torch.nonzero((t["scores"] > 0.1) & (t["labels"] == 2)).squeeze() for t in outputs]
+        for output in outputs:                                                            # reshape_output
+            n = output["boxes"].shape[0]
+            output["boxes"] = output["boxes"].reshape(n, 4)
+            output["labels"] = output["labels"].reshape(n, 1)
+            output["scores"] = output["scores"].reshape(n, 1)
+            output["contacts"] = output["contacts"].reshape(n, 1)
+            output["dxdymags"] = output["dxdymags"].reshape(n, 3)
+            output["sides"] = output["sides"].reshape(n, 1)
+    assert len(outputs) == 2 and len(obj_ind) == 2 and len(hand_ind) == 2
+    for o in outputs:
+        assert o["boxes"].is_cuda and o["labels"].dtype == torch.int64 and o["contacts"].dtype == torch.int64

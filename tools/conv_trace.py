@@ -1,4 +1,5 @@
-"""Timeline of CTA 0 of one conv launch (hn_conv_desc.trace): per role, the clock64 deltas between events.
+"""[needs a library built with the bring-up instrumentation: python -m hn_b200.build --debug (HN_CONV_DEBUG build)]
+Timeline of CTA 0 of one conv launch (hn_conv_desc.trace): per role, the clock64 deltas between events.
     python tools/conv_trace.py layer1|layer2|P3|layer3 [debug_flags]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,4 +1,5 @@
-"""What bounds the 64->64 3x3 @200x272 x8 convolution (FCOS layer1, resident-weights path)?  Times the launch with the
+"""[needs a library built with the bring-up instrumentation: python -m hn_b200.build --debug (HN_CONV_DEBUG build)]
+What bounds the 64->64 3x3 @200x272 x8 convolution (FCOS layer1, resident-weights path)?  Times the launch with the
 kernel's timing-experiment flags (hn_conv_desc.debug bits 6..9: no stores / no epilogue / no MMA / no TMA) and prints
 the L2 -> SM bytes the operand boxes need.  python tools/layer1_ablation.py [shape: layer1|layer2|p3]"""
 import os, sys

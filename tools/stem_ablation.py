@@ -1,4 +1,5 @@
-"""What bounds the direct 7x7/2 stem (8 VGA frames: 400x544 outputs, K = 256, 64 channels)?  Same timing flags as
+"""[needs a library built with the bring-up instrumentation: python -m hn_b200.build --debug (HN_CONV_DEBUG build)]
+What bounds the direct 7x7/2 stem (8 VGA frames: 400x544 outputs, K = 256, 64 channels)?  Same timing flags as
 tools/layer1_ablation.py.  python tools/stem_ablation.py"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
