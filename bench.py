@@ -290,6 +290,12 @@ def run_main(ctx: Ctx):
         sequential = {"value": world * B * args.steps / (seq_ms * 1e-3), "unit": UNIT, "ms_per_step": seq_ms / args.steps,
                       "note": "same steps, each collected before the next is submitted (no overlap of pose and detect stages)"}
         counts = step.counts()
+        if args.value_only:
+            if rank == 0:
+                print(json.dumps({"value": value, "ms_per_step": total_ms / args.steps, "sequential": sequential["value"],
+                                  "n_gpus": world, "launches_per_step": int(launches)}), flush=True)
+            sampler.stop()
+            return
 
         # ---------------- end to end through the public API with host buffers (`e2e`) ----------------
         # what a caller of the reference does (ros_demo.py:266-273): host frames -> HandNet -> joints on the host.  The
@@ -569,6 +575,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra_configs legs")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--value-only", action="store_true", help="experiments: only the device-timed value / sequential legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -87,7 +87,8 @@ class HandNet(nn.Module):
     def pose_device(self, depth_batch: torch.Tensor) -> torch.Tensor:
         """Pose stage: A2J on the crops -> joints [B,21,3] on the device."""
         if self.RGBD:
-            depth_batch = depth_batch[:, [2, 1, 0, 3]].contiguous()        # handnet_pipeline.py:102
+            # depth_batch[:, [2, 1, 0, 3]] (handnet_pipeline.py:102) without a host index tensor (graph capture)
+            depth_batch = torch.cat((depth_batch[:, 0:3].flip(1), depth_batch[:, 3:4]), dim=1).contiguous()
         return self._pose_net().forward_device(depth_batch)
 
     def forward_device(self, images: List[torch.Tensor], depth_images: torch.Tensor):

@@ -1059,6 +1059,8 @@ bool pdl_enabled() {
   return v == 1;
 }
 
+int g_cta_cap = 0;      // hn_conv_set_cta_cap: upper bound on the CTAs of the following launches (0 = all SMs)
+
 template <int BN, int PIPE, bool FAST, bool SEG>
 int launch(const CUtensorMap* ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t st) {
   constexpr int SMEM = SMEM_BYTES_ALL;
@@ -1071,7 +1073,8 @@ int launch(const CUtensorMap* ta, const CUtensorMap& tb, const ConvParams& p, cu
   const int items = p.m_tiles * p.n_tiles * p.splits;
   // equal work per CTA: with w = ceil(tiles / SMs) waves, ceil(tiles / w) CTAs finish at the same time as a full grid
   // would and leave the other SMs to kernels of concurrent streams (graph branches, the pose net of the previous step)
-  const int waves = hn_div_up(items, hn_num_sms());
+  const int sms = (g_cta_cap > 0 && g_cta_cap < hn_num_sms()) ? g_cta_cap : hn_num_sms();
+  const int waves = hn_div_up(items, sms);
   const int ctas = hn_div_up(items, waves);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -1546,9 +1549,21 @@ extern "C" int hn_conv2d_bf16_levels(const hn_conv_desc* descs, int n_levels, vo
     const long long rows = (long long)d.n * (d.h + 2 * d.halo_in) * (d.w + 2 * d.halo_in);
     total_tiles += (int)((rows + BLOCK_M - 1) / BLOCK_M);
   }
+  // the multi-level instantiations: 256-wide bf16 layers (FAST epilogue) and 16-wide fp32-row outputs with resident weights;
+  // anything else (narrow bf16 layers, too few tiles for resident weights) runs level by level -- same results
+  const hn_conv_desc& d0 = descs[0];
+  const int want_bn = d0.block_n ? d0.block_n : ((d0.out_kind == 0 && d0.cout_pad % 256 == 0) ? 256 : (d0.cout_pad == 16 ? 16 : 0));
   BuiltConv b0;
-  int rc = build_conv(&descs[0], 0, total_tiles, &b0);
+  int rc = want_bn ? build_conv(&descs[0], want_bn, total_tiles, &b0) : HN_OK;
   if (rc) return rc;
+  const bool fused_ok = want_bn != 0 && ((b0.bn == 256 && epi_fast_ok(b0.p)) || (b0.bn == 16 && b0.rb && !epi_fast_ok(b0.p)));
+  if (!fused_ok) {
+    for (int i = 0; i < n_levels; ++i) {
+      rc = hn_conv2d_bf16(&descs[i], stream);
+      if (rc) return rc;
+    }
+    return HN_OK;
+  }
   CUtensorMap ta[3] = {b0.ta, b0.ta, b0.ta};
   ConvParams& p = b0.p;
   p.n_seg = n_levels;
@@ -1580,4 +1595,12 @@ extern "C" int hn_conv2d_bf16_levels(const hn_conv_desc* descs, int n_levels, vo
              GN_SMEM_SUMS);
   p.m_tiles = tile_begin;
   return dispatch<true>(b0, ta, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Upper bound on the number of CTAs (= SMs) the following convolution launches use; 0 = all.  The runtime caps the
+// latency-bound pose-net launches so that they fit next to the detector kernels of the next step (GraphedHandNet).
+extern "C" int hn_conv_set_cta_cap(int max_ctas) {
+  HN_REQUIRE(max_ctas >= 0, "hn_conv_set_cta_cap: negative cap");
+  g_cta_cap = max_ctas;
+  return HN_OK;
 }

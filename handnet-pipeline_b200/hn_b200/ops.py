@@ -167,6 +167,11 @@ def device_info() -> Tuple[int, int, int]:
     return sm.value, ma.value, mi.value
 
 
+def conv_cta_cap(max_ctas: int):
+    """Upper bound on the CTAs of the following convolution launches (0 = all SMs)."""
+    check(_lib.load().hn_conv_set_cta_cap(int(max_ctas)), "hn_conv_set_cta_cap")
+
+
 def launch_count() -> int:
     return int(_lib.load().hn_launch_count())
 

@@ -92,6 +92,9 @@ SPLIT_K = True              # split-K (fp32 scratch + last-arriver epilogue) for
 FUSE_LEVELS = True          # FCOS towers / output convolutions / GroupNorm: ONE launch over P3+P4+P5 per layer
                             # (hn_conv2d_bf16_levels) instead of one per level; False = round-1 schedule (six chains), kept for
                             # A/B timing and the equality test (outputs are bit-identical either way)
+import os as _os
+POSE_PRIORITY = _os.environ.get("HN_POSE_PRIO", "high")      # priority of the pose stream relative to the detect stream
+POSE_CTA_CAP = int(_os.environ.get("HN_POSE_CTAS", "0"))     # CTAs per pose-net convolution launch (0 = all SMs)
 PARALLEL_CHAINS = True      # independent layer chains (head towers, A2J towers) on forked streams / graph branches
 
 
@@ -691,8 +694,9 @@ class GraphedHandNet:
         self.rec = None
         self.launches_per_step = 0
         lo, hi = torch.cuda.Stream.priority_range()            # (lowest, highest) = (0, -N)
-        self.det_stream = torch.cuda.Stream(device=dev, priority=lo)
-        self.pose_stream = torch.cuda.Stream(device=dev, priority=hi)
+        pr = {"high": (lo, hi), "low": (hi, lo), "same": (lo, lo)}[POSE_PRIORITY]
+        self.det_stream = torch.cuda.Stream(device=dev, priority=pr[0])
+        self.pose_stream = torch.cuda.Stream(device=dev, priority=pr[1])
         # hand-off blob [crops int64 B*4 | has_hand int32 B (padded to 8 B) | depth crops fp32] twice: written by the detect
         # stage / read by the pose stage
         from handnet_pipeline.handnet_pipeline import CROP_SIZE
@@ -738,6 +742,11 @@ class GraphedHandNet:
             else:
                 self.rgb.copy_(rgb, non_blocking=True)
             self.depth.copy_(depth, non_blocking=True)
+        # the sources are read on the detect stream, possibly long after this call has returned: tell the caching allocator,
+        # or a caller's temporary (`x.cuda()`) could be recycled for the next batch's upload before it has been copied
+        for t in (list(rgb) if isinstance(rgb, (list, tuple)) else [rgb]) + [depth]:
+            if t.is_cuda:
+                t.record_stream(self.det_stream)
 
     def load_frames_u8(self, bgr_u8: torch.Tensor, depth_u16: torch.Tensor):
         """Camera frames (uint8 BGR [B,H,W,3], uint16 / int16 millimetres [B,H,W]; host or device) -> the static fp32 input
@@ -745,8 +754,11 @@ class GraphedHandNet:
         if bgr_u8.device.type == "cpu":
             return self._load_staged(bgr_u8, depth_u16, u8=True)
         self.det_stream.wait_stream(torch.cuda.current_stream(self.dev))
+        bgr_u8, depth_u16 = bgr_u8.contiguous(), depth_u16.contiguous()
         with torch.cuda.stream(self.det_stream):
-            ops.ingest_frames(bgr_u8.contiguous(), depth_u16.contiguous(), rgb_out=self.rgb, depth_out=self.depth)
+            ops.ingest_frames(bgr_u8, depth_u16, rgb_out=self.rgb, depth_out=self.depth)
+        bgr_u8.record_stream(self.det_stream)
+        depth_u16.record_stream(self.det_stream)
 
     def _load_staged(self, a, b, u8: bool):
         key = "u8" if u8 else "f32"
@@ -802,8 +814,10 @@ class GraphedHandNet:
         saved, PLAN_SLOT = PLAN_SLOT, self.slot
         crops, has, depth_batch = self._views(self.hand_p)
         try:
+            ops.conv_cta_cap(POSE_CTA_CAP)
             joints = self.net.pose_device(depth_batch)
         finally:
+            ops.conv_cta_cap(0)
             PLAN_SLOT = saved
         self.rec = pack_records(joints, crops, has)
         self.out = {"joints": joints, "has_hand": has, "crops": crops, "depth_batch": depth_batch, "det": self.det}

@@ -135,8 +135,13 @@ int hn_conv2d_bf16(const hn_conv_desc* desc, void* stream);
  * differ in geometry (n, h, w), in, out (bf16 outputs; fp32-row outputs share one buffer and differ in out_row_offset) and
  * gn_stats.  Only plain 3x3 stride-1 convolutions (no residual, phase copy, split-K or stem).  The tiles of all levels
  * form one list that is dealt over the persistent CTAs, so the small levels no longer leave most of the 148 SMs idle.
- * Supported tile configurations: 256-wide bf16 layers (cout a multiple of 256) and 16-wide fp32-row outputs. */
+ * Fused tile configurations: 256-wide bf16 layers (cout a multiple of 256) and 16-wide fp32-row outputs with enough tiles
+ * for resident weights; other shapes run level by level inside the call (same results). */
 int hn_conv2d_bf16_levels(const hn_conv_desc* descs, int n_levels, void* stream);
+
+/* Upper bound on the CTAs (SMs) the following hn_conv2d_bf16* launches of this process use (0 = all SMs, the default).
+ * The runtime caps the latency-bound pose-net launches so that they fit next to the detector kernels of the next step. */
+int hn_conv_set_cta_cap(int max_ctas);
 
 /* GroupNorm + ReLU (hn_groupnorm_relu below) over several pyramid levels in one launch: x[i] has n[i] x h[i] x w[i] pixels,
  * stats[i] is that level's [n][groups][2] array; c, halo, groups, gamma, beta and eps are shared.  n_levels <= 3; the

@@ -403,7 +403,9 @@ def test_conv_levels_head_outputs_equal_per_level_launches(ops, n, levels, cout,
     ops.conv2d_levels(acts, wp, cout=cout, ksize=3, shift=bias, relu=relu, out_f32=buf_b, out_rows_per_image=locs + 3,
                       out_row_offsets=starts[:-1])
     torch.cuda.synchronize()
-    assert torch.equal(buf_a, buf_b)
+    # (per-level launches of the small levels stream their weights and accumulate kernel row by kernel row, the fused launch
+    # keeps them resident and accumulates chunk by chunk: fp32 rows agree to summation-order noise, not bit for bit)
+    torch.testing.assert_close(buf_a, buf_b, rtol=1e-5, atol=1e-5)
     assert (buf_b[:, locs:] == -7.0).all() and (buf_b[..., cout:] == -7.0).all(), "nothing else may be written"
     for lvl, ((h, w), x) in enumerate(zip(levels, xs)):
         ref = F.conv2d(x, wt, bias, padding=1)
@@ -419,7 +421,13 @@ def test_conv_levels_rejects_mismatched_levels(ops):
     with pytest.raises(RuntimeError, match="levels"):
         # four levels: more than the kernel's three segments
         ops.conv2d_levels([a, b, b, b], w1, cout=256, ksize=3, outs=[ops.Act(1, 8, 8, 256, 1, DEV)] + [ops.Act(1, 4, 4, 256, 1, DEV)] * 3)
-    with pytest.raises(RuntimeError, match="unsupported combination|levels"):
-        # a 64-wide layer has no multi-level instantiation
-        w64 = ops.pack_conv_weight(torch.randn(64, 256, 3, 3, device=DEV) * 0.02)
-        ops.conv2d_levels([a, b], w64, cout=64, ksize=3, outs=[ops.Act(1, 8, 8, 64, 1, DEV), ops.Act(1, 4, 4, 64, 1, DEV)])
+    # a 64-wide layer has no multi-level instantiation: it runs level by level inside the call
+    w64 = ops.pack_conv_weight(torch.randn(64, 256, 3, 3, device=DEV) * 0.02)
+    o = [ops.Act(1, 8, 8, 64, 1, DEV), ops.Act(1, 4, 4, 64, 1, DEV)]
+    ops.conv2d_levels([a, b], w64, cout=64, ksize=3, outs=o)
+    o2 = [ops.Act(1, 8, 8, 64, 1, DEV), ops.Act(1, 4, 4, 64, 1, DEV)]
+    for x, y in zip([a, b], o2):
+        ops.conv2d(x, w64, cout=64, ksize=3, out=y)
+    torch.cuda.synchronize()
+    assert torch.equal(o[0].t, o2[0].t) and torch.equal(o[1].t, o2[1].t)
+
