@@ -130,6 +130,7 @@ struct ConvParams {
                                     // chunk ([3][136 rows][128 B], the third box dimension steps by one image row), so a
                                     // k-step is a whole 64-channel chunk: 36 MMAs per barrier round trip
   int vec32;                        // epilogue may use 32-byte global accesses (cout % 16 == 0, 32-byte aligned bases)
+  int pipe_bytes;                   // bytes of the operand area this configuration really uses (host: dynamic smem size)
   int n_seg;                        // segments of the launch (SEG kernels; 1 otherwise)
   SegGeo seg[MAX_SEGS];
   int dbg_flags;                    // HN_CONV_DEBUG builds only: timing experiments (bit0 no stores, bit1 no epilogue work,
@@ -1080,7 +1081,9 @@ int launch(const CUtensorMap* ta, const CUtensorMap& tb, const ConvParams& p, cu
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(ctas);
   cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = SMEM;
+  // only what this configuration uses: the 256-wide tower layers leave ~9 KB of the SM's shared memory (and 11 K registers)
+  // free, enough for blocks of the memory-bound GroupNorm kernel of the OTHER tower to run on the same SMs underneath
+  cfg.dynamicSmemBytes = 1024 + HDR_PAD + p.pipe_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   int na = 0;
@@ -1314,6 +1317,10 @@ int build_conv(const hn_conv_desc* d, int force_bn, int total_m_tiles, BuiltConv
     p.na_stages = Cfg<256>::NA;
     p.nb_stages = Cfg<256>::NB;
   }
+  p.pipe_bytes = uni ? p.uni_stages * p.uni_stride
+                     : (rb ? p.rb_b_bytes + p.na_stages * (rb3 ? 3 * A_SLOT_BYTES : A_SLOT_BYTES)
+                           : p.na_stages * A_SLOT_BYTES + p.nb_stages * bn * BLOCK_K * 2);
+  HN_REQUIRE(p.pipe_bytes <= PIPE_BYTES_MAX, "hn_conv2d_bf16: internal: operand area %d > %d", p.pipe_bytes, PIPE_BYTES_MAX);
   p.cout = d->cout;
   p.cout_pad = d->cout_pad;
   p.scale = d->scale;
