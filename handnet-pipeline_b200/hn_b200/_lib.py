@@ -52,6 +52,7 @@ SIGNATURES = {
     "hn_conv2d_bf16": (_i, [C.POINTER(ConvDesc), _c_p]),
     "hn_conv2d_bf16_levels": (_i, [C.POINTER(ConvDesc), _i, _c_p]),
     "hn_conv_set_cta_cap": (_i, [_i]),
+    "hn_conv_set_pdl": (_i, [_i]),
     "hn_groupnorm_relu_levels": (_i, [C.POINTER(_c_p), _ip, _ip, _ip, _i, _i, _i, C.POINTER(_c_p), _i, _c_p, _c_p, _f, _c_p]),
     "hn_ingest_frames": (_i, [_c_p, _c_p, _i, _i, _i, _c_p, _c_p, _c_p]),
     "hn_pack_nhwc4_frame": (_i, [_c_p, _i, _i, _i, _i, _ip, _c_p, _i, _i, _i, _i, _c_p]),

@@ -1061,6 +1061,7 @@ bool pdl_enabled() {
 }
 
 int g_cta_cap = 0;      // hn_conv_set_cta_cap: upper bound on the CTAs of the following launches (0 = all SMs)
+int g_pdl_off = 0;      // hn_conv_set_pdl(0): the following launches do not use programmatic dependent launch
 
 template <int BN, int PIPE, bool FAST, bool SEG>
 int launch(const CUtensorMap* ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t st) {
@@ -1087,7 +1088,7 @@ int launch(const CUtensorMap* ta, const CUtensorMap& tb, const ConvParams& p, cu
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   int na = 0;
-  if (pdl_enabled()) {
+  if (pdl_enabled() && !g_pdl_off) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
@@ -1609,5 +1610,12 @@ extern "C" int hn_conv2d_bf16_levels(const hn_conv_desc* descs, int n_levels, vo
 extern "C" int hn_conv_set_cta_cap(int max_ctas) {
   HN_REQUIRE(max_ctas >= 0, "hn_conv_set_cta_cap: negative cap");
   g_cta_cap = max_ctas;
+  return HN_OK;
+}
+
+// Programmatic dependent launch for the following convolution launches: 1 (default) = a kernel's CTAs may become resident
+// while its predecessor in the stream is still running (they wait inside the kernel); 0 = plain stream order.
+extern "C" int hn_conv_set_pdl(int enabled) {
+  g_pdl_off = enabled ? 0 : 1;
   return HN_OK;
 }

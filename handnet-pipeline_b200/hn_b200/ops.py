@@ -172,6 +172,11 @@ def conv_cta_cap(max_ctas: int):
     check(_lib.load().hn_conv_set_cta_cap(int(max_ctas)), "hn_conv_set_cta_cap")
 
 
+def conv_pdl(enabled: bool):
+    """Programmatic dependent launch for the following convolution launches (default on)."""
+    check(_lib.load().hn_conv_set_pdl(int(bool(enabled))), "hn_conv_set_pdl")
+
+
 def launch_count() -> int:
     return int(_lib.load().hn_launch_count())
 

@@ -95,6 +95,8 @@ FUSE_LEVELS = True          # FCOS towers / output convolutions / GroupNorm: ONE
 import os as _os
 POSE_PRIORITY = _os.environ.get("HN_POSE_PRIO", "high")      # priority of the pose stream relative to the detect stream
 POSE_CTA_CAP = int(_os.environ.get("HN_POSE_CTAS", "0"))     # CTAs per pose-net convolution launch (0 = all SMs)
+POSE_PDL = _os.environ.get("HN_POSE_PDL", "1") != "0"        # programmatic dependent launch inside the pose stage
+DET_PDL = _os.environ.get("HN_DET_PDL", "1") != "0"
 PARALLEL_CHAINS = True      # independent layer chains (head towers, A2J towers) on forked streams / graph branches
 
 
@@ -277,26 +279,44 @@ class FCOSExecutor:
         mark("preprocess")
         ops.conv2d(pl.frame, w.stem_w, cout=64, ksize=1, scale=w.stem_scale, shift=w.stem_shift, relu=True, out=pl.stem,
                    algo_k=147)
-        x = ops.maxpool3x3s2(pl.stem.t, pl.stage[0][0])
+        ops.maxpool3x3s2(pl.stem.t, pl.stage[0][0])
         feats = []
         mark("stem+maxpool")
         for li in range(4):
             bufs = pl.stage[li]
-            blocks = w.blocks[li]
-            for bi, blk in enumerate(blocks):
-                free = [b for b in bufs if b is not x]
-                last = bi == len(blocks) - 1
+            # the layer as a list of convolutions over buffer indices (three rotating buffers per stage)
+            prog = []
+            xi = 0 if li == 0 else None          # layer1 starts from the pooled stem in bufs[0]; later layers from the phase copy
+            for bi, blk in enumerate(w.blocks[li]):
+                last = bi == len(w.blocks[li]) - 1
+                ph = last and li < 3
                 if "down" in blk:
-                    src = pl.phase[li - 1]
-                    y = blk["conv1"].run(src, relu=True, out=free[0])
-                    idn = blk["down"].run(src, out=free[1])
+                    f0, f1 = (0, 1) if xi is None else [i for i in range(3) if i != xi][:2]
+                    prog.append(dict(conv=blk["conv1"], src="phase", relu=True, out=f0, res=None, out_phase=False))
+                    prog.append(dict(conv=blk["down"], src="phase", relu=False, out=f1, res=None, out_phase=False))
                     # the identity buffer is read and overwritten by the same threads of the epilogue
-                    x = blk["conv2"].run(y, relu=True, res=idn, res_mode=1, out=idn,
-                                         out_phase=pl.phase[li] if (last and li < 3) else None)
+                    prog.append(dict(conv=blk["conv2"], src=f0, relu=True, out=f1, res=f1, out_phase=ph))
+                    xi = f1
                 else:
-                    y = blk["conv1"].run(x, relu=True, out=free[0])
-                    x = blk["conv2"].run(y, relu=True, res=x, res_mode=1, out=free[1],
-                                         out_phase=pl.phase[li] if (last and li < 3) else None)
+                    f0, f1 = [i for i in range(3) if i != xi][:2]
+                    prog.append(dict(conv=blk["conv1"], src=xi, relu=True, out=f0, res=None, out_phase=False))
+                    prog.append(dict(conv=blk["conv2"], src=f0, relu=True, out=f1, res=xi, out_phase=ph))
+                    xi = f1
+
+            def emit(ins, bset, phase_in, phase_out):
+                src = phase_in if ins["src"] == "phase" else bset[ins["src"]]
+                ins["conv"].run(src, relu=ins["relu"], out=bset[ins["out"]],
+                                res=None if ins["res"] is None else bset[ins["res"]], res_mode=1 if ins["res"] is not None else 0,
+                                out_phase=phase_out if ins["out_phase"] else None)
+
+            phase_in = pl.phase[li - 1] if li > 0 else None
+            phase_out = pl.phase[li] if li < 3 else None
+            # (Running a badly quantised layer -- layer3 at 8 VGA frames: 228 tiles = two rounds at 77 % -- as two half-batch
+            # chains on two streams, so that one chain's next convolution takes the SMs the other leaves idle, was measured:
+            # layer3 388 -> 382 us, step unchanged within noise; not kept.)
+            for ins in prog:
+                emit(ins, bufs, phase_in, phase_out)
+            x = bufs[xi]
             if li >= 1:
                 feats.append(x)
             mark(f"layer{li + 1}")
@@ -803,8 +823,10 @@ class GraphedHandNet:
         global PLAN_SLOT
         saved, PLAN_SLOT = PLAN_SLOT, self.slot
         try:
+            ops.conv_pdl(DET_PDL)
             det, crops, has, depth_batch = self.net.detect_crop_device(self.images, self.depth, out=self._views(self.hand_d))
         finally:
+            ops.conv_pdl(True)
             PLAN_SLOT = saved
         self.det = det
         return det
@@ -815,9 +837,11 @@ class GraphedHandNet:
         crops, has, depth_batch = self._views(self.hand_p)
         try:
             ops.conv_cta_cap(POSE_CTA_CAP)
+            ops.conv_pdl(POSE_PDL)
             joints = self.net.pose_device(depth_batch)
         finally:
             ops.conv_cta_cap(0)
+            ops.conv_pdl(True)
             PLAN_SLOT = saved
         self.rec = pack_records(joints, crops, has)
         self.out = {"joints": joints, "has_hand": has, "crops": crops, "depth_batch": depth_batch, "det": self.det}

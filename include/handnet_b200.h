@@ -142,6 +142,9 @@ int hn_conv2d_bf16_levels(const hn_conv_desc* descs, int n_levels, void* stream)
 /* Upper bound on the CTAs (SMs) the following hn_conv2d_bf16* launches of this process use (0 = all SMs, the default).
  * The runtime caps the latency-bound pose-net launches so that they fit next to the detector kernels of the next step. */
 int hn_conv_set_cta_cap(int max_ctas);
+/* Programmatic dependent launch for the following hn_conv2d_bf16* launches (default 1: a kernel's CTAs may become resident
+ * and wait inside the kernel while its predecessor in the stream is still running; 0: plain stream order). */
+int hn_conv_set_pdl(int enabled);
 
 /* GroupNorm + ReLU (hn_groupnorm_relu below) over several pyramid levels in one launch: x[i] has n[i] x h[i] x w[i] pixels,
  * stats[i] is that level's [n][groups][2] array; c, halo, groups, gamma, beta and eps are shared.  n_levels <= 3; the
