@@ -15,7 +15,7 @@ so the published algorithm is restated here in numpy float32:
   (boxes shifted by ``label * (max_coord + 1)``) when ``boxes.numel() <= 4000`` on the
   CPU and per-class NMS followed by a descending score sort above that.
 
-Pinned against ``torchvision.ops.nms`` / ``batched_nms`` in tests/test_oracle_nms.py.
+Pinned against ``torchvision.ops.nms`` / ``batched_nms`` in tests/test_oracle_golden.py.
 """
 from __future__ import annotations
 
