@@ -107,8 +107,14 @@ static __device__ __noinline__ void hn_mbar_timeout(const void* bar, uint32_t pa
 __device__ __forceinline__ void hn_mbar_wait(uint64_t* bar, uint32_t parity) {
   if (hn_mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
+  long long t0 = 0;
   while (!hn_mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) hn_mbar_timeout(bar, parity);
+    // time-based bound (~2 s of SM clock): a try_wait may suspend the thread for a while, so a spin count alone says little
+    if ((++spins & 1023u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) hn_mbar_timeout(bar, parity);
+    }
   }
 }
 // One lane of a CONVERGED warp (all 32 lanes must execute this).  Code guarded by the result is known to the
@@ -244,6 +250,68 @@ __device__ __forceinline__ void hn_umma_commit_addr(uint32_t bar_addr) {
                  ::"r"(bar_addr), "h"((uint16_t)((1u << CS) - 1u)) : "memory");
   }
 }
+
+// ---- CTA pairs (tcgen05 cta_group::2) -------------------------------------------------------------------------------
+// A pair = the two CTAs of a cluster of 2 (same TPC).  The leader (cluster rank 0) issues tcgen05.mma.cta_group::2 for
+// both: M = 256 (each CTA's own 128 rows of A), B split in halves (each CTA's shared memory holds N/2 rows of the weight
+// tile), accumulators in each CTA's own TMEM.  Operand loads of BOTH CTAs signal the leader's mbarrier.
+constexpr uint32_t HN_PEER_BIT_MASK = 0xFEFFFFFFu;     // clears the CTA-rank bit of a shared::cluster address (-> rank 0)
+
+template <int COLS>
+__device__ __forceinline__ void hn_tmem_alloc_pair(uint32_t* smem_dst) {      // one warp of EACH CTA, same smem offset
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(hn_smem_u32(smem_dst)),
+               "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void hn_tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+// TMA loads whose completion bytes go to the mbarrier at `bar`'s offset in the LEADER CTA (executed by either CTA)
+__device__ __forceinline__ void hn_tma_load_2d_pair(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(hn_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(hn_smem_u32(bar) & HN_PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void hn_tma_load_3d_pair(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(hn_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(hn_smem_u32(bar) & HN_PEER_BIT_MASK), "r"(c0), "r"(c1),
+        "r"(c2)
+      : "memory");
+}
+// arrive on the mbarrier at `bar`'s offset in the leader CTA's shared memory (from either CTA of the pair)
+__device__ __forceinline__ void hn_mbar_arrive_leader(uint64_t* bar) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(hn_smem_u32(bar)));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// Four K=16 steps of a pair MMA (see hn_umma_bf16_x4); issued by ONE thread of the leader CTA
+__device__ __forceinline__ void hn_umma_bf16_x4_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                     uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %5, %6, %3, 1;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %7, %8, %3, 1;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %9, %10, %3, 1;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "l"(desc_a + 2), "l"(desc_b + 2),
+        "l"(desc_a + 4), "l"(desc_b + 4), "l"(desc_a + 6), "l"(desc_b + 6)
+      : "memory");
+}
+// tcgen05.commit of the pair's MMAs: arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void hn_umma_commit_pair(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar_addr), "h"((uint16_t)3) : "memory");
+}
+// Instruction descriptor of a pair MMA: bf16 A/B (K-major both), fp32 accumulate, M = 256 over the two CTAs
+__host__ __device__ constexpr uint32_t hn_umma_idesc_bf16_pair(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(256 >> 4) << 24);
+}
+
 __device__ __forceinline__ void hn_tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives lane (taddr.lane + t).

@@ -199,7 +199,7 @@ __device__ __forceinline__ int seg_of(const ConvParams& p, int mt) {
 // ---------------------------------------------------------------------------------------------------------------
 // The whole kernel: prologue (barriers, TMEM), the three role loops, teardown.
 // ---------------------------------------------------------------------------------------------------------------
-template <int BN, int PIPE, bool FAST, bool SEG>
+template <int BN, int PIPE, bool FAST, bool SEG, bool PAIR = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a1,
                   const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_b,
@@ -210,6 +210,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   static_assert(PIPE != PIPE_RING || BN == 256, "two rings: 256-wide tiles only");
   static_assert(PIPE != PIPE_UNI || BN <= 128, "unified stages: tiles of at most 128 columns");
   static_assert(PIPE != PIPE_RB || BN <= 64, "resident weights: narrow tiles only");
+  static_assert(!SEG || PIPE != PIPE_UNI, "segments: two-ring and resident-weights pipelines only");
+  static_assert(!PAIR || (PIPE == PIPE_RING && FAST), "CTA pairs: the 256-wide two-ring pipeline with the FAST epilogue");
+  // PAIR: the two CTAs of a cluster work on two consecutive M tiles of the same N tile as ONE tcgen05.mma.cta_group::2
+  // (M = 256): each CTA loads its own A boxes and HALF of every weight tile, the leader (cluster rank 0) issues the MMAs
+  // for both, every CTA drains its own TMEM.  Halves the weight traffic L2 -> shared memory and the B operand reads per SM.
+  constexpr int B_ROWS = PAIR ? BN / 2 : BN;                        // weight rows this CTA holds per tap
+  constexpr int B_STAGE = B_ROWS * BLOCK_K * 2;
+  const int cta_rank = PAIR ? (int)hn_cluster_ctarank() : 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem_hdr = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_hdr);
@@ -239,13 +247,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     hn_mbar_init(b_full, 1);
     for (int b = 0; b < 8; ++b) {
       hn_mbar_init(&tmem_full[b], 1);
-      hn_mbar_init(&tmem_empty[b], EPI_WARPS);   // one arrive per epilogue warp
+      hn_mbar_init(&tmem_empty[b], PAIR ? 2 * EPI_WARPS : EPI_WARPS);   // one arrive per epilogue warp (of both CTAs)
     }
     hn_mbar_init_fence();
   }
-  if ((threadIdx.x >> 5) == 1) hn_tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  if constexpr (PAIR) {
+    __syncthreads();
+    hn_cluster_sync();                       // the peer's barriers exist before anything can signal them
+    if ((threadIdx.x >> 5) == 1) hn_tmem_alloc_pair<C::TMEM_COLS>(tmem_slot);
+  } else {
+    if ((threadIdx.x >> 5) == 1) hn_tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  }
   hn_tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) hn_cluster_sync();     // both CTAs hold their TMEM before the leader issues an MMA into it
   hn_tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may run
@@ -277,8 +292,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   // tile schedule: work item = (M tile, N tile, K split), N fastest, strided over the CTAs
-  const int first_tile = blockIdx.x, tile_stride = gridDim.x;
-  const int num_items = p.m_tiles * n_tiles * splits;
+  const int first_tile = PAIR ? blockIdx.x >> 1 : blockIdx.x, tile_stride = PAIR ? gridDim.x >> 1 : gridDim.x;
+  const int num_items = PAIR ? ((p.m_tiles + 1) >> 1) * n_tiles : p.m_tiles * n_tiles * splits;   // PAIR: pairs of M tiles
   const int s_base = k_steps / splits, s_rem = k_steps - s_base * splits;
 
   // The producer and MMA loops are single-instruction-stream code on the kernel's critical path (a 64-wide tile has
@@ -337,6 +352,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       }
       int mt = st, nt = 0;
       if (n_tiles > 1) { mt = st / n_tiles; nt = st - mt * n_tiles; }
+      if constexpr (PAIR) mt = mt * 2 + cta_rank;
       int m0 = mt * BLOCK_M;
       const int n0 = nt * BN;
       // segments: the tile's rows, box shifts and tensor map are those of its pyramid level
@@ -391,8 +407,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             if (HN_DBG(8)) {                                 // timing experiment: no loads at all
               hn_mbar_arrive(&a_full[a_stage]);
             } else {
-              hn_mbar_expect_tx(&a_full[a_stage], (uint32_t)a_box_bytes);
-              hn_tma_load_3d(a_ring + a_stage * a_slot_bytes, tma, &a_full[a_stage], cc * BLOCK_K, m0 + shift, info >> 24);
+              if constexpr (PAIR) {
+                // both CTAs' boxes complete on the LEADER's barrier, which the leader arms for both
+                if (cta_rank == 0) hn_mbar_expect_tx(&a_full[a_stage], 2u * (uint32_t)a_box_bytes);
+                hn_tma_load_3d_pair(a_ring + a_stage * a_slot_bytes, tma, &a_full[a_stage], cc * BLOCK_K, m0 + shift, info >> 24);
+              } else {
+                hn_mbar_expect_tx(&a_full[a_stage], (uint32_t)a_box_bytes);
+                hn_tma_load_3d(a_ring + a_stage * a_slot_bytes, tma, &a_full[a_stage], cc * BLOCK_K, m0 + shift, info >> 24);
+              }
             }
           }
           if (++a_stage == na) { a_stage = 0; a_phase ^= 1; }
@@ -409,8 +431,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 if (HN_DBG(8)) {
                   hn_mbar_arrive(&b_full_ring[b_stage]);
                 } else {
-                  hn_mbar_expect_tx(&b_full_ring[b_stage], (uint32_t)C::B_STAGE_BYTES);
-                  hn_tma_load_2d(b_ring + b_stage * C::B_STAGE_BYTES, &tm_b, &b_full_ring[b_stage], 0, krow);
+                  if constexpr (PAIR) {
+                    // this CTA's half of the weight tile: rows [rank * BN/2, +BN/2)
+                    if (cta_rank == 0) hn_mbar_expect_tx(&b_full_ring[b_stage], 2u * (uint32_t)B_STAGE);
+                    hn_tma_load_2d_pair(b_ring + b_stage * B_STAGE, &tm_b, &b_full_ring[b_stage], 0, krow + cta_rank * B_ROWS);
+                  } else {
+                    hn_mbar_expect_tx(&b_full_ring[b_stage], (uint32_t)C::B_STAGE_BYTES);
+                    hn_tma_load_2d(b_ring + b_stage * C::B_STAGE_BYTES, &tm_b, &b_full_ring[b_stage], 0, krow);
+                  }
                 }
               }
               krow += krow_step;
@@ -427,10 +455,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
+    // (CTA pairs: the leader's warp issues for both CTAs; the follower's warp 1 only allocates / frees its TMEM)
+    if (!PAIR || cta_rank == 0) {
     // Converged warp; tcgen05.mma / commit are issued by one elected lane.  (A second issuing warp taking alternate
     // tiles was tried twice for the narrow tiles and bought nothing once the epilogue ran, so there is one issuer.)
-    constexpr uint32_t idesc = hn_umma_idesc_bf16(BN);
-    constexpr uint32_t A_SLOT_D = A_SLOT_BYTES >> 4, B_SLOT_D = C::B_STAGE_BYTES >> 4, ROW_D = (BLOCK_K * 2) >> 4;
+    constexpr uint32_t idesc = PAIR ? hn_umma_idesc_bf16_pair(BN) : hn_umma_idesc_bf16(BN);
+    constexpr uint32_t A_SLOT_D = A_SLOT_BYTES >> 4, B_SLOT_D = B_STAGE >> 4, ROW_D = (BLOCK_K * 2) >> 4;
     int a_stage = 0, b_stage = 0, it = 0;
     uint32_t a_phase = 0, b_phase = 0;
     // low words of the shared-memory descriptors of slot 0 of each ring (start address >> 4 in bits 0..13); the high
@@ -564,8 +594,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
               const uint32_t db_lo = b_desc0 + b_stage * B_SLOT_D;
               const uint32_t eb = hn_smem_u32(&b_empty[b_stage]);
               if (hn_elect_one()) {
-                if (!HN_DBG(4)) hn_umma_bf16_x4(d_tmem, desc_hi | da_t, desc_hi | db_lo, idesc, accumulate);
-                hn_umma_commit_addr<1>(eb);                     // weight slot free once these MMAs have read it
+                if constexpr (PAIR) {
+                  hn_umma_bf16_x4_pair(d_tmem, desc_hi | da_t, desc_hi | db_lo, idesc, accumulate);
+                  hn_umma_commit_pair(eb);                      // both CTAs' weight slots
+                } else {
+                  if (!HN_DBG(4)) hn_umma_bf16_x4(d_tmem, desc_hi | da_t, desc_hi | db_lo, idesc, accumulate);
+                  hn_umma_commit_addr<1>(eb);                   // weight slot free once these MMAs have read it
+                }
               }
               accumulate = 1;
               da_t += off_step;
@@ -573,8 +608,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             }
             const uint32_t ea = hn_smem_u32(&a_empty[a_stage]), tf = hn_smem_u32(&tmem_full[buf]);
             if (hn_elect_one()) {
-              hn_umma_commit_addr<1>(ea);                         // A box free
-              if (last) hn_umma_commit_addr<1>(tf);               // accumulator complete -> epilogue
+              if constexpr (PAIR) {
+                hn_umma_commit_pair(ea);
+                if (last) hn_umma_commit_pair(tf);                // both CTAs' epilogues
+              } else {
+                hn_umma_commit_addr<1>(ea);                       // A box free
+                if (last) hn_umma_commit_addr<1>(tf);             // accumulator complete -> epilogue
+              }
             }
           }
           accumulate = 1;
@@ -587,6 +627,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           }
         }
       }
+    }
     }
   } else if (!HN_DBG(32)) {     // (experiment bit 5: no epilogue role at all -- the MMA warp does not wait for it)
     // ===================================== epilogue ==========================================
@@ -638,6 +679,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       const uint32_t acc_phase = (it >> C::NBUF_LOG) & 1;
       int mt = st, nt = 0;
       if (n_tiles > 1) { mt = st / n_tiles; nt = st - mt * n_tiles; }
+      if constexpr (PAIR) mt = mt * 2 + cta_rank;
       const int n0 = nt * BN;
       // geometry of the tile's segment
       int g_rows = p.rows, g_hp = p.hp, g_wp = p.wp, g_nimg = p.n_img, g_tile0 = 0, g_gn_off = 0;
@@ -981,7 +1023,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       if (!split) {
         hn_tc_fence_before();
         __syncwarp();
-        if (lane < (alt ? 2 : 1)) hn_mbar_arrive(&tmem_empty[buf]);
+        if constexpr (PAIR) {
+          if (lane == 0) hn_mbar_arrive_leader(&tmem_empty[buf]);     // the leader's MMA warp waits for both CTAs' drains
+        } else {
+          if (lane < (alt ? 2 : 1)) hn_mbar_arrive(&tmem_empty[buf]);
+        }
       }
       if (warp == 2) hn_trace(trace, 2, tri, 3);
     }
@@ -1007,9 +1053,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   // ---- teardown ----
   hn_tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) hn_cluster_sync();       // no CTA may retire (or free its TMEM) while its peer can still signal / use it
   if ((threadIdx.x >> 5) == 1) {
     hn_tc_fence_after();
-    hn_tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    if constexpr (PAIR) hn_tmem_dealloc_pair<C::TMEM_COLS>(tmem_base);
+    else hn_tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -1063,21 +1111,23 @@ bool pdl_enabled() {
 int g_cta_cap = 0;      // hn_conv_set_cta_cap: upper bound on the CTAs of the following launches (0 = all SMs)
 int g_pdl_off = 0;      // hn_conv_set_pdl(0): the following launches do not use programmatic dependent launch
 
-template <int BN, int PIPE, bool FAST, bool SEG>
+template <int BN, int PIPE, bool FAST, bool SEG, bool PAIR = false>
 int launch(const CUtensorMap* ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t st) {
   constexpr int SMEM = SMEM_BYTES_ALL;
   static bool attr_set = false;
   if (!attr_set) {
-    HN_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, PIPE, FAST, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HN_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, PIPE, FAST, SEG, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        SMEM));
     attr_set = true;
   }
-  const int items = p.m_tiles * p.n_tiles * p.splits;
+  // CTA pairs: a work item is a pair of M tiles and occupies a cluster of two CTAs (two SMs of one TPC)
+  const int items = PAIR ? ((p.m_tiles + 1) / 2) * p.n_tiles : p.m_tiles * p.n_tiles * p.splits;
   // equal work per CTA: with w = ceil(tiles / SMs) waves, ceil(tiles / w) CTAs finish at the same time as a full grid
   // would and leave the other SMs to kernels of concurrent streams (graph branches, the pose net of the previous step)
-  const int sms = (g_cta_cap > 0 && g_cta_cap < hn_num_sms()) ? g_cta_cap : hn_num_sms();
+  int sms = (g_cta_cap > 0 && g_cta_cap < hn_num_sms()) ? g_cta_cap : hn_num_sms();
+  if (PAIR) sms /= 2;
   const int waves = hn_div_up(items, sms);
-  const int ctas = hn_div_up(items, waves);
+  const int ctas = hn_div_up(items, waves) * (PAIR ? 2 : 1);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(ctas);
@@ -1086,8 +1136,15 @@ int launch(const CUtensorMap* ta, const CUtensorMap& tb, const ConvParams& p, cu
   // free, enough for blocks of the memory-bound GroupNorm kernel of the OTHER tower to run on the same SMs underneath
   cfg.dynamicSmemBytes = 1024 + HDR_PAD + p.pipe_bytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   int na = 0;
+  if (PAIR) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   if (pdl_enabled() && !g_pdl_off) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
@@ -1095,7 +1152,7 @@ int launch(const CUtensorMap* ta, const CUtensorMap& tb, const ConvParams& p, cu
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, PIPE, FAST, SEG>, ta[0], ta[1], ta[2], tb, p));
+  HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, PIPE, FAST, SEG, PAIR>, ta[0], ta[1], ta[2], tb, p));
   hn_count_launch();
   return HN_OK;
 }
@@ -1162,7 +1219,17 @@ struct BuiltConv {
   CUtensorMap ta, tb;
   int bn;
   bool rb;
+  bool pair;      // CTA pairs (tcgen05 cta_group::2): 256-wide FAST layers
 };
+
+bool pair_enabled() {           // HN_CONV_PAIR=0 switches the CTA-pair kernels off (A/B timing)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HN_CONV_PAIR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 // Validate a descriptor and derive kernel parameters + tensor maps.  total_m_tiles > 0: the descriptor is one segment of
 // a multi-segment launch -- tile width and pipeline are chosen for the launch's total number of M tiles, force_bn pins the
@@ -1411,6 +1478,18 @@ int build_conv(const hn_conv_desc* d, int force_bn, int total_m_tiles, BuiltConv
   }
   p.epi_alt = (p.n_tiles == 1 && p.splits == 1 && !(d->debug & 32768) &&
                ((d->debug & 65536) || bn <= epi_alt_max_bn())) ? 1 : 0;
+  // CTA pairs for the 256-wide layers that take the FAST epilogue: every CTA then holds half of each weight tile, so the
+  // B ring is twice as deep in the same shared memory
+  const bool fast = p.out_kind == 0 && p.vec32 != 0 && (p.cout % 32) == 0 && p.cout_pad == p.cout && p.splits == 1 &&
+                    !(p.dbg_flags & 64);
+  const bool pair = pair_enabled() && bn == 256 && !rb && !uni && fast && !(d->debug & 131072) &&
+                    (total_m_tiles > 0 ? total_m_tiles : p.m_tiles) >= 2;
+  if (pair) {
+    const int nb = (PIPE_BYTES_MAX - p.na_stages * A_SLOT_BYTES) / ((bn / 2) * BLOCK_K * 2);
+    p.nb_stages = nb > MAX_STAGES ? MAX_STAGES : nb;
+    p.pipe_bytes = p.na_stages * A_SLOT_BYTES + p.nb_stages * (bn / 2) * BLOCK_K * 2;
+  }
+  out->pair = pair;
   CUtensorMap& ta = out->ta;
   CUtensorMap& tb = out->tb;
   if (stem) {
@@ -1476,7 +1555,7 @@ int build_conv(const hn_conv_desc* d, int force_bn, int total_m_tiles, BuiltConv
     // [k_block][cout_pad][64] bf16: a 2-D matrix of 128-byte rows, row = k_block * cout_pad + n
     const cuuint64_t dims[2] = {(cuuint64_t)BLOCK_K, (cuuint64_t)k_blocks_total * d->cout_pad};
     const cuuint64_t strides[1] = {(cuuint64_t)BLOCK_K * 2};
-    const cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)bn};
+    const cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)(pair ? bn / 2 : bn)};    // pairs: each CTA fetches half of the tile
     int rc = make_map(&tb, d->weight, 2, dims, strides, box);
     if (rc) return rc;
   }
@@ -1501,6 +1580,7 @@ int dispatch(const BuiltConv& b, const CUtensorMap* ta, cudaStream_t st) {
   const bool fast = epi_fast_ok(p);
   if constexpr (SEG) {
     // segment launches: the 256-wide tower layers (FAST) and the 16-wide output convolutions (fp32 rows)
+    if (b.bn == 256 && fast && b.pair) return launch<256, PIPE_RING, true, true, true>(ta, tb, p, st);
     if (b.bn == 256 && fast) return launch<256, PIPE_RING, true, true>(ta, tb, p, st);
     if (b.bn == 16 && b.rb && !fast) return launch<16, PIPE_RB, false, true>(ta, tb, p, st);
     hn_set_error("hn_conv2d_bf16_levels: unsupported combination (block_n=%d resident=%d fast=%d); supported: 256-wide bf16 "
@@ -1515,7 +1595,9 @@ int dispatch(const BuiltConv& b, const CUtensorMap* ta, cudaStream_t st) {
       }
     }
     switch (b.bn) {
-      case 256: return fast ? launch<256, PIPE_RING, true, false>(ta, tb, p, st) : launch<256, PIPE_RING, false, false>(ta, tb, p, st);
+      case 256:
+        if (fast && b.pair) return launch<256, PIPE_RING, true, false, true>(ta, tb, p, st);
+        return fast ? launch<256, PIPE_RING, true, false>(ta, tb, p, st) : launch<256, PIPE_RING, false, false>(ta, tb, p, st);
       case 128: return fast ? launch<128, PIPE_UNI, true, false>(ta, tb, p, st) : launch<128, PIPE_UNI, false, false>(ta, tb, p, st);
       case 64: return fast ? launch<64, PIPE_UNI, true, false>(ta, tb, p, st) : launch<64, PIPE_UNI, false, false>(ta, tb, p, st);
       case 32: return fast ? launch<32, PIPE_UNI, true, false>(ta, tb, p, st) : launch<32, PIPE_UNI, false, false>(ta, tb, p, st);
@@ -1581,7 +1663,7 @@ extern "C" int hn_conv2d_bf16_levels(const hn_conv_desc* descs, int n_levels, vo
     if (i > 0) {
       rc = build_conv(&descs[i], b0.bn, total_tiles, &bi);
       if (rc) return rc;
-      HN_REQUIRE(bi.bn == b0.bn && bi.rb == b0.rb && bi.p.rb3 == p.rb3 && bi.p.n_groups == p.n_groups &&
+      HN_REQUIRE(bi.bn == b0.bn && bi.rb == b0.rb && bi.pair == b0.pair && bi.p.rb3 == p.rb3 && bi.p.n_groups == p.n_groups &&
                      bi.p.na_stages == p.na_stages && bi.p.a_box_bytes == p.a_box_bytes && bi.p.epi_alt == p.epi_alt &&
                      bi.p.vec32 == p.vec32,
                  "hn_conv2d_bf16_levels: level %d needs a different kernel configuration than level 0", i);
