@@ -482,7 +482,8 @@ def run_post_stress(ctx: Ctx, net):
     peaks = load_peaks()
     lv = ops.Levels([(100, 136), (50, 68), (25, 34)], (800, 1088), (8, 16, 32))
     B = FRAMES_PER_GPU
-    ho = {k: v.to(dev) for k, v in synth.stress_head_tensors(31, B, lv.locs, 3, -0.35).items()}
+    # channel planes [B][channel][locs], the layout the detector's output convolutions write
+    ho = {k: v.to(dev).permute(0, 2, 1).contiguous().permute(0, 2, 1) for k, v in synth.stress_head_tensors(31, B, lv.locs, 3, -0.35).items()}
     m = net.detector
     ws_sel = torch.empty(int(ops._lib.load().hn_fcos_select_workspace_bytes(B, lv.locs)), dtype=torch.uint8, device=dev)
     ws_nms = ops.nms_workspace(B, lv.locs, dev)
@@ -500,6 +501,7 @@ def run_post_stress(ctx: Ctx, net):
         ts = []
         for _ in range(reps):
             ctx.l2_flush.zero_()
+            torch.cuda._sleep(3_000_000)       # the host enqueues the launches while the GPU spins: no launch gaps are timed
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()

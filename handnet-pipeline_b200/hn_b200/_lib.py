@@ -60,12 +60,12 @@ SIGNATURES = {
     "hn_maxpool3x3s2": (_i, [_c_p, _i, _i, _i, _i, _c_p, _i, _c_p]),
     "hn_groupnorm_relu": (_i, [_c_p, _i, _i, _i, _i, _i, _c_p, _i, _c_p, _c_p, _f, _c_p]),
     "hn_fcos_select_workspace_bytes": (_i64, [_i, _i]),
-    "hn_fcos_decode_select": (_i, [_c_p, _i, _c_p, _i, _c_p, _i, _i, _i, _i, _i, _ip, _ip, _ip, _ip, _ip, _d,
+    "hn_fcos_decode_select": (_i, [_c_p, _i64, _i, _i, _c_p, _i64, _i, _c_p, _i64, _i, _i, _i, _i, _i, _i, _ip, _ip, _ip, _ip, _ip, _d,
                                     _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _i64, _c_p]),
     "hn_nms_workspace_bytes": (_i64, [_i, _i]),
     "hn_nms_batched": (_i, [_c_p, _c_p, _c_p, _c_p, _i, _i, _d, _i, _c_p, _c_p, _c_p, _i64, _c_p]),
-    "hn_fcos_gather": (_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _i, _c_p, _i, _c_p, _i, _i, _i, _i, _i, _ip,
-                            _fp, _fp,
+    "hn_fcos_gather": (_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _i64, _i, _i, _c_p, _i64, _i, _i, _c_p, _i64, _i, _i,
+                            _i, _i, _i, _i, _ip, _fp, _fp,
                             _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),
     "hn_select_crop_resize": (_i, [_c_p, _c_p, _c_p, _i, _i, _i, _c_p, _i, _i, _i, _i, _c_p, _c_p, _c_p, _c_p]),
     "hn_a2j_workspace_bytes": (_i64, [_i, _i]),

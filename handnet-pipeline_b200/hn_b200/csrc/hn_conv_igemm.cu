@@ -720,6 +720,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       if (interior) {
         if (FAST || p.out_kind == 0) {
           out_off = ((long long)(img * g_out_hp + h + p.out_halo) * g_out_wp + (w + p.out_halo)) * p.cout;
+        } else if (p.out_kind == 2) {
+          // channel-planar fp32 [image][out_ld planes][out_rows_per_image]: channel c of this pixel at out_off + c * rows
+          out_off = (long long)img * p.out_ld * p.out_rows_per_image + g_out_row_offset + (h * W + w);
         } else {
           const int pix = p.out_transpose_hw ? (w * H + h) : (h * W + w);
           out_off = ((long long)img * p.out_rows_per_image + g_out_row_offset + pix) * p.out_ld;
@@ -911,6 +914,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 #pragma unroll
               for (int j = 0; j < CHUNK; ++j)
                 if (cbase + j < p.cout) op[j] = v[j];
+            }
+            return;
+          }
+          if (p.out_kind == 2) {
+            // consecutive lanes = consecutive pixels: every channel's store of a warp is one contiguous run
+            if (interior) {
+              float* op = reinterpret_cast<float*>(g_out) + out_off + (long long)cbase * p.out_rows_per_image;
+#pragma unroll
+              for (int j = 0; j < CHUNK; ++j)
+                if (cbase + j < p.cout) op[(long long)j * p.out_rows_per_image] = v[j];
             }
             return;
           }
@@ -1418,7 +1431,11 @@ int build_conv(const hn_conv_desc* d, int force_bn, int total_m_tiles, BuiltConv
   p.out_row_offset = d->out_row_offset;
   p.out_ld = d->out_ld;
   p.out_transpose_hw = d->out_transpose_hw;
+  HN_REQUIRE(d->out_kind >= 0 && d->out_kind <= 2, "hn_conv2d_bf16: out_kind %d", d->out_kind);
   if (d->out_kind == 1) HN_REQUIRE(d->out_ld >= d->cout, "hn_conv2d_bf16: out_ld < cout");
+  if (d->out_kind == 2)
+    HN_REQUIRE(d->out_ld >= d->cout && d->out_rows_per_image >= d->out_row_offset + d->h * d->w && !d->out_transpose_hw,
+               "hn_conv2d_bf16: planar output needs out_ld (planes per image) >= cout and rows_per_image >= offset + h*w");
   p.out_phase = reinterpret_cast<__nv_bfloat16*>(d->out_phase);
   if (p.out_phase) {
     HN_REQUIRE(d->out_kind == 0, "hn_conv2d_bf16: phase-split copy only for bf16 outputs");

@@ -5,6 +5,8 @@
 // Integer/fp32 work on tiny data: coalesced vector loads, warp ballots/matches, no tensor cores.
 #include "hn_common.cuh"
 
+#include <math.h>
+
 namespace {
 
 // x > (double)t for a float x  <=>  x >= smallest float whose value exceeds t.  This is how a python-float
@@ -28,70 +30,164 @@ constexpr int SEL_BLOCK = 256;
 
 __device__ __forceinline__ float sigmoid_rn(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
 
-// score = max_c sqrt(sigmoid(cls_c) * sigmoid(ctr)), label = first arg max (fcos_utils/fcos.py:598-599)
-__device__ __forceinline__ void score_label(const float* __restrict__ cls, float ctr, int nc, float& best, int& label) {
+// A head tensor [batch][locs][channels] of any layout: element (b, loc, c) at p[b * img + loc * loc_stride + c * chan_stride].
+// The detector writes its heads channel-PLANAR ([batch][channel][locs]: loc_stride 1, chan_stride locs), so that a warp's
+// loads of one channel are one contiguous 128-byte run and no padding bytes travel; row layouts work as well.
+struct HeadView {
+  const float* p;
+  long long img;
+  int loc, chan;
+};
+
+// score = max_c sqrt(sigmoid(cls_c) * sigmoid(ctr)), label = first arg max (fcos_utils/fcos.py:598-599), on logits already
+// in registers.  Every rounding of the chain (IEEE division, multiply, square root) is monotone and CUDA's expf is within
+// 2 ulp, so the class with the largest LOGIT has the largest score; an EARLIER class can only tie with it if its logit is
+// within a hair of the largest one (or both sit in the saturated tail, where sigmoid rounds to 1.0).  So: one exact score
+// for the arg-max logit, and exact scores only for classes whose logit is inside that neighbourhood -- for typical heads one
+// sigmoid chain per location instead of one per class, with the reference's first-max label semantics kept bit for bit.
+template <int NC_MAX>
+__device__ __forceinline__ void score_label_regs(const float (&lg)[NC_MAX], int nc, float ctr, float& best, int& label) {
   const float sc = sigmoid_rn(ctr);
-  best = -1.f;
-  label = 0;
-  for (int c = 0; c < nc; ++c) {
-    const float s = __fsqrt_rn(__fmul_rn(sigmoid_rn(__ldg(cls + c)), sc));
-    if (c == 0 || s > best) { best = s; label = c; }
+  int cm = 0;
+  float mx = lg[0];
+#pragma unroll
+  for (int c = 1; c < NC_MAX; ++c)
+    if (c < nc && lg[c] > mx) { mx = lg[c]; cm = c; }
+  best = __fsqrt_rn(__fmul_rn(sigmoid_rn(mx), sc));
+  label = cm;
+  // neighbourhood in which another class's score may round to the same float: tiny below 4, a full unit up to 15 (the
+  // sigmoid's slope there is ~1e-6 per ulp of its value), everything beyond (saturation)
+  const float margin = mx <= 4.f ? 1e-4f * (1.f + fabsf(mx)) : (mx <= 15.f ? 1.f : INFINITY);
+#pragma unroll
+  for (int c = NC_MAX - 1; c >= 0; --c) {              // descending: the FIRST class among equal scores wins
+    if (c < nc && c != cm && lg[c] >= mx - margin) {
+      const float s = __fsqrt_rn(__fmul_rn(sigmoid_rn(lg[c]), sc));
+      if (s > best || (s == best && c < label)) { best = s; label = c; }
+    }
   }
 }
 
-// pass 1: dense score / label and the number of survivors per 256-location chunk
-__global__ void __launch_bounds__(SEL_BLOCK)
-select_score_kernel(const float* __restrict__ cls, int cls_ld, const float* __restrict__ ctr, int ctr_ld, int locs,
-                    int nc, float thresh_ge,
-                    float* __restrict__ dense_score, int* __restrict__ dense_label, int* __restrict__ chunk_count) {
-  const int b = blockIdx.y;
-  const int loc = blockIdx.x * SEL_BLOCK + threadIdx.x;
-  bool pass = false;
-  if (loc < locs) {
-    float s;
-    int l;
-    score_label(cls + ((size_t)b * locs + loc) * cls_ld, __ldg(ctr + ((size_t)b * locs + loc) * ctr_ld), nc, s, l);
-    dense_score[(size_t)b * locs + loc] = s;
-    dense_label[(size_t)b * locs + loc] = l;
-    pass = s >= thresh_ge;
-  }
-  const int cnt = __syncthreads_count(pass);
-  if (threadIdx.x == 0) chunk_count[b * gridDim.x + blockIdx.x] = cnt;
-}
+// pass 1: score / label of every location that CAN pass, survivors compacted inside their chunk of SEL_CHUNK locations (in
+// location order) into the scratch, and the number of survivors per chunk.  A location whose centre-ness logit or whose
+// largest class logit is below `skip_below` cannot reach the threshold (sqrt(sigmoid(c) * sigmoid(t)) <= sqrt(sigmoid(min(c,
+// t)))), so the sigmoids and square roots are evaluated only where the outcome is open: in the sparse regime a detector
+// normally runs in, the pass is a pure stream over the cls / ctr planes.  A thread takes SEL_PER consecutive locations (one
+// 16-byte load per plane when the heads are channel planes).
+constexpr int SEL_PER = 4;
+constexpr int SEL_CHUNK = SEL_BLOCK * SEL_PER;
+constexpr int SEL_NC_MAX = 8;
+struct SelScratch {
+  float* score;      // [batch][locs]: chunk k's survivors at [k * SEL_CHUNK ...)
+  int* label;
+  int* loc;
+  int* chunk_count;  // [batch][chunks]
+};
 
-// pass 2: ordered compaction; boxes are decoded for survivors only (det_utils.py:266-294)
 __global__ void __launch_bounds__(SEL_BLOCK)
-select_compact_kernel(const float* __restrict__ reg, int reg_ld, const float* __restrict__ dense_score,
-                      const int* __restrict__ dense_label, const int* __restrict__ chunk_count, int locs, float thresh_ge,
-                      const Levels lv, int* __restrict__ cand_count, int* __restrict__ cand_loc,
-                      float* __restrict__ cand_score, int* __restrict__ cand_label, float4* __restrict__ cand_box) {
+select_score_kernel(const HeadView cls, const HeadView ctr, int locs, int nc, float thresh_ge, float skip_below, SelScratch ws) {
   __shared__ int warp_sums[SEL_BLOCK / 32];
+  const int b = blockIdx.y;
+  const int loc0 = (blockIdx.x * SEL_BLOCK + threadIdx.x) * SEL_PER;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float lg[SEL_PER][SEL_NC_MAX], tt[SEL_PER];
+  const float* cbase = cls.p + (size_t)b * cls.img;
+  const float* tbase = ctr.p + (size_t)b * ctr.img;
+  const bool vec = cls.loc == 1 && ctr.loc == 1 && loc0 + SEL_PER <= locs &&
+                   ((reinterpret_cast<uintptr_t>(cbase + loc0) | reinterpret_cast<uintptr_t>(tbase + loc0) |
+                     ((size_t)cls.chan * 4)) & 15) == 0;
+  if (vec) {
+    const float4 t4 = __ldg(reinterpret_cast<const float4*>(tbase + loc0));
+    tt[0] = t4.x; tt[1] = t4.y; tt[2] = t4.z; tt[3] = t4.w;
+#pragma unroll
+    for (int c = 0; c < SEL_NC_MAX; ++c) {
+      if (c < nc) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(cbase + (size_t)c * cls.chan + loc0));
+        lg[0][c] = v.x; lg[1][c] = v.y; lg[2][c] = v.z; lg[3][c] = v.w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < SEL_PER; ++i) {
+      const int loc = loc0 + i;
+      tt[i] = loc < locs ? __ldg(tbase + (size_t)loc * ctr.loc) : -INFINITY;
+#pragma unroll
+      for (int c = 0; c < SEL_NC_MAX; ++c)
+        if (c < nc) lg[i][c] = loc < locs ? __ldg(cbase + (size_t)loc * cls.loc + (size_t)c * cls.chan) : -INFINITY;
+    }
+  }
+  float s[SEL_PER];
+  int l[SEL_PER];
+  int mine = 0;
+  unsigned pmask = 0;
+#pragma unroll
+  for (int i = 0; i < SEL_PER; ++i) {
+    float mx = lg[i][0];
+#pragma unroll
+    for (int c = 1; c < SEL_NC_MAX; ++c)
+      if (c < nc) mx = fmaxf(mx, lg[i][c]);
+    s[i] = 0.f;
+    l[i] = 0;
+    if (loc0 + i < locs && tt[i] >= skip_below && mx >= skip_below) {
+      score_label_regs<SEL_NC_MAX>(lg[i], nc, tt[i], s[i], l[i]);
+      if (s[i] >= thresh_ge) { pmask |= 1u << i; ++mine; }
+    }
+  }
+  // exclusive prefix of `mine` over the block (location order = thread order)
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  int before = 0, total = 0;
+#pragma unroll
+  for (int i = 0; i < SEL_BLOCK / 32; ++i) {
+    const int c = warp_sums[i];
+    if (i < warp) before += c;
+    total += c;
+  }
+  if (mine) {
+    size_t o = (size_t)b * locs + (size_t)blockIdx.x * SEL_CHUNK + before + (incl - mine);
+#pragma unroll
+    for (int i = 0; i < SEL_PER; ++i) {
+      if (pmask & (1u << i)) {
+        ws.score[o] = s[i];
+        ws.label[o] = l[i];
+        ws.loc[o] = loc0 + i;
+        ++o;
+      }
+    }
+  }
+  if (threadIdx.x == 0) ws.chunk_count[b * gridDim.x + blockIdx.x] = total;
+}
+
+// pass 2: chunk k's survivors move to their place in the image's candidate list (offset = survivors of the chunks before it)
+// and get their boxes decoded (det_utils.py:266-294).  Chunks without survivors leave at once.
+__global__ void __launch_bounds__(SEL_BLOCK)
+select_compact_kernel(const HeadView reg, SelScratch ws, int locs, const Levels lv, int* __restrict__ cand_count,
+                      int* __restrict__ cand_loc, float* __restrict__ cand_score, int* __restrict__ cand_label,
+                      float4* __restrict__ cand_box) {
   __shared__ int base_s;
   const int b = blockIdx.y;
   const int chunks = gridDim.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int mine = ws.chunk_count[b * chunks + blockIdx.x];
+  const bool last_chunk = blockIdx.x == chunks - 1;
+  if (mine == 0 && !last_chunk) return;
   // offset of this chunk = sum of the counts of the chunks before it
   if (warp == 0) {
     int acc = 0;
-    for (int i = lane; i < blockIdx.x; i += 32) acc += chunk_count[b * chunks + i];
+    for (int i = lane; i < blockIdx.x; i += 32) acc += ws.chunk_count[b * chunks + i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) base_s = acc;
   }
-  const int loc = blockIdx.x * SEL_BLOCK + threadIdx.x;
-  float s = 0.f;
-  bool pass = false;
-  if (loc < locs) {
-    s = dense_score[(size_t)b * locs + loc];
-    pass = s >= thresh_ge;
-  }
-  const unsigned bal = __ballot_sync(0xffffffffu, pass);
-  if (lane == 0) warp_sums[warp] = __popc(bal);
   __syncthreads();
-  int before = 0;
-  for (int i = 0; i < warp; ++i) before += warp_sums[i];
-  const int rank = base_s + before + __popc(bal & ((1u << lane) - 1u));
-  if (pass) {
+  for (int q = threadIdx.x; q < mine; q += SEL_BLOCK) {
+    const size_t src = (size_t)b * locs + (size_t)blockIdx.x * SEL_CHUNK + q;
+    const int loc = ws.loc[src];
     int l = 0;
     while (l + 1 < lv.n && loc >= lv.start[l + 1]) ++l;
     const int cell = loc - lv.start[l];
@@ -102,22 +198,21 @@ select_compact_kernel(const float* __restrict__ reg, int reg_ld, const float* __
     const float a2 = (float)(x * lv.sw[l]) + half, a3 = (float)(y * lv.sh[l]) + half;
     const float cx = __fmul_rn(0.5f, __fadd_rn(a0, a2)), cy = __fmul_rn(0.5f, __fadd_rn(a1, a3));
     const float bw = __fsub_rn(a2, a0), bh = __fsub_rn(a3, a1);
-    const float4 r = __ldg(reinterpret_cast<const float4*>(reg + ((size_t)b * locs + loc) * reg_ld));
+    const float* rp = reg.p + (size_t)b * reg.img + (size_t)loc * reg.loc;
+    const float r0 = __ldg(rp), r1 = __ldg(rp + (size_t)reg.chan), r2 = __ldg(rp + 2 * (size_t)reg.chan),
+                r3 = __ldg(rp + 3 * (size_t)reg.chan);
     float4 box;
-    box.x = __fsub_rn(cx, __fmul_rn(r.x, bw));
-    box.y = __fsub_rn(cy, __fmul_rn(r.y, bh));
-    box.z = __fadd_rn(cx, __fmul_rn(r.z, bw));
-    box.w = __fadd_rn(cy, __fmul_rn(r.w, bh));
-    const size_t o = (size_t)b * locs + rank;
+    box.x = __fsub_rn(cx, __fmul_rn(r0, bw));
+    box.y = __fsub_rn(cy, __fmul_rn(r1, bh));
+    box.z = __fadd_rn(cx, __fmul_rn(r2, bw));
+    box.w = __fadd_rn(cy, __fmul_rn(r3, bh));
+    const size_t o = (size_t)b * locs + base_s + q;
     cand_loc[o] = loc;
-    cand_score[o] = s;
-    cand_label[o] = dense_label[(size_t)b * locs + loc];
+    cand_score[o] = ws.score[src];
+    cand_label[o] = ws.label[src];
     cand_box[o] = box;
   }
-  if (blockIdx.x == chunks - 1 && threadIdx.x == SEL_BLOCK - 1) {
-    // last thread of the last chunk knows the total
-    cand_count[b] = base_s + before + __popc(bal);
-  }
+  if (last_chunk && threadIdx.x == 0) cand_count[b] = base_s + mine;     // the last chunk knows the total
 }
 
 // ------------------------------------------------------------------------------------- NMS
@@ -493,8 +588,7 @@ struct Ratios {
 __global__ void __launch_bounds__(256)
 gather_kernel(const int* __restrict__ keep, const int* __restrict__ keep_count, const int* __restrict__ cand_loc,
               const float* __restrict__ cand_score, const int* __restrict__ cand_label,
-              const float4* __restrict__ cand_box, const float* __restrict__ hand_lr, int lr_ld,
-              const float* __restrict__ contact_logits, int contact_ld, const float* __restrict__ dxdy, int dxdy_ld,
+              const float4* __restrict__ cand_box, const HeadView hand_lr, const HeadView contact_logits, const HeadView dxdy,
               int cap, int locs,
               int batch_offset, GatherParams gp, Ratios rt, float4* __restrict__ boxes, float* __restrict__ scores,
               long long* __restrict__ labels, long long* __restrict__ sides, float* __restrict__ level,
@@ -513,26 +607,26 @@ gather_kernel(const int* __restrict__ keep, const int* __restrict__ keep_count, 
   boxes[off + k] = bx;
   scores[off + k] = cand_score[off + ci];
   labels[off + k] = cand_label[off + ci];
-  const float* lr = hand_lr + ((size_t)b * locs + loc) * lr_ld;
-  sides[off + k] = (sigmoid_rn(__ldg(lr + 1)) > sigmoid_rn(__ldg(lr))) ? 1 : 0;
+  const float* lr = hand_lr.p + (size_t)b * hand_lr.img + (size_t)loc * hand_lr.loc;
+  sides[off + k] = (sigmoid_rn(__ldg(lr + hand_lr.chan)) > sigmoid_rn(__ldg(lr))) ? 1 : 0;
   int l = 0;
   while (l + 1 < gp.num_levels && loc >= gp.level_start[l + 1]) ++l;
   level[off + k] = (float)l;
   if (contacts) {
-    const float* cl = contact_logits + ((size_t)b * locs + loc) * contact_ld;
+    const float* cl = contact_logits.p + (size_t)b * contact_logits.img + (size_t)loc * contact_logits.loc;
     float best = sigmoid_rn(__ldg(cl));
     int bi = 0;
     for (int c = 1; c < 5; ++c) {
-      const float s = sigmoid_rn(__ldg(cl + c));
+      const float s = sigmoid_rn(__ldg(cl + (size_t)c * contact_logits.chan));
       if (s > best) { best = s; bi = c; }
     }
     contacts[off + k] = bi;
   }
   if (dxdymags) {
     // (d0, 0.1 * normalize((d1, d2), p=2, eps=1e-12))   fcos_utils/fcos.py:299-303
-    const float* dp = dxdy + ((size_t)b * locs + loc) * dxdy_ld;
+    const float* dp = dxdy.p + (size_t)b * dxdy.img + (size_t)loc * dxdy.loc;
     float* o = dxdymags + (off + k) * 3;
-    const float d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
+    const float d1 = __ldg(dp + dxdy.chan), d2 = __ldg(dp + 2 * (size_t)dxdy.chan);
     const float nrm = fmaxf(__fsqrt_rn(__fadd_rn(__fmul_rn(d1, d1), __fmul_rn(d2, d2))), 1e-12f);
     o[0] = __ldg(dp);
     o[1] = __fmul_rn(0.1f, __fdiv_rn(d1, nrm));
@@ -544,22 +638,24 @@ gather_kernel(const int* __restrict__ keep, const int* __restrict__ keep_count, 
 
 extern "C" int64_t hn_fcos_select_workspace_bytes(int batch, int locs) {
   const size_t n = (size_t)batch * locs;
-  return (int64_t)(align256(n * 4) * 2 + align256((size_t)batch * hn_div_up(locs, SEL_BLOCK) * 4));
+  return (int64_t)(align256(n * 4) * 3 + align256((size_t)batch * hn_div_up(locs, SEL_CHUNK) * 4));
 }
 
-extern "C" int hn_fcos_decode_select(const float* cls_logits, int cls_ld, const float* bbox_ctrness, int ctr_ld,
-                                     const float* bbox_regression, int reg_ld, int batch, int locs, int num_classes, int num_levels, const int* level_h_host,
-                                     const int* level_w_host, const int* level_stride_h_host,
+extern "C" int hn_fcos_decode_select(const float* cls_logits, int64_t cls_img_stride, int cls_loc_stride, int cls_chan_stride,
+                                     const float* bbox_ctrness, int64_t ctr_img_stride, int ctr_loc_stride,
+                                     const float* bbox_regression, int64_t reg_img_stride, int reg_loc_stride,
+                                     int reg_chan_stride, int batch, int locs, int num_classes, int num_levels,
+                                     const int* level_h_host, const int* level_w_host, const int* level_stride_h_host,
                                      const int* level_stride_w_host, const int* level_anchor_host, double score_thresh,
                                      int* cand_count, int* cand_loc, float* cand_score, int* cand_label,
                                      float* cand_box, void* workspace, int64_t workspace_bytes, void* stream) {
   HN_REQUIRE(cls_logits && bbox_ctrness && bbox_regression && cand_count && cand_loc && cand_score && cand_label &&
                  cand_box && workspace, "hn_fcos_decode_select: null pointer");
-  HN_REQUIRE(batch > 0 && locs > 0 && num_classes > 0 && num_levels > 0 && num_levels <= MAX_LEVELS,
-             "hn_fcos_decode_select: bad sizes");
-  HN_REQUIRE(cls_ld >= num_classes && ctr_ld >= 1 && reg_ld >= 4 && reg_ld % 4 == 0 &&
-                 (reinterpret_cast<uintptr_t>(bbox_regression) & 15) == 0,
-             "hn_fcos_decode_select: row strides (reg rows must be 16-byte aligned)");
+  HN_REQUIRE(batch > 0 && locs > 0 && num_classes > 0 && num_classes <= SEL_NC_MAX && num_levels > 0 && num_levels <= MAX_LEVELS,
+             "hn_fcos_decode_select: bad sizes (at most %d classes)", SEL_NC_MAX);
+  HN_REQUIRE(cls_loc_stride >= 1 && cls_chan_stride >= 1 && ctr_loc_stride >= 1 && reg_loc_stride >= 1 && reg_chan_stride >= 1 &&
+                 (reinterpret_cast<uintptr_t>(cand_box) & 15) == 0,
+             "hn_fcos_decode_select: strides must be positive and cand_box 16-byte aligned");
   HN_REQUIRE(workspace_bytes >= hn_fcos_select_workspace_bytes(batch, locs), "hn_fcos_decode_select: workspace too small");
   Levels lv;
   memset(&lv, 0, sizeof(lv));
@@ -578,18 +674,28 @@ extern "C" int hn_fcos_decode_select(const float* cls_logits, int cls_ld, const 
   HN_REQUIRE(acc == locs, "hn_fcos_decode_select: levels cover %d locations, locs=%d", acc, locs);
   const size_t n = (size_t)batch * locs;
   uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
-  float* dense_score = reinterpret_cast<float*>(w);
-  int* dense_label = reinterpret_cast<int*>(w + align256(n * 4));
-  int* chunk_count = reinterpret_cast<int*>(w + 2 * align256(n * 4));
+  SelScratch ws;
+  ws.score = reinterpret_cast<float*>(w);
+  ws.label = reinterpret_cast<int*>(w + align256(n * 4));
+  ws.loc = reinterpret_cast<int*>(w + 2 * align256(n * 4));
+  ws.chunk_count = reinterpret_cast<int*>(w + 3 * align256(n * 4));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  dim3 grid(hn_div_up(locs, SEL_BLOCK), batch);
+  dim3 grid(hn_div_up(locs, SEL_CHUNK), batch);
   const float thresh_ge = float_gt_as_ge(score_thresh);
-  select_score_kernel<<<grid, SEL_BLOCK, 0, st>>>(cls_logits, cls_ld, bbox_ctrness, ctr_ld, locs, num_classes, thresh_ge,
-                                                  dense_score, dense_label, chunk_count);
+  // score >= t needs sigmoid(cls) * sigmoid(ctr) >= t^2, hence each logit >= logit(t^2); 0.01 of margin covers the rounding
+  // of the fp32 evaluation many times over (at t = 0.7: skip below -0.05, where the score can reach 0.698 at most)
+  float skip_below = -INFINITY;
+  if (score_thresh > 0.0 && score_thresh < 1.0) {
+    const double t2 = score_thresh * score_thresh;
+    skip_below = (float)(log(t2 / (1.0 - t2)) - 0.01);
+  }
+  const HeadView vcls = {cls_logits, (long long)cls_img_stride, cls_loc_stride, cls_chan_stride};
+  const HeadView vctr = {bbox_ctrness, (long long)ctr_img_stride, ctr_loc_stride, 1};
+  const HeadView vreg = {bbox_regression, (long long)reg_img_stride, reg_loc_stride, reg_chan_stride};
+  select_score_kernel<<<grid, SEL_BLOCK, 0, st>>>(vcls, vctr, locs, num_classes, thresh_ge, skip_below, ws);
   hn_count_launch();
   HN_LAUNCH_CHECK();
-  select_compact_kernel<<<grid, SEL_BLOCK, 0, st>>>(bbox_regression, reg_ld, dense_score, dense_label, chunk_count, locs,
-                                                    thresh_ge, lv, cand_count, cand_loc, cand_score, cand_label,
+  select_compact_kernel<<<grid, SEL_BLOCK, 0, st>>>(vreg, ws, locs, lv, cand_count, cand_loc, cand_score, cand_label,
                                                     reinterpret_cast<float4*>(cand_box));
   hn_count_launch();
   HN_LAUNCH_CHECK();
@@ -633,9 +739,10 @@ extern "C" int hn_nms_batched(const float* cand_box, const float* cand_score, co
 }
 
 extern "C" int hn_fcos_gather(const int* keep, const int* keep_count, const int* cand_loc, const float* cand_score,
-                              const int* cand_label, const float* cand_box, const float* hand_lr, int lr_ld,
-                              const float* contact_logits, int contact_ld, const float* dxdy, int dxdy_ld, int batch,
-                              int cap, int locs,
+                              const int* cand_label, const float* cand_box, const float* hand_lr, int64_t lr_img_stride,
+                              int lr_loc_stride, int lr_chan_stride, const float* contact_logits, int64_t contact_img_stride,
+                              int contact_loc_stride, int contact_chan_stride, const float* dxdy, int64_t dxdy_img_stride,
+                              int dxdy_loc_stride, int dxdy_chan_stride, int batch, int cap, int locs,
                               int num_levels, const int* level_start_host, const float* ratio_h_host,
                               const float* ratio_w_host, float* boxes, float* scores, int64_t* labels, int64_t* sides,
                               float* level, int64_t* contacts, float* dxdymags, void* stream) {
@@ -655,8 +762,11 @@ extern "C" int hn_fcos_gather(const int* keep, const int* keep_count, const int*
     for (int i = 0; i < nb; ++i) { rt.rh[i] = ratio_h_host[b0 + i]; rt.rw[i] = ratio_w_host[b0 + i]; }
     dim3 grid(hn_div_up(cap, 256), nb);
     gather_kernel<<<grid, 256, 0, st>>>(keep, keep_count, cand_loc, cand_score, cand_label,
-                                        reinterpret_cast<const float4*>(cand_box), hand_lr, lr_ld, contact_logits,
-                                        contact_ld, dxdy, dxdy_ld, cap, locs, b0, gp, rt, reinterpret_cast<float4*>(boxes), scores,
+                                        reinterpret_cast<const float4*>(cand_box),
+                                        HeadView{hand_lr, (long long)lr_img_stride, lr_loc_stride, lr_chan_stride},
+                                        HeadView{contact_logits, (long long)contact_img_stride, contact_loc_stride, contact_chan_stride},
+                                        HeadView{dxdy, (long long)dxdy_img_stride, dxdy_loc_stride, dxdy_chan_stride},
+                                        cap, locs, b0, gp, rt, reinterpret_cast<float4*>(boxes), scores,
                                         reinterpret_cast<long long*>(labels), reinterpret_cast<long long*>(sides), level,
                                         reinterpret_cast<long long*>(contacts), dxdymags);
     hn_count_launch();

@@ -300,7 +300,7 @@ def _conv_desc(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 
                scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None, relu=False,
                res: Optional[Act] = None, res_mode: int = 0, out: Optional[Act] = None,
                out_f32: Optional[torch.Tensor] = None, out_rows_per_image: int = 0, out_row_offset: int = 0,
-               out_transpose_hw: bool = False, out_phase: Optional[PhaseAct] = None,
+               out_transpose_hw: bool = False, out_planar: bool = False, out_phase: Optional[PhaseAct] = None,
                gn_stats: Optional[torch.Tensor] = None, gn_groups: int = 0, block_n: int = 0, cluster: int = 0,
                debug: int = 0, splitk=None, splits: int = 0, trace: Optional[torch.Tensor] = None) -> ConvDesc:
     """Fill a struct hn_conv_desc.  x: Act (stride 1), PhaseAct (stride 2) or StemFrame (direct 7x7/2 stem; ksize = 1, the
@@ -331,9 +331,10 @@ def _conv_desc(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 
         assert res.c == cout
     if out_f32 is not None:
         assert out_f32.dtype == torch.float32 and out_f32.is_contiguous()
-        d.out, d.out_kind = out_f32.data_ptr(), 1
+        d.out, d.out_kind = out_f32.data_ptr(), 2 if out_planar else 1
         d.out_rows_per_image = out_rows_per_image or d.h * d.w
-        d.out_row_offset, d.out_ld, d.out_transpose_hw = out_row_offset, out_f32.shape[-1], int(out_transpose_hw)
+        # rows [.., rows, ld] (kind 1) or channel planes [.., planes, rows] (kind 2: ld = planes per image)
+        d.out_row_offset, d.out_ld, d.out_transpose_hw = out_row_offset, out_f32.shape[-2 if out_planar else -1], int(out_transpose_hw)
     else:
         assert out is not None and out.c == cout and (out.n, out.h, out.w) == (d.n, d.h, d.w), "output geometry"
         d.out, d.out_kind, d.out_halo = out.t.data_ptr(), 0, out.halo
@@ -456,9 +457,17 @@ class Levels:
         self.start_arr = (C.c_int * (self.n + 1))(*starts)
 
 
+def _head_strides(t: Optional[torch.Tensor]):
+    """(pointer, image stride, location stride, channel stride) of a head tensor view [B, locs, k] in any layout."""
+    if t is None:
+        return 0, 0, 0, 0
+    assert t.dtype == torch.float32 and t.dim() == 3
+    return t.data_ptr(), t.stride(0), t.stride(1), t.stride(2) if t.shape[2] > 1 else 1
+
+
 def fcos_decode_select(cls: torch.Tensor, ctr: torch.Tensor, reg: torch.Tensor, num_classes: int, levels: Levels,
                        score_thresh: float, ws: Optional[torch.Tensor] = None):
-    """P1-P4.  cls/ctr/reg are fp32 views [B, locs, k] whose last-dim stride is 1 (row stride = stride(1))."""
+    """P1-P4.  cls / ctr / reg are fp32 views [B, locs, k] of any layout (channel planes or rows): strides are passed on."""
     b, locs = cls.shape[0], cls.shape[1]
     assert locs == levels.locs
     dev = cls.device
@@ -472,10 +481,11 @@ def fcos_decode_select(cls: torch.Tensor, ctr: torch.Tensor, reg: torch.Tensor, 
         "label": torch.empty((b, locs), dtype=torch.int32, device=dev),
         "box": torch.empty((b, locs, 4), dtype=torch.float32, device=dev),
     }
-    for t in (cls, ctr, reg):
-        assert t.dtype == torch.float32 and t.stride(-1) == 1 and t.stride(0) == t.stride(1) * locs
+    pc, ic, lc, cc = _head_strides(cls)
+    pt, it, lt, _ = _head_strides(ctr)
+    pr, ir, lr, cr = _head_strides(reg)
     check(_lib.load().hn_fcos_decode_select(
-        cls.data_ptr(), cls.stride(1), ctr.data_ptr(), ctr.stride(1), reg.data_ptr(), reg.stride(1), b, locs,
+        pc, ic, lc, cc, pt, it, lt, pr, ir, lr, cr, b, locs,
         num_classes, levels.n, levels.h, levels.w, levels.sh, levels.sw, levels.anchor, float(score_thresh),
         cand["count"].data_ptr(), cand["loc"].data_ptr(), cand["score"].data_ptr(), cand["label"].data_ptr(),
         cand["box"].data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr()), "hn_fcos_decode_select")
@@ -519,11 +529,13 @@ def fcos_gather(keep, keep_count, cand, hand_lr: torch.Tensor, levels: Levels, r
         out["dxdymags"] = torch.empty((b, cap, 3), dtype=torch.float32, device=dev)
     rh = (C.c_float * b)(*[float(v) for v in ratios_h])
     rw = (C.c_float * b)(*[float(v) for v in ratios_w])
+    pl, il, ll, cl = _head_strides(hand_lr)
+    pk, ik, lk, ck = _head_strides(contact)
+    pd, id_, ld_, cd = _head_strides(dxdy)
     check(_lib.load().hn_fcos_gather(
         keep.data_ptr(), keep_count.data_ptr(), cand["loc"].data_ptr(), cand["score"].data_ptr(),
-        cand["label"].data_ptr(), cand["box"].data_ptr(), hand_lr.data_ptr(), hand_lr.stride(1),
-        ptr(contact), contact.stride(1) if contact is not None else 0, ptr(dxdy),
-        dxdy.stride(1) if dxdy is not None else 0, b, cap, levels.locs, levels.n, levels.start_arr, rh, rw,
+        cand["label"].data_ptr(), cand["box"].data_ptr(), pl, il, ll, cl, pk, ik, lk, ck, pd, id_, ld_, cd,
+        b, cap, levels.locs, levels.n, levels.start_arr, rh, rw,
         out["boxes"].data_ptr(), out["scores"].data_ptr(), out["labels"].data_ptr(), out["sides"].data_ptr(),
         out["level"].data_ptr(), ptr(out.get("contacts")), ptr(out.get("dxdymags")), stream_ptr()), "hn_fcos_gather")
     return out

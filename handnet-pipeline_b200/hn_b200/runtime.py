@@ -239,8 +239,10 @@ class FCOSPlan:
         self.levels = ops.Levels(self.lvl_hw, canvas_hw, anchor_sizes)
         L = self.levels.locs
         self.locs = L
-        self.cls_buf = torch.zeros((B, L, wts.cls_ld), dtype=torch.float32, device=device)
-        self.reg_buf = torch.zeros((B, L, wts.reg_ld), dtype=torch.float32, device=device)
+        # fused head outputs as fp32 channel PLANES [B][channel][locs] (hn_conv_desc.out_kind 2): coalesced stores in the
+        # convolution epilogue, and the decode kernel streams just the planes it needs (cls, ctr) without padding bytes
+        self.cls_buf = torch.zeros((B, wts.cls_ld, L), dtype=torch.float32, device=device)
+        self.reg_buf = torch.zeros((B, wts.reg_ld, L), dtype=torch.float32, device=device)
         self.gn_stats = torch.zeros((2, 4, 3, B, 32, 2), dtype=torch.int64, device=device)    # fixed-point sums (ops.GN_FIX_SCALE)
         self.sel_ws = torch.empty(int(ops._lib.load().hn_fcos_select_workspace_bytes(B, L)), dtype=torch.uint8, device=device)
         self.nms_ws = ops.nms_workspace(B, L, device)
@@ -342,10 +344,10 @@ class FCOSExecutor:
                     x = o
                 if t == "cls":
                     w.cls_out.run(x, relu=w.cls_relu, out_f32=pl.cls_buf, out_rows_per_image=pl.locs,
-                                  out_row_offset=pl.levels.starts[lvl])
+                                  out_row_offset=pl.levels.starts[lvl], out_planar=True)
                 else:
                     w.reg_out.run(x, relu=w.reg_relu, out_f32=pl.reg_buf, out_rows_per_image=pl.locs,
-                                  out_row_offset=pl.levels.starts[lvl])
+                                  out_row_offset=pl.levels.starts[lvl], out_planar=True)
             return run
 
         def tower_chain_levels(ti, t):
@@ -364,7 +366,7 @@ class FCOSExecutor:
                     xs = outs
                 oc, relu, buf = (w.cls_out, w.cls_relu, pl.cls_buf) if t == "cls" else (w.reg_out, w.reg_relu, pl.reg_buf)
                 ops.conv2d_levels(xs, oc.w, cout=oc.cout, ksize=oc.k, shift=oc.shift, relu=relu, out_f32=buf,
-                                  out_rows_per_image=pl.locs, out_row_offsets=pl.levels.starts[:nl])
+                                  out_rows_per_image=pl.locs, out_row_offsets=pl.levels.starts[:nl], out_planar=True)
             return run
 
         if FUSE_LEVELS and len(pl.p) <= 3:
@@ -377,12 +379,14 @@ class FCOSExecutor:
         return pl.cls_buf, pl.reg_buf
 
     def head_views(self, pl: FCOSPlan):
+        """The reference's head tensors [B, locs, k] as (strided) views of the channel-planar buffers."""
         c = self.wts.cls_cols
-        v = {"cls_logits": pl.cls_buf[..., c["cls"][0]:c["cls"][1]], "hand_lr": pl.cls_buf[..., c["lr"][0]:c["lr"][1]],
-             "bbox_regression": pl.reg_buf[..., 0:4], "bbox_ctrness": pl.reg_buf[..., 4:5]}
+        cv = lambda a, b: pl.cls_buf[:, a:b, :].permute(0, 2, 1)
+        v = {"cls_logits": cv(*c["cls"]), "hand_lr": cv(*c["lr"]),
+             "bbox_regression": pl.reg_buf[:, 0:4, :].permute(0, 2, 1), "bbox_ctrness": pl.reg_buf[:, 4:5, :].permute(0, 2, 1)}
         if "contact" in c:
-            v["hand_contact_state"] = pl.cls_buf[..., c["contact"][0]:c["contact"][1]]
-            v["hand_dxdy_relu"] = pl.cls_buf[..., c["dxdy"][0]:c["dxdy"][1]]
+            v["hand_contact_state"] = cv(*c["contact"])
+            v["hand_dxdy_relu"] = cv(*c["dxdy"])
         return v
 
     def postprocess(self, pl: FCOSPlan, ratios_h, ratios_w):

@@ -92,7 +92,10 @@ typedef struct hn_conv_desc {
   void* out;
   int out_kind; /* 0: bf16 haloed NHWC [n][h+2*out_halo][w+2*out_halo][cout];
                    1: fp32 rows: out[(img*out_rows_per_image + out_row_offset + pix)*out_ld + c],
-                      pix = h*W + w, or w*H + h when out_transpose_hw */
+                      pix = h*W + w, or w*H + h when out_transpose_hw;
+                   2: fp32 channel planes: out[(img*out_ld + c)*out_rows_per_image + out_row_offset + pix], out_ld = planes
+                      per image (>= cout): a warp's stores of one channel are one contiguous run and a consumer that reads a
+                      few channels of every location (hn_fcos_decode_select) moves no padding bytes */
   int out_halo;
   int out_rows_per_image, out_row_offset, out_ld, out_transpose_hw;
   void* out_phase; /* optional second bf16 output, phase-split with halo out_phase_halo; NULL if unused */
@@ -188,17 +191,21 @@ int hn_groupnorm_relu(void* x, int n, int h, int w, int c, int halo, const int64
 
 /* ---- P1..P4: decode + score + threshold (fcos_utils/fcos.py:591-632; det_utils.py:266-294;
  *      anchor_utils.py:56-132) -------------------------------------------------------------------------------
- * Head tensors are fp32 rows [batch][locs][*_ld] (the fused output convs write several heads side by side, so
- * each tensor has its own row stride; reg_ld must be a multiple of 4 and bbox_regression 16-byte aligned).
+ * Head tensors are fp32 [batch][locs][channels] in ANY layout: element (b, loc, c) of a tensor lives at
+ * ptr[b * img_stride + loc * loc_stride + c * chan_stride] (the detector's fused output convolutions write channel planes:
+ * loc_stride 1, chan_stride locs; row layouts [batch][locs][ld] are loc_stride ld, chan_stride 1).
  * Levels are described by level_h/w/stride (host arrays).  For every
  * location: box = anchor-centre -/+ reg * anchor-size (anchors are generated on the fly), score = max over classes
  * of sqrt(sigmoid(cls_c) * sigmoid(ctr)), label = first arg-max class (class 0 included), candidate when
- * score > score_thresh (a double, compared the way `scores > 0.7` is in the reference).  Candidates are written
- * per image in ascending location order:
+ * score > score_thresh (a double, compared the way `scores > 0.7` is in the reference).  The sigmoids / square roots are
+ * evaluated only where the outcome is open (a location whose centre-ness or largest class logit is below
+ * logit(score_thresh^2) - 0.01 cannot pass).  Candidates are written per image in ascending location order:
  *   cand_count[batch], cand_loc[batch][locs] (int32), cand_score[batch][locs] (fp32),
  *   cand_label[batch][locs] (int32), cand_box[batch][locs][4] (fp32, canvas pixels, NOT clipped). */
-int hn_fcos_decode_select(const float* cls_logits, int cls_ld, const float* bbox_ctrness, int ctr_ld,
-                          const float* bbox_regression, int reg_ld, int batch, int locs, int num_classes, int num_levels, const int* level_h_host,
+int hn_fcos_decode_select(const float* cls_logits, int64_t cls_img_stride, int cls_loc_stride, int cls_chan_stride,
+                          const float* bbox_ctrness, int64_t ctr_img_stride, int ctr_loc_stride,
+                          const float* bbox_regression, int64_t reg_img_stride, int reg_loc_stride, int reg_chan_stride,
+                          int batch, int locs, int num_classes, int num_levels, const int* level_h_host,
                           const int* level_w_host, const int* level_stride_h_host, const int* level_stride_w_host,
                           const int* level_anchor_host, double score_thresh, int* cand_count, int* cand_loc,
                           float* cand_score, int* cand_label, float* cand_box, void* workspace,
@@ -226,8 +233,11 @@ int hn_nms_batched(const float* cand_box, const float* cand_score, const int* ca
  * dxdy rows [..][dxdy_ld] (3 used, already ReLU'd) -> dxdymags[batch][cap][3] = (d0, 0.1 * normalize(d1, d2))
  * (fcos_utils/fcos.py:299-303). */
 int hn_fcos_gather(const int* keep, const int* keep_count, const int* cand_loc, const float* cand_score,
-                   const int* cand_label, const float* cand_box, const float* hand_lr, int lr_ld,
-                   const float* contact_logits, int contact_ld, const float* dxdy, int dxdy_ld, int batch, int cap, int locs, int num_levels, const int* level_start_host,
+                   const int* cand_label, const float* cand_box, const float* hand_lr, int64_t lr_img_stride,
+                   int lr_loc_stride, int lr_chan_stride, const float* contact_logits, int64_t contact_img_stride,
+                   int contact_loc_stride, int contact_chan_stride, const float* dxdy, int64_t dxdy_img_stride,
+                   int dxdy_loc_stride, int dxdy_chan_stride, int batch, int cap, int locs, int num_levels,
+                   const int* level_start_host,
                    const float* ratio_h_host, const float* ratio_w_host, float* boxes, float* scores, int64_t* labels,
                    int64_t* sides, float* level, int64_t* contacts, float* dxdymags, void* stream);
 

@@ -58,6 +58,34 @@ def test_decode_select_matches_oracle(ops):
         assert torch.equal(box, ref_box)
 
 
+def test_decode_select_channel_planes_equal_rows(ops):
+    """The detector's head buffers are channel planes [B][channel][locs] (out_kind 2 of the output convolutions): decode and
+    gather over planar views give exactly what they give over row-layout tensors, incl. the early-out for hopeless
+    locations (logits far below the cut) next to candidates."""
+    lv = ops.Levels([(25, 34), (13, 17), (7, 9)], (200, 272), (8, 16, 32))
+    ho = stress_head_tensors(5, 3, lv.locs, 3, -0.35)
+    ho["cls_logits"][1] -= 8.0                       # an image in the sparse regime: almost everything is skipped
+    ho["cls_logits"][1, ::97] += 10.0
+    rows = {k: v.cuda() for k, v in ho.items()}
+    planar = {k: v.cuda().permute(0, 2, 1).contiguous().permute(0, 2, 1) for k, v in ho.items()}
+    assert planar["cls_logits"].stride(1) == 1 and planar["cls_logits"].stride(2) == lv.locs
+    a = ops.fcos_decode_select(rows["cls_logits"], rows["bbox_ctrness"], rows["bbox_regression"], 3, lv, 0.7)
+    b = ops.fcos_decode_select(planar["cls_logits"], planar["bbox_ctrness"], planar["bbox_regression"], 3, lv, 0.7)
+    torch.cuda.synchronize()
+    assert torch.equal(a["count"], b["count"]) and int(a["count"][1]) < int(a["count"][0]) // 4
+    for i in range(3):
+        n = int(a["count"][i])
+        for k in ("loc", "score", "label", "box"):
+            assert torch.equal(a[k][i, :n], b[k][i, :n]), k
+    ka, ca = ops.nms_batched(a["box"], a["score"], a["label"], a["count"], 0.3)
+    ga = ops.fcos_gather(ka, ca, a, rows["hand_lr"], lv, [0.6] * 3, [0.6] * 3)
+    gb = ops.fcos_gather(ka, ca, a, planar["hand_lr"], lv, [0.6] * 3, [0.6] * 3)
+    torch.cuda.synchronize()
+    for i in range(3):
+        n = int(ca[i])
+        assert torch.equal(ga["sides"][i, :n], gb["sides"][i, :n]) and torch.equal(ga["boxes"][i, :n], gb["boxes"][i, :n])
+
+
 def test_decode_select_strided_rows_and_empty(ops):
     """Fused head buffers (row stride 8) and an image with no candidate at all."""
     lv = _levels(ops)

@@ -175,6 +175,29 @@ def test_conv_fp32_rows_output_fused_heads(ops):
     assert (buf[:, :1000] == -7.0).all() and (buf[:, 1000:, 5:] == -7.0).all(), "nothing else may be written"
 
 
+def test_conv_fp32_channel_planes_output(ops):
+    """out_kind 2: the fused FCOS output convolutions write fp32 channel planes [n][planes][rows] at a level's row offset
+    (what hn_fcos_decode_select streams); same values as the row layout, nothing else written."""
+    g = torch.Generator().manual_seed(19)
+    n, h, w = 2, 25, 34
+    x = rand(g, n, 256, h, w).to(DEV)
+    wt = rand(g, 5, 256, 3, 3, scale=0.02).to(DEV)
+    bias = torch.randn(5, generator=g).to(DEV)
+    ref = F.conv2d(x, wt, bias, padding=1)
+    ref[:, 0:4] = F.relu(ref[:, 0:4])
+    rows_total = 300 + h * w + 7
+    planes = torch.full((n, 8, rows_total), -7.0, device=DEV)
+    ops.conv2d(ops.Act.from_nchw(x, 1), ops.pack_conv_weight(wt), cout=5, ksize=3, shift=bias, relu=(0, 4),
+               out_f32=planes, out_rows_per_image=rows_total, out_row_offset=300, out_planar=True)
+    rowbuf = torch.zeros((n, h * w, 8), device=DEV)
+    ops.conv2d(ops.Act.from_nchw(x, 1), ops.pack_conv_weight(wt), cout=5, ksize=3, shift=bias, relu=(0, 4), out_f32=rowbuf)
+    torch.cuda.synchronize()
+    got = planes[:, :5, 300:300 + h * w]
+    torch.testing.assert_close(got, ref.reshape(n, 5, h * w), rtol=1e-4, atol=1e-4)
+    assert torch.equal(got, rowbuf[..., :5].permute(0, 2, 1)), "planes and rows hold the same fp32 values"
+    assert (planes[:, 5:] == -7.0).all() and (planes[:, :, :300] == -7.0).all() and (planes[:, :, 300 + h * w:] == -7.0).all()
+
+
 def test_conv_fp32_rows_transposed_a2j_layout(ops):
     """A2J output convs: rows ordered w-major (permute(0,3,2,1), a2j/a2j.py:85-89)."""
     g = torch.Generator().manual_seed(10)
@@ -407,6 +430,13 @@ def test_conv_levels_head_outputs_equal_per_level_launches(ops, n, levels, cout,
     # keeps them resident and accumulates chunk by chunk: fp32 rows agree to summation-order noise, not bit for bit)
     torch.testing.assert_close(buf_a, buf_b, rtol=1e-5, atol=1e-5)
     assert (buf_b[:, locs:] == -7.0).all() and (buf_b[..., cout:] == -7.0).all(), "nothing else may be written"
+    # the product's layout: channel planes [n][planes][locs] in one launch over all levels
+    planes = torch.full((n, ld, locs + 3), -7.0, device=DEV)
+    ops.conv2d_levels(acts, wp, cout=cout, ksize=3, shift=bias, relu=relu, out_f32=planes, out_rows_per_image=locs + 3,
+                      out_row_offsets=starts[:-1], out_planar=True)
+    torch.cuda.synchronize()
+    assert torch.equal(planes[:, :cout, :locs], buf_b[:, :locs, :cout].permute(0, 2, 1))
+    assert (planes[:, cout:] == -7.0).all() and (planes[:, :, locs:] == -7.0).all()
     for lvl, ((h, w), x) in enumerate(zip(levels, xs)):
         ref = F.conv2d(x, wt, bias, padding=1)
         ref[:, relu[0]:relu[1]] = F.relu(ref[:, relu[0]:relu[1]])
