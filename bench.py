@@ -483,7 +483,7 @@ def run_post_stress(ctx: Ctx, net):
     lv = ops.Levels([(100, 136), (50, 68), (25, 34)], (800, 1088), (8, 16, 32))
     B = FRAMES_PER_GPU
     # channel planes [B][channel][locs], the layout the detector's output convolutions write
-    ho = {k: v.to(dev).permute(0, 2, 1).contiguous().permute(0, 2, 1) for k, v in synth.stress_head_tensors(31, B, lv.locs, 3, -0.35).items()}
+    ho = {k: ops.head_planes(v.to(dev)) for k, v in synth.stress_head_tensors(31, B, lv.locs, 3, -0.35).items()}
     m = net.detector
     ws_sel = torch.empty(int(ops._lib.load().hn_fcos_select_workspace_bytes(B, lv.locs)), dtype=torch.uint8, device=dev)
     ws_nms = ops.nms_workspace(B, lv.locs, dev)

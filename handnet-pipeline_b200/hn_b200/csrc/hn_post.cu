@@ -39,180 +39,256 @@ struct HeadView {
   int loc, chan;
 };
 
-// score = max_c sqrt(sigmoid(cls_c) * sigmoid(ctr)), label = first arg max (fcos_utils/fcos.py:598-599), on logits already
-// in registers.  Every rounding of the chain (IEEE division, multiply, square root) is monotone and CUDA's expf is within
-// 2 ulp, so the class with the largest LOGIT has the largest score; an EARLIER class can only tie with it if its logit is
-// within a hair of the largest one (or both sit in the saturated tail, where sigmoid rounds to 1.0).  So: one exact score
-// for the arg-max logit, and exact scores only for classes whose logit is inside that neighbourhood -- for typical heads one
-// sigmoid chain per location instead of one per class, with the reference's first-max label semantics kept bit for bit.
-template <int NC_MAX>
-__device__ __forceinline__ void score_label_regs(const float (&lg)[NC_MAX], int nc, float ctr, float& best, int& label) {
-  const float sc = sigmoid_rn(ctr);
-  int cm = 0;
-  float mx = lg[0];
-#pragma unroll
-  for (int c = 1; c < NC_MAX; ++c)
-    if (c < nc && lg[c] > mx) { mx = lg[c]; cm = c; }
-  best = __fsqrt_rn(__fmul_rn(sigmoid_rn(mx), sc));
-  label = cm;
-  // neighbourhood in which another class's score may round to the same float: tiny below 4, a full unit up to 15 (the
-  // sigmoid's slope there is ~1e-6 per ulp of its value), everything beyond (saturation)
-  const float margin = mx <= 4.f ? 1e-4f * (1.f + fabsf(mx)) : (mx <= 15.f ? 1.f : INFINITY);
-#pragma unroll
-  for (int c = NC_MAX - 1; c >= 0; --c) {              // descending: the FIRST class among equal scores wins
-    if (c < nc && c != cm && lg[c] >= mx - margin) {
-      const float s = __fsqrt_rn(__fmul_rn(sigmoid_rn(lg[c]), sc));
-      if (s > best || (s == best && c < label)) { best = s; label = c; }
-    }
+// ------------------------------------------------------------------------ decode + score + select (P1-P4), one pass
+// score = max_c sqrt(sigmoid(cls_c) * sigmoid(ctr)), label = first arg max (fcos_utils/fcos.py:598-599).  Every rounding of
+// the chain (IEEE division, multiply, square root) is monotone and CUDA's expf is within 2 ulp, so the class with the largest
+// LOGIT has the largest score; an EARLIER class can only tie with it if its logit is within a hair of the largest one (or both
+// sit in the saturated tail, where sigmoid rounds to 1.0).  So the kernel tracks the two largest logits of a location while it
+// streams the class planes, evaluates ONE sigmoid chain for the arg-max logit, and falls back to the reference's loop over all
+// classes (score_label_exact, re-reading the logits) only when the runner-up is inside that neighbourhood: first-max label
+// semantics bit for bit at one chain per location instead of one per class.
+__device__ __noinline__ void score_label_exact(const float* __restrict__ cls, size_t chan, int nc, float sc, float& best,
+                                               int& label) {
+  best = -1.f;
+  label = 0;
+  for (int c = 0; c < nc; ++c) {
+    const float s = __fsqrt_rn(__fmul_rn(sigmoid_rn(__ldg(cls + c * chan)), sc));
+    if (c == 0 || s > best) { best = s; label = c; }
   }
 }
 
-// pass 1: score / label of every location that CAN pass, survivors compacted inside their chunk of SEL_CHUNK locations (in
-// location order) into the scratch, and the number of survivors per chunk.  A location whose centre-ness logit or whose
-// largest class logit is below `skip_below` cannot reach the threshold (sqrt(sigmoid(c) * sigmoid(t)) <= sqrt(sigmoid(min(c,
-// t)))), so the sigmoids and square roots are evaluated only where the outcome is open: in the sparse regime a detector
-// normally runs in, the pass is a pure stream over the cls / ctr planes.  A thread takes SEL_PER consecutive locations (one
-// 16-byte load per plane when the heads are channel planes).
-constexpr int SEL_PER = 4;
-constexpr int SEL_CHUNK = SEL_BLOCK * SEL_PER;
-constexpr int SEL_NC_MAX = 8;
-struct SelScratch {
-  float* score;      // [batch][locs]: chunk k's survivors at [k * SEL_CHUNK ...)
-  int* label;
-  int* loc;
-  int* chunk_count;  // [batch][chunks]
+// neighbourhood of the largest logit in which another class's score may round to the same float: tiny below 4, a full unit
+// up to 15 (the sigmoid's slope there is ~1e-6 per ulp of its value), everything beyond (saturation).  Far in the negative
+// tail (exp overflows, scores underflow to equal values) the exact loop runs as well.
+__device__ __forceinline__ bool needs_exact(float mx, float second, float ctr) {
+  const float margin = mx <= 4.f ? 1e-4f * (1.f + fabsf(mx)) : (mx <= 15.f ? 1.f : INFINITY);
+  return second >= mx - margin || mx < -80.f || ctr < -80.f;
+}
+
+constexpr int SEL_PER = 4;                        // consecutive locations of a thread: one 16-byte load per plane
+constexpr int SEL_WARPS = SEL_BLOCK / 32;
+constexpr int SEL_ROUND = 32 * SEL_PER;           // locations a warp takes per round
+constexpr int SEL_CHUNK = SEL_BLOCK * SEL_PER;    // locations of a block per round
+
+__device__ __forceinline__ void top2(float v, int c, float& mx, float& second, int& cm) {
+  if (v > mx) { second = mx; mx = v; cm = c; }
+  else second = fmaxf(second, v);
+}
+
+// One block = one chunk of G * SEL_CHUNK locations of one image (grid = batch * chunks, image-major; G = rounds per block, picked
+// by the host so that the grid fills whole waves of resident blocks); a warp owns G * 128 consecutive locations and takes them
+// in G rounds.  All rounds' loads are issued up front as 16-byte cp.async copies into the warp's own shared-memory staging
+// (one commit group per round): the bytes in flight per SM are bounded by shared memory, not by registers, and a lane reads back
+// exactly what it copied (no block barrier).  Survivors are parked, in location order, in the staging of the round they came
+// from (consumed by then); the block counts them, publishes the count in state[] and sums the counts of the chunks before it in
+// the same image (they have lower block indices: scheduled no later than this block, so the wait cannot deadlock; a chunk
+// without survivors does not look back at all).  Then every survivor decodes its box (det_utils.py:266-294, anchors generated
+// on the fly: anchor_utils.py:56-112) and goes to its place in the image's candidate list, ascending in location, with
+// coalesced stores.
+//
+// A location whose centre-ness logit or whose largest class logit is below `skip_below` cannot reach the threshold
+// (sqrt(sigmoid(c) * sigmoid(t)) <= sqrt(sigmoid(min(c, t)))), so in the sparse regime a detector normally runs in the
+// kernel is a pure stream over the cls / ctr planes.  NC > 0: class count known at compile time (staged planes); NC = 0: any
+// class count up to 256 (direct loads).
+// state word: 0 = not published yet (the host clears the array before the launch), else survivors + 1.
+constexpr int SEL_MAX_ROUNDS = 4;
+template <int NC>
+struct SelStage {
+  static constexpr int PLANES = NC > 0 ? NC + 1 : 2;            // staged planes per round (>= 2: room for 128 parked survivors)
+  static constexpr int ROUND_FLOATS = PLANES * SEL_ROUND;       // per warp and round
 };
 
+__device__ __forceinline__ void sel_cp16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(hn_smem_u32(dst)), "l"(src) : "memory");
+}
+
+template <int NC>
 __global__ void __launch_bounds__(SEL_BLOCK)
-select_score_kernel(const HeadView cls, const HeadView ctr, int locs, int nc, float thresh_ge, float skip_below, SelScratch ws) {
-  __shared__ int warp_sums[SEL_BLOCK / 32];
-  const int b = blockIdx.y;
-  const int loc0 = (blockIdx.x * SEL_BLOCK + threadIdx.x) * SEL_PER;
+select_decode_kernel(const HeadView cls, const HeadView ctr, const HeadView reg, int locs, int nc_rt, int chunks, int G,
+                     float thresh_ge, float skip_below, const Levels lv, unsigned* __restrict__ state,
+                     int* __restrict__ cand_count, int* __restrict__ cand_loc, float* __restrict__ cand_score,
+                     int* __restrict__ cand_label, float4* __restrict__ cand_box) {
+  extern __shared__ __align__(16) float stage[];          // [SEL_WARPS][G][PLANES][SEL_ROUND]
+  __shared__ int warp_sums[SEL_WARPS];
+  __shared__ int round_count[SEL_WARPS][SEL_MAX_ROUNDS];
+  __shared__ int base_s;
+  constexpr int RF = SelStage<NC>::ROUND_FLOATS;
+  const int nc = NC > 0 ? NC : nc_rt;
+  const int b = blockIdx.x / chunks, chunk = blockIdx.x - b * chunks;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float lg[SEL_PER][SEL_NC_MAX], tt[SEL_PER];
+  const int warp_loc0 = (chunk * SEL_WARPS + warp) * (SEL_ROUND * G);
   const float* cbase = cls.p + (size_t)b * cls.img;
   const float* tbase = ctr.p + (size_t)b * ctr.img;
-  const bool vec = cls.loc == 1 && ctr.loc == 1 && loc0 + SEL_PER <= locs &&
-                   ((reinterpret_cast<uintptr_t>(cbase + loc0) | reinterpret_cast<uintptr_t>(tbase + loc0) |
-                     ((size_t)cls.chan * 4)) & 15) == 0;
-  if (vec) {
-    const float4 t4 = __ldg(reinterpret_cast<const float4*>(tbase + loc0));
-    tt[0] = t4.x; tt[1] = t4.y; tt[2] = t4.z; tt[3] = t4.w;
+  const size_t chan = (size_t)cls.chan;
+  // channel planes whose rows are 16-byte aligned: vector loads (every loc0 is a multiple of 4)
+  const bool planes = cls.loc == 1 && ctr.loc == 1 &&
+                      ((reinterpret_cast<uintptr_t>(cbase) | reinterpret_cast<uintptr_t>(tbase) | (chan * 4)) & 15) == 0;
+  float* my_stage = stage + (size_t)warp * G * RF;
+  if (NC > 0 && planes) {
+    for (int g = 0; g < G; ++g) {
+      const int loc0 = warp_loc0 + g * SEL_ROUND + lane * SEL_PER;
+      if (loc0 + SEL_PER <= locs) {
+        float* d = my_stage + g * RF + lane * SEL_PER;
+        sel_cp16(d, tbase + loc0);
 #pragma unroll
-    for (int c = 0; c < SEL_NC_MAX; ++c) {
-      if (c < nc) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(cbase + (size_t)c * cls.chan + loc0));
-        lg[0][c] = v.x; lg[1][c] = v.y; lg[2][c] = v.z; lg[3][c] = v.w;
+        for (int c = 0; c < NC; ++c) sel_cp16(d + (c + 1) * SEL_ROUND, cbase + c * chan + loc0);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  }
+  int nsurv = 0;                                          // survivors of this warp so far (warp-uniform)
+#pragma unroll 1
+  for (int g = 0; g < G; ++g) {
+    const int loc0 = warp_loc0 + g * SEL_ROUND + lane * SEL_PER;
+    const bool vec = planes && loc0 + SEL_PER <= locs;
+    float tt[SEL_PER], mx[SEL_PER], second[SEL_PER];
+    int cm[SEL_PER];
+#pragma unroll
+    for (int i = 0; i < SEL_PER; ++i) { mx[i] = -INFINITY; second[i] = -INFINITY; cm[i] = 0; tt[i] = -INFINITY; }
+    if (NC > 0 && planes) {
+      switch (G - 1 - g) {                                // this round's copies have landed (later rounds may still fly)
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
       }
     }
-  } else {
+    if (vec) {
+      if (NC > 0) {
+        const float* d = my_stage + g * RF + lane * SEL_PER;
+        const float4 t4 = *reinterpret_cast<const float4*>(d);
+        tt[0] = t4.x; tt[1] = t4.y; tt[2] = t4.z; tt[3] = t4.w;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(d + (c + 1) * SEL_ROUND);
+          top2(v.x, c, mx[0], second[0], cm[0]);
+          top2(v.y, c, mx[1], second[1], cm[1]);
+          top2(v.z, c, mx[2], second[2], cm[2]);
+          top2(v.w, c, mx[3], second[3], cm[3]);
+        }
+      } else {
+        const float4 t4 = __ldg(reinterpret_cast<const float4*>(tbase + loc0));
+        tt[0] = t4.x; tt[1] = t4.y; tt[2] = t4.z; tt[3] = t4.w;
+#pragma unroll 4
+        for (int c = 0; c < nc; ++c) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(cbase + c * chan + loc0));
+          top2(v.x, c, mx[0], second[0], cm[0]);
+          top2(v.y, c, mx[1], second[1], cm[1]);
+          top2(v.z, c, mx[2], second[2], cm[2]);
+          top2(v.w, c, mx[3], second[3], cm[3]);
+        }
+      }
+    } else if (loc0 < locs) {
+      for (int i = 0; i < SEL_PER; ++i) {                 // the ragged end of an image, or a row layout
+        const int loc = loc0 + i;
+        if (loc < locs) {
+          tt[i] = __ldg(tbase + (size_t)loc * ctr.loc);
+          for (int c = 0; c < nc; ++c) top2(__ldg(cbase + (size_t)loc * cls.loc + c * chan), c, mx[i], second[i], cm[i]);
+        }
+      }
+    }
+    float s[SEL_PER];
+    int mine = 0;
+    unsigned pmask = 0;
 #pragma unroll
     for (int i = 0; i < SEL_PER; ++i) {
-      const int loc = loc0 + i;
-      tt[i] = loc < locs ? __ldg(tbase + (size_t)loc * ctr.loc) : -INFINITY;
-#pragma unroll
-      for (int c = 0; c < SEL_NC_MAX; ++c)
-        if (c < nc) lg[i][c] = loc < locs ? __ldg(cbase + (size_t)loc * cls.loc + (size_t)c * cls.chan) : -INFINITY;
+      s[i] = 0.f;
+      if (loc0 + i < locs && tt[i] >= skip_below && mx[i] >= skip_below) {
+        const float sc = sigmoid_rn(tt[i]);
+        if (needs_exact(mx[i], second[i], tt[i]))
+          score_label_exact(cbase + (size_t)(loc0 + i) * cls.loc, chan, nc, sc, s[i], cm[i]);
+        else
+          s[i] = __fsqrt_rn(__fmul_rn(sigmoid_rn(mx[i]), sc));
+        if (s[i] >= thresh_ge) { pmask |= 1u << i; ++mine; }
+      }
     }
-  }
-  float s[SEL_PER];
-  int l[SEL_PER];
-  int mine = 0;
-  unsigned pmask = 0;
+    int cnt = 0;
+    if (__any_sync(0xffffffffu, mine != 0)) {
+      int incl = mine;
 #pragma unroll
-  for (int i = 0; i < SEL_PER; ++i) {
-    float mx = lg[i][0];
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      // every lane has read its staged logits (the shuffles above are warp-wide): the round's staging is free for parking
+      uint2* parked = reinterpret_cast<uint2*>(my_stage + g * RF);
+      int q = incl - mine;
 #pragma unroll
-    for (int c = 1; c < SEL_NC_MAX; ++c)
-      if (c < nc) mx = fmaxf(mx, lg[i][c]);
-    s[i] = 0.f;
-    l[i] = 0;
-    if (loc0 + i < locs && tt[i] >= skip_below && mx >= skip_below) {
-      score_label_regs<SEL_NC_MAX>(lg[i], nc, tt[i], s[i], l[i]);
-      if (s[i] >= thresh_ge) { pmask |= 1u << i; ++mine; }
+      for (int i = 0; i < SEL_PER; ++i)
+        if (pmask & (1u << i)) parked[q++] = make_uint2((unsigned)(loc0 + i) | ((unsigned)cm[i] << 24), __float_as_uint(s[i]));
+      cnt = __shfl_sync(0xffffffffu, incl, 31);
     }
+    if (lane == 0) round_count[warp][g] = cnt;
+    nsurv += cnt;
   }
-  // exclusive prefix of `mine` over the block (location order = thread order)
-  int incl = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) warp_sums[warp] = incl;
+  if (lane == 0) warp_sums[warp] = nsurv;
   __syncthreads();
   int before = 0, total = 0;
 #pragma unroll
-  for (int i = 0; i < SEL_BLOCK / 32; ++i) {
+  for (int i = 0; i < SEL_WARPS; ++i) {
     const int c = warp_sums[i];
     if (i < warp) before += c;
     total += c;
   }
-  if (mine) {
-    size_t o = (size_t)b * locs + (size_t)blockIdx.x * SEL_CHUNK + before + (incl - mine);
+  unsigned* st = state + (size_t)b * chunks;
+  const bool last = chunk == chunks - 1;
+  if (warp == 0) {
+    if (lane == 0) atomicExch(st + chunk, (unsigned)total + 1u);           // publish
+    if (total != 0 || last) {
+      int acc = 0;
+      const long long t0 = clock64();
+      for (int i = lane; i < chunk; i += 32) {                              // look back
+        unsigned v;
+        while ((v = *reinterpret_cast<volatile unsigned*>(st + i)) == 0u) {
+          __nanosleep(40);
+          if (clock64() - t0 > 4000000000LL) asm volatile("trap;");         // ~2 s: a predecessor never ran
+        }
+        acc += (int)(v - 1u);
+      }
 #pragma unroll
-    for (int i = 0; i < SEL_PER; ++i) {
-      if (pmask & (1u << i)) {
-        ws.score[o] = s[i];
-        ws.label[o] = l[i];
-        ws.loc[o] = loc0 + i;
-        ++o;
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) {
+        base_s = acc;
+        if (last) cand_count[b] = acc + total;                              // the last chunk knows the image's total
       }
     }
   }
-  if (threadIdx.x == 0) ws.chunk_count[b * gridDim.x + blockIdx.x] = total;
-}
-
-// pass 2: chunk k's survivors move to their place in the image's candidate list (offset = survivors of the chunks before it)
-// and get their boxes decoded (det_utils.py:266-294).  Chunks without survivors leave at once.
-__global__ void __launch_bounds__(SEL_BLOCK)
-select_compact_kernel(const HeadView reg, SelScratch ws, int locs, const Levels lv, int* __restrict__ cand_count,
-                      int* __restrict__ cand_loc, float* __restrict__ cand_score, int* __restrict__ cand_label,
-                      float4* __restrict__ cand_box) {
-  __shared__ int base_s;
-  const int b = blockIdx.y;
-  const int chunks = gridDim.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int mine = ws.chunk_count[b * chunks + blockIdx.x];
-  const bool last_chunk = blockIdx.x == chunks - 1;
-  if (mine == 0 && !last_chunk) return;
-  // offset of this chunk = sum of the counts of the chunks before it
-  if (warp == 0) {
-    int acc = 0;
-    for (int i = lane; i < blockIdx.x; i += 32) acc += ws.chunk_count[b * chunks + i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) base_s = acc;
-  }
+  if (total == 0) return;
   __syncthreads();
-  for (int q = threadIdx.x; q < mine; q += SEL_BLOCK) {
-    const size_t src = (size_t)b * locs + (size_t)blockIdx.x * SEL_CHUNK + q;
-    const int loc = ws.loc[src];
-    int l = 0;
-    while (l + 1 < lv.n && loc >= lv.start[l + 1]) ++l;
-    const int cell = loc - lv.start[l];
-    const int y = cell / lv.w[l], x = cell - y * lv.w[l];
-    // anchor = (x*sw, y*sh, x*sw, y*sh) + round([-s,-s,s,s]/2)   (anchor_utils.py:56-112)
-    const float half = rintf((float)lv.anchor[l] * 0.5f);
-    const float a0 = (float)(x * lv.sw[l]) - half, a1 = (float)(y * lv.sh[l]) - half;
-    const float a2 = (float)(x * lv.sw[l]) + half, a3 = (float)(y * lv.sh[l]) + half;
-    const float cx = __fmul_rn(0.5f, __fadd_rn(a0, a2)), cy = __fmul_rn(0.5f, __fadd_rn(a1, a3));
-    const float bw = __fsub_rn(a2, a0), bh = __fsub_rn(a3, a1);
-    const float* rp = reg.p + (size_t)b * reg.img + (size_t)loc * reg.loc;
-    const float r0 = __ldg(rp), r1 = __ldg(rp + (size_t)reg.chan), r2 = __ldg(rp + 2 * (size_t)reg.chan),
-                r3 = __ldg(rp + 3 * (size_t)reg.chan);
-    float4 box;
-    box.x = __fsub_rn(cx, __fmul_rn(r0, bw));
-    box.y = __fsub_rn(cy, __fmul_rn(r1, bh));
-    box.z = __fadd_rn(cx, __fmul_rn(r2, bw));
-    box.w = __fadd_rn(cy, __fmul_rn(r3, bh));
-    const size_t o = (size_t)b * locs + base_s + q;
-    cand_loc[o] = loc;
-    cand_score[o] = ws.score[src];
-    cand_label[o] = ws.label[src];
-    cand_box[o] = box;
+  const float* rbase = reg.p + (size_t)b * reg.img;
+  size_t out0 = (size_t)b * locs + base_s + before;
+  for (int g = 0; g < G; ++g) {
+    const int cnt = round_count[warp][g];
+    const uint2* parked = reinterpret_cast<const uint2*>(my_stage + g * RF);
+    for (int q = lane; q < cnt; q += 32) {
+      const uint2 e = parked[q];
+      const int loc = (int)(e.x & 0xffffffu);
+      int l = 0;
+      while (l + 1 < lv.n && loc >= lv.start[l + 1]) ++l;
+      const int cell = loc - lv.start[l];
+      const int y = cell / lv.w[l], x = cell - y * lv.w[l];
+      // anchor = (x*sw, y*sh, x*sw, y*sh) + round([-s,-s,s,s]/2)   (anchor_utils.py:56-112)
+      const float half = rintf((float)lv.anchor[l] * 0.5f);
+      const float a0 = (float)(x * lv.sw[l]) - half, a1 = (float)(y * lv.sh[l]) - half;
+      const float a2 = (float)(x * lv.sw[l]) + half, a3 = (float)(y * lv.sh[l]) + half;
+      const float cx = __fmul_rn(0.5f, __fadd_rn(a0, a2)), cy = __fmul_rn(0.5f, __fadd_rn(a1, a3));
+      const float bw = __fsub_rn(a2, a0), bh = __fsub_rn(a3, a1);
+      const float* rp = rbase + (size_t)loc * reg.loc;
+      const float r0 = __ldg(rp), r1 = __ldg(rp + (size_t)reg.chan), r2 = __ldg(rp + 2 * (size_t)reg.chan),
+                  r3 = __ldg(rp + 3 * (size_t)reg.chan);
+      float4 box;
+      box.x = __fsub_rn(cx, __fmul_rn(r0, bw));
+      box.y = __fsub_rn(cy, __fmul_rn(r1, bh));
+      box.z = __fadd_rn(cx, __fmul_rn(r2, bw));
+      box.w = __fadd_rn(cy, __fmul_rn(r3, bh));
+      const size_t o = out0 + q;
+      cand_loc[o] = loc;
+      cand_score[o] = __uint_as_float(e.y);
+      cand_label[o] = (int)(e.x >> 24);
+      cand_box[o] = box;
+    }
+    out0 += cnt;
   }
-  if (last_chunk && threadIdx.x == 0) cand_count[b] = base_s + mine;     // the last chunk knows the total
 }
 
 // ------------------------------------------------------------------------------------- NMS
@@ -637,8 +713,7 @@ gather_kernel(const int* __restrict__ keep, const int* __restrict__ keep_count, 
 }  // namespace
 
 extern "C" int64_t hn_fcos_select_workspace_bytes(int batch, int locs) {
-  const size_t n = (size_t)batch * locs;
-  return (int64_t)(align256(n * 4) * 3 + align256((size_t)batch * hn_div_up(locs, SEL_CHUNK) * 4));
+  return (int64_t)align256((size_t)batch * hn_div_up(locs, SEL_CHUNK) * 4);      // one state word per chunk (of the finest split)
 }
 
 extern "C" int hn_fcos_decode_select(const float* cls_logits, int64_t cls_img_stride, int cls_loc_stride, int cls_chan_stride,
@@ -651,8 +726,8 @@ extern "C" int hn_fcos_decode_select(const float* cls_logits, int64_t cls_img_st
                                      float* cand_box, void* workspace, int64_t workspace_bytes, void* stream) {
   HN_REQUIRE(cls_logits && bbox_ctrness && bbox_regression && cand_count && cand_loc && cand_score && cand_label &&
                  cand_box && workspace, "hn_fcos_decode_select: null pointer");
-  HN_REQUIRE(batch > 0 && locs > 0 && num_classes > 0 && num_classes <= SEL_NC_MAX && num_levels > 0 && num_levels <= MAX_LEVELS,
-             "hn_fcos_decode_select: bad sizes (at most %d classes)", SEL_NC_MAX);
+  HN_REQUIRE(batch > 0 && locs > 0 && num_classes > 0 && num_levels > 0 && num_levels <= MAX_LEVELS,
+             "hn_fcos_decode_select: bad sizes");
   HN_REQUIRE(cls_loc_stride >= 1 && cls_chan_stride >= 1 && ctr_loc_stride >= 1 && reg_loc_stride >= 1 && reg_chan_stride >= 1 &&
                  (reinterpret_cast<uintptr_t>(cand_box) & 15) == 0,
              "hn_fcos_decode_select: strides must be positive and cand_box 16-byte aligned");
@@ -672,15 +747,16 @@ extern "C" int hn_fcos_decode_select(const float* cls_logits, int64_t cls_img_st
   }
   lv.start[num_levels] = acc;
   HN_REQUIRE(acc == locs, "hn_fcos_decode_select: levels cover %d locations, locs=%d", acc, locs);
-  const size_t n = (size_t)batch * locs;
-  uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
-  SelScratch ws;
-  ws.score = reinterpret_cast<float*>(w);
-  ws.label = reinterpret_cast<int*>(w + align256(n * 4));
-  ws.loc = reinterpret_cast<int*>(w + 2 * align256(n * 4));
-  ws.chunk_count = reinterpret_cast<int*>(w + 3 * align256(n * 4));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  dim3 grid(hn_div_up(locs, SEL_CHUNK), batch);
+  HN_REQUIRE(num_classes <= 256 && locs < (1 << 24), "hn_fcos_decode_select: at most 256 classes and 2^24 locations per image");
+  // Rounds per block.  Measured on one B200 (256 frames, 17 850 locations, sparse / stress regime, tools/membound_roofline.py):
+  // 1 round 35.8 / 66.7 us, 2 rounds 35.6 / 64.5, 3 rounds 37.9 / 74.5, 4 rounds 39.6 / 80.9 -- two rounds halve the block
+  // tails (scan, look-back, exit) without emptying the last wave of resident blocks; small grids take one round.
+  const int stage_planes = num_classes <= 4 ? num_classes + 1 : 2;
+  int rounds = (long long)batch * hn_div_up(locs, SEL_CHUNK * 2) >= 2 * 5 * 148 ? 2 : 1;
+  if (const char* e = getenv("HN_SELECT_ROUNDS")) { const int v = atoi(e); if (v >= 1 && v <= SEL_MAX_ROUNDS) rounds = v; }
+  const int chunks = hn_div_up(locs, SEL_CHUNK * rounds);
+  HN_REQUIRE((long long)batch * chunks < (1ll << 31), "hn_fcos_decode_select: grid too large");
   const float thresh_ge = float_gt_as_ge(score_thresh);
   // score >= t needs sigmoid(cls) * sigmoid(ctr) >= t^2, hence each logit >= logit(t^2); 0.01 of margin covers the rounding
   // of the fp32 evaluation many times over (at t = 0.7: skip below -0.05, where the score can reach 0.698 at most)
@@ -692,11 +768,29 @@ extern "C" int hn_fcos_decode_select(const float* cls_logits, int64_t cls_img_st
   const HeadView vcls = {cls_logits, (long long)cls_img_stride, cls_loc_stride, cls_chan_stride};
   const HeadView vctr = {bbox_ctrness, (long long)ctr_img_stride, ctr_loc_stride, 1};
   const HeadView vreg = {bbox_regression, (long long)reg_img_stride, reg_loc_stride, reg_chan_stride};
-  select_score_kernel<<<grid, SEL_BLOCK, 0, st>>>(vcls, vctr, locs, num_classes, thresh_ge, skip_below, ws);
-  hn_count_launch();
-  HN_LAUNCH_CHECK();
-  select_compact_kernel<<<grid, SEL_BLOCK, 0, st>>>(vreg, ws, locs, lv, cand_count, cand_loc, cand_score, cand_label,
-                                                    reinterpret_cast<float4*>(cand_box));
+  unsigned* state = reinterpret_cast<unsigned*>(workspace);
+  HN_CHECK_CUDA(cudaMemsetAsync(state, 0, (size_t)batch * chunks * sizeof(unsigned), st));
+  float4* box4 = reinterpret_cast<float4*>(cand_box);
+  const size_t parked_bytes = (size_t)SEL_WARPS * rounds * stage_planes * SEL_ROUND * sizeof(float);
+#define HN_SELECT_LAUNCH(NC)                                                                                                 \
+  {                                                                                                                            \
+    static bool attr = false;                                                                                                  \
+    if (!attr) {                                                                                                               \
+      HN_CHECK_CUDA(cudaFuncSetAttribute(select_decode_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));   \
+      attr = true;                                                                                                             \
+    }                                                                                                                          \
+  }                                                                                                                            \
+  select_decode_kernel<NC><<<batch * chunks, SEL_BLOCK, parked_bytes, st>>>(vcls, vctr, vreg, locs, num_classes, chunks, rounds, \
+                                                                            thresh_ge, skip_below, lv, state, cand_count,    \
+                                                                            cand_loc, cand_score, cand_label, box4)
+  switch (num_classes) {
+    case 1: HN_SELECT_LAUNCH(1); break;
+    case 2: HN_SELECT_LAUNCH(2); break;
+    case 3: HN_SELECT_LAUNCH(3); break;
+    case 4: HN_SELECT_LAUNCH(4); break;
+    default: HN_SELECT_LAUNCH(0); break;
+  }
+#undef HN_SELECT_LAUNCH
   hn_count_launch();
   HN_LAUNCH_CHECK();
   return HN_OK;

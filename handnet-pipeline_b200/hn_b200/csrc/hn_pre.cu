@@ -9,7 +9,7 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------ T1
-constexpr int PRE_MAX_IMAGES = 32;
+constexpr int PRE_MAX_IMAGES = 64;
 struct PreParams {
   const float* img[PRE_MAX_IMAGES];
   int in_h[PRE_MAX_IMAGES], in_w[PRE_MAX_IMAGES], out_h[PRE_MAX_IMAGES], out_w[PRE_MAX_IMAGES];
@@ -147,6 +147,155 @@ __global__ void __launch_bounds__(512) preprocess_rows_kernel(const PreParams p,
       o.y = hn_pack_bf16((t2 - m2) * s2, 0.f);
     }
     dst_row[x * xs] = o;
+  }
+}
+
+// Row-pair variant (the default when the source rows are 16-byte aligned): one CTA walks `ppc` consecutive PAIRS of frame rows
+// of one image.  Per pair: (1) the four source rows the two canvas rows blend (3 colour planes each) arrive in shared memory
+// by cp.async, issued while the previous pair is being interpolated; (2) a vertical blend pass in shared memory that leaves,
+// per source column, the six blended values (row a: c0 c1 c2, row b: c0 c1 c2) side by side; (3) consecutive lanes interpolate
+// consecutive canvas pixels horizontally for BOTH rows of the pair from 2 x 3 eight-byte reads, in packed fp32x2 arithmetic,
+// and, in the paired frame layout of the direct stem ([rows/2][width][2 rows][4 ch]), write the pixel's two rows as one
+// 16-byte store (the one-row kernel wrote 8-byte halves of every 16 bytes, twice).  The horizontal source index and weight
+// of every canvas column are tabulated once per CTA.  Same arithmetic as preprocess_rows_kernel (vertical blend first, then
+// the horizontal one, then (t - mean) * (1 / std)).
+constexpr int PRE_T = 256;       // threads at most (the host picks a multiple of 32 that tiles the canvas width tightly)
+
+__device__ __forceinline__ void pre_cp16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(hn_smem_u32(dst)), "l"(src) : "memory");
+}
+
+template <bool PAIRED>
+__global__ void __launch_bounds__(PRE_T, 4)
+preprocess_pairs_kernel(const PreParams p, uint2* __restrict__ canvas, int pitch, int ppc, int first_pair, int npairs) {
+  extern __shared__ __align__(16) float sm[];
+  float* raw = sm;                    // [2 canvas rows][2 source rows][3 planes][pitch]
+  float* bl = sm + 12 * pitch;        // [pitch columns][row a: c0 c1 c2, row b: c0 c1 c2]: vertically blended
+  float2* xtab = reinterpret_cast<float2*>(sm + 18 * pitch);   // [canvas_w]: (source column x0, weight of x0 + 1)
+  const int b = blockIdx.z;
+  const int oh = p.out_h[b], ow = p.out_w[b];
+  const int ih = p.in_h[b], iw = p.in_w[b];
+  const int q = iw >> 2;
+  const int plane = ih * iw;
+  const float* base = p.img[b];
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int pr_begin = first_pair + blockIdx.x * ppc;
+  const int pr_end = min(pr_begin + ppc, first_pair + npairs);
+  if (pr_begin >= pr_end) return;
+  for (int x = tid; x < p.canvas_w; x += T) {
+    int x0 = 0, x1;
+    float l0, l1 = 0.f;
+    if (x < ow) bilinear_axis(x, iw, p.scale_x[b], x0, x1, l0, l1);
+    xtab[x] = make_float2(__int_as_float(x0), l1);
+  }
+  const float2 nm01 = make_float2(-p.mean[0], -p.mean[1]), nm20 = make_float2(-p.mean[2], -p.mean[0]), nm12 = make_float2(-p.mean[1], -p.mean[2]);
+  const float2 s01 = make_float2(p.inv_std[0], p.inv_std[1]), s20 = make_float2(p.inv_std[2], p.inv_std[0]), s12 = make_float2(p.inv_std[1], p.inv_std[2]);
+  const int iw1 = iw - 1;
+
+  // rows of a pair: liveness, vertical weights; the cp.async copies of its four source rows
+  bool live_a, live_b;
+  float wa, wb;                       // weight of the lower source row (y1) for canvas row a / b
+  auto issue = [&](int pr) {
+    int ya0 = 0, ya1 = 0, yb0 = 0, yb1 = 0;
+    float l0;
+    const int y = 2 * pr - p.pad_top;
+    live_a = y >= 0 && y < oh;
+    live_b = y + 1 >= 0 && y + 1 < oh;
+    wa = wb = 0.f;
+    if (live_a) bilinear_axis(y, ih, p.scale_y[b], ya0, ya1, l0, wa);
+    if (live_b) bilinear_axis(y + 1, ih, p.scale_y[b], yb0, yb1, l0, wb);
+    const float* ra0 = base + (size_t)ya0 * iw;
+    const float* ra1 = base + (size_t)ya1 * iw;
+    const float* rb0 = base + (size_t)yb0 * iw;
+    const float* rb1 = base + (size_t)yb1 * iw;
+    for (int it = tid; it < 3 * q; it += T) {
+      const int c = (it >= q) + (it >= 2 * q);
+      const int col = (it - c * q) * 4;
+      const int go = c * plane + col;
+      float* d = raw + c * pitch + col;
+      if (live_a) {
+        pre_cp16(d, ra0 + go);
+        pre_cp16(d + 3 * pitch, ra1 + go);
+      }
+      if (live_b) {
+        pre_cp16(d + 6 * pitch, rb0 + go);
+        pre_cp16(d + 9 * pitch, rb1 + go);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  issue(pr_begin);
+  for (int pr = pr_begin; pr < pr_end; ++pr) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                     // the pair's source rows are in; the previous pair has been written out
+    {
+      // vertical blend: a thread takes 4 source columns, all planes, both rows -> 24 consecutive floats of bl
+      const float2 wa1 = make_float2(wa, wa), wa0 = make_float2(1.f - wa, 1.f - wa);
+      const float2 wb1 = make_float2(wb, wb), wb0 = make_float2(1.f - wb, 1.f - wb);
+      for (int g = tid; g < q; g += T) {
+        float v[2][3][4];                                // [row a / b][plane][column]
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float* r = raw + c * pitch + g * 4;
+          float4 u0 = make_float4(0.f, 0.f, 0.f, 0.f), u1 = u0, u2 = u0, u3 = u0;
+          if (live_a) { u0 = *reinterpret_cast<const float4*>(r); u1 = *reinterpret_cast<const float4*>(r + 3 * pitch); }
+          if (live_b) { u2 = *reinterpret_cast<const float4*>(r + 6 * pitch); u3 = *reinterpret_cast<const float4*>(r + 9 * pitch); }
+          const float2 alo = __ffma2_rn(wa1, make_float2(u1.x, u1.y), __fmul2_rn(wa0, make_float2(u0.x, u0.y)));
+          const float2 ahi = __ffma2_rn(wa1, make_float2(u1.z, u1.w), __fmul2_rn(wa0, make_float2(u0.z, u0.w)));
+          const float2 blo = __ffma2_rn(wb1, make_float2(u3.x, u3.y), __fmul2_rn(wb0, make_float2(u2.x, u2.y)));
+          const float2 bhi = __ffma2_rn(wb1, make_float2(u3.z, u3.w), __fmul2_rn(wb0, make_float2(u2.z, u2.w)));
+          v[0][c][0] = alo.x; v[0][c][1] = alo.y; v[0][c][2] = ahi.x; v[0][c][3] = ahi.y;
+          v[1][c][0] = blo.x; v[1][c][1] = blo.y; v[1][c][2] = bhi.x; v[1][c][3] = bhi.y;
+        }
+        float4* d = reinterpret_cast<float4*>(bl + g * 24);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                    // two columns = 12 floats = three 16-byte stores
+          const int i = 2 * h;
+          d[3 * h + 0] = make_float4(v[0][0][i], v[0][1][i], v[0][2][i], v[1][0][i]);
+          d[3 * h + 1] = make_float4(v[1][1][i], v[1][2][i], v[0][0][i + 1], v[0][1][i + 1]);
+          d[3 * h + 2] = make_float4(v[0][2][i + 1], v[1][0][i + 1], v[1][1][i + 1], v[1][2][i + 1]);
+        }
+      }
+    }
+    __syncthreads();                                     // blended rows complete; the raw rows are free again
+    const bool la = live_a, lb = live_b;
+    if (pr + 1 < pr_end) issue(pr + 1);
+    const int fy = 2 * pr;
+    uint4* dst16 = nullptr;
+    uint2* dst8 = nullptr;
+    bool row_ok0 = true, row_ok1 = true;
+    if (PAIRED) {
+      dst16 = reinterpret_cast<uint4*>(canvas) + ((size_t)(p.batch_offset + b) * (p.pitch_h >> 1) + pr) * p.pitch_w + p.pad_left;
+    } else {
+      dst8 = canvas + ((size_t)(p.batch_offset + b) * p.pitch_h + fy) * p.pitch_w + p.pad_left;
+      row_ok0 = fy - p.pad_top >= 0 && fy - p.pad_top < p.canvas_h;
+      row_ok1 = fy + 1 - p.pad_top >= 0 && fy + 1 - p.pad_top < p.canvas_h;
+    }
+#pragma unroll 2
+    for (int x = tid; x < p.canvas_w; x += T) {
+      const float2 xc = xtab[x];
+      const float2 l11 = make_float2(xc.y, xc.y), l00 = make_float2(1.f - xc.y, 1.f - xc.y);
+      const int i0 = __float_as_int(xc.x);
+      const float2* p0 = reinterpret_cast<const float2*>(bl + i0 * 6);
+      const float2* p1 = reinterpret_cast<const float2*>(bl + min(i0 + 1, iw1) * 6);
+      float2 t01 = __ffma2_rn(l11, p1[0], __fmul2_rn(l00, p0[0]));     // row a: c0, c1
+      float2 t20 = __ffma2_rn(l11, p1[1], __fmul2_rn(l00, p0[1]));     // row a: c2; row b: c0
+      float2 t12 = __ffma2_rn(l11, p1[2], __fmul2_rn(l00, p0[2]));     // row b: c1, c2
+      t01 = __fmul2_rn(__fadd2_rn(t01, nm01), s01);
+      t20 = __fmul2_rn(__fadd2_rn(t20, nm20), s20);
+      t12 = __fmul2_rn(__fadd2_rn(t12, nm12), s12);
+      const bool in = x < ow;
+      uint2 oa = make_uint2(0u, 0u), ob = make_uint2(0u, 0u);
+      if (in && la) oa = make_uint2(hn_pack_bf16(t01.x, t01.y), hn_pack_bf16(t20.x, 0.f));
+      if (in && lb) ob = make_uint2(hn_pack_bf16(t20.y, t12.x), hn_pack_bf16(t12.y, 0.f));
+      if (PAIRED) {
+        dst16[x] = make_uint4(oa.x, oa.y, ob.x, ob.y);
+      } else {
+        if (row_ok0) dst8[x] = oa;
+        if (row_ok1) dst8[p.pitch_w + x] = ob;
+      }
+    }
   }
 }
 
@@ -359,10 +508,37 @@ static int preprocess_impl(const float* const* images_host, const int* in_h_host
     p.paired = paired;
     p.batch_offset = b0;
     int max_w = 0;
-    for (int i = 0; i < nb; ++i) max_w = p.in_w[i] > max_w ? p.in_w[i] : max_w;
+    bool aligned = true;                             // every source row starts on a 16-byte boundary
+    for (int i = 0; i < nb; ++i) {
+      max_w = p.in_w[i] > max_w ? p.in_w[i] : max_w;
+      aligned = aligned && (p.in_w[i] & 3) == 0 && (reinterpret_cast<uintptr_t>(p.img[i]) & 15) == 0;
+    }
     const int pitch = (max_w + 3) & ~3;
     const size_t staged_bytes = (size_t)3 * pitch * sizeof(float);
-    if (staged_bytes <= 48 * 1024) {
+    const size_t pair_bytes = (size_t)18 * pitch * sizeof(float) + (size_t)canvas_w * sizeof(float2);
+    static const bool use_pairs = !(getenv("HN_PRE_PAIRS") && atoi(getenv("HN_PRE_PAIRS")) == 0);
+    if (use_pairs && aligned && pair_bytes <= 200 * 1024) {
+      // frame rows 2k, 2k+1 that hold canvas rows: pairs first_pair .. first_pair + npairs - 1
+      const int first_pair = pad_top >> 1, npairs = ((pad_top + canvas_h - 1) >> 1) - first_pair + 1;
+      // pairs per CTA: long walks amortise the per-CTA set-up, but keep at least ~4 CTAs per SM slot in the grid
+      const long long total = (long long)npairs * nb;
+      int ppc = total >= 8 * 1776 ? 8 : (total >= 4 * 1776 ? 4 : 2);          // (64 VGA frames: 2 / 4 / 8 / 16 pairs -> 180 / 174 / 172 / 176 us)
+      if (const char* e = getenv("HN_PRE_PPC")) { const int v = atoi(e); if (v >= 1) ppc = v; }
+      dim3 grid(hn_div_up(npairs, ppc), 1, nb);
+      static const int thr_env = getenv("HN_PRE_THREADS") ? atoi(getenv("HN_PRE_THREADS")) : 0;
+      const int per_thread = hn_div_up(canvas_w, PRE_T);                              // pixels of a row per thread
+      int threads = (hn_div_up(canvas_w, per_thread) + 31) / 32 * 32;
+      if (thr_env >= 32 && thr_env <= PRE_T) threads = thr_env;
+      static bool attr_set = false;
+      if (!attr_set) {
+        HN_CHECK_CUDA(cudaFuncSetAttribute(preprocess_pairs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        HN_CHECK_CUDA(cudaFuncSetAttribute(preprocess_pairs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+      }
+      uint2* cv = reinterpret_cast<uint2*>(canvas_bf16);
+      if (paired) preprocess_pairs_kernel<true><<<grid, threads, pair_bytes, st>>>(p, cv, pitch, ppc, first_pair, npairs);
+      else preprocess_pairs_kernel<false><<<grid, threads, pair_bytes, st>>>(p, cv, pitch, ppc, first_pair, npairs);
+    } else if (staged_bytes <= 48 * 1024) {
       int threads = ((hn_div_up(canvas_w, 4) + 31) / 32) * 32;   // ~4 canvas pixels per thread
       threads = threads > 512 ? 512 : threads;
       preprocess_rows_kernel<<<dim3(1, canvas_h, nb), threads, staged_bytes, st>>>(p, reinterpret_cast<uint2*>(canvas_bf16),

@@ -457,6 +457,16 @@ class Levels:
         self.start_arr = (C.c_int * (self.n + 1))(*starts)
 
 
+def head_planes(t: torch.Tensor) -> torch.Tensor:
+    """A head tensor [B, locs, k] re-laid as fp32 channel planes [B][k][pitch] (pitch = locs rounded up to 32, so that every
+    plane starts 128-byte aligned), returned as the strided view [B, locs, k]: the layout the detector's output convolutions
+    write (hn_conv_desc.out_kind 2) and hn_fcos_decode_select streams with 16-byte loads."""
+    b, locs, k = t.shape
+    buf = torch.zeros((b, k, (locs + 31) // 32 * 32), dtype=torch.float32, device=t.device)
+    buf[:, :, :locs] = t.permute(0, 2, 1)
+    return buf[:, :, :locs].permute(0, 2, 1)
+
+
 def _head_strides(t: Optional[torch.Tensor]):
     """(pointer, image stride, location stride, channel stride) of a head tensor view [B, locs, k] in any layout."""
     if t is None:

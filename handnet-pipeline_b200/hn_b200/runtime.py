@@ -241,8 +241,10 @@ class FCOSPlan:
         self.locs = L
         # fused head outputs as fp32 channel PLANES [B][channel][locs] (hn_conv_desc.out_kind 2): coalesced stores in the
         # convolution epilogue, and the decode kernel streams just the planes it needs (cls, ctr) without padding bytes
-        self.cls_buf = torch.zeros((B, wts.cls_ld, L), dtype=torch.float32, device=device)
-        self.reg_buf = torch.zeros((B, wts.reg_ld, L), dtype=torch.float32, device=device)
+        # (plane pitch rounded up to 32 locations: every plane starts 128-byte aligned, 16-byte loads over 4 locations)
+        self.loc_pitch = (L + 31) // 32 * 32
+        self.cls_buf = torch.zeros((B, wts.cls_ld, self.loc_pitch), dtype=torch.float32, device=device)
+        self.reg_buf = torch.zeros((B, wts.reg_ld, self.loc_pitch), dtype=torch.float32, device=device)
         self.gn_stats = torch.zeros((2, 4, 3, B, 32, 2), dtype=torch.int64, device=device)    # fixed-point sums (ops.GN_FIX_SCALE)
         self.sel_ws = torch.empty(int(ops._lib.load().hn_fcos_select_workspace_bytes(B, L)), dtype=torch.uint8, device=device)
         self.nms_ws = ops.nms_workspace(B, L, device)
@@ -343,10 +345,10 @@ class FCOSExecutor:
                     ops.groupnorm_relu(o, st, 32, gamma, beta, GN_EPS)
                     x = o
                 if t == "cls":
-                    w.cls_out.run(x, relu=w.cls_relu, out_f32=pl.cls_buf, out_rows_per_image=pl.locs,
+                    w.cls_out.run(x, relu=w.cls_relu, out_f32=pl.cls_buf, out_rows_per_image=pl.loc_pitch,
                                   out_row_offset=pl.levels.starts[lvl], out_planar=True)
                 else:
-                    w.reg_out.run(x, relu=w.reg_relu, out_f32=pl.reg_buf, out_rows_per_image=pl.locs,
+                    w.reg_out.run(x, relu=w.reg_relu, out_f32=pl.reg_buf, out_rows_per_image=pl.loc_pitch,
                                   out_row_offset=pl.levels.starts[lvl], out_planar=True)
             return run
 
@@ -366,7 +368,7 @@ class FCOSExecutor:
                     xs = outs
                 oc, relu, buf = (w.cls_out, w.cls_relu, pl.cls_buf) if t == "cls" else (w.reg_out, w.reg_relu, pl.reg_buf)
                 ops.conv2d_levels(xs, oc.w, cout=oc.cout, ksize=oc.k, shift=oc.shift, relu=relu, out_f32=buf,
-                                  out_rows_per_image=pl.locs, out_row_offsets=pl.levels.starts[:nl], out_planar=True)
+                                  out_rows_per_image=pl.loc_pitch, out_row_offsets=pl.levels.starts[:nl], out_planar=True)
             return run
 
         if FUSE_LEVELS and len(pl.p) <= 3:
@@ -381,9 +383,9 @@ class FCOSExecutor:
     def head_views(self, pl: FCOSPlan):
         """The reference's head tensors [B, locs, k] as (strided) views of the channel-planar buffers."""
         c = self.wts.cls_cols
-        cv = lambda a, b: pl.cls_buf[:, a:b, :].permute(0, 2, 1)
+        cv = lambda a, b: pl.cls_buf[:, a:b, :pl.locs].permute(0, 2, 1)
         v = {"cls_logits": cv(*c["cls"]), "hand_lr": cv(*c["lr"]),
-             "bbox_regression": pl.reg_buf[:, 0:4, :].permute(0, 2, 1), "bbox_ctrness": pl.reg_buf[:, 4:5, :].permute(0, 2, 1)}
+             "bbox_regression": pl.reg_buf[:, 0:4, :pl.locs].permute(0, 2, 1), "bbox_ctrness": pl.reg_buf[:, 4:5, :pl.locs].permute(0, 2, 1)}
         if "contact" in c:
             v["hand_contact_state"] = cv(*c["contact"])
             v["hand_dxdy_relu"] = cv(*c["dxdy"])

@@ -199,7 +199,9 @@ int hn_groupnorm_relu(void* x, int n, int h, int w, int c, int halo, const int64
  * of sqrt(sigmoid(cls_c) * sigmoid(ctr)), label = first arg-max class (class 0 included), candidate when
  * score > score_thresh (a double, compared the way `scores > 0.7` is in the reference).  The sigmoids / square roots are
  * evaluated only where the outcome is open (a location whose centre-ness or largest class logit is below
- * logit(score_thresh^2) - 0.01 cannot pass).  Candidates are written per image in ascending location order:
+ * logit(score_thresh^2) - 0.01 cannot pass).  One kernel: every block of 1024 locations scores, counts, looks back over
+ * the counts of the blocks before it in the same image (one state word per block in `workspace`, cleared by a memset node
+ * in front of the kernel) and writes its survivors in place.  Candidates are written per image in ascending location order:
  *   cand_count[batch], cand_loc[batch][locs] (int32), cand_score[batch][locs] (fp32),
  *   cand_label[batch][locs] (int32), cand_box[batch][locs][4] (fp32, canvas pixels, NOT clipped). */
 int hn_fcos_decode_select(const float* cls_logits, int64_t cls_img_stride, int cls_loc_stride, int cls_chan_stride,

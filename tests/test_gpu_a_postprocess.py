@@ -67,8 +67,8 @@ def test_decode_select_channel_planes_equal_rows(ops):
     ho["cls_logits"][1] -= 8.0                       # an image in the sparse regime: almost everything is skipped
     ho["cls_logits"][1, ::97] += 10.0
     rows = {k: v.cuda() for k, v in ho.items()}
-    planar = {k: v.cuda().permute(0, 2, 1).contiguous().permute(0, 2, 1) for k, v in ho.items()}
-    assert planar["cls_logits"].stride(1) == 1 and planar["cls_logits"].stride(2) == lv.locs
+    planar = {k: ops.head_planes(v.cuda()) for k, v in ho.items()}
+    assert planar["cls_logits"].stride(1) == 1 and planar["cls_logits"].stride(2) == (lv.locs + 31) // 32 * 32
     a = ops.fcos_decode_select(rows["cls_logits"], rows["bbox_ctrness"], rows["bbox_regression"], 3, lv, 0.7)
     b = ops.fcos_decode_select(planar["cls_logits"], planar["bbox_ctrness"], planar["bbox_regression"], 3, lv, 0.7)
     torch.cuda.synchronize()
@@ -84,6 +84,26 @@ def test_decode_select_channel_planes_equal_rows(ops):
     for i in range(3):
         n = int(ca[i])
         assert torch.equal(ga["sides"][i, :n], gb["sides"][i, :n]) and torch.equal(ga["boxes"][i, :n], gb["boxes"][i, :n])
+
+
+def test_decode_select_large_batch_four_round_blocks(ops):
+    """From ~600 blocks on, a block takes four rounds of 1024 locations (loads of the next round in flight while it scores the
+    current one): same candidates as the one-round kernel a small batch gets, image by image, incl. the look-back over the
+    chunks of an image and the ragged last chunk."""
+    lv = ops.Levels([(50, 68), (25, 34), (13, 17)], (400, 544), (8, 16, 32))     # 4471 locations: 2 chunks of 4096
+    ho = stress_head_tensors(9, 4, lv.locs, 3, -0.35)
+    ho["cls_logits"][2] -= 6.0
+    small = {k: ops.head_planes(v.cuda()) for k, v in ho.items()}
+    big = {k: ops.head_planes(v.repeat(75, 1, 1).cuda()) for k, v in ho.items()}      # 300 images
+    a = ops.fcos_decode_select(small["cls_logits"], small["bbox_ctrness"], small["bbox_regression"], 3, lv, 0.7)
+    b = ops.fcos_decode_select(big["cls_logits"], big["bbox_ctrness"], big["bbox_regression"], 3, lv, 0.7)
+    torch.cuda.synchronize()
+    assert torch.equal(b["count"], a["count"].repeat(75)) and int(a["count"][0]) > 1500
+    for j in (0, 1, 2, 3, 150, 297, 298, 299):
+        i = j % 4
+        n = int(a["count"][i])
+        for k in ("loc", "score", "label", "box"):
+            assert torch.equal(a[k][i, :n], b[k][j, :n]), (k, j)
 
 
 def test_decode_select_strided_rows_and_empty(ops):

@@ -53,13 +53,13 @@ report("groupnorm+relu P3 x64", B * 100 * 136 * 256 * 2 * 2, timeit(lambda: ops.
 Bp = 256
 lv = ops.Levels([(100, 136), (50, 68), (25, 34)], (800, 1088), (8, 16, 32))
 ho = {k: v.cuda() for k, v in stress_head_tensors(31, 4, lv.locs, 3, -0.35).items()}
-ho = {k: v.repeat(Bp // 4, 1, 1).permute(0, 2, 1).contiguous().permute(0, 2, 1) for k, v in ho.items()}   # channel planes, as the detector writes them
+ho = {k: ops.head_planes(v.repeat(Bp // 4, 1, 1)) for k, v in ho.items()}   # channel planes, as the detector writes them
 cand = ops.fcos_decode_select(ho["cls_logits"], ho["bbox_ctrness"], ho["bbox_regression"], 3, lv, 0.7)
 ncand = int(cand["count"].sum())
 report("decode+score+select x256 (stress)", Bp * lv.locs * (3 + 1 + 4) * 4 + ncand * 28,
        timeit(lambda: ops.fcos_decode_select(ho["cls_logits"], ho["bbox_ctrness"], ho["bbox_regression"], 3, lv, 0.7)),
        f"{ncand // Bp} candidates/frame")
-lo = {k: v.clone() for k, v in ho.items()}; lo["cls_logits"] -= 3.0
+lo = dict(ho); lo["cls_logits"] = ops.head_planes(ho["cls_logits"] - 3.0)
 c2 = ops.fcos_decode_select(lo["cls_logits"], lo["bbox_ctrness"], lo["bbox_regression"], 3, lv, 0.7)
 report("decode+score+select x256 (sparse)", Bp * lv.locs * (3 + 1) * 4 + int(c2["count"].sum()) * 44,
        timeit(lambda: ops.fcos_decode_select(lo["cls_logits"], lo["bbox_ctrness"], lo["bbox_regression"], 3, lv, 0.7)),
