@@ -34,7 +34,7 @@ class ConvDesc(C.Structure):
         ("gn_stats", _c_p), ("gn_groups", _i),
         ("block_n", _i), ("cluster", _i), ("debug", _i),
         ("splitk_ws", _c_p), ("splitk_ws_bytes", _i64), ("splitk_counters", _c_p), ("splitk_counters_len", _i), ("splits", _i),
-        ("trace", _c_p), ("stem_pitch_h", _i), ("stem_pitch_w", _i),
+        ("trace", _c_p), ("stem_pitch_h", _i), ("stem_pitch_w", _i), ("stem_window", _i),
     ]
 
 

@@ -98,6 +98,7 @@ struct ConvParams {
   // direct 7x7/2 stem: an M tile is 128 consecutive output columns of one output row; the A tensor map is the
   // overlapping-stride patch view of the canvas (build_conv)
   int stem_tpr, stem_h;                     // tiles per output row (0 = ordinary convolution), output rows per image
+  int stem_win, stem_tile_w;                // window stem (see build_conv): output columns per tile (125; row-pair stem: 128)
   int epi_alt;                              // epilogue: the two warps of a lane quarter take alternate TILES (all chunks
                                             // of their tile) instead of alternate chunks of the same tile
   int m_tiles, n_tiles;
@@ -365,6 +366,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         tma = si == 0 ? &tm_a : (si == 1 ? &tm_a1 : &tm_a2);
       }
       int info = p.grp_info[g], shift = gshift[g];
+      if constexpr (RB) {
+        if (p.stem_win) {
+          // window stem: ONE box per tile -- 8 canvas rows x 256 pixels from (2*ox0 - 4, 2*oy - 3) of the tile's image
+          const int row = mt / p.stem_tpr;
+          const int ox0 = (mt - row * p.stem_tpr) * p.stem_tile_w;
+          const int sn = row / p.stem_h, oy = row - sn * p.stem_h;
+          hn_mbar_wait(&a_empty[a_stage], a_phase ^ 1);
+          if (hn_elect_one()) {
+            hn_mbar_expect_tx(&a_full[a_stage], (uint32_t)a_box_bytes);
+            hn_tma_load_3d(a_ring + a_stage * a_slot_bytes, &tm_a, &a_full[a_stage], 2 * ox0 - 4, 2 * oy - 3, sn);
+          }
+          if (++a_stage == na) { a_stage = 0; a_phase ^= 1; }
+          continue;
+        }
+      }
       if constexpr (UNI) {
         int st_n = 0, st_oy = 0, st_ox = 0;                  // stem: image, output row, first output column of the tile
         if (p.stem_tpr > 0) {
@@ -571,6 +587,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
               hn_umma_commit_addr<1>(ea);
               if (last) hn_umma_commit_addr<1>(tf);
             }
+          } else if (RB && p.stem_win) {
+            // window stem: kernel row ky of the box is an un-swizzled K-major operand of 32 K values (8 pixels x 4 channels)
+            // whose rows (output pixels) start 16 bytes apart: LBO = 16 (the descriptor's low word already says so), SBO =
+            // 128.  Weights: k = ky * 32 + px * 4 + ch, i.e. k-block ky / 2, bytes (ky & 1) * 64 + 32 * s of its 128-byte rows.
+            const uint32_t sa = a_desc0 + a_stage * A_SLOT_D;
+            const uint64_t a_hi = (uint64_t(128 >> 4) << 32) | (uint64_t(1) << 46);
+            const uint32_t ea = hn_smem_u32(&a_empty[a_stage]), tf = hn_smem_u32(&tmem_full[buf]);
+            hn_tc_fence_after();
+            if (hn_elect_one()) {
+#pragma unroll
+              for (int ky = 0; ky < 8; ++ky) {
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+                  hn_umma_bf16(d_tmem, a_hi | (sa + ky * (2048 >> 4) + ks * 2),
+                               desc_hi | (b_desc0 + (ky >> 1) * B_SLOT_D + (ky & 1) * 4 + ks * 2), idesc, (ky | ks) ? 1u : accumulate);
+              }
+              hn_umma_commit_addr<1>(ea);
+              if (last) hn_umma_commit_addr<1>(tf);
+            }
           } else if constexpr (RB) {
             // resident weights, one A box per group: poll once, issue the group's (up to three) taps as one burst
             const uint32_t ea = hn_smem_u32(&a_empty[a_stage]), tf = hn_smem_u32(&tmem_full[buf]);
@@ -703,8 +738,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         const int row = mt / p.stem_tpr;
         img = row / p.stem_h;
         h = row - img * p.stem_h;
-        w = (mt - row * p.stem_tpr) * BLOCK_M + quarter * 32 + lane;
-        interior = w < g_wp && img < g_nimg;
+        w = (mt - row * p.stem_tpr) * p.stem_tile_w + quarter * 32 + lane;
+        interior = quarter * 32 + lane < p.stem_tile_w && w < g_wp && img < g_nimg;
       } else if (m < g_rows) {
         img = (int)((__umulhi((uint32_t)m, div_img_mul) + (uint32_t)m) >> div_img_sh);
         const int rem = m - img * (g_hp * g_wp);
@@ -1094,14 +1129,15 @@ PFN_encodeTiled get_encode() {
 }
 
 int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-             const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+             const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B,
+             CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     hn_set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
     return HN_ERR_CUDA;
   }
   cuuint32_t ones[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides_bytes, box, ones,
+  CUresult r = enc(m, dtype, rank, const_cast<void*>(ptr), dims, strides_bytes, box, ones,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1281,19 +1317,39 @@ int build_conv(const hn_conv_desc* d, int force_bn, int total_m_tiles, BuiltConv
              d->dilation);
   p.m_tiles = hn_div_up(p.rows, BLOCK_M);
   const bool stem = d->stem_pitch_w > 0;
+  const bool stem_win = stem && d->stem_window != 0;
   if (stem) {
     HN_REQUIRE(!total_m_tiles && d->kh == 1 && d->stride == 1 && d->cin == 256 && d->halo_in == 0 && d->in_phases == 1 &&
                    d->cout_pad <= 128 && !d->res && !d->gn_stats && !d->splitk_ws,
                "hn_conv2d_bf16: a direct stem is a plain 1x1-over-patches convolution with cin = 256, cout_pad <= 128");
-    HN_REQUIRE(d->stem_pitch_h >= 2 * d->h + 6 && d->stem_pitch_h % 2 == 0 && d->stem_pitch_w >= 2 * d->w + 8,
-               "hn_conv2d_bf16: stem frame %dx%d too small for a %dx%d output (needs >= %dx%d, even height)",
-               d->stem_pitch_h, d->stem_pitch_w, d->h, d->w, 2 * d->h + 6, 2 * d->w + 8);
-    p.stem_tpr = hn_div_up(d->w, BLOCK_M);
+    if (stem_win) {
+      // Window stem: `in` is the plain row-major canvas [n][H][W][4] bf16 (8 bytes per pixel), no frame.  For output pixel
+      // (oy, ox) kernel row ky reads the 8 pixels 2*ox - 4 .. 2*ox + 3 of canvas row 2*oy - 3 + ky: 64 bytes that start 16
+      // bytes after those of ox - 1.  In the UN-SWIZZLED K-major operand layout element (row r, 16-byte K chunk j) lives at
+      // start + 16 * (r % 8) + SBO * (r / 8) + LBO * j; with SBO = 128 and LBO = 16 that is start + 16 * r + 16 * j, i.e. the
+      // im2col matrix of a kernel row IS the canvas row (tools/umma_overlap_test.cu: tcgen05.mma reads overlapping core
+      // matrices correctly).  One TMA box {256 pixels, 8 rows} = 8 row requests of 2 KB brings everything a tile of 125 output
+      // pixels needs (the row-pair stem: 512 requests of 128 B and 4x the bytes; it was bound by exactly that); borders are
+      // TMA zero fill.  Accumulator rows 125..127 of a tile read into the next kernel row and are not stored.
+      HN_REQUIRE(d->cout_pad == 64 && d->cout == 64, "hn_conv2d_bf16: the window stem has 64 output channels");
+      HN_REQUIRE((d->stem_pitch_h + 1) / 2 == d->h && (d->stem_pitch_w + 1) / 2 == d->w && d->stem_pitch_w % 2 == 0 &&
+                     reinterpret_cast<uintptr_t>(d->in) % 16 == 0,
+                 "hn_conv2d_bf16: window stem: canvas %dx%d (even width, 16-byte aligned) does not give a %dx%d output",
+                 d->stem_pitch_h, d->stem_pitch_w, d->h, d->w);
+      p.stem_win = 1;
+      p.stem_tile_w = 125;
+    } else {
+      HN_REQUIRE(d->stem_pitch_h >= 2 * d->h + 6 && d->stem_pitch_h % 2 == 0 && d->stem_pitch_w >= 2 * d->w + 8,
+                 "hn_conv2d_bf16: stem frame %dx%d too small for a %dx%d output (needs >= %dx%d, even height)",
+                 d->stem_pitch_h, d->stem_pitch_w, d->h, d->w, 2 * d->h + 6, 2 * d->w + 8);
+      p.stem_tile_w = BLOCK_M;
+    }
+    p.stem_tpr = hn_div_up(d->w, p.stem_tile_w);
     p.stem_h = d->h;
     p.m_tiles = d->n * d->h * p.stem_tpr;
   }
   const int sched_m_tiles = total_m_tiles > 0 ? total_m_tiles : p.m_tiles;     // tiles the launch spreads over the SMs
-  int bn = force_bn ? force_bn
+  int bn = stem_win ? 64 : force_bn ? force_bn
                     : (d->block_n ? d->block_n
                                   : pick_block_n(d->cout_pad, sched_m_tiles, p.num_taps * p.cin_chunks, d->gn_stats ? 32 : 16));
   HN_REQUIRE((bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256) && d->cout_pad % bn == 0,
@@ -1306,8 +1362,8 @@ int build_conv(const hn_conv_desc* d, int force_bn, int total_m_tiles, BuiltConv
   // narrow N tile whose weights fit next to >= 4 A slots and there are enough tiles per CTA to amortise the load
   const int k_blocks_total = p.num_taps * p.cin_chunks;
   const long long b_bytes = (long long)k_blocks_total * bn * BLOCK_K * 2;
-  bool rb = p.n_tiles == 1 && bn <= 64 && b_bytes <= PIPE_BYTES_MAX - 4 * A_SLOT_BYTES &&
-            sched_m_tiles >= 2 * hn_num_sms() && !(d->debug & 16) && !stem;
+  bool rb = (p.n_tiles == 1 && bn <= 64 && b_bytes <= PIPE_BYTES_MAX - 4 * A_SLOT_BYTES &&
+             sched_m_tiles >= 2 * hn_num_sms() && !(d->debug & 16) && !stem) || stem_win;
   const bool uni = bn <= 128 && !rb;      // unified stages (must match the kernel's constexpr UNI)
   const bool rb3 = rb && d->kh == 3 && d->stride == 1 && !(d->debug & 32) &&
                    PIPE_BYTES_MAX - b_bytes >= 2 * 3 * A_SLOT_BYTES && p.rows > 2 * d->dilation * p.wp;
@@ -1373,8 +1429,8 @@ int build_conv(const hn_conv_desc* d, int force_bn, int total_m_tiles, BuiltConv
       }
     }
   }
-  p.a_box_bytes = box_rows * BLOCK_K * 2;
-  p.k_steps = (uni && p.uni_chunk_step > 1) ? hn_div_up(p.cin_chunks, p.uni_chunk_step) : p.n_groups * p.cin_chunks;
+  p.a_box_bytes = stem_win ? 8 * 2048 : box_rows * BLOCK_K * 2;
+  p.k_steps = stem_win ? 1 : (uni && p.uni_chunk_step > 1) ? hn_div_up(p.cin_chunks, p.uni_chunk_step) : p.n_groups * p.cin_chunks;
   if (uni) {
     p.uni_plane_bytes = box_rows * BLOCK_K * 2;
     p.uni_a_bytes = a_planes * p.uni_plane_bytes;
@@ -1509,7 +1565,15 @@ int build_conv(const hn_conv_desc* d, int force_bn, int total_m_tiles, BuiltConv
   out->pair = pair;
   CUtensorMap& ta = out->ta;
   CUtensorMap& tb = out->tb;
-  if (stem) {
+  if (stem_win) {
+    // one element = one pixel (4 bf16 channels = 8 bytes): dims (W, H, n), box {256 pixels, 8 rows, 1}, dense in shared memory
+    const cuuint64_t pw = (cuuint64_t)d->stem_pitch_w, ph = (cuuint64_t)d->stem_pitch_h;
+    const cuuint64_t dims[3] = {pw, ph, (cuuint64_t)d->n};
+    const cuuint64_t strides[2] = {pw * 8, ph * pw * 8};
+    const cuuint32_t box[3] = {256, 8, 1};
+    int rc = make_map(&ta, d->in, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_DATA_TYPE_UINT64);
+    if (rc) return rc;
+  } else if (stem) {
     // Patch view of the zero-framed canvas.  The frame stores its rows in PAIRS, [n][ph/2][pw][2 rows][4 ch] (16 bytes per
     // column), so that kernel rows 2j and 2j+1 of output pixel (oy, ox) -- 8 pixels x 2 rows x 4 channels = 64 elements
     // -- are ONE contiguous 128-byte run starting at row pair oy + j, column 2*ox:

@@ -83,6 +83,26 @@ class StemFrame:
         return self
 
 
+class StemCanvas:
+    """Plain row-major 4-channel bf16 canvas [n, hc, wc, 4] of the WINDOW stem (hn_conv_desc.stem_window): no frame, the
+    convolution's TMA loads zero-fill the borders."""
+
+    __slots__ = ("t", "n", "hc", "wc", "oh", "ow")
+
+    def __init__(self, n: int, canvas_hw: Tuple[int, int], device="cuda"):
+        self.n, (self.hc, self.wc) = n, canvas_hw
+        assert self.wc % 2 == 0, "the window stem needs an even canvas width (16-byte row pitch)"
+        self.oh, self.ow = (canvas_hw[0] + 1) // 2, (canvas_hw[1] + 1) // 2
+        self.t = torch.zeros((n, self.hc, self.wc, 4), dtype=BF16, device=device)
+
+    def canvas(self) -> torch.Tensor:
+        return self.t
+
+    def set_canvas(self, x: torch.Tensor) -> "StemCanvas":
+        self.t.copy_(x.to(BF16))
+        return self
+
+
 class PhaseAct:
     """Phase-split haloed NHWC bf16: t[4, n, h2 + 2*halo, w2 + 2*halo, c], phase = (y & 1) * 2 + (x & 1),
     (h2, w2) = ceil((h, w) / 2).  Input format of the stride-2 convolutions."""
@@ -140,16 +160,17 @@ def pack_conv_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None) -> t
     return tile_k(out)
 
 
-def pack_stem_weight(w: torch.Tensor, k_pad: int) -> torch.Tensor:
+def pack_stem_weight(w: torch.Tensor, k_pad: int, order: str = "pairs") -> torch.Tensor:
     """7x7 stem OIHW (cin = 3, 4 or 1) -> bf16 [cout_pad][k_pad] in the K order of hn_im2col_7x7s2 / the direct stem:
-    C = 1 (depth): k = r*8 + px;  C = 4 (RGB or RGBD canvas): k = j*64 + px*8 + rr*4 + ch with kernel row r = 2j + rr;
+    C = 1 (depth): k = r*8 + px;  C = 4 (RGB or RGBD canvas): order "pairs" (row-pair frame, StemFrame): k = j*64 + px*8 +
+    rr*4 + ch with kernel row r = 2j + rr; order "window" (plain canvas, StemCanvas): k = r*32 + px*4 + ch.
     px = 0, r = 7 and (for RGB) ch = 3 carry zero weights."""
     cout, cin, kh, kw = w.shape
-    assert (kh, kw) == (7, 7) and (cin, k_pad) in ((3, 256), (4, 256), (1, 64))
+    assert (kh, kw) == (7, 7) and (cin, k_pad) in ((3, 256), (4, 256), (1, 64)) and order in ("pairs", "window")
     c = 4 if cin >= 3 else 1
     m = torch.zeros((cout, 8, 8, c), dtype=torch.float32, device=w.device)
     m[:, :7, 1:, :cin] = w.detach().float().permute(0, 2, 3, 1)
-    if c == 4:
+    if c == 4 and order == "pairs":
         # 4-channel canvas: a k-block is two kernel rows interleaved per pixel, k = j*64 + px*8 + rr*4 + ch (r = 2j + rr),
         # the order in which the row-pair frame holds them contiguously
         m = m.view(cout, 4, 2, 8, c).permute(0, 1, 3, 2, 4)
@@ -310,6 +331,10 @@ def _conv_desc(x, weight: torch.Tensor, *, cout: int, ksize: int, stride: int = 
         assert stride == 1 and ksize == 1
         d.in_, d.n, d.h, d.w, d.cin, d.halo_in, d.in_phases = x.t.data_ptr(), x.n, x.oh, x.ow, 256, 0, 1
         d.stem_pitch_h, d.stem_pitch_w = x.fh, x.fw
+    elif isinstance(x, StemCanvas):
+        assert stride == 1 and ksize == 1
+        d.in_, d.n, d.h, d.w, d.cin, d.halo_in, d.in_phases = x.t.data_ptr(), x.n, x.oh, x.ow, 256, 0, 1
+        d.stem_pitch_h, d.stem_pitch_w, d.stem_window = x.hc, x.wc, 1
     elif isinstance(x, PhaseAct):
         assert stride == 2
         d.in_, d.n, d.h, d.w, d.cin, d.halo_in, d.in_phases = x.t.data_ptr(), x.n, x.h2, x.w2, x.c, x.halo, 4

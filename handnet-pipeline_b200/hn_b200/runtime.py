@@ -94,6 +94,8 @@ FUSE_LEVELS = True          # FCOS towers / output convolutions / GroupNorm: ONE
                             # A/B timing and the equality test (outputs are bit-identical either way)
 import os as _os
 POSE_PRIORITY = _os.environ.get("HN_POSE_PRIO", "high")      # priority of the pose stream relative to the detect stream
+STEM_WINDOW = _os.environ.get("HN_STEM_WINDOW", "1") != "0"    # detector stem: plain canvas + window descriptors (0: row-pair frame)
+DET_CTA_CAP = int(_os.environ.get("HN_DET_CTAS", "0"))       # CTAs per detector convolution launch (0 = all SMs): leaves SMs to the pose stage
 POSE_CTA_CAP = int(_os.environ.get("HN_POSE_CTAS", "0"))     # CTAs per pose-net convolution launch (0 = all SMs)
 POSE_PDL = _os.environ.get("HN_POSE_PDL", "1") != "0"        # programmatic dependent launch inside the pose stage
 DET_PDL = _os.environ.get("HN_DET_PDL", "1") != "0"
@@ -164,7 +166,7 @@ class FCOSWeights:
         bn = lambda p: bn_affine(g(p + ".weight"), g(p + ".bias"), g(p + ".running_mean"), g(p + ".running_var"))
         b = "backbone.body."
         s, sh = bn(b + "bn1")
-        self.stem_w = ops.pack_stem_weight(g(b + "conv1.weight"), STEM_K_RGB)
+        self.stem_w = ops.pack_stem_weight(g(b + "conv1.weight"), STEM_K_RGB, order="window" if STEM_WINDOW else "pairs")
         self.stem_scale, self.stem_shift = s, sh
         self.blocks: List[List[Dict[str, ConvLayer]]] = []
         for li, nblocks in enumerate((3, 4, 6, 3), start=1):
@@ -221,8 +223,9 @@ class FCOSPlan:
         assert hc % 32 == 0 and wc % 32 == 0
         B = batch
         self.batch, self.canvas_hw = B, canvas_hw
-        # zero-framed canvas: the stem convolution gathers its 7x7 patches straight from it (no im2col buffer)
-        self.frame = ops.StemFrame(B, (hc, wc), device)
+        # the stem convolution gathers its 7x7 patches straight from the canvas (no im2col buffer): a plain row-major canvas
+        # read through window descriptors, or (HN_STEM_WINDOW=0) the zero-framed row-pair canvas of rounds 1-2
+        self.frame = ops.StemCanvas(B, (hc, wc), device) if STEM_WINDOW else ops.StemFrame(B, (hc, wc), device)
         self.canvas = self.frame.t            # (device handle for the chain launcher; read pixels with frame.canvas())
         h1, w1 = hc // 2, wc // 2
         self.stem = Act(B, h1, w1, 64, 0, device)
@@ -417,7 +420,10 @@ class FCOSExecutor:
         hc = int(math.ceil(max(s[0] for s in sizes) / 32.0) * 32)
         wc = int(math.ceil(max(s[1] for s in sizes) / 32.0) * 32)
         pl = self.plan(len(images), (hc, wc), dev)
-        ops.preprocess(images, sizes, (hc, wc), m.image_mean, m.image_std, frame=pl.frame.t)
+        if isinstance(pl.frame, ops.StemCanvas):
+            ops.preprocess(images, sizes, (hc, wc), m.image_mean, m.image_std, canvas=pl.frame.t)
+        else:
+            ops.preprocess(images, sizes, (hc, wc), m.image_mean, m.image_std, frame=pl.frame.t)
         self.backbone_heads(pl)
         # resize_boxes ratios are float32 tensor divisions in the reference (fcos_utils/fcos.py:771-776)
         f32 = torch.float32
@@ -829,9 +835,11 @@ class GraphedHandNet:
         global PLAN_SLOT
         saved, PLAN_SLOT = PLAN_SLOT, self.slot
         try:
+            ops.conv_cta_cap(DET_CTA_CAP)
             ops.conv_pdl(DET_PDL)
             det, crops, has, depth_batch = self.net.detect_crop_device(self.images, self.depth, out=self._views(self.hand_d))
         finally:
+            ops.conv_cta_cap(0)
             ops.conv_pdl(True)
             PLAN_SLOT = saved
         self.det = det

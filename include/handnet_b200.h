@@ -129,6 +129,12 @@ typedef struct hn_conv_desc {
    * contiguous 128-byte run of the frame.  TMA gathers the runs straight from the frame with an overlapping-stride
    * tensor map. */
   int stem_pitch_h, stem_pitch_w;
+  /* 1: WINDOW stem (the default of the detector): `in` is the plain row-major canvas bf16 [n][stem_pitch_h][stem_pitch_w][4]
+   * without any frame (stem_pitch_w even, (stem_pitch_h + 1) / 2 == h, (stem_pitch_w + 1) / 2 == w, cout = cout_pad = 64);
+   * borders are zero-filled by TMA.  Weights: pack_stem_weight(..., order="window"), k = ky * 32 + px * 4 + ch.  One TMA box
+   * of 8 canvas rows x 256 pixels serves a tile of 125 output pixels: the im2col matrix of a kernel row is the canvas row
+   * itself, read through an un-swizzled UMMA descriptor whose rows start 16 bytes apart (overlapping core matrices). */
+  int stem_window;
 } hn_conv_desc;
 int hn_conv2d_bf16(const hn_conv_desc* desc, void* stream);
 

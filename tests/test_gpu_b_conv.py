@@ -311,6 +311,38 @@ def test_stem_direct_from_framed_canvas(ops, n, h, w):
     assert torch.equal(stem.t, stem2.t), "direct stem and im2col + GEMM must agree exactly"
 
 
+@pytest.mark.parametrize("n,h,w", [(2, 64, 96), (1, 96, 320), (3, 32, 544), (2, 50, 250), (1, 800, 1088)])
+def test_stem_window_from_plain_canvas(ops, n, h, w):
+    """backbone.body.conv1 + FrozenBN + ReLU straight from the PLAIN row-major canvas: the im2col matrix of a kernel row is
+    the canvas row itself, read through an un-swizzled UMMA descriptor whose rows start 16 bytes apart (stem_window); one
+    TMA box of 8 rows x 256 pixels per tile of 125 output pixels, borders zero-filled by TMA.  == F.conv2d(stride 2,
+    padding 3) and == the row-pair frame stem / im2col + GEMM path bit for bit (same products, same fp32 accumulation
+    order inside the tensor core is not guaranteed across K orders: compared to bf16 rounding)."""
+    g = torch.Generator().manual_seed(16)
+    canvas = torch.zeros(n, h, w, 4)
+    canvas[..., :3] = rand(g, n, h, w, 3)
+    wt = rand(g, 64, 3, 7, 7, scale=0.08)
+    scale = 0.5 + torch.rand(64, generator=g)
+    shift = 0.2 * torch.randn(64, generator=g)
+    x_nchw = canvas[..., :3].permute(0, 3, 1, 2).contiguous()
+    conv = q(F.relu(F.conv2d(x_nchw, wt, stride=2, padding=3) * scale[None, :, None, None] + shift[None, :, None, None]))
+    cv = ops.StemCanvas(n, (h, w), DEV).set_canvas(canvas.to(torch.bfloat16).cuda())
+    stem = ops.Act(n, cv.oh, cv.ow, 64, 0, DEV)
+    stem.t.fill_(-7.0)
+    ops.conv2d(cv, ops.pack_stem_weight(wt.cuda(), 256, order="window"), cout=64, ksize=1, scale=scale.cuda(), shift=shift.cuda(),
+               relu=True, out=stem)
+    torch.cuda.synchronize()
+    close_bf16(stem.to_nchw().cpu(), conv, "window stem conv")
+    if h % 2 == 0:
+        frame = ops.StemFrame(n, (h, w), DEV)
+        frame.set_canvas(canvas.to(torch.bfloat16))
+        stem2 = ops.Act(n, h // 2, w // 2, 64, 0, DEV)
+        ops.conv2d(frame, ops.pack_stem_weight(wt.cuda(), 256), cout=64, ksize=1, scale=scale.cuda(), shift=shift.cuda(), relu=True,
+                   out=stem2)
+        torch.cuda.synchronize()
+        close_bf16(stem.to_nchw().cpu(), stem2.to_nchw().cpu(), "window stem vs row-pair stem")
+
+
 def test_stem_fp32_depth_one_channel(ops):
     """A2J stem: one depth channel expanded to three == weights summed over Cin (a2j/a2j.py:197-199)."""
     g = torch.Generator().manual_seed(14)
