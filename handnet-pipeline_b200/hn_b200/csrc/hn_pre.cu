@@ -395,50 +395,91 @@ struct GnLevels {
   int block_begin[GN_MAX_LEVELS + 1];
   int n_levels;
 };
-__global__ void __launch_bounds__(256)
+// (Round 2: one thread per 16 bytes, (a, b) of all channels rebuilt in double arithmetic by every block of 32 pixels and read
+// from shared memory per element, row / column by division per element: ~120 warp instructions per 32 elements, 3.5 TB/s,
+// instruction-bound.  Now: statistics once per group and block, coefficients in registers, one pixel per warp step: 4.2 TB/s,
+// what a copy of the same 153 MB reaches under the same protocol.)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 4)
 groupnorm_relu_kernel(const __grid_constant__ GnLevels lv, int c, int halo, int groups, int group_size,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int pixels_per_block) {
   __shared__ float sa[GN_MAX_C], sb[GN_MAX_C];
-  const int b = blockIdx.x;
-  const int l = (lv.n_levels > 2 && b >= lv.block_begin[2]) ? 2 : ((lv.n_levels > 1 && b >= lv.block_begin[1]) ? 1 : 0);
-  const int rem_b = b - lv.block_begin[l];
-  const int img = rem_b / lv.blocks_per_image[l], pb = rem_b - img * lv.blocks_per_image[l];
-  const int h = lv.h[l], w = lv.w[l];
-  uint4* __restrict__ x = lv.x[l];
-  const long long* __restrict__ stats = lv.stats[l];
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    const int g = ch / group_size;
-    const double cnt = (double)h * (double)w * (double)group_size;
-    const double s = (double)stats[((size_t)img * groups + g) * 2] * (1.0 / 16777216.0);
-    const double q = (double)stats[((size_t)img * groups + g) * 2 + 1] * (1.0 / 16777216.0);
-    const double mean = s / cnt;
-    double var = q / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float a = rstd * __ldg(gamma + ch);
-    sa[ch] = a;
-    sb[ch] = __ldg(beta + ch) - (float)mean * a;
-  }
-  __syncthreads();
-  const int c8 = c >> 3;
-  const int hp = h + 2 * halo, wp = w + 2 * halo;
-  const int total = h * w;
-  const int p0 = pb * pixels_per_block;
-  const int p1 = min(total, p0 + pixels_per_block);
-  const int items = (p1 - p0) * c8;
-  for (int i = threadIdx.x; i < items; i += blockDim.x) {
-    const int pix = p0 + i / c8;
-    const int cg = i - (i / c8) * c8;
-    const int yy = pix / w, xx = pix - yy * w;
-    uint4* ptr = x + (((size_t)img * hp + yy + halo) * wp + xx + halo) * c8 + cg;
-    uint4 v = *ptr;
-    const float* a = sa + cg * 8;
-    const float* b = sb + cg * 8;
-    v.x = hn_pack_bf16(fmaxf(hn_bf16_lo(v.x) * a[0] + b[0], 0.f), fmaxf(hn_bf16_hi(v.x) * a[1] + b[1], 0.f));
-    v.y = hn_pack_bf16(fmaxf(hn_bf16_lo(v.y) * a[2] + b[2], 0.f), fmaxf(hn_bf16_hi(v.y) * a[3] + b[3], 0.f));
-    v.z = hn_pack_bf16(fmaxf(hn_bf16_lo(v.z) * a[4] + b[4], 0.f), fmaxf(hn_bf16_hi(v.z) * a[5] + b[5], 0.f));
-    v.w = hn_pack_bf16(fmaxf(hn_bf16_lo(v.w) * a[6] + b[6], 0.f), fmaxf(hn_bf16_hi(v.w) * a[7] + b[7], 0.f));
-    *ptr = v;
+  __shared__ float s_mean[GN_MAX_C], s_rstd[GN_MAX_C];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int blk = blockIdx.x; blk < lv.block_begin[lv.n_levels]; blk += gridDim.x) {
+    const int l = (lv.n_levels > 2 && blk >= lv.block_begin[2]) ? 2 : ((lv.n_levels > 1 && blk >= lv.block_begin[1]) ? 1 : 0);
+    const int rem_b = blk - lv.block_begin[l];
+    const int img = rem_b / lv.blocks_per_image[l], pb = rem_b - img * lv.blocks_per_image[l];
+    const int h = lv.h[l], w = lv.w[l];
+    uint4* __restrict__ x = lv.x[l];
+    const long long* __restrict__ stats = lv.stats[l];
+    // mean / rstd of the image's groups (double arithmetic on the fixed-point sums: one thread per group) ...
+    for (int g = threadIdx.x; g < groups; g += THREADS) {
+      const double cnt = (double)h * (double)w * (double)group_size;
+      const double s = (double)stats[((size_t)img * groups + g) * 2] * (1.0 / 16777216.0);
+      const double q = (double)stats[((size_t)img * groups + g) * 2 + 1] * (1.0 / 16777216.0);
+      const double mean = s / cnt;
+      double var = q / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+      s_mean[g] = (float)mean;
+    }
+    __syncthreads();
+    const int c8 = c >> 3;
+    const int hp = h + 2 * halo, wp = w + 2 * halo;
+    const int p0 = pb * pixels_per_block;
+    const int p1 = min(h * w, p0 + pixels_per_block);
+    auto relu_affine = [](uint4 v, const float* a, const float* b) {
+      v.x = hn_pack_bf16(fmaxf(hn_bf16_lo(v.x) * a[0] + b[0], 0.f), fmaxf(hn_bf16_hi(v.x) * a[1] + b[1], 0.f));
+      v.y = hn_pack_bf16(fmaxf(hn_bf16_lo(v.y) * a[2] + b[2], 0.f), fmaxf(hn_bf16_hi(v.y) * a[3] + b[3], 0.f));
+      v.z = hn_pack_bf16(fmaxf(hn_bf16_lo(v.z) * a[4] + b[4], 0.f), fmaxf(hn_bf16_hi(v.z) * a[5] + b[5], 0.f));
+      v.w = hn_pack_bf16(fmaxf(hn_bf16_lo(v.w) * a[6] + b[6], 0.f), fmaxf(hn_bf16_hi(v.w) * a[7] + b[7], 0.f));
+      return v;
+    };
+    if (c8 == 32) {
+      // ... and y = relu(x * a + b) with a = rstd * gamma, b = beta - mean * a.  256 channels: a warp takes one pixel per
+      // step (32 lanes x 16 bytes = the pixel's 512 contiguous bytes), so a lane keeps the (a, b) of ITS eight channels in
+      // registers for the whole pixel block, the pixel's row / column is computed once per warp, and U pixels are in flight.
+      float a[8], b[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int ch = lane * 8 + k, g = ch / group_size;
+        a[k] = s_rstd[g] * __ldg(gamma + ch);
+        b[k] = __ldg(beta + ch) - s_mean[g] * a[k];
+      }
+      constexpr int U = 4, NW = THREADS / 32;
+      for (int pix0 = p0 + warp; pix0 < p1; pix0 += U * NW) {
+        uint4* ptr[U];
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int pix = min(pix0 + u * NW, p1 - 1);
+          const int yy = pix / w, xx = pix - yy * w;
+          ptr[u] = x + (((size_t)img * hp + yy + halo) * wp + xx + halo) * 32 + lane;
+          v[u] = *ptr[u];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (pix0 + u * NW < p1) *ptr[u] = relu_affine(v[u], a, b);
+      }
+    } else {
+      for (int ch = threadIdx.x; ch < c; ch += THREADS) {
+        const int g = ch / group_size;
+        const float av = s_rstd[g] * __ldg(gamma + ch);
+        sa[ch] = av;
+        sb[ch] = __ldg(beta + ch) - s_mean[g] * av;
+      }
+      __syncthreads();
+      const int items = (p1 - p0) * c8;
+      for (int i = threadIdx.x; i < items; i += THREADS) {
+        const int pix = p0 + i / c8;
+        const int cg = i - (i / c8) * c8;
+        const int yy = pix / w, xx = pix - yy * w;
+        uint4* ptr = x + (((size_t)img * hp + yy + halo) * wp + xx + halo) * c8 + cg;
+        *ptr = relu_affine(*ptr, sa + cg * 8, sb + cg * 8);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -602,9 +643,12 @@ extern "C" int hn_groupnorm_relu_levels(void* const* x_host, const int* n_host, 
     HN_REQUIRE(x_host[l] && stats_host[l] && n_host[l] > 0 && h_host[l] > 0 && w_host[l] > 0, "hn_groupnorm_relu: level %d", l);
     pixels += (long long)n_host[l] * h_host[l] * w_host[l];
   }
-  // ~8 waves of 256-thread blocks over the batch; each block amortises its per-image coefficient set-up
-  int ppb = (int)((pixels + hn_num_sms() * 8 * 4 - 1) / (hn_num_sms() * 8 * 4));
+  // four resident 256-thread blocks per SM, all at once; each block amortises its image's statistics over its pixels
+  // (8 frames, P3+P4+P5: 32 / 64 / 128 / 256 / 512 pixels per block -> 45.0 / 36.9 / 34.8 / 34.8 / 36.9 us)
+  const long long want = (long long)hn_num_sms() * 4;
+  int ppb = (int)((pixels + want - 1) / want);
   if (ppb < 32) ppb = 32;
+  if (const char* e = getenv("HN_GN_PPB")) { const int v = atoi(e); if (v >= 8) ppb = v; }
   GnLevels lv;
   memset(&lv, 0, sizeof(lv));
   lv.n_levels = n_levels;
@@ -619,8 +663,8 @@ extern "C" int hn_groupnorm_relu_levels(void* const* x_host, const int* n_host, 
     blocks += lv.blocks_per_image[l] * n_host[l];
   }
   lv.block_begin[n_levels] = blocks;
-  groupnorm_relu_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(lv, c, halo, groups, c / groups, gamma, beta,
-                                                                                  eps, ppb);
+  groupnorm_relu_kernel<256><<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(lv, c, halo, groups, c / groups, gamma,
+                                                                                       beta, eps, ppb);
   hn_count_launch();
   HN_LAUNCH_CHECK();
   return HN_OK;
