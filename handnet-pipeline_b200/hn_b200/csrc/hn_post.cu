@@ -347,10 +347,29 @@ nms_sort_kernel(const float4* __restrict__ cand_box, const float* __restrict__ c
     idx[0][i] = i;
   }
   __syncthreads();
+  int cur = 0;
+  if (n <= SORT_THREADS) {
+    // At most one candidate per thread (what a detector normally produces: tens per frame): rank by counting -- the number
+    // of candidates with a smaller key, or the same key and a smaller index, IS the position in the stable order -- instead
+    // of four radix passes with their 8192-entry histograms.  Keys are broadcast from shared memory.
+    uint32_t* skey = reinterpret_cast<uint32_t*>(hist);
+    const uint32_t mine = tid < n ? keys[0][tid] : 0xffffffffu;
+    if (tid < n) skey[tid] = mine;
+    __syncthreads();
+    if (tid < n) {
+      int rank = 0;
+      for (int j = 0; j < n; ++j) {
+        const uint32_t k = skey[j];
+        rank += (k < mine) || (k == mine && j < tid);
+      }
+      idx[1][rank] = tid;
+    }
+    __syncthreads();
+    cur = 1;
+  } else {
   // contiguous, 32-aligned segment per warp keeps the scatter stable
   const int per_warp = ((n + SORT_WARPS - 1) / SORT_WARPS + 31) & ~31;
   const int seg0 = min(warp * per_warp, n), seg1 = min(seg0 + per_warp, n);
-  int cur = 0;
   for (int shift = 0; shift < 32; shift += 8) {
     for (int i = tid; i < 256 * SORT_WARPS; i += SORT_THREADS) hist[i] = 0;
     if (tid == 0) skip_pass = 0;
@@ -412,6 +431,7 @@ nms_sort_kernel(const float4* __restrict__ cand_box, const float* __restrict__ c
     }
     cur ^= 1;
     __syncthreads();
+  }
   }
   // sorted candidate indices live in idx[cur]; publish them in idx[0] for the scan kernel
   if (cur != 0) {
