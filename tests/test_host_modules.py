@@ -142,6 +142,36 @@ def test_weight_tiling_round_trip_and_layout():
     assert s[:, 7].abs().sum() == 0 and s[:, :, 0].abs().sum() == 0 and s[..., 3].abs().sum() == 0
     assert torch.equal(s[:, :7, 1:, :3], ws.permute(0, 2, 3, 1).to(torch.bfloat16))
     assert ops.stem_frame_hw((800, 1088)) == (806, 1096)
+    # window stem: k = r*32 + px*4 + ch (a kernel row's 8 pixels x 4 channels are 64 contiguous bytes of the canvas row)
+    sw = ops.untile_k(ops.pack_stem_weight(ws, 256, order="window")).view(64, 8, 8, 4)
+    assert sw[:, 7].abs().sum() == 0 and sw[:, :, 0].abs().sum() == 0 and sw[..., 3].abs().sum() == 0
+    assert torch.equal(sw[:, :7, 1:, :3], ws.permute(0, 2, 3, 1).to(torch.bfloat16))
+
+
+def test_window_stem_k_order_is_a_sliding_window_over_canvas_rows():
+    """The window stem's GEMM (hn_conv_desc.stem_window): for output pixel (oy, ox) kernel row r reads the 64 contiguous bytes
+    of canvas row 2*oy - 3 + r that start at pixel 2*ox - 4 (zero outside the canvas), against pack_stem_weight(order="window").
+    Emulated on the CPU with unfold: equals F.conv2d(stride 2, padding 3) (backbone.body.conv1, fcos_utils/fcos.py:476)."""
+    import torch.nn.functional as F
+    from hn_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    n, h, w = 2, 10, 14
+    canvas = torch.zeros(n, h, w, 4)
+    canvas[..., :3] = torch.randn(n, h, w, 3, generator=g)
+    wt = torch.randn(8, 3, 7, 7, generator=g)
+    ref = F.conv2d(canvas[..., :3].permute(0, 3, 1, 2), wt, stride=2, padding=3)
+    wk = ops.untile_k(ops.pack_stem_weight(wt.to(torch.bfloat16).float(), 256, order="window"))[:8].float()      # [cout, 256]
+    padded = torch.zeros(n, h + 8, w + 8, 4)                        # 3 rows above (+ the zero-weight 8th row below), 4 px left
+    padded[:, 3:3 + h, 4:4 + w] = canvas
+    oh, ow = (h + 1) // 2, (w + 1) // 2
+    out = torch.zeros(n, 8, oh, ow)
+    for oy in range(oh):
+        for ox in range(ow):
+            win = padded[:, 2 * oy:2 * oy + 8, 2 * ox:2 * ox + 8, :].reshape(n, 256)        # rows 2oy-3.., pixels 2ox-4..
+            out[:, :, oy, ox] = win @ wk.t()
+    ref_bf = F.conv2d(canvas[..., :3].permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), stride=2, padding=3)
+    torch.testing.assert_close(out, ref_bf, rtol=1e-4, atol=1e-4)
+    assert (ref - ref_bf).abs().max() < 0.2
 
 
 # ------------------------------------------------------------------------------------------------
