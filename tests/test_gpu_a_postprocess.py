@@ -58,6 +58,48 @@ def test_decode_select_matches_oracle(ops):
         assert torch.equal(box, ref_box)
 
 
+@pytest.mark.parametrize("nc", [1, 2, 4, 6, 11])
+def test_decode_select_class_counts_ties_and_saturation(ops, nc):
+    """Class counts with compile-time plane staging (1..4) and the generic path (any count): the arg-max-on-logits shortcut keeps
+    the reference's FIRST-max label (fcos_utils/fcos.py:598-599) when logits are exactly equal, within rounding of each other,
+    saturated (sigmoid == 1.0 for several classes) or far in the negative tail; both layouts."""
+    lv = ops.Levels([(25, 34), (13, 17), (7, 9)], (200, 272), (8, 16, 32))
+    ho = stress_head_tensors(17 + nc, 2, lv.locs, nc, -0.35)
+    cl = ho["cls_logits"]
+    g = torch.Generator().manual_seed(nc)
+    L = lv.locs
+    if nc > 1:
+        cl[0, 0:L:7, :] = cl[0, 0:L:7, :1]                                   # all classes exactly equal -> label 0
+        cl[0, 1:L:7, nc - 1] = cl[0, 1:L:7, :].max(dim=1).values            # last class ties with the max -> the earlier one wins
+        cl[0, 2:L:7, :] = 17.0 + torch.rand(len(range(2, L, 7)), nc, generator=g) * 8      # saturated: sigmoid rounds to 1.0
+        cl[0, 3:L:7, 0] = cl[0, 3:L:7, 1] * (1 + 2 ** -22)                  # within rounding of each other
+        cl[1, 0:L:5, :] = -95.0 - torch.rand(len(range(0, L, 5)), nc, generator=g) * 20    # exp overflows: all scores 0
+    s_ref, l_ref, m_ref, _ = fcos_oracle.score_and_select(ho)
+    rows = {k: v.cuda() for k, v in ho.items()}
+    for layout in ("rows", "planes"):
+        dev = rows if layout == "rows" else {k: ops.head_planes(v) for k, v in rows.items()}
+        for thr in (0.7, 0.0):                                              # 0.0: every location is a candidate
+            cand = ops.fcos_decode_select(dev["cls_logits"], dev["bbox_ctrness"], dev["bbox_regression"], nc, lv, thr)
+            torch.cuda.synchronize()
+            for b in range(2):
+                n, loc, score, label, box = _cand_lists(cand, b)
+                ref_pass = s_ref[b] > thr
+                border = (s_ref[b] - thr).abs() < 3e-7
+                sym = set(loc.tolist()) ^ set(torch.nonzero(ref_pass).reshape(-1).tolist())
+                assert all(bool(border[i]) for i in sym), (layout, thr, b, len(sym))
+                torch.testing.assert_close(score, s_ref[b][loc.long()], rtol=0, atol=2.4e-7)
+                # labels: where the two best scores of the CPU path differ by more than the expf disagreement (CUDA vs Sleef,
+                # ~1 ulp) the label must match; STRUCTURAL ties (identical logits, saturation, all-zero scores) must give the
+                # first class here as well.  Logits one or two ulp apart may round either way on either side: not compared.
+                sc_all = torch.sqrt(torch.sigmoid(ho["cls_logits"][b]) * torch.sigmoid(ho["bbox_ctrness"][b]))
+                top2 = sc_all.topk(min(2, nc), dim=1).values
+                lg2 = ho["cls_logits"][b].topk(min(2, nc), dim=1).values
+                structural = (lg2[:, 0] == lg2[:, -1]) | (lg2[:, -1] >= 17.0) | (lg2[:, 0] <= -95.0)
+                clear = (top2[:, 0] - top2[:, -1] > 5e-7) | structural if nc > 1 else torch.ones(L, dtype=torch.bool)
+                sel = clear[loc.long()]
+                assert torch.equal(label[sel].long(), l_ref[b][loc.long()][sel]), (layout, thr, b)
+
+
 def test_decode_select_channel_planes_equal_rows(ops):
     """The detector's head buffers are channel planes [B][channel][locs] (out_kind 2 of the output convolutions): decode and
     gather over planar views give exactly what they give over row-layout tensors, incl. the early-out for hopeless
