@@ -6,6 +6,8 @@
 // Both are HBM-bound: coalesced streaming reads, warp-shuffle reductions, no tensor cores.
 #include "hn_common.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 // ------------------------------------------------------------------------------- S1 + S2
@@ -106,7 +108,7 @@ constexpr int AGG_SPLITS = 16;          // anchor ranges per crop (workspace is 
 __global__ void __launch_bounds__(AGG_MAX_THREADS)
 a2j_partial_kernel(const float* __restrict__ cls, const float2* __restrict__ reg, const float* __restrict__ dep,
                    const float2* __restrict__ anchor_xy, int anchors, int joints, int rows_per_iter,
-                   Partial* __restrict__ part) {
+                   Partial* __restrict__ part, float* __restrict__ out) {
   extern __shared__ Partial sh[];
   const int n = blockIdx.y, split = blockIdx.x, splits = gridDim.x;
   const int per = (anchors + splits - 1) / splits;
@@ -154,7 +156,12 @@ a2j_partial_kernel(const float* __restrict__ cls, const float2* __restrict__ reg
   if (t < joints) {
     Partial acc = sh[t];
     for (int rr = 1; rr < rows_per_iter; ++rr) merge(acc, sh[rr * joints + t]);
-    part[((size_t)n * splits + split) * joints + t] = acc;
+    if (splits == 1) {                             // the crop's only block: finish here (a2j/anchor.py:73-82), no combine launch
+      float* o = out + ((size_t)n * joints + t) * 3;
+      o[0] = acc.x / acc.s; o[1] = acc.y / acc.s; o[2] = acc.d / acc.s;
+    } else {
+      part[((size_t)n * splits + split) * joints + t] = acc;
+    }
   }
 }
 
@@ -166,7 +173,7 @@ template <int U, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 a2j_partial_vec_kernel(const float4* __restrict__ cls, const float4* __restrict__ reg, const float4* __restrict__ dep,
                        const float2* __restrict__ anchor_xy, int anchors, int joints, int rows_per_round,
-                       Partial* __restrict__ part) {
+                       Partial* __restrict__ part, float* __restrict__ out) {
   extern __shared__ Partial sh[];                // [4 * T] then reused for the merge tree
   const int n = blockIdx.y, split = blockIdx.x, splits = gridDim.x;
   const int T = blockDim.x, t = threadIdx.x;
@@ -244,7 +251,12 @@ a2j_partial_vec_kernel(const float4* __restrict__ cls, const float4* __restrict_
   if (t < joints) {
     Partial a2 = sh[t];
     for (int i = 1; i < rows_per_round / 4; ++i) merge(a2, sh[i * joints + t]);
-    part[((size_t)n * splits + split) * joints + t] = a2;
+    if (splits == 1) {                             // the crop's only block: finish here, no combine launch
+      float* o = out + ((size_t)n * joints + t) * 3;
+      o[0] = a2.x / a2.s; o[1] = a2.y / a2.s; o[2] = a2.d / a2.s;
+    } else {
+      part[((size_t)n * splits + split) * joints + t] = a2;
+    }
   }
 }
 
@@ -298,7 +310,14 @@ extern "C" int hn_a2j_aggregate(const float* cls, const float* reg, const float*
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // few crops: many anchor ranges per crop for parallelism; many crops: long ranges, so that the per-block
   // shared-memory merge tail is amortised over more streamed rows
-  const int splits = n >= 64 ? AGG_SPLITS / 4 : AGG_SPLITS;
+  // (512 crops: 4 ranges + combine 89 us, 2 ranges 85 us, 1 range per crop finished in place 80 us)
+  int splits = n >= 64 ? AGG_SPLITS / 4 : AGG_SPLITS;
+  {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+        n >= 2 * sms)
+      splits = 1;                                  // enough crops to fill every SM with whole-crop blocks
+  }
   dim3 grid(splits, n);
   // vector path: T = rows_per_round * joints / 4 threads, rows_per_round a multiple of 4 -> T a multiple of joints
   int rows_per_round = (4 * 256 / joints) & ~3;
@@ -314,19 +333,21 @@ extern "C" int hn_a2j_aggregate(const float* cls, const float* reg, const float*
     kern<<<grid, vec_threads, sh_bytes, st>>>(reinterpret_cast<const float4*>(cls), reinterpret_cast<const float4*>(reg),
                                               reinterpret_cast<const float4*>(depth),
                                               reinterpret_cast<const float2*>(anchor_xy), anchors, joints, rows_per_round,
-                                              reinterpret_cast<Partial*>(workspace));
+                                              reinterpret_cast<Partial*>(workspace), out);
   } else {
     const int rows = AGG_MAX_THREADS / joints > 12 ? 12 : AGG_MAX_THREADS / joints;
     const int threads = ((rows * joints + 31) / 32) * 32;
     a2j_partial_kernel<<<grid, threads, threads * sizeof(Partial), st>>>(
         cls, reinterpret_cast<const float2*>(reg), depth, reinterpret_cast<const float2*>(anchor_xy), anchors, joints, rows,
-        reinterpret_cast<Partial*>(workspace));
+        reinterpret_cast<Partial*>(workspace), out);
   }
   hn_count_launch();
   HN_LAUNCH_CHECK();
-  a2j_combine_kernel<<<hn_div_up(n * joints, 128), 128, 0, st>>>(reinterpret_cast<const Partial*>(workspace), splits,
-                                                                 joints, n, out);
-  hn_count_launch();
-  HN_LAUNCH_CHECK();
+  if (splits > 1) {
+    a2j_combine_kernel<<<hn_div_up(n * joints, 128), 128, 0, st>>>(reinterpret_cast<const Partial*>(workspace), splits,
+                                                                   joints, n, out);
+    hn_count_launch();
+    HN_LAUNCH_CHECK();
+  }
   return HN_OK;
 }

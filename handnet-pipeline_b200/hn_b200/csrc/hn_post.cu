@@ -773,8 +773,7 @@ extern "C" int hn_fcos_decode_select(const float* cls_logits, int64_t cls_img_st
   // 1 round 35.8 / 66.7 us, 2 rounds 35.6 / 64.5, 3 rounds 37.9 / 74.5, 4 rounds 39.6 / 80.9 -- two rounds halve the block
   // tails (scan, look-back, exit) without emptying the last wave of resident blocks; small grids take one round.
   const int stage_planes = num_classes <= 4 ? num_classes + 1 : 2;
-  int rounds = (long long)batch * hn_div_up(locs, SEL_CHUNK * 2) >= 2 * 5 * 148 ? 2 : 1;
-  if (const char* e = getenv("HN_SELECT_ROUNDS")) { const int v = atoi(e); if (v >= 1 && v <= SEL_MAX_ROUNDS) rounds = v; }
+  const int rounds = (long long)batch * hn_div_up(locs, SEL_CHUNK * 2) >= 2 * 5 * 148 ? 2 : 1;
   const int chunks = hn_div_up(locs, SEL_CHUNK * rounds);
   HN_REQUIRE((long long)batch * chunks < (1ll << 31), "hn_fcos_decode_select: grid too large");
   const float thresh_ge = float_gt_as_ge(score_thresh);

@@ -563,13 +563,10 @@ static int preprocess_impl(const float* const* images_host, const int* in_h_host
       const int first_pair = pad_top >> 1, npairs = ((pad_top + canvas_h - 1) >> 1) - first_pair + 1;
       // pairs per CTA: long walks amortise the per-CTA set-up, but keep at least ~4 CTAs per SM slot in the grid
       const long long total = (long long)npairs * nb;
-      int ppc = total >= 8 * 1776 ? 8 : (total >= 4 * 1776 ? 4 : 2);          // (64 VGA frames: 2 / 4 / 8 / 16 pairs -> 180 / 174 / 172 / 176 us)
-      if (const char* e = getenv("HN_PRE_PPC")) { const int v = atoi(e); if (v >= 1) ppc = v; }
+      const int ppc = total >= 8 * 1776 ? 8 : (total >= 4 * 1776 ? 4 : 2);          // (64 VGA frames: 2 / 4 / 8 / 16 pairs -> 180 / 174 / 172 / 176 us)
       dim3 grid(hn_div_up(npairs, ppc), 1, nb);
-      static const int thr_env = getenv("HN_PRE_THREADS") ? atoi(getenv("HN_PRE_THREADS")) : 0;
       const int per_thread = hn_div_up(canvas_w, PRE_T);                              // pixels of a row per thread
-      int threads = (hn_div_up(canvas_w, per_thread) + 31) / 32 * 32;
-      if (thr_env >= 32 && thr_env <= PRE_T) threads = thr_env;
+      const int threads = (hn_div_up(canvas_w, per_thread) + 31) / 32 * 32;     // (64 VGA frames: 192 / 224 / 256 threads within 2 %)
       static bool attr_set = false;
       if (!attr_set) {
         HN_CHECK_CUDA(cudaFuncSetAttribute(preprocess_pairs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -648,7 +645,6 @@ extern "C" int hn_groupnorm_relu_levels(void* const* x_host, const int* n_host, 
   const long long want = (long long)hn_num_sms() * 4;
   int ppb = (int)((pixels + want - 1) / want);
   if (ppb < 32) ppb = 32;
-  if (const char* e = getenv("HN_GN_PPB")) { const int v = atoi(e); if (v >= 8) ppb = v; }
   GnLevels lv;
   memset(&lv, 0, sizeof(lv));
   lv.n_levels = n_levels;

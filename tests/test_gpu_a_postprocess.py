@@ -128,20 +128,20 @@ def test_decode_select_channel_planes_equal_rows(ops):
         assert torch.equal(ga["sides"][i, :n], gb["sides"][i, :n]) and torch.equal(ga["boxes"][i, :n], gb["boxes"][i, :n])
 
 
-def test_decode_select_large_batch_four_round_blocks(ops):
-    """From ~600 blocks on, a block takes four rounds of 1024 locations (loads of the next round in flight while it scores the
-    current one): same candidates as the one-round kernel a small batch gets, image by image, incl. the look-back over the
+def test_decode_select_large_batch_multi_round_blocks(ops):
+    """On large grids a block takes two rounds of 1024 locations (both rounds' cp.async copies in flight while it scores the
+    first): same candidates as the one-round kernel a small batch gets, image by image, incl. the look-back over the
     chunks of an image and the ragged last chunk."""
-    lv = ops.Levels([(50, 68), (25, 34), (13, 17)], (400, 544), (8, 16, 32))     # 4471 locations: 2 chunks of 4096
+    lv = ops.Levels([(50, 68), (25, 34), (13, 17)], (400, 544), (8, 16, 32))     # 4471 locations: 3 chunks of 2048
     ho = stress_head_tensors(9, 4, lv.locs, 3, -0.35)
     ho["cls_logits"][2] -= 6.0
     small = {k: ops.head_planes(v.cuda()) for k, v in ho.items()}
-    big = {k: ops.head_planes(v.repeat(75, 1, 1).cuda()) for k, v in ho.items()}      # 300 images
+    big = {k: ops.head_planes(v.repeat(150, 1, 1).cuda()) for k, v in ho.items()}      # 600 images x 3 chunks >= 1480 blocks
     a = ops.fcos_decode_select(small["cls_logits"], small["bbox_ctrness"], small["bbox_regression"], 3, lv, 0.7)
     b = ops.fcos_decode_select(big["cls_logits"], big["bbox_ctrness"], big["bbox_regression"], 3, lv, 0.7)
     torch.cuda.synchronize()
-    assert torch.equal(b["count"], a["count"].repeat(75)) and int(a["count"][0]) > 1500
-    for j in (0, 1, 2, 3, 150, 297, 298, 299):
+    assert torch.equal(b["count"], a["count"].repeat(150)) and int(a["count"][0]) > 1500
+    for j in (0, 1, 2, 3, 150, 297, 298, 599):
         i = j % 4
         n = int(a["count"][i])
         for k in ("loc", "score", "label", "box"):
@@ -311,7 +311,7 @@ def test_select_crop_resize_bit_exact(ops, golden):
         assert torch.equal(db[i], ref)
 
 
-@pytest.mark.parametrize("n", [5, 70])        # 70: the many-crops launch shape (4 anchor ranges per crop instead of 16)
+@pytest.mark.parametrize("n", [5, 70, 300])   # 70: 4 anchor ranges per crop instead of 16; 300: one block per crop, finished in place
 def test_a2j_aggregate_matches_oracle(ops, n):
     g = torch.Generator().manual_seed(3)
     cls = torch.randn(n, 1936, 21, generator=g) * 4
@@ -325,7 +325,7 @@ def test_a2j_aggregate_matches_oracle(ops, n):
     torch.testing.assert_close(out.cpu(), ref, rtol=1e-5, atol=1e-4)
 
 
-@pytest.mark.parametrize("n,anchors,joints", [(3, 7, 5), (2, 1936, 14), (66, 50, 3), (2, 40, 3)])
+@pytest.mark.parametrize("n,anchors,joints", [(3, 7, 5), (2, 1936, 14), (66, 50, 3), (2, 40, 3), (301, 50, 3), (297, 64, 21)])
 def test_a2j_aggregate_other_shapes(ops, n, anchors, joints):
     """Shapes other than the shipped 1936 x 21 head: anchors * joints not a multiple of 4 takes the scalar kernel;
     joints = 14 changes the round geometry of the vector kernel."""
