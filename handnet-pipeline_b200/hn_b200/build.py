@@ -18,7 +18,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhandnet_b200.so")
-SOURCES = ["hn_lib.cu", "hn_conv_igemm.cu", "hn_pre.cu", "hn_post.cu", "hn_pose.cu", "hn_io.cu"]
+SOURCES = ["hn_lib.cu", "hn_conv_igemm.cu", "hn_pre.cu", "hn_post.cu", "hn_pose.cu", "hn_io.cu", "hn_mesh.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "shared"]
 

@@ -1,0 +1,173 @@
+// pose2mesh lifting (last "next" row): the three kernels behind models.pose2mesh_net.FlatPose2Mesh
+//   Chebyshev graph convolution   pose2mesh/lib/models/backbones/cheby_graph_conv.py:5-47  (torch.sparse.mm + nn.Linear + BN1d)
+//   PoseNet residual MLP          pose2mesh/lib/models/posenet.py:11-84                    (BN1d -> ReLU -> Linear, twice, + x)
+//   mesh block glue               pose2mesh/lib/models/meshnet.py:86-117                   (linear interpolate of the block input
+//                                                                                           along the FEATURE axis + add + x2 vertex upsample)
+// One hand is 21 joints -> 1024 (778) vertices x <= 256 features: ~0.2 GFLOP and 300 MB of fp32 weights (the 4096-wide PoseNet).
+// Everything is fp32 SIMT on purpose: the work is weight streaming (GEMV) and 5-nonzero-per-row sparse products, not tensor-core
+// shaped, and fp32 keeps the result within 1e-5 of the reference.
+#include "hn_common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------- Chebyshev basis
+// One warp per (batch, vertex) row of the CSR Laplacian; lanes stride over the features.
+//   out[b][v][f] = alpha * sum_j L[v][j] * x[b][col_j][f] + beta * z[b][v][f]
+// T1 = L T0 (alpha 1, beta 0), T2 = 2 L T1 - T0 (alpha 2, beta -1)   (cheby_graph_conv.py:26-31)
+__global__ void __launch_bounds__(256)
+cheby_spmm_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, const float* __restrict__ val,
+                  const float* __restrict__ x, const float* __restrict__ z, float alpha, float beta, int batch, int verts,
+                  int feats, float* __restrict__ out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= batch * verts) return;
+  const int lane = threadIdx.x & 31;
+  const int b = row / verts, v = row - b * verts;
+  const int j0 = row_ptr[v], j1 = row_ptr[v + 1];
+  const float* xb = x + (size_t)b * verts * feats;
+  for (int f = lane; f < feats; f += 32) {
+    float acc = 0.f;
+    for (int j = j0; j < j1; ++j) acc = fmaf(__ldg(val + j), __ldg(xb + (size_t)__ldg(col + j) * feats + f), acc);
+    float r = alpha * acc;
+    if (z) r = fmaf(beta, z[(size_t)row * feats + f], r);
+    out[(size_t)row * feats + f] = r;
+  }
+}
+
+// ---------------------------------------------------------------------------------- linear + affine + ReLU
+// y[m][n] = post( sum_kk pre(A[m][kk]) * W[n][kk] + bias[n] ) (+ res[m][n])
+//   A is given as `planes` matrices [M][fin] and kk = f * planes + p reads plane p, feature f -- the order in which
+//   graph_conv_cheby flattens its K Chebyshev terms (x.permute(3, 1, 2, 0).view(B*V, Fin*K), cheby_graph_conv.py:33-35);
+//   planes = 1 is an ordinary matrix.
+//   pre(a)  = relu(a * in_scale[kk] + in_shift[kk])   when in_scale != nullptr  (eval BatchNorm1d + ReLU in front: posenet.py:25-28)
+//   post(t) = t * out_scale[n] + out_shift[n], ReLU when relu_out              (eval BatchNorm1d behind: cheby_graph_conv.py:40-41)
+// A block = 8 warps = 8 output columns x a chunk of LIN_ROWS rows; the chunk's inputs are staged in shared memory K tile by
+// K tile (pre applied once), every warp streams its weight row with coalesced loads and keeps LIN_ROWS accumulators.
+constexpr int LIN_ROWS = 16, LIN_KT = 512, LIN_COLS = 8;
+struct LinArgs {
+  const float* a[3];
+  const float* w;
+  const float* bias;
+  const float* in_scale;
+  const float* in_shift;
+  const float* out_scale;
+  const float* out_shift;
+  const float* res;
+  float* y;
+  int m, n, fin, planes, relu_out;
+};
+
+__global__ void __launch_bounds__(32 * LIN_COLS)
+linear_kernel(const LinArgs p) {
+  __shared__ float xs[LIN_ROWS][LIN_KT];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * LIN_COLS + warp;
+  const int m0 = blockIdx.y * LIN_ROWS;
+  const int rows = min(LIN_ROWS, p.m - m0);
+  const int kd = p.fin * p.planes;
+  float acc[LIN_ROWS];
+#pragma unroll
+  for (int r = 0; r < LIN_ROWS; ++r) acc[r] = 0.f;
+  for (int k0 = 0; k0 < kd; k0 += LIN_KT) {
+    const int kt = min(LIN_KT, kd - k0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * kt; i += blockDim.x) {
+      const int r = i / kt, kk = k0 + i - r * kt;
+      const int f = kk / p.planes, pl = kk - f * p.planes;
+      float a = __ldg(p.a[pl] + (size_t)(m0 + r) * p.fin + f);
+      if (p.in_scale) a = fmaxf(fmaf(a, __ldg(p.in_scale + kk), __ldg(p.in_shift + kk)), 0.f);
+      xs[r][i - r * kt] = a;
+    }
+    __syncthreads();
+    if (n < p.n) {
+      const float* wr = p.w + (size_t)n * kd + k0;
+      for (int k = lane; k < kt; k += 32) {
+        const float wv = __ldg(wr + k);
+#pragma unroll
+        for (int r = 0; r < LIN_ROWS; ++r) acc[r] = fmaf(wv, xs[r][k], acc[r]);      // (rows beyond `rows` hold stale finite data)
+      }
+    }
+  }
+  if (n >= p.n) return;
+#pragma unroll
+  for (int r = 0; r < LIN_ROWS; ++r) {
+    float v = acc[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && r < rows) {
+      v += p.bias ? __ldg(p.bias + n) : 0.f;
+      if (p.out_scale) v = fmaf(v, __ldg(p.out_scale + n), __ldg(p.out_shift + n));
+      if (p.relu_out) v = fmaxf(v, 0.f);
+      if (p.res) v += p.res[(size_t)(m0 + r) * p.n + n];
+      p.y[(size_t)(m0 + r) * p.n + n] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- block residual + vertex upsample
+// out[b][v * up + j][f] = x[b][v][f] + interp(skip[b][v][:], f)      j < up
+// interp = F.interpolate(skip, size=fout, mode='linear', align_corners=False) along the FEATURE axis (meshnet.py:107-114 treats
+// [B, V, F] as (batch, channels, length)); up = 2 is nn.Upsample(scale_factor=2) (nearest) along the vertices (meshnet.py:69-76).
+__global__ void __launch_bounds__(256)
+mesh_residual_kernel(const float* __restrict__ x, const float* __restrict__ skip, int rows, int fout, int fskip, int up,
+                     float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * fout) return;
+  const int r = i / fout, f = i - r * fout;
+  // ATen area_pixel_compute_source_index(scale = in / out, align_corners = false), clamped at 0
+  const float scale = (float)fskip / (float)fout;
+  float src = scale * ((float)f + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  int i0 = (int)src;
+  if (i0 > fskip - 1) i0 = fskip - 1;
+  const int i1 = i0 + (i0 < fskip - 1 ? 1 : 0);
+  const float l1 = src - (float)i0, l0 = 1.f - l1;
+  const float* s = skip + (size_t)r * fskip;
+  const float v = x[i] + (l0 * s[i0] + l1 * s[i1]);
+  for (int j = 0; j < up; ++j) out[((size_t)r * up + j) * fout + f] = v;
+}
+
+}  // namespace
+
+extern "C" int hn_cheby_spmm(const int* row_ptr, const int* col, const float* val, const float* x, const float* z, float alpha,
+                             float beta, int batch, int verts, int feats, float* out, void* stream) {
+  HN_REQUIRE(row_ptr && col && val && x && out, "hn_cheby_spmm: null pointer");
+  HN_REQUIRE(batch > 0 && verts > 0 && feats > 0, "hn_cheby_spmm: bad sizes");
+  const int rows = batch * verts;
+  cheby_spmm_kernel<<<hn_div_up(rows, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(row_ptr, col, val, x, z, alpha, beta,
+                                                                                           batch, verts, feats, out);
+  hn_count_launch();
+  HN_LAUNCH_CHECK();
+  return HN_OK;
+}
+
+extern "C" int hn_linear_f32(const float* a0, const float* a1, const float* a2, int planes, int m, int fin, const float* weight,
+                             const float* bias, int n, const float* in_scale, const float* in_shift, const float* out_scale,
+                             const float* out_shift, int relu_out, const float* res, float* y, void* stream) {
+  HN_REQUIRE(a0 && weight && y, "hn_linear_f32: null pointer");
+  HN_REQUIRE(planes >= 1 && planes <= 3 && (planes < 2 || a1) && (planes < 3 || a2), "hn_linear_f32: 1..3 input planes");
+  HN_REQUIRE(m > 0 && fin > 0 && n > 0, "hn_linear_f32: bad sizes");
+  HN_REQUIRE((in_scale == nullptr) == (in_shift == nullptr) && (out_scale == nullptr) == (out_shift == nullptr),
+             "hn_linear_f32: scale and shift come in pairs");
+  LinArgs p;
+  p.a[0] = a0; p.a[1] = a1; p.a[2] = a2;
+  p.w = weight; p.bias = bias;
+  p.in_scale = in_scale; p.in_shift = in_shift; p.out_scale = out_scale; p.out_shift = out_shift;
+  p.res = res; p.y = y;
+  p.m = m; p.n = n; p.fin = fin; p.planes = planes; p.relu_out = relu_out;
+  dim3 grid(hn_div_up(n, LIN_COLS), hn_div_up(m, LIN_ROWS));
+  linear_kernel<<<grid, 32 * LIN_COLS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  hn_count_launch();
+  HN_LAUNCH_CHECK();
+  return HN_OK;
+}
+
+extern "C" int hn_mesh_residual_upsample(const float* x, const float* skip, int rows, int fout, int fskip, int up, float* out,
+                                         void* stream) {
+  HN_REQUIRE(x && skip && out, "hn_mesh_residual_upsample: null pointer");
+  HN_REQUIRE(rows > 0 && fout > 0 && fskip > 0 && up >= 1, "hn_mesh_residual_upsample: bad sizes");
+  mesh_residual_kernel<<<hn_div_up(rows * fout, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, skip, rows, fout, fskip,
+                                                                                                       up, out);
+  hn_count_launch();
+  HN_LAUNCH_CHECK();
+  return HN_OK;
+}

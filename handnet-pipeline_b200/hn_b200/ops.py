@@ -613,3 +613,79 @@ def a2j_aggregate(cls: torch.Tensor, reg: torch.Tensor, dep: torch.Tensor, ancho
     check(_lib.load().hn_a2j_aggregate(cls.data_ptr(), reg.data_ptr(), dep.data_ptr(), anchors.data_ptr(), n, a, j,
                                        out.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr()), "hn_a2j_aggregate")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# pose2mesh lifting: Chebyshev graph convolution, fp32 linear layers, mesh block residual
+# ------------------------------------------------------------------------------------------------
+class CsrGraph:
+    """A (rescaled) graph Laplacian on the device in CSR form.  Accepts a scipy sparse matrix, a torch sparse tensor or a
+    dense tensor (what pose2mesh's graph_utils.build_coarse_graphs / sparse_python_to_torch hand over)."""
+
+    __slots__ = ("n", "row_ptr", "col", "val")
+
+    def __init__(self, lap, device="cuda"):
+        if hasattr(lap, "tocsr"):                              # scipy
+            m = lap.tocsr()
+            m.sort_indices()
+            rp, ci, vv = torch.from_numpy(m.indptr.copy()), torch.from_numpy(m.indices.copy()), torch.from_numpy(m.data.copy())
+            self.n = int(m.shape[0])
+        else:
+            t = lap.detach().cpu()
+            t = (t if t.is_sparse else t.to_sparse()).coalesce()              # COO, sorted by (row, col)
+            self.n = int(t.shape[0])
+            ri, ci, vv = t.indices()[0], t.indices()[1], t.values()
+            rp = torch.zeros(self.n + 1, dtype=torch.int64)
+            rp[1:] = torch.cumsum(torch.bincount(ri, minlength=self.n), 0)
+        self.row_ptr = rp.to(torch.int32).to(device).contiguous()
+        self.col = ci.to(torch.int32).to(device).contiguous()
+        self.val = vv.to(torch.float32).to(device).contiguous()
+
+
+def cheby_spmm(g: CsrGraph, x: torch.Tensor, z: Optional[torch.Tensor] = None, alpha: float = 1.0, beta: float = 0.0,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = alpha * L x + beta * z for x, z [B, V, F] fp32 (cheby_graph_conv.py:26-31)."""
+    _require_cuda(x, "x")
+    b, v, f = x.shape
+    assert v == g.n and x.dtype == torch.float32 and x.is_contiguous()
+    if z is not None:
+        assert z.shape == x.shape and z.dtype == torch.float32 and z.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.load().hn_cheby_spmm(g.row_ptr.data_ptr(), g.col.data_ptr(), g.val.data_ptr(), x.data_ptr(), ptr(z), float(alpha),
+                                    float(beta), b, v, f, out.data_ptr(), stream_ptr()), "hn_cheby_spmm")
+    return out
+
+
+def linear_f32(planes: Sequence[torch.Tensor], weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+               in_affine=None, out_affine=None, relu: bool = False, res: Optional[torch.Tensor] = None,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = post(pre([planes interleaved]) @ weight.T + bias) (+ res); planes: 1..3 tensors [M, fin] whose features are
+    interleaved plane-fastest (kk = f * len(planes) + p), see hn_linear_f32 in the header."""
+    a0 = planes[0]
+    _require_cuda(a0, "input")
+    m, fin = a0.shape
+    n = weight.shape[0]
+    assert weight.shape[1] == fin * len(planes) and weight.dtype == torch.float32 and weight.is_contiguous()
+    for t in planes:
+        assert t.shape == a0.shape and t.dtype == torch.float32 and t.is_contiguous()
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=a0.device)
+    isc, ish = in_affine if in_affine is not None else (None, None)
+    osc, osh = out_affine if out_affine is not None else (None, None)
+    pp = [t.data_ptr() for t in planes] + [0, 0]
+    check(_lib.load().hn_linear_f32(pp[0], pp[1], pp[2], len(planes), m, fin, weight.data_ptr(), ptr(bias), n, ptr(isc), ptr(ish),
+                                    ptr(osc), ptr(osh), int(relu), ptr(res), out.data_ptr(), stream_ptr()), "hn_linear_f32")
+    return out
+
+
+def mesh_residual_upsample(x: torch.Tensor, skip: torch.Tensor, up: int) -> torch.Tensor:
+    """[B, V, F] + linear interpolation of skip [B, V, Fs] along the feature axis, vertices repeated `up` times
+    (meshnet.py:107-114, 69-76)."""
+    _require_cuda(x, "x")
+    b, v, f = x.shape
+    assert skip.shape[:2] == (b, v) and x.is_contiguous() and skip.is_contiguous() and x.dtype == skip.dtype == torch.float32
+    out = torch.empty((b, v * up, f), dtype=torch.float32, device=x.device)
+    check(_lib.load().hn_mesh_residual_upsample(x.data_ptr(), skip.data_ptr(), b * v, f, skip.shape[2], up, out.data_ptr(),
+                                                stream_ptr()), "hn_mesh_residual_upsample")
+    return out

@@ -158,3 +158,27 @@ def stress_head_tensors(seed: int, batch: int, locs: int, num_classes: int = 3, 
         "bbox_regression": 0.5 + 3.5 * torch.rand(batch, locs, 4, generator=g),
         "hand_lr": torch.randn(batch, locs, 2, generator=g),
     }
+
+
+def fill_state_dict(shapes, seed: int = 0):
+    """Deterministic synthetic weights for a list of (key, shape) pairs (pose2mesh: no checkpoint is available offline).
+    Linear weights ~ N(0, 1 / fan_in), biases ~ N(0, 0.05); BatchNorm weight ~ U(0.6, 1.4), bias ~ N(0, 0.1), running_mean ~
+    N(0, 0.2), running_var ~ U(0.5, 1.5).  Generated on the CPU in key order, so the same list gives the same tensors anywhere."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for key, shape in shapes:
+        shape = tuple(shape)
+        leaf = key.rsplit(".", 1)[-1]
+        if leaf == "num_batches_tracked":
+            sd[key] = torch.zeros((), dtype=torch.int64)
+        elif leaf == "running_var":
+            sd[key] = 0.5 + torch.rand(shape, generator=g)
+        elif leaf == "running_mean":
+            sd[key] = 0.2 * torch.randn(shape, generator=g)
+        elif len(shape) == 2:
+            sd[key] = torch.randn(shape, generator=g) * (1.0 / shape[1]) ** 0.5
+        elif ".bn." in key or "batch_norm" in key:
+            sd[key] = (0.6 + 0.8 * torch.rand(shape, generator=g)) if leaf == "weight" else 0.1 * torch.randn(shape, generator=g)
+        else:
+            sd[key] = 0.05 * torch.randn(shape, generator=g)
+    return sd

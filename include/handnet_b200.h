@@ -266,6 +266,29 @@ int64_t hn_a2j_workspace_bytes(int n, int joints);
 int hn_a2j_aggregate(const float* cls, const float* reg, const float* depth, const float* anchor_xy, int n,
                      int anchors, int joints, float* out, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- pose2mesh lifting (last row): models.pose2mesh_net.FlatPose2Mesh ---------------------------
+ * fp32 SIMT kernels; one hand is 21 joints -> ~1000 vertices x <= 256 features (weight streaming and 5-nonzero rows).
+ *
+ * Chebyshev term of a graph convolution (pose2mesh/lib/models/backbones/cheby_graph_conv.py:26-31): with the rescaled graph
+ * Laplacian L [verts x verts] in CSR form and x, z, out [batch][verts][feats]:  out = alpha * L x + beta * z  (z may be NULL).
+ * T1 = L T0 is (1, 0); T2 = 2 L T1 - T0 is (2, -1) with z = T0. */
+int hn_cheby_spmm(const int* row_ptr, const int* col, const float* val, const float* x, const float* z, float alpha, float beta,
+                  int batch, int verts, int feats, float* out, void* stream);
+/* y[m][n] = post(sum_kk pre(A[m][kk]) * weight[n][kk] + bias[n]) (+ res[m][n]).  A is `planes` (1..3) matrices a0, a1, a2 of
+ * [m][fin] and kk = f * planes + p reads plane p, feature f: the order in which graph_conv_cheby flattens its Chebyshev terms
+ * (cheby_graph_conv.py:33-35); planes = 1 is an ordinary [m][fin] matrix.  pre(a) = relu(a * in_scale[kk] + in_shift[kk]) when
+ * in_scale != NULL (eval-mode BatchNorm1d + ReLU in front of the layer, posenet.py:25-28); post(t) = t * out_scale[n] +
+ * out_shift[n] when out_scale != NULL (eval-mode BatchNorm1d behind it, cheby_graph_conv.py:40-41), then ReLU when relu_out.
+ * weight [n][fin * planes], bias / res may be NULL. */
+int hn_linear_f32(const float* a0, const float* a1, const float* a2, int planes, int m, int fin, const float* weight,
+                  const float* bias, int n, const float* in_scale, const float* in_shift, const float* out_scale,
+                  const float* out_shift, int relu_out, const float* res, float* y, void* stream);
+/* Residual of a mesh block (meshnet.py:107-114, 69-76): out[r * up + j][f] = x[r][f] + interp(skip[r][0..fskip), f) for
+ * j < up, where interp is F.interpolate(mode='linear', align_corners=False) to fout samples along the FEATURE axis and up = 2
+ * is the nearest x2 vertex upsample.  x [rows][fout], skip [rows][fskip], out [rows * up][fout]. */
+int hn_mesh_residual_upsample(const float* x, const float* skip, int rows, int fout, int fskip, int up, float* out,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

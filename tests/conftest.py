@@ -6,7 +6,8 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "handnet-pipeline_b200")
-for p in (PKG, ROOT):
+P2M = os.path.join(PKG, "pose2mesh", "lib")            # `import models.pose2mesh_net`, as ros_demo.py:22-30 sets its path up
+for p in (P2M, PKG, ROOT):
     if p not in sys.path:
         sys.path.insert(0, p)
 

@@ -171,3 +171,43 @@ def test_handnet_vga_matches_reference(golden):
     _same(sample(depth_batch)[0], fx["depth_batch_s"])
     torch.testing.assert_close(final, fx["final"], rtol=1e-3, atol=1e-3)
     assert hit.all()
+
+
+# ------------------------------------------------------------------------------------------------
+# pose2mesh (last row): oracle and the mirrored modules against the reference-generated golden case
+# ------------------------------------------------------------------------------------------------
+def _dense_laplacians(case):
+    out = []
+    for c in case["graph_L"]:
+        L = torch.zeros(c["shape"])
+        L.index_put_((c["row"], c["col"]), c["val"], accumulate=True)
+        out.append(L)
+    return out
+
+
+def test_pose2mesh_oracle_matches_reference(golden):
+    """oracle/pose2mesh_oracle.py == the unmodified FlatPose2Mesh (oracle/make_golden_pose2mesh.py) on the synthetic demo-shaped
+    case: weights regenerated from the seed (hn_b200.synth.fill_state_dict), Laplacians from the golden file."""
+    from hn_b200 import synth
+    from oracle import pose2mesh_oracle
+    case = golden("pose2mesh_case.pt")
+    sd = synth.fill_state_dict(case["shapes"], seed=case["seed"])
+    mesh, pose3d = pose2mesh_oracle.flat_pose2mesh(sd, _dense_laplacians(case), case["pose2d"])
+    torch.testing.assert_close(pose3d, case["pose3d"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(mesh, case["mesh"], rtol=1e-4, atol=1e-4)
+
+
+def test_pose2mesh_modules_mirror_the_reference_state_dict(golden):
+    """models.pose2mesh_net.get_model(21, graph_L) (ros_demo.py:145) of this package has exactly the reference's state-dict keys
+    and shapes, so checkpoint['model_state_dict'] loads unchanged (ros_demo.py:146-147)."""
+    import scipy.sparse as sp
+    import models.pose2mesh_net as net
+    case = golden("pose2mesh_case.pt")
+    graph_L = [sp.coo_matrix((c["val"].numpy(), (c["row"].numpy(), c["col"].numpy())), shape=c["shape"]).tocsr()
+               for c in case["graph_L"]]
+    m = net.get_model(21, graph_L)
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, tuple(s)) for k, s in case["shapes"]]
+    assert len(graph_L) == 7, "the caller's list is not modified (the reference deletes the 48 x 48 level in place)"
+    m.eval()
+    with pytest.raises(RuntimeError):
+        m(case["pose2d"])                       # CPU tensors: no CPU path
