@@ -361,7 +361,8 @@ def run_main(ctx: Ctx):
 
         extras = None
         if rank == 0 and world == 1 and not args.no_extras:
-            extras = {"fcos_b8": run_fcos_b8(ctx, step), "post_stress": run_post_stress(ctx, net)}
+            extras = {"fcos_b8": run_fcos_b8(ctx, step), "post_stress": run_post_stress(ctx, net),
+                      "pose2mesh": run_pose2mesh(ctx, with_cpu=not args.no_cpu_baseline)}
         hd = None
         if not args.no_extras:
             hd = run_hd1080(ctx, net, quick=True)
@@ -537,6 +538,72 @@ def run_post_stress(ctx: Ctx, net):
                             "traffic n*ceil(n/64)*8 B each way as the stated definition"}}
 
 
+def run_pose2mesh(ctx: Ctx, with_cpu: bool):
+    """SURVEY.md 8f, last row: pose2mesh lifting (21 joints -> 1024-vertex mesh) behind models.pose2mesh_net.get_model, on the
+    demo-shaped synthetic case of tests/golden/pose2mesh_case.pt (graph Laplacians from the reference's own coarsening of an
+    icosphere, seeded weights): one CUDA graph per batch of 8 hands.  The forward streams 298 MB of fp32 weights whatever the
+    batch (the 4096-wide PoseNet), so the roofline is HBM: weight bytes / time."""
+    import scipy.sparse as sp
+    sys.path.insert(0, os.path.join(ROOT, "handnet-pipeline_b200", "pose2mesh", "lib"))
+    import models.pose2mesh_net as p2m
+    from hn_b200 import synth
+    case = torch.load(os.path.join(ROOT, "tests", "golden", "pose2mesh_case.pt"), weights_only=False)
+    graph_L = [sp.coo_matrix((c["val"].numpy(), (c["row"].numpy(), c["col"].numpy())), shape=c["shape"]).tocsr()
+               for c in case["graph_L"]]
+    sd = synth.fill_state_dict(case["shapes"], seed=case["seed"])
+    model = p2m.get_model(21, graph_L)
+    model.load_state_dict(sd)
+    model = model.to(ctx.dev).eval()
+    hands = 8
+    g = torch.Generator().manual_seed(3)
+    joints = torch.randn(hands, 21, 2, generator=g).to(ctx.dev)
+    peaks = load_peaks()
+    out = {}
+    with torch.no_grad():
+        for _ in range(3):
+            model(joints)
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream(device=ctx.dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            model(joints)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph, stream=side):
+                mesh, pose3d = model(joints)
+        torch.cuda.synchronize()
+        reps = max(10, ctx.args.steps // 2)
+        ts = []
+        for _ in range(reps):
+            ctx.l2_flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        ms = ts[len(ts) // 2]
+    wbytes = sum(int(v.numel()) * 4 for k, v in sd.items() if v.dtype == torch.float32 and v.dim() == 2)
+    out = {"value": hands / (ms * 1e-3), "unit": "hands/s", "ms_per_batch": ms, "hands_per_batch": hands,
+           "workload": "SURVEY 8f: pose2mesh lifting, 21 joints -> 1024-vertex mesh, 8 hands per CUDA-graph replay (L2 flushed)",
+           "weight_bytes": wbytes, "gb_per_s": wbytes / (ms * 1e-3) / 1e9, "hbm_frac": wbytes / (ms * 1e-3) / 1e9 / peaks["hbm"]}
+    if with_cpu:
+        from oracle import pose2mesh_oracle                        # CPU baseline leg only
+        dense = []
+        for c in case["graph_L"]:
+            L = torch.zeros(c["shape"])
+            L.index_put_((c["row"], c["col"]), c["val"], accumulate=True)
+            dense.append(L)
+        jc = joints.cpu()
+        pose2mesh_oracle.flat_pose2mesh(sd, dense, jc)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            pose2mesh_oracle.flat_pose2mesh(sd, dense, jc)
+        out["cpu_baseline"] = {"value": 3 * hands / (time.perf_counter() - t0), "unit": "hands/s", "cores": os.cpu_count() or 1,
+                               "kind": "port", "sample": "3 batches of 8 hands (oracle/pose2mesh_oracle.py, dense torch)"}
+    return out
+
+
 def run_hd1080(ctx: Ctx, net, quick: bool):
     """BASELINE.json configs[4]: 1920x1080 frames, GLOBAL batch 256 split over the ranks (strong scaling: 256 / 128 / 64 /
     32 frames per GPU at 1 / 2 / 4 / 8 GPUs), each rank streaming its slice through the pipeline in steps of 8 frames;
@@ -571,7 +638,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--config", default="e2e", choices=["e2e", "a2j_cpu", "fcos_b8", "post_stress", "hd1080"],
+    ap.add_argument("--config", default="e2e", choices=["e2e", "a2j_cpu", "fcos_b8", "post_stress", "hd1080", "pose2mesh"],
                     help="e2e (default, BASELINE.json configs[2] per-GPU slice, with the others as extra keys) or one of the "
                          "other BASELINE.json configs alone")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -600,6 +667,8 @@ def main():
                     out = run_hd1080(ctx, net, quick=False)
                 elif args.config == "post_stress":
                     out = run_post_stress(ctx, net)
+                elif args.config == "pose2mesh":
+                    out = run_pose2mesh(ctx, with_cpu=not args.no_cpu_baseline)
                 else:
                     from hn_b200.runtime import GraphedHandNet
                     step = GraphedHandNet(net, FRAMES_PER_GPU, IMG_H, IMG_W)

@@ -42,7 +42,7 @@ cheby_spmm_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col, 
 //   post(t) = t * out_scale[n] + out_shift[n], ReLU when relu_out              (eval BatchNorm1d behind: cheby_graph_conv.py:40-41)
 // A block = 8 warps = 8 output columns x a chunk of LIN_ROWS rows; the chunk's inputs are staged in shared memory K tile by
 // K tile (pre applied once), every warp streams its weight row with coalesced loads and keeps LIN_ROWS accumulators.
-constexpr int LIN_ROWS = 16, LIN_KT = 512, LIN_COLS = 8;
+constexpr int LIN_ROWS = 8, LIN_KT = 1024, LIN_COLS = 8;
 struct LinArgs {
   const float* a[3];
   const float* w;
@@ -58,7 +58,7 @@ struct LinArgs {
 
 __global__ void __launch_bounds__(32 * LIN_COLS)
 linear_kernel(const LinArgs p) {
-  __shared__ float xs[LIN_ROWS][LIN_KT];
+  __shared__ __align__(16) float xs[LIN_ROWS][LIN_KT];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = blockIdx.x * LIN_COLS + warp;
   const int m0 = blockIdx.y * LIN_ROWS;
@@ -67,23 +67,58 @@ linear_kernel(const LinArgs p) {
   float acc[LIN_ROWS];
 #pragma unroll
   for (int r = 0; r < LIN_ROWS; ++r) acc[r] = 0.f;
+  for (int i = threadIdx.x; i < LIN_ROWS * LIN_KT; i += blockDim.x) xs[i / LIN_KT][i % LIN_KT] = 0.f;
   for (int k0 = 0; k0 < kd; k0 += LIN_KT) {
     const int kt = min(LIN_KT, kd - k0);
     __syncthreads();
-    for (int i = threadIdx.x; i < rows * kt; i += blockDim.x) {
-      const int r = i / kt, kk = k0 + i - r * kt;
-      const int f = kk / p.planes, pl = kk - f * p.planes;
-      float a = __ldg(p.a[pl] + (size_t)(m0 + r) * p.fin + f);
-      if (p.in_scale) a = fmaxf(fmaf(a, __ldg(p.in_scale + kk), __ldg(p.in_shift + kk)), 0.f);
-      xs[r][i - r * kt] = a;
+    // (eight independent loads per thread in flight: staged one element at a time this loop was a chain of load latencies)
+    for (int i0 = threadIdx.x; i0 < rows * kt; i0 += 8 * blockDim.x) {
+      float a[8], sc[8], sh[8];
+      int rr[8], cc[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * blockDim.x;
+        const bool ok = i < rows * kt;
+        const int r = ok ? i / kt : 0, c = ok ? i - r * kt : 0, kk = k0 + c;
+        const int f = p.planes == 1 ? kk : (p.planes == 3 ? kk / 3 : kk >> 1), pl = kk - f * p.planes;
+        rr[u] = ok ? r : -1;
+        cc[u] = c;
+        a[u] = __ldg(p.a[pl] + (size_t)(m0 + r) * p.fin + f);
+        sc[u] = p.in_scale ? __ldg(p.in_scale + kk) : 1.f;
+        sh[u] = p.in_scale ? __ldg(p.in_shift + kk) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (rr[u] >= 0) xs[rr[u]][cc[u]] = p.in_scale ? fmaxf(fmaf(a[u], sc[u], sh[u]), 0.f) : a[u];
     }
     __syncthreads();
     if (n < p.n) {
       const float* wr = p.w + (size_t)n * kd + k0;
-      for (int k = lane; k < kt; k += 32) {
-        const float wv = __ldg(wr + k);
+      if ((kd & 3) == 0 && (kt & 127) == 0 && (reinterpret_cast<uintptr_t>(p.w) & 15) == 0) {
+        // weight streaming: 16 bytes per lane and load, four loads in flight per lane (a warp has 2 KB on the way)
+#pragma unroll 1
+        for (int k = lane * 4; k < kt; k += 512) {
+          float4 wv[4];
 #pragma unroll
-        for (int r = 0; r < LIN_ROWS; ++r) acc[r] = fmaf(wv, xs[r][k], acc[r]);      // (rows beyond `rows` hold stale finite data)
+          for (int u = 0; u < 4; ++u)
+            wv[u] = (k + u * 128 < kt) ? __ldg(reinterpret_cast<const float4*>(wr + k + u * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (k + u * 128 < kt) {
+#pragma unroll
+              for (int r = 0; r < LIN_ROWS; ++r) {
+                const float4 xv = *reinterpret_cast<const float4*>(&xs[r][k + u * 128]);
+                acc[r] = fmaf(wv[u].x, xv.x, fmaf(wv[u].y, xv.y, fmaf(wv[u].z, xv.z, fmaf(wv[u].w, xv.w, acc[r]))));
+              }
+            }
+          }
+        }
+      } else {
+        for (int k = lane; k < kt; k += 32) {
+          const float wv = __ldg(wr + k);
+#pragma unroll
+          for (int r = 0; r < LIN_ROWS; ++r) acc[r] = fmaf(wv, xs[r][k], acc[r]);    // (rows beyond `rows` hold stale finite data)
+        }
       }
     }
   }
@@ -99,6 +134,88 @@ linear_kernel(const LinArgs p) {
       if (p.relu_out) v = fmaxf(v, 0.f);
       if (p.res) v += p.res[(size_t)(m0 + r) * p.n + n];
       p.y[(size_t)(m0 + r) * p.n + n] = v;
+    }
+  }
+}
+
+// Tall inputs (the mesh levels: M = hands x vertices >= 64 rows, K <= 768, N <= 256) are ordinary fp32 GEMMs: 64 x 64 block
+// tile, 4 x 4 accumulators per thread, K tiles of 16 staged (transposed) in shared memory, same pre / post as linear_kernel.
+constexpr int GT = 64, GK = 32, GE = GT * GK / 256;        // GE elements of A and of W per thread and K tile
+__global__ void __launch_bounds__(256)
+linear_tiled_kernel(const LinArgs p) {
+  __shared__ __align__(16) float as[2][GK][GT + 4], ws[2][GK][GT + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;          // thread -> columns 4*tx.., rows 4*ty..
+  const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+  const int kd = p.fin * p.planes;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // 64 rows x 32 k of A and of W per K tile: 8 elements per thread each, k fastest across threads (coalesced along K).  The
+  // next tile's elements are fetched into registers while the current one is multiplied: a block's K loop is a chain of
+  // global-load latencies otherwise (48 tiles x ~3 us on the 768-wide layers, whatever the grid).
+  float ra[GE], rw[GE];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int e = 0; e < GE; ++e) {
+      const int idx = threadIdx.x + e * 256;
+      const int r = idx / GK, kk = k0 + (idx % GK);
+      float a = 0.f, w = 0.f;
+      if (kk < kd) {
+        if (m0 + r < p.m) {
+          const int f = p.planes == 1 ? kk : (p.planes == 3 ? kk / 3 : kk >> 1), pl = kk - f * p.planes;
+          a = __ldg(p.a[pl] + (size_t)(m0 + r) * p.fin + f);
+          if (p.in_scale) a = fmaxf(fmaf(a, __ldg(p.in_scale + kk), __ldg(p.in_shift + kk)), 0.f);
+        }
+        if (n0 + r < p.n) w = __ldg(p.w + (size_t)(n0 + r) * kd + kk);
+      }
+      ra[e] = a;
+      rw[e] = w;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int e = 0; e < GE; ++e) {
+      const int idx = threadIdx.x + e * 256;
+      as[buf][idx % GK][idx / GK] = ra[e];
+      ws[buf][idx % GK][idx / GK] = rw[e];
+    }
+  };
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < kd; k0 += GK) {
+    const bool more = k0 + GK < kd;
+    if (more) fetch(k0 + GK);
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&as[buf][k][4 * ty]);
+      const float4 wv = *reinterpret_cast<const float4*>(&ws[buf][k][4 * tx]);
+      const float a4[4] = {av.x, av.y, av.z, av.w}, w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], w4[j], acc[i][j]);
+    }
+    if (more) stash(buf ^ 1);                                         // (the other buffer: nobody reads it in this iteration)
+    __syncthreads();
+    buf ^= 1;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + 4 * ty + i;
+    if (m >= p.m) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + 4 * tx + j;
+      if (n >= p.n) continue;
+      float v = acc[i][j] + (p.bias ? __ldg(p.bias + n) : 0.f);
+      if (p.out_scale) v = fmaf(v, __ldg(p.out_scale + n), __ldg(p.out_shift + n));
+      if (p.relu_out) v = fmaxf(v, 0.f);
+      if (p.res) v += p.res[(size_t)m * p.n + n];
+      p.y[(size_t)m * p.n + n] = v;
     }
   }
 }
@@ -154,8 +271,13 @@ extern "C" int hn_linear_f32(const float* a0, const float* a1, const float* a2, 
   p.in_scale = in_scale; p.in_shift = in_shift; p.out_scale = out_scale; p.out_shift = out_shift;
   p.res = res; p.y = y;
   p.m = m; p.n = n; p.fin = fin; p.planes = planes; p.relu_out = relu_out;
-  dim3 grid(hn_div_up(n, LIN_COLS), hn_div_up(m, LIN_ROWS));
-  linear_kernel<<<grid, 32 * LIN_COLS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  if (m >= 64) {                                                    // mesh levels: a tiled GEMM; few rows (PoseNet, fc): weight streaming
+    dim3 grid(hn_div_up(n, GT), hn_div_up(m, GT));
+    linear_tiled_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  } else {
+    dim3 grid(hn_div_up(n, LIN_COLS), hn_div_up(m, LIN_ROWS));
+    linear_kernel<<<grid, 32 * LIN_COLS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  }
   hn_count_launch();
   HN_LAUNCH_CHECK();
   return HN_OK;

@@ -25,15 +25,24 @@ def as_graph(L, device) -> "ops.CsrGraph":
     return g[1]
 
 
+_bn_cache = {}
+
+
 def bn_affine(bn):
-    """Eval-mode BatchNorm1d as (scale, shift)."""
+    """Eval-mode BatchNorm1d as (scale, shift), folded once per set of parameter versions."""
     if bn is None:
         return None
     if bn.training:
         raise NotImplementedError("pose2mesh on the B200 build is inference only: call .eval() (BatchNorm uses running statistics)")
-    scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float().contiguous()
-    shift = (bn.bias - bn.running_mean * scale).detach().float().contiguous()
-    return scale, shift
+    ts = (bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    key = tuple((t.data_ptr(), -1 if t.is_inference() else t._version) for t in ts)      # (inference tensors are immutable)
+    hit = _bn_cache.get(id(bn))
+    if hit is None or hit[0] != key:
+        scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float().contiguous()
+        shift = (bn.bias - bn.running_mean * scale).detach().float().contiguous()
+        hit = (key, scale, shift)
+        _bn_cache[id(bn)] = hit
+    return hit[1], hit[2]
 
 
 def graph_conv_cheby(x, cl, bn, L, Fout, K, relu: bool = False):
