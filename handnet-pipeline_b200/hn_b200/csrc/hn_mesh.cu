@@ -138,6 +138,75 @@ linear_kernel(const LinArgs p) {
   }
 }
 
+// Few rows, long K (the PoseNet layers: <= 8 hands x 4096 -> 4096, the joints -> mesh lift): weight streaming.  The whole
+// (transformed) input sits in shared memory, staged once per block; a block is 16 warps, a warp owns one output column at a
+// time and streams its weight row with 16-byte loads, eight in flight per lane, no barrier inside the column loop.  One block
+// per SM walks the columns.
+constexpr int GV_ROWS = 8, GV_WARPS = 16;
+__global__ void __launch_bounds__(32 * GV_WARPS)
+linear_gemv_kernel(const LinArgs p) {
+  extern __shared__ __align__(16) float gx[];                      // [rows][kd]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int kd = p.fin * p.planes;
+  for (int i0 = threadIdx.x; i0 < p.m * kd; i0 += 8 * blockDim.x) {
+    float a[8], sc[8], sh[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * blockDim.x;
+      const bool ok = i < p.m * kd;
+      const int r = ok ? i / kd : 0, kk = ok ? i - r * kd : 0;
+      const int f = p.planes == 1 ? kk : (p.planes == 3 ? kk / 3 : kk >> 1), pl = kk - f * p.planes;
+      a[u] = __ldg(p.a[pl] + (size_t)r * p.fin + f);
+      sc[u] = p.in_scale ? __ldg(p.in_scale + kk) : 1.f;
+      sh[u] = p.in_scale ? __ldg(p.in_shift + kk) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < p.m * kd) gx[i] = p.in_scale ? fmaxf(fmaf(a[u], sc[u], sh[u]), 0.f) : a[u];
+    }
+  }
+  __syncthreads();
+  for (int n = blockIdx.x * GV_WARPS + warp; n < p.n; n += gridDim.x * GV_WARPS) {
+    const float* wr = p.w + (size_t)n * kd;
+    float acc[GV_ROWS];
+#pragma unroll
+    for (int r = 0; r < GV_ROWS; ++r) acc[r] = 0.f;
+#pragma unroll 1
+    for (int k = lane * 4; k < kd; k += 8 * 128) {
+      float4 wv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        wv[u] = (k + u * 128 < kd) ? __ldg(reinterpret_cast<const float4*>(wr + k + u * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (k + u * 128 < kd) {
+#pragma unroll
+          for (int r = 0; r < GV_ROWS; ++r) {
+            if (r < p.m) {
+              const float4 xv = *reinterpret_cast<const float4*>(gx + (size_t)r * kd + k + u * 128);
+              acc[r] = fmaf(wv[u].x, xv.x, fmaf(wv[u].y, xv.y, fmaf(wv[u].z, xv.z, fmaf(wv[u].w, xv.w, acc[r]))));
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < GV_ROWS; ++r) {
+      float v = acc[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && r < p.m) {
+        v += p.bias ? __ldg(p.bias + n) : 0.f;
+        if (p.out_scale) v = fmaf(v, __ldg(p.out_scale + n), __ldg(p.out_shift + n));
+        if (p.relu_out) v = fmaxf(v, 0.f);
+        if (p.res) v += p.res[(size_t)r * p.n + n];
+        p.y[(size_t)r * p.n + n] = v;
+      }
+    }
+  }
+}
+
 // Tall inputs (the mesh levels: M = hands x vertices >= 64 rows, K <= 768, N <= 256) are ordinary fp32 GEMMs: 64 x 64 block
 // tile, 4 x 4 accumulators per thread, K tiles of 16 staged (transposed) in shared memory, same pre / post as linear_kernel.
 constexpr int GT = 64, GK = 32, GE = GT * GK / 256;        // GE elements of A and of W per thread and K tile
@@ -271,7 +340,16 @@ extern "C" int hn_linear_f32(const float* a0, const float* a1, const float* a2, 
   p.in_scale = in_scale; p.in_shift = in_shift; p.out_scale = out_scale; p.out_shift = out_shift;
   p.res = res; p.y = y;
   p.m = m; p.n = n; p.fin = fin; p.planes = planes; p.relu_out = relu_out;
-  if (m >= 64) {                                                    // mesh levels: a tiled GEMM; few rows (PoseNet, fc): weight streaming
+  const long long kd = (long long)fin * planes;
+  if (m <= GV_ROWS && kd >= 512 && kd % 4 == 0 && (size_t)m * kd * 4 <= 200 * 1024 && (reinterpret_cast<uintptr_t>(weight) & 15) == 0) {
+    static bool attr = false;
+    if (!attr) {
+      HN_CHECK_CUDA(cudaFuncSetAttribute(linear_gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
+    }
+    const int blocks = hn_div_up(n, GV_WARPS) < hn_num_sms() ? hn_div_up(n, GV_WARPS) : hn_num_sms();
+    linear_gemv_kernel<<<blocks, 32 * GV_WARPS, (size_t)m * kd * 4, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  } else if (m >= 64) {                                             // mesh levels: a tiled GEMM; else: row chunks x 8 columns per block
     dim3 grid(hn_div_up(n, GT), hn_div_up(m, GT));
     linear_tiled_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   } else {
