@@ -207,47 +207,56 @@ linear_gemv_kernel(const LinArgs p) {
   }
 }
 
-// Tall inputs (the mesh levels: M = hands x vertices >= 64 rows, K <= 768, N <= 256) are ordinary fp32 GEMMs: 64 x 64 block
-// tile, 4 x 4 accumulators per thread, K tiles of 16 staged (transposed) in shared memory, same pre / post as linear_kernel.
-constexpr int GT = 64, GK = 32, GE = GT * GK / 256;        // GE elements of A and of W per thread and K tile
+// Tall inputs (the mesh levels: M = hands x vertices >= 64 rows, K <= 768, N <= 256) are ordinary fp32 GEMMs: GM x 64 block
+// tile (GM = 128 when there are enough rows to fill the SMs, else 64), (GM / 16) x 4 accumulators per thread, K tiles of 32
+// staged (transposed) in shared memory with the next tile prefetched into registers, same pre / post as linear_kernel.
+constexpr int GN_ = 64;
+template <int GM, int GK>
 __global__ void __launch_bounds__(256)
 linear_tiled_kernel(const LinArgs p) {
-  __shared__ __align__(16) float as[2][GK][GT + 4], ws[2][GK][GT + 4];
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;          // thread -> columns 4*tx.., rows 4*ty..
-  const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+  constexpr int RA = GM / 16;                                       // rows per thread
+  constexpr int EA = GM * GK / 256, EW = GN_ * GK / 256;            // elements of A / W a thread moves per K tile
+  __shared__ __align__(16) float as[2][GK][GM + 4], ws[2][GK][GN_ + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;           // thread -> columns 4*tx.., rows RA*ty..
+  const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN_;
   const int kd = p.fin * p.planes;
-  float acc[4][4];
+  float acc[RA][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < RA; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  // 64 rows x 32 k of A and of W per K tile: 8 elements per thread each, k fastest across threads (coalesced along K).  The
-  // next tile's elements are fetched into registers while the current one is multiplied: a block's K loop is a chain of
-  // global-load latencies otherwise (48 tiles x ~3 us on the 768-wide layers, whatever the grid).
-  float ra[GE], rw[GE];
+  // k fastest across threads (coalesced along K).  The next tile's elements are fetched into registers while the current one is
+  // multiplied: a block's K loop is a chain of global-load latencies otherwise.
+  float ra[EA], rw[EW];
   auto fetch = [&](int k0) {
 #pragma unroll
-    for (int e = 0; e < GE; ++e) {
+    for (int e = 0; e < EA; ++e) {
       const int idx = threadIdx.x + e * 256;
       const int r = idx / GK, kk = k0 + (idx % GK);
-      float a = 0.f, w = 0.f;
-      if (kk < kd) {
-        if (m0 + r < p.m) {
-          const int f = p.planes == 1 ? kk : (p.planes == 3 ? kk / 3 : kk >> 1), pl = kk - f * p.planes;
-          a = __ldg(p.a[pl] + (size_t)(m0 + r) * p.fin + f);
-          if (p.in_scale) a = fmaxf(fmaf(a, __ldg(p.in_scale + kk), __ldg(p.in_shift + kk)), 0.f);
-        }
-        if (n0 + r < p.n) w = __ldg(p.w + (size_t)(n0 + r) * kd + kk);
+      float a = 0.f;
+      if (kk < kd && m0 + r < p.m) {
+        const int f = p.planes == 1 ? kk : (p.planes == 3 ? kk / 3 : kk >> 1), pl = kk - f * p.planes;
+        a = __ldg(p.a[pl] + (size_t)(m0 + r) * p.fin + f);
+        if (p.in_scale) a = fmaxf(fmaf(a, __ldg(p.in_scale + kk), __ldg(p.in_shift + kk)), 0.f);
       }
       ra[e] = a;
-      rw[e] = w;
+    }
+#pragma unroll
+    for (int e = 0; e < EW; ++e) {
+      const int idx = threadIdx.x + e * 256;
+      const int r = idx / GK, kk = k0 + (idx % GK);
+      rw[e] = (kk < kd && n0 + r < p.n) ? __ldg(p.w + (size_t)(n0 + r) * kd + kk) : 0.f;
     }
   };
   auto stash = [&](int buf) {
 #pragma unroll
-    for (int e = 0; e < GE; ++e) {
+    for (int e = 0; e < EA; ++e) {
       const int idx = threadIdx.x + e * 256;
       as[buf][idx % GK][idx / GK] = ra[e];
+    }
+#pragma unroll
+    for (int e = 0; e < EW; ++e) {
+      const int idx = threadIdx.x + e * 256;
       ws[buf][idx % GK][idx / GK] = rw[e];
     }
   };
@@ -260,11 +269,16 @@ linear_tiled_kernel(const LinArgs p) {
     if (more) fetch(k0 + GK);
 #pragma unroll
     for (int k = 0; k < GK; ++k) {
-      const float4 av = *reinterpret_cast<const float4*>(&as[buf][k][4 * ty]);
-      const float4 wv = *reinterpret_cast<const float4*>(&ws[buf][k][4 * tx]);
-      const float a4[4] = {av.x, av.y, av.z, av.w}, w4[4] = {wv.x, wv.y, wv.z, wv.w};
+      float a4[RA];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RA; i += 4) {
+        const float4 av = *reinterpret_cast<const float4*>(&as[buf][k][RA * ty + i]);
+        a4[i] = av.x; a4[i + 1] = av.y; a4[i + 2] = av.z; a4[i + 3] = av.w;
+      }
+      const float4 wv = *reinterpret_cast<const float4*>(&ws[buf][k][4 * tx]);
+      const float w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int i = 0; i < RA; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], w4[j], acc[i][j]);
     }
@@ -273,8 +287,8 @@ linear_tiled_kernel(const LinArgs p) {
     buf ^= 1;
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + 4 * ty + i;
+  for (int i = 0; i < RA; ++i) {
+    const int m = m0 + RA * ty + i;
     if (m >= p.m) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -350,8 +364,13 @@ extern "C" int hn_linear_f32(const float* a0, const float* a1, const float* a2, 
     const int blocks = hn_div_up(n, GV_WARPS) < hn_num_sms() ? hn_div_up(n, GV_WARPS) : hn_num_sms();
     linear_gemv_kernel<<<blocks, 32 * GV_WARPS, (size_t)m * kd * 4, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   } else if (m >= 64) {                                             // mesh levels: a tiled GEMM; else: row chunks x 8 columns per block
-    dim3 grid(hn_div_up(n, GT), hn_div_up(m, GT));
-    linear_tiled_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    if ((long long)hn_div_up(m, 128) * hn_div_up(n, GN_) >= hn_num_sms()) {
+      dim3 grid(hn_div_up(n, GN_), hn_div_up(m, 128));
+      linear_tiled_kernel<128, 16><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    } else {
+      dim3 grid(hn_div_up(n, GN_), hn_div_up(m, 64));
+      linear_tiled_kernel<64, 32><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    }
   } else {
     dim3 grid(hn_div_up(n, LIN_COLS), hn_div_up(m, LIN_ROWS));
     linear_kernel<<<grid, 32 * LIN_COLS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
