@@ -416,6 +416,14 @@ def conv_roofline(step, step_ms, conv_profile, conv_flops_per_step):
     """Whole-kernel roofline: every conv launch of one step.  The launches are timed back to back inside a step (behind a
     spin kernel, at the clocks a long step settles at), so the denominator is the SUSTAINED measured bf16 peak."""
     peaks = load_peaks()
+    # the same launches with every SM allowed to the tower convolutions (the product caps them to ~80 % of the SMs: alone they
+    # are then slower, in the step they are as fast and leave SMs to the kernels that run next to them)
+    from hn_b200 import runtime as _rt
+    cap_saved, _rt.TOWER_CTA_CAP = _rt.TOWER_CTA_CAP, 0
+    try:
+        uncapped_ms, _ = conv_profile(step, repeats=2)
+    finally:
+        _rt.TOWER_CTA_CAP = cap_saved
     conv_ms, n_conv = conv_profile(step, repeats=3)
     flops = conv_flops_per_step(step)
     tbl = step.last_conv_table
@@ -449,6 +457,9 @@ def conv_roofline(step, step_ms, conv_profile, conv_flops_per_step):
             "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": peaks["source"] + ", sustained figure: launches timed back to back inside a step",
             "launches_per_step": n_conv, "ms_per_step_serial": conv_ms, "flops_per_step": flops,
+            "tower_cta_cap": cap_saved if cap_saved >= 0 else "80 % of the SMs",
+            "frac_with_all_sms_per_launch": flops / (uncapped_ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
+            "frac_of_step_time": flops / (step_ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
             "frac_of_burst": ach_all / peaks["bf16_burst"], "best_shape": best}
 
 

@@ -95,6 +95,11 @@ FUSE_LEVELS = True          # FCOS towers / output convolutions / GroupNorm: ONE
 import os as _os
 POSE_PRIORITY = _os.environ.get("HN_POSE_PRIO", "high")      # priority of the pose stream relative to the detect stream
 STEM_WINDOW = _os.environ.get("HN_STEM_WINDOW", "1") != "0"    # detector stem: plain canvas + window descriptors (0: row-pair frame)
+# CTAs per fused 256-wide tower convolution launch (HN_TOWER_CTAS; -1 = 80 % of the SMs, 0 = no cap).  These launches are not
+# limited by the number of SMs (8 VGA frames, one B200: 148 / 140 / 124 / 108 / 98 / 84 CTAs -> towers phase 1126 / 1089 / 1083 /
+# 1085 / 1114 / 1202 us): capped to ~80 % they are as fast, and the SMs they leave run the GroupNorm pass of the other tower
+# and the pose stage of the previous step next to them.
+TOWER_CTA_CAP = int(_os.environ.get("HN_TOWER_CTAS", "-1"))
 DET_CTA_CAP = int(_os.environ.get("HN_DET_CTAS", "0"))       # CTAs per detector convolution launch (0 = all SMs): leaves SMs to the pose stage
 POSE_CTA_CAP = int(_os.environ.get("HN_POSE_CTAS", "0"))     # CTAs per pose-net convolution launch (0 = all SMs)
 POSE_PDL = _os.environ.get("HN_POSE_PDL", "1") != "0"        # programmatic dependent launch inside the pose stage
@@ -355,6 +360,8 @@ class FCOSExecutor:
                                   out_row_offset=pl.levels.starts[lvl], out_planar=True)
             return run
 
+        tower_cap = TOWER_CTA_CAP if TOWER_CTA_CAP >= 0 else (ops.device_info()[0] * 4 // 5) & ~1
+
         def tower_chain_levels(ti, t):
             # the reference applies the SAME tower modules to every level (fcos_utils/fcos.py:278-289, 378-380): one launch per
             # layer over the concatenated tile list of P3+P4+P5 (1169 tiles for 8 VGA frames = 8 full waves of 147 CTAs)
@@ -365,8 +372,12 @@ class FCOSExecutor:
                 for i, (conv, gamma, beta) in enumerate(w.towers[t]):
                     outs = [pl.tower[t][lvl][i & 1] for lvl in range(nl)]
                     sts = [pl.gn_stats[ti, i, lvl] for lvl in range(nl)]
+                    if tower_cap:
+                        ops.conv_cta_cap(tower_cap)
                     ops.conv2d_levels(xs, conv.w, cout=conv.cout, ksize=conv.k, shift=conv.shift, outs=outs, gn_stats=sts,
                                       gn_groups=32)
+                    if tower_cap:
+                        ops.conv_cta_cap(DET_CTA_CAP)
                     ops.groupnorm_relu_levels(outs, sts, 32, gamma, beta, GN_EPS)
                     xs = outs
                 oc, relu, buf = (w.cls_out, w.cls_relu, pl.cls_buf) if t == "cls" else (w.reg_out, w.reg_relu, pl.reg_buf)
