@@ -16,10 +16,12 @@ hard-coded 0.7 cut and every frame yields a hand crop (candidate / kept counts a
              depth maps and D2H of joints / crops / hit mask inside the timed region, host wall clock
   roofline   the dominant kernel (tcgen05 shifted-GEMM conv, ~87 % of a step): algorithmic conv FLOPs of ALL its launches
              in one step / their summed device time (CUDA events on the launch stream, launches back to back behind a
-             spin kernel), against the SUSTAINED measured bf16 peak; the best launch shape is a sub-key
+             spin kernel), against the SUSTAINED measured bf16 peak; the best launch shape is a sub-key.  `frac` is the
+             product's configuration (tower launches capped to 80 % of the SMs: slower alone, as fast in the step);
+             `frac_with_all_sms_per_launch` the same launches uncapped, `frac_of_step_time` conv FLOPs / the timed step
   cpu_baseline  the oracle (a torch-CPU restatement of the reference, oracle/) timed on this box's host cores
   extra_configs  BASELINE.json configs 1, 2, 4 and 5 (A2J on the CPU, FCOS alone, post-process stress, 1080p strong
-             scaling): `--config NAME` runs one of them alone
+             scaling) and the pose2mesh lifting network: `--config NAME` runs one of them alone
 
 `--impl reference` times that CPU restatement alone (the reference itself is Python that needs packages which
 are not installed on the box) on the same 8-frame batch per step.
