@@ -1,6 +1,8 @@
 // FCOS post-processing (fcos_utils/fcos.py:572-669) as batch-wide kernels:
-//   decode + score + threshold with ordered compaction        (P1-P4, anchors generated on the fly: A1)
-//   stable radix sort by score + 64x64 IoU bitmask + serial scan (P5, torchvision CPU NMS semantics, bit-exact)
+//   decode + score + threshold with ordered compaction, ONE pass (look-back over per-chunk survivor counts)
+//                                                              (P1-P4, anchors generated on the fly: A1)
+//   stable sort by score (rank by counting up to 1024 candidates, radix beyond) + 64x64 IoU bitmask + serial scan
+//                                                              (P5, torchvision CPU NMS semantics, bit-exact)
 //   gather of the kept detections + resize_boxes                (P6)
 // Integer/fp32 work on tiny data: coalesced vector loads, warp ballots/matches, no tensor cores.
 #include "hn_common.cuh"

@@ -3,7 +3,8 @@
 //   7x7/2 stem patches as GEMM rows (feeds hn_conv2d_bf16 for backbone.body.conv1 / Backbone.model.conv1)
 //   3x3/2 max pool (resnet maxpool)
 //   GroupNorm + ReLU of the FCOS towers (fcos_utils/fcos.py:232-240)
-// All are HBM/L2-bound streaming kernels: 16-byte vector accesses, one pass, no data reuse to stage.
+// All are HBM/L2-bound streaming kernels: 16-byte vector accesses, one pass.  (Two of them were instruction-bound until the end of
+// round 2 -- per-element index arithmetic and per-block coefficient set-up -- see preprocess_pairs_kernel, groupnorm_relu_kernel.)
 #include "hn_common.cuh"
 
 namespace {
