@@ -99,6 +99,10 @@ struct ConvParams {
   // overlapping-stride patch view of the canvas (build_conv)
   int stem_tpr, stem_h;                     // tiles per output row (0 = ordinary convolution), output rows per image
   int stem_win, stem_tile_w;                // window stem (see build_conv): output columns per tile (125; row-pair stem: 128)
+  int duo;                                  // unified stages, 3x3 stride 1, one N tile: a work item is TWO consecutive M tiles that
+                                            // share every weight box (stage = A box of tile 0 | A box of tile 1 | weight tiles).
+                                            // The <= 128-column layers run at the L2 throughput cap and 73 % of their L2 -> SM
+                                            // traffic is weights re-streamed for every M tile
   int epi_alt;                              // epilogue: the two warps of a lane quarter take alternate TILES (all chunks
                                             // of their tile) instead of alternate chunks of the same tile
   int m_tiles, n_tiles;
@@ -294,7 +298,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   const int lane = threadIdx.x & 31;
   // tile schedule: work item = (M tile, N tile, K split), N fastest, strided over the CTAs
   const int first_tile = PAIR ? blockIdx.x >> 1 : blockIdx.x, tile_stride = PAIR ? gridDim.x >> 1 : gridDim.x;
-  const int num_items = PAIR ? ((p.m_tiles + 1) >> 1) * n_tiles : p.m_tiles * n_tiles * splits;   // PAIR: pairs of M tiles
+  const bool duo = UNI && p.duo != 0;                    // (launch constant)
+  const int num_items = (PAIR || duo) ? ((p.m_tiles + 1) >> 1) * n_tiles : p.m_tiles * n_tiles * splits;   // pairs of M tiles
   const int s_base = k_steps / splits, s_rem = k_steps - s_base * splits;
 
   // The producer and MMA loops are single-instruction-stream code on the kernel's critical path (a 64-wide tile has
@@ -325,7 +330,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         if (hn_elect_one()) {
           int g0 = 0, cc0 = 0;
           for (int e = 0; e < early_b; ++e) {
-            hn_mbar_expect_tx(&a_full[e], (uint32_t)uni_stage_bytes);
+            hn_mbar_expect_tx(&a_full[e], (uint32_t)(uni_stage_bytes - ((duo && 2 * first_tile + 1 >= p.m_tiles) ? p.uni_plane_bytes : 0)));
             hn_tma_load_4d(a_ring + e * uni_stride + p.uni_a_bytes, &tm_b, &a_full[e], 0, nt0 * BN, cc0,
                            (p.grp_info[g0] >> 8) & 255);
             cc0 += uni_chunk_step;
@@ -354,6 +359,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       int mt = st, nt = 0;
       if (n_tiles > 1) { mt = st / n_tiles; nt = st - mt * n_tiles; }
       if constexpr (PAIR) mt = mt * 2 + cta_rank;
+      if (duo) mt *= 2;                                    // first tile of the pair; the second one is mt + 1
       int m0 = mt * BLOCK_M;
       const int n0 = nt * BN;
       // segments: the tile's rows, box shifts and tensor map are those of its pyramid level
@@ -398,10 +404,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             } else {
               uint8_t* sa = a_ring + a_stage * uni_stride;
               const bool b_pending = w_ == first_tile && step - s_begin < early_b;   // armed and B issued before the wait
-              if (!b_pending) hn_mbar_expect_tx(&a_full[a_stage], (uint32_t)uni_stage_bytes);
+              const bool second = duo && mt + 1 < p.m_tiles;   // (the last pair of an odd tile count is a single tile)
+              if (!b_pending)
+                hn_mbar_expect_tx(&a_full[a_stage], (uint32_t)(uni_stage_bytes - ((duo && !second) ? p.uni_plane_bytes : 0)));
               if (p.stem_tpr > 0) hn_tma_load_4d(sa, &tm_a, &a_full[a_stage], 0, st_ox, st_oy + cc, st_n);
               else if (p.uni_a_rank4) hn_tma_load_4d(sa, &tm_a, &a_full[a_stage], 0, m0 + shift, cc, info >> 24);
               else hn_tma_load_3d(sa, &tm_a, &a_full[a_stage], cc * BLOCK_K, m0 + shift, info >> 24);
+              if (second)
+                hn_tma_load_3d(sa + p.uni_plane_bytes, &tm_a, &a_full[a_stage], cc * BLOCK_K, m0 + BLOCK_M + shift, info >> 24);
               if (!b_pending) hn_tma_load_4d(sa + p.uni_a_bytes, &tm_b, &a_full[a_stage], 0, n0, cc, (info >> 8) & 255);
             }
           }
@@ -507,10 +517,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           cc = s_begin - g * cin_chunks;
         }
       }
-      const int buf = it & (C::NBUF - 1);
-      const uint32_t d_tmem = tmem_base + buf * BN;
+      int buf = it & (C::NBUF - 1);
+      uint32_t d_tmem = tmem_base + buf * BN, empty_parity = ((it >> C::NBUF_LOG) & 1) ^ 1;
+      bool duo_second = false;
+      if constexpr (UNI) {
+        if (duo) {                                           // an item = two M tiles = two adjacent accumulators
+          constexpr int GROUPS = C::NBUF / 2;
+          buf = it & (GROUPS - 1);
+          d_tmem = tmem_base + buf * 2 * BN;
+          empty_parity = ((it / GROUPS) & 1) ^ 1;
+          duo_second = 2 * w_ + 1 < p.m_tiles;
+        }
+      }
       int info = p.grp_info[g];
-      if (!HN_DBG(32)) hn_mbar_wait(&tmem_empty[buf], ((it >> C::NBUF_LOG) & 1) ^ 1);   // the epilogue has drained this buffer
+      if (!HN_DBG(32)) hn_mbar_wait(&tmem_empty[buf], empty_parity);   // the epilogue has drained this buffer
       hn_trace(trace, 1, tri, 4);
       uint32_t accumulate = 0;
       if constexpr (UNI) {
@@ -541,6 +561,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
               if (nu > 2)
                 hn_umma_bf16_x4(d_tmem, desc_hi | (sa + ((units >> 16) & 3) * uni_plane_d + ((units >> 18) & 15) * ROW_D),
                                 desc_hi | (sb + ((units >> 22) & 3) * B_SLOT_D), idesc, 1u);
+              if (duo_second) {       // the pair's second tile: its A box one plane further, the next accumulator, the same weights
+                const uint32_t s2 = sa + uni_plane_d, d2 = d_tmem + BN;
+                hn_umma_bf16_x4(d2, desc_hi | (s2 + ((units >> 2) & 15) * ROW_D), desc_hi | (sb + ((units >> 6) & 3) * B_SLOT_D), idesc,
+                                accumulate);
+                if (nu > 1)
+                  hn_umma_bf16_x4(d2, desc_hi | (s2 + ((units >> 10) & 15) * ROW_D), desc_hi | (sb + ((units >> 14) & 3) * B_SLOT_D),
+                                  idesc, 1u);
+                if (nu > 2)
+                  hn_umma_bf16_x4(d2, desc_hi | (s2 + ((units >> 18) & 15) * ROW_D), desc_hi | (sb + ((units >> 22) & 3) * B_SLOT_D),
+                                  idesc, 1u);
+              }
             }
             hn_umma_commit_addr<1>(ea);                        // stage free once these MMAs have read it
             if (last) hn_umma_commit_addr<1>(tf);              // accumulator complete -> epilogue
@@ -695,8 +726,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     // tcgen05.ld, residual / store round trips); with both warps of a quarter on the SAME tile nothing overlaps it.  Here
     // warps 2-5 drain the even tiles and warps 6-9 the odd ones, so two tiles are in flight.  Each warp arrives twice on
     // tmem_empty (the barrier counts eight arrivals per tile).  scale/shift are staged once for both buffers.
+    // Duo items (two M tiles, two accumulators): warps 2-5 drain the first tile and warps 6-9 the second one, every chunk each.
     const bool alt = p.epi_alt != 0;
-    if (alt) {
+    const bool own_tile = alt || duo;          // this warp takes every chunk of its tile
+    if (own_tile) {
       for (int i = threadIdx.x - 64; i < BN; i += EPI_THREADS) {
         const float sc = (p.scale && i < p.cout) ? __ldg(p.scale + i) : 1.0f;
         const float sh = (p.shift && i < p.cout) ? __ldg(p.shift + i) : 0.0f;
@@ -710,11 +743,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       if (alt && (it & 1) != half) continue;
       const int st = splits > 1 ? w_ / splits : w_;
       if (warp == 2) hn_trace(trace, 2, tri, 1);
-      const int buf = it & (C::NBUF - 1);
-      const uint32_t acc_phase = (it >> C::NBUF_LOG) & 1;
+      int buf = it & (C::NBUF - 1);
+      uint32_t acc_phase = (it >> C::NBUF_LOG) & 1;
+      int tcol = buf * BN;                               // first TMEM column of this tile's accumulator
       int mt = st, nt = 0;
       if (n_tiles > 1) { mt = st / n_tiles; nt = st - mt * n_tiles; }
       if constexpr (PAIR) mt = mt * 2 + cta_rank;
+      if constexpr (UNI) {
+        if (duo) {
+          constexpr int GROUPS = C::NBUF / 2;
+          buf = it & (GROUPS - 1);
+          acc_phase = (it / GROUPS) & 1;
+          tcol = (buf * 2 + half) * BN;
+          mt = mt * 2 + half;
+        }
+      }
+      const bool absent = duo && mt >= p.m_tiles;        // second half of the single last pair: wait and hand back only
       const int n0 = nt * BN;
       // geometry of the tile's segment
       int g_rows = p.rows, g_hp = p.hp, g_wp = p.wp, g_nimg = p.n_img, g_tile0 = 0, g_gn_off = 0;
@@ -796,9 +840,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       const bool res_vec = p.res_mode != 0 && interior && vec32;
       uint32_t res_next[CHUNK / 2];
       constexpr int STEP = (BN / CHUNK >= 2) ? 2 * CHUNK : CHUNK;   // two warps interleave chunks when there are >= 2
-      const int step_rt = alt ? CHUNK : STEP;                       // (alternate-tile mode: this warp takes every chunk)
-      const int c_first = (!alt && BN / CHUNK >= 2) ? half * CHUNK : 0;
-      const bool idle_half = !alt && (BN / CHUNK < 2) && half == 1; // a single chunk: the second warp only arrives
+      const int step_rt = own_tile ? CHUNK : STEP;                  // (alternate-tile / duo mode: this warp takes every chunk)
+      const int c_first = (!own_tile && BN / CHUNK >= 2) ? half * CHUNK : 0;
+      const bool idle_half = !own_tile && (BN / CHUNK < 2) && half == 1; // a single chunk: the second warp only arrives
       const bool res_first = res_vec && !idle_half && n0 + c_first + CHUNK <= p.cout;
       if (res_first) {
 #pragma unroll
@@ -808,7 +852,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       hn_mbar_wait(&tmem_full[buf], acc_phase);
       hn_tc_fence_after();
       if (warp == 2) hn_trace(trace, 2, tri, 2);
-      const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + buf * BN;
+      const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + tcol;
 
       // Split-K: every work item stores its partial accumulator into its own slice of an fp32 scratch; the item that
       // arrives last (per-tile counter) adds the slices in split order -- a fixed summation order, so results do not
@@ -1061,7 +1105,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           }
         }
       };
-      const int c_end = (idle_half || HN_DBG(2) || !finalize) ? 0 : BN;
+      const int c_end = (idle_half || absent || HN_DBG(2) || !finalize) ? 0 : BN;
       // (TMEM loads one chunk ahead -- tcgen05.ld of chunk i+1 in flight while chunk i is scaled, packed and stored -- were
       // measured in round 1: isolated 256-wide layers +5 %, the whole step -2 % with 48 bytes of spills at the 168-register
       // cap; not built.)
@@ -1157,6 +1201,15 @@ bool pdl_enabled() {
   return v == 1;
 }
 
+bool duo_enabled() {            // HN_CONV_DUO=0: one M tile per work item everywhere
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HN_CONV_DUO");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int g_cta_cap = 0;      // hn_conv_set_cta_cap: upper bound on the CTAs of the following launches (0 = all SMs)
 int g_pdl_off = 0;      // hn_conv_set_pdl(0): the following launches do not use programmatic dependent launch
 
@@ -1170,7 +1223,7 @@ int launch(const CUtensorMap* ta, const CUtensorMap& tb, const ConvParams& p, cu
     attr_set = true;
   }
   // CTA pairs: a work item is a pair of M tiles and occupies a cluster of two CTAs (two SMs of one TPC)
-  const int items = PAIR ? ((p.m_tiles + 1) / 2) * p.n_tiles : p.m_tiles * p.n_tiles * p.splits;
+  const int items = (PAIR || p.duo) ? ((p.m_tiles + 1) / 2) * p.n_tiles : p.m_tiles * p.n_tiles * p.splits;
   // equal work per CTA: with w = ceil(tiles / SMs) waves, ceil(tiles / w) CTAs finish at the same time as a full grid
   // would and leave the other SMs to kernels of concurrent streams (graph branches, the pose net of the previous step)
   int sms = (g_cta_cap > 0 && g_cta_cap < hn_num_sms()) ? g_cta_cap : hn_num_sms();
@@ -1432,6 +1485,10 @@ int build_conv(const hn_conv_desc* d, int force_bn, int total_m_tiles, BuiltConv
   p.a_box_bytes = stem_win ? 8 * 2048 : box_rows * BLOCK_K * 2;
   p.k_steps = stem_win ? 1 : (uni && p.uni_chunk_step > 1) ? hn_div_up(p.cin_chunks, p.uni_chunk_step) : p.n_groups * p.cin_chunks;
   if (uni) {
+    // duo: two M tiles per work item behind one weight box (see ConvParams::duo)
+    p.duo = (duo_enabled() && d->kh == 3 && d->stride == 1 && p.n_tiles == 1 && total_m_tiles == 0 && a_planes == 1 &&
+             Cfg<128>::NBUF >= 2 && bn >= 64 && p.m_tiles >= 2 * hn_num_sms() && !(d->debug & 262144)) ? 1 : 0;
+    if (p.duo) a_planes = 2;
     p.uni_plane_bytes = box_rows * BLOCK_K * 2;
     p.uni_a_bytes = a_planes * p.uni_plane_bytes;
     p.uni_b_bytes = b_tiles * bn * BLOCK_K * 2;
@@ -1549,7 +1606,8 @@ int build_conv(const hn_conv_desc* d, int force_bn, int total_m_tiles, BuiltConv
       p.sk_ld = d->cout_pad;
     }
   }
-  p.epi_alt = (p.n_tiles == 1 && p.splits == 1 && !(d->debug & 32768) &&
+  HN_REQUIRE(!(p.duo && p.splits > 1), "hn_conv2d_bf16: internal: duo items with split-K");
+  p.epi_alt = (p.n_tiles == 1 && p.splits == 1 && !p.duo && !(d->debug & 32768) &&
                ((d->debug & 65536) || bn <= epi_alt_max_bn())) ? 1 : 0;
   // CTA pairs for the 256-wide layers that take the FAST epilogue: every CTA then holds half of each weight tile, so the
   // B ring is twice as deep in the same shared memory
@@ -1618,7 +1676,7 @@ int build_conv(const hn_conv_desc* d, int force_bn, int total_m_tiles, BuiltConv
                                 (cuuint64_t)(rb3 ? 3 : d->in_phases)};
     const cuuint64_t strides[2] = {(cuuint64_t)d->cin * 2,
                                    rb3 ? (cuuint64_t)d->dilation * p.wp * d->cin * 2 : (cuuint64_t)p.rows * d->cin * 2};
-    const cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)box_rows, (cuuint32_t)(rb3 ? 3 : (uni ? a_planes : 1))};
+    const cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)box_rows, (cuuint32_t)(rb3 ? 3 : ((uni && !p.duo) ? a_planes : 1))};   // (duo: the second plane is the next M tile's box)
     int rc = make_map(&ta, d->in, 3, dims, strides, box);
     if (rc) return rc;
   }

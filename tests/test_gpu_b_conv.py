@@ -122,6 +122,31 @@ def test_conv_epilogue_alternate_tiles(ops, shape):
     assert torch.equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("shape", [(3, 100, 136, 128, 128), (3, 100, 137, 128, 128), (4, 90, 120, 64, 128), (8, 100, 136, 128, 128)],
+                         ids=["even_tiles", "odd_tiles", "one_chunk_odd", "layer2_vga_b8"])
+def test_conv_duo_items_share_weight_boxes(ops, shape):
+    """3x3 stride-1 layers of one <= 128-column N tile with >= 2 tiles per SM take work items of TWO M tiles behind one weight
+    box per k-step (debug bit 18 forbids it): same accumulation order per tile, so the outputs are bit-identical."""
+    n, h, w, cin, cout = shape
+    g = torch.Generator().manual_seed(h * w + cin)
+    x = rand(g, n, cin, h, w).to(DEV)
+    wt = rand(g, cout, cin, 3, 3, scale=(cin * 9) ** -0.5).to(DEV)
+    scale = (0.5 + torch.rand(cout, generator=g)).to(DEV)
+    shift = (0.3 * torch.randn(cout, generator=g)).to(DEV)
+    idn = rand(g, n, cout, h, w).to(DEV)
+    ref = F.relu(F.conv2d(x, wt, None, padding=1) * scale[None, :, None, None] + shift[None, :, None, None] + idn)
+    outs = []
+    for debug in (0, 262144):
+        out = ops.Act(n, h, w, cout, 1, DEV)
+        ops.conv2d(ops.Act.from_nchw(x, 1), ops.pack_conv_weight(wt), cout=cout, ksize=3, scale=scale, shift=shift, relu=True,
+                   res=ops.Act.from_nchw(idn, 1), res_mode=1, out=out, debug=debug)
+        torch.cuda.synchronize()
+        close_bf16(out.to_nchw(), ref, f"duo debug={debug}")
+        assert torch.isclose(out.t.float().abs().sum(), out.interior().float().abs().sum()), "halo of the output must stay zero"
+        outs.append(out.t.clone())
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_conv_residual_phase_copy_and_geometry_remap(ops):
     """BasicBlock tail: conv + scale/shift + identity + ReLU, written twice (plain halo-2 and phase-split)."""
     g = torch.Generator().manual_seed(7)
