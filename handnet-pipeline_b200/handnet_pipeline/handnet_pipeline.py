@@ -4,6 +4,8 @@ Drop-in for the reference's ``handnet_pipeline.handnet_pipeline`` (handnet_pipel
 ``HandNet(args, reload_detector, num_classes, reload_a2j, RGBD)`` constructor, ``.detector`` / ``.a2j``
 attributes, and ``forward(images, depth_images, is_3D=False, is_detect=False)`` returning
 ``(final_results [B,21,3] float32 CPU, depth_batch [n,C,176,176] float32 device, crops [n,4] int64 device)``.
+``max_hands=H`` (extension, default 1) runs the pose path on the first H hand boxes of every frame: ``final_results``
+becomes [B,H,21,3] and ``depth_batch`` / ``crops`` list the hits in (frame, hand) order.
 
 The whole frame batch stays on the device: detector kernels, then ONE kernel for hand selection + box padding
 + crop + nearest resize (``hn_select_crop_resize``), then the pose net for all frames at once; the only
@@ -56,8 +58,14 @@ class HandNet(nn.Module):
     """End-to-end HandNet."""
 
     def __init__(self, args, reload_detector: bool = False, num_classes: int = 2, reload_a2j: bool = False,
-                 RGBD: bool = False):
+                 RGBD: bool = False, max_hands: int = 1):
         super().__init__()
+        if max_hands < 1:
+            raise ValueError("max_hands must be >= 1")
+        # max_hands = 1 is the reference (it keeps the first hand box of a frame, handnet_pipeline.py:84-85).  max_hands = H > 1
+        # is an extension (BASELINE.json config 5, "up to 4 hands/frame"): the same pad / crop / pose path for the first H hand
+        # boxes of every frame; forward() then returns final_results [B,H,21,3] and the hits in (frame, hand) order.
+        self.max_hands = int(max_hands)
         self.detector = load_pretrained_fcos(args, reload_detector, num_classes)
         self.detector.eval()
         self.a2j = load_pretrained_a2j(args, reload_a2j, RGBD)
@@ -80,7 +88,8 @@ class HandNet(nn.Module):
             # it; with different sizes its slicing semantics are not reproduced here
             raise RuntimeError(f"depth images {tuple(depth.shape[-2:])} and RGB images {tuple(images[0].shape[-2:])} differ in size")
         crops, has_hand, depth_batch = ops.select_crop_resize(det["boxes"], det["labels"], det["keep_count"],
-                                                              self.num_classes - 1, depth, CROP_SIZE, out=out)
+                                                              self.num_classes - 1, depth, CROP_SIZE, out=out,
+                                                              hands=self.max_hands)
         runtime.mark("crop")
         return det, crops, has_hand, depth_batch
 
@@ -110,7 +119,7 @@ class HandNet(nn.Module):
         return self._step_for(len(images), shp[-2], shp[-1], int(depth_images.shape[1]), dev)
 
     def _step_for(self, b: int, h: int, w: int, depth_c: int, dev) -> "runtime.GraphedHandNet":
-        key = (b, h, w, depth_c, str(dev))
+        key = (b, h, w, depth_c, str(dev), self.max_hands)
         if key not in self._steps:
             self._steps[key] = runtime.GraphedHandNet(self, b, h, w, depth_c)
         step = self._steps[key]
@@ -198,11 +207,13 @@ class HandNet(nn.Module):
             _, step, t, bsz, depth_images = ticket
             rec_host, outs = step.result(t)
         # the single read-back of the path: fixed-size per-frame records (joints, crop, hit flag)
-        joints, _, hit = runtime.unpack_records(rec_host)
-        final_results = torch.zeros((bsz, 21, 3))
+        joints, _, hit = runtime.unpack_records(rec_host)          # one row per (frame, hand) slot
+        final_results = torch.zeros((bsz * self.max_hands, 21, 3))
+        shape = (bsz, 21, 3) if self.max_hands == 1 else (bsz, self.max_hands, 21, 3)
         if not bool(hit.any()):
-            return final_results, torch.zeros_like(depth_images), torch.zeros((bsz, 4))
+            return final_results.reshape(shape), torch.zeros_like(depth_images), torch.zeros((bsz, 4))
         final_results[hit] = joints[hit]
+        final_results = final_results.reshape(shape)
         depth_batch, crops = outs
         if bool(hit.all()):
             return final_results, depth_batch, crops

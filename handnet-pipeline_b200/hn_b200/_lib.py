@@ -68,6 +68,7 @@ SIGNATURES = {
                             _i, _i, _i, _i, _ip, _fp, _fp,
                             _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),
     "hn_select_crop_resize": (_i, [_c_p, _c_p, _c_p, _i, _i, _i, _c_p, _i, _i, _i, _i, _c_p, _c_p, _c_p, _c_p]),
+    "hn_select_crop_resize_multi": (_i, [_c_p, _c_p, _c_p, _i, _i, _i, _i, _c_p, _i, _i, _i, _i, _c_p, _c_p, _c_p, _c_p]),
     "hn_cheby_spmm": (_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _f, _f, _i, _i, _i, _c_p, _c_p]),
     "hn_linear_f32": (_i, [_c_p, _c_p, _c_p, _i, _i, _i, _c_p, _c_p, _i, _c_p, _c_p, _c_p, _c_p, _i, _c_p, _c_p, _c_p]),
     "hn_mesh_residual_upsample": (_i, [_c_p, _c_p, _i, _i, _i, _i, _c_p, _c_p]),

@@ -15,32 +15,41 @@ __device__ __forceinline__ long long trunc_ll(float v) { return (long long)v; } 
 
 __global__ void __launch_bounds__(256)
 select_crop_resize_kernel(const float4* __restrict__ boxes, const long long* __restrict__ labels,
-                          const int* __restrict__ keep_count, int cap, int hand_label,
+                          const int* __restrict__ keep_count, int cap, int hand_label, int hands,
                           const float* __restrict__ depth, int depth_c, int img_h, int img_w, int out_size,
                           long long* __restrict__ crops, int* __restrict__ has_hand, float* __restrict__ depth_batch) {
   __shared__ int found_s;
-  const int b = blockIdx.y;
+  // blockIdx.y = output slot = frame * hands + h: the h-th kept detection (score-descending order) whose label is the hand
+  // class.  hands == 1 is the reference (handnet_pipeline.py:84-85 keeps boxes[:1]); hands > 1 applies the same per-box path
+  // to the next hand boxes of the frame.
+  const int slot = blockIdx.y;
+  const int b = slot / hands, h = slot - b * hands;
   const int n = min(keep_count[b], cap);
-  // first kept detection (score-descending order) whose label is the hand class
-  if (threadIdx.x == 0) found_s = 0x7fffffff;
-  __syncthreads();
-  for (int base = 0; base < n; base += blockDim.x) {
-    const int k = base + threadIdx.x;
-    if (k < n && labels[(size_t)b * cap + k] == (long long)hand_label) atomicMin(&found_s, k);
-    __syncthreads();
-    const int f = found_s;
-    __syncthreads();
-    if (f != 0x7fffffff) break;
+  if (threadIdx.x < 32) {                        // warp 0 walks the kept list 32 entries at a time, counting hand labels
+    int seen = 0, found = 0x7fffffff;
+    for (int base = 0; base < n; base += 32) {
+      const int k = base + (int)threadIdx.x;
+      const bool is_hand = k < n && labels[(size_t)b * cap + k] == (long long)hand_label;
+      const unsigned m = __ballot_sync(0xffffffffu, is_hand);
+      const int c = __popc(m);
+      if (seen + c > h) {
+        found = base + (int)__fns(m, 0, h - seen + 1);
+        break;
+      }
+      seen += c;
+    }
+    if (threadIdx.x == 0) found_s = found;
   }
+  __syncthreads();
   const int found = found_s;
   const int out_pixels = out_size * out_size;
-  const size_t out_base = (size_t)b * depth_c * out_pixels;
+  const size_t out_base = (size_t)slot * depth_c * out_pixels;
   if (found == 0x7fffffff) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < depth_c * out_pixels; i += gridDim.x * blockDim.x)
       depth_batch[out_base + i] = 0.f;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-      has_hand[b] = 0;
-      for (int j = 0; j < 4; ++j) crops[(size_t)b * 4 + j] = 0;
+      has_hand[slot] = 0;
+      for (int j = 0; j < 4; ++j) crops[(size_t)slot * 4 + j] = 0;
     }
     return;
   }
@@ -60,9 +69,9 @@ select_crop_resize_kernel(const float4* __restrict__ boxes, const long long* __r
   v = __fadd_rn((float)b3, ph);
   const long long y2 = (v < (float)img_h) ? trunc_ll(v) : img_h;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    has_hand[b] = 1;
-    crops[(size_t)b * 4 + 0] = x1; crops[(size_t)b * 4 + 1] = y1;
-    crops[(size_t)b * 4 + 2] = x2; crops[(size_t)b * 4 + 3] = y2;
+    has_hand[slot] = 1;
+    crops[(size_t)slot * 4 + 0] = x1; crops[(size_t)slot * 4 + 1] = y1;
+    crops[(size_t)slot * 4 + 2] = x2; crops[(size_t)slot * 4 + 3] = y2;
   }
   // python slice [y1 : y2+1, x1 : x2+1] clamps to the image
   const long long ys = min(max(y1, 0ll), (long long)img_h), ye = min(max(y2 + 1, 0ll), (long long)img_h);
@@ -280,21 +289,30 @@ __global__ void a2j_combine_kernel(const Partial* __restrict__ part, int splits,
 
 }  // namespace
 
-extern "C" int hn_select_crop_resize(const float* boxes, const int64_t* labels, const int* keep_count, int batch,
-                                     int cap, int hand_label, const float* depth, int depth_c, int img_h, int img_w,
-                                     int out_size, int64_t* crops, int* has_hand, float* depth_batch, void* stream) {
+extern "C" int hn_select_crop_resize_multi(const float* boxes, const int64_t* labels, const int* keep_count, int batch,
+                                           int cap, int hand_label, int max_hands, const float* depth, int depth_c,
+                                           int img_h, int img_w, int out_size, int64_t* crops, int* has_hand,
+                                           float* depth_batch, void* stream) {
   HN_REQUIRE(boxes && labels && keep_count && depth && crops && has_hand && depth_batch,
              "hn_select_crop_resize: null pointer");
   HN_REQUIRE(batch > 0 && cap > 0 && depth_c > 0 && img_h > 0 && img_w > 0 && out_size > 0,
              "hn_select_crop_resize: bad sizes");
+  HN_REQUIRE(max_hands >= 1 && (long long)batch * max_hands <= 65535, "hn_select_crop_resize: bad max_hands");
   const int per_image = depth_c * out_size * out_size;
-  dim3 grid(hn_div_up(per_image, 256 * 4), batch);
+  dim3 grid(hn_div_up(per_image, 256 * 4), batch * max_hands);
   select_crop_resize_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(boxes), reinterpret_cast<const long long*>(labels), keep_count, cap, hand_label,
-      depth, depth_c, img_h, img_w, out_size, reinterpret_cast<long long*>(crops), has_hand, depth_batch);
+      max_hands, depth, depth_c, img_h, img_w, out_size, reinterpret_cast<long long*>(crops), has_hand, depth_batch);
   hn_count_launch();
   HN_LAUNCH_CHECK();
   return HN_OK;
+}
+
+extern "C" int hn_select_crop_resize(const float* boxes, const int64_t* labels, const int* keep_count, int batch,
+                                     int cap, int hand_label, const float* depth, int depth_c, int img_h, int img_w,
+                                     int out_size, int64_t* crops, int* has_hand, float* depth_batch, void* stream) {
+  return hn_select_crop_resize_multi(boxes, labels, keep_count, batch, cap, hand_label, 1, depth, depth_c, img_h, img_w,
+                                     out_size, crops, has_hand, depth_batch, stream);
 }
 
 extern "C" int64_t hn_a2j_workspace_bytes(int n, int joints) {

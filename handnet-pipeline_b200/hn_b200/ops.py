@@ -577,25 +577,28 @@ def fcos_gather(keep, keep_count, cand, hand_lr: torch.Tensor, levels: Levels, r
 
 
 def select_crop_resize(boxes: torch.Tensor, labels: torch.Tensor, keep_count: torch.Tensor, hand_label: int,
-                       depth: torch.Tensor, out_size: int = 176, out=None):
-    """S1 + S2.  depth: fp32 [B, C, H, W].  Returns (crops [B,4] int64, has_hand [B] int32, depth_batch); `out` supplies
-    those three tensors (the pipeline's hand-off buffers) instead of allocating them."""
+                       depth: torch.Tensor, out_size: int = 176, out=None, hands: int = 1):
+    """S1 + S2.  depth: fp32 [B, C, H, W].  Returns (crops [B*hands,4] int64, has_hand [B*hands] int32, depth_batch
+    [B*hands,C,out,out]); slot i*hands + h is the h-th kept hand detection of frame i (hands = 1: the reference's
+    boxes[:1]).  `out` supplies those three tensors (the pipeline's hand-off buffers) instead of allocating them."""
     b, cap = labels.shape
     _, dc, ih, iw = depth.shape
-    assert depth.dtype == torch.float32 and depth.is_contiguous() and depth.shape[0] == b
+    assert depth.dtype == torch.float32 and depth.is_contiguous() and depth.shape[0] == b and hands >= 1
     dev = depth.device
+    n = b * hands
     if out is None:
-        crops = torch.empty((b, 4), dtype=torch.int64, device=dev)
-        has = torch.empty(b, dtype=torch.int32, device=dev)
-        db = torch.empty((b, dc, out_size, out_size), dtype=torch.float32, device=dev)
+        crops = torch.empty((n, 4), dtype=torch.int64, device=dev)
+        has = torch.empty(n, dtype=torch.int32, device=dev)
+        db = torch.empty((n, dc, out_size, out_size), dtype=torch.float32, device=dev)
     else:
         crops, has, db = out
-        assert crops.dtype == torch.int64 and tuple(crops.shape) == (b, 4) and crops.is_contiguous()
-        assert has.dtype == torch.int32 and has.numel() == b and has.is_contiguous()
-        assert db.dtype == torch.float32 and tuple(db.shape) == (b, dc, out_size, out_size) and db.is_contiguous()
-    check(_lib.load().hn_select_crop_resize(boxes.data_ptr(), labels.data_ptr(), keep_count.data_ptr(), b, cap,
-                                            hand_label, depth.data_ptr(), dc, ih, iw, out_size, crops.data_ptr(),
-                                            has.data_ptr(), db.data_ptr(), stream_ptr()), "hn_select_crop_resize")
+        assert crops.dtype == torch.int64 and tuple(crops.shape) == (n, 4) and crops.is_contiguous()
+        assert has.dtype == torch.int32 and has.numel() == n and has.is_contiguous()
+        assert db.dtype == torch.float32 and tuple(db.shape) == (n, dc, out_size, out_size) and db.is_contiguous()
+    check(_lib.load().hn_select_crop_resize_multi(boxes.data_ptr(), labels.data_ptr(), keep_count.data_ptr(), b, cap,
+                                                  hand_label, hands, depth.data_ptr(), dc, ih, iw, out_size,
+                                                  crops.data_ptr(), has.data_ptr(), db.data_ptr(), stream_ptr()),
+          "hn_select_crop_resize_multi")
     return crops, has, db
 
 

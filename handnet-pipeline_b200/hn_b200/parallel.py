@@ -49,7 +49,8 @@ def submit_sharded(net, rgb, depth):
     world, rank = _world_rank()
     total = len(rgb)
     begin, end = shard_range(total, world, rank)
-    per_rank = (total + world - 1) // world
+    hands = int(getattr(net, "max_hands", 1))            # record rows per frame (HandNet(max_hands=H): one per hand slot)
+    per_rank = ((total + world - 1) // world) * hands
     holder = {}
 
     def post(rec: torch.Tensor):
@@ -60,21 +61,22 @@ def submit_sharded(net, rgb, depth):
     if isinstance(images, torch.Tensor):
         images = list(images.unbind(0))
     ticket = net.submit_records(list(images), depth[begin:end], post)
-    return (net, ticket, holder, total, world, per_rank)
+    return (net, ticket, holder, total, world, per_rank, hands)
 
 
 def result_sharded(handle):
     """Wait for a step enqueued by ``submit_sharded``: (joints [N,21,3], crops [N,4] int64, has_hand [N] bool) for the
-    WHOLE batch, on every rank (device tensors; rank 0 is the consumer in the HandNet deployment)."""
+    WHOLE batch, on every rank (device tensors; rank 0 is the consumer in the HandNet deployment).  With
+    ``HandNet(max_hands=H)``, H > 1, the leading dimension is N*H: row n*H + h is hand slot h of frame n."""
     from .runtime import unpack_records
-    net, ticket, holder, total, world, per_rank = handle
+    net, ticket, holder, total, world, per_rank, hands = handle
     net.result_records(ticket)
     rec = holder["all"]
-    if world > 1 and per_rank * world != total:          # drop the padding rows of the short slices
+    if world > 1 and per_rank * world != total * hands:  # drop the padding rows of the short slices
         rows = []
         for r in range(world):
             b, e = shard_range(total, world, r)
-            rows.extend(range(r * per_rank, r * per_rank + (e - b)))
+            rows.extend(range(r * per_rank, r * per_rank + (e - b) * hands))
         rec = rec[torch.tensor(rows, device=rec.device)]
     return unpack_records(rec)
 

@@ -21,8 +21,14 @@ STEM_K_RGB = 256   # 8 kernel rows x 8 pixels x 4 channels (147 real taps), see 
 STEM_K_DEPTH = 64  # 8 kernel rows x 8 pixels (49 real taps)
 
 
+def _version(t: torch.Tensor) -> int:
+    # tensors created under torch.inference_mode() carry no version counter (reading it raises); they cannot be edited in
+    # place outside inference mode either, so a constant is a correct fingerprint for them
+    return 0 if t.is_inference() else t._version
+
+
 def _sig(tensors: Sequence[torch.Tensor]):
-    return tuple((t.data_ptr(), t._version, str(t.device), tuple(t.shape)) for t in tensors)
+    return tuple((t.data_ptr(), _version(t), str(t.device), tuple(t.shape)) for t in tensors)
 
 
 class WeightsEpochMixin:
@@ -52,7 +58,7 @@ class WeightsEpochMixin:
     def weights_epoch(self):
         if self._w_tensors is None:
             self._w_tensors = list(self.parameters()) + list(self.buffers())
-        return (self._w_epoch, sum(t._version for t in self._w_tensors))
+        return (self._w_epoch, sum(_version(t) for t in self._w_tensors))
 
     def load_state_dict(self, *args, **kwargs):
         out = super().load_state_dict(*args, **kwargs)
@@ -727,6 +733,7 @@ class GraphedHandNet:
         dev = next(net.parameters()).device
         self.dev = dev
         self.batch = batch
+        self.hands = int(getattr(net, "max_hands", 1))     # hand slots per frame: the pose stage runs batch * hands crops
         self.rgb = torch.zeros((batch, 3, h, w), dtype=torch.float32, device=dev)
         self.depth = torch.zeros((batch, depth_c, h, w), dtype=torch.float32, device=dev)
         self.images = list(self.rgb.unbind(0))
@@ -744,13 +751,14 @@ class GraphedHandNet:
         # stage / read by the pose stage
         from handnet_pipeline.handnet_pipeline import CROP_SIZE
         self.crop = CROP_SIZE
-        self._off_has = batch * 4 * 8
-        self._off_depth = self._off_has + ((batch * 4 + 7) // 8) * 8
-        nbytes = self._off_depth + batch * depth_c * CROP_SIZE * CROP_SIZE * 4
+        slots = batch * self.hands
+        self._off_has = slots * 4 * 8
+        self._off_depth = self._off_has + ((slots * 4 + 7) // 8) * 8
+        nbytes = self._off_depth + slots * depth_c * CROP_SIZE * CROP_SIZE * 4
         self.hand_d = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
         self.hand_p = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
         self.depth_c = depth_c
-        self.ring_host = [torch.empty((batch, RECORD_WIDTH), dtype=torch.float32).pin_memory() for _ in range(self.RING)]
+        self.ring_host = [torch.empty((slots, RECORD_WIDTH), dtype=torch.float32).pin_memory() for _ in range(self.RING)]
         self.ring_done = [None] * self.RING
         self.ring_out = [None] * self.RING
         self.rec_host = self.ring_host[0]
@@ -763,7 +771,7 @@ class GraphedHandNet:
 
     # ---------------------------------------------------------------------------------------------- buffers
     def _views(self, blob):
-        b, c, s = self.batch, self.depth_c, self.crop
+        b, c, s = self.batch * self.hands, self.depth_c, self.crop
         crops = blob[:self._off_has].view(torch.int64).view(b, 4)
         has = blob[self._off_has:self._off_has + b * 4].view(torch.int32)
         depth = blob[self._off_depth:].view(torch.float32).view(b, c, s, s)

@@ -257,6 +257,14 @@ int hn_fcos_gather(const int* keep, const int* keep_count, const int* cand_loc, 
 int hn_select_crop_resize(const float* boxes, const int64_t* labels, const int* keep_count, int batch, int cap,
                           int hand_label, const float* depth, int depth_c, int img_h, int img_w, int out_size,
                           int64_t* crops, int* has_hand, float* depth_batch, void* stream);
+/* The same per-box path for the first `max_hands` hand detections of every image (an extension: the reference keeps
+ * boxes[:1], handnet_pipeline.py:84-85; BASELINE.json config 5 names "up to 4 hands/frame").  Output slot i*max_hands + h
+ * holds the h-th kept detection of image i with label == hand_label: crops[batch*max_hands][4], has_hand[batch*max_hands],
+ * depth_batch [batch*max_hands][depth_c][out][out]; slots without a detection are zero.  max_hands == 1 is
+ * hn_select_crop_resize. */
+int hn_select_crop_resize_multi(const float* boxes, const int64_t* labels, const int* keep_count, int batch, int cap,
+                                int hand_label, int max_hands, const float* depth, int depth_c, int img_h, int img_w,
+                                int out_size, int64_t* crops, int* has_hand, float* depth_batch, void* stream);
 
 /* ---- J4: anchor aggregation (a2j/anchor.py:57-82) ------------------------------------------------------------
  * cls [n][anchors][joints], reg [n][anchors][joints][2], depth [n][anchors][joints] fp32; anchor_xy

@@ -65,28 +65,35 @@ def crop_resize(depth: torch.Tensor, box: np.ndarray, out: int = CROP) -> torch.
 def handnet_forward(fcos_sd: Dict[str, torch.Tensor], a2j_sd: Dict[str, torch.Tensor],
                     images: Sequence[torch.Tensor], depth_images: torch.Tensor, num_classes: int = 3,
                     min_size: int = 800, max_size: int = 1333, emulate_bf16: bool = False,
-                    detections: Optional[List[Dict[str, torch.Tensor]]] = None):
+                    detections: Optional[List[Dict[str, torch.Tensor]]] = None, max_hands: int = 1):
     """Ensemble branch of HandNet.forward (is_detect=False, is_3D=False).
 
     Returns (final_results [B,21,3], depth_batch [n,1,176,176], crops [n,4] int64, hit_mask [B]).
     Where the reference raises on mixed hit/miss batches (torch.stack over a list holding
-    None, handnet_pipeline.py:111) the oracle keeps only the hits."""
+    None, handnet_pipeline.py:111) the oracle keeps only the hits.
+
+    ``max_hands = H > 1`` is NOT reference behaviour (the reference keeps ``boxes[:1]``,
+    handnet_pipeline.py:84-85): it restates the extension of the B200 path (BASELINE.json config 5,
+    "up to 4 hands/frame") as the reference's own per-box steps (:88-102, then A2J) applied to
+    ``boxes[:H]``; final_results is then [B,H,21,3], hit_mask [B,H], and depth_batch / crops list the
+    hits in (frame, hand) order.  Column 0 of every output equals the max_hands = 1 result."""
     if detections is None:
         detections = fcos_oracle.fcos_forward(fcos_sd, images, num_classes, ext=False, min_size=min_size,
                                               max_size=max_size, emulate_bf16=emulate_bf16)
     bsz = len(images)
-    final = torch.zeros((bsz, 21, 3))
-    hit = torch.zeros(bsz, dtype=torch.bool)
+    final = torch.zeros((bsz, max_hands, 21, 3))
+    hit = torch.zeros((bsz, max_hands), dtype=torch.bool)
     crops, depth_batch = [], []
     for i, det in enumerate(detections):
         boxes = det["boxes"][det["labels"] == num_classes - 1]
-        if boxes.shape[0] == 0:
-            continue
         h, w = images[i].shape[-2:]
-        box = pad_box(boxes[0].numpy(), int(h), int(w))
-        hit[i] = True
-        crops.append(torch.from_numpy(box))
-        depth_batch.append(crop_resize(depth_images[i], box))
+        for k in range(min(max_hands, boxes.shape[0])):
+            box = pad_box(boxes[k].numpy(), int(h), int(w))
+            hit[i, k] = True
+            crops.append(torch.from_numpy(box))
+            depth_batch.append(crop_resize(depth_images[i], box))
+    if max_hands == 1:
+        final, hit = final[:, 0], hit[:, 0]
     if not depth_batch:
         return final, torch.zeros_like(depth_images), torch.zeros((bsz, 4)), hit
     depth_batch = torch.stack(depth_batch)

@@ -311,6 +311,42 @@ def test_select_crop_resize_bit_exact(ops, golden):
         assert torch.equal(db[i], ref)
 
 
+@pytest.mark.parametrize("hands", [1, 2, 4])
+def test_select_crop_resize_hand_slots(ops, hands):
+    """hn_select_crop_resize_multi: slot i*H + h = the h-th kept detection of frame i with the hand label, through the same
+    pad / crop / nearest-resize arithmetic (oracle pad_box / crop_resize, pinned to the reference by pad_crop_cases.pt);
+    hand labels spread over more than one 32-entry round of the kept list; slots beyond a frame's hand boxes are zero;
+    H = 1 equals the single-hand entry point."""
+    g = torch.Generator().manual_seed(11)
+    nb, cap, hh, ww = 6, 90, 240, 320
+    depth = torch.rand(nb, 1, hh, ww, generator=g) * 1.5
+    x1 = torch.rand(nb, cap, generator=g) * (ww - 40) - 8
+    y1 = torch.rand(nb, cap, generator=g) * (hh - 40) - 8
+    bx = torch.stack((x1, y1, x1 + 4 + torch.rand(nb, cap, generator=g) * 150, y1 + 4 + torch.rand(nb, cap, generator=g) * 120), dim=2)
+    lab = torch.ones(nb, cap, dtype=torch.int64)
+    hand_pos = [[3, 40, 41, 77], [0], [], [31, 32, 33, 64, 65], [89], [10, 70]]   # kept-list positions with the hand label
+    for i, pos in enumerate(hand_pos):
+        lab[i, pos] = 2
+    kc = torch.tensor([90, 90, 90, 90, 89, 50], dtype=torch.int32)               # frame 4: its hand box is cut off; frame 5: one of two
+    crops, has, db = ops.select_crop_resize(bx.cuda(), lab.cuda(), kc.cuda(), 2, depth.cuda(), hands=hands)
+    torch.cuda.synchronize()
+    crops, has, db = crops.cpu(), has.cpu(), db.cpu()
+    assert crops.shape == (nb * hands, 4) and has.shape == (nb * hands,) and db.shape == (nb * hands, 1, 176, 176)
+    for i, pos in enumerate(hand_pos):
+        pos = [k for k in pos if k < int(kc[i])]
+        for h in range(hands):
+            s_ = i * hands + h
+            if h >= len(pos):
+                assert has[s_] == 0 and crops[s_].abs().sum() == 0 and db[s_].abs().sum() == 0
+                continue
+            box = handnet_oracle.pad_box(bx[i, pos[h]].numpy(), hh, ww)
+            assert has[s_] == 1 and crops[s_].tolist() == box.tolist(), (i, h)
+            assert torch.equal(db[s_], handnet_oracle.crop_resize(depth[i], box))
+    if hands == 1:
+        c1, h1, d1 = ops.select_crop_resize(bx.cuda(), lab.cuda(), kc.cuda(), 2, depth.cuda())
+        assert torch.equal(c1.cpu(), crops) and torch.equal(h1.cpu(), has) and torch.equal(d1.cpu(), db)
+
+
 @pytest.mark.parametrize("n", [5, 70, 300])   # 70: 4 anchor ranges per crop instead of 16; 300: one block per crop, finished in place
 def test_a2j_aggregate_matches_oracle(ops, n):
     g = torch.Generator().manual_seed(3)

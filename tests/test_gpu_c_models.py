@@ -323,6 +323,52 @@ def test_handnet_async_pipeline_equals_synchronous(handnet_vga):
         net.result(t2)
 
 
+def test_handnet_max_hands_slots(handnet_vga):
+    """HandNet(max_hands=4) (extension; BASELINE.json config 5 "up to 4 hands/frame"): slot (i, h) is the reference's per-box
+    path (pad, crop, nearest resize, A2J) on the h-th hand detection of frame i -- crops and crop pixels bit-exact against
+    the oracle on the GPU's own detections, joints 1e-3 relative against the bf16-emulating oracle on the same crops; hand
+    slot 0 is bit-identical to the max_hands = 1 network; graph replay == eager; async == sync."""
+    from handnet_pipeline.handnet_pipeline import HandNet
+    net1, fsd, asd = handnet_vga
+    net = HandNet(Args(), reload_detector=False, num_classes=3, reload_a2j=False, max_hands=4).eval()
+    net.detector.load_state_dict(fsd)
+    net.a2j.load_state_dict(asd)
+    net = net.cuda()
+    imgs = inputs_images(91, 2, 480, 640)
+    depth = torch.rand(2, 1, 480, 640, generator=torch.Generator().manual_seed(92)) * 1.5
+    cu = [i.cuda() for i in imgs]
+    with torch.inference_mode():
+        final, depth_batch, crops = net(cu, depth_images=depth.cuda())
+        final_r, depth_batch_r, crops_r = net(cu, depth_images=depth.cuda())             # graph replay
+        net.use_cuda_graph = False
+        final_e, depth_batch_e, crops_e = net(cu, depth_images=depth.cuda())             # eager launches
+        net.use_cuda_graph = True
+        t = [net.submit([i.pin_memory() for i in imgs], depth.pin_memory()) for _ in range(2)]
+        async_ = [net.result(x) for x in t]
+        one = net1(cu, depth_images=depth.cuda())
+        dets = net.detector(cu)
+    assert final.shape == (2, 4, 21, 3) and final.device.type == "cpu"
+    for other in ((final_r, depth_batch_r, crops_r), (final_e, depth_batch_e, crops_e), async_[0], async_[1]):
+        assert torch.equal(final, other[0]) and torch.equal(depth_batch, other[1]) and torch.equal(crops, other[2])
+    # oracle on the GPU's detections
+    det_cpu = [{k: v.cpu() for k, v in d.items()} for d in dets]
+    n_hand = [int((d["labels"] == 2).sum()) for d in det_cpu]
+    assert min(n_hand) >= 2, n_hand                      # the synthetic detector finds several hand boxes per frame
+    with torch.inference_mode():
+        o_final, o_db, o_crops, o_hit = handnet_oracle.handnet_forward(fsd, asd, imgs, depth, detections=det_cpu,
+                                                                       max_hands=4, emulate_bf16=True)
+    assert depth_batch.shape[0] == int(o_hit.sum()) == sum(min(4, n) for n in n_hand)
+    assert torch.equal(crops.cpu(), o_crops) and torch.equal(depth_batch.cpu(), o_db)
+    rel = ((final - o_final).abs() / o_final.abs().clamp(min=1.0)).max().item()
+    record("handnet_max_hands4", joints_rel_max_vs_bf16_oracle=rel, hand_slots_filled=int(o_hit.sum()))
+    assert rel < 1e-3
+    assert (final[~o_hit] == 0).all()
+    # hand slot 0 == the single-hand network: same crop bit for bit; the joints agree to rounding (the pose net of 8 crops
+    # and of 2 crops may pick different split-K factors for its deep layers, i.e. another fp32 summation order)
+    assert torch.equal(one[2].cpu(), crops.cpu()[torch.tensor([0, min(4, n_hand[0])])])
+    assert ((one[0] - final[:, 0]).abs() / final[:, 0].abs().clamp(min=1.0)).max().item() < 1e-3
+
+
 def test_fcos_fused_levels_equal_per_level_schedule(fcos_small):
     """runtime.FUSE_LEVELS: towers / output convolutions / GroupNorm as one launch over P3+P4+P5 == the per-level
     schedule, bit for bit (same MMAs per tile; integer GroupNorm sums do not depend on the accumulation order)."""

@@ -215,6 +215,29 @@ def test_weights_epoch_changes_on_nested_load_inplace_edit_and_apply():
     assert weights_token(net)[1] != t4[1]
 
 
+def test_weights_epoch_of_a_model_built_under_inference_mode():
+    """Parameters created inside torch.inference_mode() are inference tensors: they have no version counter (reading
+    ``_version`` raises).  bench.py --config hd1080 builds its network that way; the epoch must still work and still change
+    on a reload."""
+    from hn_b200.runtime import weights_token
+    with torch.inference_mode():
+        net = _quiet_handnet(_Args(), num_classes=3).eval()
+        assert all(p.is_inference() for p in net.parameters())
+        t0 = weights_token(net)
+        assert weights_token(net) == t0
+        net.load_state_dict(net.state_dict())
+        assert weights_token(net) != t0
+
+
+def test_handnet_max_hands_surface():
+    """max_hands is an extension of the constructor (default 1 = the reference, handnet_pipeline.py:84-85)."""
+    import pytest
+    assert _quiet_handnet(_Args(), num_classes=3).max_hands == 1
+    assert _quiet_handnet(_Args(), num_classes=3, max_hands=4).max_hands == 4
+    with pytest.raises(ValueError):
+        _quiet_handnet(_Args(), num_classes=3, max_hands=0)
+
+
 def test_handnet_reloads_fcos_and_a2j_checkpoints(tmp_path):
     """HandNet(args, reload_detector=True, reload_a2j=True): {"model": state_dict} files, strict=False
     (handnet_pipeline.py:17-19, 36-38)."""

@@ -173,6 +173,40 @@ def test_handnet_vga_matches_reference(golden):
     assert hit.all()
 
 
+def test_handnet_oracle_max_hands_is_the_per_box_path_of_the_reference():
+    """max_hands = H (extension; the reference keeps boxes[:1], handnet_pipeline.py:84-85): slot (i, k) is exactly what the
+    max_hands = 1 oracle -- pinned to the reference above -- returns for a frame whose FIRST hand box is box k; frames with
+    fewer hand boxes leave the remaining slots empty."""
+    asd = synth.a2j_state_dict(seed=3)
+    g = torch.Generator().manual_seed(5)
+    imgs = [torch.rand(3, 120, 160, generator=g) for _ in range(3)]
+    depth = torch.rand(3, 1, 120, 160, generator=g) * 1.5
+    mk = lambda boxes, labels: {"boxes": torch.tensor(boxes, dtype=torch.float32).reshape(-1, 4), "labels": torch.tensor(labels, dtype=torch.int64)}
+    dets = [mk([[10.2, 20.7, 60.1, 90.9], [5, 5, 30, 30], [100.5, 40.5, 150.5, 110.5], [0, 0, 159, 119]], [2, 1, 2, 2]),
+            mk([[30, 30, 80, 70]], [2]),
+            mk([[1, 1, 9, 9]], [1])]
+    with torch.inference_mode():
+        final, db, crops, hit = handnet_oracle.handnet_forward(None, asd, imgs, depth, detections=dets, max_hands=3)
+        assert final.shape == (3, 3, 21, 3) and hit.tolist() == [[True, True, True], [True, False, False], [False] * 3]
+        assert db.shape == (4, 1, 176, 176) and crops.shape == (4, 4)
+        row = 0
+        for i, d in enumerate(dets):
+            hand = d["boxes"][d["labels"] == 2]
+            for k in range(min(3, len(hand))):
+                one = [mk(hand[k].tolist(), [2]) if j == i else mk([], []) for j in range(3)]
+                f1, db1, c1, h1 = handnet_oracle.handnet_forward(None, asd, imgs, depth, detections=one)
+                assert h1.tolist() == [j == i for j in range(3)]
+                _same(crops[row], c1[0])
+                _same(db[row], db1[0])
+                _same(final[i, k], f1[i])
+                row += 1
+        # and max_hands = 1 is unchanged: first hand box only
+        f0, db0, c0, h0 = handnet_oracle.handnet_forward(None, asd, imgs, depth, detections=dets)
+        assert f0.shape == (3, 21, 3) and h0.tolist() == [True, True, False]
+        _same(f0[0], final[0, 0])
+        _same(c0, torch.stack((crops[0], crops[3])))
+
+
 # ------------------------------------------------------------------------------------------------
 # pose2mesh (SURVEY.md 8f, last row): oracle and the mirrored modules against the reference-generated golden case
 # ------------------------------------------------------------------------------------------------

@@ -37,9 +37,16 @@ class _StubNet:
     """Stands in for HandNet on the CPU: a frame's record is a function of its content, so the test can tell which rank
     processed which frame.  Implements the two methods parallel.run_sharded needs."""
 
+    def __init__(self, max_hands: int = 1):
+        self.max_hands = max_hands
+
     def submit_records(self, images, depth, post):
         from hn_b200 import runtime
         idx = torch.stack([im.reshape(-1)[0] for im in images]) if images else torch.zeros(0)
+        if self.max_hands > 1:     # one record row per (frame, hand) slot: slot h of frame i carries i + h / 10
+            idx = (idx[:, None] + torch.arange(self.max_hands) / 10.0).reshape(-1)
+            depth = depth.repeat_interleave(self.max_hands, dim=0)
+            images = [None] * idx.numel()
         joints = idx[:, None, None] + torch.arange(63, dtype=torch.float32).reshape(1, 21, 3) / 100
         crops = torch.stack((idx, idx + 1, idx + 2, idx + 3), 1).to(torch.int64)
         has = (depth.reshape(len(images), -1)[:, 0] > 0.5).to(torch.int32)
@@ -81,6 +88,37 @@ def test_run_sharded_world2_gloo():
         assert j0 == [float(i) for i in range(total)]
         assert c3 == [i + 3 for i in range(total)]
         assert h == [bool(i % 2) for i in range(total)]
+
+
+def _worker_run_sharded_hands(rank, world, port, total, hands, q):
+    sys.path.insert(0, os.path.join(ROOT, "handnet-pipeline_b200"))
+    from hn_b200 import parallel
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rgb = torch.arange(total, dtype=torch.float32).reshape(total, 1, 1, 1).expand(total, 3, 4, 4).contiguous()
+    depth = torch.ones(total, 1, 4, 4)
+    joints, crops, has = parallel.run_sharded(_StubNet(max_hands=hands), rgb, depth)
+    assert joints.shape == (total * hands, 21, 3) and has.shape == (total * hands,)
+    q.put((rank, joints[:, 0, 0].tolist()))
+    dist.destroy_process_group()
+
+
+def test_run_sharded_world2_gloo_hand_slots():
+    """HandNet(max_hands=H): H record rows per frame travel through the same all-gather; uneven split, padding rows of the
+    short slice dropped, rows in (frame, hand) order on every rank."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    total, world, hands, port = 5, 2, 3, 33000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_run_sharded_hands, args=(r, world, port, total, hands, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = [round(i + h / 10.0, 4) for i in range(total) for h in range(hands)]
+    for rank, j0 in got:
+        assert [round(v, 4) for v in j0] == want
 
 
 def test_run_sharded_single_process():
