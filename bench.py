@@ -21,7 +21,9 @@ hard-coded 0.7 cut and every frame yields a hand crop (candidate / kept counts a
              `frac_with_all_sms_per_launch` the same launches uncapped, `frac_of_step_time` conv FLOPs / the timed step
   cpu_baseline  the oracle (a torch-CPU restatement of the reference, oracle/) timed on this box's host cores
   extra_configs  BASELINE.json configs 1, 2, 4 and 5 (A2J on the CPU, FCOS alone, post-process stress, 1080p strong
-             scaling) and the pose2mesh lifting network: `--config NAME` runs one of them alone
+             scaling with up to 4 hands per frame = HandNet(max_hands=4)), the pose2mesh lifting network
+             and `latency_b1` (one VGA frame per HandNet.forward call, the ros_demo.py loop: median host latency in ms):
+             `--config NAME` runs one of them alone
 
 `--impl reference` times that CPU restatement alone (the reference itself is Python that needs packages which
 are not installed on the box) on the same 8-frame batch per step.
@@ -364,7 +366,8 @@ def run_main(ctx: Ctx):
         extras = None
         if rank == 0 and world == 1 and not args.no_extras:
             extras = {"fcos_b8": run_fcos_b8(ctx, step), "post_stress": run_post_stress(ctx, net),
-                      "pose2mesh": run_pose2mesh(ctx, with_cpu=not args.no_cpu_baseline)}
+                      "pose2mesh": run_pose2mesh(ctx, with_cpu=not args.no_cpu_baseline),
+                      "latency_b1": run_latency_b1(ctx, net)}
         hd = None
         if not args.no_extras:
             hd = run_hd1080(ctx, net, quick=True)
@@ -486,6 +489,26 @@ def run_fcos_b8(ctx: Ctx, step):
     ms = e0.elapsed_time(e1) / n
     return {"value": FRAMES_PER_GPU / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
             "workload": "BASELINE.json configs[1]: FCOS forward + post-process, batch 8 x 640x480, 1 GPU (L2 flush inside)"}
+
+
+def run_latency_b1(ctx: Ctx, net):
+    """The reference's deployment case (ros_demo.py:264-289: one camera frame per call): ``HandNet.forward`` on ONE VGA frame
+    in pinned host memory, host wall clock from the call to the returned CPU joints (H2D, both stages, D2H, one host wait)."""
+    rgb, depth = synthetic_frames(3000, 1)
+    img = [rgb[0].pin_memory()]
+    dpt = depth.pin_memory()
+    for _ in range(5):
+        net(img, depth_images=dpt)
+    ts = []
+    for _ in range(40):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        net(img, depth_images=dpt)
+        ts.append((time.perf_counter() - t0) * 1e3)
+    ts.sort()
+    return {"value": ts[len(ts) // 2], "unit": "ms", "p95_ms": ts[int(len(ts) * 0.95)], "min_ms": ts[0], "higher_is_better": False,
+            "frames_per_s": 1e3 / ts[len(ts) // 2], "calls": len(ts),
+            "workload": "one 640x480 frame per HandNet.forward call from pinned host memory (ros_demo.py's loop), median host latency"}
 
 
 def run_post_stress(ctx: Ctx, net):
@@ -661,7 +684,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--config", default="e2e", choices=["e2e", "a2j_cpu", "fcos_b8", "post_stress", "hd1080", "pose2mesh"],
+    ap.add_argument("--config", default="e2e", choices=["e2e", "a2j_cpu", "fcos_b8", "post_stress", "hd1080", "pose2mesh", "latency_b1"],
                     help="e2e (default, BASELINE.json configs[2] per-GPU slice, with the others as extra keys) or one of the "
                          "other BASELINE.json configs alone")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -690,6 +713,8 @@ def main():
                     out = run_hd1080(ctx, net, quick=False)
                 elif args.config == "post_stress":
                     out = run_post_stress(ctx, net)
+                elif args.config == "latency_b1":
+                    out = run_latency_b1(ctx, net)
                 elif args.config == "pose2mesh":
                     out = run_pose2mesh(ctx, with_cpu=not args.no_cpu_baseline)
                 else:
