@@ -226,6 +226,60 @@ def test_nms_stress_config4_matches_oracle(ops):
         assert np.array_equal(got, ref)
 
 
+def test_postprocess_full_size_properties(ops):
+    """BASELINE.json config 4 at its FULL size (8 frames x ~10 k candidates), through properties that need no oracle run:
+    the kept list is score-descending; no kept box suppresses a later kept box of its class (IoU <= 0.3, fp32, torchvision's
+    formula); every dropped candidate is suppressed by a kept box of its class that ranks before it; NMS is idempotent (the kept
+    set through NMS again keeps everything, in order); decode / select is invariant to the frame's position in the batch."""
+    lv = _levels(ops)
+    ho = stress_head_tensors(31, 8, lv.locs, 3, -0.35)
+    dev = {k: v.cuda() for k, v in ho.items()}
+    cand = ops.fcos_decode_select(dev["cls_logits"], dev["bbox_ctrness"], dev["bbox_regression"], 3, lv, 0.7)
+    keep, kc = ops.nms_batched(cand["box"], cand["score"], cand["label"], cand["count"], 0.3, 4000)
+    torch.cuda.synchronize()
+
+    def iou(a, b):          # torchvision/ops/boxes.py box_iou arithmetic, fp32
+        area_a = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
+        area_b = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+        lt = torch.max(a[:, None, :2], b[None, :, :2])
+        rb = torch.min(a[:, None, 2:], b[None, :, 2:])
+        wh = (rb - lt).clamp(min=0)
+        inter = wh[..., 0] * wh[..., 1]
+        return inter / (area_a[:, None] + area_b[None, :] - inter)
+
+    for b in range(8):
+        n, k = int(cand["count"][b]), int(kc[b])
+        assert n > 9000 and 0 < k < n
+        box, score, label = cand["box"][b, :n], cand["score"][b, :n], cand["label"][b, :n]
+        kept = keep[b, :k].long()
+        ks, kl, kb = score[kept], label[kept], box[kept]
+        assert bool((ks[:-1] >= ks[1:]).all())                                   # sortedness
+        same = kl[:, None] == kl[None, :]
+        m = iou(kb, kb)
+        m.fill_diagonal_(0)
+        assert not bool(((m > 0.3) & same).any())                                # kept boxes do not suppress each other
+        dropped = torch.ones(n, dtype=torch.bool, device="cuda")
+        dropped[kept] = False
+        d_idx = torch.nonzero(dropped).reshape(-1)
+        md = iou(box[d_idx], kb)                                                 # [dropped, kept]
+        earlier = (ks[None, :] > score[d_idx][:, None]) | ((ks[None, :] == score[d_idx][:, None]) & (kept[None, :] < d_idx[:, None]))
+        ok = ((md > 0.3) & (kl[None, :] == label[d_idx][:, None]) & earlier).any(dim=1)
+        assert bool(ok.all()), int((~ok).sum())                                  # every dropped candidate has a suppressor
+        # idempotence
+        cnt = torch.tensor([k], dtype=torch.int32, device="cuda")
+        keep2, kc2 = ops.nms_batched(kb[None].contiguous(), ks[None].contiguous(), kl[None].contiguous(), cnt, 0.3, 4000)
+        assert int(kc2[0]) == k and torch.equal(keep2[0, :k].long().cpu(), torch.arange(k))
+    # batch-position invariance of decode / select: frames reversed
+    rev = {k_: v.flip(0).contiguous() for k_, v in dev.items()}
+    cand_r = ops.fcos_decode_select(rev["cls_logits"], rev["bbox_ctrness"], rev["bbox_regression"], 3, lv, 0.7)
+    torch.cuda.synchronize()
+    for b in range(8):
+        n = int(cand["count"][b])
+        assert int(cand_r["count"][7 - b]) == n
+        for key in ("loc", "score", "label", "box"):
+            assert torch.equal(cand[key][b, :n], cand_r[key][7 - b, :n])
+
+
 @pytest.mark.parametrize("thr", [0.3, 0.5])
 def test_nms_random_integer_boxes_all_chunk_shapes(ops, thr):
     """Boxes on a small integer grid (IoUs are ratios of small integers: many land exactly on the threshold, e.g.
