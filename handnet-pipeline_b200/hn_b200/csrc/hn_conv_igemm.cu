@@ -53,8 +53,9 @@ constexpr int GN_SMEM_FLOATS = 4096;   // bytes / 4 of the CTA's GroupNorm accum
 constexpr int GN_SMEM_SUMS = GN_SMEM_FLOATS / 2;   // [segments][images][groups][2] fixed-point partial sums kept per CTA
 // GroupNorm statistics are accumulated as 40.24 FIXED-POINT integers (hn_conv_desc.gn_stats): integer addition is
 // associative, so the sums -- and everything downstream of them -- do not depend on the order in which warps and CTAs
-// arrive (fp32 / fp64 atomics made the tower outputs differ in the last bits from run to run).  One warp-level partial
-// (32 rows x 8 channels, reduced in a fixed shuffle order) is rounded to 2^-24; |sum| < 5.5e11 fits.
+// arrive (fp32 / fp64 atomics made the tower outputs differ in the last bits from run to run).  One pixel's partial
+// (8 channels, summed in fp32 in a fixed order) is rounded to 2^-24 and every addition across pixels is an integer one, so
+// the sums do not depend on the tile alignment of a frame (its position in the batch) either; |sum| < 5.5e11 fits.
 constexpr float GN_FIX_SCALE = 16777216.0f;
 constexpr int MAX_SEGS = 3;
 
@@ -1037,11 +1038,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         }
         if (warp == 2) hn_trace(trace, 2, tri, 5);
         if (p.gn_stats) {
-          // GroupNorm partial sums over the bf16-rounded values.  Per lane: (sum, sumsq) of the 4 channel octets of
-          // this chunk = 8 values; a transposing butterfly (4+2+1+1+1 shuffles) leaves total k in lane 4*k, which
-          // adds it to the CTA's shared-memory accumulator of its (image, group); flushed once at kernel end.
+          // GroupNorm partial sums over the bf16-rounded values.  Per lane (= one output pixel): (sum, sumsq) of the 4
+          // channel octets of this chunk = 8 values, summed in a fixed channel order and converted to FIXED POINT before
+          // anything is added across pixels: every cross-pixel addition is an integer addition, so the statistics -- and
+          // everything downstream of them -- depend neither on the arrival order of warps and CTAs nor on which 32 rows
+          // share a warp, i.e. not on where a frame sits in the batch (tile alignment) or how the batch is sharded.  A
+          // transposing butterfly (4+2+1+1+1 64-bit shuffles) leaves total k in lane 4*k, which adds it to the CTA's
+          // shared-memory accumulator of its (image, group); flushed once at kernel end.
           if constexpr (CHUNK == 32) {
-            float v8[8];
+            long long v8[8];
 #pragma unroll
             for (int o8 = 0; o8 < 4; ++o8) {
               float s = 0.f, q = 0.f;
@@ -1052,16 +1057,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 s += x0 + x1;
                 q += x0 * x0 + x1 * x1;
               }
-              v8[2 * o8] = interior ? s : 0.f;
-              v8[2 * o8 + 1] = interior ? q : 0.f;
+              v8[2 * o8] = interior ? __float2ll_rn(s * GN_FIX_SCALE) : 0ll;
+              v8[2 * o8 + 1] = interior ? __float2ll_rn(q * GN_FIX_SCALE) : 0ll;
             }
             if (warp_uniform_img) {
               {
                 const bool hi = lane & 16;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  const float send = hi ? v8[i] : v8[i + 4];
-                  const float keep = hi ? v8[i + 4] : v8[i];
+                  const long long send = hi ? v8[i] : v8[i + 4];
+                  const long long keep = hi ? v8[i + 4] : v8[i];
                   v8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
                 }
               }
@@ -1069,15 +1074,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 const bool hi = lane & 8;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                  const float send = hi ? v8[i] : v8[i + 2];
-                  const float keep = hi ? v8[i + 2] : v8[i];
+                  const long long send = hi ? v8[i] : v8[i + 2];
+                  const long long keep = hi ? v8[i + 2] : v8[i];
                   v8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
                 }
               }
               {
                 const bool hi = lane & 4;
-                const float send = hi ? v8[0] : v8[1];
-                const float keep = hi ? v8[1] : v8[0];
+                const long long send = hi ? v8[0] : v8[1];
+                const long long keep = hi ? v8[1] : v8[0];
                 v8[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
               }
               v8[0] += __shfl_xor_sync(0xffffffffu, v8[0], 2);
@@ -1086,7 +1091,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 const int k = lane >> 2;                         // value index: octet k/2, stat k&1
                 const int group = (cbase + (k >> 1) * 8) / p.gn_group_size;
                 if (group < p.gn_groups) {
-                  const unsigned long long fx = (unsigned long long)__float2ll_rn(v8[0] * GN_FIX_SCALE);
+                  const unsigned long long fx = (unsigned long long)v8[0];
                   if (gn_smem) atomicAdd(&gn_acc[g_gn_off + (warp_img * p.gn_groups + group) * 2 + (k & 1)], fx);
                   else atomicAdd(g_gn_stats + ((long long)warp_img * p.gn_groups + group) * 2 + (k & 1), fx);
                 }
@@ -1096,7 +1101,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
               for (int k = 0; k < 8; ++k) {
                 const int group = (cbase + (k >> 1) * 8) / p.gn_group_size;
                 if (group < p.gn_groups) {
-                  const unsigned long long fx = (unsigned long long)__float2ll_rn(v8[k] * GN_FIX_SCALE);
+                  const unsigned long long fx = (unsigned long long)v8[k];
                   if (gn_smem) atomicAdd(&gn_acc[g_gn_off + (img * p.gn_groups + group) * 2 + (k & 1)], fx);
                   else atomicAdd(g_gn_stats + ((long long)img * p.gn_groups + group) * 2 + (k & 1), fx);
                 }

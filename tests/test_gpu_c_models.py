@@ -371,19 +371,25 @@ def test_handnet_max_hands_slots(handnet_vga):
 
 def test_handnet_full_size_batch_permutation_invariance(handnet_vga):
     """The bench workload at its full size (8 VGA frames per step): a frame's result does not depend on its position in the
-    batch.  Reversing the batch reverses joints, crops and depth crops bit for bit, and everything up to the pyramid levels
-    (canvas, backbone, FPN) is bit-identical per frame.  Behind the first GroupNorm the head tensors agree to bf16 rounding
-    only: the GroupNorm partial sums of a tower layer are formed in fp32 per 32-row warp slice of an M tile before they enter
-    the fixed-point accumulators, and where a frame's pixels fall inside the 128-row tiles depends on its position
-    (14 076 haloed P3 rows per frame = 28 mod 32).  Run to run, at a fixed position, the path is bit-reproducible."""
+    batch.  Reversing the batch reverses EVERYTHING bit for bit: canvas, pyramid levels, head tensors, detections, crops, depth
+    crops and joints.  (GroupNorm statistics are the one place where pixels of a frame are summed across warps and CTAs: a
+    pixel's partial sums are converted to fixed point before any cross-pixel addition, so neither the arrival order nor the
+    alignment of a frame's rows inside the 128-row tiles -- 14 076 haloed P3 rows per frame = 28 mod 32 -- can matter.)
+    Another BATCH SIZE selects other tile shapes / pipelines / split-K factors, i.e. other fp32 summation orders: results then
+    agree to bf16 rounding, not bit for bit (tools/shard_probe.py)."""
     net, _, _ = handnet_vga
     imgs = [i.cuda() for i in inputs_images(131, 8, 480, 640)]
     depth = (torch.rand(8, 1, 480, 640, generator=torch.Generator().manual_seed(132)) * 1.5).cuda()
     with torch.inference_mode():
         a = net(imgs, depth_images=depth)
         b = net(imgs[::-1], depth_images=depth.flip(0).contiguous())
+        da = net.detector(imgs)
+        db = net.detector(imgs[::-1])
     assert a[0].shape == (8, 21, 3) and a[1].shape[0] == 8            # the synthetic detector finds a hand in every frame
     assert torch.equal(a[0], b[0].flip(0)) and torch.equal(a[1], b[1].flip(0)) and torch.equal(a[2], b[2].flip(0))
+    for i in range(8):
+        for key in ("boxes", "scores", "labels"):
+            assert torch.equal(da[i][key], db[7 - i][key]), (i, key)
 
     def run(lst):
         with torch.inference_mode():
@@ -396,11 +402,8 @@ def test_handnet_full_size_batch_permutation_invariance(handnet_vga):
     assert torch.equal(cv_a, cv_b.flip(0))
     for x, y in zip(p_a, p_b):
         assert torch.equal(x, y.flip(0))
-    vals = {}
     for k in ho_a:
-        vals[k] = (ho_a[k].float() - ho_b[k].flip(0).float()).abs().max().item()
-    record("full_size_batch_permutation", **{f"{k}_max_abs": v for k, v in vals.items()})
-    assert vals["cls_logits"] < 0.1 and vals["bbox_regression"] < 5e-3 and vals["bbox_ctrness"] < 5e-3, vals
+        assert torch.equal(ho_a[k], ho_b[k].flip(0)), k
 
 
 def test_fcos_fused_levels_equal_per_level_schedule(fcos_small):
