@@ -18,7 +18,9 @@ hard-coded 0.7 cut and every frame yields a hand crop (candidate / kept counts a
              in one step / their summed device time (CUDA events on the launch stream, launches back to back behind a
              spin kernel), against the SUSTAINED measured bf16 peak; the best launch shape is a sub-key.  `frac` is the
              product's configuration (tower launches capped to 80 % of the SMs: slower alone, as fast in the step);
-             `frac_with_all_sms_per_launch` the same launches uncapped, `frac_of_step_time` conv FLOPs / the timed step
+             `frac_with_all_sms_per_launch` the same launches uncapped, `frac_of_step_time` conv FLOPs / the timed step;
+             `event_pair_overhead_us` = what an empty CUDA-event pair reads under the same protocol, which every one of
+             the ~120 timed launches carries: `frac` keeps it, `frac_net_of_event_overhead` subtracts it
   cpu_baseline  the oracle (a torch-CPU restatement of the reference, oracle/) timed on this box's host cores
   extra_configs  BASELINE.json configs 1, 2, 4 and 5 (A2J on the CPU, FCOS alone, post-process stress, 1080p strong
              scaling with up to 4 hands per frame = HandNet(max_hands=4)), the pose2mesh lifting network
@@ -431,6 +433,19 @@ def conv_roofline(step, step_ms, conv_profile, conv_flops_per_step):
         _rt.TOWER_CTA_CAP = cap_saved
     conv_ms, n_conv = conv_profile(step, repeats=3)
     flops = conv_flops_per_step(step)
+    # what the protocol itself adds to every timed launch: an event pair with NOTHING between its two records, enqueued like
+    # the launches (behind a spin kernel, same stream), reads ~2.6 us.  `frac` keeps it (conservative); the net figure is reported
+    # next to it
+    torch.cuda._sleep(30_000_000)
+    pairs = []
+    for _ in range(101):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e1.record()
+        pairs.append((e0, e1))
+    torch.cuda.synchronize()
+    ev_ms = sorted(a.elapsed_time(b) for a, b in pairs)[len(pairs) // 2]
+    net_ms = conv_ms - n_conv * ev_ms
     tbl = step.last_conv_table
     if os.environ.get("HN_CONV_TABLE"):
         json.dump(tbl, open(os.environ["HN_CONV_TABLE"], "w"))
@@ -465,7 +480,10 @@ def conv_roofline(step, step_ms, conv_profile, conv_flops_per_step):
             "tower_cta_cap": cap_saved if cap_saved >= 0 else "80 % of the SMs",
             "frac_with_all_sms_per_launch": flops / (uncapped_ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
             "frac_of_step_time": flops / (step_ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
-            "frac_of_burst": ach_all / peaks["bf16_burst"], "best_shape": best}
+            "frac_of_burst": ach_all / peaks["bf16_burst"],
+            "event_pair_overhead_us": ev_ms * 1e3, "ms_per_step_serial_net_of_event_overhead": net_ms,
+            "frac_net_of_event_overhead": flops / (net_ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
+            "best_shape": best}
 
 
 def run_fcos_b8(ctx: Ctx, step):
