@@ -87,7 +87,7 @@ select_crop_resize_kernel(const float4* __restrict__ boxes, const long long* __r
       // upsample_nearest (legacy): src = min(floor(dst * scale), in - 1)
       const int syi = min((int)floorf(__fmul_rn((float)oy, sy)), ih - 1);
       const int sxi = min((int)floorf(__fmul_rn((float)ox, sx)), iw - 1);
-      val = __ldg(depth + (((size_t)b * depth_c + c) * img_h + (ys + syi)) * img_w + (xs + sxi));
+      val = __ldcs(depth + (((size_t)b * depth_c + c) * img_h + (ys + syi)) * img_w + (xs + sxi));   // streamed
     }
     depth_batch[out_base + i] = val;
   }
@@ -205,10 +205,10 @@ a2j_partial_vec_kernel(const float4* __restrict__ cls, const float4* __restrict_
       const int v = (r0 + u) * T + t;              // float4 index within the crop
       ok[u] = (r0 + u) < r_end && v < row_vecs;
       const size_t e = base + (ok[u] ? v : 0);
-      c[u] = __ldg(cls + e);
-      d[u] = __ldg(dep + e);
-      g0[u] = __ldg(reg + 2 * e);
-      g1[u] = __ldg(reg + 2 * e + 1);
+      c[u] = __ldcs(cls + e);                      // streamed once: evict-first, no reuse
+      d[u] = __ldcs(dep + e);
+      g0[u] = __ldcs(reg + 2 * e);
+      g1[u] = __ldcs(reg + 2 * e + 1);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int a = (r0 + u) * rows_per_round + arow[k];

@@ -101,7 +101,10 @@ struct SelStage {
 };
 
 __device__ __forceinline__ void sel_cp16(float* dst, const float* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(hn_smem_u32(dst)), "l"(src) : "memory");
+  // the head planes are streamed once: L2 evict-first, so that they replace each other instead of lines somebody will read
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(hn_smem_u32(dst)), "l"(src), "l"(pol) : "memory");
 }
 
 template <int NC>
