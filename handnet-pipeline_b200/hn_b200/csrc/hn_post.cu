@@ -330,6 +330,12 @@ __device__ __forceinline__ uint32_t desc_key(float s) {
   return ~u;                                         // descending
 }
 
+// Lists long enough for the radix path that take torchvision's per-class branch are processed in class-major order (see
+// nms_sort_kernel); every kernel of the chain derives the mode from (n, trick_max) alone.
+__host__ __device__ inline bool class_major(int n, int trick_max) {
+  return n > SORT_THREADS && 4ll * n > (long long)trick_max;
+}
+
 // One CTA per image: stable LSD radix sort of (score desc) with candidate index payload, then gather the boxes
 // in sorted order, applying torchvision's coordinate trick when 4*n <= trick_max (ops/boxes.py:80-104).
 __global__ void __launch_bounds__(SORT_THREADS)
@@ -375,7 +381,15 @@ nms_sort_kernel(const float4* __restrict__ cand_box, const float* __restrict__ c
   // contiguous, 32-aligned segment per warp keeps the scatter stable
   const int per_warp = ((n + SORT_WARPS - 1) / SORT_WARPS + 31) & ~31;
   const int seg0 = min(warp * per_warp, n), seg1 = min(seg0 + per_warp, n);
-  for (int shift = 0; shift < 32; shift += 8) {
+  // Class-major mode (per-class branch of batched_nms, ops/boxes.py:107-121, on a long list): a FIFTH stable pass on the label
+  // leaves the order (label asc, score desc, index asc).  Greedy suppression only acts inside a class and the order inside a
+  // class is unchanged, so the kept SET is the same; the mask kernel can skip every tile whose row and column blocks hold
+  // different classes (2/3 of the upper triangle for three balanced classes), and the scan kernel restores the score order of
+  // the kept list from the score ranks saved in keys[0].
+  const int n_pass = class_major(n, trick_max) ? 5 : 4;
+  for (int pass = 0; pass < n_pass; ++pass) {
+    const int shift = pass * 8;
+    const bool by_label = pass == 4;
     for (int i = tid; i < 256 * SORT_WARPS; i += SORT_THREADS) hist[i] = 0;
     if (tid == 0) skip_pass = 0;
     __syncthreads();
@@ -384,7 +398,7 @@ nms_sort_kernel(const float4* __restrict__ cand_box, const float* __restrict__ c
       const bool act = i < seg1;
       const unsigned amask = __ballot_sync(0xffffffffu, act);
       if (act) {
-        const int d = (keys[cur][i] >> shift) & 255;
+        const int d = by_label ? (cand_label[off + idx[cur][i]] & 255) : (int)((keys[cur][i] >> shift) & 255);
         const unsigned peers = __match_any_sync(amask, d);
         if (lane == __ffs(peers) - 1) hist[d * SORT_WARPS + warp] += __popc(peers);
       }
@@ -411,7 +425,12 @@ nms_sort_kernel(const float4* __restrict__ cand_box, const float* __restrict__ c
     }
     if (lane == 31) warp_tot[warp] = inc;
     __syncthreads();
-    if (skip_pass) { __syncthreads(); continue; }
+    if (skip_pass) {
+      if (by_label)                                 // one class only: the order stays the score order; ranks all the same
+        for (int i = tid; i < n; i += SORT_THREADS) keys[0][idx[cur][i]] = (uint32_t)i;
+      __syncthreads();
+      continue;
+    }
     int wbase = 0;
     for (int i = 0; i < warp; ++i) wbase += warp_tot[i];
     int run = wbase + inc - tsum;
@@ -423,12 +442,14 @@ nms_sort_kernel(const float4* __restrict__ cand_box, const float* __restrict__ c
       const bool act = i < seg1;
       const unsigned amask = __ballot_sync(0xffffffffu, act);
       if (act) {
-        const uint32_t k = keys[cur][i];
-        const int d = (k >> shift) & 255;
+        const uint32_t k = by_label ? 0u : keys[cur][i];
+        const uint32_t ci = idx[cur][i];
+        const int d = by_label ? (cand_label[off + ci] & 255) : (int)((k >> shift) & 255);
         const unsigned peers = __match_any_sync(amask, d);
         const int pos = hist[d * SORT_WARPS + warp] + __popc(peers & ((1u << lane) - 1u));
-        keys[cur ^ 1][pos] = k;
-        idx[cur ^ 1][pos] = idx[cur][i];
+        if (!by_label) keys[cur ^ 1][pos] = k;
+        else keys[0][ci] = (uint32_t)i;             // score rank of the candidate (position in the stable score order)
+        idx[cur ^ 1][pos] = ci;
         __syncwarp(amask);
         if (lane == __ffs(peers) - 1) hist[d * SORT_WARPS + warp] += __popc(peers);
       }
@@ -477,7 +498,7 @@ nms_sort_kernel(const float4* __restrict__ cand_box, const float* __restrict__ c
 // 64x64 tiles of the upper triangle: bit j of mask[i][cb] says "sorted box i suppresses sorted box cb*64+j".
 // Arithmetic follows torchvision/csrc/ops/cpu/nms_kernel.cpp in fp32 with no contraction.
 __global__ void __launch_bounds__(64)
-nms_mask_kernel(const int* __restrict__ cand_count, int batch, int cap, float thr_ge, NmsWs ws) {
+nms_mask_kernel(const int* __restrict__ cand_count, int batch, int cap, float thr_ge, int trick_max, NmsWs ws) {
   __shared__ float4 cb_box[64];
   __shared__ int cb_lab[64];
   __shared__ float cb_area[64];
@@ -516,6 +537,13 @@ nms_mask_kernel(const int* __restrict__ cand_count, int batch, int cap, float th
     const int cb = rb + (int)(t - ((long long)rb * nb - (long long)rb * (rb - 1) / 2));
     const size_t off = (size_t)b * cap;
     const int j0 = cb * 64;
+    if (cb > rb && class_major(n, trick_max) && ws.slabel[off + rb * 64 + 63] < ws.slabel[off + j0]) {
+      // class-major order (labels ascending): every row of this block belongs to an earlier class than every column
+      const int i = rb * 64 + threadIdx.x;
+      if (i < n) ws.mask[((size_t)b * cap + i) * ws.words + cb] = 0ull;
+      tile += gridDim.x;
+      continue;
+    }
     __syncthreads();
     if (j0 + (int)threadIdx.x < n) {
       const float4 bx = ws.sbox[off + j0 + threadIdx.x];
@@ -587,9 +615,9 @@ nms_mask_kernel(const int* __restrict__ cand_count, int batch, int cap, float th
 constexpr int SCAN_THREADS = 1024;
 constexpr int SCAN_OR_WARPS = SCAN_THREADS / 32 - 5;
 __global__ void __launch_bounds__(SCAN_THREADS)
-nms_scan_kernel(const int* __restrict__ cand_count, int cap, NmsWs ws, int* __restrict__ keep,
+nms_scan_kernel(const int* __restrict__ cand_count, int cap, int trick_max, NmsWs ws, int* __restrict__ keep,
                 int* __restrict__ keep_count) {
-  extern __shared__ unsigned long long removed[];   // [words]
+  extern __shared__ unsigned long long removed[];   // [words], then [words] ints (class-major mode: word prefix counts)
   __shared__ unsigned long long diag[2][64];
   __shared__ unsigned long long kept_bits_s;
   const int b = blockIdx.x;
@@ -674,6 +702,44 @@ nms_scan_kernel(const int* __restrict__ cand_count, int cap, NmsWs ws, int* __re
     __syncthreads();
   }
   if (tid == 0) keep_count[b] = kept_total;
+  if (class_major(n, trick_max) && kept_total > 0) {
+    // The kept list is in (label, score) order; batched_nms returns it by descending score (ops/boxes.py:120-121; ties: the
+    // stable order, ascending candidate index, as everywhere in this file).  Every candidate's rank in the stable score order
+    // was saved by the sort kernel: set bit `rank` for every kept candidate, count the bits below -> its output position.
+    const uint32_t* rank = ws.keys[0] + off;
+    int* tmp = reinterpret_cast<int*>(ws.idx[1] + off);            // free after the sort
+    int* wprefix = reinterpret_cast<int*>(removed + words);
+    for (int i = tid; i < nb; i += SCAN_THREADS) removed[i] = 0ull;
+    __syncthreads();
+    for (int k = tid; k < kept_total; k += SCAN_THREADS) {
+      const uint32_t r = rank[keep[off + k]];
+      atomicOr(rem32 + (r >> 5), 1u << (r & 31));
+    }
+    __syncthreads();
+    if (warp == 0) {                                                // exclusive prefix of the per-word popcounts
+      int run = 0;
+      for (int w0 = 0; w0 < nb; w0 += 32) {
+        const int w = w0 + lane;
+        const int c = w < nb ? __popcll(removed[w]) : 0;
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        if (w < nb) wprefix[w] = run + inc - c;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+      }
+    }
+    __syncthreads();
+    for (int k = tid; k < kept_total; k += SCAN_THREADS) {
+      const int cand = keep[off + k];
+      const uint32_t r = rank[cand];
+      tmp[wprefix[r >> 6] + __popcll(removed[r >> 6] & ((1ull << (r & 63)) - 1ull))] = cand;
+    }
+    __syncthreads();
+    for (int k = tid; k < kept_total; k += SCAN_THREADS) keep[off + k] = tmp[k];
+  }
 }
 
 // ---------------------------------------------------------------------------------- gather
@@ -834,23 +900,23 @@ extern "C" int hn_nms_batched(const float* cand_box, const float* cand_score, co
   HN_REQUIRE(batch > 0 && cap > 0, "hn_nms_batched: bad sizes");
   HN_REQUIRE(workspace_bytes >= hn_nms_workspace_bytes(batch, cap), "hn_nms_batched: workspace too small");
   NmsWs ws = carve(workspace, batch, cap);
-  HN_REQUIRE((size_t)ws.words * 8 <= 200 * 1024, "hn_nms_batched: cap too large for the scan kernel");
+  HN_REQUIRE((size_t)ws.words * 12 <= 200 * 1024, "hn_nms_batched: cap too large for the scan kernel");
   const float thr_ge = float_gt_as_ge(iou_thresh);   // (double)iou > thr, as torchvision's CPU kernel compares
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   nms_sort_kernel<<<batch, SORT_THREADS, 0, st>>>(reinterpret_cast<const float4*>(cand_box), cand_score, cand_label,
                                                   cand_count, cap, coord_trick_max_numel, ws);
   hn_count_launch();
   HN_LAUNCH_CHECK();
-  nms_mask_kernel<<<hn_num_sms() * 32, 64, 0, st>>>(cand_count, batch, cap, thr_ge, ws);
+  nms_mask_kernel<<<hn_num_sms() * 32, 64, 0, st>>>(cand_count, batch, cap, thr_ge, coord_trick_max_numel, ws);
   hn_count_launch();
   HN_LAUNCH_CHECK();
-  const size_t scan_smem = (size_t)ws.words * 8;
+  const size_t scan_smem = (size_t)ws.words * 12;     // removed[] + the word prefix counts of the class-major reorder
   static bool attr = false;
   if (!attr && scan_smem > 40 * 1024) {
     HN_CHECK_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  nms_scan_kernel<<<batch, SCAN_THREADS, scan_smem, st>>>(cand_count, cap, ws, keep, keep_count);
+  nms_scan_kernel<<<batch, SCAN_THREADS, scan_smem, st>>>(cand_count, cap, coord_trick_max_numel, ws, keep, keep_count);
   hn_count_launch();
   HN_LAUNCH_CHECK();
   return HN_OK;
