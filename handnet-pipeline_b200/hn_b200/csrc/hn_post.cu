@@ -493,6 +493,8 @@ nms_sort_kernel(const float4* __restrict__ cand_box, const float* __restrict__ c
     ws.sbox[off + i] = bx;
     ws.slabel[off + i] = lab;
   }
+  __syncthreads();
+  if (tid == 0) keys[1][0] = 0u;       // arrival counter of the scan kernel's segment CTAs (keys[1] is free from here on)
 }
 
 // 64x64 tiles of the upper triangle: bit j of mask[i][cb] says "sorted box i suppresses sorted box cb*64+j".
@@ -614,34 +616,70 @@ nms_mask_kernel(const int* __restrict__ cand_count, int batch, int cap, float th
 // 19 us per chunk at 10 k candidates; this one ~1.5.)
 constexpr int SCAN_THREADS = 1024;
 constexpr int SCAN_OR_WARPS = SCAN_THREADS / 32 - 5;
+// Class-major mode: the classes are independent chains, so grid.y CTAs scan one label segment each (labels 0, 1, 2 and >= 3:
+// the last CTA takes whatever is left, which the chain handles like any mixed list) and the CTA that finishes last restores the
+// score order of the image's kept list.  A chunk that straddles two segments is resolved by both CTAs, each counting the other
+// segment's rows as removed (rows of different labels never suppress each other).  seg_info (in keys[1], free after the sort):
+// [0] arrival counter (zeroed by the sort kernel), [1 + 2s] first row of segment s, [2 + 2s] its kept count; the segment's kept
+// candidates are parked in idx[1] from its first row on.
+constexpr int SCAN_SEGS = 4;
+
+__device__ __forceinline__ int first_row_with_label_ge(const int* __restrict__ slabel, int n, int label) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (slabel[mid] < label) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS)
 nms_scan_kernel(const int* __restrict__ cand_count, int cap, int trick_max, NmsWs ws, int* __restrict__ keep,
                 int* __restrict__ keep_count) {
   extern __shared__ unsigned long long removed[];   // [words], then [words] ints (class-major mode: word prefix counts)
   __shared__ unsigned long long diag[2][64];
   __shared__ unsigned long long kept_bits_s;
-  const int b = blockIdx.x;
+  __shared__ int seg_rows[2];
+  __shared__ int last_s;
+  const int b = blockIdx.x, seg = blockIdx.y;
   const int n = min(cand_count[b], cap);
-  const int nb = (n + 63) / 64;
   const size_t off = (size_t)b * cap;
   const int words = ws.words;
   const uint32_t* order = ws.idx[0] + off;
   const unsigned long long* mask = ws.mask + off * words;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t* rem32 = reinterpret_cast<uint32_t*>(removed);
-  for (int i = tid; i < nb; i += SCAN_THREADS) removed[i] = 0ull;
-  if (tid < 64 && tid < n) diag[0][tid] = mask[(size_t)tid * words];
+  const bool cm = class_major(n, trick_max);
+  if (!cm && seg != 0) return;
+  int row_lo = 0, row_hi = n;
+  if (cm) {
+    if (tid == 0) {
+      const int* sl = ws.slabel + off;
+      seg_rows[0] = seg == 0 ? 0 : first_row_with_label_ge(sl, n, seg);
+      seg_rows[1] = seg == SCAN_SEGS - 1 ? n : first_row_with_label_ge(sl, n, seg + 1);
+    }
+    __syncthreads();
+    row_lo = seg_rows[0];
+    row_hi = seg_rows[1];
+  }
+  uint32_t* seg_info = ws.keys[1] + off;
+  int* parked = reinterpret_cast<int*>(ws.idx[1] + off);
+  int* out = cm ? parked + row_lo : keep + off;
+  const int c0 = row_lo >> 6, c_end = row_hi > row_lo ? (row_hi + 63) >> 6 : c0;
+  for (int i = c0 + tid; i < c_end; i += SCAN_THREADS) removed[i] = 0ull;
+  if (tid < 64 && c0 < c_end && c0 * 64 + tid < n) diag[c0 & 1][tid] = mask[(size_t)(c0 * 64 + tid) * words + c0];
   int kept_total = 0;                                // uniform: every thread adds the popcount of each chunk
   unsigned long long kept_prev = 0ull;               // kept bits of chunk c-1 (uniform)
   __syncthreads();
-  for (int c = 0; c < nb; ++c) {
-    const int cnt = min(64, n - c * 64);
+  for (int c = c0; c < c_end; ++c) {
+    const int cnt = min(64, row_hi - c * 64);
     unsigned long long next_word = 0ull;
     uint32_t ord = 0u;
     if (tid == 0) {
       const unsigned long long* dg = diag[c & 1];
       unsigned long long cur = removed[c], kept = 0ull;
-      if (cnt < 64) cur |= ~0ull << cnt;             // boxes beyond n count as removed
+      if (cnt < 64) cur |= ~0ull << cnt;             // rows beyond the segment (or beyond n) count as removed
+      if (row_lo > c * 64) cur |= (1ull << (row_lo - c * 64)) - 1ull;   // and so do the rows of the segment before (first chunk)
 #pragma unroll 1
       for (int r0 = 0; r0 < 64; r0 += 8) {
         unsigned long long d[8];
@@ -659,21 +697,21 @@ nms_scan_kernel(const int* __restrict__ cand_count, int cap, int trick_max, NmsW
       const int r = tid - 32;
       if (r < cnt) {
         ord = order[c * 64 + r];
-        if (c + 1 < nb) next_word = mask[(size_t)(c * 64 + r) * words + (c + 1)];
+        if (c + 1 < c_end) next_word = mask[(size_t)(c * 64 + r) * words + (c + 1)];
       }
     } else if (warp == 3 || warp == 4) {
       const int r = tid - 96, i = (c + 1) * 64 + r;
-      if (c + 1 < nb && i < n) diag[(c + 1) & 1][r] = mask[(size_t)i * words + (c + 1)];
-    } else if (warp >= 5 && kept_prev != 0ull && c + 1 < nb) {
+      if (c + 1 < c_end && i < n) diag[(c + 1) & 1][r] = mask[(size_t)i * words + (c + 1)];
+    } else if (warp >= 5 && kept_prev != 0ull && c + 1 < c_end) {
       // warp w owns the rows w-5, w-5+27, w-5+54 of the chunk (no enumeration of the kept bits: ncu showed the
       // kernel issue-bound on exactly that loop, run by all 27 warps)
       for (int r = warp - 5; r < 64; r += SCAN_OR_WARPS) {
         if (!((kept_prev >> r) & 1ull)) continue;
         const unsigned long long* row = mask + (size_t)((c - 1) * 64 + r) * words;
-        for (int w0 = c + 1 + lane; w0 < nb; w0 += 256) {
+        for (int w0 = c + 1 + lane; w0 < c_end; w0 += 256) {
           unsigned long long v[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = (w0 + 32 * i < nb) ? row[w0 + 32 * i] : 0ull;
+          for (int i = 0; i < 8; ++i) v[i] = (w0 + 32 * i < c_end) ? row[w0 + 32 * i] : 0ull;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const uint32_t lo = (uint32_t)v[i], hi = (uint32_t)(v[i] >> 32);
@@ -688,11 +726,11 @@ nms_scan_kernel(const int* __restrict__ cand_count, int cap, int trick_max, NmsW
     if (warp == 1 || warp == 2) {
       const int r = tid - 32;
       const bool mine = r < cnt && ((kept >> r) & 1ull);
-      if (mine) keep[off + kept_total + __popcll(kept & ((1ull << r) - 1ull))] = (int)ord;
+      if (mine) out[kept_total + __popcll(kept & ((1ull << r) - 1ull))] = (int)ord;
       const unsigned long long v = mine ? next_word : 0ull;
       const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)v);
       const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
-      if (lane == 0 && c + 1 < nb) {
+      if (lane == 0 && c + 1 < c_end) {
         if (lo) atomicOr(rem32 + 2 * (c + 1), lo);
         if (hi) atomicOr(rem32 + 2 * (c + 1) + 1, hi);
       }
@@ -701,45 +739,71 @@ nms_scan_kernel(const int* __restrict__ cand_count, int cap, int trick_max, NmsW
     kept_prev = kept;
     __syncthreads();
   }
-  if (tid == 0) keep_count[b] = kept_total;
-  if (class_major(n, trick_max) && kept_total > 0) {
-    // The kept list is in (label, score) order; batched_nms returns it by descending score (ops/boxes.py:120-121; ties: the
-    // stable order, ascending candidate index, as everywhere in this file).  Every candidate's rank in the stable score order
-    // was saved by the sort kernel: set bit `rank` for every kept candidate, count the bits below -> its output position.
-    const uint32_t* rank = ws.keys[0] + off;
-    int* tmp = reinterpret_cast<int*>(ws.idx[1] + off);            // free after the sort
-    int* wprefix = reinterpret_cast<int*>(removed + words);
-    for (int i = tid; i < nb; i += SCAN_THREADS) removed[i] = 0ull;
-    __syncthreads();
-    for (int k = tid; k < kept_total; k += SCAN_THREADS) {
-      const uint32_t r = rank[keep[off + k]];
+  if (!cm) {
+    if (tid == 0) keep_count[b] = kept_total;
+    return;
+  }
+  // ---- class-major mode: publish this segment, and let the CTA that arrives last restore the score order
+  if (tid == 0) {
+    seg_info[1 + 2 * seg] = (uint32_t)row_lo;
+    seg_info[2 + 2 * seg] = (uint32_t)kept_total;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned old = atomicAdd(seg_info, 1u);
+    last_s = old == (unsigned)SCAN_SEGS - 1u;
+    if (last_s) seg_info[0] = 0u;                   // everyone has arrived: reset for the next launch
+  }
+  __syncthreads();
+  if (!last_s) return;
+  __threadfence();
+  // The kept candidates are in (label, score) order; batched_nms returns them by descending score (ops/boxes.py:120-121; ties:
+  // the stable order, ascending candidate index, as everywhere in this file).  Every candidate's rank in the stable score order
+  // was saved by the sort kernel: set bit `rank` for every kept candidate, count the bits below -> its output position.
+  const uint32_t* rank = ws.keys[0] + off;
+  const int nb = (n + 63) / 64;
+  int* wprefix = reinterpret_cast<int*>(removed + words);
+  int lo_s[SCAN_SEGS], kept_s[SCAN_SEGS], total = 0;
+#pragma unroll
+  for (int s_ = 0; s_ < SCAN_SEGS; ++s_) {
+    lo_s[s_] = (int)__ldcg(seg_info + 1 + 2 * s_);
+    kept_s[s_] = (int)__ldcg(seg_info + 2 + 2 * s_);
+    total += kept_s[s_];
+  }
+  for (int i = tid; i < nb; i += SCAN_THREADS) removed[i] = 0ull;
+  __syncthreads();
+#pragma unroll
+  for (int s_ = 0; s_ < SCAN_SEGS; ++s_)
+    for (int k = tid; k < kept_s[s_]; k += SCAN_THREADS) {
+      const uint32_t r = rank[__ldcg(parked + lo_s[s_] + k)];
       atomicOr(rem32 + (r >> 5), 1u << (r & 31));
     }
-    __syncthreads();
-    if (warp == 0) {                                                // exclusive prefix of the per-word popcounts
-      int run = 0;
-      for (int w0 = 0; w0 < nb; w0 += 32) {
-        const int w = w0 + lane;
-        const int c = w < nb ? __popcll(removed[w]) : 0;
-        int inc = c;
+  __syncthreads();
+  if (warp == 0) {                                                // exclusive prefix of the per-word popcounts
+    int run = 0;
+    for (int w0 = 0; w0 < nb; w0 += 32) {
+      const int w = w0 + lane;
+      const int cw = w < nb ? __popcll(removed[w]) : 0;
+      int inc = cw;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, inc, o);
-          if (lane >= o) inc += t;
-        }
-        if (w < nb) wprefix[w] = run + inc - c;
-        run += __shfl_sync(0xffffffffu, inc, 31);
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
       }
+      if (w < nb) wprefix[w] = run + inc - cw;
+      run += __shfl_sync(0xffffffffu, inc, 31);
     }
-    __syncthreads();
-    for (int k = tid; k < kept_total; k += SCAN_THREADS) {
-      const int cand = keep[off + k];
-      const uint32_t r = rank[cand];
-      tmp[wprefix[r >> 6] + __popcll(removed[r >> 6] & ((1ull << (r & 63)) - 1ull))] = cand;
-    }
-    __syncthreads();
-    for (int k = tid; k < kept_total; k += SCAN_THREADS) keep[off + k] = tmp[k];
   }
+  __syncthreads();
+#pragma unroll
+  for (int s_ = 0; s_ < SCAN_SEGS; ++s_)
+    for (int k = tid; k < kept_s[s_]; k += SCAN_THREADS) {
+      const int cand = __ldcg(parked + lo_s[s_] + k);
+      const uint32_t r = rank[cand];
+      keep[off + wprefix[r >> 6] + __popcll(removed[r >> 6] & ((1ull << (r & 63)) - 1ull))] = cand;
+    }
+  if (tid == 0) keep_count[b] = total;
 }
 
 // ---------------------------------------------------------------------------------- gather
@@ -916,7 +980,8 @@ extern "C" int hn_nms_batched(const float* cand_box, const float* cand_score, co
     HN_CHECK_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  nms_scan_kernel<<<batch, SCAN_THREADS, scan_smem, st>>>(cand_count, cap, coord_trick_max_numel, ws, keep, keep_count);
+  nms_scan_kernel<<<dim3(batch, SCAN_SEGS), SCAN_THREADS, scan_smem, st>>>(cand_count, cap, coord_trick_max_numel, ws, keep,
+                                                                            keep_count);
   hn_count_launch();
   HN_LAUNCH_CHECK();
   return HN_OK;

@@ -303,6 +303,35 @@ def test_nms_random_integer_boxes_all_chunk_shapes(ops, thr):
         assert np.array_equal(g, ref), (len(sc), g[:10], ref[:10])
 
 
+def test_nms_class_major_segments(ops):
+    """The per-class branch on long lists runs in class-major order with one scan chain per label segment (labels 0, 1, 2 and
+    >= 3) and restores the score order at the end: label sets that leave segments empty, start above 0, put several classes
+    into the last segment, a single class, very unequal class sizes, list lengths around the radix-path switch (1024) and
+    the 64-box chunk edges, score ties across classes -- kept indices and their order identical to the numpy oracle
+    (torchvision CPU semantics); the same lists in one batch (different modes side by side) and called twice (the arrival
+    counters reset themselves)."""
+    rng = np.random.default_rng(17)
+    boxes, scores, labels = [], [], []
+    spec = [(1025, [0, 1, 2], None), (1500, [2, 5, 6], None), (3000, [0, 1, 2, 3, 4, 5, 6], None), (2200, [1], None),
+            (4100, [0, 3], [0.97, 0.03]), (1900, [0, 1, 2], [0.01, 0.01, 0.98]), (1024, [0, 1, 2], None), (70, [0, 4], None),
+            (2049, [7, 9], None)]
+    for n, labs, prob in spec:
+        xy = rng.integers(0, 60, size=(n, 2)).astype(np.float32)
+        wh = rng.integers(1, 13, size=(n, 2)).astype(np.float32)
+        boxes.append(torch.from_numpy(np.concatenate([xy, xy + wh], axis=1)))
+        scores.append(torch.from_numpy((rng.integers(0, 400, size=n) / 400.0).astype(np.float32)))
+        labels.append(torch.from_numpy(rng.choice(np.array(labs), size=n, p=prob).astype(np.int64)))
+    for _ in range(2):
+        got = _run_nms(ops, boxes, scores, labels, thr=0.3)
+        for bx, sc, lb, g in zip(boxes, scores, labels, got):
+            ref = nms_oracle.batched_nms(bx.numpy(), sc.numpy(), lb.numpy(), 0.3)
+            if bx.numel() > 4000:      # per-class branch: order inside exact score ties is unspecified in torchvision
+                s64 = sc.numpy().astype(np.float64)
+                ref = ref[np.lexsort((ref, -s64[ref]))]
+                assert np.array_equal(g, g[np.lexsort((g, -s64[g]))]), "kept list must be score-descending, ties by index"
+            assert np.array_equal(g, ref), (len(sc), g[:10], ref[:10])
+
+
 def test_gather_and_full_postprocess_chain(ops, golden):
     """decode -> NMS -> gather on the reference's own config-4 fixture: boxes / labels / sides / levels of the
     kept detections are identical to the reference's output (scores at 2 ulp)."""
