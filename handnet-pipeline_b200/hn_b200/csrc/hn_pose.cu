@@ -137,9 +137,9 @@ a2j_partial_kernel(const float* __restrict__ cls, const float2* __restrict__ reg
         const int a = a0 + u * rows_per_iter;
         const bool ok = a < a_end;
         const size_t e = base + (size_t)(ok ? a : a0) * joints + j;
-        c[u] = __ldg(cls + e);
-        rg[u] = __ldg(reg + e);
-        d[u] = __ldg(dep + e);
+        c[u] = __ldcs(cls + e);                    // streamed once (as in the vector kernel below)
+        rg[u] = __ldcs(reg + e);
+        d[u] = __ldcs(dep + e);
         an[u] = __ldg(anchor_xy + (ok ? a : a0));
         if (!ok) c[u] = -INFINITY;
       }
